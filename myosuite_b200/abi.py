@@ -1,0 +1,151 @@
+"""ctypes binding of the C-ABI in include/myo_b200.h (libmyo_b200.so, built in-tree by myosuite_b200.build).
+
+Host code stays Python over torch tensors: tensors are passed as ``data_ptr()`` only; no torch types
+cross the ABI.  There is NO CPU fallback: if the library or a CUDA device is missing the calls raise.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_LIB = None
+
+c_i32, c_i64, c_u64, c_f64, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_double, ctypes.c_void_p
+
+TASK_NONE, TASK_POSE = 0, 1
+COND_NONE, COND_FATIGUE = 0, 2
+
+
+class MyoDims(ctypes.Structure):
+    _fields_ = [(n, c_i32) for n in ("nq", "nv", "nu", "na", "nbody", "njnt", "ntendon", "nM", "npair", "nta", "maxcon",
+                                      "maxefc", "smem_bytes_per_env")] + [("reserved", c_i32 * 3)]
+
+
+class MyoTaskCfg(ctypes.Structure):
+    _fields_ = [(n, c_i32) for n in ("task", "frame_skip", "max_episode_steps", "normalize_act", "muscle_condition",
+                                      "auto_reset", "reset_random", "maxcon")] + \
+               [("pose_thd", c_f64), ("weights", c_f64 * 4), ("solver_tolerance", c_f64), ("reserved", c_f64 * 6)]
+
+
+BUFFER_FIELDS = ["action", "qpos", "qvel", "act", "qacc_warmstart", "time", "fatigue", "target", "target_range", "init_qpos",
+                 "step_count", "episode_count", "obs", "reward", "done", "truncated", "ep_return", "last_return",
+                 "tap_qacc", "tap_actuator_force", "tap_ten_length", "tap_qfrc_smooth", "tap_ncon", "tap_contact_pair",
+                 "tap_contact_dist", "tap_moment", "tap_qM"]
+
+
+class MyoBuffers(ctypes.Structure):
+    _fields_ = [(n, c_vp) for n in BUFFER_FIELDS] + [("reserved", c_vp * 4)]
+
+
+EXPORTS = ["myo_last_error", "myo_version", "myo_model_from_blob", "myo_model_dims", "myo_model_destroy", "myo_batch_create",
+           "myo_batch_bind", "myo_batch_destroy", "myo_batch_obs_dim", "myo_batch_reset", "myo_batch_step",
+           "myo_batch_forward_debug", "myo_batch_launch_count"]
+
+
+class MyoError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _build.LIB
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = _build.LIB
+        if not os.path.exists(path):
+            path = _build.build()
+        L = ctypes.CDLL(path)
+        L.myo_last_error.restype = ctypes.c_char_p
+        L.myo_model_from_blob.argtypes = [c_vp, c_i64, c_vp, c_i64, ctypes.POINTER(c_vp)]
+        L.myo_model_dims.argtypes = [c_vp, ctypes.POINTER(MyoTaskCfg), ctypes.POINTER(MyoDims)]
+        L.myo_model_destroy.argtypes = [c_vp]
+        L.myo_model_destroy.restype = None
+        L.myo_batch_create.argtypes = [c_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(MyoTaskCfg), ctypes.POINTER(c_vp)]
+        L.myo_batch_bind.argtypes = [c_vp, ctypes.POINTER(MyoBuffers)]
+        L.myo_batch_destroy.argtypes = [c_vp]
+        L.myo_batch_destroy.restype = None
+        L.myo_batch_obs_dim.argtypes = [c_vp]
+        L.myo_batch_reset.argtypes = [c_vp, c_vp, c_u64, c_i64, c_vp]
+        L.myo_batch_step.argtypes = [c_vp, c_vp]
+        L.myo_batch_forward_debug.argtypes = [c_vp, c_vp, ctypes.c_int, c_vp]
+        L.myo_batch_launch_count.argtypes = [c_vp]
+        L.myo_batch_launch_count.restype = c_i64
+        _LIB = L
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        raise MyoError(lib().myo_last_error().decode())
+
+
+class DeviceModel:
+    """Host handle of a packed model (myo_model*)."""
+
+    def __init__(self, I, D):
+        self.I = np.ascontiguousarray(I, dtype=np.int32)
+        self.D = np.ascontiguousarray(D, dtype=np.float64)
+        h = c_vp()
+        _check(lib().myo_model_from_blob(self.I.ctypes.data, self.I.size, self.D.ctypes.data, self.D.size, ctypes.byref(h)))
+        self.handle = h
+
+    def dims(self, cfg=None):
+        d = MyoDims()
+        _check(lib().myo_model_dims(self.handle, ctypes.byref(cfg) if cfg is not None else None, ctypes.byref(d)))
+        return d
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            lib().myo_model_destroy(self.handle)
+            self.handle = None
+
+
+class Batch:
+    """myo_batch*: n_env envs of one model on one CUDA device, driven through bound torch tensors."""
+
+    def __init__(self, model, device, n_env, cfg):
+        self.model, self.cfg, self.n_env, self.device = model, cfg, n_env, device
+        h = c_vp()
+        _check(lib().myo_batch_create(model.handle, device, n_env, ctypes.byref(cfg), ctypes.byref(h)))
+        self.handle = h
+        self.tensors = {}
+
+    @property
+    def obs_dim(self):
+        return lib().myo_batch_obs_dim(self.handle)
+
+    def bind(self, **tensors):
+        """tensors: name -> torch CUDA tensor (contiguous) for the fields of myo_buffers."""
+        self.tensors.update(tensors)
+        b = MyoBuffers()
+        for k, t in self.tensors.items():
+            if k not in BUFFER_FIELDS:
+                raise KeyError(k)
+            if t is None:
+                continue
+            if not t.is_contiguous():
+                raise ValueError("%s must be contiguous" % k)
+            setattr(b, k, t.data_ptr())
+        _check(lib().myo_batch_bind(self.handle, ctypes.byref(b)))
+
+    def reset(self, mask=None, seed=0, env_offset=0, stream=None):
+        _check(lib().myo_batch_reset(self.handle, mask.data_ptr() if mask is not None else None, seed, env_offset, stream))
+
+    def step(self, stream=None):
+        _check(lib().myo_batch_step(self.handle, stream))
+
+    def forward_debug(self, ctrl, n_substeps=0, stream=None):
+        _check(lib().myo_batch_forward_debug(self.handle, ctrl.data_ptr(), n_substeps, stream))
+
+    @property
+    def launches(self):
+        return lib().myo_batch_launch_count(self.handle)
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            lib().myo_batch_destroy(self.handle)
+            self.handle = None

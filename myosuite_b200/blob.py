@@ -46,18 +46,19 @@ RAW_SECTIONS = [
 # kernel "program" sections (index lists precomputed by myosuite_b200.program); appended after the raw ones
 PROGRAM_SECTIONS = [
     ("P_dims", "i"),
-    ("P_body_level_adr", "i"), ("P_body_order", "i"),
-    ("P_dof_anc_adr", "i"), ("P_dof_anc", "i"),
-    ("P_body_sub_adr", "i"), ("P_body_sub", "i"),
-    ("P_piece", "i"), ("P_piece_tendon_adr", "i"),
-    ("P_wrap", "i"), ("P_wrap_d", "d"),
-    ("P_nz_adr", "i"), ("P_nz_dof", "i"), ("P_nz_tendon", "i"),
-    ("P_term_adr", "i"), ("P_term", "i"),
-    ("P_act", "d"), ("P_act_tendon", "i"),
-    ("P_pair", "i"), ("P_pair_d", "d"),
-    ("P_limit", "i"), ("P_limit_d", "d"),
-    ("P_eq", "i"), ("P_eq_d", "d"),
-    ("P_obs", "i"), ("P_obs_d", "d"),
+    # dynamic bodies (level order)
+    ("PB_level_adr", "i"), ("PB_parent", "i"), ("PB_jadr", "i"), ("PB_jnum", "i"), ("PB_model_id", "i"), ("PB_d", "d"),
+    ("PD_body", "i"), ("PD_lin", "i"), ("PDOF_d", "d"),
+    ("PCH_adr", "i"), ("PCH", "i"), ("PSUB_adr", "i"), ("PSUB", "i"),
+    ("PM_i", "i"), ("PM_j", "i"), ("PROW_adr", "i"), ("PROW_col", "i"), ("PROW_idx", "i"),
+    # tendons
+    ("PPT_body", "i"), ("PPT_xyz", "d"), ("PSP", "i"), ("PWE", "i"), ("PWE_d", "d"),
+    ("PT_const", "d"), ("PT_piece_adr", "i"), ("PT_piece", "i"), ("PT_nz_adr", "i"),
+    ("PNZ_dof", "i"), ("PNZ_tendon", "i"), ("PNZ_term_adr", "i"), ("PTERM", "i"), ("PCOL_adr", "i"), ("PCOL", "i"),
+    ("PA_tendon", "i"), ("PA_d", "d"),
+    # collision / constraints
+    ("PG_body", "i"), ("PG_type", "i"), ("PG_d", "d"), ("PPAIR", "i"), ("PPAIR_d", "d"), ("PPATH", "i"),
+    ("PLIM", "i"), ("PLIM_d", "d"), ("PEQ", "i"), ("PEQ_d", "d"),
 ]
 
 SECTIONS = RAW_SECTIONS + PROGRAM_SECTIONS

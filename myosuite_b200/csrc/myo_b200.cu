@@ -1,0 +1,270 @@
+// myo_b200.cu -- kernels + C-ABI of libmyo_b200.so (see include/myo_b200.h for the boundary contract).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "myo_solver.cuh"
+
+// ------------------------------------------------------------------ kernel arguments
+struct StepArgs {
+  myo_buffers b; myo_task_cfg cfg;
+  int n_env, obs_dim, mode;     // mode 0: env step ; 1: debug forward (ctrl verbatim, optional substeps) ; 2: reset only
+  int n_substeps;               // mode 1
+  const double* dbg_ctrl;       // mode 1
+  const uint8_t* reset_mask;    // mode 2 (nullable)
+  unsigned long long seed; long long env_offset;
+  double tol, dt;
+};
+
+// ------------------------------------------------------------------ Philox4x32-10 (counter-based RNG, one stream per (seed, env, episode))
+struct Philox { uint32_t c[4], k[2]; uint32_t out[4]; int have; };
+__device__ __forceinline__ void philox_round(uint32_t* c, const uint32_t* k) {
+  uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u*c[0], hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u*c[2];
+  uint32_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0; c[0]=n0; c[1]=n1; c[2]=n2; c[3]=n3; }
+__device__ __forceinline__ void philox_gen(Philox& p) {
+  uint32_t c[4] = {p.c[0], p.c[1], p.c[2], p.c[3]}, k[2] = {p.k[0], p.k[1]};
+  for (int r = 0; r < 10; r++) { philox_round(c, k); k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u; }
+  p.out[0]=c[0]; p.out[1]=c[1]; p.out[2]=c[2]; p.out[3]=c[3]; p.have = 4; if (++p.c[0] == 0) ++p.c[1]; }
+__device__ __forceinline__ void philox_init(Philox& p, unsigned long long seed, unsigned long long env, unsigned long long episode, uint32_t lane) {
+  p.k[0] = (uint32_t)seed; p.k[1] = (uint32_t)(seed >> 32); p.c[0] = 0; p.c[1] = lane; p.c[2] = (uint32_t)env ^ (uint32_t)(episode << 20); p.c[3] = (uint32_t)(env >> 32) ^ (uint32_t)(episode >> 12) ^ 0x4D594F42u; p.have = 0; }
+__device__ __forceinline__ double philox_uniform(Philox& p) {   // [0,1) with 53 random bits
+  if (p.have < 2) philox_gen(p);
+  uint32_t a = p.out[4-p.have], b = p.out[5-p.have]; p.have -= 2;
+  return ((double)(((unsigned long long)(a >> 5) << 26) | (b >> 6))) * (1.0/9007199254740992.0); }
+
+// ------------------------------------------------------------------ one physics substep = forward dynamics (+ optional taps) + Euler
+__device__ void substep(const DevModel& m, Warp& w, const StepArgs& a, int env, bool tap, bool integrate) {
+  phase_kinematics(m, w);
+  phase_tendon(m, w);
+  phase_actuation(m, w);
+  phase_crb(m, w);
+  phase_bias(m, w);
+  phase_collision(m, w);
+  phase_constraints(m, w);
+  phase_solve(m, w, a.tol);
+  if (tap) { Solv s = solv_views(m, w); const myo_buffers& b = a.b;
+    if (b.tap_qacc) for (int i = w.lane; i < m.nv; i += 32) b.tap_qacc[(size_t)env*m.nv+i] = s.a[i];
+    if (b.tap_qfrc_smooth) for (int i = w.lane; i < m.nv; i += 32) b.tap_qfrc_smooth[(size_t)env*m.nv+i] = w.fsm[i];
+    if (b.tap_actuator_force) for (int i = w.lane; i < m.nu; i += 32) b.tap_actuator_force[(size_t)env*m.nu+i] = w.aforce[i];
+    if (b.tap_ten_length) { const int* at = ISEC(m, PA_tendon); const double* PA = DSEC(m, PA_d); for (int i = w.lane; i < m.nu; i += 32) b.tap_ten_length[(size_t)env*m.nu+i] = PA[i*PA_STRIDE+26]*w.tlen[at[i]]; }
+    if (b.tap_moment) for (int i = w.lane; i < m.nnz; i += 32) b.tap_moment[(size_t)env*m.nnz+i] = w.mom[i];
+    if (b.tap_qM) for (int i = w.lane; i < m.nM; i += 32) b.tap_qM[(size_t)env*m.nM+i] = w.qM[i];
+    if (b.tap_ncon && w.lane == 0) { int* t = b.tap_ncon + 4*(size_t)env; t[0] = w.ncon; t[1] = w.nefc; t[2] = w.niter; t[3] = w.overflow; }
+    if (b.tap_contact_pair) for (int c = w.lane; c < m.maxcon; c += 32) b.tap_contact_pair[(size_t)env*m.maxcon+c] = c < w.ncon ? s.cpair[c] : -1;
+    if (b.tap_contact_dist) for (int c = w.lane; c < m.maxcon; c += 32) b.tap_contact_dist[(size_t)env*m.maxcon+c] = c < w.ncon ? s.con[c*CON_STRIDE] : 0.0;
+    __syncwarp(); }
+  if (integrate) phase_integrate(m, w);
+}
+
+// ------------------------------------------------------------------ task logic: pose task (pose_v0.py:100-140,154-170,174-257)
+__device__ void env_reset(const DevModel& m, Warp& w, const StepArgs& a, int env) {
+  const myo_buffers& b = a.b; long long ep = b.episode_count ? b.episode_count[env] : 0;
+  Philox rng; philox_init(rng, a.seed, (unsigned long long)(a.env_offset + env), (unsigned long long)ep, (uint32_t)w.lane);
+  const int* jtype = ISEC(m, jnt_type); const int* jq = ISEC(m, jnt_qposadr); const double* jrange = DSEC(m, jnt_range); const double* qpos0 = DSEC(m, qpos0);
+  for (int i = w.lane; i < m.nq; i += 32) w.qpos[i] = b.init_qpos ? b.init_qpos[i] : qpos0[i];
+  __syncwarp();
+  if (a.cfg.task == MYO_TASK_POSE) {
+    // target_jnt_value ~ U(target_jnt_range) ; reset_type "random": qpos ~ U(jnt_range)
+    for (int j = w.lane; j < m.njnt; j += 32) { if (jtype[j] == 0) continue; int qa = jq[j];
+      double u0 = philox_uniform(rng), u1 = philox_uniform(rng);
+      if (b.target && b.target_range) b.target[(size_t)env*m.nq+qa] = b.target_range[2*qa] + u0*(b.target_range[2*qa+1]-b.target_range[2*qa]);
+      if (a.cfg.reset_random) w.qpos[qa] = jrange[2*j] + u1*(jrange[2*j+1]-jrange[2*j]); }
+  }
+  for (int i = w.lane; i < m.nv; i += 32) { w.qvel[i] = 0; w.qws[i] = 0; }
+  for (int i = w.lane; i < m.na; i += 32) w.act[i] = 0;
+  if (b.fatigue && a.cfg.muscle_condition == MYO_COND_FATIGUE) for (int i = w.lane; i < m.nu; i += 32) { double* f = b.fatigue + (size_t)env*3*m.nu; f[i] = 0; f[m.nu+i] = 1; f[2*m.nu+i] = 0; }
+  if (w.lane == 0) { if (b.time) b.time[env] = 0; if (b.step_count) b.step_count[env] = 0; if (b.episode_count) b.episode_count[env] = ep+1; if (b.ep_return) b.ep_return[env] = 0; }
+  __syncwarp();
+}
+
+__device__ void write_obs_pose(const DevModel& m, Warp& w, const StepArgs& a, int env, double* dist_out, double* actmag_out) {
+  const myo_buffers& b = a.b; float* o = b.obs ? b.obs + (size_t)env*a.obs_dim : nullptr; double d2 = 0, a2 = 0;
+  for (int i = w.lane; i < m.nq; i += 32) { double tgt = b.target ? b.target[(size_t)env*m.nq+i] : 0.0, err = tgt - w.qpos[i]; d2 += err*err;
+    if (o) { o[i] = (float)w.qpos[i]; o[m.nq+m.nv+i] = (float)err; } }
+  if (o) for (int i = w.lane; i < m.nv; i += 32) o[m.nq+i] = (float)(w.qvel[i]*a.dt);
+  for (int i = w.lane; i < m.na; i += 32) { a2 += w.act[i]*w.act[i]; if (o) o[2*m.nq+m.nv+i] = (float)w.act[i]; }
+  *dist_out = sqrt(warp_sum(d2)); double am = sqrt(warp_sum(a2)); *actmag_out = m.na ? am/m.na : am;
+}
+
+// ------------------------------------------------------------------ the kernel
+extern "C" __global__ void __launch_bounds__(256) myo_env_kernel(DevModel m, StepArgs a) {
+  extern __shared__ double smem[];
+  int wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  Warp w; w.lane = threadIdx.x & 31;
+  double* base = smem + (size_t)wid*m.n_per_warp;
+  w.qpos = base+m.o_qpos; w.qvel = base+m.o_qvel; w.act = base+m.o_act; w.ctrl = base+m.o_ctrl; w.qws = base+m.o_qws; w.xpos = base+m.o_xpos; w.xquat = base+m.o_xquat;
+  w.xmat = base+m.o_xmat; w.cin = base+m.o_cin; w.dax = base+m.o_dax; w.dan = base+m.o_dan; w.mom = base+m.o_mom; w.tlen = base+m.o_tlen; w.tvel = base+m.o_tvel;
+  w.tfrc = base+m.o_tfrc; w.aforce = base+m.o_aforce; w.actdot = base+m.o_actdot; w.qM = base+m.o_qM; w.fsm = base+m.o_fsm; w.arena = base+m.o_arena;
+  w.ncon = w.nefc = w.nlimrow = w.niter = w.overflow = 0;
+  const myo_buffers& b = a.b;
+  for (int env = blockIdx.x*nw + wid; env < a.n_env; env += gridDim.x*nw) {
+    // ---- load state (coalesced: one env's row per warp)
+    for (int i = w.lane; i < m.nq; i += 32) w.qpos[i] = b.qpos[(size_t)env*m.nq+i];
+    for (int i = w.lane; i < m.nv; i += 32) { w.qvel[i] = b.qvel[(size_t)env*m.nv+i]; w.qws[i] = b.qacc_warmstart[(size_t)env*m.nv+i]; }
+    for (int i = w.lane; i < m.na; i += 32) w.act[i] = b.act[(size_t)env*m.na+i];
+    __syncwarp();
+    if (a.mode == 2) {
+      if (!a.reset_mask || a.reset_mask[env]) { env_reset(m, w, a, env);
+        if (a.cfg.task == MYO_TASK_POSE) { double d, am; write_obs_pose(m, w, a, env, &d, &am); }
+        if (w.lane == 0) { if (b.done) b.done[env] = 0; if (b.truncated) b.truncated[env] = 0; if (b.reward) b.reward[env] = 0; } }
+    } else if (a.mode == 1) {
+      for (int i = w.lane; i < m.nu; i += 32) w.ctrl[i] = a.dbg_ctrl[(size_t)env*m.nu+i];
+      __syncwarp();
+      int ns = a.n_substeps > 0 ? a.n_substeps : 1;
+      for (int s = 0; s < ns; s++) substep(m, w, a, env, s == ns-1, a.n_substeps > 0);
+      if (a.n_substeps > 0 && w.lane == 0 && b.time) b.time[env] += ns*m.timestep;
+    } else {
+      // ---- action -> ctrl  (base_v0.py:83-96); fatigue (fatigue.py:38-76)
+      for (int i = w.lane; i < m.nu; i += 32) { double c = (double)b.action[(size_t)env*m.nu+i];
+        if (a.cfg.normalize_act) c = 1.0/(1.0+exp(-5.0*(c-0.5)));
+        if (a.cfg.muscle_condition == MYO_COND_FATIGUE && b.fatigue) { double* F = b.fatigue + (size_t)env*3*m.nu; const double* PA = DSEC(m, PA_d) + i*PA_STRIDE;
+          double MA = F[i], MR = F[m.nu+i], MF = F[2*m.nu+i], TL = c, fdt = a.dt, tauact = PA[0], taudeact = PA[1];
+          const double r = 10*15, Fc = 0.00912, Rc = 0.1*0.00094;
+          double LD = 1.0/tauact*(0.5+1.5*MA), LR = (0.5+1.5*MA)/taudeact, C = 0;
+          if (MA < TL && MR > TL-MA) C = LD*(TL-MA);
+          if (MA < TL && MR <= TL-MA) C = LD*MR;
+          if (MA >= TL) C = LR*(TL-MA);
+          double rR = MA >= TL ? r*Rc : Rc;
+          double lo = fmax(-MA/fdt + Fc*MA, (MR-1)/fdt + rR*MF), hi = fmin((1-MA)/fdt + Fc*MA, MR/fdt + rR*MF);
+          C = fmin(fmax(C, lo), hi);   // np.clip(C, lo, hi) == minimum(maximum(C, lo), hi)
+          double dMA = (C-Fc*MA)*fdt, dMR = (-C+rR*MF)*fdt, dMF = (Fc*MA-rR*MF)*fdt;
+          MA += dMA; MR += dMR; MF += dMF; F[i] = MA; F[m.nu+i] = MR; F[2*m.nu+i] = MF; c = MA; }
+        w.ctrl[i] = c; }
+      __syncwarp();
+      for (int s = 0; s < a.cfg.frame_skip; s++) substep(m, w, a, env, s == a.cfg.frame_skip-1, true);
+      // ---- obs / reward / done / TimeLimit / auto-reset
+      if (a.cfg.task == MYO_TASK_POSE) { double dist, am; write_obs_pose(m, w, a, env, &dist, &am);
+        const double far_th = 4*3.14159265358979323846/2; double thd = a.cfg.pose_thd;
+        double rw = a.cfg.weights[0]*(-dist) + a.cfg.weights[1]*((dist < thd ? 1.0 : 0.0)+(dist < 1.5*thd ? 1.0 : 0.0)) + a.cfg.weights[2]*(-am) + a.cfg.weights[3]*(dist > far_th ? -1.0 : 0.0);
+        bool done = dist > far_th; int sc = b.step_count ? b.step_count[env]+1 : 0; bool trunc = a.cfg.max_episode_steps > 0 && sc >= a.cfg.max_episode_steps;
+        __syncwarp();
+        if (w.lane == 0) { if (b.reward) b.reward[env] = (float)rw; if (b.done) b.done[env] = done; if (b.truncated) b.truncated[env] = trunc && !done;
+          if (b.step_count) b.step_count[env] = sc; if (b.time) b.time[env] += a.cfg.frame_skip*m.timestep;
+          if (b.ep_return) { float R = b.ep_return[env] + (float)rw; b.ep_return[env] = R; if ((done || trunc) && b.last_return) b.last_return[env] = R; } }
+        __syncwarp();
+        if ((done || trunc) && a.cfg.auto_reset) { env_reset(m, w, a, env); double d2, a2; write_obs_pose(m, w, a, env, &d2, &a2); }
+      } else if (w.lane == 0 && b.time) b.time[env] += a.cfg.frame_skip*m.timestep;
+    }
+    __syncwarp();
+    // ---- store state
+    for (int i = w.lane; i < m.nq; i += 32) b.qpos[(size_t)env*m.nq+i] = w.qpos[i];
+    for (int i = w.lane; i < m.nv; i += 32) { b.qvel[(size_t)env*m.nv+i] = w.qvel[i]; b.qacc_warmstart[(size_t)env*m.nv+i] = w.qws[i]; }
+    for (int i = w.lane; i < m.na; i += 32) b.act[(size_t)env*m.na+i] = w.act[i];
+    __syncwarp();
+  }
+}
+
+// ================================================================== host side (C-ABI)
+static thread_local std::string g_err;
+static int fail(const std::string& s) { g_err = s; return -1; }
+#define CUDA_OK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
+
+struct myo_model { std::vector<int32_t> I; std::vector<double> D; };
+struct myo_batch { const myo_model* model; int device, n_env; myo_task_cfg cfg; myo_buffers bufs; bool bound; DevModel dm; int32_t* dI; double* dD;
+  int warps_per_cta, grid, smem_bytes, obs_dim; long long launches; unsigned long long seed; long long env_offset; };
+
+extern "C" const char* myo_last_error(void) { return g_err.c_str(); }
+extern "C" int myo_version(void) { return 1; }
+
+extern "C" int myo_model_from_blob(const int32_t* I, int64_t nI, const double* D, int64_t nD, myo_model** out) {
+  if (!I || !out || nI < MYO_BLOB_HDR + MYO_NDIM + 3*MYO_NSEC) return fail("myo_model_from_blob: bad arguments");
+  if (I[0] != MYO_BLOB_MAGIC || I[1] != MYO_BLOB_VERSION || I[2] != MYO_NDIM || I[3] != MYO_NSEC) return fail("myo_model_from_blob: blob magic/version/layout mismatch");
+  for (int s = 0; s < MYO_NSEC; s++) { long long off = MYO_SEC_OFF(I, s), len = MYO_SEC_LEN(I, s); int kind = I[MYO_BLOB_HDR+MYO_NDIM+3*s];
+    if (off < 0 || len < 0 || off + len > (kind ? nD : nI)) return fail("myo_model_from_blob: section out of range"); }
+  if (MYO_SEC_LEN(I, MYO_SEC_P_dims) < 22) return fail("myo_model_from_blob: blob carries no kernel program (pack with program=build_program(m))");
+  myo_model* m = new myo_model(); m->I.assign(I, I+nI); m->D.assign(D, D+nD); *out = m; return 0;
+}
+extern "C" void myo_model_destroy(myo_model* m) { delete m; }
+
+static int al2(int x) { return (x + 1) & ~1; }
+static void fill_devmodel(const myo_model* mm, const myo_task_cfg* cfg, DevModel& d) {
+  const int32_t* I = mm->I.data(); const double* D = mm->D.data(); memset(&d, 0, sizeof(d));
+  for (int s = 0; s < MYO_NSEC; s++) d.off[s] = MYO_SEC_OFF(I, s);
+  d.nq = MYO_DIM(I, MYO_DIM_nq); d.nv = MYO_DIM(I, MYO_DIM_nv); d.nu = MYO_DIM(I, MYO_DIM_nu); d.na = MYO_DIM(I, MYO_DIM_na); d.nM = MYO_DIM(I, MYO_DIM_nM); d.njnt = MYO_DIM(I, MYO_DIM_njnt);
+  const int32_t* P = MYO_ISEC(I, MYO_SEC_P_dims);
+  d.nbd = P[PD_NBD]; d.nlevel = P[PD_NLEVEL]; d.nsp = P[PD_NSP]; d.nwe = P[PD_NWE]; d.nta = P[PD_NTA]; d.nnz = P[PD_NNZ]; d.nlim = P[PD_NLIM]; d.neq = P[PD_NEQ];
+  d.npair = P[PD_NPAIR]; d.maxpath = P[PD_MAXPATH];
+  const double* opt = MYO_DSEC(I, D, MYO_SEC_opt); d.timestep = opt[0]; d.gx = opt[1]; d.gy = opt[2]; d.gz = opt[3]; d.tolerance = opt[4]; d.meaninertia = opt[6];
+  int mc = cfg && cfg->maxcon > 0 ? cfg->maxcon : 32; if (mc > 2*d.npair) mc = 2*d.npair; d.maxcon = mc; d.maxefc = d.neq + 2*d.nlim + 4*mc;
+  int o = 0;
+  #define TAKE(field, n) d.field = o; o += al2(n)
+  TAKE(o_qpos, d.nq); TAKE(o_qvel, d.nv); TAKE(o_act, d.na); TAKE(o_ctrl, d.nu); TAKE(o_qws, d.nv); TAKE(o_xpos, 3*d.nbd); TAKE(o_xquat, 4*d.nbd); TAKE(o_xmat, 9*d.nbd);
+  TAKE(o_cin, 10*d.nbd); TAKE(o_dax, 3*d.nv); TAKE(o_dan, 3*d.nv); TAKE(o_mom, d.nnz); TAKE(o_tlen, d.nta); TAKE(o_tvel, d.nta); TAKE(o_tfrc, d.nta);
+  TAKE(o_aforce, d.nu); TAKE(o_actdot, d.na); TAKE(o_qM, d.nM); TAKE(o_fsm, d.nv); TAKE(o_arena, 0);
+  #undef TAKE
+  int t = 0; d.a_U = t; t += al2(3*(d.nsp+2*d.nwe)); d.a_WP = t; t += al2(6*d.nwe); d.a_PL = t; t += al2(d.nsp+d.nwe); int sizeT = t;
+  t = 0; d.a_crb = t; t += al2(10*d.nbd); d.a_bf = t; t += al2(6*d.nbd); int sizeC = t;
+  t = 0; d.a_H = t; t += al2(d.nv*d.nv); d.a_con = t; t += al2(CON_STRIDE*mc); d.a_conJ = t; t += al2(3*d.maxpath*mc);
+  d.a_efD = t; t += al2(d.maxefc); d.a_efA = t; t += al2(d.maxefc); d.a_efR = t; t += al2(d.maxefc); d.a_efV = t; t += al2(d.maxefc);
+  d.a_va = t; t += al2(d.nv); d.a_vg = t; t += al2(d.nv); d.a_vp = t; t += al2(d.nv); d.a_vMa = t; t += al2(d.nv); d.a_vMp = t; t += al2(d.nv); d.a_eqJ = t; t += al2(d.neq);
+  d.a_icon = t; t += al2((3*mc + 2*d.nlim + 4 + 1)/2); int sizeS = t;
+  int arena = sizeT > sizeC ? sizeT : sizeC; if (sizeS > arena) arena = sizeS;
+  d.n_per_warp = o + arena;
+}
+
+extern "C" int myo_model_dims(const myo_model* m, const myo_task_cfg* cfg, myo_dims* out) {
+  if (!m || !out) return fail("myo_model_dims: null"); DevModel d; fill_devmodel(m, cfg, d); const int32_t* I = m->I.data();
+  memset(out, 0, sizeof(*out)); out->nq = d.nq; out->nv = d.nv; out->nu = d.nu; out->na = d.na; out->nbody = MYO_DIM(I, MYO_DIM_nbody); out->njnt = d.njnt; out->ntendon = MYO_DIM(I, MYO_DIM_ntendon);
+  out->nM = d.nM; out->npair = d.npair; out->nta = d.nta; out->maxcon = d.maxcon; out->maxefc = d.maxefc; out->smem_bytes_per_env = d.n_per_warp*8; out->reserved[0] = d.nnz; return 0;
+}
+
+extern "C" int myo_batch_create(const myo_model* m, int device, int n_env, const myo_task_cfg* cfg, myo_batch** out) {
+  if (!m || !cfg || !out || n_env <= 0) return fail("myo_batch_create: bad arguments");
+  int ndev = 0; cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail("myo_batch_create: no CUDA device available (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail("myo_batch_create: bad device index");
+  CUDA_OK(cudaSetDevice(device));
+  myo_batch* b = new myo_batch(); memset(&b->bufs, 0, sizeof(b->bufs)); b->model = m; b->device = device; b->n_env = n_env; b->cfg = *cfg; b->bound = false; b->launches = 0; b->seed = 0; b->env_offset = 0;
+  fill_devmodel(m, cfg, b->dm);
+  if (b->cfg.frame_skip <= 0) b->cfg.frame_skip = 1;
+  if (cfg->task == MYO_TASK_POSE && b->dm.nq != b->dm.nv) { delete b; return fail("pose task needs nq == nv"); }
+  b->obs_dim = cfg->task == MYO_TASK_POSE ? 2*b->dm.nq + b->dm.nv + b->dm.na : 0;
+  CUDA_OK(cudaMalloc(&b->dI, m->I.size()*4)); CUDA_OK(cudaMalloc(&b->dD, (m->D.size() ? m->D.size() : 1)*8));
+  CUDA_OK(cudaMemcpy(b->dI, m->I.data(), m->I.size()*4, cudaMemcpyHostToDevice)); CUDA_OK(cudaMemcpy(b->dD, m->D.data(), m->D.size()*8, cudaMemcpyHostToDevice));
+  b->dm.I = b->dI; b->dm.D = b->dD;
+  cudaDeviceProp prop; CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  int per = b->dm.n_per_warp*8, maxs = (int)prop.sharedMemPerBlockOptin;
+  int wpc = maxs/per; if (wpc > 8) wpc = 8; if (wpc < 1) { delete b; return fail("model working set exceeds shared memory of one CTA"); }
+  b->warps_per_cta = wpc; b->smem_bytes = wpc*per;
+  CUDA_OK(cudaFuncSetAttribute(myo_env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes));
+  int ctas_per_sm = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, myo_env_kernel, wpc*32, b->smem_bytes); if (ctas_per_sm < 1) ctas_per_sm = 1;
+  int need = (n_env + wpc - 1)/wpc, cap = prop.multiProcessorCount*ctas_per_sm; b->grid = need < cap ? need : cap;
+  *out = b; return 0;
+}
+extern "C" void myo_batch_destroy(myo_batch* b) { if (!b) return; cudaSetDevice(b->device); cudaFree(b->dI); cudaFree(b->dD); delete b; }
+extern "C" int myo_batch_obs_dim(const myo_batch* b) { return b ? b->obs_dim : -1; }
+extern "C" int64_t myo_batch_launch_count(const myo_batch* b) { return b ? b->launches : -1; }
+
+extern "C" int myo_batch_bind(myo_batch* b, const myo_buffers* bufs) {
+  if (!b || !bufs) return fail("myo_batch_bind: null");
+  if (!bufs->qpos || !bufs->qvel || !bufs->qacc_warmstart || (b->dm.na && !bufs->act)) return fail("myo_batch_bind: qpos/qvel/act/qacc_warmstart are required");
+  if (b->cfg.muscle_condition == MYO_COND_FATIGUE && !bufs->fatigue) return fail("myo_batch_bind: fatigue buffer required for MYO_COND_FATIGUE");
+  b->bufs = *bufs; b->bound = true; return 0;
+}
+
+static int launch(myo_batch* b, StepArgs& a, void* stream) {
+  if (!b->bound) return fail("batch has no bound buffers (call myo_batch_bind)");
+  CUDA_OK(cudaSetDevice(b->device));
+  a.b = b->bufs; a.cfg = b->cfg; a.n_env = b->n_env; a.obs_dim = b->obs_dim; a.dt = b->dm.timestep*b->cfg.frame_skip;
+  a.seed = b->seed; a.env_offset = b->env_offset;
+  a.tol = b->cfg.solver_tolerance > 0 ? b->cfg.solver_tolerance : 1e-10;
+  myo_env_kernel<<<b->grid, b->warps_per_cta*32, b->smem_bytes, (cudaStream_t)stream>>>(b->dm, a);
+  CUDA_OK(cudaGetLastError()); b->launches++; return 0;
+}
+extern "C" int myo_batch_step(myo_batch* b, void* stream) {
+  if (!b) return fail("null batch"); if (!b->bufs.action) return fail("myo_batch_step: action buffer not bound");
+  StepArgs a; memset(&a, 0, sizeof(a)); a.mode = 0; return launch(b, a, stream);
+}
+extern "C" int myo_batch_reset(myo_batch* b, const uint8_t* mask, uint64_t seed, int64_t env_offset, void* stream) {
+  if (!b) return fail("null batch");
+  StepArgs a; memset(&a, 0, sizeof(a)); a.mode = 2; a.reset_mask = mask; b->seed = seed; b->env_offset = env_offset;
+  return launch(b, a, stream);
+}
+extern "C" int myo_batch_forward_debug(myo_batch* b, const double* ctrl, int n_substeps, void* stream) {
+  if (!b || !ctrl) return fail("myo_batch_forward_debug: null");
+  StepArgs a; memset(&a, 0, sizeof(a)); a.mode = 1; a.dbg_ctrl = ctrl; a.n_substeps = n_substeps; return launch(b, a, stream);
+}

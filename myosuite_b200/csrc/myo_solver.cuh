@@ -1,0 +1,214 @@
+// myo_solver.cuh -- constraint assembly, primal Newton solver and semi-implicit Euler (one env per warp).
+// Semantics: MuJoCo's soft-constraint model: rows = joint equalities, joint
+// limits, pyramidal/frictionless contacts; cost 1/2 (a-a0)'M(a-a0) + sum_i s_i(J_i a - aref_i);
+// Newton with exact line search on H = M + J' D_active J (dense Cholesky in shared memory).
+#pragma once
+#include "myo_device.cuh"
+
+struct Solv {   // arena views
+  double *H, *con, *conJ, *D, *aref, *jar, *jv, *a, *g, *p, *Ma, *Mp, *eqJ;
+  int *cpair, *crow, *cnrow, *lrow;   // contact pair idx, first efc row, #rows ; limit row descriptors (dof | sign bit 16 | limit idx << 17)
+};
+__device__ __forceinline__ Solv solv_views(const DevModel& m, Warp& w) {
+  Solv s; double* A = w.arena;
+  s.H = A + m.a_H; s.con = A + m.a_con; s.conJ = A + m.a_conJ; s.D = A + m.a_efD; s.aref = A + m.a_efA; s.jar = A + m.a_efR; s.jv = A + m.a_efV;
+  s.a = A + m.a_va; s.g = A + m.a_vg; s.p = A + m.a_vp; s.Ma = A + m.a_vMa; s.Mp = A + m.a_vMp; s.eqJ = A + m.a_eqJ;
+  int* ic = (int*)(A + m.a_icon); s.cpair = ic; s.crow = ic + m.maxcon; s.cnrow = ic + 2*m.maxcon; s.lrow = ic + 3*m.maxcon;
+  return s; }
+
+__device__ __forceinline__ double impedance(const double* si, double pos, double margin) {
+  if (si[0] == si[1] || si[2] <= MYO_MINVAL) return 0.5*(si[0]+si[1]);
+  double x = fabs((pos-margin)/si[2]);
+  if (x >= 1 || x <= 0) return x >= 1 ? si[1] : si[0];
+  double y;
+  if (si[4] == 1) y = x;
+  else if (x <= si[3]) y = pow(x, si[4])/pow(si[3], si[4]-1);
+  else y = 1-pow(1-x, si[4])/pow(1-si[3], si[4]-1);
+  return si[0]+y*(si[1]-si[0]); }
+
+// y = M x using the per-row non-zero lists
+__device__ __forceinline__ void mul_M(const DevModel& m, const Warp& w, double* y, const double* x) {
+  const int* radr = ISEC(m, PROW_adr); const int* rcol = ISEC(m, PROW_col); const int* ridx = ISEC(m, PROW_idx);
+  for (int i = w.lane; i < m.nv; i += 32) { double s = 0; for (int e = radr[i]; e < radr[i+1]; e++) s += w.qM[ridx[e]]*x[rcol[e]]; y[i] = s; } }
+
+// out[r] = (J x)_r for every constraint row
+__device__ void rows_apply(const DevModel& m, const Warp& w, const Solv& s, const double* x, double* out) {
+  const int* eq = ISEC(m, PEQ);
+  for (int e = w.lane; e < m.neq; e += 32) { double v = x[eq[4*e+1]]; if (eq[4*e+3] >= 0) v += s.eqJ[e]*x[eq[4*e+3]]; out[e] = v; }
+  for (int r = w.lane; r < w.nlimrow; r += 32) { int dsc = s.lrow[r]; double sg = (dsc >> 16) & 1 ? -1.0 : 1.0; out[m.neq + r] = sg*x[dsc & 0xffff]; }
+  const int* pr = ISEC(m, PPAIR); const double* pd = DSEC(m, PPAIR_d); const int* path = ISEC(m, PPATH);
+  for (int c = w.lane; c < w.ncon; c += 32) { int nr = s.cnrow[c]; if (!nr) continue;
+    const int* q = pr + 6*s.cpair[c]; const double* J = s.conJ + (size_t)c*3*m.maxpath; double n = 0, t1 = 0, t2 = 0;
+    for (int e = 0; e < q[4]; e++) { double xv = x[path[q[3]+e] >> 1]; n += J[3*e]*xv; t1 += J[3*e+1]*xv; t2 += J[3*e+2]*xv; }
+    int rb = s.crow[c];
+    if (nr == 1) out[rb] = n;
+    else { const double* P = pd + s.cpair[c]*PPAIR_STRIDE; double mu1 = P[2], mu2 = P[3]; out[rb] = n+mu1*t1; out[rb+1] = n-mu1*t1; out[rb+2] = n+mu2*t2; out[rb+3] = n-mu2*t2; } }
+}
+
+// vec[d] += sum_r J[r][d] * wgt[r]  (wgt already includes D and the active mask)
+__device__ void rows_applyT_add(const DevModel& m, const Warp& w, const Solv& s, const double* wgt, double* vec) {
+  const int* eq = ISEC(m, PEQ);
+  if (w.lane == 0) for (int e = 0; e < m.neq; e++) { vec[eq[4*e+1]] += wgt[e]; if (eq[4*e+3] >= 0) vec[eq[4*e+3]] += s.eqJ[e]*wgt[e]; }
+  __syncwarp();
+  for (int pass = 0; pass < 2; pass++) {
+    for (int r = w.lane; r < w.nlimrow; r += 32) { int dsc = s.lrow[r]; int neg = (dsc >> 16) & 1; if (neg == pass) vec[dsc & 0xffff] += (neg ? -1.0 : 1.0)*wgt[m.neq + r]; }
+    __syncwarp(); }
+  const int* pr = ISEC(m, PPAIR); const double* pd = DSEC(m, PPAIR_d); const int* path = ISEC(m, PPATH);
+  for (int c = 0; c < w.ncon; c++) { int nr = s.cnrow[c]; if (!nr) continue;
+    const int* q = pr + 6*s.cpair[c]; const double* J = s.conJ + (size_t)c*3*m.maxpath; int rb = s.crow[c]; double wn, w1 = 0, w2 = 0;
+    if (nr == 1) wn = wgt[rb];
+    else { const double* P = pd + s.cpair[c]*PPAIR_STRIDE; wn = wgt[rb]+wgt[rb+1]+wgt[rb+2]+wgt[rb+3]; w1 = P[2]*(wgt[rb]-wgt[rb+1]); w2 = P[3]*(wgt[rb+2]-wgt[rb+3]); }
+    for (int e = w.lane; e < q[4]; e += 32) vec[path[q[3]+e] >> 1] += J[3*e]*wn + J[3*e+1]*w1 + J[3*e+2]*w2;
+    __syncwarp(); }
+}
+
+// ------------------------------------------------------------------ constraint assembly
+__device__ void phase_constraints(const DevModel& m, Warp& w) {
+  Solv s = solv_views(m, w);
+  // joint equalities (always active)
+  const int* eq = ISEC(m, PEQ); const double* eqd = DSEC(m, PEQ_d);
+  for (int e = w.lane; e < m.neq; e += 32) { const double* c = eqd + e*PEQ_STRIDE; int q1 = eq[4*e], d1 = eq[4*e+1], q2 = eq[4*e+2], d2 = eq[4*e+3];
+    double pos0 = w.qpos[q1]-c[5], cpos, deriv = 0, vel = w.qvel[d1];
+    if (q2 >= 0) { double x = w.qpos[q2]-c[6]; cpos = pos0-(c[0]+x*(c[1]+x*(c[2]+x*(c[3]+x*c[4])))); deriv = c[1]+x*(2*c[2]+x*(3*c[3]+x*4*c[4])); vel -= deriv*w.qvel[d2]; }
+    else cpos = pos0-c[0];
+    s.eqJ[e] = -deriv;
+    double imp = impedance(c+10, cpos, 0), R = fmax(MYO_MINVAL, (1-imp)*c[7]/imp);
+    s.D[e] = 1.0/R; s.aref[e] = -c[9]*vel - c[8]*imp*cpos; }
+  // joint limits (one-sided)
+  const int* lim = ISEC(m, PLIM); const double* limd = DSEC(m, PLIM_d); int nrow = 0;
+  for (int base = 0; base < m.nlim; base += 32) { int l = base + w.lane; bool lo = false, hi = false; double dlo = 0, dhi = 0; const double* c = limd + (l < m.nlim ? l : 0)*PLIM_STRIDE; int d = 0;
+    if (l < m.nlim) { d = lim[2*l]; double q = w.qpos[lim[2*l+1]]; dlo = q-c[0]; dhi = c[1]-q; lo = dlo < c[2]; hi = dhi < c[2]; }
+    unsigned m0 = __ballot_sync(FULL, lo), m1 = __ballot_sync(FULL, hi), lt = (1u << w.lane)-1; int idx = nrow + __popc(m0 & lt) + __popc(m1 & lt);
+    for (int side = 0; side < 2; side++) { if (!(side ? hi : lo)) continue;
+      double dist = side ? dhi : dlo, sg = side ? -1.0 : 1.0; int r = m.neq + idx; idx++;
+      s.lrow[r - m.neq] = d | (side << 16);
+      double imp = impedance(c+6, dist, c[2]), R = fmax(MYO_MINVAL, (1-imp)*c[3]/imp);
+      s.D[r] = 1.0/R; s.aref[r] = -c[5]*sg*w.qvel[d] - c[4]*imp*(dist-c[2]); }
+    nrow += __popc(m0) + __popc(m1); }
+  w.nlimrow = nrow;
+  // contacts: Jacobian over the dofs between the two bodies, regulariser, reference acceleration
+  const int* pr = ISEC(m, PPAIR); const double* pd = DSEC(m, PPAIR_d); const int* path = ISEC(m, PPATH);
+  int rowbase = m.neq + nrow;
+  for (int base = 0; base < w.ncon; base += 32) { int c = base + w.lane; int nr = 0;
+    if (c < w.ncon) { const int* q = pr + 6*s.cpair[c]; const double* P = pd + s.cpair[c]*PPAIR_STRIDE; double dist = s.con[c*CON_STRIDE];
+      nr = (dist < P[0]-P[1]) ? (q[2] == 1 ? 1 : 4) : 0; }
+    int incl = nr;   // inclusive warp scan
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, incl, o); if (w.lane >= o) incl += t; }
+    int total = __shfl_sync(FULL, incl, 31);
+    if (c < w.ncon) { s.crow[c] = rowbase + incl - nr; s.cnrow[c] = nr; }
+    if (c < w.ncon && nr) { const int* q = pr + 6*s.cpair[c]; const double* P = pd + s.cpair[c]*PPAIR_STRIDE; const double* cd = s.con + c*CON_STRIDE;
+      const double* pos = cd + 1; const double* f = cd + 4; double* J = s.conJ + (size_t)c*3*m.maxpath; double vn = 0, v1 = 0, v2 = 0;
+      for (int e = 0; e < q[4]; e++) { int code = path[q[3]+e], d = code >> 1; double sg = (code & 1) ? 1.0 : -1.0, cv[3]; dof_point_vel(m, w, d, pos, cv);
+        double jn = sg*dot3(f, cv), j1 = sg*dot3(f+3, cv), j2 = sg*dot3(f+6, cv); J[3*e] = jn; J[3*e+1] = j1; J[3*e+2] = j2;
+        double qd = w.qvel[d]; vn += jn*qd; v1 += j1*qd; v2 += j2*qd; }
+      double dist = cd[0], inc = P[0]-P[1], imp = impedance(P+7, dist, inc), K = P[5], B = P[6], tran = P[4]; int rb = rowbase + incl - nr;
+      if (nr == 1) { double R = fmax(MYO_MINVAL, (1-imp)*tran/imp); s.D[rb] = 1.0/R; s.aref[rb] = -B*vn - K*imp*(dist-inc); }
+      else { double mu1 = P[2], mu2 = P[3]; double R0 = fmax(MYO_MINVAL, (1-imp)*(tran+mu1*mu1*tran)/imp), Rpy = 2*mu1*mu1*R0, Dv = 1.0/Rpy, kp = K*imp*(dist-inc);
+        s.D[rb] = s.D[rb+1] = s.D[rb+2] = s.D[rb+3] = Dv;
+        s.aref[rb] = -B*(vn+mu1*v1)-kp; s.aref[rb+1] = -B*(vn-mu1*v1)-kp; s.aref[rb+2] = -B*(vn+mu2*v2)-kp; s.aref[rb+3] = -B*(vn-mu2*v2)-kp; } }
+    rowbase += total; }
+  w.nefc = rowbase;
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------ dense Cholesky (lower, in place) + solve, nv x nv in shared memory
+__device__ void chol_factor(double* H, int n, int lane) {
+  for (int k = 0; k < n; k++) {
+    double dkk = sqrt(fmax(H[k*n+k], MYO_MINVAL));
+    __syncwarp();
+    if (lane == 0) H[k*n+k] = dkk;
+    double inv = 1.0/dkk;
+    for (int i = k+1+lane; i < n; i += 32) H[i*n+k] *= inv;
+    __syncwarp();
+    for (int i = k+1+lane; i < n; i += 32) { double lik = H[i*n+k]; for (int j = k+1; j <= i; j++) H[i*n+j] -= lik*H[j*n+k]; }
+    __syncwarp(); }
+}
+// x <- H^-1 x  (H holds the Cholesky factor)
+__device__ void chol_solve(const double* H, int n, double* x, int lane) {
+  for (int k = 0; k < n; k++) { double xk = x[k]/H[k*n+k]; __syncwarp(); if (lane == 0) x[k] = xk;
+    for (int i = k+1+lane; i < n; i += 32) x[i] -= H[i*n+k]*xk; __syncwarp(); }
+  for (int k = n-1; k >= 0; k--) { double xk = x[k]/H[k*n+k]; __syncwarp(); if (lane == 0) x[k] = xk;
+    for (int i = lane; i < k; i += 32) x[i] -= H[k*n+i]*xk; __syncwarp(); }
+}
+__device__ __forceinline__ void load_M_dense(const DevModel& m, const Warp& w, double* H, double diag_scale /* h */) {
+  int n = m.nv; for (int i = w.lane; i < n*n; i += 32) H[i] = 0; __syncwarp();
+  const int* mi = ISEC(m, PM_i); const int* mj = ISEC(m, PM_j); const double* dofp = DSEC(m, PDOF_d);
+  for (int e = w.lane; e < m.nM; e += 32) { int i = mi[e], j = mj[e]; double v = w.qM[e]; if (i == j) v += diag_scale*dofp[2*i+1]; H[i*n+j] = v; H[j*n+i] = v; }
+  __syncwarp(); }
+
+// ------------------------------------------------------------------ Newton solver: leaves qacc in s.a
+__device__ void phase_solve(const DevModel& m, Warp& w, double tol) {
+  Solv s = solv_views(m, w); int n = m.nv, nefc = w.nefc; w.niter = 0;
+  if (nefc == 0) {   // unconstrained: qacc = M^-1 qfrc_smooth
+    load_M_dense(m, w, s.H, 0.0); chol_factor(s.H, n, w.lane);
+    for (int i = w.lane; i < n; i += 32) s.a[i] = w.fsm[i]; __syncwarp();
+    chol_solve(s.H, n, s.a, w.lane); return; }
+  for (int i = w.lane; i < n; i += 32) s.a[i] = w.qws[i]; __syncwarp();
+  mul_M(m, w, s.Ma, s.a); rows_apply(m, w, s, s.a, s.jar); __syncwarp();
+  for (int r = w.lane; r < nefc; r += 32) s.jar[r] -= s.aref[r]; __syncwarp();
+  const double scale = 1.0/(m.meaninertia*(n > 1 ? n : 1));
+  const int* eq = ISEC(m, PEQ); const int* pr = ISEC(m, PPAIR); const double* pd = DSEC(m, PPAIR_d); const int* path = ISEC(m, PPATH);
+  for (int iter = 0; iter < 50; iter++) {
+    // gradient
+    for (int i = w.lane; i < n; i += 32) s.g[i] = s.Ma[i]-w.fsm[i];
+    for (int r = w.lane; r < nefc; r += 32) { double x = s.jar[r]; s.jv[r] = (r < m.neq || x < 0) ? s.D[r]*x : 0.0; }   // jv used as scratch weights
+    __syncwarp(); rows_applyT_add(m, w, s, s.jv, s.g); __syncwarp();
+    double gn = 0; for (int i = w.lane; i < n; i += 32) gn += s.g[i]*s.g[i]; gn = sqrt(warp_sum(gn));
+    if (scale*gn < tol) break;
+    // Hessian
+    load_M_dense(m, w, s.H, 0.0);
+    if (w.lane == 0) for (int e = 0; e < m.neq; e++) { int d1 = eq[4*e+1], d2 = eq[4*e+3]; double De = s.D[e], j2 = s.eqJ[e]; s.H[d1*n+d1] += De;
+      if (d2 >= 0) { s.H[d1*n+d2] += De*j2; s.H[d2*n+d1] += De*j2; s.H[d2*n+d2] += De*j2*j2; } }
+    __syncwarp();
+    for (int pass = 0; pass < 2; pass++) { for (int r = w.lane; r < w.nlimrow; r += 32) { int dsc = s.lrow[r]; if (((dsc >> 16) & 1) == pass && s.jar[m.neq+r] < 0) { int d = dsc & 0xffff; s.H[d*n+d] += s.D[m.neq+r]; } } __syncwarp(); }
+    for (int c = 0; c < w.ncon; c++) { int nr = s.cnrow[c]; if (!nr) continue; int rb = s.crow[c]; const int* q = pr + 6*s.cpair[c]; double W[6] = {0,0,0,0,0,0};  // nn n1 n2 11 12 22
+      if (nr == 1) { if (s.jar[rb] < 0) W[0] = s.D[rb]; }
+      else { const double* P = pd + s.cpair[c]*PPAIR_STRIDE; double mu1 = P[2], mu2 = P[3], Dv = s.D[rb];
+        double a0 = s.jar[rb] < 0 ? Dv : 0, a1 = s.jar[rb+1] < 0 ? Dv : 0, a2 = s.jar[rb+2] < 0 ? Dv : 0, a3 = s.jar[rb+3] < 0 ? Dv : 0;
+        W[0] = a0+a1+a2+a3; W[1] = mu1*(a0-a1); W[2] = mu2*(a2-a3); W[3] = mu1*mu1*(a0+a1); W[5] = mu2*mu2*(a2+a3); }
+      if (W[0] != 0) { const double* J = s.conJ + (size_t)c*3*m.maxpath; int np = q[4];
+        for (int t = w.lane; t < np*np; t += 32) { int ei = t / np, ej = t - ei*np; const double* a = J + 3*ei; const double* b = J + 3*ej;
+          double wa0 = W[0]*a[0]+W[1]*a[1]+W[2]*a[2], wa1 = W[1]*a[0]+W[3]*a[1]+W[4]*a[2], wa2 = W[2]*a[0]+W[4]*a[1]+W[5]*a[2];
+          s.H[(path[q[3]+ei] >> 1)*n + (path[q[3]+ej] >> 1)] += wa0*b[0]+wa1*b[1]+wa2*b[2]; } }
+      __syncwarp(); }
+    chol_factor(s.H, n, w.lane);
+    for (int i = w.lane; i < n; i += 32) s.p[i] = -s.g[i]; __syncwarp();
+    chol_solve(s.H, n, s.p, w.lane);
+    // exact line search along p
+    mul_M(m, w, s.Mp, s.p); rows_apply(m, w, s, s.p, s.jv); __syncwarp();
+    double ga = 0, gb = 0; for (int i = w.lane; i < n; i += 32) { ga += s.p[i]*(s.Ma[i]-w.fsm[i]); gb += s.p[i]*s.Mp[i]; } ga = warp_sum(ga); gb = warp_sum(gb);
+    double alpha = 0, lo = 0, hi = -1, d0 = 0;
+    for (int it = 0; it < 40; it++) { double dv = 0, hh = 0;
+      for (int r = w.lane; r < nefc; r += 32) { double x = s.jar[r]+alpha*s.jv[r]; if (r < m.neq || x < 0) { dv += s.D[r]*x*s.jv[r]; hh += s.D[r]*s.jv[r]*s.jv[r]; } }
+      dv = warp_sum(dv) + ga + gb*alpha; hh = warp_sum(hh) + gb;
+      if (it == 0) { d0 = fabs(dv); if (dv >= 0) break; } else { if (dv < 0) lo = alpha; else hi = alpha; if (fabs(dv) <= 1e-10*d0) break; }
+      double an = alpha - dv/hh;
+      if (it > 0 && (an <= lo || (hi > 0 && an >= hi))) an = hi > 0 ? 0.5*(lo+hi) : 2*alpha+1;
+      if (an == alpha) break;
+      alpha = an; }
+    if (alpha == 0) break;   // no descent possible: converged to round-off
+    for (int i = w.lane; i < n; i += 32) { s.a[i] += alpha*s.p[i]; s.Ma[i] += alpha*s.Mp[i]; }
+    for (int r = w.lane; r < nefc; r += 32) s.jar[r] += alpha*s.jv[r];
+    __syncwarp(); w.niter = iter+1; }
+}
+
+// ------------------------------------------------------------------ semi-implicit Euler with implicit joint damping
+__device__ void phase_integrate(const DevModel& m, Warp& w) {
+  Solv s = solv_views(m, w); int n = m.nv; double h = m.timestep;
+  // (M + h B) qacc' = M qacc  (= qfrc_smooth + qfrc_constraint at the solver optimum)
+  mul_M(m, w, s.g, s.a); __syncwarp();
+  load_M_dense(m, w, s.H, h); chol_factor(s.H, n, w.lane); chol_solve(s.H, n, s.g, w.lane);
+  for (int i = w.lane; i < m.na; i += 32) w.act[i] += h*w.actdot[i];
+  for (int i = w.lane; i < n; i += 32) { w.qvel[i] += h*s.g[i]; w.qws[i] = s.a[i]; }
+  __syncwarp();
+  const int* jtype = ISEC(m, jnt_type); const int* jq = ISEC(m, jnt_qposadr); const int* jd = ISEC(m, jnt_dofadr);
+  for (int j = w.lane; j < m.njnt; j += 32) { int qa = jq[j], da = jd[j];
+    if (jtype[j] == 0) { for (int c = 0; c < 3; c++) w.qpos[qa+c] += h*w.qvel[da+c];
+      double wv[3] = {w.qvel[da+3], w.qvel[da+4], w.qvel[da+5]}, nn = sqrt(dot3(wv,wv)), ang = h*nn;
+      if (nn < MYO_MINVAL) { wv[0]=1; wv[1]=0; wv[2]=0; } else { wv[0]/=nn; wv[1]/=nn; wv[2]/=nn; }
+      double sn, cs; sincos(0.5*ang, &sn, &cs); double ql[4] = {cs, wv[0]*sn, wv[1]*sn, wv[2]*sn}, qn[4]; quat_mul(qn, w.qpos+qa+3, ql); quat_norm(qn);
+      for (int c = 0; c < 4; c++) w.qpos[qa+3+c] = qn[c]; }
+    else w.qpos[qa] += h*w.qvel[da]; }
+  __syncwarp();
+}

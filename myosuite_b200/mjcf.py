@@ -1054,3 +1054,38 @@ def _unreachable(m, kin, g1, g2, margin):
         return "static cylinder out of reach (%.3f m clear)" % dist if dist > margin else None
     dist = float(np.linalg.norm(c1 - c2)) - rad1 - rad2
     return "bounding reach spheres %.3f m apart" % dist if dist > margin else None
+
+
+# ----------------------------------------------------------------------------- (de)serialisation of compiled models
+
+def save_model(m, path):
+    """Write a compiled Model to a single .npz (arrays + a JSON blob of scalars / names)."""
+    import json
+    arrays, meta = {}, {"names": m.names, "scalars": {}, "lists": {}}
+    for k, v in m.__dict__.items():
+        if k == "names":
+            continue
+        if isinstance(v, np.ndarray):
+            arrays[k] = v
+        elif isinstance(v, (int, float, str, np.integer, np.floating)):
+            meta["scalars"][k] = v.item() if hasattr(v, "item") else v
+        elif isinstance(v, (list, tuple)):
+            meta["lists"][k] = [list(map(lambda x: x.item() if hasattr(x, "item") else x, e)) if isinstance(e, (list, tuple)) else e for e in v]
+    arrays["__meta__"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(path, **arrays)
+
+
+def load_model(path):
+    import json
+    z = np.load(path, allow_pickle=False)
+    m = Model()
+    meta = json.loads(bytes(z["__meta__"]).decode())
+    for k in z.files:
+        if k != "__meta__":
+            setattr(m, k, z[k])
+    for k, v in meta["scalars"].items():
+        setattr(m, k, v)
+    for k, v in meta["lists"].items():
+        setattr(m, k, [tuple(e) if isinstance(e, list) else e for e in v])
+    m.names = meta["names"]
+    return m

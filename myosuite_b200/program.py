@@ -1,0 +1,378 @@
+"""Kernel "program" builder: turns a compiled Model into the flat index lists the CUDA kernels execute.
+
+The kernels run one env per warp; every phase is a loop ``for (i = lane; i < n; i += 32)`` over a
+list built here, so that all data-dependent structure (tree levels, which dofs lie between two
+bodies, which tendon segments are compile-time constants, which wrap is inside/outside, which
+geom pairs survive the static collision filters) is resolved once per model on the host.
+
+Formulation notes (deliberately different from the oracle's MuJoCo-style formulation):
+  * only DYNAMIC bodies (those below a joint) are simulated; static bodies are folded into constants;
+  * spatial quantities are taken about the world origin, not the subtree COM;
+  * a tendon segment whose two end points ride on the same body has constant length and no moment:
+    it is summed into ``PT_const`` at build time;
+  * the tendon moment is assembled per structural non-zero (tendon, dof) from "terms"
+    (segment direction . (axis x (point - anchor))) for dofs lying between the segment's bodies.
+"""
+import numpy as np
+
+from . import mjcf
+from . import mjmath as mm
+
+# P_dims slots
+(PD_NBD, PD_NLEVEL, PD_NPT, PD_NSP, PD_NWE, PD_NTA, PD_NNZ, PD_NTERM, PD_NLIM, PD_NEQ, PD_NPAIR, PD_NGC, PD_MAXPATH,
+ PD_MAXCHAIN, PD_NSUB, PD_NROW, PD_NCOL, PD_NPIECE, PD_NWE_SPH_OUT, PD_NWE_SPH_IN, PD_NWE_CYL_OUT, PD_NWE_CYL_IN) = range(22)
+NPDIM = 24
+
+PB_STRIDE, PWE_STRIDE, PA_STRIDE, PG_STRIDE, PPAIR_STRIDE, PLIM_STRIDE, PEQ_STRIDE = 18, 16, 28, 16, 12, 12, 16
+
+# collision function ids
+CT_NONE, CT_CAP_CAP, CT_SPH_SPH, CT_SPH_CAP, CT_PLANE_SPH, CT_PLANE_CAP = range(6)
+
+
+def _kbimp(solref, solimp, timestep):
+    """Clamp solimp like MuJoCo's getsolparam and precompute K, B (refsafe) -> (K, B, solimp[5])."""
+    si = np.array(solimp, dtype=np.float64).copy()
+    si[0] = np.clip(si[0], 0.0001, 0.9999); si[1] = np.clip(si[1], 0.0001, 0.9999); si[2] = max(0.0, si[2])
+    si[3] = np.clip(si[3], 0.0001, 0.9999); si[4] = max(1.0, si[4])
+    if solref[0] <= 0:
+        raise mjcf.MJCFError("direct (negative) solref not supported")
+    tc = max(solref[0], 2 * timestep)
+    K = 1.0 / max(1e-15, si[1] ** 2 * tc ** 2 * solref[1] ** 2)
+    B = 2.0 / max(1e-15, si[1] * tc)
+    return K, B, si
+
+
+def build_program(m):
+    nb = m.nbody
+    dyn_ids = [b for b in range(1, nb) if m.body_weldid[b] != 0]
+    kin0 = mjcf.kinematics(m, m.qpos0)
+    # ---- levels (depth among dynamic bodies)
+    depth = {}
+    for b in dyn_ids:
+        p = m.body_parentid[b]
+        depth[b] = depth[p] + 1 if p in depth else 0
+    order = sorted(dyn_ids, key=lambda b: (depth[b], b))
+    idx = {b: k for k, b in enumerate(order)}          # model body id -> dyn index
+    nbd = len(order)
+    nlevel = (max(depth.values()) + 1) if order else 0
+    level_adr = [0] * (nlevel + 1)
+    for b in order:
+        level_adr[depth[b] + 1] += 1
+    level_adr = np.cumsum(level_adr).tolist()
+
+    def bidx(b):
+        return idx.get(b, -1)
+
+    PB_parent, PB_jadr, PB_jnum, PB_d = [], [], [], np.zeros((nbd, PB_STRIDE))
+    for k, b in enumerate(order):
+        p = m.body_parentid[b]
+        PB_parent.append(bidx(p))
+        PB_jadr.append(int(m.body_jntadr[b])); PB_jnum.append(int(m.body_jntnum[b]))
+        if p in idx:
+            pos, quat = m.body_pos[b], m.body_quat[b]
+        else:   # static parent: fold its world pose in
+            pos = kin0["xpos"][p] + kin0["xmat"][p] @ m.body_pos[b]
+            quat = mm.quat_normalize(mm.quat_mul(kin0["xquat"][p], m.body_quat[b]))
+        R = mm.quat2mat(m.body_iquat[b])
+        Il = R @ np.diag(m.body_inertia[b]) @ R.T
+        PB_d[k, 0:3], PB_d[k, 3:7], PB_d[k, 7:10], PB_d[k, 10] = pos, quat, m.body_ipos[b], m.body_mass[b]
+        PB_d[k, 11:17] = [Il[0, 0], Il[1, 1], Il[2, 2], Il[0, 1], Il[0, 2], Il[1, 2]]
+        for j in range(m.body_jntadr[b], m.body_jntadr[b] + m.body_jntnum[b]):
+            if m.jnt_type[j] == mjcf.JNT_FREE and (p in idx or m.body_jntnum[b] != 1):
+                raise mjcf.MJCFError("free joints must be alone on a child of a static body")
+    # ---- dofs
+    nv = m.nv
+    PD_body = [idx[int(b)] for b in m.dof_bodyid]
+    PD_lin = []
+    for d in range(nv):
+        j = m.dof_jntid[d]
+        t = m.jnt_type[j]
+        PD_lin.append(1 if (t == mjcf.JNT_SLIDE or (t == mjcf.JNT_FREE and d - m.jnt_dofadr[j] < 3)) else 0)
+    if np.any(m.jnt_stiffness != 0):
+        raise mjcf.MJCFError("joint stiffness not supported (all hot-path models use 0)")
+    PDOF_d = np.stack([m.dof_armature, m.dof_damping], axis=1) if nv else np.zeros((0, 2))
+    chains = {b: mjcf.dof_chain(m, b) for b in order}
+    PCH_adr, PCH = [0], []
+    for b in order:
+        for d in chains[b]:
+            j = m.dof_jntid[d]
+            flag = 1 if (m.jnt_type[j] == mjcf.JNT_FREE and d - m.jnt_dofadr[j] >= 4) else 0
+            PCH.append(d | (flag << 16))
+        PCH_adr.append(len(PCH))
+    maxchain = max([len(c) for c in chains.values()] + [0])
+    # subtrees among dynamic bodies (self included)
+    subtree = {b: [b] for b in order}
+    for b in reversed(order):
+        p = m.body_parentid[b]
+        if p in subtree:
+            subtree[p] = subtree[p] + subtree[b]
+    PSUB_adr, PSUB = [0], []
+    for b in order:
+        PSUB += [idx[x] for x in sorted(subtree[b])]
+        PSUB_adr.append(len(PSUB))
+    # mass-matrix entries (same order as qM: row i -> i, parent(i), ...)
+    PM_i, PM_j = [], []
+    for i in range(nv):
+        j = i
+        while j >= 0:
+            PM_i.append(i); PM_j.append(j)
+            j = m.dof_parentid[j]
+    assert len(PM_i) == m.nM
+    rows = [[] for _ in range(nv)]
+    for e, (i, j) in enumerate(zip(PM_i, PM_j)):
+        rows[i].append((j, e))
+        if i != j:
+            rows[j].append((i, e))
+    PROW_adr, PROW_col, PROW_idx = [0], [], []
+    for i in range(nv):
+        for c, e in sorted(rows[i]):
+            PROW_col.append(c); PROW_idx.append(e)
+        PROW_adr.append(len(PROW_col))
+
+    def moves(d, b):
+        """does dof d move model body b?"""
+        return d in chains.get(b, ())
+
+    # ---- tendon program
+    PPT_body, PPT_xyz, pt_cache = [], [], {}
+
+    def point_ref(body, local):
+        """(body model id, local pos) -> PT index; static bodies are folded to world coordinates."""
+        if body in idx:
+            key = (idx[body], tuple(np.round(local, 15)))
+            xyz = np.asarray(local, dtype=np.float64)
+            bi = idx[body]
+        else:
+            xyz = kin0["xpos"][body] + kin0["xmat"][body] @ np.asarray(local, dtype=np.float64)
+            key = (-1, tuple(np.round(xyz, 15)))
+            bi = -1
+        if key not in pt_cache:
+            pt_cache[key] = len(PPT_body)
+            PPT_body.append(bi); PPT_xyz.append(xyz)
+        return pt_cache[key]
+
+    def site_ref(s):
+        return point_ref(int(m.site_bodyid[s]), m.site_pos[s])
+
+    act_tendons = sorted(set(int(t) for t in m.actuator_trnid[:, 0])) if m.nu else []
+    if m.nu and not np.all(m.actuator_trntype == mjcf.TRN_TENDON):
+        raise mjcf.MJCFError("only tendon transmissions are supported")
+    ta_index = {t: k for k, t in enumerate(act_tendons)}
+    sp_list, we_list = [], []      # runtime pieces
+    T_const, T_pieces = [], []     # per active tendon
+    # term bookkeeping: terms[(ta, dof)] = list of (ukind, uidx, ptcode, sign)
+    terms = {}
+
+    def add_terms(ta, ba, bb, uref, pa_code, pb_code):
+        """straight piece from point a (on body ba) to point b (on bb) with unit-vector slot `uref`."""
+        ds = set(chains.get(ba, ())) ^ set(chains.get(bb, ()))
+        for d in ds:
+            if moves(d, bb):
+                terms.setdefault((ta, d), []).append((uref, pb_code, +1))
+            else:
+                terms.setdefault((ta, d), []).append((uref, pa_code, -1))
+
+    for t in act_tendons:
+        ta = ta_index[t]
+        adr, num = int(m.tendon_adr[t]), int(m.tendon_num[t])
+        const, pieces = 0.0, []
+        j = 0
+        while j < num - 1:
+            t1 = m.wrap_type[adr + j + 1]
+            s0 = int(m.wrap_objid[adr + j])
+            b0 = int(m.site_bodyid[s0])
+            if t1 == mjcf.WRAP_SITE:
+                s1 = int(m.wrap_objid[adr + j + 1])
+                b1 = int(m.site_bodyid[s1])
+                if _same_rigid(m, b0, b1):
+                    const += float(np.linalg.norm(_site_world(m, kin0, s1) - _site_world(m, kin0, s0)))
+                else:
+                    pa, pb = site_ref(s0), site_ref(s1)
+                    k = len(sp_list)
+                    sp_list.append((pa, pb))
+                    pieces.append(("S", k))
+                    add_terms(ta, b0, b1, ("S", k), pa, pb)
+                j += 1
+            else:
+                g = int(m.wrap_objid[adr + j + 1]); s1 = int(m.wrap_objid[adr + j + 2]); ss = int(m.wrap_prm[adr + j + 1])
+                b1, bg = int(m.site_bodyid[s1]), int(m.geom_bodyid[g])
+                pa, pb = site_ref(s0), site_ref(s1)
+                typ = 0 if m.wrap_type[adr + j + 1] == mjcf.WRAP_SPHERE else 1
+                inside = 0
+                side = -1
+                s_local = np.zeros(3)
+                if ss >= 0:
+                    if not _same_rigid(m, int(m.site_bodyid[ss]), bg):
+                        raise mjcf.MJCFError("side site must ride on the wrap geom's body")
+                    sw, gw = _site_world(m, kin0, ss), kin0["xpos"][bg] + kin0["xmat"][bg] @ m.geom_pos[g]
+                    inside = int(np.linalg.norm(sw - gw) < m.geom_size[g][0])
+                    side = site_ref(ss)
+                    s_local = (kin0["xmat"][bg] @ mm.quat2mat(m.geom_quat[g])).T @ (sw - gw)
+                if bg in idx:
+                    gpos, gmat, gb = m.geom_pos[g], mm.quat2mat(m.geom_quat[g]), idx[bg]
+                else:
+                    gpos = kin0["xpos"][bg] + kin0["xmat"][bg] @ m.geom_pos[g]
+                    gmat = kin0["xmat"][bg] @ mm.quat2mat(m.geom_quat[g]); gb = -1
+                k = len(we_list)
+                we_list.append(dict(pa=pa, pb=pb, gb=gb, typ=typ, side=side, inside=inside, gpos=gpos, gmat=gmat,
+                                    r=float(m.geom_size[g][0]), ta=ta, b0=b0, b1=b1, bg=bg, s_local=s_local))
+                pieces.append(("W", k))
+                j += 2
+        T_const.append(const); T_pieces.append(pieces)
+    # sort wrap elements by (type, inside) so that a warp round is branch-uniform
+    we_order = sorted(range(len(we_list)), key=lambda k: (we_list[k]["typ"], we_list[k]["inside"], k))
+    we_new = {old: new for new, old in enumerate(we_order)}
+    we_sorted = [we_list[k] for k in we_order]
+    nsp, nwe = len(sp_list), len(we_sorted)
+    for new, w in enumerate(we_sorted):
+        # piece A: pa (b0) -> w0 (bg), unit slot nsp+2*new ; piece B: w1 (bg) -> pb (b1), unit slot nsp+2*new+1
+        add_terms(w["ta"], w["b0"], w["bg"], ("W", 2 * new), w["pa"], -(1 + 2 * new))
+        add_terms(w["ta"], w["bg"], w["b1"], ("W", 2 * new + 1), -(1 + 2 * new + 1), w["pb"])
+    counts = [0, 0, 0, 0]
+    for w in we_sorted:
+        counts[2 * w["typ"] + w["inside"]] += 1
+    PT_piece_adr, PT_piece = [0], []
+    for pieces in T_pieces:
+        for kind, k in pieces:
+            PT_piece.append(k if kind == "S" else nsp + we_new[k])
+        PT_piece_adr.append(len(PT_piece))
+    # non-zeros sorted by (tendon, dof)
+    keys = sorted(terms.keys())
+    PNZ_dof, PNZ_tendon, PNZ_term_adr, PTERM = [], [], [0], []
+    PT_nz_adr = [0] * (len(act_tendons) + 1)
+    for (ta, d) in keys:
+        PNZ_dof.append(d); PNZ_tendon.append(ta); PT_nz_adr[ta + 1] += 1
+        for (ukind, uk), ptcode, sign in terms[(ta, d)]:
+            PTERM += [uk if ukind == "S" else nsp + uk, ptcode, sign]
+        PNZ_term_adr.append(len(PTERM) // 3)
+    PT_nz_adr = np.cumsum(PT_nz_adr).tolist()
+    cols = [[] for _ in range(nv)]
+    for k, d in enumerate(PNZ_dof):
+        cols[d].append(k)
+    PCOL_adr, PCOL = [0], []
+    for d in range(nv):
+        PCOL += cols[d]; PCOL_adr.append(len(PCOL))
+    PWE = np.array([[w["pa"], w["pb"], w["gb"], w["typ"], w["side"], w["inside"]] for w in we_sorted], dtype=np.int32).reshape(-1, 6)
+    PWE_d = np.zeros((nwe, PWE_STRIDE))
+    for k, w in enumerate(we_sorted):
+        PWE_d[k, 0:3], PWE_d[k, 3:12], PWE_d[k, 12] = w["gpos"], np.asarray(w["gmat"]).ravel(), w["r"]
+        PWE_d[k, 13:16] = w["s_local"]
+    # actuators
+    PA_tendon = [ta_index[int(t)] for t in m.actuator_trnid[:, 0]] if m.nu else []
+    PA_d = np.zeros((m.nu, PA_STRIDE))
+    for i in range(m.nu):
+        if not (m.actuator_dyntype[i] == mjcf.DYN_MUSCLE and m.actuator_gaintype[i] == mjcf.GAIN_MUSCLE
+                and m.actuator_biastype[i] == mjcf.BIAS_MUSCLE):
+            raise mjcf.MJCFError("only muscle actuators are supported on the device path")
+        PA_d[i, 0:3], PA_d[i, 3:12], PA_d[i, 12:21] = m.actuator_dynprm[i, :3], m.actuator_gainprm[i, :9], m.actuator_biasprm[i, :9]
+        PA_d[i, 21:23], PA_d[i, 23:25] = m.actuator_lengthrange[i], m.actuator_ctrlrange[i]
+        PA_d[i, 25], PA_d[i, 26] = float(m.actuator_ctrllimited[i]), m.actuator_gear[i, 0]
+
+    # ---- collision geoms + pairs
+    h = m.opt_timestep
+    gmap, PG_body, PG_type, PG_d = {}, [], [], []
+
+    def geom_ref(g):
+        if g not in gmap:
+            b = int(m.geom_bodyid[g])
+            if b in idx:
+                pos, mat, bi = m.geom_pos[g], mm.quat2mat(m.geom_quat[g]), idx[b]
+            else:
+                pos = kin0["xpos"][b] + kin0["xmat"][b] @ m.geom_pos[g]
+                mat = kin0["xmat"][b] @ mm.quat2mat(m.geom_quat[g]); bi = -1
+            gmap[g] = len(PG_body)
+            PG_body.append(bi); PG_type.append(int(m.geom_type[g]))
+            row = np.zeros(PG_STRIDE); row[0:3], row[3:12], row[12:15] = pos, np.asarray(mat).ravel(), m.geom_size[g]
+            PG_d.append(row)
+        return gmap[g]
+
+    ctype_of = {(mjcf.GEOM_CAPSULE, mjcf.GEOM_CAPSULE): CT_CAP_CAP, (mjcf.GEOM_SPHERE, mjcf.GEOM_SPHERE): CT_SPH_SPH,
+                (mjcf.GEOM_SPHERE, mjcf.GEOM_CAPSULE): CT_SPH_CAP, (mjcf.GEOM_PLANE, mjcf.GEOM_SPHERE): CT_PLANE_SPH,
+                (mjcf.GEOM_PLANE, mjcf.GEOM_CAPSULE): CT_PLANE_CAP}
+    PPAIR, PPAIR_d, PPATH = [], [], []
+    maxpath = 0
+    pair_model_index = []
+    for p in range(m.npair):
+        g1, g2 = int(m.pair_geom1[p]), int(m.pair_geom2[p])
+        ct = ctype_of.get((int(m.geom_type[g1]), int(m.geom_type[g2])), CT_NONE)
+        if ct == CT_NONE:
+            continue     # unsupported narrow-phase (ellipsoid/mesh/hfield): listed in m.pair_unsupported
+        dim = int(m.pair_dim[p])
+        if dim not in (1, 3):
+            raise mjcf.MJCFError("condim %d not supported" % dim)
+        b1, b2 = int(m.geom_bodyid[g1]), int(m.geom_bodyid[g2])
+        ds = sorted(set(chains.get(b1, ())) ^ set(chains.get(b2, ())))
+        path_adr = len(PPATH)
+        for d in ds:
+            PPATH.append(d * 2 + (1 if moves(d, b2) else 0))
+        maxpath = max(maxpath, len(ds))
+        K, B, si = _kbimp(m.pair_solref[p], m.pair_solimp[p], h)
+        PPAIR.append([geom_ref(g1), geom_ref(g2), dim, path_adr, len(ds), ct])
+        tran = m.body_invweight0[b1, 0] + m.body_invweight0[b2, 0]
+        PPAIR_d.append([m.pair_margin[p], m.pair_gap[p], m.pair_friction[p, 0], m.pair_friction[p, 1], tran, K, B, *si])
+        pair_model_index.append(p)
+    # ---- joint limits
+    PLIM, PLIM_d = [], []
+    for j in range(m.njnt):
+        if m.jnt_limited[j] and m.jnt_type[j] in (mjcf.JNT_HINGE, mjcf.JNT_SLIDE):
+            K, B, si = _kbimp(m.jnt_solref[j], m.jnt_solimp[j], h)
+            d = int(m.jnt_dofadr[j])
+            PLIM.append([d, int(m.jnt_qposadr[j])])
+            PLIM_d.append([m.jnt_range[j, 0], m.jnt_range[j, 1], m.jnt_margin[j], m.dof_invweight0[d], K, B, *si, 0.0])
+    # ---- joint equalities
+    PEQ, PEQ_d = [], []
+    for e in range(m.neq):
+        if not m.eq_active0[e]:
+            continue
+        j1, j2 = int(m.eq_obj1id[e]), int(m.eq_obj2id[e])
+        K, B, si = _kbimp(m.eq_solref[e], m.eq_solimp[e], h)
+        q1, d1 = int(m.jnt_qposadr[j1]), int(m.jnt_dofadr[j1])
+        q2, d2 = (int(m.jnt_qposadr[j2]), int(m.jnt_dofadr[j2])) if j2 >= 0 else (-1, -1)
+        iw = m.dof_invweight0[d1] + (m.dof_invweight0[d2] if j2 >= 0 else 0.0)
+        PEQ.append([q1, d1, q2, d2])
+        PEQ_d.append([*m.eq_data[e], m.qpos0[q1], m.qpos0[q2] if j2 >= 0 else 0.0, iw, K, B, *si, 0.0])
+
+    dims = np.zeros(NPDIM, np.int32)
+    dims[PD_NBD], dims[PD_NLEVEL], dims[PD_NPT], dims[PD_NSP], dims[PD_NWE] = nbd, nlevel, len(PPT_body), nsp, nwe
+    dims[PD_NTA], dims[PD_NNZ], dims[PD_NTERM] = len(act_tendons), len(PNZ_dof), len(PTERM) // 3
+    dims[PD_NLIM], dims[PD_NEQ], dims[PD_NPAIR], dims[PD_NGC] = len(PLIM), len(PEQ), len(PPAIR), len(PG_body)
+    dims[PD_MAXPATH], dims[PD_MAXCHAIN], dims[PD_NSUB], dims[PD_NROW], dims[PD_NCOL] = maxpath, maxchain, len(PSUB), len(PROW_col), len(PCOL)
+    dims[PD_NPIECE] = len(PT_piece)
+    dims[PD_NWE_SPH_OUT], dims[PD_NWE_SPH_IN], dims[PD_NWE_CYL_OUT], dims[PD_NWE_CYL_IN] = counts
+
+    def ia(x, shape=None):
+        a = np.asarray(x, dtype=np.int32)
+        return a.reshape(shape) if shape else a
+
+    prog = {
+        "P_dims": dims,
+        "PB_level_adr": ia(level_adr), "PB_parent": ia(PB_parent), "PB_jadr": ia(PB_jadr), "PB_jnum": ia(PB_jnum),
+        "PB_model_id": ia(order), "PB_d": PB_d,
+        "PD_body": ia(PD_body), "PD_lin": ia(PD_lin), "PDOF_d": PDOF_d,
+        "PCH_adr": ia(PCH_adr), "PCH": ia(PCH), "PSUB_adr": ia(PSUB_adr), "PSUB": ia(PSUB),
+        "PM_i": ia(PM_i), "PM_j": ia(PM_j), "PROW_adr": ia(PROW_adr), "PROW_col": ia(PROW_col), "PROW_idx": ia(PROW_idx),
+        "PPT_body": ia(PPT_body), "PPT_xyz": np.array(PPT_xyz, dtype=np.float64).reshape(-1, 3),
+        "PSP": ia(sp_list).reshape(-1, 2), "PWE": PWE, "PWE_d": PWE_d,
+        "PT_const": np.array(T_const, dtype=np.float64), "PT_piece_adr": ia(PT_piece_adr), "PT_piece": ia(PT_piece),
+        "PT_nz_adr": ia(PT_nz_adr), "PNZ_dof": ia(PNZ_dof), "PNZ_tendon": ia(PNZ_tendon), "PNZ_term_adr": ia(PNZ_term_adr),
+        "PTERM": ia(PTERM), "PCOL_adr": ia(PCOL_adr), "PCOL": ia(PCOL),
+        "PA_tendon": ia(PA_tendon), "PA_d": PA_d,
+        "PG_body": ia(PG_body), "PG_type": ia(PG_type), "PG_d": np.array(PG_d, dtype=np.float64).reshape(-1, PG_STRIDE),
+        "PPAIR": ia(PPAIR).reshape(-1, 6), "PPAIR_d": np.array(PPAIR_d, dtype=np.float64).reshape(-1, PPAIR_STRIDE),
+        "PPATH": ia(PPATH),
+        "PLIM": ia(PLIM).reshape(-1, 2), "PLIM_d": np.array(PLIM_d, dtype=np.float64).reshape(-1, PLIM_STRIDE),
+        "PEQ": ia(PEQ).reshape(-1, 4), "PEQ_d": np.array(PEQ_d, dtype=np.float64).reshape(-1, PEQ_STRIDE),
+    }
+    info = dict(dyn_body_ids=order, act_tendons=act_tendons, pair_model_index=pair_model_index,
+                geom_model_ids={v: k for k, v in gmap.items()})
+    return prog, info
+
+
+def _same_rigid(m, b0, b1):
+    """True if the two bodies are rigidly attached (same weld body)."""
+    return m.body_weldid[b0] == m.body_weldid[b1]
+
+
+def _site_world(m, kin, s):
+    b = m.site_bodyid[s]
+    return kin["xpos"][b] + kin["xmat"][b] @ m.site_pos[s]

@@ -1,0 +1,218 @@
+"""Batched env mirror of the reference's BaseV0 / PoseEnvV0 stack on top of the C-ABI library.
+
+Reference interface mirrored (same names, argument meaning, return layout):
+  * ``gym.make(id)`` registry ids + kwargs      /root/reference/myosuite/envs/myo/myobase/__init__.py:124-138,402-415
+  * ``env.reset() -> (obs, info)``               /root/reference/myosuite/envs/env_base.py:647-654
+  * ``env.step(a) -> (obs, reward, terminated, truncated, info)``   envs/env_base.py:403-407, envs/myo/base_v0.py:82-118
+  * muscle-condition variants myoFati*/myoSarc*/myoReaf*           myobase/__init__.py:17-49, base_v0.py:60-79
+All per-env state lives in torch CUDA tensors owned here and bound to the library by pointer.
+"""
+import json
+import os
+
+import numpy as np
+
+from . import abi, assets, blob, program
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REG = None
+
+
+def registry():
+    global _REG
+    if _REG is None:
+        _REG = json.load(open(os.path.join(_HERE, "assets", "registry.json")))
+    return _REG
+
+
+def env_spec(env_id):
+    """id -> (max_episode_steps, merged kwargs) including the Sarc/Fati/Reaf variants."""
+    reg = registry()
+    if env_id in reg["envs"]:
+        e = reg["envs"][env_id]
+        return e["max_episode_steps"], dict(e["kwargs"]), e["entry_point"]
+    if env_id in reg["variants"]:
+        v = reg["variants"][env_id]
+        steps, kw, ep = env_spec(v["base"])
+        kw.update(v["variants"])
+        return steps, kw, ep
+    raise KeyError("unknown env id %r (known: %s)" % (env_id, sorted(reg["envs"]) + sorted(reg["variants"])))
+
+
+def registered_ids():
+    reg = registry()
+    return sorted(reg["envs"]) + sorted(reg["variants"])
+
+
+_MODEL_OF_XML = {v[0]: k for k, v in assets.MODEL_XML.items()}
+
+
+class MyoVecEnv:
+    """n independent envs of one registry id, resident on one GPU.  Tensors in, tensors out."""
+
+    def __init__(self, env_id, num_envs, device=0, seed=0, env_offset=0, auto_reset=True, taps=False, model=None, **overrides):
+        import torch
+        self.torch = torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("MyoVecEnv needs a CUDA device: the physics has no CPU fallback (the CPU oracle under oracle/ is test-only)")
+        self.env_id, self.num_envs, self.seed_value, self.env_offset = env_id, int(num_envs), int(seed), int(env_offset)
+        self.max_episode_steps, kw, entry = env_spec(env_id)
+        kw.update(overrides)
+        self.kwargs = kw
+        if not entry.endswith("pose_v0:PoseEnvV0"):
+            raise NotImplementedError("device task for %s (%s) is not built yet; pose tasks are" % (env_id, entry))
+        self.mj_model = m = model if model is not None else assets.load(_MODEL_OF_XML[kw["model_path"]])
+        self.muscle_condition = kw.get("muscle_condition", "")
+        if self.muscle_condition == "sarcopenia":       # base_v0.py:62-67: gainprm[:,2] *= 0.5 (biasprm untouched)
+            import copy
+            self.mj_model = m = copy.deepcopy(m)
+            m.actuator_gainprm[:, 2] *= 0.5
+        self.frame_skip = int(kw.get("frame_skip", 10))
+        self.dt = m.opt_timestep * self.frame_skip
+        self.n_frames = int(self.dt / m.opt_timestep)      # robot.py:901
+        prog, self.prog_info = program.build_program(m)
+        self.I, self.D = blob.pack(m, prog)
+        self.dev_model = abi.DeviceModel(self.I, self.D)
+        cfg = abi.MyoTaskCfg()
+        cfg.task = abi.TASK_POSE
+        cfg.frame_skip = self.n_frames
+        cfg.max_episode_steps = int(self.max_episode_steps or 0)
+        cfg.normalize_act = int(bool(kw.get("normalize_act", True)))
+        cfg.muscle_condition = abi.COND_FATIGUE if self.muscle_condition == "fatigue" else abi.COND_NONE
+        cfg.auto_reset = int(bool(auto_reset))
+        cfg.reset_random = int(kw.get("reset_type", "init") == "random")
+        cfg.pose_thd = float(kw.get("pose_thd", 0.35))
+        w = kw.get("weighted_reward_keys", {"pose": 1.0, "bonus": 4.0, "act_reg": 1.0, "penalty": 50})
+        cfg.weights[0], cfg.weights[1], cfg.weights[2], cfg.weights[3] = w["pose"], w["bonus"], w["act_reg"], w["penalty"]
+        cfg.solver_tolerance = float(kw.get("solver_tolerance", 0.0))
+        cfg.maxcon = int(kw.get("maxcon", 0))
+        self.cfg = cfg
+        self.device_index = int(device)
+        self.device = torch.device("cuda", self.device_index)
+        self.batch = abi.Batch(self.dev_model, self.device_index, self.num_envs, cfg)
+        self.dims = self.dev_model.dims(cfg)
+        n, dv = self.num_envs, self.device
+        f64, f32 = torch.float64, torch.float32
+        z = lambda *s, dtype=f64: torch.zeros(*s, dtype=dtype, device=dv)
+        self.obs_dim, self.act_dim = self.batch.obs_dim, m.nu
+        t = dict(action=z(n, m.nu, dtype=f32), qpos=z(n, m.nq), qvel=z(n, m.nv), act=z(n, max(m.na, 1)), qacc_warmstart=z(n, m.nv),
+                 time=z(n), target=z(n, m.nq), step_count=z(n, dtype=torch.int32), episode_count=z(n, dtype=torch.int64),
+                 obs=z(n, self.obs_dim, dtype=f32), reward=z(n, dtype=f32), done=z(n, dtype=torch.uint8), truncated=z(n, dtype=torch.uint8),
+                 ep_return=z(n, dtype=f32), last_return=z(n, dtype=f32))
+        t["qpos"][:] = torch.as_tensor(m.qpos0, device=dv)
+        # target ranges per qpos (pose_v0.py:60-70); "fixed" targets collapse the range
+        tr = np.zeros((m.nq, 2))
+        if kw.get("target_jnt_range"):
+            for jn, (lo, hi) in kw["target_jnt_range"].items():
+                qa = m.jnt_qposadr[m.name2id("joint", jn)]
+                tr[qa] = (lo, hi)
+        elif kw.get("target_jnt_value") is not None:
+            v = np.asarray(kw["target_jnt_value"], dtype=np.float64)
+            tr[:, 0] = tr[:, 1] = v
+        t["target_range"] = torch.as_tensor(tr, device=dv).contiguous()
+        t["init_qpos"] = torch.as_tensor(np.asarray(m.qpos0, dtype=np.float64), device=dv).contiguous()
+        if cfg.muscle_condition == abi.COND_FATIGUE:
+            t["fatigue"] = z(n, 3, m.nu)
+            t["fatigue"][:, 1, :] = 1.0
+        if taps:
+            t.update(tap_qacc=z(n, m.nv), tap_actuator_force=z(n, m.nu), tap_ten_length=z(n, m.nu), tap_qfrc_smooth=z(n, m.nv),
+                     tap_ncon=z(n, 4, dtype=torch.int32), tap_contact_pair=z(n, max(self.dims.maxcon, 1), dtype=torch.int32),
+                     tap_contact_dist=z(n, max(self.dims.maxcon, 1)), tap_moment=z(n, max(self.dims.reserved[0], 1)), tap_qM=z(n, m.nM))
+        self.t = t
+        self.batch.bind(**t)
+        if self.muscle_condition == "reafferentation":   # base_v0.py:78-79,104-108
+            self.EPLpos, self.EIPpos = m.name2id("actuator", "EPL"), m.name2id("actuator", "EIP")
+        self._h_action = None
+
+    # ---------------------------------------------------------------- gym-style API (batched)
+    @property
+    def horizon(self):
+        return self.max_episode_steps
+
+    def reset(self, seed=None, mask=None):
+        if seed is not None:
+            self.seed_value = int(seed)
+        self.batch.reset(mask=mask, seed=self.seed_value, env_offset=self.env_offset, stream=self._stream())
+        return self.t["obs"], {}
+
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def step(self, action):
+        """action: float32 CUDA tensor [num_envs, nu] (values as the reference's action_space: [-1, 1])."""
+        a = self.t["action"]
+        if action.data_ptr() != a.data_ptr():
+            a.copy_(action, non_blocking=True)
+        if self.muscle_condition == "reafferentation":
+            # applied on the remapped ctrl in the reference; equivalent pre-sigmoid swap is not: do it after remap on host side
+            raise NotImplementedError("reafferentation variant: TODO device-side ctrl swap")
+        self.batch.step(stream=self._stream())
+        t = self.t
+        return t["obs"], t["reward"], t["done"], t["truncated"], {"last_return": t["last_return"], "time": t["time"]}
+
+    def step_host(self, action_cpu_pinned):
+        """End-to-end call with HOST buffers: H2D action copy, step, D2H of reward/done (the e2e bench path)."""
+        torch = self.torch
+        self.t["action"].copy_(action_cpu_pinned, non_blocking=True)
+        self.batch.step(stream=self._stream())
+        if self._h_action is None:
+            self._h_reward = torch.empty(self.num_envs, dtype=torch.float32, pin_memory=True)
+            self._h_done = torch.empty(self.num_envs, dtype=torch.uint8, pin_memory=True)
+            self._h_obs = torch.empty(self.num_envs, self.obs_dim, dtype=torch.float32, pin_memory=True)
+            self._h_action = True
+        self._h_obs.copy_(self.t["obs"], non_blocking=True)
+        self._h_reward.copy_(self.t["reward"], non_blocking=True)
+        self._h_done.copy_(self.t["done"], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._h_obs, self._h_reward, self._h_done
+
+    # ---------------------------------------------------------------- state access (get_env_state-like) and parity taps
+    def set_state(self, qpos=None, qvel=None, act=None, target=None):
+        torch = self.torch
+        for name, v in (("qpos", qpos), ("qvel", qvel), ("act", act), ("target", target)):
+            if v is not None:
+                self.t[name][:, : np.shape(v)[-1]] = torch.as_tensor(np.asarray(v), dtype=torch.float64, device=self.device)
+        self.t["qacc_warmstart"].zero_()
+
+    def forward_debug(self, ctrl, n_substeps=0):
+        c = self.torch.as_tensor(np.asarray(ctrl), dtype=self.torch.float64, device=self.device).contiguous()
+        self._dbg_ctrl = c
+        self.batch.forward_debug(c, n_substeps, stream=self._stream())
+
+
+class MyoEnv:
+    """Single-env façade with the reference's gym call shapes (numpy in / numpy out), n_env = 1 on the GPU."""
+
+    def __init__(self, env_id, seed=None, device=0, **kwargs):
+        self.vec = MyoVecEnv(env_id, 1, device=device, seed=0 if seed is None else seed, auto_reset=False, **kwargs)
+        self.unwrapped = self
+        self.mj_model = self.vec.mj_model
+        self.dt, self.horizon = self.vec.dt, self.vec.max_episode_steps
+        self.input_seed = seed
+        self._elapsed = 0
+
+    def seed(self, seed=None):
+        self.input_seed = seed
+        self.vec.seed_value = 0 if seed is None else int(seed)
+        return [seed]
+
+    def get_input_seed(self):
+        return self.input_seed
+
+    def reset(self, seed=None, **kwargs):
+        obs, info = self.vec.reset(seed=seed)
+        self._elapsed = 0
+        return obs[0].cpu().numpy(), info
+
+    def step(self, a):
+        torch = self.vec.torch
+        act = torch.as_tensor(np.asarray(a, dtype=np.float32)[None], device=self.vec.device)
+        obs, rew, done, trunc, info = self.vec.step(act)
+        return obs[0].cpu().numpy(), float(rew[0].item()), bool(done[0].item()), bool(trunc[0].item()), {"time": float(info["time"][0].item())}
+
+
+def make(env_id, num_envs=None, **kwargs):
+    """``make(id)`` -> single env (reference call shape); ``make(id, num_envs=N)`` -> batched MyoVecEnv."""
+    if num_envs is None:
+        return MyoEnv(env_id, **kwargs)
+    return MyoVecEnv(env_id, num_envs, **kwargs)
