@@ -58,6 +58,7 @@ typedef struct {
   int32_t auto_reset;        /* 1: envs that finish are reset inside the step kernel */
   int32_t reset_random;      /* pose: 1 = qpos ~ U(jnt_range) (reset_type="random"), 0 = init_qpos */
   int32_t maxcon;            /* 0 = library default */
+  int32_t reaf_dst, reaf_src;/* reafferentation (base_v0.py:104-108): ctrl[dst] = ctrl[src]; ctrl[src] = 0 ; dst == src = off */
   double pose_thd;           /* pose_v0.py:43 */
   double weights[4];         /* pose, bonus, act_reg, penalty (pose_v0.py:18-23) */
   double solver_tolerance;   /* scaled-gradient stop of the Newton solver; 0 = library default (1e-10) */
@@ -121,6 +122,10 @@ int myo_batch_reset(myo_batch* b, const uint8_t* mask_dev_or_null, uint64_t seed
  * reward, done, TimeLimit, optional auto-reset.  Asynchronous on `stream`.
  * Replaces BaseV0.step (base_v0.py:82-118) for the whole batch. */
 int myo_batch_step(myo_batch* b, void* stream);
+
+/* obs / reward / done of the CURRENT state without advancing it.
+ * Replaces env.forward() (envs/env_base.py:393-432). */
+int myo_batch_observe(myo_batch* b, void* stream);
 
 /* Parity tap: ONE forward pass (mj_forward) on the bound qpos/qvel/act with ctrl := action taken
  * verbatim (no sigmoid), writing the tap_* buffers; state is not advanced.  If n_substeps > 0 the

@@ -25,7 +25,7 @@ class MyoDims(ctypes.Structure):
 
 class MyoTaskCfg(ctypes.Structure):
     _fields_ = [(n, c_i32) for n in ("task", "frame_skip", "max_episode_steps", "normalize_act", "muscle_condition",
-                                      "auto_reset", "reset_random", "maxcon")] + \
+                                      "auto_reset", "reset_random", "maxcon", "reaf_dst", "reaf_src")] + \
                [("pose_thd", c_f64), ("weights", c_f64 * 4), ("solver_tolerance", c_f64), ("reserved", c_f64 * 6)]
 
 
@@ -41,7 +41,7 @@ class MyoBuffers(ctypes.Structure):
 
 EXPORTS = ["myo_last_error", "myo_version", "myo_model_from_blob", "myo_model_dims", "myo_model_destroy", "myo_batch_create",
            "myo_batch_bind", "myo_batch_destroy", "myo_batch_obs_dim", "myo_batch_reset", "myo_batch_step",
-           "myo_batch_forward_debug", "myo_batch_launch_count"]
+           "myo_batch_forward_debug", "myo_batch_launch_count", "myo_batch_observe"]
 
 
 class MyoError(RuntimeError):
@@ -71,6 +71,7 @@ def lib():
         L.myo_batch_obs_dim.argtypes = [c_vp]
         L.myo_batch_reset.argtypes = [c_vp, c_vp, c_u64, c_i64, c_vp]
         L.myo_batch_step.argtypes = [c_vp, c_vp]
+        L.myo_batch_observe.argtypes = [c_vp, c_vp]
         L.myo_batch_forward_debug.argtypes = [c_vp, c_vp, ctypes.c_int, c_vp]
         L.myo_batch_launch_count.argtypes = [c_vp]
         L.myo_batch_launch_count.restype = c_i64
@@ -137,6 +138,9 @@ class Batch:
 
     def step(self, stream=None):
         _check(lib().myo_batch_step(self.handle, stream))
+
+    def observe(self, stream=None):
+        _check(lib().myo_batch_observe(self.handle, stream))
 
     def forward_debug(self, ctrl, n_substeps=0, stream=None):
         _check(lib().myo_batch_forward_debug(self.handle, ctrl.data_ptr(), n_substeps, stream))

@@ -90,6 +90,13 @@ __device__ void write_obs_pose(const DevModel& m, Warp& w, const StepArgs& a, in
   *dist_out = sqrt(warp_sum(d2)); double am = sqrt(warp_sum(a2)); *actmag_out = m.na ? am/m.na : am;
 }
 
+// reward / done of the current state (pose_v0.py:113-140); lane 0 writes
+__device__ void pose_reward_done(const DevModel& m, Warp& w, const StepArgs& a, int env, double* rw_out, bool* done_out) {
+  double dist, am; write_obs_pose(m, w, a, env, &dist, &am);
+  const double far_th = 4*3.14159265358979323846/2; double thd = a.cfg.pose_thd;
+  *rw_out = a.cfg.weights[0]*(-dist) + a.cfg.weights[1]*((dist < thd ? 1.0 : 0.0)+(dist < 1.5*thd ? 1.0 : 0.0)) + a.cfg.weights[2]*(-am) + a.cfg.weights[3]*(dist > far_th ? -1.0 : 0.0);
+  *done_out = dist > far_th; }
+
 // ------------------------------------------------------------------ the kernel
 extern "C" __global__ void __launch_bounds__(256) myo_env_kernel(DevModel m, StepArgs a) {
   extern __shared__ double smem[];
@@ -111,6 +118,9 @@ extern "C" __global__ void __launch_bounds__(256) myo_env_kernel(DevModel m, Ste
       if (!a.reset_mask || a.reset_mask[env]) { env_reset(m, w, a, env);
         if (a.cfg.task == MYO_TASK_POSE) { double d, am; write_obs_pose(m, w, a, env, &d, &am); }
         if (w.lane == 0) { if (b.done) b.done[env] = 0; if (b.truncated) b.truncated[env] = 0; if (b.reward) b.reward[env] = 0; } }
+    } else if (a.mode == 3) {   // observe: obs/reward/done of the current state, nothing advanced (env.forward(), env_base.py:393-432)
+      if (a.cfg.task == MYO_TASK_POSE) { double rw; bool done; pose_reward_done(m, w, a, env, &rw, &done);
+        if (w.lane == 0) { if (b.reward) b.reward[env] = (float)rw; if (b.done) b.done[env] = done; } }
     } else if (a.mode == 1) {
       for (int i = w.lane; i < m.nu; i += 32) w.ctrl[i] = a.dbg_ctrl[(size_t)env*m.nu+i];
       __syncwarp();
@@ -120,7 +130,9 @@ extern "C" __global__ void __launch_bounds__(256) myo_env_kernel(DevModel m, Ste
     } else {
       // ---- action -> ctrl  (base_v0.py:83-96); fatigue (fatigue.py:38-76)
       for (int i = w.lane; i < m.nu; i += 32) { double c = (double)b.action[(size_t)env*m.nu+i];
+        if (a.cfg.reaf_dst != a.cfg.reaf_src && i == a.cfg.reaf_dst) c = (double)b.action[(size_t)env*m.nu+a.cfg.reaf_src];
         if (a.cfg.normalize_act) c = 1.0/(1.0+exp(-5.0*(c-0.5)));
+        if (a.cfg.reaf_dst != a.cfg.reaf_src && i == a.cfg.reaf_src) c = 0.0;
         if (a.cfg.muscle_condition == MYO_COND_FATIGUE && b.fatigue) { double* F = b.fatigue + (size_t)env*3*m.nu; const double* PA = DSEC(m, PA_d) + i*PA_STRIDE;
           double MA = F[i], MR = F[m.nu+i], MF = F[2*m.nu+i], TL = c, fdt = a.dt, tauact = PA[0], taudeact = PA[1];
           const double r = 10*15, Fc = 0.00912, Rc = 0.1*0.00094;
@@ -137,10 +149,8 @@ extern "C" __global__ void __launch_bounds__(256) myo_env_kernel(DevModel m, Ste
       __syncwarp();
       for (int s = 0; s < a.cfg.frame_skip; s++) substep(m, w, a, env, s == a.cfg.frame_skip-1, true);
       // ---- obs / reward / done / TimeLimit / auto-reset
-      if (a.cfg.task == MYO_TASK_POSE) { double dist, am; write_obs_pose(m, w, a, env, &dist, &am);
-        const double far_th = 4*3.14159265358979323846/2; double thd = a.cfg.pose_thd;
-        double rw = a.cfg.weights[0]*(-dist) + a.cfg.weights[1]*((dist < thd ? 1.0 : 0.0)+(dist < 1.5*thd ? 1.0 : 0.0)) + a.cfg.weights[2]*(-am) + a.cfg.weights[3]*(dist > far_th ? -1.0 : 0.0);
-        bool done = dist > far_th; int sc = b.step_count ? b.step_count[env]+1 : 0; bool trunc = a.cfg.max_episode_steps > 0 && sc >= a.cfg.max_episode_steps;
+      if (a.cfg.task == MYO_TASK_POSE) { double rw; bool done; pose_reward_done(m, w, a, env, &rw, &done);
+        int sc = b.step_count ? b.step_count[env]+1 : 0; bool trunc = a.cfg.max_episode_steps > 0 && sc >= a.cfg.max_episode_steps;
         __syncwarp();
         if (w.lane == 0) { if (b.reward) b.reward[env] = (float)rw; if (b.done) b.done[env] = done; if (b.truncated) b.truncated[env] = trunc && !done;
           if (b.step_count) b.step_count[env] = sc; if (b.time) b.time[env] += a.cfg.frame_skip*m.timestep;
@@ -263,6 +273,10 @@ extern "C" int myo_batch_reset(myo_batch* b, const uint8_t* mask, uint64_t seed,
   if (!b) return fail("null batch");
   StepArgs a; memset(&a, 0, sizeof(a)); a.mode = 2; a.reset_mask = mask; b->seed = seed; b->env_offset = env_offset;
   return launch(b, a, stream);
+}
+extern "C" int myo_batch_observe(myo_batch* b, void* stream) {
+  if (!b) return fail("null batch");
+  StepArgs a; memset(&a, 0, sizeof(a)); a.mode = 3; return launch(b, a, stream);
 }
 extern "C" int myo_batch_forward_debug(myo_batch* b, const double* ctrl, int n_substeps, void* stream) {
   if (!b || !ctrl) return fail("myo_batch_forward_debug: null");

@@ -86,6 +86,9 @@ class MyoVecEnv:
         cfg.weights[0], cfg.weights[1], cfg.weights[2], cfg.weights[3] = w["pose"], w["bonus"], w["act_reg"], w["penalty"]
         cfg.solver_tolerance = float(kw.get("solver_tolerance", 0.0))
         cfg.maxcon = int(kw.get("maxcon", 0))
+        cfg.reaf_dst = cfg.reaf_src = -1
+        if self.muscle_condition == "reafferentation":   # base_v0.py:78-79,104-108
+            cfg.reaf_dst, cfg.reaf_src = m.name2id("actuator", "EPL"), m.name2id("actuator", "EIP")
         self.cfg = cfg
         self.device_index = int(device)
         self.device = torch.device("cuda", self.device_index)
@@ -120,8 +123,6 @@ class MyoVecEnv:
                      tap_contact_dist=z(n, max(self.dims.maxcon, 1)), tap_moment=z(n, max(self.dims.reserved[0], 1)), tap_qM=z(n, m.nM))
         self.t = t
         self.batch.bind(**t)
-        if self.muscle_condition == "reafferentation":   # base_v0.py:78-79,104-108
-            self.EPLpos, self.EIPpos = m.name2id("actuator", "EPL"), m.name2id("actuator", "EIP")
         self._h_action = None
 
     # ---------------------------------------------------------------- gym-style API (batched)
@@ -143,9 +144,6 @@ class MyoVecEnv:
         a = self.t["action"]
         if action.data_ptr() != a.data_ptr():
             a.copy_(action, non_blocking=True)
-        if self.muscle_condition == "reafferentation":
-            # applied on the remapped ctrl in the reference; equivalent pre-sigmoid swap is not: do it after remap on host side
-            raise NotImplementedError("reafferentation variant: TODO device-side ctrl swap")
         self.batch.step(stream=self._stream())
         t = self.t
         return t["obs"], t["reward"], t["done"], t["truncated"], {"last_return": t["last_return"], "time": t["time"]}
@@ -173,6 +171,11 @@ class MyoVecEnv:
             if v is not None:
                 self.t[name][:, : np.shape(v)[-1]] = torch.as_tensor(np.asarray(v), dtype=torch.float64, device=self.device)
         self.t["qacc_warmstart"].zero_()
+
+    def refresh_obs(self):
+        """obs / reward / done of the current state (the reference's env.forward(), env_base.py:393-432)."""
+        self.batch.observe(stream=self._stream())
+        return self.t["obs"], self.t["reward"], self.t["done"]
 
     def forward_debug(self, ctrl, n_substeps=0):
         c = self.torch.as_tensor(np.asarray(ctrl), dtype=self.torch.float64, device=self.device).contiguous()

@@ -716,6 +716,8 @@ void oracle_step(ora* o) {
   o->time+=h; memcpy(o->qacc_warmstart,o->qacc,sizeof(double)*nv); free(qacc);
 }
 
+void oracle_step_n(ora* o, int n) { for (int i = 0; i < n; i++) oracle_step(o); }
+
 /* ---------------------------------------------------------------- field access for the Python test harness */
 double* oracle_field(ora* o, const char* name, int* len) {
   #define F(n, ptr, l) if (!strcmp(name, n)) { *len=(l); return (ptr); }

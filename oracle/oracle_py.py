@@ -30,6 +30,8 @@ def lib():
         for f in ("oracle_forward", "oracle_step", "oracle_reset", "oracle_destroy"):
             getattr(L, f).argtypes = [ctypes.c_void_p]
             getattr(L, f).restype = None
+        L.oracle_step_n.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.oracle_step_n.restype = None
         L.oracle_info.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.oracle_info.restype = ctypes.c_int
         _LIB = L
@@ -76,8 +78,7 @@ class Oracle:
         self._L.oracle_forward(self._h)
 
     def step(self, n=1):
-        for _ in range(n):
-            self._L.oracle_step(self._h)
+        self._L.oracle_step_n(self._h, n)
 
     @property
     def ncon(self):

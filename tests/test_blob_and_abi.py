@@ -1,0 +1,116 @@
+"""Host-side checks that need no GPU: blob layout, program invariants, C-ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from myosuite_b200 import abi, blob, build, program
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_layout_header_in_sync():
+    assert open(os.path.join(ROOT, "include", "myo_blob_layout.h")).read() == blob.emit_header()
+
+
+def test_pack_roundtrip(models):
+    for name, m in models.items():
+        prog, _ = program.build_program(m)
+        I, D = blob.pack(m, prog)
+        assert I[0] == blob.MAGIC and I[1] == blob.VERSION
+        assert np.array_equal(blob.section(I, D, "body_parentid"), m.body_parentid)
+        assert np.allclose(blob.section(I, D, "qpos0"), m.qpos0)
+        assert np.array_equal(blob.section(I, D, "PM_i"), prog["PM_i"])
+        for sname, kind in blob.SECTIONS:      # 16-byte alignment of every double section (bulk-copy granularity)
+            if kind == "d":
+                sid = blob.SEC_ID[sname]
+                assert int(I[blob.HDR + int(I[2]) + 3 * sid + 1]) % 2 == 0
+
+
+def test_model_dims_match_survey(models):
+    # SURVEY.md Appendix B.1
+    exp = {"myoelbow_1dof6muscles": (1, 1, 6, 1), "myohand_pose": (23, 23, 39, 116), "myohand_hold": (30, 29, 39, 137), "myolegs": (35, 34, 80, 351)}
+    for name, (nq, nv, nu, nM) in exp.items():
+        m = models[name]
+        assert (m.nq, m.nv, m.nu, m.nM) == (nq, nv, nu, nM)
+        assert m.na == nu
+    assert models["myohand_pose"].nwrap == 325 and models["myolegs"].neq == 14 and models["myolegs"].nkey == 4
+
+
+def test_program_invariants(models):
+    for name, m in models.items():
+        p, info = program.build_program(m)
+        d = p["P_dims"]
+        nbd = d[program.PD_NBD]
+        assert p["PB_level_adr"][-1] == nbd == len(info["dyn_body_ids"])
+        # parents precede children in level order
+        for k, par in enumerate(p["PB_parent"]):
+            assert par < k
+        # every actuated tendon owns exactly one actuator (the kernel writes tfrc without atomics)
+        assert len(set(p["PA_tendon"].tolist())) == m.nu
+        # each structural non-zero of the moment has at least one term and terms reference valid slots
+        adr = p["PNZ_term_adr"]
+        assert np.all(np.diff(adr) >= 1)
+        t = p["PTERM"].reshape(-1, 3)
+        assert np.all(t[:, 0] < d[program.PD_NSP] + 2 * d[program.PD_NWE]) and np.all(np.abs(t[:, 2]) == 1)
+        # collision path dofs are those moving exactly one of the two bodies
+        assert len(p["PPATH"]) == int(p["PPAIR"][:, 4].sum()) if len(p["PPAIR"]) else True
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "myo_b200.h")).read()
+    return sorted(set(re.findall(r"\b(myo_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    path = build.build()
+    L = ctypes.CDLL(path)
+    names = _header_functions()
+    assert set(abi.EXPORTS) == set(names), (set(abi.EXPORTS) ^ set(names))
+    for n in names:
+        assert hasattr(L, n), n
+    assert abi.lib().myo_version() >= 1
+
+
+def test_no_cpu_fallback_without_gpu(models):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = models["myoelbow_1dof6muscles"]
+    prog, _ = program.build_program(m)
+    dm = abi.DeviceModel(*blob.pack(m, prog))
+    d = dm.dims()
+    assert (d.nq, d.nv, d.nu) == (1, 1, 6) and d.smem_bytes_per_env > 0
+    cfg = abi.MyoTaskCfg()
+    cfg.task, cfg.frame_skip = abi.TASK_POSE, 10
+    cfg.reaf_dst = cfg.reaf_src = -1
+    with pytest.raises(abi.MyoError, match="no CUDA device"):
+        abi.Batch(dm, 0, 4, cfg)
+    from myosuite_b200 import vec_env
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        vec_env.MyoVecEnv("myoElbowPose1D6MRandom-v0", 4)
+
+
+def test_blob_rejects_bad_magic(models):
+    m = models["myoelbow_1dof6muscles"]
+    I, D = blob.pack(m, program.build_program(m)[0])
+    I2 = I.copy(); I2[0] = 123
+    with pytest.raises(abi.MyoError):
+        abi.DeviceModel(I2, D)
+    I3, D3 = blob.pack(m)       # no program
+    with pytest.raises(abi.MyoError, match="program"):
+        abi.DeviceModel(I3, D3)
+
+
+def test_registry_ids():
+    from myosuite_b200 import vec_env
+    ids = vec_env.registered_ids()
+    for want in ("myoElbowPose1D6MRandom-v0", "myoHandPoseRandom-v0", "myoLegWalk-v0", "myoHandObjHoldRandom-v0",
+                 "myoFatiLegWalk-v0", "myoSarcHandPoseRandom-v0", "myoReafHandPoseRandom-v0"):
+        assert want in ids
+    steps, kw, ep = vec_env.env_spec("myoFatiHandPoseRandom-v0")
+    assert steps == 100 and kw["muscle_condition"] == "fatigue" and kw["pose_thd"] == 0.7 and len(kw["target_jnt_range"]) == 23
+    steps, kw, ep = vec_env.env_spec("myoElbowPose1D6MRandom-v0")
+    assert kw["target_jnt_range"]["r_elbow_flex"] == [0, 2.27] and kw["reset_type"] == "random"

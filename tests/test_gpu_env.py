@@ -1,0 +1,114 @@
+"""GPU tests of the batched env behaviour at BASELINE sizes: size-independent properties (determinism, batch-size
+independence, auto-reset, TimeLimit, bounded observations) -- the oracle is too slow for 4096 envs x many steps."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(eid, n, steps, seed, act_seed=0, **kw):
+    import torch
+    from myosuite_b200 import vec_env
+    env = vec_env.MyoVecEnv(eid, n, seed=seed, **kw)
+    env.reset(seed=seed)
+    g = torch.Generator(device="cpu").manual_seed(act_seed)
+    out = []
+    for _ in range(steps):
+        a = (torch.rand(n, env.act_dim, generator=g) * 2 - 1).to(env.device)
+        obs, rew, done, trunc, info = env.step(a)
+        out.append((obs.clone(), rew.clone(), done.clone(), trunc.clone()))
+    torch.cuda.synchronize()
+    return env, out
+
+
+@pytest.mark.parametrize("eid", ["myoElbowPose1D6MRandom-v0", "myoHandPoseRandom-v0"])
+def test_full_size_rollout_properties(eid):
+    import torch
+    n, steps = 4096, 110
+    env, out = _run(eid, n, steps, seed=3)
+    obs = torch.stack([o[0] for o in out]); rew = torch.stack([o[1] for o in out])
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+    m = env.mj_model
+    act = obs[..., 2 * m.nq + m.nv:]
+    assert act.min() >= -1e-6 and act.max() <= 1 + 1e-6                       # activations stay in [0,1]
+    # TimeLimit: with no early termination every env truncates exactly at step 100 and is auto-reset
+    trunc = torch.stack([o[3] for o in out]); done = torch.stack([o[2] for o in out])
+    first = (trunc | done).float().argmax(0)
+    assert ((trunc | done).sum(0) >= 1).all()
+    assert (first[~done.any(0)] == env.max_episode_steps - 1).all()
+    assert (env.t["episode_count"] >= 2).all()
+    # after auto-reset the obs is the reset obs: qvel*dt == 0 and act == 0 for envs reset on the last step before
+    k = env.max_episode_steps - 1
+    o_reset = out[k][0]
+    assert torch.all(o_reset[:, m.nq:m.nq + m.nv][trunc[k].bool()] == 0)
+    assert torch.all(o_reset[:, 2 * m.nq + m.nv:][trunc[k].bool()] == 0)
+    # reset poses are inside the joint ranges; targets inside the target ranges
+    q0 = o_reset[:, :m.nq][trunc[k].bool()].double().cpu().numpy()
+    lo, hi = m.jnt_range[:, 0], m.jnt_range[:, 1]
+    assert np.all(q0 >= lo - 1e-6) and np.all(q0 <= hi + 1e-6)
+    tr = env.t["target_range"].cpu().numpy(); tg = env.t["target"].cpu().numpy()
+    assert np.all(tg >= tr[:, 0] - 1e-12) and np.all(tg <= tr[:, 1] + 1e-12)
+    assert env.t["last_return"].abs().sum() > 0
+
+
+def test_determinism_and_batch_size_independence():
+    """Same seed -> bit-identical rollouts; env i's trajectory does not depend on how many envs share the launch."""
+    import torch
+    eid = "myoHandPoseRandom-v0"
+    _, a = _run(eid, 256, 12, seed=5)
+    _, b = _run(eid, 256, 12, seed=5)
+    for (oa, ra, da, ta), (ob, rb, db, tb) in zip(a, b):
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db)
+    env_s, c = _run(eid, 64, 12, seed=5)
+    for (oa, ra, _, _), (oc, rc, _, _) in zip(a, c):
+        assert torch.equal(oa[:64], oc) and torch.equal(ra[:64], rc)
+    _, d = _run(eid, 256, 12, seed=6)
+    assert not torch.equal(a[0][0], d[0][0])
+
+
+def test_env_offset_shards_reproduce_global_batch():
+    """Multi-GPU sharding rule: rank r simulates envs [r*n, (r+1)*n) with env_offset = r*n and gets exactly the
+    rows a single big batch would have produced (no data-path collective needed)."""
+    import torch
+    from myosuite_b200 import vec_env
+    eid, n = "myoElbowPose1D6MRandom-v0", 128
+    big = vec_env.MyoVecEnv(eid, 2 * n, seed=9); big.reset(seed=9)
+    lo = vec_env.MyoVecEnv(eid, n, seed=9, env_offset=0); lo.reset(seed=9)
+    hi = vec_env.MyoVecEnv(eid, n, seed=9, env_offset=n); hi.reset(seed=9)
+    g = torch.Generator().manual_seed(1)
+    for _ in range(20):
+        a = (torch.rand(2 * n, big.act_dim, generator=g) * 2 - 1).cuda()
+        ob, rb, *_ = big.step(a); ol, rl, *_ = lo.step(a[:n].contiguous()); oh, rh, *_ = hi.step(a[n:].contiguous())
+        assert torch.equal(ob[:n], ol) and torch.equal(ob[n:], oh) and torch.equal(rb[n:], rh)
+
+
+def test_single_env_gym_facade():
+    """make(id) -> reset()/step() with the reference's call shapes and dtypes (env_base.py:403-407,647-654)."""
+    from myosuite_b200 import make
+    env = make("myoElbowPose1D6MRandom-v0", seed=1234)
+    obs, info = env.reset(seed=1234)
+    assert obs.dtype == np.float32 and obs.shape == (9,) and isinstance(info, dict)
+    o2, r, term, trunc, info = env.step(np.zeros(6, dtype=np.float32))
+    assert o2.shape == (9,) and isinstance(r, float) and isinstance(term, bool) and trunc is False
+    assert env.unwrapped.mj_model.nu == 6 and env.unwrapped.mj_model.na == 6 and env.dt == pytest.approx(0.02)
+    # determinism check of the reference's test strategy (tests/test_envs.py:100-121): same seed, same reset obs / step obs
+    env2 = make("myoElbowPose1D6MRandom-v0", seed=1234)
+    obs_b, _ = env2.reset(seed=1234)
+    np.testing.assert_allclose(obs, obs_b, atol=1e-5)
+    o2b, rb, *_ = env2.step(np.zeros(6, dtype=np.float32))
+    np.testing.assert_allclose(o2, o2b, atol=1e-5); assert r == pytest.approx(rb, abs=1e-5)
+
+
+def test_sarcopenia_variant_halves_gain():
+    import torch
+    from myosuite_b200 import vec_env
+    a = vec_env.MyoVecEnv("myoElbowPose1D6MRandom-v0", 4, taps=True)
+    b = vec_env.MyoVecEnv("myoSarcElbowPose1D6MRandom-v0", 4, taps=True)
+    q = np.full((4, 1), 1.0); act = np.ones((4, 6)); ctrl = np.ones((4, 6))
+    for e in (a, b):
+        e.set_state(qpos=q, qvel=np.zeros((4, 1)), act=act); e.forward_debug(ctrl, 0)
+    torch.cuda.synchronize()
+    fa, fb = a.t["tap_actuator_force"].cpu().numpy(), b.t["tap_actuator_force"].cpu().numpy()
+    a.set_state(qpos=q, qvel=np.zeros((4, 1)), act=np.zeros((4, 6))); a.forward_debug(ctrl, 0); torch.cuda.synchronize()
+    passive = a.t["tap_actuator_force"].cpu().numpy()
+    np.testing.assert_allclose(fb - passive, 0.5 * (fa - passive), rtol=1e-12, atol=1e-9)   # gainprm[:,2]*=0.5, biasprm untouched (base_v0.py:62-67)

@@ -1,0 +1,170 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances: north_star asks <= 1e-5 relative on qacc and muscle force; the two f64 implementations agree to
+~1e-10, so the tests assert 1e-7 (headroom for FMA / summation-order differences).  Contact pair lists are
+compared bit-exactly (integer indexing)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "pylogic.npz"))
+RTOL = 1e-7
+
+
+def relerr(a, b):
+    return float(np.max(np.abs(a - b) / (np.abs(b) + 1e-6 * max(1.0, np.abs(b).max()))))
+
+
+def _states(m, n, rng, overshoot=0.02, vel=1.0):
+    qpos = np.tile(m.qpos0, (n, 1))
+    for j in range(m.njnt):
+        if m.jnt_type[j] != 0:
+            lo, hi = m.jnt_range[j]
+            span = hi - lo
+            qpos[:, m.jnt_qposadr[j]] = rng.uniform(lo - overshoot * span, hi + overshoot * span, n)
+    return qpos, rng.normal(0, vel, (n, m.nv)), rng.uniform(0, 1, (n, m.na)), rng.uniform(0, 1, (n, m.nu))
+
+
+@pytest.fixture(scope="module")
+def envs():
+    from myosuite_b200 import vec_env
+    return {eid: vec_env.MyoVecEnv(eid, 64, taps=True) for eid in ("myoElbowPose1D6MRandom-v0", "myoHandPoseRandom-v0")}
+
+
+@pytest.mark.parametrize("eid", ["myoElbowPose1D6MRandom-v0", "myoHandPoseRandom-v0"])
+def test_forward_parity(envs, eid):
+    """qacc, actuator_force, tendon length, mass matrix, smooth force and the contact list of one mj_forward."""
+    import torch
+    from oracle.oracle_py import Oracle
+    env = envs[eid]; m = env.mj_model; n = env.num_envs
+    qpos, qvel, act, ctrl = _states(m, n, np.random.default_rng(11))
+    env.set_state(qpos=qpos, qvel=qvel, act=act)
+    env.forward_debug(ctrl, 0); torch.cuda.synchronize()
+    t = {k: v.cpu().numpy() for k, v in env.t.items() if k.startswith("tap_")}
+    o = Oracle(env.I, env.D)
+    pmi = env.prog_info["pair_model_index"]
+    total_con = 0
+    for e in range(n):
+        o.reset(); o.set(qpos=qpos[e], qvel=qvel[e], act=act[e], ctrl=ctrl[e]); o.forward()
+        assert relerr(t["tap_qacc"][e], o.f("qacc")) < RTOL
+        assert relerr(t["tap_actuator_force"][e], o.f("actuator_force")) < RTOL
+        assert relerr(t["tap_ten_length"][e], o.f("actuator_length")) < 1e-10
+        assert relerr(t["tap_qM"][e], o.f("qM")) < 1e-8
+        assert relerr(t["tap_qfrc_smooth"][e], o.f("qfrc_smooth")) < RTOL
+        nc = int(t["tap_ncon"][e, 0])
+        got = [pmi[p] for p in t["tap_contact_pair"][e][:nc]]
+        exp = [int(p) for p in o.i("con_pair") if int(p) in set(pmi)]
+        assert got == exp                                    # integer contact-pair indexing: bit-exact, same order
+        np.testing.assert_allclose(t["tap_contact_dist"][e][:nc], [d for d, p in zip(o.f("con_dist"), o.i("con_pair")) if int(p) in set(pmi)], rtol=1e-9, atol=1e-13)
+        assert t["tap_ncon"][e, 3] == 0                      # no contact-capacity overflow
+        total_con += nc
+    if m.nv > 1:
+        assert total_con > 0                                 # the hand batch really exercised contacts
+
+
+@pytest.mark.parametrize("eid", ["myoElbowPose1D6MRandom-v0", "myoHandPoseRandom-v0"])
+def test_rollout_parity(envs, eid):
+    """10 chained mj_step's with a fixed ctrl (one control step of robot.py:901-905)."""
+    import torch
+    from oracle.oracle_py import Oracle
+    env = envs[eid]; m = env.mj_model; n = env.num_envs
+    qpos, qvel, act, ctrl = _states(m, n, np.random.default_rng(12), overshoot=0.0)
+    env.set_state(qpos=qpos, qvel=qvel, act=act)
+    env.forward_debug(ctrl, 10); torch.cuda.synchronize()
+    gq, gv, ga = env.t["qpos"].cpu().numpy(), env.t["qvel"].cpu().numpy(), env.t["act"].cpu().numpy()
+    o = Oracle(env.I, env.D)
+    for e in range(16):
+        o.reset(); o.set(qpos=qpos[e], qvel=qvel[e], act=act[e], ctrl=ctrl[e]); o.step(10)
+        np.testing.assert_allclose(gq[e], o.f("qpos"), rtol=0, atol=1e-9)
+        assert relerr(gv[e], o.f("qvel")) < RTOL
+        np.testing.assert_allclose(ga[e, :m.na], o.f("act"), rtol=0, atol=1e-12)
+
+
+def test_elbow_joint_limit_rows(envs):
+    """Edge cases of the one-sided limit row: exactly at, just inside, beyond both ends of the range."""
+    import torch
+    from oracle.oracle_py import Oracle
+    env = envs["myoElbowPose1D6MRandom-v0"]; m = env.mj_model; n = env.num_envs
+    lo, hi = m.jnt_range[0]
+    q = np.linspace(lo - 0.1, hi + 0.1, n)[:, None]
+    q[0], q[1], q[2], q[3] = lo, hi, lo - 1e-9, hi + 1e-9
+    rng = np.random.default_rng(5)
+    qvel, act, ctrl = rng.normal(0, 3, (n, 1)), rng.uniform(0, 1, (n, 6)), rng.uniform(0, 1, (n, 6))
+    env.set_state(qpos=q, qvel=qvel, act=act); env.forward_debug(ctrl, 0); torch.cuda.synchronize()
+    t = {k: v.cpu().numpy() for k, v in env.t.items() if k.startswith("tap_")}
+    o = Oracle(env.I, env.D)
+    for e in range(n):
+        o.reset(); o.set(qpos=q[e], qvel=qvel[e], act=act[e], ctrl=ctrl[e]); o.forward()
+        assert int(t["tap_ncon"][e, 1]) == o.nefc
+        assert relerr(t["tap_qacc"][e], o.f("qacc")) < RTOL
+    assert t["tap_ncon"][:, 1].max() == 1 and t["tap_ncon"][0, 1] == 0 and t["tap_ncon"][2, 1] == 1
+
+
+@pytest.mark.parametrize("eid,tag,thd", [("myoElbowPose1D6MRandom-v0", "elbow", 0.175), ("myoHandPoseRandom-v0", "hand", 0.7)])
+def test_env_step_obs_reward_vs_oracle(eid, tag, thd):
+    """Full env.step through the public batched API vs (env_oracle + physics oracle), auto-reset off."""
+    import torch
+    from myosuite_b200 import vec_env
+    from oracle import env_oracle
+    from oracle.oracle_py import Oracle
+    n = 32
+    env = vec_env.MyoVecEnv(eid, n, auto_reset=False)
+    m = env.mj_model
+    rng = np.random.default_rng(21)
+    qpos, qvel, act, _ = _states(m, n, rng, overshoot=0.0, vel=0.5)
+    target = np.stack([rng.uniform(env.t["target_range"][:, 0].cpu().numpy(), env.t["target_range"][:, 1].cpu().numpy()) for _ in range(n)])
+    env.set_state(qpos=qpos, qvel=qvel, act=act, target=target)
+    oracles = []
+    for e in range(n):
+        o = Oracle(env.I, env.D); o.reset(); o.set(qpos=qpos[e], qvel=qvel[e], act=act[e]); oracles.append(o)
+    for step in range(3):
+        a = rng.uniform(-1, 1, (n, m.nu)).astype(np.float32)
+        obs, rew, done, trunc, info = env.step(torch.as_tensor(a, device=env.device)); torch.cuda.synchronize()
+        obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        for e in range(n):
+            o = oracles[e]
+            env_oracle.env_step(o, a[e].astype(np.float64), env.n_frames)
+            exp_obs = env_oracle.pose_obs(o.f("qpos"), o.f("qvel"), o.f("act"), target[e], env.dt)
+            np.testing.assert_allclose(obs[e], exp_obs, rtol=2e-6, atol=2e-6)
+            r = env_oracle.pose_reward(o.f("qpos"), o.f("act"), target[e], thd)
+            assert rew[e] == pytest.approx(r["dense"], rel=1e-5, abs=1e-5) and bool(done[e]) == bool(r["done"])
+    assert np.all(env.t["step_count"].cpu().numpy() == 3)
+    assert np.allclose(env.t["time"].cpu().numpy(), 3 * env.dt)
+
+
+def test_pose_obs_reward_golden_from_reference():
+    """obs / reward / done produced by the kernel epilogue on states whose expected values were computed by the
+    reference's own PoseEnvV0.get_obs_dict / get_reward_dict / obsdict2obsvec (tests/golden/make_golden.py)."""
+    import torch
+    from myosuite_b200 import vec_env
+    for eid, tag in (("myoElbowPose1D6MRandom-v0", "elbow"), ("myoHandPoseRandom-v0", "hand")):
+        q, v, a, tg = (G["pose_%s_%s" % (tag, k)] for k in ("qpos", "qvel", "act", "target"))
+        env = vec_env.MyoVecEnv(eid, len(q), auto_reset=False)
+        env.set_state(qpos=q, qvel=v, act=a, target=tg)
+        env.refresh_obs(); torch.cuda.synchronize()
+        np.testing.assert_array_equal(env.t["obs"].cpu().numpy(), G["pose_%s_obs" % tag])      # float32, bit-exact
+        np.testing.assert_allclose(env.t["reward"].cpu().numpy(), G["pose_%s_rwd_dense" % tag], rtol=2e-6, atol=2e-6)
+        np.testing.assert_array_equal(env.t["done"].cpu().numpy().astype(bool), G["pose_%s_rwd_done" % tag].astype(bool))
+
+
+def test_fatigue_variant_vs_reference_golden():
+    """myoFati*: the device-side 3CC-r update against the golden MA/MR/MF produced by the reference's fatigue.py
+    (same actions as tests/golden/make_golden.py BaseV0.step run: 39 muscles, dt=0.02)."""
+    import torch
+    from myosuite_b200 import vec_env
+    env = vec_env.MyoVecEnv("myoFatiHandPoseRandom-v0", 2, auto_reset=False)
+    A = G["step_action_fatigue"].astype(np.float32)   # float32 is what crosses the ABI
+    from oracle import env_oracle
+    f = env_oracle.Fatigue(39, dt=0.02)
+    for k in range(len(A)):
+        a = torch.as_tensor(np.stack([A[k], A[k]]), device=env.device)
+        env.step(a)
+        exp = f.compute_act(env_oracle.action_to_ctrl(A[k].astype(np.float64)))
+        torch.cuda.synchronize()
+        got = env.t["fatigue"][0].cpu().numpy()
+        np.testing.assert_allclose(got, np.stack(exp), rtol=1e-12, atol=1e-15)
+    # and the chain agrees with the reference golden to float32-action round-off
+    np.testing.assert_allclose(env.t["fatigue"][0, 0].cpu().numpy(), G["step_ctrl_fatigue"][-1], rtol=0, atol=5e-6)

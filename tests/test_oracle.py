@@ -1,0 +1,180 @@
+"""The CPU oracle against (a) golden vectors produced by the reference's own Python code, and
+(b) independent numpy computations / finite differences for the MuJoCo-restatement part (parity unpinned:
+no MuJoCo available, see oracle/myo_oracle.c header)."""
+import os
+
+import numpy as np
+import pytest
+
+from myosuite_b200 import blob, mjcf, program
+from oracle import env_oracle
+from oracle.oracle_py import Oracle
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "pylogic.npz"))
+
+
+# ----------------------------------------------------------------------------- golden: python-side logic
+def test_fatigue_known_answer():
+    f = env_oracle.Fatigue(5, dt=0.002 * 5)
+    for a, exp in zip(G["fatigue_kat_in"], G["fatigue_kat_out"]):
+        MA, MR, MF = f.compute_act(a)
+        np.testing.assert_allclose(np.stack([MA, MR, MF]), exp, rtol=1e-13, atol=1e-15)
+    # SURVEY.md section 8c known answers (verified there against the reference)
+    np.testing.assert_allclose(G["fatigue_kat_out"][3, 0], [0.509728576, 0.499965801, 0.6483463034, 0.5102154323, 0.7049798034], rtol=1e-9)
+    np.testing.assert_allclose(G["fatigue_kat_out"][3, 2], [8.5495798416e-05, 9.1195798416e-05, 1.1398941168e-04, 8.2645798416e-05, 1.2538941168e-04], rtol=1e-9)
+
+
+def test_fatigue_long_run():
+    acts = np.random.default_rng(7).uniform(0, 1, (2000, 80))
+    acts[500:700] = 1.0
+    acts[1200:1300] = 0.0
+    f = env_oracle.Fatigue(80, dt=0.001 * 10)
+    for k, a in enumerate(acts):
+        out = f.compute_act(a)
+        if k % 50 == 0:
+            np.testing.assert_allclose(np.stack(out), G["fatigue_long_out"][k // 50], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(np.stack(out), G["fatigue_long_final"], rtol=1e-12, atol=1e-14)
+    assert np.allclose(f.MA + f.MR + f.MF, 1.0)
+
+
+def test_action_remap_and_fatigue_chain():
+    np.testing.assert_allclose(np.stack([env_oracle.action_to_ctrl(a) for a in G["step_action_none"]]), G["step_ctrl_none"], rtol=1e-15)
+    f = env_oracle.Fatigue(39, dt=0.02)
+    got = np.stack([f.compute_act(env_oracle.action_to_ctrl(a))[0].copy() for a in G["step_action_fatigue"]])
+    np.testing.assert_allclose(got, G["step_ctrl_fatigue"], rtol=1e-13)
+    # float32 actions: the reference evaluates the sigmoid in float32 -> agrees with the f64 remap to f32 round-off
+    np.testing.assert_allclose(G["step_ctrl_f32in"], G["step_ctrl_none"], rtol=0, atol=2e-7)
+
+
+@pytest.mark.parametrize("tag,thd", [("elbow", 0.175), ("hand", 0.7)])
+def test_pose_obs_reward(tag, thd):
+    q, v, a, t = (G["pose_%s_%s" % (tag, k)] for k in ("qpos", "qvel", "act", "target"))
+    for i in range(len(q)):
+        obs = env_oracle.pose_obs(q[i], v[i], a[i], t[i], 0.02)
+        assert obs.dtype == np.float32
+        np.testing.assert_array_equal(obs, G["pose_%s_obs" % tag][i])
+        r = env_oracle.pose_reward(q[i], a[i], t[i], thd)
+        for k in ("pose", "bonus", "penalty", "act_reg", "sparse", "dense"):
+            np.testing.assert_allclose(r[k], G["pose_%s_rwd_%s" % (tag, k)][i], rtol=1e-14, atol=1e-15)
+        assert bool(r["solved"]) == bool(G["pose_%s_rwd_solved" % tag][i]) and bool(r["done"]) == bool(G["pose_%s_rwd_done" % tag][i])
+    assert G["pose_%s_rwd_done" % tag].sum() >= 2 and G["pose_%s_rwd_bonus" % tag].max() == 2
+
+
+# ----------------------------------------------------------------------------- physics restatement: independent cross-checks
+def _rand_state(m, rng, margin=0.1):
+    q = m.qpos0.copy()
+    for j in range(m.njnt):
+        if m.jnt_type[j] != 0:
+            lo, hi = m.jnt_range[j]
+            q[m.jnt_qposadr[j]] = rng.uniform(lo + margin * (hi - lo), hi - margin * (hi - lo))
+    return q
+
+
+def _dense_M(m, qM):
+    M = np.zeros((m.nv, m.nv))
+    for i in range(m.nv):
+        adr, j = m.dof_Madr[i], i
+        while j >= 0:
+            M[i, j] = M[j, i] = qM[adr]
+            adr += 1
+            j = m.dof_parentid[j]
+    return M
+
+
+@pytest.mark.parametrize("name", ["myoelbow_1dof6muscles", "myohand_pose", "myolegs"])
+def test_oracle_kinematics_mass_gravity_tendon(models, name):
+    m = models[name]
+    o = Oracle(*blob.pack(m))
+    rng = np.random.default_rng(0)
+    q = _rand_state(m, rng)
+    o.set(qpos=q, qvel=np.zeros(m.nv), act=rng.uniform(0, 1, m.na), ctrl=rng.uniform(0, 1, m.nu))
+    o.forward()
+    kin = mjcf.kinematics(m, q)
+    np.testing.assert_allclose(o.f("xpos").reshape(-1, 3), kin["xpos"], atol=1e-13)
+    M1 = _dense_M(m, o.f("qM").copy())
+    np.testing.assert_allclose(M1, mjcf.mass_matrix(m, kin), rtol=1e-10, atol=1e-14)
+    o.forward()                                           # forward is idempotent (no state leaks between calls)
+    np.testing.assert_array_equal(_dense_M(m, o.f("qM")), M1)
+    g = np.zeros(m.nv)
+    for b in range(1, m.nbody):
+        if m.body_weldid[b]:
+            jp, _ = mjcf.jac_point(m, kin, kin["xipos"][b], b)
+            g -= m.body_mass[b] * (jp.T @ m.opt_gravity)
+    np.testing.assert_allclose(o.f("qfrc_bias"), g, rtol=1e-9, atol=1e-12)
+    # tendon Jacobian (incl. sphere/cylinder/inside wrapping) == finite difference of tendon length
+    J = o.f("ten_J").reshape(m.ntendon, m.nv).copy()
+    for d in range(m.nv):
+        j = m.dof_jntid[d]
+        if m.jnt_type[j] == 0:
+            continue
+        L = []
+        for s in (+1, -1):
+            qq = q.copy(); qq[m.jnt_qposadr[j]] += s * 1e-6
+            o.set(qpos=qq); o.forward(); L.append(o.f("ten_length").copy())
+        np.testing.assert_allclose((L[0] - L[1]) / 2e-6, J[:, d], atol=2e-8)
+
+
+def test_oracle_muscle_curves():
+    """MuJoCo's documented muscle curves: FL(1)=1, FL(lmin)=FL(lmax)=0, FV(0)=1, FV(-1)=0, FV(>=fvmax-1)=fvmax, passive 0 below L=1."""
+    # exercised through a 1-muscle forward: elbow model, vary act/len via qpos
+    from myosuite_b200 import assets
+    m = assets.load("myoelbow_1dof6muscles")
+    o = Oracle(*blob.pack(m))
+    o.set(qpos=[1.0], act=np.zeros(6)); o.forward()
+    f0 = o.f("actuator_force").copy()                      # act=0 -> passive force only (<= 0)
+    assert np.all(f0 <= 0)
+    o.set(act=np.ones(6)); o.forward()
+    assert np.all(o.f("actuator_force") <= f0 + 1e-12)    # activation adds contractile (negative) force
+    o.set(ctrl=np.ones(6), act=np.zeros(6)); o.forward()
+    np.testing.assert_allclose(o.f("act_dot"), (1.0 - 0.0) / (0.01 * 0.5))        # tau_act*(0.5+1.5*0)
+    o.set(ctrl=np.zeros(6), act=np.ones(6)); o.forward()
+    np.testing.assert_allclose(o.f("act_dot"), (0.001 - 1.0) / (0.04 / 2.0))    # tau_deact/(0.5+1.5*1); ctrl is clamped to ctrlrange[0]=0.001 first
+
+
+def test_oracle_joint_limit_and_solver(models):
+    m = models["myoelbow_1dof6muscles"]
+    o = Oracle(*blob.pack(m))
+    o.set(qpos=[-0.05], qvel=[-1.0]); o.forward()          # below the lower limit (range 0..2.26893)
+    assert o.nefc == 1 and o.f("efc_pos")[0] == pytest.approx(-0.05)
+    assert o.f("efc_force")[0] > 0 and o.f("qacc")[0] > o.f("qacc_smooth")[0]
+    # closed form for nv=1: a = (f + D*aref)/(M + D)
+    M, D, aref, f = o.f("qM")[0], o.f("efc_D")[0], o.f("efc_aref")[0], o.f("qfrc_smooth")[0]
+    assert o.f("qacc")[0] == pytest.approx((f + D * aref) / (M + D), rel=1e-12)
+    o.set(qpos=[1.0], qvel=[0.0]); o.forward()
+    assert o.nefc == 0 and o.f("qacc")[0] == pytest.approx(o.f("qacc_smooth")[0])
+
+
+def test_oracle_hand_contacts_and_kkt(models):
+    """Random hand poses produce capsule contacts; the Newton solution satisfies the optimality conditions."""
+    m = models["myohand_pose"]
+    o = Oracle(*blob.pack(m))
+    rng = np.random.default_rng(3)
+    seen = 0
+    for _ in range(20):
+        q = _rand_state(m, rng, margin=-0.02)
+        o.set(qpos=q, qvel=rng.normal(0, 1, m.nv), act=rng.uniform(0, 1, m.na), ctrl=rng.uniform(0, 1, m.nu)); o.forward()
+        seen += o.ncon
+        nefc = o.nefc
+        J = o.f("efc_J").reshape(nefc, m.nv); force = o.f("efc_force")
+        Mq = _dense_M(m, o.f("qM")) @ o.f("qacc")
+        np.testing.assert_allclose(Mq, o.f("qfrc_smooth") + J.T @ force, rtol=1e-8, atol=1e-8 * np.abs(Mq).max())
+        jar = J @ o.f("qacc") - o.f("efc_aref")
+        assert np.all(force >= 0) and np.all(force[jar > 1e-9] == 0)
+        g1, g2 = o.i("con_geom1"), o.i("con_geom2")
+        assert np.all(g1 < g2)
+    assert seen > 0
+
+
+def test_oracle_rollout_stable(models):
+    for name, n in (("myoelbow_1dof6muscles", 1000), ("myohand_pose", 300), ("myolegs", 100)):
+        m = models[name]
+        o = Oracle(*blob.pack(m))
+        if m.nkey:
+            o.set(qpos=m.key_qpos[0])
+        rng = np.random.default_rng(1)
+        for s in range(n):
+            if s % 10 == 0:
+                o.set(ctrl=rng.uniform(0, 1, m.nu))
+            o.step()
+        assert np.all(np.isfinite(o.f("qpos"))) and np.abs(o.f("qvel")).max() < 100
+        assert np.all(o.f("act") >= -1e-9) and np.all(o.f("act") <= 1 + 1e-9)
