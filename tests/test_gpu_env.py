@@ -6,7 +6,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _run(eid, n, steps, seed, act_seed=0, **kw):
+def _run(eid, n, steps, seed, act_seed=0, n_act=4096, **kw):
     import torch
     from myosuite_b200 import vec_env
     env = vec_env.MyoVecEnv(eid, n, seed=seed, **kw)
@@ -14,7 +14,8 @@ def _run(eid, n, steps, seed, act_seed=0, **kw):
     g = torch.Generator(device="cpu").manual_seed(act_seed)
     out = []
     for _ in range(steps):
-        a = (torch.rand(n, env.act_dim, generator=g) * 2 - 1).to(env.device)
+        # env i always receives row i of the same [n_act, nu] random matrix, whatever the batch size
+        a = (torch.rand(n_act, env.act_dim, generator=g) * 2 - 1)[:n].contiguous().to(env.device)
         obs, rew, done, trunc, info = env.step(a)
         out.append((obs.clone(), rew.clone(), done.clone(), trunc.clone()))
     torch.cuda.synchronize()
@@ -35,7 +36,7 @@ def test_full_size_rollout_properties(eid):
     trunc = torch.stack([o[3] for o in out]); done = torch.stack([o[2] for o in out])
     first = (trunc | done).float().argmax(0)
     assert ((trunc | done).sum(0) >= 1).all()
-    assert (first[~done.any(0)] == env.max_episode_steps - 1).all()
+    assert (first[~done.bool().any(0)] == env.max_episode_steps - 1).all()
     assert (env.t["episode_count"] >= 2).all()
     # after auto-reset the obs is the reset obs: qvel*dt == 0 and act == 0 for envs reset on the last step before
     k = env.max_episode_steps - 1
