@@ -12,7 +12,7 @@ kernels stage the hot sections into shared memory with bulk async copies.
 import numpy as np
 
 MAGIC = 0x4D594F42  # 'MYOB'
-VERSION = 3
+VERSION = 4
 
 DIMS = ["nq", "nv", "nu", "na", "nbody", "njnt", "ngeom", "nsite", "ntendon", "nwrap", "nM", "npair", "neq", "nkey",
         "iterations", "ls_iterations"]
@@ -59,6 +59,8 @@ PROGRAM_SECTIONS = [
     # collision / constraints
     ("PG_body", "i"), ("PG_type", "i"), ("PG_d", "d"), ("PPAIR", "i"), ("PPAIR_d", "d"), ("PPATH", "i"),
     ("PLIM", "i"), ("PLIM_d", "d"), ("PEQ", "i"), ("PEQ_d", "d"),
+    # level-scheduled tree-sparse L'DL
+    ("PLV_adr", "i"), ("PLV", "i"), ("PFE_adr", "i"), ("PFE", "i"), ("PFT_adr", "i"), ("PFT", "i"), ("PDS_adr", "i"), ("PDS", "i"),
 ]
 
 SECTIONS = RAW_SECTIONS + PROGRAM_SECTIONS

@@ -36,28 +36,19 @@ __device__ __forceinline__ double philox_uniform(Philox& p) {   // [0,1) with 53
   uint32_t a = p.out[4-p.have], b = p.out[5-p.have]; p.have -= 2;
   return ((double)(((unsigned long long)(a >> 5) << 26) | (b >> 6))) * (1.0/9007199254740992.0); }
 
-// ------------------------------------------------------------------ one physics substep = forward dynamics (+ optional taps) + Euler
-__device__ void substep(const DevModel& m, Warp& w, const StepArgs& a, int env, bool tap, bool integrate) {
-  phase_kinematics(m, w);
-  phase_tendon(m, w);
-  phase_actuation(m, w);
-  phase_crb(m, w);
-  phase_bias(m, w);
-  phase_collision(m, w);
-  phase_constraints(m, w);
-  phase_solve(m, w, a.tol);
-  if (tap) { Solv s = solv_views(m, w); const myo_buffers& b = a.b;
-    if (b.tap_qacc) for (int i = w.lane; i < m.nv; i += 32) b.tap_qacc[(size_t)env*m.nv+i] = s.a[i];
-    if (b.tap_qfrc_smooth) for (int i = w.lane; i < m.nv; i += 32) b.tap_qfrc_smooth[(size_t)env*m.nv+i] = w.fsm[i];
-    if (b.tap_actuator_force) for (int i = w.lane; i < m.nu; i += 32) b.tap_actuator_force[(size_t)env*m.nu+i] = w.aforce[i];
-    if (b.tap_ten_length) { const int* at = ISEC(m, PA_tendon); const double* PA = DSEC(m, PA_d); for (int i = w.lane; i < m.nu; i += 32) b.tap_ten_length[(size_t)env*m.nu+i] = PA[i*PA_STRIDE+26]*w.tlen[at[i]]; }
-    if (b.tap_moment) for (int i = w.lane; i < m.nnz; i += 32) b.tap_moment[(size_t)env*m.nnz+i] = w.mom[i];
-    if (b.tap_qM) for (int i = w.lane; i < m.nM; i += 32) b.tap_qM[(size_t)env*m.nM+i] = w.qM[i];
-    if (b.tap_ncon && w.lane == 0) { int* t = b.tap_ncon + 4*(size_t)env; t[0] = w.ncon; t[1] = w.nefc; t[2] = w.niter; t[3] = w.overflow; }
-    if (b.tap_contact_pair) for (int c = w.lane; c < m.maxcon; c += 32) b.tap_contact_pair[(size_t)env*m.maxcon+c] = c < w.ncon ? s.cpair[c] : -1;
-    if (b.tap_contact_dist) for (int c = w.lane; c < m.maxcon; c += 32) b.tap_contact_dist[(size_t)env*m.maxcon+c] = c < w.ncon ? s.con[c*CON_STRIDE] : 0.0;
-    __syncwarp(); }
-  if (integrate) phase_integrate(m, w);
+// ------------------------------------------------------------------ parity taps (values of the forward pass just computed)
+__device__ void write_taps(const DevModel& m, Warp& w, const StepArgs& a, int env) {
+  Solv s = solv_views(m, w); const myo_buffers& b = a.b;
+  if (b.tap_qacc) for (int i = w.lane; i < m.nv; i += 32) b.tap_qacc[(size_t)env*m.nv+i] = s.a[i];
+  if (b.tap_qfrc_smooth) for (int i = w.lane; i < m.nv; i += 32) b.tap_qfrc_smooth[(size_t)env*m.nv+i] = w.fsm[i];
+  if (b.tap_actuator_force) for (int i = w.lane; i < m.nu; i += 32) b.tap_actuator_force[(size_t)env*m.nu+i] = w.aforce[i];
+  if (b.tap_ten_length) { const int* at = ISEC(m, PA_tendon); const double* PA = DSEC(m, PA_d); for (int i = w.lane; i < m.nu; i += 32) b.tap_ten_length[(size_t)env*m.nu+i] = PA[i*PA_STRIDE+26]*w.tlen[at[i]]; }
+  if (b.tap_moment) for (int i = w.lane; i < m.nnz; i += 32) b.tap_moment[(size_t)env*m.nnz+i] = w.mom[i];
+  if (b.tap_qM) for (int i = w.lane; i < m.nM; i += 32) b.tap_qM[(size_t)env*m.nM+i] = w.qM[i];
+  if (b.tap_ncon && w.lane == 0) { int* t = b.tap_ncon + 4*(size_t)env; t[0] = w.ncon; t[1] = w.nefc; t[2] = w.niter; t[3] = w.overflow; }
+  if (b.tap_contact_pair) for (int c = w.lane; c < m.maxcon; c += 32) b.tap_contact_pair[(size_t)env*m.maxcon+c] = c < w.ncon ? s.cpair[c] : -1;
+  if (b.tap_contact_dist) for (int c = w.lane; c < m.maxcon; c += 32) b.tap_contact_dist[(size_t)env*m.maxcon+c] = c < w.ncon ? s.con[c*CON_STRIDE] : 0.0;
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------ task logic: pose task (pose_v0.py:100-140,154-170,174-257)
@@ -108,63 +99,83 @@ extern "C" __global__ void __launch_bounds__(256) myo_env_kernel(DevModel m, Ste
   w.tfrc = base+m.o_tfrc; w.aforce = base+m.o_aforce; w.actdot = base+m.o_actdot; w.qM = base+m.o_qM; w.fsm = base+m.o_fsm; w.arena = base+m.o_arena;
   w.ncon = w.nefc = w.nlimrow = w.niter = w.overflow = 0;
   const myo_buffers& b = a.b;
-  for (int env = blockIdx.x*nw + wid; env < a.n_env; env += gridDim.x*nw) {
-    // ---- load state (coalesced: one env's row per warp)
-    for (int i = w.lane; i < m.nq; i += 32) w.qpos[i] = b.qpos[(size_t)env*m.nq+i];
-    for (int i = w.lane; i < m.nv; i += 32) { w.qvel[i] = b.qvel[(size_t)env*m.nv+i]; w.qws[i] = b.qacc_warmstart[(size_t)env*m.nv+i]; }
-    for (int i = w.lane; i < m.na; i += 32) w.act[i] = b.act[(size_t)env*m.na+i];
-    __syncwarp();
-    if (a.mode == 2) {
-      if (!a.reset_mask || a.reset_mask[env]) { env_reset(m, w, a, env);
-        if (a.cfg.task == MYO_TASK_POSE) { double d, am; write_obs_pose(m, w, a, env, &d, &am); }
-        if (w.lane == 0) { if (b.done) b.done[env] = 0; if (b.truncated) b.truncated[env] = 0; if (b.reward) b.reward[env] = 0; } }
-    } else if (a.mode == 3) {   // observe: obs/reward/done of the current state, nothing advanced (env.forward(), env_base.py:393-432)
-      if (a.cfg.task == MYO_TASK_POSE) { double rw; bool done; pose_reward_done(m, w, a, env, &rw, &done);
-        if (w.lane == 0) { if (b.reward) b.reward[env] = (float)rw; if (b.done) b.done[env] = done; } }
-    } else if (a.mode == 1) {
-      for (int i = w.lane; i < m.nu; i += 32) w.ctrl[i] = a.dbg_ctrl[(size_t)env*m.nu+i];
+  // All warps of a CTA walk the phases in lockstep (CTA barriers between phases) so that they share instruction fetches:
+  // the step is a long, mostly straight-line program and the instruction cache, not the data path, is the scarce resource.
+  const int nsub = a.mode == 0 ? a.cfg.frame_skip : (a.mode == 1 ? (a.n_substeps > 0 ? a.n_substeps : 1) : 0);
+  const bool integrate = a.mode == 0 || (a.mode == 1 && a.n_substeps > 0);
+  for (int ebase = blockIdx.x*nw; ebase < a.n_env; ebase += gridDim.x*nw) {
+    const int env = ebase + wid; const bool live = env < a.n_env;
+    if (live) {
+      // ---- load state (coalesced: one env's row per warp)
+      for (int i = w.lane; i < m.nq; i += 32) w.qpos[i] = b.qpos[(size_t)env*m.nq+i];
+      for (int i = w.lane; i < m.nv; i += 32) { w.qvel[i] = b.qvel[(size_t)env*m.nv+i]; w.qws[i] = b.qacc_warmstart[(size_t)env*m.nv+i]; }
+      for (int i = w.lane; i < m.na; i += 32) w.act[i] = b.act[(size_t)env*m.na+i];
       __syncwarp();
-      int ns = a.n_substeps > 0 ? a.n_substeps : 1;
-      for (int s = 0; s < ns; s++) substep(m, w, a, env, s == ns-1, a.n_substeps > 0);
-      if (a.n_substeps > 0 && w.lane == 0 && b.time) b.time[env] += ns*m.timestep;
-    } else {
-      // ---- action -> ctrl  (base_v0.py:83-96); fatigue (fatigue.py:38-76)
-      for (int i = w.lane; i < m.nu; i += 32) { double c = (double)b.action[(size_t)env*m.nu+i];
-        if (a.cfg.reaf_dst != a.cfg.reaf_src && i == a.cfg.reaf_dst) c = (double)b.action[(size_t)env*m.nu+a.cfg.reaf_src];
-        if (a.cfg.normalize_act) c = 1.0/(1.0+exp(-5.0*(c-0.5)));
-        if (a.cfg.reaf_dst != a.cfg.reaf_src && i == a.cfg.reaf_src) c = 0.0;
-        if (a.cfg.muscle_condition == MYO_COND_FATIGUE && b.fatigue) { double* F = b.fatigue + (size_t)env*3*m.nu; const double* PA = DSEC(m, PA_d) + i*PA_STRIDE;
-          double MA = F[i], MR = F[m.nu+i], MF = F[2*m.nu+i], TL = c, fdt = a.dt, tauact = PA[0], taudeact = PA[1];
-          const double r = 10*15, Fc = 0.00912, Rc = 0.1*0.00094;
-          double LD = 1.0/tauact*(0.5+1.5*MA), LR = (0.5+1.5*MA)/taudeact, C = 0;
-          if (MA < TL && MR > TL-MA) C = LD*(TL-MA);
-          if (MA < TL && MR <= TL-MA) C = LD*MR;
-          if (MA >= TL) C = LR*(TL-MA);
-          double rR = MA >= TL ? r*Rc : Rc;
-          double lo = fmax(-MA/fdt + Fc*MA, (MR-1)/fdt + rR*MF), hi = fmin((1-MA)/fdt + Fc*MA, MR/fdt + rR*MF);
-          C = fmin(fmax(C, lo), hi);   // np.clip(C, lo, hi) == minimum(maximum(C, lo), hi)
-          double dMA = (C-Fc*MA)*fdt, dMR = (-C+rR*MF)*fdt, dMF = (Fc*MA-rR*MF)*fdt;
-          MA += dMA; MR += dMR; MF += dMF; F[i] = MA; F[m.nu+i] = MR; F[2*m.nu+i] = MF; c = MA; }
-        w.ctrl[i] = c; }
+      if (a.mode == 2) {
+        if (!a.reset_mask || a.reset_mask[env]) { env_reset(m, w, a, env);
+          if (a.cfg.task == MYO_TASK_POSE) { double d, am; write_obs_pose(m, w, a, env, &d, &am); }
+          if (w.lane == 0) { if (b.done) b.done[env] = 0; if (b.truncated) b.truncated[env] = 0; if (b.reward) b.reward[env] = 0; } }
+      } else if (a.mode == 3) {   // observe: obs/reward/done of the current state, nothing advanced (env.forward(), env_base.py:393-432)
+        if (a.cfg.task == MYO_TASK_POSE) { double rw; bool done; pose_reward_done(m, w, a, env, &rw, &done);
+          if (w.lane == 0) { if (b.reward) b.reward[env] = (float)rw; if (b.done) b.done[env] = done; } }
+      } else if (a.mode == 1) {
+        for (int i = w.lane; i < m.nu; i += 32) w.ctrl[i] = a.dbg_ctrl[(size_t)env*m.nu+i];
+      } else {
+        // ---- action -> ctrl  (base_v0.py:83-96); fatigue (fatigue.py:38-76)
+        for (int i = w.lane; i < m.nu; i += 32) { double c = (double)b.action[(size_t)env*m.nu+i];
+          if (a.cfg.reaf_dst != a.cfg.reaf_src && i == a.cfg.reaf_dst) c = (double)b.action[(size_t)env*m.nu+a.cfg.reaf_src];
+          if (a.cfg.normalize_act) c = 1.0/(1.0+exp(-5.0*(c-0.5)));
+          if (a.cfg.reaf_dst != a.cfg.reaf_src && i == a.cfg.reaf_src) c = 0.0;
+          if (a.cfg.muscle_condition == MYO_COND_FATIGUE && b.fatigue) { double* F = b.fatigue + (size_t)env*3*m.nu; const double* PA = DSEC(m, PA_d) + i*PA_STRIDE;
+            double MA = F[i], MR = F[m.nu+i], MF = F[2*m.nu+i], TL = c, fdt = a.dt, tauact = PA[0], taudeact = PA[1];
+            const double r = 10*15, Fc = 0.00912, Rc = 0.1*0.00094;
+            double LD = 1.0/tauact*(0.5+1.5*MA), LR = (0.5+1.5*MA)/taudeact, C = 0;
+            if (MA < TL && MR > TL-MA) C = LD*(TL-MA);
+            if (MA < TL && MR <= TL-MA) C = LD*MR;
+            if (MA >= TL) C = LR*(TL-MA);
+            double rR = MA >= TL ? r*Rc : Rc;
+            double lo = fmax(-MA/fdt + Fc*MA, (MR-1)/fdt + rR*MF), hi = fmin((1-MA)/fdt + Fc*MA, MR/fdt + rR*MF);
+            C = fmin(fmax(C, lo), hi);   // np.clip(C, lo, hi) == minimum(maximum(C, lo), hi)
+            double dMA = (C-Fc*MA)*fdt, dMR = (-C+rR*MF)*fdt, dMF = (Fc*MA-rR*MF)*fdt;
+            MA += dMA; MR += dMR; MF += dMF; F[i] = MA; F[m.nu+i] = MR; F[2*m.nu+i] = MF; c = MA; }
+          w.ctrl[i] = c; }
+      }
       __syncwarp();
-      for (int s = 0; s < a.cfg.frame_skip; s++) substep(m, w, a, env, s == a.cfg.frame_skip-1, true);
-      // ---- obs / reward / done / TimeLimit / auto-reset
-      if (a.cfg.task == MYO_TASK_POSE) { double rw; bool done; pose_reward_done(m, w, a, env, &rw, &done);
-        int sc = b.step_count ? b.step_count[env]+1 : 0; bool trunc = a.cfg.max_episode_steps > 0 && sc >= a.cfg.max_episode_steps;
-        __syncwarp();
-        if (w.lane == 0) { if (b.reward) b.reward[env] = (float)rw; if (b.done) b.done[env] = done; if (b.truncated) b.truncated[env] = trunc && !done;
-          if (b.step_count) b.step_count[env] = sc; if (b.time) b.time[env] += a.cfg.frame_skip*m.timestep;
-          if (b.ep_return) { float R = b.ep_return[env] + (float)rw; b.ep_return[env] = R; if ((done || trunc) && b.last_return) b.last_return[env] = R; } }
-        __syncwarp();
-        if ((done || trunc) && a.cfg.auto_reset) { env_reset(m, w, a, env); double d2, a2; write_obs_pose(m, w, a, env, &d2, &a2); }
-      } else if (w.lane == 0 && b.time) b.time[env] += a.cfg.frame_skip*m.timestep;
     }
-    __syncwarp();
-    // ---- store state
-    for (int i = w.lane; i < m.nq; i += 32) b.qpos[(size_t)env*m.nq+i] = w.qpos[i];
-    for (int i = w.lane; i < m.nv; i += 32) { b.qvel[(size_t)env*m.nv+i] = w.qvel[i]; b.qacc_warmstart[(size_t)env*m.nv+i] = w.qws[i]; }
-    for (int i = w.lane; i < m.na; i += 32) b.act[(size_t)env*m.na+i] = w.act[i];
-    __syncwarp();
+    // ---- physics substeps: forward dynamics + semi-implicit Euler (the only copy of the phase code in the kernel)
+    #pragma unroll 1
+    for (int s = 0; s < nsub; s++) {
+      __syncthreads(); if (live) phase_kinematics(m, w);
+      __syncthreads(); if (live) phase_tendon(m, w);
+      __syncthreads(); if (live) phase_actuation(m, w);
+      __syncthreads(); if (live) { phase_crb(m, w); phase_bias(m, w); }
+      __syncthreads(); if (live) phase_collision(m, w);
+      __syncthreads(); if (live) phase_constraints(m, w);
+      __syncthreads(); if (live) phase_solve(m, w, a.tol);
+      __syncthreads();
+      if (live) { if (s == nsub-1) write_taps(m, w, a, env); if (integrate) phase_integrate(m, w); }
+    }
+    if (live) {
+      if (a.mode == 1) { if (integrate && w.lane == 0 && b.time) b.time[env] += nsub*m.timestep; }
+      else if (a.mode == 0) {
+        // ---- obs / reward / done / TimeLimit / auto-reset
+        if (a.cfg.task == MYO_TASK_POSE) { double rw; bool done; pose_reward_done(m, w, a, env, &rw, &done);
+          int sc = b.step_count ? b.step_count[env]+1 : 0; bool trunc = a.cfg.max_episode_steps > 0 && sc >= a.cfg.max_episode_steps;
+          __syncwarp();
+          if (w.lane == 0) { if (b.reward) b.reward[env] = (float)rw; if (b.done) b.done[env] = done; if (b.truncated) b.truncated[env] = trunc && !done;
+            if (b.step_count) b.step_count[env] = sc; if (b.time) b.time[env] += a.cfg.frame_skip*m.timestep;
+            if (b.ep_return) { float R = b.ep_return[env] + (float)rw; b.ep_return[env] = R; if ((done || trunc) && b.last_return) b.last_return[env] = R; } }
+          __syncwarp();
+          if ((done || trunc) && a.cfg.auto_reset) { env_reset(m, w, a, env); double d2, a2; write_obs_pose(m, w, a, env, &d2, &a2); }
+        } else if (w.lane == 0 && b.time) b.time[env] += a.cfg.frame_skip*m.timestep;
+      }
+      __syncwarp();
+      // ---- store state
+      for (int i = w.lane; i < m.nq; i += 32) b.qpos[(size_t)env*m.nq+i] = w.qpos[i];
+      for (int i = w.lane; i < m.nv; i += 32) { b.qvel[(size_t)env*m.nv+i] = w.qvel[i]; b.qacc_warmstart[(size_t)env*m.nv+i] = w.qws[i]; }
+      for (int i = w.lane; i < m.na; i += 32) b.act[(size_t)env*m.na+i] = w.act[i];
+      __syncwarp();
+    }
   }
 }
 
@@ -185,7 +196,7 @@ extern "C" int myo_model_from_blob(const int32_t* I, int64_t nI, const double* D
   if (I[0] != MYO_BLOB_MAGIC || I[1] != MYO_BLOB_VERSION || I[2] != MYO_NDIM || I[3] != MYO_NSEC) return fail("myo_model_from_blob: blob magic/version/layout mismatch");
   for (int s = 0; s < MYO_NSEC; s++) { long long off = MYO_SEC_OFF(I, s), len = MYO_SEC_LEN(I, s); int kind = I[MYO_BLOB_HDR+MYO_NDIM+3*s];
     if (off < 0 || len < 0 || off + len > (kind ? nD : nI)) return fail("myo_model_from_blob: section out of range"); }
-  if (MYO_SEC_LEN(I, MYO_SEC_P_dims) < 22) return fail("myo_model_from_blob: blob carries no kernel program (pack with program=build_program(m))");
+  if (MYO_SEC_LEN(I, MYO_SEC_P_dims) < 24) return fail("myo_model_from_blob: blob carries no kernel program (pack with program=build_program(m))");
   myo_model* m = new myo_model(); m->I.assign(I, I+nI); m->D.assign(D, D+nD); *out = m; return 0;
 }
 extern "C" void myo_model_destroy(myo_model* m) { delete m; }
@@ -197,7 +208,7 @@ static void fill_devmodel(const myo_model* mm, const myo_task_cfg* cfg, DevModel
   d.nq = MYO_DIM(I, MYO_DIM_nq); d.nv = MYO_DIM(I, MYO_DIM_nv); d.nu = MYO_DIM(I, MYO_DIM_nu); d.na = MYO_DIM(I, MYO_DIM_na); d.nM = MYO_DIM(I, MYO_DIM_nM); d.njnt = MYO_DIM(I, MYO_DIM_njnt);
   const int32_t* P = MYO_ISEC(I, MYO_SEC_P_dims);
   d.nbd = P[PD_NBD]; d.nlevel = P[PD_NLEVEL]; d.nsp = P[PD_NSP]; d.nwe = P[PD_NWE]; d.nta = P[PD_NTA]; d.nnz = P[PD_NNZ]; d.nlim = P[PD_NLIM]; d.neq = P[PD_NEQ];
-  d.npair = P[PD_NPAIR]; d.maxpath = P[PD_MAXPATH];
+  d.npair = P[PD_NPAIR]; d.maxpath = P[PD_MAXPATH]; d.ndepth = P[PD_NDEPTH]; d.eq_tree = P[PD_EQ_TREE];
   const double* opt = MYO_DSEC(I, D, MYO_SEC_opt); d.timestep = opt[0]; d.gx = opt[1]; d.gy = opt[2]; d.gz = opt[3]; d.tolerance = opt[4]; d.meaninertia = opt[6];
   int mc = cfg && cfg->maxcon > 0 ? cfg->maxcon : 32; if (mc > 2*d.npair) mc = 2*d.npair; d.maxcon = mc; d.maxefc = d.neq + 2*d.nlim + 4*mc;
   int o = 0;
@@ -210,7 +221,7 @@ static void fill_devmodel(const myo_model* mm, const myo_task_cfg* cfg, DevModel
   t = 0; d.a_crb = t; t += al2(10*d.nbd); d.a_bf = t; t += al2(6*d.nbd); int sizeC = t;
   t = 0; d.a_H = t; t += al2(d.nv*d.nv); d.a_con = t; t += al2(CON_STRIDE*mc); d.a_conJ = t; t += al2(3*d.maxpath*mc);
   d.a_efD = t; t += al2(d.maxefc); d.a_efA = t; t += al2(d.maxefc); d.a_efR = t; t += al2(d.maxefc); d.a_efV = t; t += al2(d.maxefc);
-  d.a_va = t; t += al2(d.nv); d.a_vg = t; t += al2(d.nv); d.a_vp = t; t += al2(d.nv); d.a_vMa = t; t += al2(d.nv); d.a_vMp = t; t += al2(d.nv); d.a_eqJ = t; t += al2(d.neq);
+  d.a_va = t; t += al2(d.nv); d.a_vg = t; t += al2(d.nv); d.a_vp = t; t += al2(d.nv); d.a_vMa = t; t += al2(d.nv); d.a_vMp = t; t += al2(d.nv); d.a_eqJ = t; t += al2(d.neq); d.a_Hs = t; t += al2(d.nM); d.a_LD = t; t += al2(d.nM); d.a_Dinv = t; t += al2(d.nv);
   d.a_icon = t; t += al2((3*mc + 2*d.nlim + 4 + 1)/2); int sizeS = t;
   int arena = sizeT > sizeC ? sizeT : sizeC; if (sizeS > arena) arena = sizeS;
   d.n_per_warp = o + arena;

@@ -16,7 +16,7 @@
 
 // P_dims slots (must match myosuite_b200/program.py)
 enum { PD_NBD, PD_NLEVEL, PD_NPT, PD_NSP, PD_NWE, PD_NTA, PD_NNZ, PD_NTERM, PD_NLIM, PD_NEQ, PD_NPAIR, PD_NGC, PD_MAXPATH,
-       PD_MAXCHAIN, PD_NSUB, PD_NROW, PD_NCOL, PD_NPIECE, PD_NWE_SPH_OUT, PD_NWE_SPH_IN, PD_NWE_CYL_OUT, PD_NWE_CYL_IN };
+       PD_MAXCHAIN, PD_NSUB, PD_NROW, PD_NCOL, PD_NPIECE, PD_NWE_SPH_OUT, PD_NWE_SPH_IN, PD_NWE_CYL_OUT, PD_NWE_CYL_IN, PD_NDEPTH, PD_EQ_TREE };
 #define PB_STRIDE 18
 #define PWE_STRIDE 16
 #define PA_STRIDE 28
@@ -24,6 +24,7 @@ enum { PD_NBD, PD_NLEVEL, PD_NPT, PD_NSP, PD_NWE, PD_NTA, PD_NNZ, PD_NTERM, PD_N
 #define PPAIR_STRIDE 12
 #define PLIM_STRIDE 12
 #define PEQ_STRIDE 16
+#define PEQ_ISTRIDE 6
 enum { CT_NONE, CT_CAP_CAP, CT_SPH_SPH, CT_SPH_CAP, CT_PLANE_SPH, CT_PLANE_CAP };
 #define CON_STRIDE 14   // dist, pos[3], frame[9], D(common regulariser inverse)
 
@@ -32,7 +33,7 @@ struct DevModel {
   const int32_t* I; const double* D;   // blob in HBM
   int32_t off[MYO_NSEC];               // section offsets
   int32_t nq, nv, nu, na, nM, njnt;
-  int32_t nbd, nlevel, nsp, nwe, nta, nnz, nlim, neq, npair, maxpath;
+  int32_t nbd, nlevel, nsp, nwe, nta, nnz, nlim, neq, npair, maxpath, ndepth, eq_tree;
   int32_t maxcon, maxefc;
   double timestep, gx, gy, gz, meaninertia, tolerance;
   // per-warp shared-memory layout, in doubles
@@ -41,7 +42,7 @@ struct DevModel {
   // arena sub-offsets (relative to arena)
   int32_t a_U, a_WP, a_PL;                 // tendon: unit vectors, wrap points, piece lengths
   int32_t a_crb, a_bf;                     // CRB / RNE
-  int32_t a_H, a_con, a_conJ, a_efD, a_efA, a_efR, a_efV, a_va, a_vg, a_vp, a_vMa, a_vMp, a_eqJ, a_icon;  // solver (a_icon: int region, in doubles)
+  int32_t a_H, a_con, a_conJ, a_efD, a_efA, a_efR, a_efV, a_va, a_vg, a_vp, a_vMa, a_vMp, a_eqJ, a_icon, a_Hs, a_LD, a_Dinv;  // solver (a_icon: int region, in doubles)
 };
 #define ISEC(m, name) ((m).I + (m).off[MYO_SEC_##name])
 #define DSEC(m, name) ((m).D + (m).off[MYO_SEC_##name])

@@ -6,22 +6,23 @@
 #include "myo_device.cuh"
 
 struct Solv {   // arena views
-  double *H, *con, *conJ, *D, *aref, *jar, *jv, *a, *g, *p, *Ma, *Mp, *eqJ;
+  double *H, *con, *conJ, *D, *aref, *jar, *jv, *a, *g, *p, *Ma, *Mp, *eqJ, *Hs, *LD, *Dinv;
   int *cpair, *crow, *cnrow, *lrow;   // contact pair idx, first efc row, #rows ; limit row descriptors (dof | sign bit 16 | limit idx << 17)
 };
 __device__ __forceinline__ Solv solv_views(const DevModel& m, Warp& w) {
   Solv s; double* A = w.arena;
   s.H = A + m.a_H; s.con = A + m.a_con; s.conJ = A + m.a_conJ; s.D = A + m.a_efD; s.aref = A + m.a_efA; s.jar = A + m.a_efR; s.jv = A + m.a_efV;
-  s.a = A + m.a_va; s.g = A + m.a_vg; s.p = A + m.a_vp; s.Ma = A + m.a_vMa; s.Mp = A + m.a_vMp; s.eqJ = A + m.a_eqJ;
+  s.a = A + m.a_va; s.g = A + m.a_vg; s.p = A + m.a_vp; s.Ma = A + m.a_vMa; s.Mp = A + m.a_vMp; s.eqJ = A + m.a_eqJ; s.Hs = A + m.a_Hs; s.LD = A + m.a_LD; s.Dinv = A + m.a_Dinv;
   int* ic = (int*)(A + m.a_icon); s.cpair = ic; s.crow = ic + m.maxcon; s.cnrow = ic + 2*m.maxcon; s.lrow = ic + 3*m.maxcon;
   return s; }
 
-__device__ __forceinline__ double impedance(const double* si, double pos, double margin) {
+__device__ __noinline__ double impedance(const double* si, double pos, double margin) {
   if (si[0] == si[1] || si[2] <= MYO_MINVAL) return 0.5*(si[0]+si[1]);
   double x = fabs((pos-margin)/si[2]);
   if (x >= 1 || x <= 0) return x >= 1 ? si[1] : si[0];
   double y;
   if (si[4] == 1) y = x;
+  else if (si[4] == 2) y = x <= si[3] ? x*x/si[3] : 1-(1-x)*(1-x)/(1-si[3]);   // the default power, without pow()
   else if (x <= si[3]) y = pow(x, si[4])/pow(si[3], si[4]-1);
   else y = 1-pow(1-x, si[4])/pow(1-si[3], si[4]-1);
   return si[0]+y*(si[1]-si[0]); }
@@ -34,7 +35,7 @@ __device__ __forceinline__ void mul_M(const DevModel& m, const Warp& w, double* 
 // out[r] = (J x)_r for every constraint row
 __device__ void rows_apply(const DevModel& m, const Warp& w, const Solv& s, const double* x, double* out) {
   const int* eq = ISEC(m, PEQ);
-  for (int e = w.lane; e < m.neq; e += 32) { double v = x[eq[4*e+1]]; if (eq[4*e+3] >= 0) v += s.eqJ[e]*x[eq[4*e+3]]; out[e] = v; }
+  for (int e = w.lane; e < m.neq; e += 32) { double v = x[eq[PEQ_ISTRIDE*e+1]]; if (eq[PEQ_ISTRIDE*e+3] >= 0) v += s.eqJ[e]*x[eq[PEQ_ISTRIDE*e+3]]; out[e] = v; }
   for (int r = w.lane; r < w.nlimrow; r += 32) { int dsc = s.lrow[r]; double sg = (dsc >> 16) & 1 ? -1.0 : 1.0; out[m.neq + r] = sg*x[dsc & 0xffff]; }
   const int* pr = ISEC(m, PPAIR); const double* pd = DSEC(m, PPAIR_d); const int* path = ISEC(m, PPATH);
   for (int c = w.lane; c < w.ncon; c += 32) { int nr = s.cnrow[c]; if (!nr) continue;
@@ -48,7 +49,7 @@ __device__ void rows_apply(const DevModel& m, const Warp& w, const Solv& s, cons
 // vec[d] += sum_r J[r][d] * wgt[r]  (wgt already includes D and the active mask)
 __device__ void rows_applyT_add(const DevModel& m, const Warp& w, const Solv& s, const double* wgt, double* vec) {
   const int* eq = ISEC(m, PEQ);
-  if (w.lane == 0) for (int e = 0; e < m.neq; e++) { vec[eq[4*e+1]] += wgt[e]; if (eq[4*e+3] >= 0) vec[eq[4*e+3]] += s.eqJ[e]*wgt[e]; }
+  if (w.lane == 0) for (int e = 0; e < m.neq; e++) { vec[eq[PEQ_ISTRIDE*e+1]] += wgt[e]; if (eq[PEQ_ISTRIDE*e+3] >= 0) vec[eq[PEQ_ISTRIDE*e+3]] += s.eqJ[e]*wgt[e]; }
   __syncwarp();
   for (int pass = 0; pass < 2; pass++) {
     for (int r = w.lane; r < w.nlimrow; r += 32) { int dsc = s.lrow[r]; int neg = (dsc >> 16) & 1; if (neg == pass) vec[dsc & 0xffff] += (neg ? -1.0 : 1.0)*wgt[m.neq + r]; }
@@ -67,7 +68,7 @@ __device__ void phase_constraints(const DevModel& m, Warp& w) {
   Solv s = solv_views(m, w);
   // joint equalities (always active)
   const int* eq = ISEC(m, PEQ); const double* eqd = DSEC(m, PEQ_d);
-  for (int e = w.lane; e < m.neq; e += 32) { const double* c = eqd + e*PEQ_STRIDE; int q1 = eq[4*e], d1 = eq[4*e+1], q2 = eq[4*e+2], d2 = eq[4*e+3];
+  for (int e = w.lane; e < m.neq; e += 32) { const double* c = eqd + e*PEQ_STRIDE; int q1 = eq[PEQ_ISTRIDE*e], d1 = eq[PEQ_ISTRIDE*e+1], q2 = eq[PEQ_ISTRIDE*e+2], d2 = eq[PEQ_ISTRIDE*e+3];
     double pos0 = w.qpos[q1]-c[5], cpos, deriv = 0, vel = w.qvel[d1];
     if (q2 >= 0) { double x = w.qpos[q2]-c[6]; cpos = pos0-(c[0]+x*(c[1]+x*(c[2]+x*(c[3]+x*c[4])))); deriv = c[1]+x*(2*c[2]+x*(3*c[3]+x*4*c[4])); vel -= deriv*w.qvel[d2]; }
     else cpos = pos0-c[0];
@@ -137,13 +138,43 @@ __device__ __forceinline__ void load_M_dense(const DevModel& m, const Warp& w, d
   for (int e = w.lane; e < m.nM; e += 32) { int i = mi[e], j = mj[e]; double v = w.qM[e]; if (i == j) v += diag_scale*dofp[2*i+1]; H[i*n+j] = v; H[j*n+i] = v; }
   __syncwarp(); }
 
+// ------------------------------------------------------------------ tree-sparse L'DL (level-scheduled, left-looking) on the qM layout
+// Hs (nM, input) -> LD (nM: D on the diagonal slots, unit-L off-diagonals), Dinv (nv)
+__device__ void ldl_factor(const DevModel& m, const Warp& w, const double* Hs, double* LD, double* Dinv) {
+  const int* fadr = ISEC(m, PFE_adr); const int* fe = ISEC(m, PFE); const int* tadr = ISEC(m, PFT_adr); const int* ft = ISEC(m, PFT);
+  const int* mi = ISEC(m, PM_i); const int* mj = ISEC(m, PM_j); const int* madr = ISEC(m, dof_Madr);
+  for (int lev = m.ndepth-1; lev >= 0; lev--) {
+    for (int t = fadr[lev] + w.lane; t < fadr[lev+1]; t += 32) { int e = fe[t]; double v = Hs[e];
+      for (int q = tadr[t]; q < tadr[t+1]; q++) v -= LD[ft[3*q]]*LD[ft[3*q+1]]*LD[madr[ft[3*q+2]]];
+      LD[e] = v; }
+    __syncwarp();
+    for (int t = fadr[lev] + w.lane; t < fadr[lev+1]; t += 32) { int e = fe[t], k = mi[e];
+      if (k == mj[e]) Dinv[k] = 1.0/LD[e]; else LD[e] /= LD[madr[k]]; }
+    __syncwarp(); }
+}
+// x <- (L'DL)^-1 x
+__device__ void ldl_solve(const DevModel& m, const Warp& w, const double* LD, const double* Dinv, double* x) {
+  const int* ladr = ISEC(m, PLV_adr); const int* lv = ISEC(m, PLV); const int* dadr = ISEC(m, PDS_adr); const int* ds = ISEC(m, PDS);
+  const int* madr = ISEC(m, dof_Madr); const int* mj = ISEC(m, PM_j);
+  for (int lev = m.ndepth-1; lev >= 0; lev--) {
+    for (int t = ladr[lev] + w.lane; t < ladr[lev+1]; t += 32) { int j = lv[t]; double s = x[j];
+      for (int q = dadr[j]; q < dadr[j+1]; q++) s -= LD[ds[2*q+1]]*x[ds[2*q]];
+      x[j] = s; }
+    __syncwarp(); }
+  for (int lev = 0; lev < m.ndepth; lev++) {
+    for (int t = ladr[lev] + w.lane; t < ladr[lev+1]; t += 32) { int i = lv[t]; double s = x[i]*Dinv[i];
+      for (int e = madr[i]+1; e <= madr[i]+lev; e++) s -= LD[e]*x[mj[e]];
+      x[i] = s; }
+    __syncwarp(); }
+}
+
 // ------------------------------------------------------------------ Newton solver: leaves qacc in s.a
 __device__ void phase_solve(const DevModel& m, Warp& w, double tol) {
   Solv s = solv_views(m, w); int n = m.nv, nefc = w.nefc; w.niter = 0;
   if (nefc == 0) {   // unconstrained: qacc = M^-1 qfrc_smooth
-    load_M_dense(m, w, s.H, 0.0); chol_factor(s.H, n, w.lane);
+    ldl_factor(m, w, w.qM, s.LD, s.Dinv);
     for (int i = w.lane; i < n; i += 32) s.a[i] = w.fsm[i]; __syncwarp();
-    chol_solve(s.H, n, s.a, w.lane); return; }
+    ldl_solve(m, w, s.LD, s.Dinv, s.a); return; }
   for (int i = w.lane; i < n; i += 32) s.a[i] = w.qws[i]; __syncwarp();
   mul_M(m, w, s.Ma, s.a); rows_apply(m, w, s, s.a, s.jar); __syncwarp();
   for (int r = w.lane; r < nefc; r += 32) s.jar[r] -= s.aref[r]; __syncwarp();
@@ -156,9 +187,24 @@ __device__ void phase_solve(const DevModel& m, Warp& w, double tol) {
     __syncwarp(); rows_applyT_add(m, w, s, s.jv, s.g); __syncwarp();
     double gn = 0; for (int i = w.lane; i < n; i += 32) gn += s.g[i]*s.g[i]; gn = sqrt(warp_sum(gn));
     if (scale*gn < tol) break;
-    // Hessian
+    // Hessian: tree-sparse L'DL when no contact row is active (limits/equalities keep M's sparsity), dense Cholesky otherwise
+    bool dense = (m.neq > 0 && !m.eq_tree);
+    for (int c = w.lane; c < w.ncon && !dense; c += 32) { int nr = s.cnrow[c], rb = s.crow[c]; for (int r = 0; r < nr; r++) if (s.jar[rb+r] < 0) dense = true; }
+    dense = __any_sync(FULL, dense);
+    for (int i = w.lane; i < n; i += 32) s.p[i] = -s.g[i];
+    __syncwarp();
+    if (!dense) {
+      const int* madr = ISEC(m, dof_Madr);
+      for (int e = w.lane; e < m.nM; e += 32) s.Hs[e] = w.qM[e];
+      __syncwarp();
+      if (w.lane == 0) for (int e = 0; e < m.neq; e++) { int d1 = eq[PEQ_ISTRIDE*e+1], d2 = eq[PEQ_ISTRIDE*e+3]; double De = s.D[e], j2 = s.eqJ[e]; s.Hs[madr[d1]] += De;
+        if (d2 >= 0) { s.Hs[eq[PEQ_ISTRIDE*e+4]] += De*j2; s.Hs[madr[d2]] += De*j2*j2; } }
+      __syncwarp();
+      for (int pass = 0; pass < 2; pass++) { for (int r = w.lane; r < w.nlimrow; r += 32) { int dsc = s.lrow[r]; if (((dsc >> 16) & 1) == pass && s.jar[m.neq+r] < 0) s.Hs[madr[dsc & 0xffff]] += s.D[m.neq+r]; } __syncwarp(); }
+      ldl_factor(m, w, s.Hs, s.LD, s.Dinv); ldl_solve(m, w, s.LD, s.Dinv, s.p);
+    } else {
     load_M_dense(m, w, s.H, 0.0);
-    if (w.lane == 0) for (int e = 0; e < m.neq; e++) { int d1 = eq[4*e+1], d2 = eq[4*e+3]; double De = s.D[e], j2 = s.eqJ[e]; s.H[d1*n+d1] += De;
+    if (w.lane == 0) for (int e = 0; e < m.neq; e++) { int d1 = eq[PEQ_ISTRIDE*e+1], d2 = eq[PEQ_ISTRIDE*e+3]; double De = s.D[e], j2 = s.eqJ[e]; s.H[d1*n+d1] += De;
       if (d2 >= 0) { s.H[d1*n+d2] += De*j2; s.H[d2*n+d1] += De*j2; s.H[d2*n+d2] += De*j2*j2; } }
     __syncwarp();
     for (int pass = 0; pass < 2; pass++) { for (int r = w.lane; r < w.nlimrow; r += 32) { int dsc = s.lrow[r]; if (((dsc >> 16) & 1) == pass && s.jar[m.neq+r] < 0) { int d = dsc & 0xffff; s.H[d*n+d] += s.D[m.neq+r]; } } __syncwarp(); }
@@ -173,8 +219,8 @@ __device__ void phase_solve(const DevModel& m, Warp& w, double tol) {
           s.H[(path[q[3]+ei] >> 1)*n + (path[q[3]+ej] >> 1)] += wa0*b[0]+wa1*b[1]+wa2*b[2]; } }
       __syncwarp(); }
     chol_factor(s.H, n, w.lane);
-    for (int i = w.lane; i < n; i += 32) s.p[i] = -s.g[i]; __syncwarp();
     chol_solve(s.H, n, s.p, w.lane);
+    }
     // exact line search along p
     mul_M(m, w, s.Mp, s.p); rows_apply(m, w, s, s.p, s.jv); __syncwarp();
     double ga = 0, gb = 0; for (int i = w.lane; i < n; i += 32) { ga += s.p[i]*(s.Ma[i]-w.fsm[i]); gb += s.p[i]*s.Mp[i]; } ga = warp_sum(ga); gb = warp_sum(gb);
@@ -198,7 +244,9 @@ __device__ void phase_integrate(const DevModel& m, Warp& w) {
   Solv s = solv_views(m, w); int n = m.nv; double h = m.timestep;
   // (M + h B) qacc' = M qacc  (= qfrc_smooth + qfrc_constraint at the solver optimum)
   mul_M(m, w, s.g, s.a); __syncwarp();
-  load_M_dense(m, w, s.H, h); chol_factor(s.H, n, w.lane); chol_solve(s.H, n, s.g, w.lane);
+  { const int* mi = ISEC(m, PM_i); const int* mj = ISEC(m, PM_j); const double* dofp = DSEC(m, PDOF_d);
+    for (int e = w.lane; e < m.nM; e += 32) { double v = w.qM[e]; if (mi[e] == mj[e]) v += h*dofp[2*mi[e]+1]; s.Hs[e] = v; } __syncwarp(); }
+  ldl_factor(m, w, s.Hs, s.LD, s.Dinv); ldl_solve(m, w, s.LD, s.Dinv, s.g);
   for (int i = w.lane; i < m.na; i += 32) w.act[i] += h*w.actdot[i];
   for (int i = w.lane; i < n; i += 32) { w.qvel[i] += h*s.g[i]; w.qws[i] = s.a[i]; }
   __syncwarp();

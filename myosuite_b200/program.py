@@ -20,7 +20,8 @@ from . import mjmath as mm
 
 # P_dims slots
 (PD_NBD, PD_NLEVEL, PD_NPT, PD_NSP, PD_NWE, PD_NTA, PD_NNZ, PD_NTERM, PD_NLIM, PD_NEQ, PD_NPAIR, PD_NGC, PD_MAXPATH,
- PD_MAXCHAIN, PD_NSUB, PD_NROW, PD_NCOL, PD_NPIECE, PD_NWE_SPH_OUT, PD_NWE_SPH_IN, PD_NWE_CYL_OUT, PD_NWE_CYL_IN) = range(22)
+ PD_MAXCHAIN, PD_NSUB, PD_NROW, PD_NCOL, PD_NPIECE, PD_NWE_SPH_OUT, PD_NWE_SPH_IN, PD_NWE_CYL_OUT, PD_NWE_CYL_IN,
+ PD_NDEPTH, PD_EQ_TREE) = range(24)
 NPDIM = 24
 
 PB_STRIDE, PWE_STRIDE, PA_STRIDE, PG_STRIDE, PPAIR_STRIDE, PLIM_STRIDE, PEQ_STRIDE = 18, 16, 28, 16, 12, 12, 16
@@ -128,6 +129,45 @@ def build_program(m):
         for c, e in sorted(rows[i]):
             PROW_col.append(c); PROW_idx.append(e)
         PROW_adr.append(len(PROW_col))
+
+    # ---- level-scheduled tree-sparse L'DL (left-looking): dofs by depth; per entry the descendant products to gather
+    dpar = m.dof_parentid
+    ddepth = np.zeros(nv, dtype=np.int64)
+    for d in range(nv):
+        ddepth[d] = 0 if dpar[d] < 0 else ddepth[dpar[d]] + 1
+    ndepth = int(ddepth.max()) + 1 if nv else 0
+    anc = {d: [] for d in range(nv)}            # proper ancestors, nearest first
+    for d in range(nv):
+        j = dpar[d]
+        while j >= 0:
+            anc[d].append(int(j)); j = dpar[j]
+    eidx = {}                                   # (i, j) -> index in the qM layout (j ancestor-or-self of i)
+    for i in range(nv):
+        eidx[(i, i)] = int(m.dof_Madr[i])
+        for c, j in enumerate(anc[i]):
+            eidx[(i, j)] = int(m.dof_Madr[i]) + c + 1
+    desc = {d: [] for d in range(nv)}
+    for i in range(nv):
+        for j in anc[i]:
+            desc[j].append(i)
+    PLV_adr, PLV = [0], []
+    for dep in range(ndepth):
+        PLV += [d for d in range(nv) if ddepth[d] == dep]
+        PLV_adr.append(len(PLV))
+    PFE_adr, PFE, PFT_adr, PFT = [0], [], [0], []
+    for dep in range(ndepth):                   # stored ascending; the kernel walks levels deepest-first
+        for k in PLV[PLV_adr[dep]:PLV_adr[dep + 1]]:
+            for j in [k] + anc[k]:
+                PFE.append(eidx[(k, j)])
+                for d_ in desc[k]:
+                    PFT += [eidx[(d_, k)], eidx[(d_, j)], d_]
+                PFT_adr.append(len(PFT) // 3)
+        PFE_adr.append(len(PFE))
+    PDS_adr, PDS = [0], []
+    for j in range(nv):
+        for i in desc[j]:
+            PDS += [i, eidx[(i, j)]]
+        PDS_adr.append(len(PDS) // 2)
 
     def moves(d, b):
         """does dof d move model body b?"""
@@ -321,6 +361,7 @@ def build_program(m):
             PLIM_d.append([m.jnt_range[j, 0], m.jnt_range[j, 1], m.jnt_margin[j], m.dof_invweight0[d], K, B, *si, 0.0])
     # ---- joint equalities
     PEQ, PEQ_d = [], []
+    eq_tree = 1
     for e in range(m.neq):
         if not m.eq_active0[e]:
             continue
@@ -329,7 +370,10 @@ def build_program(m):
         q1, d1 = int(m.jnt_qposadr[j1]), int(m.jnt_dofadr[j1])
         q2, d2 = (int(m.jnt_qposadr[j2]), int(m.jnt_dofadr[j2])) if j2 >= 0 else (-1, -1)
         iw = m.dof_invweight0[d1] + (m.dof_invweight0[d2] if j2 >= 0 else 0.0)
-        PEQ.append([q1, d1, q2, d2])
+        i12 = -1 if j2 < 0 else eidx.get((d1, d2), eidx.get((d2, d1), -2))
+        if i12 == -2:
+            eq_tree = 0
+        PEQ.append([q1, d1, q2, d2, i12 if i12 >= 0 else -1, 0])
         PEQ_d.append([*m.eq_data[e], m.qpos0[q1], m.qpos0[q2] if j2 >= 0 else 0.0, iw, K, B, *si, 0.0])
 
     dims = np.zeros(NPDIM, np.int32)
@@ -339,6 +383,7 @@ def build_program(m):
     dims[PD_MAXPATH], dims[PD_MAXCHAIN], dims[PD_NSUB], dims[PD_NROW], dims[PD_NCOL] = maxpath, maxchain, len(PSUB), len(PROW_col), len(PCOL)
     dims[PD_NPIECE] = len(PT_piece)
     dims[PD_NWE_SPH_OUT], dims[PD_NWE_SPH_IN], dims[PD_NWE_CYL_OUT], dims[PD_NWE_CYL_IN] = counts
+    dims[PD_NDEPTH], dims[PD_EQ_TREE] = ndepth, eq_tree
 
     def ia(x, shape=None):
         a = np.asarray(x, dtype=np.int32)
@@ -361,7 +406,9 @@ def build_program(m):
         "PPAIR": ia(PPAIR).reshape(-1, 6), "PPAIR_d": np.array(PPAIR_d, dtype=np.float64).reshape(-1, PPAIR_STRIDE),
         "PPATH": ia(PPATH),
         "PLIM": ia(PLIM).reshape(-1, 2), "PLIM_d": np.array(PLIM_d, dtype=np.float64).reshape(-1, PLIM_STRIDE),
-        "PEQ": ia(PEQ).reshape(-1, 4), "PEQ_d": np.array(PEQ_d, dtype=np.float64).reshape(-1, PEQ_STRIDE),
+        "PEQ": ia(PEQ).reshape(-1, 6),
+        "PLV_adr": ia(PLV_adr), "PLV": ia(PLV), "PFE_adr": ia(PFE_adr), "PFE": ia(PFE), "PFT_adr": ia(PFT_adr), "PFT": ia(PFT),
+        "PDS_adr": ia(PDS_adr), "PDS": ia(PDS), "PEQ_d": np.array(PEQ_d, dtype=np.float64).reshape(-1, PEQ_STRIDE),
     }
     info = dict(dyn_body_ids=order, act_tendons=act_tendons, pair_model_index=pair_model_index,
                 geom_model_ids={v: k for k, v in gmap.items()})

@@ -11,8 +11,8 @@ _LIB = None
 
 def build(force=False):
     so = os.path.join(_HERE, "libmyo_oracle.so")
-    src = os.path.join(_HERE, "myo_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    deps = [os.path.join(_HERE, "myo_oracle.c"), os.path.join(_HERE, "..", "include", "myo_blob_layout.h")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(d) for d in deps):
         subprocess.check_call(["make", "-s", "-C", _HERE, "-B"])
     return so
 
