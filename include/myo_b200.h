@@ -96,7 +96,8 @@ typedef struct {
   double* tap_contact_dist;  /* [n, maxcon] */
   double* tap_moment;        /* [n, nnz] structural non-zeros of the tendon moment */
   double* tap_qM;            /* [n, nM] */
-  void* reserved[4];
+  long long* tap_phase_cycles; /* [n, 16] SM-clock cycles spent per phase over the whole call (profiling aid; slots 12,13: max ncon / max nefc over substeps) */
+  void* reserved[3];
 } myo_buffers;
 
 const char* myo_last_error(void);

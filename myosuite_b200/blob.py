@@ -12,7 +12,7 @@ kernels stage the hot sections into shared memory with bulk async copies.
 import numpy as np
 
 MAGIC = 0x4D594F42  # 'MYOB'
-VERSION = 4
+VERSION = 5
 
 DIMS = ["nq", "nv", "nu", "na", "nbody", "njnt", "ngeom", "nsite", "ntendon", "nwrap", "nM", "npair", "neq", "nkey",
         "iterations", "ls_iterations"]
@@ -55,13 +55,19 @@ PROGRAM_SECTIONS = [
     ("PPT_body", "i"), ("PPT_xyz", "d"), ("PSP", "i"), ("PWE", "i"), ("PWE_d", "d"),
     ("PT_const", "d"), ("PT_piece_adr", "i"), ("PT_piece", "i"), ("PT_nz_adr", "i"),
     ("PNZ_dof", "i"), ("PNZ_tendon", "i"), ("PNZ_term_adr", "i"), ("PTERM", "i"), ("PCOL_adr", "i"), ("PCOL", "i"),
-    ("PA_tendon", "i"), ("PA_d", "d"),
+    ("PA_tendon", "i"), ("PA_d", "d"), ("PA_cls", "i"), ("PAM_d", "d"),
     # collision / constraints
-    ("PG_body", "i"), ("PG_type", "i"), ("PG_d", "d"), ("PPAIR", "i"), ("PPAIR_d", "d"), ("PPATH", "i"),
+    ("PG_body", "i"), ("PG_type", "i"), ("PG_d", "d"), ("PPAIR", "i"), ("PPAIR_d", "d"), ("PPAIR_tran", "d"), ("PPATH", "i"),
     ("PLIM", "i"), ("PLIM_d", "d"), ("PEQ", "i"), ("PEQ_d", "d"),
     # level-scheduled tree-sparse L'DL
     ("PLV_adr", "i"), ("PLV", "i"), ("PFE_adr", "i"), ("PFE", "i"), ("PFT_adr", "i"), ("PFT", "i"), ("PDS_adr", "i"), ("PDS", "i"),
+    # "hot" copy of everything the kernels read: int lists narrowed to int16 (packed two per int32 word) and the double
+    # tables, each contiguous, staged into shared memory with one bulk async copy per CTA; HOT_off[sec] = offset or -1
+    ("HOT_I16", "i"), ("HOT_D", "d"), ("HOT_off", "i"),
 ]
+
+# sections the kernels read (everything else in the blob is for the host / the oracle)
+KERNEL_RAW = ["jnt_type", "jnt_qposadr", "jnt_dofadr", "dof_Madr", "jnt_pos", "jnt_axis", "jnt_range", "qpos0"]
 
 SECTIONS = RAW_SECTIONS + PROGRAM_SECTIONS
 SEC_ID = {name: i for i, (name, _) in enumerate(SECTIONS)}
@@ -90,11 +96,36 @@ def _raw_arrays(m):
     return a
 
 
+def _hot_pack(arrays):
+    kinds = dict(SECTIONS)
+    names = KERNEL_RAW + [n for n, _ in PROGRAM_SECTIONS if not n.startswith("HOT_") and n != "P_dims"]
+    i16, dd, off = [], [], np.full(len(SECTIONS), -1, dtype=np.int64)
+    ni = nd = 0
+    for n in names:
+        a = np.asarray(arrays.get(n, np.zeros(0)))
+        if kinds[n] == "i":
+            v = a.astype(np.int64).ravel()
+            if v.size and (v.max() > 32767 or v.min() < -32768):
+                raise ValueError("section %s does not fit int16" % n)
+            off[SEC_ID[n]] = ni
+            i16.append(v.astype(np.int16)); ni += v.size
+        else:
+            v = a.astype(np.float64).ravel()
+            off[SEC_ID[n]] = nd
+            dd.append(v); nd += v.size
+    I16 = np.concatenate(i16) if i16 else np.zeros(0, np.int16)
+    I16 = np.concatenate([I16, np.zeros((-I16.size) % 8, np.int16)])          # 16-byte multiple
+    Dh = np.concatenate(dd) if dd else np.zeros(0)
+    Dh = np.concatenate([Dh, np.zeros((-Dh.size) % 2)])
+    return {"HOT_I16": I16.view(np.int32), "HOT_D": Dh, "HOT_off": off}
+
+
 def pack(m, program=None):
     """Model (+ optional program dict name->array) -> (I int32[], D float64[])."""
     arrays = _raw_arrays(m)
     if program:
         arrays.update(program)
+        arrays.update(_hot_pack(arrays))
     dims = [int({"iterations": m.opt_iterations, "ls_iterations": m.opt_ls_iterations}.get(d, getattr(m, d, 0)))
             for d in DIMS]
     head = HDR + len(DIMS) + 3 * len(SECTIONS)

@@ -36,16 +36,17 @@ __device__ __forceinline__ double philox_uniform(Philox& p) {   // [0,1) with 53
   uint32_t a = p.out[4-p.have], b = p.out[5-p.have]; p.have -= 2;
   return ((double)(((unsigned long long)(a >> 5) << 26) | (b >> 6))) * (1.0/9007199254740992.0); }
 
-// ------------------------------------------------------------------ parity taps (values of the forward pass just computed)
-__device__ void write_taps(const DevModel& m, Warp& w, const StepArgs& a, int env) {
+// ------------------------------------------------------------------ parity taps
+__device__ void write_taps_solve(const DevModel& m, Warp& w, const StepArgs& a, int env) {   // after the Newton solve
   Solv s = solv_views(m, w); const myo_buffers& b = a.b;
   if (b.tap_qacc) for (int i = w.lane; i < m.nv; i += 32) b.tap_qacc[(size_t)env*m.nv+i] = s.a[i];
   if (b.tap_qfrc_smooth) for (int i = w.lane; i < m.nv; i += 32) b.tap_qfrc_smooth[(size_t)env*m.nv+i] = w.fsm[i];
-  if (b.tap_actuator_force) for (int i = w.lane; i < m.nu; i += 32) b.tap_actuator_force[(size_t)env*m.nu+i] = w.aforce[i];
-  if (b.tap_ten_length) { const int* at = ISEC(m, PA_tendon); const double* PA = DSEC(m, PA_d); for (int i = w.lane; i < m.nu; i += 32) b.tap_ten_length[(size_t)env*m.nu+i] = PA[i*PA_STRIDE+26]*w.tlen[at[i]]; }
-  if (b.tap_moment) for (int i = w.lane; i < m.nnz; i += 32) b.tap_moment[(size_t)env*m.nnz+i] = w.mom[i];
   if (b.tap_qM) for (int i = w.lane; i < m.nM; i += 32) b.tap_qM[(size_t)env*m.nM+i] = w.qM[i];
   if (b.tap_ncon && w.lane == 0) { int* t = b.tap_ncon + 4*(size_t)env; t[0] = w.ncon; t[1] = w.nefc; t[2] = w.niter; t[3] = w.overflow; }
+  __syncwarp();
+}
+__device__ void write_taps_contacts(const DevModel& m, Warp& w, const StepArgs& a, int env) {   // after constraint assembly (con is overwritten by the solve)
+  Solv s = solv_views(m, w); const myo_buffers& b = a.b;
   if (b.tap_contact_pair) for (int c = w.lane; c < m.maxcon; c += 32) b.tap_contact_pair[(size_t)env*m.maxcon+c] = c < w.ncon ? s.cpair[c] : -1;
   if (b.tap_contact_dist) for (int c = w.lane; c < m.maxcon; c += 32) b.tap_contact_dist[(size_t)env*m.maxcon+c] = c < w.ncon ? s.con[c*CON_STRIDE] : 0.0;
   __syncwarp();
@@ -55,7 +56,7 @@ __device__ void write_taps(const DevModel& m, Warp& w, const StepArgs& a, int en
 __device__ void env_reset(const DevModel& m, Warp& w, const StepArgs& a, int env) {
   const myo_buffers& b = a.b; long long ep = b.episode_count ? b.episode_count[env] : 0;
   Philox rng; philox_init(rng, a.seed, (unsigned long long)(a.env_offset + env), (unsigned long long)ep, (uint32_t)w.lane);
-  const int* jtype = ISEC(m, jnt_type); const int* jq = ISEC(m, jnt_qposadr); const double* jrange = DSEC(m, jnt_range); const double* qpos0 = DSEC(m, qpos0);
+  const idx_t* jtype = CI(jnt_type); const idx_t* jq = CI(jnt_qposadr); const double* jrange = CD(jnt_range); const double* qpos0 = CD(qpos0);
   for (int i = w.lane; i < m.nq; i += 32) w.qpos[i] = b.init_qpos ? b.init_qpos[i] : qpos0[i];
   __syncwarp();
   if (a.cfg.task == MYO_TASK_POSE) {
@@ -89,20 +90,39 @@ __device__ void pose_reward_done(const DevModel& m, Warp& w, const StepArgs& a, 
   *done_out = dist > far_th; }
 
 // ------------------------------------------------------------------ the kernel
-extern "C" __global__ void __launch_bounds__(256) myo_env_kernel(DevModel m, StepArgs a) {
-  extern __shared__ double smem[];
-  int wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  Warp w; w.lane = threadIdx.x & 31;
-  double* base = smem + (size_t)wid*m.n_per_warp;
-  w.qpos = base+m.o_qpos; w.qvel = base+m.o_qvel; w.act = base+m.o_act; w.ctrl = base+m.o_ctrl; w.qws = base+m.o_qws; w.xpos = base+m.o_xpos; w.xquat = base+m.o_xquat;
-  w.xmat = base+m.o_xmat; w.cin = base+m.o_cin; w.dax = base+m.o_dax; w.dan = base+m.o_dan; w.mom = base+m.o_mom; w.tlen = base+m.o_tlen; w.tvel = base+m.o_tvel;
-  w.tfrc = base+m.o_tfrc; w.aforce = base+m.o_aforce; w.actdot = base+m.o_actdot; w.qM = base+m.o_qM; w.fsm = base+m.o_fsm; w.arena = base+m.o_arena;
+extern "C" __global__ void __launch_bounds__(512) myo_env_kernel(const __grid_constant__ DevModel m, const __grid_constant__ StepArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(8) unsigned long long mbar;
+  const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  // ---- stage the model constants into shared memory: bulk async copies (TMA), completion on an mbarrier
+  double* s_d = smem; idx_t* s_i = (idx_t*)(smem + m.nD); double* warp0 = smem + m.nD + (m.nI16w + 1)/2;
+  const unsigned mb = (unsigned)__cvta_generic_to_shared(&mbar);
+  if (threadIdx.x == 0) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mb)); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned bytes_d = (unsigned)m.nD*8u, bytes_i = (unsigned)m.nI16w*4u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(bytes_d + bytes_i) : "memory");
+    const unsigned CH = 32768u;   // chunked: every piece 16-byte aligned and a multiple of 16 bytes
+    for (unsigned o = 0; o < bytes_d; o += CH) { unsigned n = bytes_d - o < CH ? bytes_d - o : CH;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   :: "r"((unsigned)__cvta_generic_to_shared((char*)s_d + o)), "l"((const char*)m.gD + o), "r"(n), "r"(mb) : "memory"); }
+    for (unsigned o = 0; o < bytes_i; o += CH) { unsigned n = bytes_i - o < CH ? bytes_i - o : CH;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   :: "r"((unsigned)__cvta_generic_to_shared((char*)s_i + o)), "l"((const char*)m.gI16 + o), "r"(n), "r"(mb) : "memory"); }
+  }
+  { unsigned done = 0; while (!done) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mb) : "memory"); }
+
+  Warp w; w.lane = threadIdx.x & 31; w.cd = s_d; w.ci = s_i;
+  double* base = warp0 + (size_t)wid*m.n_per_warp;
+  w.qpos = base+m.o_qpos; w.qvel = base+m.o_qvel; w.act = base+m.o_act; w.ctrl = base+m.o_ctrl; w.qws = base+m.o_qws; w.dax = base+m.o_dax; w.dan = base+m.o_dan;
+  w.qM = base+m.o_qM; w.fsm = base+m.o_fsm; w.scr = base+m.o_scr;
   w.ncon = w.nefc = w.nlimrow = w.niter = w.overflow = 0;
   const myo_buffers& b = a.b;
   // All warps of a CTA walk the phases in lockstep (CTA barriers between phases) so that they share instruction fetches:
   // the step is a long, mostly straight-line program and the instruction cache, not the data path, is the scarce resource.
   const int nsub = a.mode == 0 ? a.cfg.frame_skip : (a.mode == 1 ? (a.n_substeps > 0 ? a.n_substeps : 1) : 0);
   const bool integrate = a.mode == 0 || (a.mode == 1 && a.n_substeps > 0);
+  const bool prof = b.tap_phase_cycles != nullptr;
   for (int ebase = blockIdx.x*nw; ebase < a.n_env; ebase += gridDim.x*nw) {
     const int env = ebase + wid; const bool live = env < a.n_env;
     if (live) {
@@ -126,7 +146,7 @@ extern "C" __global__ void __launch_bounds__(256) myo_env_kernel(DevModel m, Ste
           if (a.cfg.reaf_dst != a.cfg.reaf_src && i == a.cfg.reaf_dst) c = (double)b.action[(size_t)env*m.nu+a.cfg.reaf_src];
           if (a.cfg.normalize_act) c = 1.0/(1.0+exp(-5.0*(c-0.5)));
           if (a.cfg.reaf_dst != a.cfg.reaf_src && i == a.cfg.reaf_src) c = 0.0;
-          if (a.cfg.muscle_condition == MYO_COND_FATIGUE && b.fatigue) { double* F = b.fatigue + (size_t)env*3*m.nu; const double* PA = DSEC(m, PA_d) + i*PA_STRIDE;
+          if (a.cfg.muscle_condition == MYO_COND_FATIGUE && b.fatigue) { double* F = b.fatigue + (size_t)env*3*m.nu; const double* PA = CD(PA_d) + CI(PA_cls)[i]*PA_STRIDE;
             double MA = F[i], MR = F[m.nu+i], MF = F[2*m.nu+i], TL = c, fdt = a.dt, tauact = PA[0], taudeact = PA[1];
             const double r = 10*15, Fc = 0.00912, Rc = 0.1*0.00094;
             double LD = 1.0/tauact*(0.5+1.5*MA), LR = (0.5+1.5*MA)/taudeact, C = 0;
@@ -143,18 +163,24 @@ extern "C" __global__ void __launch_bounds__(256) myo_env_kernel(DevModel m, Ste
       __syncwarp();
     }
     // ---- physics substeps: forward dynamics + semi-implicit Euler (the only copy of the phase code in the kernel)
+    long long cyc[8] = {0,0,0,0,0,0,0,0}; int maxcon_seen = 0, maxefc_seen = 0;
+    #define PH(k, stmt) { __syncthreads(); long long t0_ = prof ? clock64() : 0; if (live) { stmt; } if (prof) cyc[k] += clock64() - t0_; }
     #pragma unroll 1
     for (int s = 0; s < nsub; s++) {
-      __syncthreads(); if (live) phase_kinematics(m, w);
-      __syncthreads(); if (live) phase_tendon(m, w);
-      __syncthreads(); if (live) phase_actuation(m, w);
-      __syncthreads(); if (live) { phase_crb(m, w); phase_bias(m, w); }
-      __syncthreads(); if (live) phase_collision(m, w);
-      __syncthreads(); if (live) phase_constraints(m, w);
-      __syncthreads(); if (live) phase_solve(m, w, a.tol);
-      __syncthreads();
-      if (live) { if (s == nsub-1) write_taps(m, w, a, env); if (integrate) phase_integrate(m, w); }
+      const bool tap = s == nsub-1;
+      PH(0, phase_kinematics(m, w));
+      PH(1, phase_tendon(m, w); if (tap && b.tap_moment) { const double* mom = SCR(s_mom); for (int i = w.lane; i < m.nnz; i += 32) b.tap_moment[(size_t)env*m.nnz+i] = mom[i]; });
+      PH(2, phase_actuation(m, w, integrate, tap && b.tap_actuator_force ? b.tap_actuator_force + (size_t)env*m.nu : nullptr, tap && b.tap_ten_length ? b.tap_ten_length + (size_t)env*m.nu : nullptr));
+      PH(3, phase_body_inertia(m, w); phase_crb(m, w); phase_bias(m, w));
+      PH(4, phase_collision(m, w));
+      PH(5, phase_constraints(m, w); if (tap) write_taps_contacts(m, w, a, env));
+      PH(6, phase_solve(m, w, a.tol));
+      PH(7, if (tap) write_taps_solve(m, w, a, env); if (integrate) phase_integrate(m, w));
+      if (w.ncon > maxcon_seen) maxcon_seen = w.ncon;
+      if (w.nefc > maxefc_seen) maxefc_seen = w.nefc;
     }
+    #undef PH
+    if (prof && live && w.lane == 0) { long long* pc = b.tap_phase_cycles + 16*(size_t)env; for (int k = 0; k < 8; k++) pc[k] = cyc[k]; pc[12] = maxcon_seen; pc[13] = maxefc_seen; }
     if (live) {
       if (a.mode == 1) { if (integrate && w.lane == 0 && b.time) b.time[env] += nsub*m.timestep; }
       else if (a.mode == 0) {
@@ -185,7 +211,7 @@ static int fail(const std::string& s) { g_err = s; return -1; }
 #define CUDA_OK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
 
 struct myo_model { std::vector<int32_t> I; std::vector<double> D; };
-struct myo_batch { const myo_model* model; int device, n_env; myo_task_cfg cfg; myo_buffers bufs; bool bound; DevModel dm; int32_t* dI; double* dD;
+struct myo_batch { const myo_model* model; int device, n_env; myo_task_cfg cfg; myo_buffers bufs; bool bound; DevModel dm; int32_t* dI; double* dD; int const_bytes;
   int warps_per_cta, grid, smem_bytes, obs_dim; long long launches; unsigned long long seed; long long env_offset; };
 
 extern "C" const char* myo_last_error(void) { return g_err.c_str(); }
@@ -196,15 +222,18 @@ extern "C" int myo_model_from_blob(const int32_t* I, int64_t nI, const double* D
   if (I[0] != MYO_BLOB_MAGIC || I[1] != MYO_BLOB_VERSION || I[2] != MYO_NDIM || I[3] != MYO_NSEC) return fail("myo_model_from_blob: blob magic/version/layout mismatch");
   for (int s = 0; s < MYO_NSEC; s++) { long long off = MYO_SEC_OFF(I, s), len = MYO_SEC_LEN(I, s); int kind = I[MYO_BLOB_HDR+MYO_NDIM+3*s];
     if (off < 0 || len < 0 || off + len > (kind ? nD : nI)) return fail("myo_model_from_blob: section out of range"); }
-  if (MYO_SEC_LEN(I, MYO_SEC_P_dims) < 24) return fail("myo_model_from_blob: blob carries no kernel program (pack with program=build_program(m))");
+  if (MYO_SEC_LEN(I, MYO_SEC_P_dims) < 24 || MYO_SEC_LEN(I, MYO_SEC_HOT_off) != MYO_NSEC) return fail("myo_model_from_blob: blob carries no kernel program (pack with program=build_program(m))");
   myo_model* m = new myo_model(); m->I.assign(I, I+nI); m->D.assign(D, D+nD); *out = m; return 0;
 }
 extern "C" void myo_model_destroy(myo_model* m) { delete m; }
 
 static int al2(int x) { return (x + 1) & ~1; }
+static int imax(int a, int b) { return a > b ? a : b; }
 static void fill_devmodel(const myo_model* mm, const myo_task_cfg* cfg, DevModel& d) {
   const int32_t* I = mm->I.data(); const double* D = mm->D.data(); memset(&d, 0, sizeof(d));
-  for (int s = 0; s < MYO_NSEC; s++) d.off[s] = MYO_SEC_OFF(I, s);
+  const int32_t* hoff = MYO_ISEC(I, MYO_SEC_HOT_off);
+  for (int s = 0; s < MYO_NSEC; s++) d.hoff[s] = hoff[s];
+  d.nI16w = MYO_SEC_LEN(I, MYO_SEC_HOT_I16); d.nD = MYO_SEC_LEN(I, MYO_SEC_HOT_D);
   d.nq = MYO_DIM(I, MYO_DIM_nq); d.nv = MYO_DIM(I, MYO_DIM_nv); d.nu = MYO_DIM(I, MYO_DIM_nu); d.na = MYO_DIM(I, MYO_DIM_na); d.nM = MYO_DIM(I, MYO_DIM_nM); d.njnt = MYO_DIM(I, MYO_DIM_njnt);
   const int32_t* P = MYO_ISEC(I, MYO_SEC_P_dims);
   d.nbd = P[PD_NBD]; d.nlevel = P[PD_NLEVEL]; d.nsp = P[PD_NSP]; d.nwe = P[PD_NWE]; d.nta = P[PD_NTA]; d.nnz = P[PD_NNZ]; d.nlim = P[PD_NLIM]; d.neq = P[PD_NEQ];
@@ -213,24 +242,35 @@ static void fill_devmodel(const myo_model* mm, const myo_task_cfg* cfg, DevModel
   int mc = cfg && cfg->maxcon > 0 ? cfg->maxcon : 32; if (mc > 2*d.npair) mc = 2*d.npair; d.maxcon = mc; d.maxefc = d.neq + 2*d.nlim + 4*mc;
   int o = 0;
   #define TAKE(field, n) d.field = o; o += al2(n)
-  TAKE(o_qpos, d.nq); TAKE(o_qvel, d.nv); TAKE(o_act, d.na); TAKE(o_ctrl, d.nu); TAKE(o_qws, d.nv); TAKE(o_xpos, 3*d.nbd); TAKE(o_xquat, 4*d.nbd); TAKE(o_xmat, 9*d.nbd);
-  TAKE(o_cin, 10*d.nbd); TAKE(o_dax, 3*d.nv); TAKE(o_dan, 3*d.nv); TAKE(o_mom, d.nnz); TAKE(o_tlen, d.nta); TAKE(o_tvel, d.nta); TAKE(o_tfrc, d.nta);
-  TAKE(o_aforce, d.nu); TAKE(o_actdot, d.na); TAKE(o_qM, d.nM); TAKE(o_fsm, d.nv); TAKE(o_arena, 0);
+  TAKE(o_qpos, d.nq); TAKE(o_qvel, d.nv); TAKE(o_act, d.na); TAKE(o_ctrl, d.nu); TAKE(o_qws, d.nv); TAKE(o_dax, 3*d.nv); TAKE(o_dan, 3*d.nv); TAKE(o_qM, d.nM); TAKE(o_fsm, d.nv);
+  d.o_scr = o;
   #undef TAKE
-  int t = 0; d.a_U = t; t += al2(3*(d.nsp+2*d.nwe)); d.a_WP = t; t += al2(6*d.nwe); d.a_PL = t; t += al2(d.nsp+d.nwe); int sizeT = t;
-  t = 0; d.a_crb = t; t += al2(10*d.nbd); d.a_bf = t; t += al2(6*d.nbd); int sizeC = t;
-  t = 0; d.a_H = t; t += al2(d.nv*d.nv); d.a_con = t; t += al2(CON_STRIDE*mc); d.a_conJ = t; t += al2(3*d.maxpath*mc);
-  d.a_efD = t; t += al2(d.maxefc); d.a_efA = t; t += al2(d.maxefc); d.a_efR = t; t += al2(d.maxefc); d.a_efV = t; t += al2(d.maxefc);
-  d.a_va = t; t += al2(d.nv); d.a_vg = t; t += al2(d.nv); d.a_vp = t; t += al2(d.nv); d.a_vMa = t; t += al2(d.nv); d.a_vMp = t; t += al2(d.nv); d.a_eqJ = t; t += al2(d.neq); d.a_Hs = t; t += al2(d.nM); d.a_LD = t; t += al2(d.nM); d.a_Dinv = t; t += al2(d.nv);
-  d.a_icon = t; t += al2((3*mc + 2*d.nlim + 4 + 1)/2); int sizeS = t;
-  int arena = sizeT > sizeC ? sizeT : sizeC; if (sizeS > arena) arena = sizeS;
-  d.n_per_warp = o + arena;
+  // ---- scratch, time-multiplexed.  Lifetimes:
+  //   K  (xpos,xmat)                       kinematics .. constraints           -> parked at the END of the scratch
+  //   T  (U,WP,PL,mom,tlen,tvel,tfrc)      tendon .. actuation                 -> from 0
+  //   C  (cin,crb,bf)                      body inertia .. bias                -> from 0
+  //   S3 (conJ,D,aref,eqJ,icon)            collision/constraints .. solve      -> from 0   (T and C are dead by then)
+  //   con                                  collision .. constraints            -> right after S3 (overwritten by the solve vectors)
+  //   S4 (jar,jv,a,g,p,Ma,Mp,H|Hs,LD,Dinv) solve .. integrate                  -> right after S3 (may overwrite con and K)
+  int K = al2(3*d.nbd) + al2(9*d.nbd);
+  int t = 0; d.s_U = t; t += al2(3*(d.nsp+2*d.nwe)); d.s_WP = t; t += al2(6*d.nwe); d.s_PL = t; t += al2(d.nsp+d.nwe); d.s_mom = t; t += al2(d.nnz);
+  d.s_tlen = t; t += al2(d.nta); d.s_tvel = t; t += al2(d.nta); d.s_tfrc = t; t += al2(d.nta); int sizeT = t;
+  t = 0; d.s_cin = t; t += al2(10*d.nbd); d.s_crb = t; t += al2(10*d.nbd); d.s_bf = t; t += al2(6*d.nbd); int sizeC = t;
+  t = 0; d.s_conJ = t; t += al2(3*d.maxpath*mc); d.s_efD = t; t += al2(d.maxefc); d.s_efA = t; t += al2(d.maxefc); d.s_eqJ = t; t += al2(d.neq);
+  d.s_icon = t; t += al2((3*mc + 2*d.nlim + 4 + 1)/2); int sizeS3 = t;
+  d.s_con = sizeS3; int sizeCon = al2(CON_STRIDE*mc);
+  t = sizeS3; d.s_efR = t; t += al2(d.maxefc); d.s_efV = t; t += al2(d.maxefc); d.s_va = t; t += al2(d.nv); d.s_vg = t; t += al2(d.nv); d.s_vp = t; t += al2(d.nv);
+  d.s_vMa = t; t += al2(d.nv); d.s_vMp = t; t += al2(d.nv);
+  d.s_H = t; d.s_Hs = t; d.s_LD = t + al2(d.nM); d.s_Dinv = t + 2*al2(d.nM); t += imax(al2(d.nv*d.nv), 2*al2(d.nM) + al2(d.nv)); int sizeS4 = t;
+  int scratch = imax(imax(sizeT, sizeC) + K, imax(sizeS3 + sizeCon + K, sizeS4));
+  d.s_xpos = scratch - K; d.s_xmat = d.s_xpos + al2(3*d.nbd);
+  d.n_per_warp = d.o_scr + scratch;
 }
 
 extern "C" int myo_model_dims(const myo_model* m, const myo_task_cfg* cfg, myo_dims* out) {
   if (!m || !out) return fail("myo_model_dims: null"); DevModel d; fill_devmodel(m, cfg, d); const int32_t* I = m->I.data();
   memset(out, 0, sizeof(*out)); out->nq = d.nq; out->nv = d.nv; out->nu = d.nu; out->na = d.na; out->nbody = MYO_DIM(I, MYO_DIM_nbody); out->njnt = d.njnt; out->ntendon = MYO_DIM(I, MYO_DIM_ntendon);
-  out->nM = d.nM; out->npair = d.npair; out->nta = d.nta; out->maxcon = d.maxcon; out->maxefc = d.maxefc; out->smem_bytes_per_env = d.n_per_warp*8; out->reserved[0] = d.nnz; return 0;
+  out->nM = d.nM; out->npair = d.npair; out->nta = d.nta; out->maxcon = d.maxcon; out->maxefc = d.maxefc; out->smem_bytes_per_env = d.n_per_warp*8; out->reserved[0] = d.nnz; out->reserved[1] = d.nD*8 + ((d.nI16w + 1)/2)*8; return 0;
 }
 
 extern "C" int myo_batch_create(const myo_model* m, int device, int n_env, const myo_task_cfg* cfg, myo_batch** out) {
@@ -244,16 +284,19 @@ extern "C" int myo_batch_create(const myo_model* m, int device, int n_env, const
   if (b->cfg.frame_skip <= 0) b->cfg.frame_skip = 1;
   if (cfg->task == MYO_TASK_POSE && b->dm.nq != b->dm.nv) { delete b; return fail("pose task needs nq == nv"); }
   b->obs_dim = cfg->task == MYO_TASK_POSE ? 2*b->dm.nq + b->dm.nv + b->dm.na : 0;
-  CUDA_OK(cudaMalloc(&b->dI, m->I.size()*4)); CUDA_OK(cudaMalloc(&b->dD, (m->D.size() ? m->D.size() : 1)*8));
-  CUDA_OK(cudaMemcpy(b->dI, m->I.data(), m->I.size()*4, cudaMemcpyHostToDevice)); CUDA_OK(cudaMemcpy(b->dD, m->D.data(), m->D.size()*8, cudaMemcpyHostToDevice));
-  b->dm.I = b->dI; b->dm.D = b->dD;
+  { const int32_t* I = m->I.data(); const double* D = m->D.data();
+    size_t nI = (size_t)b->dm.nI16w*4, nD = (size_t)b->dm.nD*8;
+    CUDA_OK(cudaMalloc(&b->dI, nI ? nI : 16)); CUDA_OK(cudaMalloc(&b->dD, nD ? nD : 16));
+    CUDA_OK(cudaMemcpy(b->dI, MYO_ISEC(I, MYO_SEC_HOT_I16), nI, cudaMemcpyHostToDevice)); CUDA_OK(cudaMemcpy(b->dD, MYO_DSEC(I, D, MYO_SEC_HOT_D), nD, cudaMemcpyHostToDevice)); }
+  b->dm.gI16 = b->dI; b->dm.gD = b->dD;
   cudaDeviceProp prop; CUDA_OK(cudaGetDeviceProperties(&prop, device));
-  int per = b->dm.n_per_warp*8, maxs = (int)prop.sharedMemPerBlockOptin;
-  int wpc = maxs/per; if (wpc > 8) wpc = 8; if (wpc < 1) { delete b; return fail("model working set exceeds shared memory of one CTA"); }
-  b->warps_per_cta = wpc; b->smem_bytes = wpc*per;
+  b->const_bytes = b->dm.nD*8 + ((b->dm.nI16w + 1)/2)*8;
+  int per = b->dm.n_per_warp*8, maxs = (int)prop.sharedMemPerBlockOptin - b->const_bytes - 64;
+  int wpc = maxs/per; if (wpc > 16) wpc = 16; if (wpc < 1) { delete b; return fail("model working set exceeds shared memory of one CTA"); }
+  if (n_env < wpc) wpc = n_env;
+  b->warps_per_cta = wpc; b->smem_bytes = b->const_bytes + wpc*per;
   CUDA_OK(cudaFuncSetAttribute(myo_env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes));
-  int ctas_per_sm = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, myo_env_kernel, wpc*32, b->smem_bytes); if (ctas_per_sm < 1) ctas_per_sm = 1;
-  int need = (n_env + wpc - 1)/wpc, cap = prop.multiProcessorCount*ctas_per_sm; b->grid = need < cap ? need : cap;
+  int need = (n_env + wpc - 1)/wpc, cap = prop.multiProcessorCount; b->grid = need < cap ? need : cap;
   *out = b; return 0;
 }
 extern "C" void myo_batch_destroy(myo_batch* b) { if (!b) return; cudaSetDevice(b->device); cudaFree(b->dI); cudaFree(b->dD); delete b; }

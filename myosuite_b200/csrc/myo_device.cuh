@@ -1,11 +1,13 @@
 // myo_device.cuh -- device-side physics of the B200-native batched musculoskeletal simulator.
 //
 // One env per warp.  Every phase is a lane-strided loop over a list from the model "program"
-// (myosuite_b200/program.py); per-env working state lives in shared memory (f64).
+// (myosuite_b200/program.py).  Both the per-env working state (f64) AND the model constants the phases
+// read (int16 index lists + f64 tables, staged once per CTA with a bulk async copy) live in shared
+// memory; HBM is touched only for the per-step state / action / observation rows.
 // What is computed is what the reference's mujoco.mj_step computes for these models
 // (/root/reference/myosuite/robot/robot.py:856-861), but the formulation is
 // this project's own: origin-centred spatial algebra over dynamic bodies only, compile-time folded
-// constant tendon segments, structural-non-zero tendon moments, dense Newton on H = M + J'DJ.
+// constant tendon segments, structural-non-zero tendon moments, tree-sparse LDL / dense Newton.
 #pragma once
 #include <stdint.h>
 #include "../../include/myo_blob_layout.h"
@@ -13,46 +15,52 @@
 
 #define MYO_MINVAL 1e-15
 #define FULL 0xffffffffu
+typedef short idx_t;
 
 // P_dims slots (must match myosuite_b200/program.py)
 enum { PD_NBD, PD_NLEVEL, PD_NPT, PD_NSP, PD_NWE, PD_NTA, PD_NNZ, PD_NTERM, PD_NLIM, PD_NEQ, PD_NPAIR, PD_NGC, PD_MAXPATH,
        PD_MAXCHAIN, PD_NSUB, PD_NROW, PD_NCOL, PD_NPIECE, PD_NWE_SPH_OUT, PD_NWE_SPH_IN, PD_NWE_CYL_OUT, PD_NWE_CYL_IN, PD_NDEPTH, PD_EQ_TREE };
-#define PB_STRIDE 18
+#define PB_STRIDE 22      // pos[3] R[9] ipos[3] mass Iloc[6]
 #define PWE_STRIDE 16
 #define PA_STRIDE 28
+#define PAM_STRIDE 6
 #define PG_STRIDE 16
 #define PPAIR_STRIDE 12
+#define PPAIR_ISTRIDE 7
 #define PLIM_STRIDE 12
 #define PEQ_STRIDE 16
 #define PEQ_ISTRIDE 6
 enum { CT_NONE, CT_CAP_CAP, CT_SPH_SPH, CT_SPH_CAP, CT_PLANE_SPH, CT_PLANE_CAP };
-#define CON_STRIDE 14   // dist, pos[3], frame[9], D(common regulariser inverse)
+#define CON_STRIDE 14   // dist, pos[3], frame[9], pad
 
-// ------------------------------------------------------------------ device-resident model view
+// ------------------------------------------------------------------ device-resident model view (kernel parameter)
 struct DevModel {
-  const int32_t* I; const double* D;   // blob in HBM
-  int32_t off[MYO_NSEC];               // section offsets
+  const int32_t* gI16; const double* gD;   // hot constant arrays in HBM (source of the per-CTA staging copy)
+  int32_t nI16w, nD;                       // sizes: int32 words of packed int16, doubles
+  int32_t hoff[MYO_NSEC];                  // offset of each hot section (in shorts / doubles), -1 if not staged
   int32_t nq, nv, nu, na, nM, njnt;
   int32_t nbd, nlevel, nsp, nwe, nta, nnz, nlim, neq, npair, maxpath, ndepth, eq_tree;
   int32_t maxcon, maxefc;
   double timestep, gx, gy, gz, meaninertia, tolerance;
-  // per-warp shared-memory layout, in doubles
-  int32_t o_qpos, o_qvel, o_act, o_ctrl, o_qws, o_xpos, o_xquat, o_xmat, o_cin, o_dax, o_dan, o_mom, o_tlen, o_tvel,
-      o_tfrc, o_aforce, o_actdot, o_qM, o_fsm, o_arena, n_per_warp;
-  // arena sub-offsets (relative to arena)
-  int32_t a_U, a_WP, a_PL;                 // tendon: unit vectors, wrap points, piece lengths
-  int32_t a_crb, a_bf;                     // CRB / RNE
-  int32_t a_H, a_con, a_conJ, a_efD, a_efA, a_efR, a_efV, a_va, a_vg, a_vp, a_vMa, a_vMp, a_eqJ, a_icon, a_Hs, a_LD, a_Dinv;  // solver (a_icon: int region, in doubles)
+  // per-warp shared-memory layout, in doubles.  Persistent part:
+  int32_t o_qpos, o_qvel, o_act, o_ctrl, o_qws, o_dax, o_dan, o_qM, o_fsm, o_scr, n_per_warp;
+  // scratch (time-multiplexed by stage; offsets relative to o_scr).  See fill_devmodel() for the overlap rules.
+  int32_t s_xpos, s_xmat;                                  // K: body poses, alive kinematics .. constraints
+  int32_t s_U, s_WP, s_PL, s_mom, s_tlen, s_tvel, s_tfrc;  // stage 1: tendons + actuation
+  int32_t s_cin, s_crb, s_bf;                              // stage 2: CRB / bias
+  int32_t s_conJ, s_efD, s_efA, s_eqJ, s_icon, s_con;      // stage 3 -> 4: contacts / constraint rows
+  int32_t s_efR, s_efV, s_va, s_vg, s_vp, s_vMa, s_vMp, s_H, s_Hs, s_LD, s_Dinv;   // stage 4: Newton
 };
-#define ISEC(m, name) ((m).I + (m).off[MYO_SEC_##name])
-#define DSEC(m, name) ((m).D + (m).off[MYO_SEC_##name])
 
-struct Warp {   // per-warp pointers into shared memory
-  double *qpos, *qvel, *act, *ctrl, *qws, *xpos, *xquat, *xmat, *cin, *dax, *dan, *mom, *tlen, *tvel, *tfrc, *aforce, *actdot, *qM,
-      *fsm, *arena;
+struct Warp {   // per-warp view (registers)
+  double *qpos, *qvel, *act, *ctrl, *qws, *dax, *dan, *qM, *fsm, *scr;
+  const double* cd; const idx_t* ci;   // staged constants
   int lane;
   int ncon, nefc, nlimrow, niter, overflow;
 };
+#define CI(name) (w.ci + m.hoff[MYO_SEC_##name])
+#define CD(name) (w.cd + m.hoff[MYO_SEC_##name])
+#define SCR(field) (w.scr + m.field)
 
 // ------------------------------------------------------------------ small math
 __device__ __forceinline__ void cross3(double* r, const double* a, const double* b) {
@@ -74,6 +82,9 @@ __device__ __forceinline__ void mat_vec(double* r, const double* m, const double
   double x=m[0]*v[0]+m[1]*v[1]+m[2]*v[2], y=m[3]*v[0]+m[4]*v[1]+m[5]*v[2], z=m[6]*v[0]+m[7]*v[1]+m[8]*v[2]; r[0]=x; r[1]=y; r[2]=z; }
 __device__ __forceinline__ void matT_vec(double* r, const double* m, const double* v) {
   double x=m[0]*v[0]+m[3]*v[1]+m[6]*v[2], y=m[1]*v[0]+m[4]*v[1]+m[7]*v[2], z=m[2]*v[0]+m[5]*v[1]+m[8]*v[2]; r[0]=x; r[1]=y; r[2]=z; }
+__device__ __forceinline__ void mat_mul(double* r, const double* a, const double* b) {   // r = a*b (3x3, row-major), r may not alias
+  #pragma unroll
+  for (int i = 0; i < 3; i++) { r[3*i] = a[3*i]*b[0]+a[3*i+1]*b[3]+a[3*i+2]*b[6]; r[3*i+1] = a[3*i]*b[1]+a[3*i+1]*b[4]+a[3*i+2]*b[7]; r[3*i+2] = a[3*i]*b[2]+a[3*i+1]*b[5]+a[3*i+2]*b[8]; } }
 __device__ __forceinline__ double clipd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 __device__ __forceinline__ double warp_sum(double v) {
   #pragma unroll
@@ -82,19 +93,19 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // world position of program point `pt`
 __device__ __forceinline__ void world_point(const DevModel& m, const Warp& w, int pt, double* out) {
-  int b = ISEC(m, PPT_body)[pt]; const double* x = DSEC(m, PPT_xyz) + 3*pt;
+  int b = CI(PPT_body)[pt]; const double* x = CD(PPT_xyz) + 3*pt;
   if (b < 0) { out[0]=x[0]; out[1]=x[1]; out[2]=x[2]; }
-  else { mat_vec(out, w.xmat + 9*b, x); out[0]+=w.xpos[3*b]; out[1]+=w.xpos[3*b+1]; out[2]+=w.xpos[3*b+2]; } }
+  else { const double* xp = SCR(s_xpos) + 3*b; mat_vec(out, SCR(s_xmat) + 9*b, x); out[0]+=xp[0]; out[1]+=xp[1]; out[2]+=xp[2]; } }
 
 // spatial motion vector of dof d about the world origin: [omega ; velocity of the point at the origin]
 __device__ __forceinline__ void dof_motion(const DevModel& m, const Warp& w, int d, double* S) {
   const double* ax = w.dax + 3*d;
-  if (ISEC(m, PD_lin)[d]) { S[0]=S[1]=S[2]=0; S[3]=ax[0]; S[4]=ax[1]; S[5]=ax[2]; }
+  if (CI(PD_lin)[d]) { S[0]=S[1]=S[2]=0; S[3]=ax[0]; S[4]=ax[1]; S[5]=ax[2]; }
   else { S[0]=ax[0]; S[1]=ax[1]; S[2]=ax[2]; cross3(S+3, w.dan + 3*d, ax); } }
 // velocity of world point p due to unit rate of dof d
 __device__ __forceinline__ void dof_point_vel(const DevModel& m, const Warp& w, int d, const double* p, double* c) {
   const double* ax = w.dax + 3*d;
-  if (ISEC(m, PD_lin)[d]) { c[0]=ax[0]; c[1]=ax[1]; c[2]=ax[2]; }
+  if (CI(PD_lin)[d]) { c[0]=ax[0]; c[1]=ax[1]; c[2]=ax[2]; }
   else { double r[3] = {p[0]-w.dan[3*d], p[1]-w.dan[3*d+1], p[2]-w.dan[3*d+2]}; cross3(c, ax, r); } }
 // f = Ic * S for a spatial inertia about the origin: Ic = (Ixx,Iyy,Izz,Ixy,Ixz,Iyz, m*c[3], m)
 __device__ __forceinline__ void inert_mul(double* f, const double* ic, const double* S) {
@@ -103,59 +114,69 @@ __device__ __forceinline__ void inert_mul(double* f, const double* ic, const dou
   cross3(t, mc, v); f[0]+=t[0]; f[1]+=t[1]; f[2]+=t[2];
   cross3(t, wv, mc); f[3] = ic[9]*v[0]+t[0]; f[4] = ic[9]*v[1]+t[1]; f[5] = ic[9]*v[2]+t[2]; }
 
-// ------------------------------------------------------------------ phase 1: kinematics
+// ------------------------------------------------------------------ phase 1: kinematics (rotation matrices, level by level)
+// also writes each dynamic body's spatial inertia about the world origin (cin) into the stage-2 scratch
 __device__ void phase_kinematics(const DevModel& m, Warp& w) {
-  const int* level = ISEC(m, PB_level_adr); const int* par = ISEC(m, PB_parent); const int* jadr = ISEC(m, PB_jadr); const int* jnum = ISEC(m, PB_jnum);
-  const double* PB = DSEC(m, PB_d);
-  const int* jtype = ISEC(m, jnt_type); const int* jq = ISEC(m, jnt_qposadr); const int* jd = ISEC(m, jnt_dofadr);
-  const double* jpos = DSEC(m, jnt_pos); const double* jaxis = DSEC(m, jnt_axis); const double* qpos0 = DSEC(m, qpos0);
+  const idx_t* level = CI(PB_level_adr); const idx_t* par = CI(PB_parent); const idx_t* jadr = CI(PB_jadr); const idx_t* jnum = CI(PB_jnum);
+  const double* PB = CD(PB_d);
+  const idx_t* jtype = CI(jnt_type); const idx_t* jq = CI(jnt_qposadr); const idx_t* jd = CI(jnt_dofadr);
+  const double* jpos = CD(jnt_pos); const double* jaxis = CD(jnt_axis); const double* qpos0 = CD(qpos0);
+  double* xpos = SCR(s_xpos); double* xmat = SCR(s_xmat);
   for (int L = 0; L < m.nlevel; L++) {
     for (int k = level[L] + w.lane; k < level[L+1]; k += 32) {
-      const double* bd = PB + k*PB_STRIDE; int p = par[k]; double pos[3], quat[4], R[9];
-      if (p < 0) { pos[0]=bd[0]; pos[1]=bd[1]; pos[2]=bd[2]; quat[0]=bd[3]; quat[1]=bd[4]; quat[2]=bd[5]; quat[3]=bd[6]; }
-      else { mat_vec(pos, w.xmat + 9*p, bd); pos[0]+=w.xpos[3*p]; pos[1]+=w.xpos[3*p+1]; pos[2]+=w.xpos[3*p+2]; quat_mul(quat, w.xquat + 4*p, bd + 3); }
+      const double* bd = PB + k*PB_STRIDE; int p = par[k]; double pos[3], R[9];
+      if (p < 0) { pos[0]=bd[0]; pos[1]=bd[1]; pos[2]=bd[2];
+        #pragma unroll
+        for (int c = 0; c < 9; c++) R[c] = bd[3+c]; }
+      else { mat_vec(pos, xmat + 9*p, bd); pos[0]+=xpos[3*p]; pos[1]+=xpos[3*p+1]; pos[2]+=xpos[3*p+2]; mat_mul(R, xmat + 9*p, bd + 3); }
       for (int j = jadr[k]; j < jadr[k] + jnum[k]; j++) {
         int t = jtype[j], qa = jq[j], da = jd[j];
-        if (t == 0) {   // free
+        if (t == 0) {   // free joint: pose straight from qpos (quaternion normalised in place, as mj_kinematics does)
           double* qp = w.qpos + qa; quat_norm(qp + 3);
-          pos[0]=qp[0]; pos[1]=qp[1]; pos[2]=qp[2]; quat[0]=qp[3]; quat[1]=qp[4]; quat[2]=qp[5]; quat[3]=qp[6];
-          quat2mat(R, quat);
+          pos[0]=qp[0]; pos[1]=qp[1]; pos[2]=qp[2]; quat2mat(R, qp + 3);
           for (int c = 0; c < 3; c++) {
             w.dax[3*(da+c)] = c==0; w.dax[3*(da+c)+1] = c==1; w.dax[3*(da+c)+2] = c==2;
             w.dan[3*(da+c)] = 0; w.dan[3*(da+c)+1] = 0; w.dan[3*(da+c)+2] = 0;
             w.dax[3*(da+3+c)] = R[c]; w.dax[3*(da+3+c)+1] = R[3+c]; w.dax[3*(da+3+c)+2] = R[6+c];
             w.dan[3*(da+3+c)] = pos[0]; w.dan[3*(da+3+c)+1] = pos[1]; w.dan[3*(da+3+c)+2] = pos[2]; }
         } else {
-          quat2mat(R, quat);
-          double ax[3], an[3]; mat_vec(ax, R, jaxis + 3*j); mat_vec(an, R, jpos + 3*j); an[0]+=pos[0]; an[1]+=pos[1]; an[2]+=pos[2];
+          const double* al = jaxis + 3*j;
+          double ax[3], an[3]; mat_vec(ax, R, al); mat_vec(an, R, jpos + 3*j); an[0]+=pos[0]; an[1]+=pos[1]; an[2]+=pos[2];
           double dq = w.qpos[qa] - qpos0[qa];
           if (t == 2) { pos[0]+=ax[0]*dq; pos[1]+=ax[1]*dq; pos[2]+=ax[2]*dq; }
-          else { double s, c; sincos(0.5*dq, &s, &c); double ql[4] = {c, jaxis[3*j]*s, jaxis[3*j+1]*s, jaxis[3*j+2]*s}, qn[4];
-            quat_mul(qn, quat, ql); quat[0]=qn[0]; quat[1]=qn[1]; quat[2]=qn[2]; quat[3]=qn[3];
-            quat2mat(R, quat); double v[3]; mat_vec(v, R, jpos + 3*j); pos[0]=an[0]-v[0]; pos[1]=an[1]-v[1]; pos[2]=an[2]-v[2]; }
+          else {   // hinge: R <- R * Rodrigues(local axis, dq); pos keeps the anchor fixed
+            double s, c; sincos(dq, &s, &c); double oc = 1-c, x = al[0], y = al[1], z = al[2];
+            double Q[9] = {c+oc*x*x, oc*x*y-s*z, oc*x*z+s*y,  oc*x*y+s*z, c+oc*y*y, oc*y*z-s*x,  oc*x*z-s*y, oc*y*z+s*x, c+oc*z*z}, Rn[9];
+            mat_mul(Rn, R, Q);
+            #pragma unroll
+            for (int q = 0; q < 9; q++) R[q] = Rn[q];
+            double v[3]; mat_vec(v, R, jpos + 3*j); pos[0]=an[0]-v[0]; pos[1]=an[1]-v[1]; pos[2]=an[2]-v[2]; }
           w.dax[3*da]=ax[0]; w.dax[3*da+1]=ax[1]; w.dax[3*da+2]=ax[2]; w.dan[3*da]=an[0]; w.dan[3*da+1]=an[1]; w.dan[3*da+2]=an[2];
         }
       }
-      quat_norm(quat); quat2mat(R, quat);
-      for (int c = 0; c < 3; c++) w.xpos[3*k+c] = pos[c];
-      for (int c = 0; c < 4; c++) w.xquat[4*k+c] = quat[c];
-      for (int c = 0; c < 9; c++) w.xmat[9*k+c] = R[c];
-      // spatial inertia about the world origin
-      double c3[3]; mat_vec(c3, R, bd + 7); c3[0]+=pos[0]; c3[1]+=pos[1]; c3[2]+=pos[2];
-      double mass = bd[10]; const double* Il = bd + 11;   // xx yy zz xy xz yz (body frame)
-      double A[9] = {Il[0],Il[3],Il[4], Il[3],Il[1],Il[5], Il[4],Il[5],Il[2]}, T[9];
-      for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) T[3*r+cc] = R[3*r]*A[cc] + R[3*r+1]*A[3+cc] + R[3*r+2]*A[6+cc];
-      double* ci = w.cin + 10*k; double cc2 = dot3(c3, c3);
-      ci[0] = T[0]*R[0]+T[1]*R[1]+T[2]*R[2] + mass*(cc2 - c3[0]*c3[0]);
-      ci[1] = T[3]*R[3]+T[4]*R[4]+T[5]*R[5] + mass*(cc2 - c3[1]*c3[1]);
-      ci[2] = T[6]*R[6]+T[7]*R[7]+T[8]*R[8] + mass*(cc2 - c3[2]*c3[2]);
-      ci[3] = T[0]*R[3]+T[1]*R[4]+T[2]*R[5] - mass*c3[0]*c3[1];
-      ci[4] = T[0]*R[6]+T[1]*R[7]+T[2]*R[8] - mass*c3[0]*c3[2];
-      ci[5] = T[3]*R[6]+T[4]*R[7]+T[5]*R[8] - mass*c3[1]*c3[2];
-      ci[6] = mass*c3[0]; ci[7] = mass*c3[1]; ci[8] = mass*c3[2]; ci[9] = mass;
+      for (int c = 0; c < 3; c++) xpos[3*k+c] = pos[c];
+      for (int c = 0; c < 9; c++) xmat[9*k+c] = R[c];
     }
     __syncwarp();
   }
+}
+
+// spatial inertia of every dynamic body about the world origin (needs final poses; writes stage-2 scratch)
+__device__ void phase_body_inertia(const DevModel& m, Warp& w) {
+  const double* PB = CD(PB_d); const double* xpos = SCR(s_xpos); const double* xmat = SCR(s_xmat); double* cin = SCR(s_cin);
+  for (int k = w.lane; k < m.nbd; k += 32) { const double* bd = PB + k*PB_STRIDE; const double* R = xmat + 9*k;
+    double c3[3]; mat_vec(c3, R, bd + 12); c3[0]+=xpos[3*k]; c3[1]+=xpos[3*k+1]; c3[2]+=xpos[3*k+2];
+    double mass = bd[15]; const double* Il = bd + 16;   // xx yy zz xy xz yz (body frame)
+    double A[9] = {Il[0],Il[3],Il[4], Il[3],Il[1],Il[5], Il[4],Il[5],Il[2]}, T[9]; mat_mul(T, R, A);
+    double* ci = cin + 10*k; double cc2 = dot3(c3, c3);
+    ci[0] = T[0]*R[0]+T[1]*R[1]+T[2]*R[2] + mass*(cc2 - c3[0]*c3[0]);
+    ci[1] = T[3]*R[3]+T[4]*R[4]+T[5]*R[5] + mass*(cc2 - c3[1]*c3[1]);
+    ci[2] = T[6]*R[6]+T[7]*R[7]+T[8]*R[8] + mass*(cc2 - c3[2]*c3[2]);
+    ci[3] = T[0]*R[3]+T[1]*R[4]+T[2]*R[5] - mass*c3[0]*c3[1];
+    ci[4] = T[0]*R[6]+T[1]*R[7]+T[2]*R[8] - mass*c3[0]*c3[2];
+    ci[5] = T[3]*R[6]+T[4]*R[7]+T[5]*R[8] - mass*c3[1]*c3[2];
+    ci[6] = mass*c3[0]; ci[7] = mass*c3[1]; ci[8] = mass*c3[2]; ci[9] = mass; }
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------ phase 2: spatial tendons
@@ -167,18 +188,18 @@ __device__ __forceinline__ bool seg_intersect(const double* p1, const double* p2
   return a >= 0 && a <= 1 && b >= 0 && b <= 1; }
 
 // 2-D tangent wrap of the path d0 -> circle(rad) -> d1 on the outside; returns arc length or -1 (no wrap)
-__device__ double wrap2d_outside(double* pnt, const double* d, const double* sd, bool has_side, double rad) {
+__device__ __noinline__ double wrap2d_outside(double* pnt, const double* d, const double* sd, bool has_side, double rad) {
   double sq0 = d[0]*d[0]+d[1]*d[1], sq1 = d[2]*d[2]+d[3]*d[3], sqr = rad*rad;
   double dif0 = d[2]-d[0], dif1 = d[3]-d[1], dd = dif0*dif0+dif1*dif1;
   if (sq0 < sqr || sq1 < sqr || rad < MYO_MINVAL || dd < MYO_MINVAL) return -1;
   double a = clipd(-(dif0*d[0]+dif1*d[1])/dd, 0, 1);
   double t0 = a*dif0+d[0], t1 = a*dif1+d[1];
   if (t0*t0+t1*t1 > sqr && (!has_side || t0*sd[0]+t1*sd[1] >= 0)) return -1;
-  double s0 = sqrt(sq0-sqr), s1 = sqrt(sq1-sqr), sol[2][4], good[2];
+  double s0 = sqrt(sq0-sqr), s1 = sqrt(sq1-sqr), sol[2][4], good[2], i0 = 1.0/sq0, i1 = 1.0/sq1;
   #pragma unroll
   for (int i = 0; i < 2; i++) { double sg = i==0 ? 1.0 : -1.0;
-    sol[i][0] = (d[0]*sqr + sg*rad*d[1]*s0)/sq0; sol[i][1] = (d[1]*sqr - sg*rad*d[0]*s0)/sq0;
-    sol[i][2] = (d[2]*sqr - sg*rad*d[3]*s1)/sq1; sol[i][3] = (d[3]*sqr + sg*rad*d[2]*s1)/sq1;
+    sol[i][0] = (d[0]*sqr + sg*rad*d[1]*s0)*i0; sol[i][1] = (d[1]*sqr - sg*rad*d[0]*s0)*i0;
+    sol[i][2] = (d[2]*sqr - sg*rad*d[3]*s1)*i1; sol[i][3] = (d[3]*sqr + sg*rad*d[2]*s1)*i1;
     if (has_side) { double x = sol[i][0]+sol[i][2], y = sol[i][1]+sol[i][3], n = sqrt(x*x+y*y);
       if (n < MYO_MINVAL) { x = 1; y = 0; } else { x /= n; y /= n; } good[i] = x*sd[0]+y*sd[1]; }
     else { double x = sol[i][0]-sol[i][2], y = sol[i][1]-sol[i][3]; good[i] = -(x*x+y*y); }
@@ -189,7 +210,7 @@ __device__ double wrap2d_outside(double* pnt, const double* d, const double* sd,
   return rad*acos(clipd((pnt[0]*pnt[2]+pnt[1]*pnt[3])/sqr, -1, 1)); }
 
 // inverse wrap: the path must pass through the inside of the circle (touches it in one point); returns 0 or -1
-__device__ double wrap2d_inside(double* pnt, const double* d, double rad) {
+__device__ __noinline__ double wrap2d_inside(double* pnt, const double* d, double rad) {
   double len0 = sqrt(d[0]*d[0]+d[1]*d[1]), len1 = sqrt(d[2]*d[2]+d[3]*d[3]);
   if (len0 <= rad || len1 <= rad || rad < MYO_MINVAL || len0 < MYO_MINVAL || len1 < MYO_MINVAL) return -1;
   double dif0 = d[2]-d[0], dif1 = d[3]-d[1], dd = dif0*dif0+dif1*dif1;
@@ -202,6 +223,7 @@ __device__ double wrap2d_inside(double* pnt, const double* d, double rad) {
   double G = acos(cosG), z = 1-1e-7, f = asin(A*z)+asin(B*z)-2*asin(z)+G;
   if (f > 0) return 0;
   int it = 0;
+  #pragma unroll 1
   for (; it < 20 && fabs(f) > 1e-6; it++) {
     double df = A/fmax(MYO_MINVAL, sqrt(1-z*z*A*A)) + B/fmax(MYO_MINVAL, sqrt(1-z*z*B*B)) - 2/fmax(MYO_MINVAL, sqrt(1-z*z));
     if (df > -MYO_MINVAL) return 0;
@@ -216,13 +238,12 @@ __device__ double wrap2d_inside(double* pnt, const double* d, double rad) {
   return 0; }
 
 __device__ void wrap_element(const DevModel& m, const Warp& w, int k, double* U, double* WP, double* PL) {
-  const int* we = ISEC(m, PWE) + 6*k; const double* wd = DSEC(m, PWE_d) + k*PWE_STRIDE;
+  const idx_t* we = CI(PWE) + 6*k; const double* wd = CD(PWE_d) + k*PWE_STRIDE;
   double x0[3], x1[3]; world_point(m, w, we[0], x0); world_point(m, w, we[1], x1);
   int gb = we[2]; bool cyl = we[3] == 1, has_side = we[4] >= 0, inside = we[5] != 0; double rad = wd[12];
   double gpos[3], gmat[9];
   if (gb < 0) { for (int c = 0; c < 3; c++) gpos[c] = wd[c]; for (int c = 0; c < 9; c++) gmat[c] = wd[3+c]; }
-  else { const double* X = w.xmat + 9*gb; mat_vec(gpos, X, wd); gpos[0]+=w.xpos[3*gb]; gpos[1]+=w.xpos[3*gb+1]; gpos[2]+=w.xpos[3*gb+2];
-    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) gmat[3*r+c] = X[3*r]*wd[3+c] + X[3*r+1]*wd[6+c] + X[3*r+2]*wd[9+c]; }
+  else { const double* X = SCR(s_xmat) + 9*gb; const double* xp = SCR(s_xpos) + 3*gb; mat_vec(gpos, X, wd); gpos[0]+=xp[0]; gpos[1]+=xp[1]; gpos[2]+=xp[2]; mat_mul(gmat, X, wd + 3); }
   double t[3], p0[3], p1[3];
   t[0]=x0[0]-gpos[0]; t[1]=x0[1]-gpos[1]; t[2]=x0[2]-gpos[2]; matT_vec(p0, gmat, t);
   t[0]=x1[0]-gpos[0]; t[1]=x1[1]-gpos[1]; t[2]=x1[2]-gpos[2]; matT_vec(p1, gmat, t);
@@ -248,41 +269,51 @@ __device__ void wrap_element(const DevModel& m, const Warp& w, int k, double* U,
   double r0[3], r1[3];
   for (int c = 0; c < 3; c++) { r0[c] = ax0[c]*pnt[0]+ax1[c]*pnt[1]; r1[c] = ax0[c]*pnt[2]+ax1[c]*pnt[3]; }
   if (cyl) { double L0 = sqrt((p0[0]-pnt[0])*(p0[0]-pnt[0])+(p0[1]-pnt[1])*(p0[1]-pnt[1])), L1 = sqrt((p1[0]-pnt[2])*(p1[0]-pnt[2])+(p1[1]-pnt[3])*(p1[1]-pnt[3]));
-    r0[2] = p0[2]+(p1[2]-p0[2])*L0/(L0+wlen+L1); r1[2] = p0[2]+(p1[2]-p0[2])*(L0+wlen)/(L0+wlen+L1);
+    double inv = 1.0/(L0+wlen+L1);
+    r0[2] = p0[2]+(p1[2]-p0[2])*L0*inv; r1[2] = p0[2]+(p1[2]-p0[2])*(L0+wlen)*inv;
     double h = fabs(r1[2]-r0[2]); wlen = sqrt(wlen*wlen+h*h); }
   mat_vec(w0, gmat, r0); mat_vec(w1, gmat, r1);
   for (int c = 0; c < 3; c++) { w0[c]+=gpos[c]; w1[c]+=gpos[c]; }
   double a[3] = {w0[0]-x0[0], w0[1]-x0[1], w0[2]-x0[2]}, b[3] = {x1[0]-w1[0], x1[1]-w1[1], x1[2]-w1[2]};
   double na = sqrt(dot3(a,a)), nb = sqrt(dot3(b,b));
-  if (na < MYO_MINVAL) { u0[0]=1; u0[1]=0; u0[2]=0; } else { u0[0]=a[0]/na; u0[1]=a[1]/na; u0[2]=a[2]/na; }
-  if (nb < MYO_MINVAL) { u1[0]=1; u1[1]=0; u1[2]=0; } else { u1[0]=b[0]/nb; u1[1]=b[1]/nb; u1[2]=b[2]/nb; }
+  if (na < MYO_MINVAL) { u0[0]=1; u0[1]=0; u0[2]=0; } else { double q = 1.0/na; u0[0]=a[0]*q; u0[1]=a[1]*q; u0[2]=a[2]*q; }
+  if (nb < MYO_MINVAL) { u1[0]=1; u1[1]=0; u1[2]=0; } else { double q = 1.0/nb; u1[0]=b[0]*q; u1[1]=b[1]*q; u1[2]=b[2]*q; }
   PL[m.nsp + k] = na + wlen + nb;
 }
 
 __device__ void phase_tendon(const DevModel& m, Warp& w) {
-  double* U = w.arena + m.a_U; double* WP = w.arena + m.a_WP; double* PL = w.arena + m.a_PL;
-  const int* sp = ISEC(m, PSP);
+  double* U = SCR(s_U); double* WP = SCR(s_WP); double* PL = SCR(s_PL); double* mom = SCR(s_mom);
+  double* tlen = SCR(s_tlen); double* tvel = SCR(s_tvel); double* tfrc = SCR(s_tfrc);
+  const idx_t* sp = CI(PSP);
   for (int k = w.lane; k < m.nsp; k += 32) { double a[3], b[3]; world_point(m, w, sp[2*k], a); world_point(m, w, sp[2*k+1], b);
     double dv[3] = {b[0]-a[0], b[1]-a[1], b[2]-a[2]}, n = sqrt(dot3(dv,dv));
-    if (n < MYO_MINVAL) { U[3*k]=1; U[3*k+1]=0; U[3*k+2]=0; } else { U[3*k]=dv[0]/n; U[3*k+1]=dv[1]/n; U[3*k+2]=dv[2]/n; }
+    if (n < MYO_MINVAL) { U[3*k]=1; U[3*k+1]=0; U[3*k+2]=0; } else { double q = 1.0/n; U[3*k]=dv[0]*q; U[3*k+1]=dv[1]*q; U[3*k+2]=dv[2]*q; }
     PL[k] = n; }
+  #pragma unroll 1
   for (int k = w.lane; k < m.nwe; k += 32) wrap_element(m, w, k, U, WP, PL);
   __syncwarp();
-  const int* nzd = ISEC(m, PNZ_dof); const int* tadr = ISEC(m, PNZ_term_adr); const int* term = ISEC(m, PTERM);
+  const idx_t* nzd = CI(PNZ_dof); const idx_t* tadr = CI(PNZ_term_adr); const idx_t* term = CI(PTERM);
   for (int z = w.lane; z < m.nnz; z += 32) { int d = nzd[z]; double acc = 0;
+    #pragma unroll 1
     for (int e = tadr[z]; e < tadr[z+1]; e++) { int ui = term[3*e], pc = term[3*e+1]; double sg = term[3*e+2];
       double pt[3], c[3]; if (pc >= 0) world_point(m, w, pc, pt); else { const double* q = WP + 3*(-pc-1); pt[0]=q[0]; pt[1]=q[1]; pt[2]=q[2]; }
       dof_point_vel(m, w, d, pt, c); acc += sg*dot3(U + 3*ui, c); }
-    w.mom[z] = acc; }
-  const int* padr = ISEC(m, PT_piece_adr); const int* piece = ISEC(m, PT_piece); const double* tconst = DSEC(m, PT_const);
-  for (int t = w.lane; t < m.nta; t += 32) { double l = tconst[t]; for (int e = padr[t]; e < padr[t+1]; e++) l += PL[piece[e]]; w.tlen[t] = l; }
+    mom[z] = acc; }
+  const idx_t* padr = CI(PT_piece_adr); const idx_t* piece = CI(PT_piece); const double* tconst = CD(PT_const);
+  for (int t = w.lane; t < m.nta; t += 32) { double l = tconst[t];
+    #pragma unroll 1
+    for (int e = padr[t]; e < padr[t+1]; e++) l += PL[piece[e]];
+    tlen[t] = l; }
   __syncwarp();
-  const int* nadr = ISEC(m, PT_nz_adr);
-  for (int t = w.lane; t < m.nta; t += 32) { double v = 0; for (int z = nadr[t]; z < nadr[t+1]; z++) v += w.mom[z]*w.qvel[nzd[z]]; w.tvel[t] = v; w.tfrc[t] = 0; }
+  const idx_t* nadr = CI(PT_nz_adr);
+  for (int t = w.lane; t < m.nta; t += 32) { double v = 0;
+    #pragma unroll 1
+    for (int z = nadr[t]; z < nadr[t+1]; z++) v += mom[z]*w.qvel[nzd[z]];
+    tvel[t] = v; tfrc[t] = 0; }
   __syncwarp();
 }
 
-// ------------------------------------------------------------------ phase 3: muscle actuation -> qfrc_smooth (passive + actuator)
+// ------------------------------------------------------------------ phase 3: muscle actuation -> qfrc_smooth (passive + actuator); act integration
 __device__ __forceinline__ double muscle_FL(double L, double lmin, double lmax) {
   if (lmin <= L && L <= lmax) { double a = 0.5*(lmin+1), b = 0.5*(1+lmax), x;
     if (L <= a) { x = (L-lmin)/fmax(MYO_MINVAL, a-lmin); return 0.5*x*x; }
@@ -291,47 +322,54 @@ __device__ __forceinline__ double muscle_FL(double L, double lmin, double lmax) 
     else { x = (lmax-L)/fmax(MYO_MINVAL, lmax-b); return 0.5*x*x; } }
   return 0; }
 
-__device__ void phase_actuation(const DevModel& m, Warp& w) {
-  const int* atend = ISEC(m, PA_tendon); const double* PA = DSEC(m, PA_d);
-  for (int i = w.lane; i < m.nu; i += 32) { const double* a = PA + i*PA_STRIDE; int t = atend[i];
-    const double *dyn = a, *gp = a+3, *bp = a+12, *lr = a+21, *cr = a+23; double gear = a[26];
-    double len = gear*w.tlen[t], vel = gear*w.tvel[t], ctrl = w.ctrl[i], act = w.act[i];
+// tap_force / tap_len: nullable global rows for the parity taps (values before the activation is advanced)
+__device__ void phase_actuation(const DevModel& m, Warp& w, bool integrate, double* tap_force, double* tap_len) {
+  const idx_t* atend = CI(PA_tendon); const idx_t* acls = CI(PA_cls); const double* PAc = CD(PA_d); const double* PAm = CD(PAM_d);
+  double* tlen = SCR(s_tlen); double* tvel = SCR(s_tvel); double* tfrc = SCR(s_tfrc); double* mom = SCR(s_mom);
+  for (int i = w.lane; i < m.nu; i += 32) { const double* a = PAc + acls[i]*PA_STRIDE; const double* am = PAm + i*PAM_STRIDE; int t = atend[i];
+    const double *dyn = a, *gp = a+3, *bp = a+12, *cr = a+23; double gear = am[4], lr0 = am[2], lr1 = am[3];
+    double len = gear*tlen[t], vel = gear*tvel[t], ctrl = w.ctrl[i], act = w.act[i];
     if (a[25] != 0) ctrl = clipd(ctrl, cr[0], cr[1]);
     // activation dynamics
     double cc = clipd(ctrl, 0, 1), ac = clipd(act, 0, 1), ta = dyn[0]*(0.5+1.5*ac), td = dyn[1]/(0.5+1.5*ac), dctrl = cc - act, tau;
     if (dyn[2] < MYO_MINVAL) tau = dctrl > 0 ? ta : td;
     else { double x = clipd(dctrl/dyn[2]+0.5, 0, 1), s = x*x*x*(3*x*(2*x-5)+10); tau = td+(ta-td)*s; }
-    w.actdot[i] = dctrl/fmax(MYO_MINVAL, tau);
+    double actdot = dctrl/fmax(MYO_MINVAL, tau);
     // gain (active force-length-velocity) and bias (passive force)
-    double F = gp[2], L0 = (lr[1]-lr[0])/fmax(MYO_MINVAL, gp[1]-gp[0]), L = gp[0]+(len-lr[0])/fmax(MYO_MINVAL, L0), V = vel/fmax(MYO_MINVAL, L0*gp[6]);
+    double F = am[0], L0 = (lr1-lr0)/fmax(MYO_MINVAL, gp[1]-gp[0]), L = gp[0]+(len-lr0)/fmax(MYO_MINVAL, L0), V = vel/fmax(MYO_MINVAL, L0*gp[6]);
     double FL = muscle_FL(L, gp[4], gp[5]), y = gp[8]-1, FV;
     if (V <= -1) FV = 0; else if (V <= 0) FV = (V+1)*(V+1); else if (V <= y) FV = gp[8]-(y-V)*(y-V)/fmax(MYO_MINVAL, y); else FV = gp[8];
     double gain = -F*FL*FV;
-    double Fb = bp[2], L0b = (lr[1]-lr[0])/fmax(MYO_MINVAL, bp[1]-bp[0]), Lb = bp[0]+(len-lr[0])/fmax(MYO_MINVAL, L0b), b = 0.5*(1+bp[5]), bias;
+    double Fb = am[1], L0b = (lr1-lr0)/fmax(MYO_MINVAL, bp[1]-bp[0]), Lb = bp[0]+(len-lr0)/fmax(MYO_MINVAL, L0b), b = 0.5*(1+bp[5]), bias;
     if (Lb <= 1) bias = 0; else if (Lb <= b) { double x = (Lb-1)/fmax(MYO_MINVAL, b-1); bias = -Fb*bp[7]*0.5*x*x; }
     else { double x = (Lb-b)/fmax(MYO_MINVAL, b-1); bias = -Fb*bp[7]*(0.5+x); }
     double force = gain*act + bias;
-    w.aforce[i] = force; w.tfrc[t] = gear*force;   // one actuator per tendon (checked on the host)
+    tfrc[t] = gear*force;   // one actuator per tendon (checked on the host)
+    if (tap_force) tap_force[i] = force;
+    if (tap_len) tap_len[i] = len;
+    if (integrate) w.act[i] = act + m.timestep*actdot;   // mj_Euler's activation update; act is not read again this substep
   }
   __syncwarp();
-  const int* cadr = ISEC(m, PCOL_adr); const int* col = ISEC(m, PCOL); const int* nzt = ISEC(m, PNZ_tendon); const double* dofp = DSEC(m, PDOF_d);
+  const idx_t* cadr = CI(PCOL_adr); const idx_t* col = CI(PCOL); const idx_t* nzt = CI(PNZ_tendon); const double* dofp = CD(PDOF_d);
   for (int d = w.lane; d < m.nv; d += 32) { double s = -dofp[2*d+1]*w.qvel[d];
-    for (int e = cadr[d]; e < cadr[d+1]; e++) { int z = col[e]; s += w.mom[z]*w.tfrc[nzt[z]]; }
+    #pragma unroll 1
+    for (int e = cadr[d]; e < cadr[d+1]; e++) { int z = col[e]; s += mom[z]*tfrc[nzt[z]]; }
     w.fsm[d] = s; }
   __syncwarp();
 }
 
 // ------------------------------------------------------------------ phase 4: composite inertia -> joint-space mass matrix
 __device__ void phase_crb(const DevModel& m, Warp& w) {
-  double* crb = w.arena + m.a_crb; const int* sadr = ISEC(m, PSUB_adr); const int* sub = ISEC(m, PSUB);
+  double* crb = SCR(s_crb); const double* cin = SCR(s_cin); const idx_t* sadr = CI(PSUB_adr); const idx_t* sub = CI(PSUB);
   for (int k = w.lane; k < m.nbd; k += 32) { double acc[10] = {0,0,0,0,0,0,0,0,0,0};
-    for (int e = sadr[k]; e < sadr[k+1]; e++) { const double* c = w.cin + 10*sub[e];
+    #pragma unroll 1
+    for (int e = sadr[k]; e < sadr[k+1]; e++) { const double* c = cin + 10*sub[e];
       #pragma unroll
       for (int q = 0; q < 10; q++) acc[q] += c[q]; }
     #pragma unroll
     for (int q = 0; q < 10; q++) crb[10*k+q] = acc[q]; }
   __syncwarp();
-  const int* mi = ISEC(m, PM_i); const int* mj = ISEC(m, PM_j); const int* dbody = ISEC(m, PD_body); const double* dofp = DSEC(m, PDOF_d);
+  const idx_t* mi = CI(PM_i); const idx_t* mj = CI(PM_j); const idx_t* dbody = CI(PD_body); const double* dofp = CD(PDOF_d);
   for (int e = w.lane; e < m.nM; e += 32) { int i = mi[e], j = mj[e]; double Si[6], Sj[6], f[6];
     dof_motion(m, w, i, Si); inert_mul(f, crb + 10*dbody[i], Si); dof_motion(m, w, j, Sj);
     double v = Sj[0]*f[0]+Sj[1]*f[1]+Sj[2]*f[2]+Sj[3]*f[3]+Sj[4]*f[4]+Sj[5]*f[5];
@@ -342,43 +380,42 @@ __device__ void phase_crb(const DevModel& m, Warp& w) {
 
 // ------------------------------------------------------------------ phase 5: Coriolis/centrifugal/gravity bias (subtracts from fsm)
 __device__ void phase_bias(const DevModel& m, Warp& w) {
-  double* bf = w.arena + m.a_bf; const int* cadr = ISEC(m, PCH_adr); const int* ch = ISEC(m, PCH);
+  double* bf = SCR(s_bf); const double* cin = SCR(s_cin); const idx_t* cadr = CI(PCH_adr); const idx_t* ch = CI(PCH);
   for (int k = w.lane; k < m.nbd; k += 32) {
     double v[6] = {0,0,0,0,0,0}, vh[6] = {0,0,0,0,0,0}, a[6] = {0,0,0,-m.gx,-m.gy,-m.gz};
-    for (int e = cadr[k]; e < cadr[k+1]; e++) { int d = ch[e] & 0xffff, flag = ch[e] >> 16; double S[6], qd = w.qvel[d];
+    #pragma unroll 1
+    for (int e = cadr[k]; e < cadr[k+1]; e++) { int d = ch[e] >> 1, flag = ch[e] & 1; double S[6], qd = w.qvel[d];
       dof_motion(m, w, d, S);
       if (!flag) { for (int c = 0; c < 6; c++) vh[c] = v[c]; }
-      // cd = vh x_m S
-      double c0[3], c1[3], c2[3]; cross3(c0, vh, S); cross3(c1, vh, S+3); cross3(c2, vh+3, S);
+      double c0[3], c1[3], c2[3]; cross3(c0, vh, S); cross3(c1, vh, S+3); cross3(c2, vh+3, S);   // vh x_m S
       a[0]+=c0[0]*qd; a[1]+=c0[1]*qd; a[2]+=c0[2]*qd; a[3]+=(c1[0]+c2[0])*qd; a[4]+=(c1[1]+c2[1])*qd; a[5]+=(c1[2]+c2[2])*qd;
       for (int c = 0; c < 6; c++) v[c] += S[c]*qd; }
-    double Ia[6], Iv[6]; inert_mul(Ia, w.cin + 10*k, a); inert_mul(Iv, w.cin + 10*k, v);
-    // f = I a + v x_f (I v)
-    double t0[3], t1[3], t2[3]; cross3(t0, v, Iv); cross3(t1, v+3, Iv+3); cross3(t2, v, Iv+3);
+    double Ia[6], Iv[6]; inert_mul(Ia, cin + 10*k, a); inert_mul(Iv, cin + 10*k, v);
+    double t0[3], t1[3], t2[3]; cross3(t0, v, Iv); cross3(t1, v+3, Iv+3); cross3(t2, v, Iv+3);   // f = I a + v x_f (I v)
     bf[6*k] = Ia[0]+t0[0]+t1[0]; bf[6*k+1] = Ia[1]+t0[1]+t1[1]; bf[6*k+2] = Ia[2]+t0[2]+t1[2];
     bf[6*k+3] = Ia[3]+t2[0]; bf[6*k+4] = Ia[4]+t2[1]; bf[6*k+5] = Ia[5]+t2[2]; }
   __syncwarp();
-  const int* sadr = ISEC(m, PSUB_adr); const int* sub = ISEC(m, PSUB); const int* dbody = ISEC(m, PD_body);
+  const idx_t* sadr = CI(PSUB_adr); const idx_t* sub = CI(PSUB); const idx_t* dbody = CI(PD_body);
   for (int d = w.lane; d < m.nv; d += 32) { double S[6], tot = 0; dof_motion(m, w, d, S); int b = dbody[d];
+    #pragma unroll 1
     for (int e = sadr[b]; e < sadr[b+1]; e++) { const double* f = bf + 6*sub[e]; tot += S[0]*f[0]+S[1]*f[1]+S[2]*f[2]+S[3]*f[3]+S[4]*f[4]+S[5]*f[5]; }
     w.fsm[d] -= tot; }
   __syncwarp();
 }
 
 // ------------------------------------------------------------------ phase 6: collision (analytic primitives)
-__device__ __forceinline__ void geom_pose(const DevModel& m, const Warp& w, int g, double* pos, double* axis /* z column */, double* mat /* nullable 9 */) {
-  int b = ISEC(m, PG_body)[g]; const double* gd = DSEC(m, PG_d) + g*PG_STRIDE;
-  if (b < 0) { pos[0]=gd[0]; pos[1]=gd[1]; pos[2]=gd[2]; axis[0]=gd[5]; axis[1]=gd[8]; axis[2]=gd[11]; if (mat) for (int c = 0; c < 9; c++) mat[c] = gd[3+c]; }
-  else { const double* X = w.xmat + 9*b; mat_vec(pos, X, gd); pos[0]+=w.xpos[3*b]; pos[1]+=w.xpos[3*b+1]; pos[2]+=w.xpos[3*b+2];
-    double z[3] = {gd[5], gd[8], gd[11]}; mat_vec(axis, X, z);
-    if (mat) for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) mat[3*r+c] = X[3*r]*gd[3+c] + X[3*r+1]*gd[6+c] + X[3*r+2]*gd[9+c]; } }
+__device__ __forceinline__ void geom_pose(const DevModel& m, const Warp& w, int g, double* pos, double* axis /* z column */) {
+  int b = CI(PG_body)[g]; const double* gd = CD(PG_d) + g*PG_STRIDE;
+  if (b < 0) { pos[0]=gd[0]; pos[1]=gd[1]; pos[2]=gd[2]; axis[0]=gd[5]; axis[1]=gd[8]; axis[2]=gd[11]; }
+  else { const double* X = SCR(s_xmat) + 9*b; const double* xp = SCR(s_xpos) + 3*b; mat_vec(pos, X, gd); pos[0]+=xp[0]; pos[1]+=xp[1]; pos[2]+=xp[2];
+    double z[3] = {gd[5], gd[8], gd[11]}; mat_vec(axis, X, z); } }
 
 struct ConOut { int n; double dist[2]; double pos[2][3]; double nrm[2][3]; double yh[3]; bool has_y; };
 __device__ __forceinline__ void sph_sph(ConOut& o, double margin, const double* p1, double r1, const double* p2, double r2) {
   double dv[3] = {p2[0]-p1[0], p2[1]-p1[1], p2[2]-p1[2]}, cd = sqrt(dot3(dv,dv)), dist = cd-r1-r2;
   if (dist > margin || o.n >= 2) return;
   int c = o.n++; o.dist[c] = dist;
-  if (cd < MYO_MINVAL) { o.nrm[c][0]=1; o.nrm[c][1]=0; o.nrm[c][2]=0; } else { o.nrm[c][0]=dv[0]/cd; o.nrm[c][1]=dv[1]/cd; o.nrm[c][2]=dv[2]/cd; }
+  if (cd < MYO_MINVAL) { o.nrm[c][0]=1; o.nrm[c][1]=0; o.nrm[c][2]=0; } else { double q = 1.0/cd; o.nrm[c][0]=dv[0]*q; o.nrm[c][1]=dv[1]*q; o.nrm[c][2]=dv[2]*q; }
   for (int k = 0; k < 3; k++) o.pos[c][k] = p1[k] + o.nrm[c][k]*(r1+0.5*dist); }
 __device__ __forceinline__ void plane_sph(ConOut& o, double margin, const double* pp, const double* pn, const double* sp, double r) {
   double dv[3] = {sp[0]-pp[0], sp[1]-pp[1], sp[2]-pp[2]}, dist = dot3(dv,pn)-r;
@@ -386,16 +423,18 @@ __device__ __forceinline__ void plane_sph(ConOut& o, double margin, const double
   int c = o.n++; o.dist[c] = dist; for (int k = 0; k < 3; k++) { o.nrm[c][k] = pn[k]; o.pos[c][k] = sp[k]-pn[k]*(r+0.5*dist); } }
 
 __device__ void collide_pair(const DevModel& m, const Warp& w, int p, ConOut& o) {
-  const int* pr = ISEC(m, PPAIR) + 6*p; const double* pd = DSEC(m, PPAIR_d) + p*PPAIR_STRIDE; const double* G = DSEC(m, PG_d);
+  const idx_t* pr = CI(PPAIR) + PPAIR_ISTRIDE*p; const double* pd = CD(PPAIR_d) + pr[6]*PPAIR_STRIDE; const double* G = CD(PG_d);
   int g1 = pr[0], g2 = pr[1], ct = pr[5]; double margin = pd[0]; o.n = 0; o.has_y = false;
   const double* s1 = G + g1*PG_STRIDE + 12; const double* s2 = G + g2*PG_STRIDE + 12;
-  double x1[3], a1[3], x2[3], a2[3]; geom_pose(m, w, g1, x1, a1, nullptr); geom_pose(m, w, g2, x2, a2, nullptr);
+  double x1[3], a1[3], x2[3], a2[3]; geom_pose(m, w, g1, x1, a1); geom_pose(m, w, g2, x2, a2);
   if (ct == CT_CAP_CAP) {
     double r1 = s1[0], h1 = s1[1], r2 = s2[0], h2 = s2[1];
     double dv[3] = {x1[0]-x2[0], x1[1]-x2[1], x1[2]-x2[2]};
+    // cheap reject: the capsules' bounding spheres are farther apart than the margin
+    { double rb = r1+h1+r2+h2+margin; if (dot3(dv,dv) > rb*rb) return; }
     double ma = dot3(a1,a1), mb = -dot3(a1,a2), mc = dot3(a2,a2), u = -dot3(a1,dv), v = dot3(a2,dv), det = ma*mc-mb*mb, v1[3], v2[3];
     if (fabs(det) >= MYO_MINVAL) {
-      double t1 = (mc*u-mb*v)/det, t2 = (ma*v-mb*u)/det;
+      double id = 1.0/det, t1 = (mc*u-mb*v)*id, t2 = (ma*v-mb*u)*id;
       if (t1 > h1) { t1 = h1; t2 = (v-mb*h1)/mc; } else if (t1 < -h1) { t1 = -h1; t2 = (v+mb*h1)/mc; }
       if (t2 > h2) { t2 = h2; t1 = clipd((u-mb*h2)/ma, -h1, h1); } else if (t2 < -h2) { t2 = -h2; t1 = clipd((u+mb*h2)/ma, -h1, h1); }
       for (int k = 0; k < 3; k++) { v1[k] = x1[k]+a1[k]*t1; v2[k] = x2[k]+a2[k]*t2; }
@@ -418,9 +457,10 @@ __device__ void collide_pair(const DevModel& m, const Warp& w, int p, ConOut& o)
 }
 
 __device__ void phase_collision(const DevModel& m, Warp& w) {
-  double* con = w.arena + m.a_con; int* icon = (int*)(w.arena + m.a_icon);
+  double* con = SCR(s_con); int* icon = (int*)SCR(s_icon);
   int ncon = 0; w.overflow = 0;
-  for (int base = 0; base < m.npair; base += 32) { int p = base + w.lane; ConOut o; o.n = 0;
+  #pragma unroll 1
+  for (int base = 0; base < m.npair; base += 32) { int p = base + w.lane; ConOut o; o.n = 0; o.has_y = false;
     if (p < m.npair) collide_pair(m, w, p, o);
     unsigned m0 = __ballot_sync(FULL, o.n >= 1), m1 = __ballot_sync(FULL, o.n >= 2), lt = (1u << w.lane) - 1;
     int idx = ncon + __popc(m0 & lt) + __popc(m1 & lt);
@@ -431,7 +471,7 @@ __device__ void phase_collision(const DevModel& m, Warp& w) {
         double y[3] = {0,0,0};
         if (o.has_y) { y[0]=o.yh[0]; y[1]=o.yh[1]; y[2]=o.yh[2]; }
         if (sqrt(dot3(y,y)) < 0.5) { y[0]=0; y[1]=0; y[2]=0; if (f[1] < 0.5 && f[1] > -0.5) y[1] = 1; else y[2] = 1; }
-        double dd = dot3(f, y); y[0]-=dd*f[0]; y[1]-=dd*f[1]; y[2]-=dd*f[2]; double n = sqrt(dot3(y,y)); y[0]/=n; y[1]/=n; y[2]/=n;
+        double dd = dot3(f, y); y[0]-=dd*f[0]; y[1]-=dd*f[1]; y[2]-=dd*f[2]; double n = 1.0/sqrt(dot3(y,y)); y[0]*=n; y[1]*=n; y[2]*=n;
         f[3]=y[0]; f[4]=y[1]; f[5]=y[2]; cross3(f+6, f, y);
         icon[ci] = p; } }
     ncon += __popc(m0) + __popc(m1); }

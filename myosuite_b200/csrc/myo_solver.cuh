@@ -5,18 +5,18 @@
 #pragma once
 #include "myo_device.cuh"
 
-struct Solv {   // arena views
+struct Solv {   // scratch views (stage 3/4)
   double *H, *con, *conJ, *D, *aref, *jar, *jv, *a, *g, *p, *Ma, *Mp, *eqJ, *Hs, *LD, *Dinv;
-  int *cpair, *crow, *cnrow, *lrow;   // contact pair idx, first efc row, #rows ; limit row descriptors (dof | sign bit 16 | limit idx << 17)
+  int *cpair, *crow, *cnrow, *lrow;   // contact pair idx, first efc row, #rows ; limit row descriptors (dof | side << 16)
 };
-__device__ __forceinline__ Solv solv_views(const DevModel& m, Warp& w) {
-  Solv s; double* A = w.arena;
-  s.H = A + m.a_H; s.con = A + m.a_con; s.conJ = A + m.a_conJ; s.D = A + m.a_efD; s.aref = A + m.a_efA; s.jar = A + m.a_efR; s.jv = A + m.a_efV;
-  s.a = A + m.a_va; s.g = A + m.a_vg; s.p = A + m.a_vp; s.Ma = A + m.a_vMa; s.Mp = A + m.a_vMp; s.eqJ = A + m.a_eqJ; s.Hs = A + m.a_Hs; s.LD = A + m.a_LD; s.Dinv = A + m.a_Dinv;
-  int* ic = (int*)(A + m.a_icon); s.cpair = ic; s.crow = ic + m.maxcon; s.cnrow = ic + 2*m.maxcon; s.lrow = ic + 3*m.maxcon;
+__device__ __forceinline__ Solv solv_views(const DevModel& m, const Warp& w) {
+  Solv s; double* A = w.scr;
+  s.H = A + m.s_H; s.con = A + m.s_con; s.conJ = A + m.s_conJ; s.D = A + m.s_efD; s.aref = A + m.s_efA; s.jar = A + m.s_efR; s.jv = A + m.s_efV;
+  s.a = A + m.s_va; s.g = A + m.s_vg; s.p = A + m.s_vp; s.Ma = A + m.s_vMa; s.Mp = A + m.s_vMp; s.eqJ = A + m.s_eqJ; s.Hs = A + m.s_Hs; s.LD = A + m.s_LD; s.Dinv = A + m.s_Dinv;
+  int* ic = (int*)(A + m.s_icon); s.cpair = ic; s.crow = ic + m.maxcon; s.cnrow = ic + 2*m.maxcon; s.lrow = ic + 3*m.maxcon;
   return s; }
 
-__device__ __noinline__ double impedance(const double* si, double pos, double margin) {
+__device__ __forceinline__ double impedance(const double* si, double pos, double margin) {
   if (si[0] == si[1] || si[2] <= MYO_MINVAL) return 0.5*(si[0]+si[1]);
   double x = fabs((pos-margin)/si[2]);
   if (x >= 1 || x <= 0) return x >= 1 ? si[1] : si[0];
@@ -29,36 +29,36 @@ __device__ __noinline__ double impedance(const double* si, double pos, double ma
 
 // y = M x using the per-row non-zero lists
 __device__ __forceinline__ void mul_M(const DevModel& m, const Warp& w, double* y, const double* x) {
-  const int* radr = ISEC(m, PROW_adr); const int* rcol = ISEC(m, PROW_col); const int* ridx = ISEC(m, PROW_idx);
+  const idx_t* radr = CI(PROW_adr); const idx_t* rcol = CI(PROW_col); const idx_t* ridx = CI(PROW_idx);
   for (int i = w.lane; i < m.nv; i += 32) { double s = 0; for (int e = radr[i]; e < radr[i+1]; e++) s += w.qM[ridx[e]]*x[rcol[e]]; y[i] = s; } }
 
 // out[r] = (J x)_r for every constraint row
 __device__ void rows_apply(const DevModel& m, const Warp& w, const Solv& s, const double* x, double* out) {
-  const int* eq = ISEC(m, PEQ);
+  const idx_t* eq = CI(PEQ);
   for (int e = w.lane; e < m.neq; e += 32) { double v = x[eq[PEQ_ISTRIDE*e+1]]; if (eq[PEQ_ISTRIDE*e+3] >= 0) v += s.eqJ[e]*x[eq[PEQ_ISTRIDE*e+3]]; out[e] = v; }
   for (int r = w.lane; r < w.nlimrow; r += 32) { int dsc = s.lrow[r]; double sg = (dsc >> 16) & 1 ? -1.0 : 1.0; out[m.neq + r] = sg*x[dsc & 0xffff]; }
-  const int* pr = ISEC(m, PPAIR); const double* pd = DSEC(m, PPAIR_d); const int* path = ISEC(m, PPATH);
+  const idx_t* pr = CI(PPAIR); const double* pd = CD(PPAIR_d); const idx_t* path = CI(PPATH);
   for (int c = w.lane; c < w.ncon; c += 32) { int nr = s.cnrow[c]; if (!nr) continue;
-    const int* q = pr + 6*s.cpair[c]; const double* J = s.conJ + (size_t)c*3*m.maxpath; double n = 0, t1 = 0, t2 = 0;
+    const idx_t* q = pr + PPAIR_ISTRIDE*s.cpair[c]; const double* J = s.conJ + (size_t)c*3*m.maxpath; double n = 0, t1 = 0, t2 = 0;
     for (int e = 0; e < q[4]; e++) { double xv = x[path[q[3]+e] >> 1]; n += J[3*e]*xv; t1 += J[3*e+1]*xv; t2 += J[3*e+2]*xv; }
     int rb = s.crow[c];
     if (nr == 1) out[rb] = n;
-    else { const double* P = pd + s.cpair[c]*PPAIR_STRIDE; double mu1 = P[2], mu2 = P[3]; out[rb] = n+mu1*t1; out[rb+1] = n-mu1*t1; out[rb+2] = n+mu2*t2; out[rb+3] = n-mu2*t2; } }
+    else { const double* P = pd + q[6]*PPAIR_STRIDE; double mu1 = P[2], mu2 = P[3]; out[rb] = n+mu1*t1; out[rb+1] = n-mu1*t1; out[rb+2] = n+mu2*t2; out[rb+3] = n-mu2*t2; } }
 }
 
 // vec[d] += sum_r J[r][d] * wgt[r]  (wgt already includes D and the active mask)
 __device__ void rows_applyT_add(const DevModel& m, const Warp& w, const Solv& s, const double* wgt, double* vec) {
-  const int* eq = ISEC(m, PEQ);
+  const idx_t* eq = CI(PEQ);
   if (w.lane == 0) for (int e = 0; e < m.neq; e++) { vec[eq[PEQ_ISTRIDE*e+1]] += wgt[e]; if (eq[PEQ_ISTRIDE*e+3] >= 0) vec[eq[PEQ_ISTRIDE*e+3]] += s.eqJ[e]*wgt[e]; }
   __syncwarp();
   for (int pass = 0; pass < 2; pass++) {
     for (int r = w.lane; r < w.nlimrow; r += 32) { int dsc = s.lrow[r]; int neg = (dsc >> 16) & 1; if (neg == pass) vec[dsc & 0xffff] += (neg ? -1.0 : 1.0)*wgt[m.neq + r]; }
     __syncwarp(); }
-  const int* pr = ISEC(m, PPAIR); const double* pd = DSEC(m, PPAIR_d); const int* path = ISEC(m, PPATH);
+  const idx_t* pr = CI(PPAIR); const double* pd = CD(PPAIR_d); const idx_t* path = CI(PPATH);
   for (int c = 0; c < w.ncon; c++) { int nr = s.cnrow[c]; if (!nr) continue;
-    const int* q = pr + 6*s.cpair[c]; const double* J = s.conJ + (size_t)c*3*m.maxpath; int rb = s.crow[c]; double wn, w1 = 0, w2 = 0;
+    const idx_t* q = pr + PPAIR_ISTRIDE*s.cpair[c]; const double* J = s.conJ + (size_t)c*3*m.maxpath; int rb = s.crow[c]; double wn, w1 = 0, w2 = 0;
     if (nr == 1) wn = wgt[rb];
-    else { const double* P = pd + s.cpair[c]*PPAIR_STRIDE; wn = wgt[rb]+wgt[rb+1]+wgt[rb+2]+wgt[rb+3]; w1 = P[2]*(wgt[rb]-wgt[rb+1]); w2 = P[3]*(wgt[rb+2]-wgt[rb+3]); }
+    else { const double* P = pd + q[6]*PPAIR_STRIDE; wn = wgt[rb]+wgt[rb+1]+wgt[rb+2]+wgt[rb+3]; w1 = P[2]*(wgt[rb]-wgt[rb+1]); w2 = P[3]*(wgt[rb+2]-wgt[rb+3]); }
     for (int e = w.lane; e < q[4]; e += 32) vec[path[q[3]+e] >> 1] += J[3*e]*wn + J[3*e+1]*w1 + J[3*e+2]*w2;
     __syncwarp(); }
 }
@@ -67,7 +67,7 @@ __device__ void rows_applyT_add(const DevModel& m, const Warp& w, const Solv& s,
 __device__ void phase_constraints(const DevModel& m, Warp& w) {
   Solv s = solv_views(m, w);
   // joint equalities (always active)
-  const int* eq = ISEC(m, PEQ); const double* eqd = DSEC(m, PEQ_d);
+  const idx_t* eq = CI(PEQ); const double* eqd = CD(PEQ_d);
   for (int e = w.lane; e < m.neq; e += 32) { const double* c = eqd + e*PEQ_STRIDE; int q1 = eq[PEQ_ISTRIDE*e], d1 = eq[PEQ_ISTRIDE*e+1], q2 = eq[PEQ_ISTRIDE*e+2], d2 = eq[PEQ_ISTRIDE*e+3];
     double pos0 = w.qpos[q1]-c[5], cpos, deriv = 0, vel = w.qvel[d1];
     if (q2 >= 0) { double x = w.qpos[q2]-c[6]; cpos = pos0-(c[0]+x*(c[1]+x*(c[2]+x*(c[3]+x*c[4])))); deriv = c[1]+x*(2*c[2]+x*(3*c[3]+x*4*c[4])); vel -= deriv*w.qvel[d2]; }
@@ -76,7 +76,7 @@ __device__ void phase_constraints(const DevModel& m, Warp& w) {
     double imp = impedance(c+10, cpos, 0), R = fmax(MYO_MINVAL, (1-imp)*c[7]/imp);
     s.D[e] = 1.0/R; s.aref[e] = -c[9]*vel - c[8]*imp*cpos; }
   // joint limits (one-sided)
-  const int* lim = ISEC(m, PLIM); const double* limd = DSEC(m, PLIM_d); int nrow = 0;
+  const idx_t* lim = CI(PLIM); const double* limd = CD(PLIM_d); int nrow = 0;
   for (int base = 0; base < m.nlim; base += 32) { int l = base + w.lane; bool lo = false, hi = false; double dlo = 0, dhi = 0; const double* c = limd + (l < m.nlim ? l : 0)*PLIM_STRIDE; int d = 0;
     if (l < m.nlim) { d = lim[2*l]; double q = w.qpos[lim[2*l+1]]; dlo = q-c[0]; dhi = c[1]-q; lo = dlo < c[2]; hi = dhi < c[2]; }
     unsigned m0 = __ballot_sync(FULL, lo), m1 = __ballot_sync(FULL, hi), lt = (1u << w.lane)-1; int idx = nrow + __popc(m0 & lt) + __popc(m1 & lt);
@@ -88,22 +88,22 @@ __device__ void phase_constraints(const DevModel& m, Warp& w) {
     nrow += __popc(m0) + __popc(m1); }
   w.nlimrow = nrow;
   // contacts: Jacobian over the dofs between the two bodies, regulariser, reference acceleration
-  const int* pr = ISEC(m, PPAIR); const double* pd = DSEC(m, PPAIR_d); const int* path = ISEC(m, PPATH);
+  const idx_t* pr = CI(PPAIR); const double* pd = CD(PPAIR_d); const idx_t* path = CI(PPATH);
   int rowbase = m.neq + nrow;
   for (int base = 0; base < w.ncon; base += 32) { int c = base + w.lane; int nr = 0;
-    if (c < w.ncon) { const int* q = pr + 6*s.cpair[c]; const double* P = pd + s.cpair[c]*PPAIR_STRIDE; double dist = s.con[c*CON_STRIDE];
+    if (c < w.ncon) { const idx_t* q = pr + PPAIR_ISTRIDE*s.cpair[c]; const double* P = pd + q[6]*PPAIR_STRIDE; double dist = s.con[c*CON_STRIDE];
       nr = (dist < P[0]-P[1]) ? (q[2] == 1 ? 1 : 4) : 0; }
     int incl = nr;   // inclusive warp scan
     #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, incl, o); if (w.lane >= o) incl += t; }
     int total = __shfl_sync(FULL, incl, 31);
     if (c < w.ncon) { s.crow[c] = rowbase + incl - nr; s.cnrow[c] = nr; }
-    if (c < w.ncon && nr) { const int* q = pr + 6*s.cpair[c]; const double* P = pd + s.cpair[c]*PPAIR_STRIDE; const double* cd = s.con + c*CON_STRIDE;
+    if (c < w.ncon && nr) { const idx_t* q = pr + PPAIR_ISTRIDE*s.cpair[c]; const double* P = pd + q[6]*PPAIR_STRIDE; const double* cd = s.con + c*CON_STRIDE;
       const double* pos = cd + 1; const double* f = cd + 4; double* J = s.conJ + (size_t)c*3*m.maxpath; double vn = 0, v1 = 0, v2 = 0;
       for (int e = 0; e < q[4]; e++) { int code = path[q[3]+e], d = code >> 1; double sg = (code & 1) ? 1.0 : -1.0, cv[3]; dof_point_vel(m, w, d, pos, cv);
         double jn = sg*dot3(f, cv), j1 = sg*dot3(f+3, cv), j2 = sg*dot3(f+6, cv); J[3*e] = jn; J[3*e+1] = j1; J[3*e+2] = j2;
         double qd = w.qvel[d]; vn += jn*qd; v1 += j1*qd; v2 += j2*qd; }
-      double dist = cd[0], inc = P[0]-P[1], imp = impedance(P+7, dist, inc), K = P[5], B = P[6], tran = P[4]; int rb = rowbase + incl - nr;
+      double dist = cd[0], inc = P[0]-P[1], imp = impedance(P+7, dist, inc), K = P[5], B = P[6], tran = CD(PPAIR_tran)[s.cpair[c]]; int rb = rowbase + incl - nr;
       if (nr == 1) { double R = fmax(MYO_MINVAL, (1-imp)*tran/imp); s.D[rb] = 1.0/R; s.aref[rb] = -B*vn - K*imp*(dist-inc); }
       else { double mu1 = P[2], mu2 = P[3]; double R0 = fmax(MYO_MINVAL, (1-imp)*(tran+mu1*mu1*tran)/imp), Rpy = 2*mu1*mu1*R0, Dv = 1.0/Rpy, kp = K*imp*(dist-inc);
         s.D[rb] = s.D[rb+1] = s.D[rb+2] = s.D[rb+3] = Dv;
@@ -134,15 +134,15 @@ __device__ void chol_solve(const double* H, int n, double* x, int lane) {
 }
 __device__ __forceinline__ void load_M_dense(const DevModel& m, const Warp& w, double* H, double diag_scale /* h */) {
   int n = m.nv; for (int i = w.lane; i < n*n; i += 32) H[i] = 0; __syncwarp();
-  const int* mi = ISEC(m, PM_i); const int* mj = ISEC(m, PM_j); const double* dofp = DSEC(m, PDOF_d);
+  const idx_t* mi = CI(PM_i); const idx_t* mj = CI(PM_j); const double* dofp = CD(PDOF_d);
   for (int e = w.lane; e < m.nM; e += 32) { int i = mi[e], j = mj[e]; double v = w.qM[e]; if (i == j) v += diag_scale*dofp[2*i+1]; H[i*n+j] = v; H[j*n+i] = v; }
   __syncwarp(); }
 
 // ------------------------------------------------------------------ tree-sparse L'DL (level-scheduled, left-looking) on the qM layout
 // Hs (nM, input) -> LD (nM: D on the diagonal slots, unit-L off-diagonals), Dinv (nv)
 __device__ void ldl_factor(const DevModel& m, const Warp& w, const double* Hs, double* LD, double* Dinv) {
-  const int* fadr = ISEC(m, PFE_adr); const int* fe = ISEC(m, PFE); const int* tadr = ISEC(m, PFT_adr); const int* ft = ISEC(m, PFT);
-  const int* mi = ISEC(m, PM_i); const int* mj = ISEC(m, PM_j); const int* madr = ISEC(m, dof_Madr);
+  const idx_t* fadr = CI(PFE_adr); const idx_t* fe = CI(PFE); const idx_t* tadr = CI(PFT_adr); const idx_t* ft = CI(PFT);
+  const idx_t* mi = CI(PM_i); const idx_t* mj = CI(PM_j); const idx_t* madr = CI(dof_Madr);
   for (int lev = m.ndepth-1; lev >= 0; lev--) {
     for (int t = fadr[lev] + w.lane; t < fadr[lev+1]; t += 32) { int e = fe[t]; double v = Hs[e];
       for (int q = tadr[t]; q < tadr[t+1]; q++) v -= LD[ft[3*q]]*LD[ft[3*q+1]]*LD[madr[ft[3*q+2]]];
@@ -154,8 +154,8 @@ __device__ void ldl_factor(const DevModel& m, const Warp& w, const double* Hs, d
 }
 // x <- (L'DL)^-1 x
 __device__ void ldl_solve(const DevModel& m, const Warp& w, const double* LD, const double* Dinv, double* x) {
-  const int* ladr = ISEC(m, PLV_adr); const int* lv = ISEC(m, PLV); const int* dadr = ISEC(m, PDS_adr); const int* ds = ISEC(m, PDS);
-  const int* madr = ISEC(m, dof_Madr); const int* mj = ISEC(m, PM_j);
+  const idx_t* ladr = CI(PLV_adr); const idx_t* lv = CI(PLV); const idx_t* dadr = CI(PDS_adr); const idx_t* ds = CI(PDS);
+  const idx_t* madr = CI(dof_Madr); const idx_t* mj = CI(PM_j);
   for (int lev = m.ndepth-1; lev >= 0; lev--) {
     for (int t = ladr[lev] + w.lane; t < ladr[lev+1]; t += 32) { int j = lv[t]; double s = x[j];
       for (int q = dadr[j]; q < dadr[j+1]; q++) s -= LD[ds[2*q+1]]*x[ds[2*q]];
@@ -179,7 +179,7 @@ __device__ void phase_solve(const DevModel& m, Warp& w, double tol) {
   mul_M(m, w, s.Ma, s.a); rows_apply(m, w, s, s.a, s.jar); __syncwarp();
   for (int r = w.lane; r < nefc; r += 32) s.jar[r] -= s.aref[r]; __syncwarp();
   const double scale = 1.0/(m.meaninertia*(n > 1 ? n : 1));
-  const int* eq = ISEC(m, PEQ); const int* pr = ISEC(m, PPAIR); const double* pd = DSEC(m, PPAIR_d); const int* path = ISEC(m, PPATH);
+  const idx_t* eq = CI(PEQ); const idx_t* pr = CI(PPAIR); const double* pd = CD(PPAIR_d); const idx_t* path = CI(PPATH);
   for (int iter = 0; iter < 50; iter++) {
     // gradient
     for (int i = w.lane; i < n; i += 32) s.g[i] = s.Ma[i]-w.fsm[i];
@@ -194,7 +194,7 @@ __device__ void phase_solve(const DevModel& m, Warp& w, double tol) {
     for (int i = w.lane; i < n; i += 32) s.p[i] = -s.g[i];
     __syncwarp();
     if (!dense) {
-      const int* madr = ISEC(m, dof_Madr);
+      const idx_t* madr = CI(dof_Madr);
       for (int e = w.lane; e < m.nM; e += 32) s.Hs[e] = w.qM[e];
       __syncwarp();
       if (w.lane == 0) for (int e = 0; e < m.neq; e++) { int d1 = eq[PEQ_ISTRIDE*e+1], d2 = eq[PEQ_ISTRIDE*e+3]; double De = s.D[e], j2 = s.eqJ[e]; s.Hs[madr[d1]] += De;
@@ -208,9 +208,9 @@ __device__ void phase_solve(const DevModel& m, Warp& w, double tol) {
       if (d2 >= 0) { s.H[d1*n+d2] += De*j2; s.H[d2*n+d1] += De*j2; s.H[d2*n+d2] += De*j2*j2; } }
     __syncwarp();
     for (int pass = 0; pass < 2; pass++) { for (int r = w.lane; r < w.nlimrow; r += 32) { int dsc = s.lrow[r]; if (((dsc >> 16) & 1) == pass && s.jar[m.neq+r] < 0) { int d = dsc & 0xffff; s.H[d*n+d] += s.D[m.neq+r]; } } __syncwarp(); }
-    for (int c = 0; c < w.ncon; c++) { int nr = s.cnrow[c]; if (!nr) continue; int rb = s.crow[c]; const int* q = pr + 6*s.cpair[c]; double W[6] = {0,0,0,0,0,0};  // nn n1 n2 11 12 22
+    for (int c = 0; c < w.ncon; c++) { int nr = s.cnrow[c]; if (!nr) continue; int rb = s.crow[c]; const idx_t* q = pr + PPAIR_ISTRIDE*s.cpair[c]; double W[6] = {0,0,0,0,0,0};  // nn n1 n2 11 12 22
       if (nr == 1) { if (s.jar[rb] < 0) W[0] = s.D[rb]; }
-      else { const double* P = pd + s.cpair[c]*PPAIR_STRIDE; double mu1 = P[2], mu2 = P[3], Dv = s.D[rb];
+      else { const double* P = pd + q[6]*PPAIR_STRIDE; double mu1 = P[2], mu2 = P[3], Dv = s.D[rb];
         double a0 = s.jar[rb] < 0 ? Dv : 0, a1 = s.jar[rb+1] < 0 ? Dv : 0, a2 = s.jar[rb+2] < 0 ? Dv : 0, a3 = s.jar[rb+3] < 0 ? Dv : 0;
         W[0] = a0+a1+a2+a3; W[1] = mu1*(a0-a1); W[2] = mu2*(a2-a3); W[3] = mu1*mu1*(a0+a1); W[5] = mu2*mu2*(a2+a3); }
       if (W[0] != 0) { const double* J = s.conJ + (size_t)c*3*m.maxpath; int np = q[4];
@@ -244,13 +244,12 @@ __device__ void phase_integrate(const DevModel& m, Warp& w) {
   Solv s = solv_views(m, w); int n = m.nv; double h = m.timestep;
   // (M + h B) qacc' = M qacc  (= qfrc_smooth + qfrc_constraint at the solver optimum)
   mul_M(m, w, s.g, s.a); __syncwarp();
-  { const int* mi = ISEC(m, PM_i); const int* mj = ISEC(m, PM_j); const double* dofp = DSEC(m, PDOF_d);
+  { const idx_t* mi = CI(PM_i); const idx_t* mj = CI(PM_j); const double* dofp = CD(PDOF_d);
     for (int e = w.lane; e < m.nM; e += 32) { double v = w.qM[e]; if (mi[e] == mj[e]) v += h*dofp[2*mi[e]+1]; s.Hs[e] = v; } __syncwarp(); }
   ldl_factor(m, w, s.Hs, s.LD, s.Dinv); ldl_solve(m, w, s.LD, s.Dinv, s.g);
-  for (int i = w.lane; i < m.na; i += 32) w.act[i] += h*w.actdot[i];
   for (int i = w.lane; i < n; i += 32) { w.qvel[i] += h*s.g[i]; w.qws[i] = s.a[i]; }
   __syncwarp();
-  const int* jtype = ISEC(m, jnt_type); const int* jq = ISEC(m, jnt_qposadr); const int* jd = ISEC(m, jnt_dofadr);
+  const idx_t* jtype = CI(jnt_type); const idx_t* jq = CI(jnt_qposadr); const idx_t* jd = CI(jnt_dofadr);
   for (int j = w.lane; j < m.njnt; j += 32) { int qa = jq[j], da = jd[j];
     if (jtype[j] == 0) { for (int c = 0; c < 3; c++) w.qpos[qa+c] += h*w.qvel[da+c];
       double wv[3] = {w.qvel[da+3], w.qvel[da+4], w.qvel[da+5]}, nn = sqrt(dot3(wv,wv)), ang = h*nn;

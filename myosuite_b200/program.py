@@ -24,7 +24,8 @@ from . import mjmath as mm
  PD_NDEPTH, PD_EQ_TREE) = range(24)
 NPDIM = 24
 
-PB_STRIDE, PWE_STRIDE, PA_STRIDE, PG_STRIDE, PPAIR_STRIDE, PLIM_STRIDE, PEQ_STRIDE = 18, 16, 28, 16, 12, 12, 16
+PB_STRIDE, PWE_STRIDE, PA_STRIDE, PG_STRIDE, PPAIR_STRIDE, PLIM_STRIDE, PEQ_STRIDE = 22, 16, 28, 16, 12, 12, 16
+PAM_STRIDE, PPAIR_ISTRIDE = 6, 7
 
 # collision function ids
 CT_NONE, CT_CAP_CAP, CT_SPH_SPH, CT_SPH_CAP, CT_PLANE_SPH, CT_PLANE_CAP = range(6)
@@ -76,8 +77,8 @@ def build_program(m):
             quat = mm.quat_normalize(mm.quat_mul(kin0["xquat"][p], m.body_quat[b]))
         R = mm.quat2mat(m.body_iquat[b])
         Il = R @ np.diag(m.body_inertia[b]) @ R.T
-        PB_d[k, 0:3], PB_d[k, 3:7], PB_d[k, 7:10], PB_d[k, 10] = pos, quat, m.body_ipos[b], m.body_mass[b]
-        PB_d[k, 11:17] = [Il[0, 0], Il[1, 1], Il[2, 2], Il[0, 1], Il[0, 2], Il[1, 2]]
+        PB_d[k, 0:3], PB_d[k, 3:12], PB_d[k, 12:15], PB_d[k, 15] = pos, mm.quat2mat(quat).ravel(), m.body_ipos[b], m.body_mass[b]
+        PB_d[k, 16:22] = [Il[0, 0], Il[1, 1], Il[2, 2], Il[0, 1], Il[0, 2], Il[1, 2]]
         for j in range(m.body_jntadr[b], m.body_jntadr[b] + m.body_jntnum[b]):
             if m.jnt_type[j] == mjcf.JNT_FREE and (p in idx or m.body_jntnum[b] != 1):
                 raise mjcf.MJCFError("free joints must be alone on a child of a static body")
@@ -98,7 +99,7 @@ def build_program(m):
         for d in chains[b]:
             j = m.dof_jntid[d]
             flag = 1 if (m.jnt_type[j] == mjcf.JNT_FREE and d - m.jnt_dofadr[j] >= 4) else 0
-            PCH.append(d | (flag << 16))
+            PCH.append(d * 2 + flag)
         PCH_adr.append(len(PCH))
     maxchain = max([len(c) for c in chains.values()] + [0])
     # subtrees among dynamic bodies (self included)
@@ -299,6 +300,8 @@ def build_program(m):
         PWE_d[k, 13:16] = w["s_local"]
     # actuators
     PA_tendon = [ta_index[int(t)] for t in m.actuator_trnid[:, 0]] if m.nu else []
+    if len(set(PA_tendon)) != m.nu:
+        raise mjcf.MJCFError("each actuated tendon must carry exactly one actuator")
     PA_d = np.zeros((m.nu, PA_STRIDE))
     for i in range(m.nu):
         if not (m.actuator_dyntype[i] == mjcf.DYN_MUSCLE and m.actuator_gaintype[i] == mjcf.GAIN_MUSCLE
@@ -307,6 +310,16 @@ def build_program(m):
         PA_d[i, 0:3], PA_d[i, 3:12], PA_d[i, 12:21] = m.actuator_dynprm[i, :3], m.actuator_gainprm[i, :9], m.actuator_biasprm[i, :9]
         PA_d[i, 21:23], PA_d[i, 23:25] = m.actuator_lengthrange[i], m.actuator_ctrlrange[i]
         PA_d[i, 25], PA_d[i, 26] = float(m.actuator_ctrllimited[i]), m.actuator_gear[i, 0]
+    # per-muscle record (peak forces, lengthrange, gear) + shared parameter classes (everything else)
+    PAM_d, PA_cls, cls_rows, cls_index = np.zeros((m.nu, PAM_STRIDE)), [], [], {}
+    for i in range(m.nu):
+        row = PA_d[i].copy()
+        PAM_d[i] = [row[5], row[14], row[21], row[22], row[26], 0.0]      # gain force, bias force, lengthrange, gear
+        row[5] = row[14] = row[21] = row[22] = row[26] = 0.0
+        key = row.tobytes()
+        if key not in cls_index:
+            cls_index[key] = len(cls_rows); cls_rows.append(row)
+        PA_cls.append(cls_index[key])
 
     # ---- collision geoms + pairs
     h = m.opt_timestep
@@ -329,7 +342,7 @@ def build_program(m):
     ctype_of = {(mjcf.GEOM_CAPSULE, mjcf.GEOM_CAPSULE): CT_CAP_CAP, (mjcf.GEOM_SPHERE, mjcf.GEOM_SPHERE): CT_SPH_SPH,
                 (mjcf.GEOM_SPHERE, mjcf.GEOM_CAPSULE): CT_SPH_CAP, (mjcf.GEOM_PLANE, mjcf.GEOM_SPHERE): CT_PLANE_SPH,
                 (mjcf.GEOM_PLANE, mjcf.GEOM_CAPSULE): CT_PLANE_CAP}
-    PPAIR, PPAIR_d, PPATH = [], [], []
+    PPAIR, PPAIR_d, PPATH, PPAIR_tran, pcls_index = [], [], [], [], {}
     maxpath = 0
     pair_model_index = []
     for p in range(m.npair):
@@ -347,9 +360,13 @@ def build_program(m):
             PPATH.append(d * 2 + (1 if moves(d, b2) else 0))
         maxpath = max(maxpath, len(ds))
         K, B, si = _kbimp(m.pair_solref[p], m.pair_solimp[p], h)
-        PPAIR.append([geom_ref(g1), geom_ref(g2), dim, path_adr, len(ds), ct])
         tran = m.body_invweight0[b1, 0] + m.body_invweight0[b2, 0]
-        PPAIR_d.append([m.pair_margin[p], m.pair_gap[p], m.pair_friction[p, 0], m.pair_friction[p, 1], tran, K, B, *si])
+        crow = np.array([m.pair_margin[p], m.pair_gap[p], m.pair_friction[p, 0], m.pair_friction[p, 1], 0.0, K, B, *si])
+        ckey = crow.tobytes()
+        if ckey not in pcls_index:
+            pcls_index[ckey] = len(PPAIR_d); PPAIR_d.append(crow)
+        PPAIR.append([geom_ref(g1), geom_ref(g2), dim, path_adr, len(ds), ct, pcls_index[ckey]])
+        PPAIR_tran.append(tran)
         pair_model_index.append(p)
     # ---- joint limits
     PLIM, PLIM_d = [], []
@@ -401,9 +418,10 @@ def build_program(m):
         "PT_const": np.array(T_const, dtype=np.float64), "PT_piece_adr": ia(PT_piece_adr), "PT_piece": ia(PT_piece),
         "PT_nz_adr": ia(PT_nz_adr), "PNZ_dof": ia(PNZ_dof), "PNZ_tendon": ia(PNZ_tendon), "PNZ_term_adr": ia(PNZ_term_adr),
         "PTERM": ia(PTERM), "PCOL_adr": ia(PCOL_adr), "PCOL": ia(PCOL),
-        "PA_tendon": ia(PA_tendon), "PA_d": PA_d,
+        "PA_tendon": ia(PA_tendon), "PA_d": np.array(cls_rows, dtype=np.float64).reshape(-1, PA_STRIDE), "PA_cls": ia(PA_cls), "PAM_d": PAM_d,
         "PG_body": ia(PG_body), "PG_type": ia(PG_type), "PG_d": np.array(PG_d, dtype=np.float64).reshape(-1, PG_STRIDE),
-        "PPAIR": ia(PPAIR).reshape(-1, 6), "PPAIR_d": np.array(PPAIR_d, dtype=np.float64).reshape(-1, PPAIR_STRIDE),
+        "PPAIR": ia(PPAIR).reshape(-1, PPAIR_ISTRIDE), "PPAIR_d": np.array(PPAIR_d, dtype=np.float64).reshape(-1, PPAIR_STRIDE),
+        "PPAIR_tran": np.array(PPAIR_tran, dtype=np.float64),
         "PPATH": ia(PPATH),
         "PLIM": ia(PLIM).reshape(-1, 2), "PLIM_d": np.array(PLIM_d, dtype=np.float64).reshape(-1, PLIM_STRIDE),
         "PEQ": ia(PEQ).reshape(-1, 6),
