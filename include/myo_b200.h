@@ -59,6 +59,8 @@ typedef struct {
   int32_t reset_random;      /* pose: 1 = qpos ~ U(jnt_range) (reset_type="random"), 0 = init_qpos */
   int32_t maxcon;            /* 0 = library default */
   int32_t reaf_dst, reaf_src;/* reafferentation (base_v0.py:104-108): ctrl[dst] = ctrl[src]; ctrl[src] = 0 ; dst == src = off */
+  int32_t barrier_mode;      /* CTA phase barriers: 0 = between all phases (default), 1 = once per substep, 2 = none (tuning knob) */
+  int32_t reserved_i;
   double pose_thd;           /* pose_v0.py:43 */
   double weights[4];         /* pose, bonus, act_reg, penalty (pose_v0.py:18-23) */
   double solver_tolerance;   /* scaled-gradient stop of the Newton solver; 0 = library default (1e-10) */

@@ -25,7 +25,7 @@ class MyoDims(ctypes.Structure):
 
 class MyoTaskCfg(ctypes.Structure):
     _fields_ = [(n, c_i32) for n in ("task", "frame_skip", "max_episode_steps", "normalize_act", "muscle_condition",
-                                      "auto_reset", "reset_random", "maxcon", "reaf_dst", "reaf_src")] + \
+                                      "auto_reset", "reset_random", "maxcon", "reaf_dst", "reaf_src", "barrier_mode", "reserved_i")] + \
                [("pose_thd", c_f64), ("weights", c_f64 * 4), ("solver_tolerance", c_f64), ("reserved", c_f64 * 6)]
 
 

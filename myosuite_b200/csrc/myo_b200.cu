@@ -90,7 +90,7 @@ __device__ void pose_reward_done(const DevModel& m, Warp& w, const StepArgs& a, 
   *done_out = dist > far_th; }
 
 // ------------------------------------------------------------------ the kernel
-extern "C" __global__ void __launch_bounds__(512) myo_env_kernel(const __grid_constant__ DevModel m, const __grid_constant__ StepArgs a) {
+extern "C" __global__ void __launch_bounds__(384) myo_env_kernel(const __grid_constant__ DevModel m, const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) unsigned long long mbar;
   const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -163,8 +163,8 @@ extern "C" __global__ void __launch_bounds__(512) myo_env_kernel(const __grid_co
       __syncwarp();
     }
     // ---- physics substeps: forward dynamics + semi-implicit Euler (the only copy of the phase code in the kernel)
-    long long cyc[8] = {0,0,0,0,0,0,0,0}; int maxcon_seen = 0, maxefc_seen = 0;
-    #define PH(k, stmt) { __syncthreads(); long long t0_ = prof ? clock64() : 0; if (live) { stmt; } if (prof) cyc[k] += clock64() - t0_; }
+    long long cyc[16] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}; int maxcon_seen = 0, maxefc_seen = 0;
+    #define PH(k, stmt) { if (a.cfg.barrier_mode == 0 || (a.cfg.barrier_mode == 1 && k == 0)) __syncthreads(); long long t0_ = prof ? clock64() : 0; if (live) { stmt; } if (prof) cyc[k] += clock64() - t0_; }
     #pragma unroll 1
     for (int s = 0; s < nsub; s++) {
       const bool tap = s == nsub-1;
@@ -174,13 +174,13 @@ extern "C" __global__ void __launch_bounds__(512) myo_env_kernel(const __grid_co
       PH(3, phase_body_inertia(m, w); phase_crb(m, w); phase_bias(m, w));
       PH(4, phase_collision(m, w));
       PH(5, phase_constraints(m, w); if (tap) write_taps_contacts(m, w, a, env));
-      PH(6, phase_solve(m, w, a.tol));
+      PH(6, phase_solve(m, w, a.tol, prof ? cyc : nullptr));
       PH(7, if (tap) write_taps_solve(m, w, a, env); if (integrate) phase_integrate(m, w));
       if (w.ncon > maxcon_seen) maxcon_seen = w.ncon;
       if (w.nefc > maxefc_seen) maxefc_seen = w.nefc;
     }
     #undef PH
-    if (prof && live && w.lane == 0) { long long* pc = b.tap_phase_cycles + 16*(size_t)env; for (int k = 0; k < 8; k++) pc[k] = cyc[k]; pc[12] = maxcon_seen; pc[13] = maxefc_seen; }
+    if (prof && live && w.lane == 0) { long long* pc = b.tap_phase_cycles + 16*(size_t)env; for (int k = 0; k < 16; k++) pc[k] = cyc[k]; pc[12] = maxcon_seen; pc[13] = maxefc_seen; }
     if (live) {
       if (a.mode == 1) { if (integrate && w.lane == 0 && b.time) b.time[env] += nsub*m.timestep; }
       else if (a.mode == 0) {
@@ -261,7 +261,7 @@ static void fill_devmodel(const myo_model* mm, const myo_task_cfg* cfg, DevModel
   d.s_con = sizeS3; int sizeCon = al2(CON_STRIDE*mc);
   t = sizeS3; d.s_efR = t; t += al2(d.maxefc); d.s_efV = t; t += al2(d.maxefc); d.s_va = t; t += al2(d.nv); d.s_vg = t; t += al2(d.nv); d.s_vp = t; t += al2(d.nv);
   d.s_vMa = t; t += al2(d.nv); d.s_vMp = t; t += al2(d.nv);
-  d.s_H = t; d.s_Hs = t; d.s_LD = t + al2(d.nM); d.s_Dinv = t + 2*al2(d.nM); t += imax(al2(d.nv*d.nv), 2*al2(d.nM) + al2(d.nv)); int sizeS4 = t;
+  d.s_H = t; d.s_Hs = t; d.s_LD = t + al2(d.nM); d.s_Dinv = t + 2*al2(d.nM); t += imax(al2(d.nv*(d.nv+1)/2), 2*al2(d.nM) + al2(d.nv)); int sizeS4 = t;
   int scratch = imax(imax(sizeT, sizeC) + K, imax(sizeS3 + sizeCon + K, sizeS4));
   d.s_xpos = scratch - K; d.s_xmat = d.s_xpos + al2(3*d.nbd);
   d.n_per_warp = d.o_scr + scratch;
@@ -292,11 +292,12 @@ extern "C" int myo_batch_create(const myo_model* m, int device, int n_env, const
   cudaDeviceProp prop; CUDA_OK(cudaGetDeviceProperties(&prop, device));
   b->const_bytes = b->dm.nD*8 + ((b->dm.nI16w + 1)/2)*8;
   int per = b->dm.n_per_warp*8, maxs = (int)prop.sharedMemPerBlockOptin - b->const_bytes - 64;
-  int wpc = maxs/per; if (wpc > 16) wpc = 16; if (wpc < 1) { delete b; return fail("model working set exceeds shared memory of one CTA"); }
+  int wpc = maxs/per; if (wpc > 12) wpc = 12; if (wpc < 1) { delete b; return fail("model working set exceeds shared memory of one CTA"); }
   if (n_env < wpc) wpc = n_env;
   b->warps_per_cta = wpc; b->smem_bytes = b->const_bytes + wpc*per;
   CUDA_OK(cudaFuncSetAttribute(myo_env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes));
-  int need = (n_env + wpc - 1)/wpc, cap = prop.multiProcessorCount; b->grid = need < cap ? need : cap;
+  int ctas_per_sm = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, myo_env_kernel, wpc*32, b->smem_bytes); if (ctas_per_sm < 1) ctas_per_sm = 1;
+  int need = (n_env + wpc - 1)/wpc, cap = prop.multiProcessorCount*ctas_per_sm; b->grid = need < cap ? need : cap;
   *out = b; return 0;
 }
 extern "C" void myo_batch_destroy(myo_batch* b) { if (!b) return; cudaSetDevice(b->device); cudaFree(b->dI); cudaFree(b->dD); delete b; }

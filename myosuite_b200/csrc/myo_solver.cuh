@@ -113,29 +113,62 @@ __device__ void phase_constraints(const DevModel& m, Warp& w) {
   __syncwarp();
 }
 
-// ------------------------------------------------------------------ dense Cholesky (lower, in place) + solve, nv x nv in shared memory
+// ------------------------------------------------------------------ dense Cholesky (packed lower triangle, in place) + solve in shared memory
+#define TRI(i, j) ((i)*((i)+1)/2 + (j))
 __device__ void chol_factor(double* H, int n, int lane) {
   for (int k = 0; k < n; k++) {
-    double dkk = sqrt(fmax(H[k*n+k], MYO_MINVAL));
+    double dkk = sqrt(fmax(H[TRI(k,k)], MYO_MINVAL));
     __syncwarp();
-    if (lane == 0) H[k*n+k] = dkk;
+    if (lane == 0) H[TRI(k,k)] = dkk;
     double inv = 1.0/dkk;
-    for (int i = k+1+lane; i < n; i += 32) H[i*n+k] *= inv;
+    for (int i = k+1+lane; i < n; i += 32) H[TRI(i,k)] *= inv;
     __syncwarp();
-    for (int i = k+1+lane; i < n; i += 32) { double lik = H[i*n+k]; for (int j = k+1; j <= i; j++) H[i*n+j] -= lik*H[j*n+k]; }
+    for (int i = k+1+lane; i < n; i += 32) { double lik = H[TRI(i,k)]; for (int j = k+1; j <= i; j++) H[TRI(i,j)] -= lik*H[TRI(j,k)]; }
     __syncwarp(); }
 }
 // x <- H^-1 x  (H holds the Cholesky factor)
 __device__ void chol_solve(const double* H, int n, double* x, int lane) {
-  for (int k = 0; k < n; k++) { double xk = x[k]/H[k*n+k]; __syncwarp(); if (lane == 0) x[k] = xk;
-    for (int i = k+1+lane; i < n; i += 32) x[i] -= H[i*n+k]*xk; __syncwarp(); }
-  for (int k = n-1; k >= 0; k--) { double xk = x[k]/H[k*n+k]; __syncwarp(); if (lane == 0) x[k] = xk;
-    for (int i = lane; i < k; i += 32) x[i] -= H[k*n+i]*xk; __syncwarp(); }
+  for (int k = 0; k < n; k++) { double xk = x[k]/H[TRI(k,k)]; __syncwarp(); if (lane == 0) x[k] = xk;
+    for (int i = k+1+lane; i < n; i += 32) x[i] -= H[TRI(i,k)]*xk; __syncwarp(); }
+  for (int k = n-1; k >= 0; k--) { double xk = x[k]/H[TRI(k,k)]; __syncwarp(); if (lane == 0) x[k] = xk;
+    for (int i = lane; i < k; i += 32) x[i] -= H[TRI(k,i)]*xk; __syncwarp(); }
 }
+// Register-resident Cholesky + solve for n <= NMAX <= 32: lane i keeps row i of the lower triangle in registers, columns are
+// exchanged with warp shuffles (no shared-memory latency, no barriers).  H: dense n x n in shared memory (read only); x: rhs in / solution out.
+template <int NMAX>
+__device__ __forceinline__ void chol_reg(const double* H, int n, double* x, int lane) {
+  double r[NMAX];
+  #pragma unroll
+  for (int j = 0; j < NMAX; j++) r[j] = (lane < n && j <= lane) ? H[TRI(lane, j)] : 0.0;
+  double b = lane < n ? x[lane] : 0.0, dinv = 1.0;
+  #pragma unroll
+  for (int k = 0; k < NMAX; k++) { if (k < n) {
+    double dk = sqrt(fmax(__shfl_sync(FULL, r[k], k), MYO_MINVAL)), inv = 1.0/dk;
+    if (lane == k) dinv = inv;
+    r[k] *= inv;                                   // lanes > k: L[i][k]; lane k: sqrt(d) (unused below); lanes < k: 0
+    #pragma unroll
+    for (int j = k+1; j < NMAX; j++) { double ljk = __shfl_sync(FULL, r[k], j); if (lane >= j) r[j] -= r[k]*ljk; } } }
+  // forward substitution  L y = b
+  #pragma unroll
+  for (int k = 0; k < NMAX; k++) { if (k < n) { double yk = __shfl_sync(FULL, b*dinv, k); if (lane == k) b = yk; else if (lane > k) b -= r[k]*yk; } }
+  // backward substitution L' x = y  (dot-product form: x_k = (y_k - sum_{i>k} L[i][k] x_i) / L[k][k])
+  #pragma unroll
+  for (int k = NMAX-1; k >= 0; k--) { if (k < n) { double t = lane > k ? r[k]*b : 0.0;
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
+    if (lane == k) b = (b - t)*dinv; } }
+  if (lane < n) x[lane] = b;
+  __syncwarp();
+}
+__device__ __noinline__ void chol_reg8(const double* H, int n, double* x, int lane) { chol_reg<8>(H, n, x, lane); }
+__device__ __noinline__ void chol_reg16(const double* H, int n, double* x, int lane) { chol_reg<16>(H, n, x, lane); }
+__device__ __noinline__ void chol_reg24(const double* H, int n, double* x, int lane) { chol_reg<24>(H, n, x, lane); }
+__device__ __noinline__ void chol_reg32(const double* H, int n, double* x, int lane) { chol_reg<32>(H, n, x, lane); }
+
 __device__ __forceinline__ void load_M_dense(const DevModel& m, const Warp& w, double* H, double diag_scale /* h */) {
-  int n = m.nv; for (int i = w.lane; i < n*n; i += 32) H[i] = 0; __syncwarp();
+  int n = m.nv; for (int i = w.lane; i < n*(n+1)/2; i += 32) H[i] = 0; __syncwarp();
   const idx_t* mi = CI(PM_i); const idx_t* mj = CI(PM_j); const double* dofp = CD(PDOF_d);
-  for (int e = w.lane; e < m.nM; e += 32) { int i = mi[e], j = mj[e]; double v = w.qM[e]; if (i == j) v += diag_scale*dofp[2*i+1]; H[i*n+j] = v; H[j*n+i] = v; }
+  for (int e = w.lane; e < m.nM; e += 32) { int i = mi[e], j = mj[e]; double v = w.qM[e]; if (i == j) v += diag_scale*dofp[2*i+1]; H[TRI(i,j)] = v; }
   __syncwarp(); }
 
 // ------------------------------------------------------------------ tree-sparse L'DL (level-scheduled, left-looking) on the qM layout
@@ -169,7 +202,9 @@ __device__ void ldl_solve(const DevModel& m, const Warp& w, const double* LD, co
 }
 
 // ------------------------------------------------------------------ Newton solver: leaves qacc in s.a
-__device__ void phase_solve(const DevModel& m, Warp& w, double tol) {
+__device__ void phase_solve(const DevModel& m, Warp& w, double tol, long long* cyc) {
+  long long tc = cyc ? clock64() : 0;
+  #define LAP(k) if (cyc) { long long t_ = clock64(); cyc[k] += t_ - tc; tc = t_; }
   Solv s = solv_views(m, w); int n = m.nv, nefc = w.nefc; w.niter = 0;
   if (nefc == 0) {   // unconstrained: qacc = M^-1 qfrc_smooth
     ldl_factor(m, w, w.qM, s.LD, s.Dinv);
@@ -186,13 +221,16 @@ __device__ void phase_solve(const DevModel& m, Warp& w, double tol) {
     for (int r = w.lane; r < nefc; r += 32) { double x = s.jar[r]; s.jv[r] = (r < m.neq || x < 0) ? s.D[r]*x : 0.0; }   // jv used as scratch weights
     __syncwarp(); rows_applyT_add(m, w, s, s.jv, s.g); __syncwarp();
     double gn = 0; for (int i = w.lane; i < n; i += 32) gn += s.g[i]*s.g[i]; gn = sqrt(warp_sum(gn));
+    LAP(8)
     if (scale*gn < tol) break;
+    if (cyc) cyc[14]++;
     // Hessian: tree-sparse L'DL when no contact row is active (limits/equalities keep M's sparsity), dense Cholesky otherwise
     bool dense = (m.neq > 0 && !m.eq_tree);
     for (int c = w.lane; c < w.ncon && !dense; c += 32) { int nr = s.cnrow[c], rb = s.crow[c]; for (int r = 0; r < nr; r++) if (s.jar[rb+r] < 0) dense = true; }
     dense = __any_sync(FULL, dense);
     for (int i = w.lane; i < n; i += 32) s.p[i] = -s.g[i];
     __syncwarp();
+    if (cyc && dense) cyc[15]++;
     if (!dense) {
       const idx_t* madr = CI(dof_Madr);
       for (int e = w.lane; e < m.nM; e += 32) s.Hs[e] = w.qM[e];
@@ -201,25 +239,30 @@ __device__ void phase_solve(const DevModel& m, Warp& w, double tol) {
         if (d2 >= 0) { s.Hs[eq[PEQ_ISTRIDE*e+4]] += De*j2; s.Hs[madr[d2]] += De*j2*j2; } }
       __syncwarp();
       for (int pass = 0; pass < 2; pass++) { for (int r = w.lane; r < w.nlimrow; r += 32) { int dsc = s.lrow[r]; if (((dsc >> 16) & 1) == pass && s.jar[m.neq+r] < 0) s.Hs[madr[dsc & 0xffff]] += s.D[m.neq+r]; } __syncwarp(); }
+      LAP(9)
       ldl_factor(m, w, s.Hs, s.LD, s.Dinv); ldl_solve(m, w, s.LD, s.Dinv, s.p);
+      LAP(10)
     } else {
     load_M_dense(m, w, s.H, 0.0);
-    if (w.lane == 0) for (int e = 0; e < m.neq; e++) { int d1 = eq[PEQ_ISTRIDE*e+1], d2 = eq[PEQ_ISTRIDE*e+3]; double De = s.D[e], j2 = s.eqJ[e]; s.H[d1*n+d1] += De;
-      if (d2 >= 0) { s.H[d1*n+d2] += De*j2; s.H[d2*n+d1] += De*j2; s.H[d2*n+d2] += De*j2*j2; } }
+    if (w.lane == 0) for (int e = 0; e < m.neq; e++) { int d1 = eq[PEQ_ISTRIDE*e+1], d2 = eq[PEQ_ISTRIDE*e+3]; double De = s.D[e], j2 = s.eqJ[e]; s.H[TRI(d1,d1)] += De;
+      if (d2 >= 0) { s.H[d1 > d2 ? TRI(d1,d2) : TRI(d2,d1)] += De*j2; s.H[TRI(d2,d2)] += De*j2*j2; } }
     __syncwarp();
-    for (int pass = 0; pass < 2; pass++) { for (int r = w.lane; r < w.nlimrow; r += 32) { int dsc = s.lrow[r]; if (((dsc >> 16) & 1) == pass && s.jar[m.neq+r] < 0) { int d = dsc & 0xffff; s.H[d*n+d] += s.D[m.neq+r]; } } __syncwarp(); }
+    for (int pass = 0; pass < 2; pass++) { for (int r = w.lane; r < w.nlimrow; r += 32) { int dsc = s.lrow[r]; if (((dsc >> 16) & 1) == pass && s.jar[m.neq+r] < 0) { int d = dsc & 0xffff; s.H[TRI(d,d)] += s.D[m.neq+r]; } } __syncwarp(); }
     for (int c = 0; c < w.ncon; c++) { int nr = s.cnrow[c]; if (!nr) continue; int rb = s.crow[c]; const idx_t* q = pr + PPAIR_ISTRIDE*s.cpair[c]; double W[6] = {0,0,0,0,0,0};  // nn n1 n2 11 12 22
       if (nr == 1) { if (s.jar[rb] < 0) W[0] = s.D[rb]; }
       else { const double* P = pd + q[6]*PPAIR_STRIDE; double mu1 = P[2], mu2 = P[3], Dv = s.D[rb];
         double a0 = s.jar[rb] < 0 ? Dv : 0, a1 = s.jar[rb+1] < 0 ? Dv : 0, a2 = s.jar[rb+2] < 0 ? Dv : 0, a3 = s.jar[rb+3] < 0 ? Dv : 0;
         W[0] = a0+a1+a2+a3; W[1] = mu1*(a0-a1); W[2] = mu2*(a2-a3); W[3] = mu1*mu1*(a0+a1); W[5] = mu2*mu2*(a2+a3); }
       if (W[0] != 0) { const double* J = s.conJ + (size_t)c*3*m.maxpath; int np = q[4];
-        for (int t = w.lane; t < np*np; t += 32) { int ei = t / np, ej = t - ei*np; const double* a = J + 3*ei; const double* b = J + 3*ej;
+        for (int t = w.lane; t < np*np; t += 32) { int ei = t / np, ej = t - ei*np; if ((path[q[3]+ei] >> 1) < (path[q[3]+ej] >> 1)) continue;
+          const double* a = J + 3*ei; const double* b = J + 3*ej;
           double wa0 = W[0]*a[0]+W[1]*a[1]+W[2]*a[2], wa1 = W[1]*a[0]+W[3]*a[1]+W[4]*a[2], wa2 = W[2]*a[0]+W[4]*a[1]+W[5]*a[2];
-          s.H[(path[q[3]+ei] >> 1)*n + (path[q[3]+ej] >> 1)] += wa0*b[0]+wa1*b[1]+wa2*b[2]; } }
+          int di = path[q[3]+ei] >> 1, dj = path[q[3]+ej] >> 1; if (di >= dj) s.H[TRI(di,dj)] += wa0*b[0]+wa1*b[1]+wa2*b[2]; } }
       __syncwarp(); }
-    chol_factor(s.H, n, w.lane);
-    chol_solve(s.H, n, s.p, w.lane);
+    LAP(9)
+    if (n <= 8) chol_reg8(s.H, n, s.p, w.lane); else if (n <= 16) chol_reg16(s.H, n, s.p, w.lane); else if (n <= 24) chol_reg24(s.H, n, s.p, w.lane);
+    else if (n <= 32) chol_reg32(s.H, n, s.p, w.lane); else { chol_factor(s.H, n, w.lane); chol_solve(s.H, n, s.p, w.lane); }
+    LAP(10)
     }
     // exact line search along p
     mul_M(m, w, s.Mp, s.p); rows_apply(m, w, s, s.p, s.jv); __syncwarp();
@@ -236,7 +279,8 @@ __device__ void phase_solve(const DevModel& m, Warp& w, double tol) {
     if (alpha == 0) break;   // no descent possible: converged to round-off
     for (int i = w.lane; i < n; i += 32) { s.a[i] += alpha*s.p[i]; s.Ma[i] += alpha*s.Mp[i]; }
     for (int r = w.lane; r < nefc; r += 32) s.jar[r] += alpha*s.jv[r];
-    __syncwarp(); w.niter = iter+1; }
+    __syncwarp(); w.niter = iter+1; LAP(11) }
+  #undef LAP
 }
 
 // ------------------------------------------------------------------ semi-implicit Euler with implicit joint damping

@@ -261,7 +261,7 @@ def build_program(m):
                 j += 2
         T_const.append(const); T_pieces.append(pieces)
     # sort wrap elements by (type, inside) so that a warp round is branch-uniform
-    we_order = sorted(range(len(we_list)), key=lambda k: (we_list[k]["typ"], we_list[k]["inside"], k))
+    we_order = sorted(range(len(we_list)), key=lambda k: (-we_list[k]["inside"], we_list[k]["typ"], k))
     we_new = {old: new for new, old in enumerate(we_order)}
     we_sorted = [we_list[k] for k in we_order]
     nsp, nwe = len(sp_list), len(we_sorted)

@@ -86,6 +86,7 @@ class MyoVecEnv:
         cfg.weights[0], cfg.weights[1], cfg.weights[2], cfg.weights[3] = w["pose"], w["bonus"], w["act_reg"], w["penalty"]
         cfg.solver_tolerance = float(kw.get("solver_tolerance", 0.0))
         cfg.maxcon = int(kw.get("maxcon", 0))
+        cfg.barrier_mode = int(kw.get("barrier_mode", 0))
         cfg.reaf_dst = cfg.reaf_src = -1
         if self.muscle_condition == "reafferentation":   # base_v0.py:78-79,104-108
             cfg.reaf_dst, cfg.reaf_src = m.name2id("actuator", "EPL"), m.name2id("actuator", "EIP")
