@@ -19,7 +19,7 @@ typedef short idx_t;
 
 // P_dims slots (must match myosuite_b200/program.py)
 enum { PD_NBD, PD_NLEVEL, PD_NPT, PD_NSP, PD_NWE, PD_NTA, PD_NNZ, PD_NTERM, PD_NLIM, PD_NEQ, PD_NPAIR, PD_NGC, PD_MAXPATH,
-       PD_MAXCHAIN, PD_NSUB, PD_NROW, PD_NCOL, PD_NPIECE, PD_NWE_SPH_OUT, PD_NWE_SPH_IN, PD_NWE_CYL_OUT, PD_NWE_CYL_IN, PD_NDEPTH, PD_EQ_TREE };
+       PD_MAXCHAIN, PD_NSUB, PD_NROW, PD_NCOL, PD_NPIECE, PD_NWE_SPH_OUT, PD_NWE_SPH_IN, PD_NWE_CYL_OUT, PD_NWE_CYL_IN, PD_NDEPTH, PD_EQ_TREE, PD_NPAIR_ANALYTIC };
 #define PB_STRIDE 22      // pos[3] R[9] ipos[3] mass Iloc[6]
 #define PWE_STRIDE 16
 #define PA_STRIDE 28
@@ -30,7 +30,7 @@ enum { PD_NBD, PD_NLEVEL, PD_NPT, PD_NSP, PD_NWE, PD_NTA, PD_NNZ, PD_NTERM, PD_N
 #define PLIM_STRIDE 12
 #define PEQ_STRIDE 16
 #define PEQ_ISTRIDE 6
-enum { CT_NONE, CT_CAP_CAP, CT_SPH_SPH, CT_SPH_CAP, CT_PLANE_SPH, CT_PLANE_CAP };
+enum { CT_NONE, CT_CAP_CAP, CT_SPH_SPH, CT_SPH_CAP, CT_PLANE_SPH, CT_PLANE_CAP, CT_PLANE_ELL, CT_CAP_ELL, CT_ELL_ELL };
 #define CON_STRIDE 14   // dist, pos[3], frame[9], pad
 
 // ------------------------------------------------------------------ device-resident model view (kernel parameter)
@@ -39,7 +39,7 @@ struct DevModel {
   int32_t nI16w, nD;                       // sizes: int32 words of packed int16, doubles
   int32_t hoff[MYO_NSEC];                  // offset of each hot section (in shorts / doubles), -1 if not staged
   int32_t nq, nv, nu, na, nM, njnt;
-  int32_t nbd, nlevel, nsp, nwe, nta, nnz, nlim, neq, npair, maxpath, ndepth, eq_tree;
+  int32_t nbd, nlevel, nsp, nwe, nta, nnz, nlim, neq, npair, npair_an, maxpath, ndepth, eq_tree;
   int32_t maxcon, maxefc;
   double timestep, gx, gy, gz, meaninertia, tolerance;
   // per-warp shared-memory layout, in doubles.  Persistent part:
@@ -49,6 +49,7 @@ struct DevModel {
   int32_t s_U, s_WP, s_PL, s_mom, s_tlen, s_tvel, s_tfrc;  // stage 1: tendons + actuation
   int32_t s_cin, s_crb, s_bf;                              // stage 2: CRB / bias
   int32_t s_conJ, s_efD, s_efA, s_eqJ, s_icon, s_con;      // stage 3 -> 4: contacts / constraint rows
+  int32_t s_cres, s_clist, s_cidx, kcand;                  // collision only: results / list / per-pair slot of the expensive (ellipsoid) candidates
   int32_t s_efR, s_efV, s_va, s_vg, s_vp, s_vMa, s_vMp, s_H, s_Hs, s_LD, s_Dinv;   // stage 4: Newton
 };
 
@@ -410,6 +411,59 @@ __device__ __forceinline__ void geom_pose(const DevModel& m, const Warp& w, int 
   else { const double* X = SCR(s_xmat) + 9*b; const double* xp = SCR(s_xpos) + 3*b; mat_vec(pos, X, gd); pos[0]+=xp[0]; pos[1]+=xp[1]; pos[2]+=xp[2];
     double z[3] = {gd[5], gd[8], gd[11]}; mat_vec(axis, X, z); } }
 
+// full world rotation of a collision geom (ellipsoids need it)
+__device__ __forceinline__ void geom_mat(const DevModel& m, const Warp& w, int g, double* mat) {
+  int b = CI(PG_body)[g]; const double* gd = CD(PG_d) + g*PG_STRIDE;
+  if (b < 0) { for (int c = 0; c < 9; c++) mat[c] = gd[3+c]; } else mat_mul(mat, SCR(s_xmat) + 9*b, gd + 3); }
+
+// ---- ellipsoid colliders.  MuJoCo routes ellipsoid-capsule / ellipsoid-ellipsoid through its general convex collider: one
+// contact, signed distance = max over unit d of  d.(c2-c1) - h1(d) - h2(-d)  (h = support function), witnesses = support points.
+// Here: Newton on the unit sphere for that maximisation (smooth for ellipsoids and points).
+// body 1: ellipsoid (R1, s1) or a point (s1 == nullptr); body 2: ellipsoid.  dl = c2 - c1.  d: in = start, out = maximiser.
+// p1, p2: support offsets (witness on body 1 = c1 + p1, on body 2 = c2 - p2).
+__device__ __noinline__ double ell_sd(const double* dl, const double* R1, const double* s1, const double* R2, const double* s2, double* d, double* p1, double* p2) {
+  double f = 0;
+  #pragma unroll 1
+  for (int it = 0; it < 40; it++) {
+    double a[3], u[3], n1 = 0, n2;
+    p1[0] = p1[1] = p1[2] = 0;
+    if (s1) { matT_vec(a, R1, d); u[0] = s1[0]*s1[0]*a[0]; u[1] = s1[1]*s1[1]*a[1]; u[2] = s1[2]*s1[2]*a[2]; n1 = sqrt(dot3(a, u)); mat_vec(p1, R1, u); double q = 1.0/n1; p1[0]*=q; p1[1]*=q; p1[2]*=q; }
+    matT_vec(a, R2, d); u[0] = s2[0]*s2[0]*a[0]; u[1] = s2[1]*s2[1]*a[1]; u[2] = s2[2]*s2[2]*a[2]; n2 = sqrt(dot3(a, u)); mat_vec(p2, R2, u); { double q = 1.0/n2; p2[0]*=q; p2[1]*=q; p2[2]*=q; }
+    double g[3] = {dl[0]-p1[0]-p2[0], dl[1]-p1[1]-p2[1], dl[2]-p1[2]-p2[2]};
+    f = dot3(d, dl) - n1 - n2;
+    // tangent basis
+    double e[3] = {0,0,0}; { int k = fabs(d[0]) < fabs(d[1]) ? (fabs(d[0]) < fabs(d[2]) ? 0 : 2) : (fabs(d[1]) < fabs(d[2]) ? 1 : 2); e[k] = 1; }
+    double t1[3], t2[3]; cross3(t1, d, e); { double q = 1.0/sqrt(dot3(t1,t1)); t1[0]*=q; t1[1]*=q; t1[2]*=q; } cross3(t2, d, t1);
+    double g1 = dot3(t1, g), g2 = dot3(t2, g), scale = sqrt(dot3(dl,dl)) + n1 + n2;
+    if (g1*g1 + g2*g2 < 1e-24*scale*scale) break;      // tangential gradient ~1e-12: direction converged to round-off
+    // tangent Hessian of the Lagrangian:  -sum_i (t_k.A_i t_l - (t_k.p_i)(t_l.p_i))/n_i - f delta_kl
+    double H11 = -f, H12 = 0, H22 = -f;
+    { double b1[3], b2[3], v[3]; matT_vec(b1, R2, t1); matT_vec(b2, R2, t2);
+      v[0] = s2[0]*s2[0]; v[1] = s2[1]*s2[1]; v[2] = s2[2]*s2[2];
+      double a11 = v[0]*b1[0]*b1[0]+v[1]*b1[1]*b1[1]+v[2]*b1[2]*b1[2], a12 = v[0]*b1[0]*b2[0]+v[1]*b1[1]*b2[1]+v[2]*b1[2]*b2[2], a22 = v[0]*b2[0]*b2[0]+v[1]*b2[1]*b2[1]+v[2]*b2[2]*b2[2];
+      double q1 = dot3(t1, p2), q2 = dot3(t2, p2), in = 1.0/n2; H11 -= (a11-q1*q1)*in; H12 -= (a12-q1*q2)*in; H22 -= (a22-q2*q2)*in;
+    }
+    if (s1) { double b1[3], b2[3], v[3]; matT_vec(b1, R1, t1); matT_vec(b2, R1, t2);
+      v[0] = s1[0]*s1[0]; v[1] = s1[1]*s1[1]; v[2] = s1[2]*s1[2];
+      double a11 = v[0]*b1[0]*b1[0]+v[1]*b1[1]*b1[1]+v[2]*b1[2]*b1[2], a12 = v[0]*b1[0]*b2[0]+v[1]*b1[1]*b2[1]+v[2]*b1[2]*b2[2], a22 = v[0]*b2[0]*b2[0]+v[1]*b2[1]*b2[1]+v[2]*b2[2]*b2[2];
+      double q1 = dot3(t1, p1), q2 = dot3(t2, p1), in = 1.0/n1; H11 -= (a11-q1*q1)*in; H12 -= (a12-q1*q2)*in; H22 -= (a22-q2*q2)*in; }
+    double det = H11*H22 - H12*H12, dx, dy;
+    if (H11 < 0 && det > 0) { double id = 1.0/det; dx = -(H22*g1 - H12*g2)*id; dy = -(-H12*g1 + H11*g2)*id; }
+    else { double L = fabs(H11) + fabs(H22) + fabs(H12) + 1e-12; dx = g1/L; dy = g2/L; }     // safeguarded ascent step
+    double nn = sqrt(dx*dx + dy*dy); if (nn > 0.5) { dx *= 0.5/nn; dy *= 0.5/nn; }
+    bool last = nn < 1e-12;                            // a step this small cannot change the result
+    // backtracking: accept the first step that does not decrease f
+    #pragma unroll 1
+    for (int bt = 0; bt < 12; bt++) { double dn[3] = {d[0]+dx*t1[0]+dy*t2[0], d[1]+dx*t1[1]+dy*t2[1], d[2]+dx*t1[2]+dy*t2[2]}; double q = 1.0/sqrt(dot3(dn,dn)); dn[0]*=q; dn[1]*=q; dn[2]*=q;
+      double fn = dot3(dn, dl); { double aa[3]; matT_vec(aa, R2, dn); fn -= sqrt(s2[0]*s2[0]*aa[0]*aa[0]+s2[1]*s2[1]*aa[1]*aa[1]+s2[2]*s2[2]*aa[2]*aa[2]); }
+      if (s1) { double aa[3]; matT_vec(aa, R1, dn); fn -= sqrt(s1[0]*s1[0]*aa[0]*aa[0]+s1[1]*s1[1]*aa[1]*aa[1]+s1[2]*s1[2]*aa[2]*aa[2]); }
+      if (fn >= f - 1e-14*scale || bt == 11) { d[0]=dn[0]; d[1]=dn[1]; d[2]=dn[2]; break; }
+      dx *= 0.5; dy *= 0.5; }
+    if (last) break;
+  }
+  return f;
+}
+
 struct ConOut { int n; double dist[2]; double pos[2][3]; double nrm[2][3]; double yh[3]; bool has_y; };
 __device__ __forceinline__ void sph_sph(ConOut& o, double margin, const double* p1, double r1, const double* p2, double r2) {
   double dv[3] = {p2[0]-p1[0], p2[1]-p1[1], p2[2]-p1[2]}, cd = sqrt(dot3(dv,dv)), dist = cd-r1-r2;
@@ -453,28 +507,102 @@ __device__ void collide_pair(const DevModel& m, const Warp& w, int p, ConOut& o)
   } else if (ct == CT_PLANE_CAP) { double e[3];
     for (int k = 0; k < 3; k++) e[k] = x2[k]+a2[k]*s2[1]; plane_sph(o, margin, x1, a1, e, s2[0]);
     for (int k = 0; k < 3; k++) e[k] = x2[k]-a2[k]*s2[1]; plane_sph(o, margin, x1, a1, e, s2[0]);
-    o.has_y = true; o.yh[0]=a2[0]; o.yh[1]=a2[1]; o.yh[2]=a2[2]; }
+    o.has_y = true; o.yh[0]=a2[0]; o.yh[1]=a2[1]; o.yh[2]=a2[2];
+  } else if (ct == CT_PLANE_ELL) {   // deepest point of the ellipsoid along -normal
+    double R2[9], nl[3], u[3], pw[3]; geom_mat(m, w, g2, R2); matT_vec(nl, R2, a1);
+    u[0] = s2[0]*s2[0]*nl[0]; u[1] = s2[1]*s2[1]*nl[1]; u[2] = s2[2]*s2[2]*nl[2]; double nn = sqrt(dot3(nl, u)); mat_vec(pw, R2, u);
+    double pos[3] = {x2[0]-pw[0]/nn, x2[1]-pw[1]/nn, x2[2]-pw[2]/nn}, dv[3] = {pos[0]-x1[0], pos[1]-x1[1], pos[2]-x1[2]}, dist = dot3(dv, a1);
+    if (dist <= margin) { o.n = 1; o.dist[0] = dist; for (int k = 0; k < 3; k++) { o.nrm[0][k] = a1[k]; o.pos[0][k] = pos[k]-a1[k]*0.5*dist; } }
+  } else if (ct == CT_CAP_ELL) {     // g1 capsule (segment + radius), g2 ellipsoid: min over the segment of the point-ellipsoid distance
+    double r = s1[0], h = s1[1], dv[3] = {x2[0]-x1[0], x2[1]-x1[1], x2[2]-x1[2]}, rb = fmax(s2[0], fmax(s2[1], s2[2]));
+    double d[3], p1[3], p2[3], t = clipd(dot3(dv, a1), -h, h), dl[3];
+    { double q[3] = {dv[0]-a1[0]*t, dv[1]-a1[1]*t, dv[2]-a1[2]*t}; if (sqrt(dot3(q,q)) - r - rb > margin) return; }
+    double R2[9]; geom_mat(m, w, g2, R2);
+    { double q[3] = {dv[0]-a1[0]*t, dv[1]-a1[1]*t, dv[2]-a1[2]*t}, n = sqrt(dot3(q,q)); if (n < MYO_MINVAL) { d[0]=a1[1]; d[1]=a1[2]; d[2]=a1[0]; } else { d[0]=q[0]/n; d[1]=q[1]/n; d[2]=q[2]/n; } }
+    double lo = -h, hi = h, tl = 0, gl = 0, sd = 0; bool have = false;
+    #pragma unroll 1
+    for (int it = 0; it < 40; it++) {
+      dl[0] = dv[0]-a1[0]*t; dl[1] = dv[1]-a1[1]*t; dl[2] = dv[2]-a1[2]*t;
+      sd = ell_sd(dl, nullptr, nullptr, R2, s2, d, p1, p2);
+      double g = -dot3(d, a1);                      // d(phi)/dt, monotone increasing in t
+      if (fabs(g) < 1e-11 || (t >= h && g <= 0) || (t <= -h && g >= 0)) break;
+      double tn;
+      if (g > 0) hi = t; else lo = t;
+      if (have && g != gl) tn = t - g*(t-tl)/(g-gl); else tn = g > 0 ? (it == 0 ? -h : 0.5*(lo+hi)) : (it == 0 ? h : 0.5*(lo+hi));
+      if (!(tn > lo && tn < hi)) tn = (it < 2) ? (g > 0 ? lo : hi) : 0.5*(lo+hi);
+      if (hi - lo < 1e-13*(h + 1e-3) || fabs(tn - t) < 1e-14*(h + 1e-3)) { t = tn; break; }
+      tl = t; gl = g; have = true; t = tn; }
+    double dist = sd - r;
+    if (dist <= margin) { o.n = 1; o.dist[0] = dist; for (int k = 0; k < 3; k++) { o.nrm[0][k] = d[k];
+        double wa = x1[k]+a1[k]*t + d[k]*r, wb = x2[k]-p2[k]; o.pos[0][k] = 0.5*(wa+wb); } }
+  } else if (ct == CT_ELL_ELL) {
+    double dl[3] = {x2[0]-x1[0], x2[1]-x1[1], x2[2]-x1[2]}, cd = sqrt(dot3(dl,dl));
+    if (cd - fmax(s1[0], fmax(s1[1], s1[2])) - fmax(s2[0], fmax(s2[1], s2[2])) > margin) return;
+    double R1[9], R2[9], d[3], p1[3], p2[3]; geom_mat(m, w, g1, R1); geom_mat(m, w, g2, R2);
+    if (cd < MYO_MINVAL) { d[0]=1; d[1]=0; d[2]=0; } else { d[0]=dl[0]/cd; d[1]=dl[1]/cd; d[2]=dl[2]/cd; }
+    double dist = ell_sd(dl, R1, s1, R2, s2, d, p1, p2);
+    if (dist <= margin) { o.n = 1; o.dist[0] = dist; for (int k = 0; k < 3; k++) { o.nrm[0][k] = d[k]; o.pos[0][k] = 0.5*((x1[k]+p1[k]) + (x2[k]-p2[k])); } }
+  }
 }
 
+// cheap conservative test for the iterative (ellipsoid) colliders: can this pair be within its margin at all?
+__device__ __forceinline__ bool expensive_candidate(const DevModel& m, const Warp& w, int p) {
+  const idx_t* pr = CI(PPAIR) + PPAIR_ISTRIDE*p; const double* pd = CD(PPAIR_d) + pr[6]*PPAIR_STRIDE; const double* G = CD(PG_d);
+  int g1 = pr[0], g2 = pr[1]; const double* s1 = G + g1*PG_STRIDE + 12; const double* s2 = G + g2*PG_STRIDE + 12; double margin = pd[0];
+  double x1[3], a1[3], x2[3], a2[3]; geom_pose(m, w, g1, x1, a1); geom_pose(m, w, g2, x2, a2);
+  double dv[3] = {x2[0]-x1[0], x2[1]-x1[1], x2[2]-x1[2]}, rb2 = fmax(s2[0], fmax(s2[1], s2[2]));
+  // any unit direction d gives a lower bound  d.(c2-c1) - h1(d) - h2(d)  on the signed distance: use the centre-to-centre
+  // (or centre-to-segment) direction -- tight for the flat finger-pad ellipsoids, unlike a bounding sphere
+  if (pr[5] == CT_CAP_ELL) { double t = clipd(dot3(dv, a1), -s1[1], s1[1]), q[3] = {dv[0]-a1[0]*t, dv[1]-a1[1]*t, dv[2]-a1[2]*t}, nq = sqrt(dot3(q,q));
+    if (nq - s1[0] - rb2 > margin) return false;
+    if (nq < MYO_MINVAL) return true;
+    double R2[9], b[3], d[3] = {q[0]/nq, q[1]/nq, q[2]/nq}; geom_mat(m, w, g2, R2); matT_vec(b, R2, d);
+    return nq - sqrt(s2[0]*s2[0]*b[0]*b[0]+s2[1]*s2[1]*b[1]*b[1]+s2[2]*s2[2]*b[2]*b[2]) - s1[0] <= margin; }
+  double cd = sqrt(dot3(dv,dv));
+  if (cd - fmax(s1[0], fmax(s1[1], s1[2])) - rb2 > margin) return false;
+  if (cd < MYO_MINVAL) return true;
+  double R1[9], R2[9], b[3], c[3], d[3] = {dv[0]/cd, dv[1]/cd, dv[2]/cd}; geom_mat(m, w, g1, R1); geom_mat(m, w, g2, R2); matT_vec(b, R1, d); matT_vec(c, R2, d);
+  return cd - sqrt(s1[0]*s1[0]*b[0]*b[0]+s1[1]*s1[1]*b[1]*b[1]+s1[2]*s1[2]*b[2]*b[2]) - sqrt(s2[0]*s2[0]*c[0]*c[0]+s2[1]*s2[1]*c[1]*c[1]+s2[2]*s2[2]*c[2]*c[2]) <= margin; }
+
+__device__ __forceinline__ void store_contact(const DevModel& m, Warp& w, double* con, int* icon, int ci, int p, const ConOut& o, int c) {
+  if (ci >= m.maxcon) return;
+  double* cd = con + ci*CON_STRIDE; cd[0] = o.dist[c]; cd[1]=o.pos[c][0]; cd[2]=o.pos[c][1]; cd[3]=o.pos[c][2];
+  double* f = cd + 4; f[0]=o.nrm[c][0]; f[1]=o.nrm[c][1]; f[2]=o.nrm[c][2];
+  // complete the contact frame (rows: normal, tangent1, tangent2)
+  double y[3] = {0,0,0};
+  if (o.has_y) { y[0]=o.yh[0]; y[1]=o.yh[1]; y[2]=o.yh[2]; }
+  if (sqrt(dot3(y,y)) < 0.5) { y[0]=0; y[1]=0; y[2]=0; if (f[1] < 0.5 && f[1] > -0.5) y[1] = 1; else y[2] = 1; }
+  double dd = dot3(f, y); y[0]-=dd*f[0]; y[1]-=dd*f[1]; y[2]-=dd*f[2]; double n = 1.0/sqrt(dot3(y,y)); y[0]*=n; y[1]*=n; y[2]*=n;
+  f[3]=y[0]; f[4]=y[1]; f[5]=y[2]; cross3(f+6, f, y);
+  icon[ci] = p; }
+
+// Contacts are listed analytic colliders first (pair order), then the iterative ellipsoid colliders (pair order).
 __device__ void phase_collision(const DevModel& m, Warp& w) {
   double* con = SCR(s_con); int* icon = (int*)SCR(s_icon);
   int ncon = 0; w.overflow = 0;
+  // analytic primitives: one pair per lane
   #pragma unroll 1
-  for (int base = 0; base < m.npair; base += 32) { int p = base + w.lane; ConOut o; o.n = 0; o.has_y = false;
-    if (p < m.npair) collide_pair(m, w, p, o);
+  for (int base = 0; base < m.npair_an; base += 32) { int p = base + w.lane; ConOut o; o.n = 0; o.has_y = false;
+    if (p < m.npair_an) collide_pair(m, w, p, o);
     unsigned m0 = __ballot_sync(FULL, o.n >= 1), m1 = __ballot_sync(FULL, o.n >= 2), lt = (1u << w.lane) - 1;
     int idx = ncon + __popc(m0 & lt) + __popc(m1 & lt);
-    for (int c = 0; c < o.n; c++) { int ci = idx + c;
-      if (ci < m.maxcon) { double* cd = con + ci*CON_STRIDE; cd[0] = o.dist[c]; cd[1]=o.pos[c][0]; cd[2]=o.pos[c][1]; cd[3]=o.pos[c][2];
-        double* f = cd + 4; f[0]=o.nrm[c][0]; f[1]=o.nrm[c][1]; f[2]=o.nrm[c][2];
-        // complete the contact frame (rows: normal, tangent1, tangent2)
-        double y[3] = {0,0,0};
-        if (o.has_y) { y[0]=o.yh[0]; y[1]=o.yh[1]; y[2]=o.yh[2]; }
-        if (sqrt(dot3(y,y)) < 0.5) { y[0]=0; y[1]=0; y[2]=0; if (f[1] < 0.5 && f[1] > -0.5) y[1] = 1; else y[2] = 1; }
-        double dd = dot3(f, y); y[0]-=dd*f[0]; y[1]-=dd*f[1]; y[2]-=dd*f[2]; double n = 1.0/sqrt(dot3(y,y)); y[0]*=n; y[1]*=n; y[2]*=n;
-        f[3]=y[0]; f[4]=y[1]; f[5]=y[2]; cross3(f+6, f, y);
-        icon[ci] = p; } }
+    for (int c = 0; c < o.n; c++) store_contact(m, w, con, icon, idx + c, p, o, c);
     ncon += __popc(m0) + __popc(m1); }
+  // iterative ellipsoid colliders: rare and expensive -> conservative cull, compact, then one surviving candidate per lane
+  int* clist = (int*)SCR(s_clist);
+  #pragma unroll 1
+  for (int cbase = m.npair_an; cbase < m.npair; ) { int ncand = 0;
+    #pragma unroll 1
+    for (; cbase < m.npair && ncand + 32 <= m.kcand; cbase += 32) { int p = cbase + w.lane; bool cand = p < m.npair && expensive_candidate(m, w, p);
+      unsigned mk = __ballot_sync(FULL, cand); if (cand) clist[ncand + __popc(mk & ((1u << w.lane) - 1))] = p; ncand += __popc(mk); }
+    __syncwarp();
+    #pragma unroll 1
+    for (int kb = 0; kb < ncand; kb += 32) { int k = kb + w.lane; ConOut o; o.n = 0; o.has_y = false; int p = k < ncand ? clist[k] : 0;
+      if (k < ncand) collide_pair(m, w, p, o);
+      unsigned m0 = __ballot_sync(FULL, o.n >= 1); int idx = ncon + __popc(m0 & ((1u << w.lane) - 1));
+      if (o.n) store_contact(m, w, con, icon, idx, p, o, 0);
+      ncon += __popc(m0); }
+    __syncwarp(); }
   if (ncon > m.maxcon) { w.overflow = 1; ncon = m.maxcon; }
   w.ncon = ncon;
   __syncwarp();

@@ -1022,7 +1022,8 @@ def _build_collision_pairs(m, xpairs, drop, meshes, mesh_props, G):
     m.pair_gap = np.array([k[2]["gap"] for k in kept], dtype=np.float64)
     m.pair_dropped = dropped
     supported = {(GEOM_PLANE, GEOM_SPHERE), (GEOM_PLANE, GEOM_CAPSULE), (GEOM_SPHERE, GEOM_SPHERE),
-                 (GEOM_SPHERE, GEOM_CAPSULE), (GEOM_CAPSULE, GEOM_CAPSULE)}
+                 (GEOM_SPHERE, GEOM_CAPSULE), (GEOM_CAPSULE, GEOM_CAPSULE), (GEOM_PLANE, GEOM_ELLIPSOID),
+                 (GEOM_CAPSULE, GEOM_ELLIPSOID), (GEOM_ELLIPSOID, GEOM_ELLIPSOID)}
     m.pair_unsupported = [(int(a), int(b)) for a, b in zip(m.pair_geom1, m.pair_geom2)
                           if (int(m.geom_type[a]), int(m.geom_type[b])) not in supported]
 

@@ -21,14 +21,14 @@ from . import mjmath as mm
 # P_dims slots
 (PD_NBD, PD_NLEVEL, PD_NPT, PD_NSP, PD_NWE, PD_NTA, PD_NNZ, PD_NTERM, PD_NLIM, PD_NEQ, PD_NPAIR, PD_NGC, PD_MAXPATH,
  PD_MAXCHAIN, PD_NSUB, PD_NROW, PD_NCOL, PD_NPIECE, PD_NWE_SPH_OUT, PD_NWE_SPH_IN, PD_NWE_CYL_OUT, PD_NWE_CYL_IN,
- PD_NDEPTH, PD_EQ_TREE) = range(24)
-NPDIM = 24
+ PD_NDEPTH, PD_EQ_TREE, PD_NPAIR_ANALYTIC) = range(25)
+NPDIM = 26
 
 PB_STRIDE, PWE_STRIDE, PA_STRIDE, PG_STRIDE, PPAIR_STRIDE, PLIM_STRIDE, PEQ_STRIDE = 22, 16, 28, 16, 12, 12, 16
 PAM_STRIDE, PPAIR_ISTRIDE = 6, 7
 
 # collision function ids
-CT_NONE, CT_CAP_CAP, CT_SPH_SPH, CT_SPH_CAP, CT_PLANE_SPH, CT_PLANE_CAP = range(6)
+CT_NONE, CT_CAP_CAP, CT_SPH_SPH, CT_SPH_CAP, CT_PLANE_SPH, CT_PLANE_CAP, CT_PLANE_ELL, CT_CAP_ELL, CT_ELL_ELL = range(9)
 
 
 def _kbimp(solref, solimp, timestep):
@@ -341,15 +341,19 @@ def build_program(m):
 
     ctype_of = {(mjcf.GEOM_CAPSULE, mjcf.GEOM_CAPSULE): CT_CAP_CAP, (mjcf.GEOM_SPHERE, mjcf.GEOM_SPHERE): CT_SPH_SPH,
                 (mjcf.GEOM_SPHERE, mjcf.GEOM_CAPSULE): CT_SPH_CAP, (mjcf.GEOM_PLANE, mjcf.GEOM_SPHERE): CT_PLANE_SPH,
-                (mjcf.GEOM_PLANE, mjcf.GEOM_CAPSULE): CT_PLANE_CAP}
+                (mjcf.GEOM_PLANE, mjcf.GEOM_CAPSULE): CT_PLANE_CAP, (mjcf.GEOM_PLANE, mjcf.GEOM_ELLIPSOID): CT_PLANE_ELL,
+                (mjcf.GEOM_CAPSULE, mjcf.GEOM_ELLIPSOID): CT_CAP_ELL, (mjcf.GEOM_ELLIPSOID, mjcf.GEOM_ELLIPSOID): CT_ELL_ELL}
     PPAIR, PPAIR_d, PPATH, PPAIR_tran, pcls_index = [], [], [], [], {}
     maxpath = 0
     pair_model_index = []
-    for p in range(m.npair):
+    def _ct(p):
+        return ctype_of.get((int(m.geom_type[int(m.pair_geom1[p])]), int(m.geom_type[int(m.pair_geom2[p])])), CT_NONE)
+    pair_order = [p for p in range(m.npair) if _ct(p) not in (CT_NONE, CT_CAP_ELL, CT_ELL_ELL)] + \
+                 [p for p in range(m.npair) if _ct(p) in (CT_CAP_ELL, CT_ELL_ELL)]
+    n_analytic = sum(1 for p in pair_order if _ct(p) not in (CT_CAP_ELL, CT_ELL_ELL))
+    for p in pair_order:
         g1, g2 = int(m.pair_geom1[p]), int(m.pair_geom2[p])
-        ct = ctype_of.get((int(m.geom_type[g1]), int(m.geom_type[g2])), CT_NONE)
-        if ct == CT_NONE:
-            continue     # unsupported narrow-phase (ellipsoid/mesh/hfield): listed in m.pair_unsupported
+        ct = _ct(p)
         dim = int(m.pair_dim[p])
         if dim not in (1, 3):
             raise mjcf.MJCFError("condim %d not supported" % dim)
@@ -400,7 +404,7 @@ def build_program(m):
     dims[PD_MAXPATH], dims[PD_MAXCHAIN], dims[PD_NSUB], dims[PD_NROW], dims[PD_NCOL] = maxpath, maxchain, len(PSUB), len(PROW_col), len(PCOL)
     dims[PD_NPIECE] = len(PT_piece)
     dims[PD_NWE_SPH_OUT], dims[PD_NWE_SPH_IN], dims[PD_NWE_CYL_OUT], dims[PD_NWE_CYL_IN] = counts
-    dims[PD_NDEPTH], dims[PD_EQ_TREE] = ndepth, eq_tree
+    dims[PD_NDEPTH], dims[PD_EQ_TREE], dims[PD_NPAIR_ANALYTIC] = ndepth, eq_tree, n_analytic
 
     def ia(x, shape=None):
         a = np.asarray(x, dtype=np.int32)

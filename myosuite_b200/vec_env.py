@@ -50,17 +50,27 @@ _MODEL_OF_XML = {v[0]: k for k, v in assets.MODEL_XML.items()}
 class MyoVecEnv:
     """n independent envs of one registry id, resident on one GPU.  Tensors in, tensors out."""
 
+    @classmethod
+    def from_model(cls, model_name, num_envs, **kw):
+        """Physics-only batch of a named model asset (no task logic: obs_dim 0, no reset sampling)."""
+        return cls(None, num_envs, model=assets.load(model_name), **kw)
+
     def __init__(self, env_id, num_envs, device=0, seed=0, env_offset=0, auto_reset=True, taps=False, model=None, **overrides):
         import torch
         self.torch = torch
         if not torch.cuda.is_available():
             raise RuntimeError("MyoVecEnv needs a CUDA device: the physics has no CPU fallback (the CPU oracle under oracle/ is test-only)")
         self.env_id, self.num_envs, self.seed_value, self.env_offset = env_id, int(num_envs), int(seed), int(env_offset)
-        self.max_episode_steps, kw, entry = env_spec(env_id)
+        if env_id is None:
+            self.max_episode_steps, kw, entry = 0, {"normalize_act": True}, None
+            auto_reset = False
+        else:
+            self.max_episode_steps, kw, entry = env_spec(env_id)
         kw.update(overrides)
         self.kwargs = kw
-        if not entry.endswith("pose_v0:PoseEnvV0"):
-            raise NotImplementedError("device task for %s (%s) is not built yet; pose tasks are" % (env_id, entry))
+        self.task_on_device = entry is None or entry.endswith("pose_v0:PoseEnvV0")
+        if not self.task_on_device:
+            raise NotImplementedError("device task for %s (%s) is not built yet; pose tasks are (use MyoVecEnv.from_model for physics only)" % (env_id, entry))
         self.mj_model = m = model if model is not None else assets.load(_MODEL_OF_XML[kw["model_path"]])
         self.muscle_condition = kw.get("muscle_condition", "")
         if self.muscle_condition == "sarcopenia":       # base_v0.py:62-67: gainprm[:,2] *= 0.5 (biasprm untouched)
@@ -74,7 +84,7 @@ class MyoVecEnv:
         self.I, self.D = blob.pack(m, prog)
         self.dev_model = abi.DeviceModel(self.I, self.D)
         cfg = abi.MyoTaskCfg()
-        cfg.task = abi.TASK_POSE
+        cfg.task = abi.TASK_POSE if entry is not None else abi.TASK_NONE
         cfg.frame_skip = self.n_frames
         cfg.max_episode_steps = int(self.max_episode_steps or 0)
         cfg.normalize_act = int(bool(kw.get("normalize_act", True)))
@@ -98,7 +108,7 @@ class MyoVecEnv:
         n, dv = self.num_envs, self.device
         f64, f32 = torch.float64, torch.float32
         z = lambda *s, dtype=f64: torch.zeros(*s, dtype=dtype, device=dv)
-        self.obs_dim, self.act_dim = self.batch.obs_dim, m.nu
+        self.obs_dim, self.act_dim = max(self.batch.obs_dim, 1), m.nu
         t = dict(action=z(n, m.nu, dtype=f32), qpos=z(n, m.nq), qvel=z(n, m.nv), act=z(n, max(m.na, 1)), qacc_warmstart=z(n, m.nv),
                  time=z(n), target=z(n, m.nq), step_count=z(n, dtype=torch.int32), episode_count=z(n, dtype=torch.int64),
                  obs=z(n, self.obs_dim, dtype=f32), reward=z(n, dtype=f32), done=z(n, dtype=torch.uint8), truncated=z(n, dtype=torch.uint8),

@@ -19,6 +19,9 @@
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/reference legs may use this file.
  */
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -35,6 +38,7 @@
 #define GEOM_PLANE 0
 #define GEOM_SPHERE 2
 #define GEOM_CAPSULE 3
+#define GEOM_ELLIPSOID 4
 #define WRAP_SITE 3
 #define WRAP_SPHERE 4
 #define WRAP_CYLINDER 5
@@ -442,6 +446,84 @@ static int capsule_capsule(ora* o, int pair, int g1, int g2, double margin) {
   n+=sphere_sphere(o,pair,g1,g2,margin,v1,r1,v2,r2,NULL);
   return n;
 }
+/* ---- ellipsoid colliders.  MuJoCo sends ellipsoid-capsule / ellipsoid-ellipsoid pairs through its general convex
+ * collider (signed distance / penetration depth along the minimum-translation direction, one contact at the midpoint of
+ * the witness points).  Restated from that definition with ROBUST, SLOW numerics (bisection / golden section / pattern
+ * search), deliberately unlike the Newton iterations of the CUDA kernels. */
+/* signed distance from world point p to the ellipsoid (c, R, s); outward unit normal n (ellipsoid -> point); witness x on the surface */
+static double point_ellipsoid(const double* p, const double* c, const double* R, const double* s, double* n, double* x) {
+  double t[3] = {p[0]-c[0], p[1]-c[1], p[2]-c[2]}, q[3]; matT_vec(q, R, t);
+  double inside = (q[0]/s[0])*(q[0]/s[0])+(q[1]/s[1])*(q[1]/s[1])+(q[2]/s[2])*(q[2]/s[2]);
+  double xl[3], lo, hi;
+  if (inside >= 1) { lo = 0; hi = norm3(q)*fmax(s[0],fmax(s[1],s[2])); }
+  else { double mn = fmin(s[0],fmin(s[1],s[2])); lo = -mn*mn*(1-1e-12); hi = 0; }      /* closest surface point from inside */
+  for (int it = 0; it < 200; it++) { double l = 0.5*(lo+hi), g = 0;
+    for (int k = 0; k < 3; k++) { double v = s[k]*q[k]/(s[k]*s[k]+l); g += v*v; }
+    if (g > 1) lo = l; else hi = l; }
+  double l = 0.5*(lo+hi); for (int k = 0; k < 3; k++) xl[k] = s[k]*s[k]*q[k]/(s[k]*s[k]+l);
+  double dl[3] = {q[0]-xl[0], q[1]-xl[1], q[2]-xl[2]}, dist = norm3(dl);
+  /* outward surface normal at xl: gradient of the implicit function */
+  double nl[3] = {xl[0]/(s[0]*s[0]), xl[1]/(s[1]*s[1]), xl[2]/(s[2]*s[2])}; normalize3(nl);
+  mat_vec(n, R, nl); double xw[3]; mat_vec(xw, R, xl); for (int k = 0; k < 3; k++) x[k] = xw[k]+c[k];
+  return inside >= 1 ? dist : -dist;
+}
+static long double ee_fl(long double th, long double ph, const double* dl, const double* R1, const double* s1, const double* R2, const double* s2) {
+  long double d[3] = {sinl(th)*cosl(ph), sinl(th)*sinl(ph), cosl(th)}, f = d[0]*dl[0]+d[1]*dl[1]+d[2]*dl[2], q1 = 0, q2 = 0;
+  for (int k = 0; k < 3; k++) { long double a = R1[k]*d[0]+R1[3+k]*d[1]+R1[6+k]*d[2], b = R2[k]*d[0]+R2[3+k]*d[1]+R2[6+k]*d[2]; q1 += (long double)s1[k]*s1[k]*a*a; q2 += (long double)s2[k]*s2[k]*b*b; }
+  return f - sqrtl(q1) - sqrtl(q2); }
+static void ang2dir(double th, double ph, double* d) { d[0] = sin(th)*cos(ph); d[1] = sin(th)*sin(ph); d[2] = cos(th); }
+static int ellipsoid_ellipsoid(ora* o, int pair, int g1, int g2, double margin) {
+  const double* gs = DSEC(o,geom_size); const double *c1=o->geom_xpos+3*g1, *c2=o->geom_xpos+3*g2, *R1=o->geom_xmat+9*g1, *R2=o->geom_xmat+9*g2, *s1=gs+3*g1, *s2=gs+3*g2;
+  double dl[3] = {c2[0]-c1[0], c2[1]-c1[1], c2[2]-c1[2]};
+  double rb1 = fmax(s1[0],fmax(s1[1],s1[2])), rb2 = fmax(s2[0],fmax(s2[1],s2[2]));
+  if (norm3(dl)-rb1-rb2 > margin) return 0;
+  /* signed distance = max over unit d of  d.(c2-c1) - h1(d) - h2(-d): coarse grid, then pattern search on the two angles */
+  long double best = -1e30L, bt = 0, bp = 0; double d[3];
+  for (int i = 1; i < 60; i++) for (int j = 0; j < 120; j++) { long double th = M_PI*i/60, ph = 2*M_PI*j/120, f = ee_fl(th, ph, dl, R1, s1, R2, s2); if (f > best) { best = f; bt = th; bp = ph; } }
+  long double step = M_PI/60;
+  while (step > 1e-13L) { int moved = 0;
+    for (int k = 0; k < 4; k++) { long double th = bt + (k==0)*step - (k==1)*step, ph = bp + (k==2)*step - (k==3)*step, f = ee_fl(th, ph, dl, R1, s1, R2, s2); if (f > best) { best = f; bt = th; bp = ph; moved = 1; } }
+    if (!moved) step *= 0.5L; }
+  if ((double)best > margin) return 0;
+  ang2dir((double)bt, (double)bp, d);
+  int c = o->ncon; if (c >= o->maxcon) return 0;
+  double a[3], b[3], u[3], pa[3], pb[3]; matT_vec(a, R1, d); for (int k = 0; k < 3; k++) u[k] = s1[k]*s1[k]*a[k]; double n1 = sqrt(dot3(a,u)); mat_vec(pa, R1, u);
+  matT_vec(b, R2, d); for (int k = 0; k < 3; k++) u[k] = s2[k]*s2[k]*b[k]; double n2 = sqrt(dot3(b,u)); mat_vec(pb, R2, u);
+  double* f = o->con_frame+9*c; memset(f, 0, 72); memcpy(f, d, 24);
+  for (int k = 0; k < 3; k++) o->con_pos[3*c+k] = 0.5*((c1[k]+pa[k]/n1) + (c2[k]-pb[k]/n2));
+  make_frame(f); o->con_dist[c] = (double)best; o->con_geom1[c] = g1; o->con_geom2[c] = g2; o->con_pair[c] = pair; o->ncon++; return 1;
+}
+static int capsule_ellipsoid(ora* o, int pair, int g1, int g2, double margin) {   /* g1 capsule, g2 ellipsoid */
+  const double* gs = DSEC(o,geom_size); const double *cc=o->geom_xpos+3*g1, *mc=o->geom_xmat+9*g1, *ce=o->geom_xpos+3*g2, *Re=o->geom_xmat+9*g2, *se=gs+3*g2;
+  double r = gs[3*g1], h = gs[3*g1+1], ax[3] = {mc[2], mc[5], mc[8]}, dl[3] = {ce[0]-cc[0], ce[1]-cc[1], ce[2]-cc[2]};
+  if (norm3(dl)-(r+h)-fmax(se[0],fmax(se[1],se[2])) > margin) return 0;
+  /* min over the segment parameter of the (convex) point-ellipsoid distance: bisection on its derivative n.a */
+  double lo = -h, hi = h, n[3], x[3], p[3];
+  for (int k = 0; k < 3; k++) p[k] = cc[k]+ax[k]*lo; point_ellipsoid(p, ce, Re, se, n, x); double glo = dot3(n, ax);
+  for (int k = 0; k < 3; k++) p[k] = cc[k]+ax[k]*hi; point_ellipsoid(p, ce, Re, se, n, x); double ghi = dot3(n, ax);
+  if (glo >= 0) hi = lo; else if (ghi <= 0) lo = hi;
+  else for (int it = 0; it < 200; it++) { double tm = 0.5*(lo+hi); for (int k = 0; k < 3; k++) p[k] = cc[k]+ax[k]*tm;
+    point_ellipsoid(p, ce, Re, se, n, x); if (dot3(n, ax) > 0) hi = tm; else lo = tm; }
+  double t = 0.5*(lo+hi); for (int k = 0; k < 3; k++) p[k] = cc[k]+ax[k]*t;
+  double dist = point_ellipsoid(p, ce, Re, se, n, x) - r;
+  if (dist > margin) return 0;
+  int c = o->ncon; if (c >= o->maxcon) return 0;
+  double* f = o->con_frame+9*c; memset(f, 0, 72); for (int k = 0; k < 3; k++) f[k] = -n[k];   /* normal from the capsule (geom1) to the ellipsoid (geom2) */
+  for (int k = 0; k < 3; k++) o->con_pos[3*c+k] = 0.5*((p[k]-n[k]*r) + x[k]);
+  make_frame(f); o->con_dist[c] = dist; o->con_geom1[c] = g1; o->con_geom2[c] = g2; o->con_pair[c] = pair; o->ncon++; return 1;
+}
+static int plane_ellipsoid(ora* o, int pair, int g1, int g2, double margin) {   /* mjc_PlaneEllipsoid: deepest point along -normal */
+  const double* gs = DSEC(o,geom_size); const double *pp=o->geom_xpos+3*g1, *pm=o->geom_xmat+9*g1, *ce=o->geom_xpos+3*g2, *Re=o->geom_xmat+9*g2, *se=gs+3*g2;
+  double n[3] = {pm[2], pm[5], pm[8]}, nl[3], u[3], pw[3]; matT_vec(nl, Re, n);
+  for (int k = 0; k < 3; k++) u[k] = se[k]*se[k]*nl[k]; double nn = sqrt(dot3(nl,u)); mat_vec(pw, Re, u);
+  double pos[3]; for (int k = 0; k < 3; k++) pos[k] = ce[k]-pw[k]/nn;
+  double dv[3] = {pos[0]-pp[0], pos[1]-pp[1], pos[2]-pp[2]}, dist = dot3(dv, n);
+  if (dist > margin) return 0;
+  int c = o->ncon; if (c >= o->maxcon) return 0;
+  double* f = o->con_frame+9*c; memset(f, 0, 72); memcpy(f, n, 24);
+  for (int k = 0; k < 3; k++) o->con_pos[3*c+k] = pos[k]-n[k]*0.5*dist;
+  make_frame(f); o->con_dist[c] = dist; o->con_geom1[c] = g1; o->con_geom2[c] = g2; o->con_pair[c] = pair; o->ncon++; return 1;
+}
 static void collision(ora* o) {
   const int *pg1=ISEC(o,pair_geom1), *pg2=ISEC(o,pair_geom2), *gt=ISEC(o,geom_type);
   const double *pm=DSEC(o,pair_margin), *gs=DSEC(o,geom_size);
@@ -457,7 +539,10 @@ static void collision(ora* o) {
     else if (t1==GEOM_PLANE && t2==GEOM_CAPSULE) { double ax[3]={m2[2],m2[5],m2[8]}, e[3];
       for (int k=0;k<3;k++) e[k]=x2[k]+ax[k]*gs[3*g2+1]; plane_sphere(o,p,g1,g2,margin,x1,m1,e,gs[3*g2],ax);
       for (int k=0;k<3;k++) e[k]=x2[k]-ax[k]*gs[3*g2+1]; plane_sphere(o,p,g1,g2,margin,x1,m1,e,gs[3*g2],ax); }
-    /* other type pairs (ellipsoid / mesh / hfield): not restated yet -- see DESIGN.md "gaps" */
+    else if (t1==GEOM_PLANE && t2==GEOM_ELLIPSOID) plane_ellipsoid(o,p,g1,g2,margin);
+    else if (t1==GEOM_CAPSULE && t2==GEOM_ELLIPSOID) capsule_ellipsoid(o,p,g1,g2,margin);
+    else if (t1==GEOM_ELLIPSOID && t2==GEOM_ELLIPSOID) ellipsoid_ellipsoid(o,p,g1,g2,margin);
+    /* mesh / hfield / cylinder pairs are dropped at model-compile time (proved unreachable) or listed in pair_unsupported */
   }
 }
 

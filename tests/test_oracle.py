@@ -149,7 +149,7 @@ def test_oracle_hand_contacts_and_kkt(models):
     m = models["myohand_pose"]
     o = Oracle(*blob.pack(m))
     rng = np.random.default_rng(3)
-    seen = 0
+    seen = seen_ell = 0
     for _ in range(20):
         q = _rand_state(m, rng, margin=-0.02)
         o.set(qpos=q, qvel=rng.normal(0, 1, m.nv), act=rng.uniform(0, 1, m.na), ctrl=rng.uniform(0, 1, m.nu)); o.forward()
@@ -161,8 +161,10 @@ def test_oracle_hand_contacts_and_kkt(models):
         jar = J @ o.f("qacc") - o.f("efc_aref")
         assert np.all(force >= 0) and np.all(force[jar > 1e-9] == 0)
         g1, g2 = o.i("con_geom1"), o.i("con_geom2")
-        assert np.all(g1 < g2)
-    assert seen > 0
+        t1, t2 = m.geom_type[g1], m.geom_type[g2]
+        assert np.all(t1 <= t2) and np.all((g1 < g2) | (t1 < t2))      # MuJoCo's collider table: lower geom type first
+        seen_ell += int(np.sum(t2 == 4))
+    assert seen > 0 and seen_ell > 0      # capsule-capsule and capsule-ellipsoid (fingertip pad) contacts both occur
 
 
 def test_oracle_rollout_stable(models):
