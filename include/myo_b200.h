@@ -34,7 +34,7 @@ extern "C" {
 typedef struct myo_model myo_model;
 typedef struct myo_batch myo_batch;
 
-enum { MYO_TASK_NONE = 0, MYO_TASK_POSE = 1 };
+enum { MYO_TASK_NONE = 0, MYO_TASK_POSE = 1, MYO_TASK_WALK = 2, MYO_TASK_HOLD = 3 };
 enum { MYO_COND_NONE = 0, MYO_COND_FATIGUE = 2 };   /* sarcopenia / reafferentation are host-side model edits */
 
 /* model dimensions (mirrors the mjModel sizes the reference reads: env.unwrapped.mj_model.{nq,nv,nu,na}) */
@@ -62,9 +62,11 @@ typedef struct {
   int32_t barrier_mode;      /* CTA phase barriers: 0 = between all phases (default), 1 = once per substep, 2 = none (tuning knob) */
   int32_t reserved_i;
   double pose_thd;           /* pose_v0.py:43 */
-  double weights[4];         /* pose, bonus, act_reg, penalty (pose_v0.py:18-23) */
+  double weights[8];         /* reward weights in the task's own key order (pose_v0.py:18-23, walk_v0.py:205-211, obj_hold_v0.py:17-21) */
   double solver_tolerance;   /* scaled-gradient stop of the Newton solver; 0 = library default (1e-10) */
-  double reserved[6];
+  int32_t task_i[16];        /* task-specific indices, filled by the host mirror (vec_env.py): WALK body/joint ids, HOLD object ids */
+  double task_d[24];         /* task-specific constants: WALK targets / thresholds / torso quaternion offset, HOLD object site */
+  double reserved[2];
 } myo_task_cfg;
 
 /* caller-owned device buffers; nullable ones are marked.  f64 state, f32 I/O like the reference
@@ -80,6 +82,8 @@ typedef struct {
   double* target;            /* [n, nq]  pose target_jnt_value, in/out */
   const double* target_range;/* [nq, 2]  per-qpos target sampling range (pose), model-level, in */
   const double* init_qpos;   /* [nq]     reset pose when !reset_random, in */
+  const double* init_qvel;   /* [nv]     reset velocity (nullable = zeros), in */
+  double* env_prm;           /* [n, 8]   per-env model overrides (HOLD: goal site pos[3], object geom size[3]); nullable */
   int32_t* step_count;       /* [n] */
   int64_t* episode_count;    /* [n]  also the Philox stream counter */
   float* obs;                /* [n, obs_dim] out */
@@ -99,7 +103,7 @@ typedef struct {
   double* tap_moment;        /* [n, nnz] structural non-zeros of the tendon moment */
   double* tap_qM;            /* [n, nM] */
   long long* tap_phase_cycles; /* [n, 16] SM-clock cycles spent per phase over the whole call (profiling aid; slots 12,13: max ncon / max nefc over substeps) */
-  void* reserved[3];
+  void* reserved[1];
 } myo_buffers;
 
 const char* myo_last_error(void);

@@ -14,7 +14,7 @@ _LIB = None
 
 c_i32, c_i64, c_u64, c_f64, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_double, ctypes.c_void_p
 
-TASK_NONE, TASK_POSE = 0, 1
+TASK_NONE, TASK_POSE, TASK_WALK, TASK_HOLD = 0, 1, 2, 3
 COND_NONE, COND_FATIGUE = 0, 2
 
 
@@ -26,17 +26,17 @@ class MyoDims(ctypes.Structure):
 class MyoTaskCfg(ctypes.Structure):
     _fields_ = [(n, c_i32) for n in ("task", "frame_skip", "max_episode_steps", "normalize_act", "muscle_condition",
                                       "auto_reset", "reset_random", "maxcon", "reaf_dst", "reaf_src", "barrier_mode", "reserved_i")] + \
-               [("pose_thd", c_f64), ("weights", c_f64 * 4), ("solver_tolerance", c_f64), ("reserved", c_f64 * 6)]
+               [("pose_thd", c_f64), ("weights", c_f64 * 8), ("solver_tolerance", c_f64), ("task_i", c_i32 * 16), ("task_d", c_f64 * 24), ("reserved", c_f64 * 2)]
 
 
-BUFFER_FIELDS = ["action", "qpos", "qvel", "act", "qacc_warmstart", "time", "fatigue", "target", "target_range", "init_qpos",
+BUFFER_FIELDS = ["action", "qpos", "qvel", "act", "qacc_warmstart", "time", "fatigue", "target", "target_range", "init_qpos", "init_qvel", "env_prm",
                  "step_count", "episode_count", "obs", "reward", "done", "truncated", "ep_return", "last_return",
                  "tap_qacc", "tap_actuator_force", "tap_ten_length", "tap_qfrc_smooth", "tap_ncon", "tap_contact_pair",
                  "tap_contact_dist", "tap_moment", "tap_qM", "tap_phase_cycles"]
 
 
 class MyoBuffers(ctypes.Structure):
-    _fields_ = [(n, c_vp) for n in BUFFER_FIELDS] + [("reserved", c_vp * 3)]
+    _fields_ = [(n, c_vp) for n in BUFFER_FIELDS] + [("reserved", c_vp * 1)]
 
 
 EXPORTS = ["myo_last_error", "myo_version", "myo_model_from_blob", "myo_model_dims", "myo_model_destroy", "myo_batch_create",

@@ -66,7 +66,14 @@ __device__ void env_reset(const DevModel& m, Warp& w, const StepArgs& a, int env
       if (b.target && b.target_range) b.target[(size_t)env*m.nq+qa] = b.target_range[2*qa] + u0*(b.target_range[2*qa+1]-b.target_range[2*qa]);
       if (a.cfg.reset_random) w.qpos[qa] = jrange[2*j] + u1*(jrange[2*j+1]-jrange[2*j]); }
   }
-  for (int i = w.lane; i < m.nv; i += 32) { w.qvel[i] = 0; w.qws[i] = 0; }
+  if (a.cfg.task == MYO_TASK_HOLD && b.env_prm) {
+    // ObjHoldRandomEnvV0.reset (obj_hold_v0.py:126-145): goal = object_init_pos + U(-3cm, 3cm)^3 ; object size ~ U(2cm, 3cm)^3
+    // (Fixed variant, reset_random == 0: model values in task_d[6..11])
+    if (w.lane < 6) { double u = philox_uniform(rng), v;
+      if (w.lane < 3) v = a.cfg.reset_random ? a.cfg.task_d[3+w.lane] + (-0.030 + 0.060*u) : a.cfg.task_d[6+w.lane];
+      else v = a.cfg.reset_random ? 0.020 + 0.010*u : a.cfg.task_d[6+w.lane];
+      w.eprm[w.lane] = v; b.env_prm[(size_t)env*8 + w.lane] = v; } }
+  for (int i = w.lane; i < m.nv; i += 32) { w.qvel[i] = b.init_qvel ? b.init_qvel[i] : 0.0; w.qws[i] = 0; }
   for (int i = w.lane; i < m.na; i += 32) w.act[i] = 0;
   if (b.fatigue && a.cfg.muscle_condition == MYO_COND_FATIGUE) for (int i = w.lane; i < m.nu; i += 32) { double* f = b.fatigue + (size_t)env*3*m.nu; f[i] = 0; f[m.nu+i] = 1; f[2*m.nu+i] = 0; }
   if (w.lane == 0) { if (b.time) b.time[env] = 0; if (b.step_count) b.step_count[env] = 0; if (b.episode_count) b.episode_count[env] = ep+1; if (b.ep_return) b.ep_return[env] = 0; }
@@ -88,6 +95,80 @@ __device__ void pose_reward_done(const DevModel& m, Warp& w, const StepArgs& a, 
   const double far_th = 4*3.14159265358979323846/2; double thd = a.cfg.pose_thd;
   *rw_out = a.cfg.weights[0]*(-dist) + a.cfg.weights[1]*((dist < thd ? 1.0 : 0.0)+(dist < 1.5*thd ? 1.0 : 0.0)) + a.cfg.weights[2]*(-am) + a.cfg.weights[3]*(dist > far_th ? -1.0 : 0.0);
   *done_out = dist > far_th; }
+
+// spatial velocity [omega; v_origin] of dynamic body k from its dof chain
+__device__ __forceinline__ void body_velocity(const DevModel& m, const Warp& w, int k, double* v) {
+  const idx_t* cadr = CI(PCH_adr); const idx_t* ch = CI(PCH);
+  for (int c = 0; c < 6; c++) v[c] = 0;
+  #pragma unroll 1
+  for (int e = cadr[k]; e < cadr[k+1]; e++) { int d = ch[e] >> 1; double S[6], qd = w.qvel[d]; dof_motion(m, w, d, S); for (int c = 0; c < 6; c++) v[c] += S[c]*qd; } }
+
+// WalkEnvV0 obs / reward / done (walk_v0.py:268-319,358-494) on the post-step state; needs kinematics + tendon + actuation of that
+// state in scratch (the reference's extra mj_forward, robot.py:607).  `steps` = WalkEnvV0.steps BEFORE its increment (walk_v0.py:339-342).
+__device__ void walk_observe(const DevModel& m, Warp& w, const StepArgs& a, int env, int steps, double* rw_out, bool* done_out) {
+  const myo_buffers& b = a.b; const int* ti = a.cfg.task_i; const double* td = a.cfg.task_d;
+  const double* PB = CD(PB_d); const double* xpos = SCR(s_xpos); const double* xmat = SCR(s_xmat);
+  double acc[9] = {0,0,0,0,0,0,0,0,0};     // sum m*xipos, sum m*v_origin, sum m*omega
+  for (int k = w.lane; k < m.nbd; k += 32) { const double* bd = PB + k*PB_STRIDE; double mass = bd[15], c3[3], v[6];
+    mat_vec(c3, xmat + 9*k, bd + 12); body_velocity(m, w, k, v);
+    for (int c = 0; c < 3; c++) { acc[c] += mass*(c3[c] + xpos[3*k+c]); acc[3+c] += mass*v[3+c]; acc[6+c] += mass*v[c]; } }
+  for (int c = 0; c < 9; c++) acc[c] = warp_sum(acc[c]);
+  double M = td[13], com[3] = {acc[0]/M, acc[1]/M, acc[2]/M}, wxc[3]; cross3(wxc, acc + 6, com);
+  // _get_com_velocity: -(sum m*cvel)/M, cvel's linear part being the velocity at the root's subtree COM
+  double vx = -(acc[3] + wxc[0])/M, vy = -(acc[4] + wxc[1])/M, height = com[2];
+  const double* quat = w.qpos + 3;
+  double tq[4]; quat_mul(tq, quat, td); quat_norm(tq);                                        // torso xquat = root quat (x) constant offset
+  const double* pl = xpos + 3*ti[1]; const double* pr_ = xpos + 3*ti[2]; const double* pp = xpos + 3*ti[3];
+  double phase = fmod((double)steps/td[6], 1.0);
+  float* o = b.obs ? b.obs + (size_t)env*a.obs_dim : nullptr;
+  if (o) { int nq2 = m.nq - 2, base = nq2 + m.nv;
+    for (int i = w.lane; i < nq2; i += 32) o[i] = (float)w.qpos[2+i];
+    for (int i = w.lane; i < m.nv; i += 32) o[nq2+i] = (float)(w.qvel[i]*a.dt);
+    if (w.lane == 0) { o[base] = (float)vx; o[base+1] = (float)vy; for (int c = 0; c < 4; c++) o[base+2+c] = (float)tq[c];
+      o[base+6] = (float)pl[2]; o[base+7] = (float)pr_[2]; o[base+8] = (float)height;
+      for (int c = 0; c < 3; c++) { o[base+9+c] = (float)(pl[c]-pp[c]); o[base+12+c] = (float)(pr_[c]-pp[c]); }
+      o[base+15] = (float)phase; }
+    const idx_t* at = CI(PA_tendon); const double* PAm = CD(PAM_d); const double* tlen = SCR(s_tlen); const double* tvel = SCR(s_tvel); const double* tfrc = SCR(s_tfrc);
+    int mb = base + 16;
+    for (int i = w.lane; i < m.nu; i += 32) { double gear = PAm[i*PAM_STRIDE+4]; int t = at[i];
+      o[mb+i] = (float)(gear*tlen[t]); o[mb+m.nu+i] = (float)clipd(gear*tvel[t], -100, 100); o[mb+2*m.nu+i] = (float)clipd(tfrc[t]/gear/1000.0, -100, 100);
+      o[mb+3*m.nu+i] = (float)w.act[i]; } }
+  // rewards
+  double vel_reward = exp(-(td[8]-vy)*(td[8]-vy)) + exp(-(td[7]-vx)*(td[7]-vx));
+  const double PI = 3.14159265358979323846;
+  double des0 = (double)(float)(0.8*cos(phase*2*PI + PI)), des1 = (double)(float)(0.8*cos(phase*2*PI));
+  double e0 = des0 - w.qpos[ti[4]], e1 = des1 - w.qpos[ti[5]], cyclic = sqrt(e0*e0 + e1*e1);
+  double rr = 0; for (int c = 0; c < 4; c++) { double dq = 5.0*(quat[c] - td[9+c]); rr += dq*dq; } double ref_rot = exp(-sqrt(rr));
+  double mag = 0.25*(fabs(w.qpos[ti[6]]) + fabs(w.qpos[ti[7]]) + fabs(w.qpos[ti[8]]) + fabs(w.qpos[ti[9]])), jrew = exp(-5.0*mag);
+  double qn = quat[0]*quat[0]+quat[1]*quat[1]+quat[2]*quat[2]+quat[3]*quat[3], r00 = (quat[0]*quat[0]+quat[1]*quat[1]-quat[2]*quat[2]-quat[3]*quat[3])/qn;
+  bool done = height < td[4] || fabs(r00) > td[5];
+  *rw_out = a.cfg.weights[0]*vel_reward + a.cfg.weights[1]*(done ? 1.0 : 0.0) + a.cfg.weights[2]*cyclic + a.cfg.weights[3]*ref_rot + a.cfg.weights[4]*jrew;
+  *done_out = done;
+}
+
+// ObjHold obs / reward / done (obj_hold_v0.py:79-121): needs kinematics of the post-step state in scratch
+__device__ void hold_observe(const DevModel& m, Warp& w, const StepArgs& a, int env, double* rw_out, bool* done_out) {
+  const myo_buffers& b = a.b; const int* ti = a.cfg.task_i; const double* td = a.cfg.task_d;
+  int ob = ti[0]; const double* xp = SCR(s_xpos) + 3*ob; double op[3]; mat_vec(op, SCR(s_xmat) + 9*ob, td); op[0]+=xp[0]; op[1]+=xp[1]; op[2]+=xp[2];
+  double err[3] = {w.eprm[0]-op[0], w.eprm[1]-op[1], w.eprm[2]-op[2]}, dist = sqrt(dot3(err, err));
+  float* o = b.obs ? b.obs + (size_t)env*a.obs_dim : nullptr; int nqh = m.nq - 7, nvh = m.nv - 6;
+  if (o) { for (int i = w.lane; i < nqh; i += 32) o[i] = (float)w.qpos[i];
+    for (int i = w.lane; i < nvh; i += 32) o[nqh+i] = (float)(w.qvel[i]*a.dt);
+    if (w.lane < 3) { o[nqh+nvh+w.lane] = (float)op[w.lane]; o[nqh+nvh+3+w.lane] = (float)err[w.lane]; }
+    for (int i = w.lane; i < m.na; i += 32) o[nqh+nvh+6+i] = (float)w.act[i]; }
+  bool drop = dist > 0.300;
+  *rw_out = a.cfg.weights[0]*(-dist) + a.cfg.weights[1]*((dist < 0.020 ? 1.0 : 0.0) + (dist < 0.010 ? 1.0 : 0.0)) + a.cfg.weights[2]*(drop ? -1.0 : 0.0);
+  *done_out = drop;
+}
+
+// obs / reward / done of the state held in shared memory, for any task (runs the extra forward stages the task needs)
+__device__ __noinline__ void task_observe(const DevModel& m, Warp& w, const StepArgs& a, int env, int steps, double* rw, bool* done) {
+  *rw = 0; *done = false;
+  if (a.cfg.task == MYO_TASK_POSE) pose_reward_done(m, w, a, env, rw, done);
+  else if (a.cfg.task == MYO_TASK_WALK) { phase_kinematics(m, w); phase_tendon(m, w); phase_actuation(m, w, false, nullptr, nullptr); walk_observe(m, w, a, env, steps, rw, done); }
+  else if (a.cfg.task == MYO_TASK_HOLD) { phase_kinematics(m, w); hold_observe(m, w, a, env, rw, done); }
+  __syncwarp();
+}
 
 // ------------------------------------------------------------------ the kernel
 extern "C" __global__ void __launch_bounds__(384) myo_env_kernel(const __grid_constant__ DevModel m, const __grid_constant__ StepArgs a) {
@@ -115,7 +196,7 @@ extern "C" __global__ void __launch_bounds__(384) myo_env_kernel(const __grid_co
   Warp w; w.lane = threadIdx.x & 31; w.cd = s_d; w.ci = s_i;
   double* base = warp0 + (size_t)wid*m.n_per_warp;
   w.qpos = base+m.o_qpos; w.qvel = base+m.o_qvel; w.act = base+m.o_act; w.ctrl = base+m.o_ctrl; w.qws = base+m.o_qws; w.dax = base+m.o_dax; w.dan = base+m.o_dan;
-  w.qM = base+m.o_qM; w.fsm = base+m.o_fsm; w.scr = base+m.o_scr;
+  w.qM = base+m.o_qM; w.fsm = base+m.o_fsm; w.eprm = base+m.o_eprm; w.scr = base+m.o_scr;
   w.ncon = w.nefc = w.nlimrow = w.niter = w.overflow = 0;
   const myo_buffers& b = a.b;
   // All warps of a CTA walk the phases in lockstep (CTA barriers between phases) so that they share instruction fetches:
@@ -130,13 +211,14 @@ extern "C" __global__ void __launch_bounds__(384) myo_env_kernel(const __grid_co
       for (int i = w.lane; i < m.nq; i += 32) w.qpos[i] = b.qpos[(size_t)env*m.nq+i];
       for (int i = w.lane; i < m.nv; i += 32) { w.qvel[i] = b.qvel[(size_t)env*m.nv+i]; w.qws[i] = b.qacc_warmstart[(size_t)env*m.nv+i]; }
       for (int i = w.lane; i < m.na; i += 32) w.act[i] = b.act[(size_t)env*m.na+i];
+      if (w.lane < 8) w.eprm[w.lane] = b.env_prm ? b.env_prm[(size_t)env*8 + w.lane] : 0.0;
       __syncwarp();
       if (a.mode == 2) {
         if (!a.reset_mask || a.reset_mask[env]) { env_reset(m, w, a, env);
-          if (a.cfg.task == MYO_TASK_POSE) { double d, am; write_obs_pose(m, w, a, env, &d, &am); }
+          { double rw_; bool dn_; task_observe(m, w, a, env, 0, &rw_, &dn_); }
           if (w.lane == 0) { if (b.done) b.done[env] = 0; if (b.truncated) b.truncated[env] = 0; if (b.reward) b.reward[env] = 0; } }
       } else if (a.mode == 3) {   // observe: obs/reward/done of the current state, nothing advanced (env.forward(), env_base.py:393-432)
-        if (a.cfg.task == MYO_TASK_POSE) { double rw; bool done; pose_reward_done(m, w, a, env, &rw, &done);
+        { double rw; bool done; task_observe(m, w, a, env, b.step_count ? b.step_count[env] : 0, &rw, &done);
           if (w.lane == 0) { if (b.reward) b.reward[env] = (float)rw; if (b.done) b.done[env] = done; } }
       } else if (a.mode == 1) {
         for (int i = w.lane; i < m.nu; i += 32) w.ctrl[i] = a.dbg_ctrl[(size_t)env*m.nu+i];
@@ -185,14 +267,14 @@ extern "C" __global__ void __launch_bounds__(384) myo_env_kernel(const __grid_co
       if (a.mode == 1) { if (integrate && w.lane == 0 && b.time) b.time[env] += nsub*m.timestep; }
       else if (a.mode == 0) {
         // ---- obs / reward / done / TimeLimit / auto-reset
-        if (a.cfg.task == MYO_TASK_POSE) { double rw; bool done; pose_reward_done(m, w, a, env, &rw, &done);
+        if (a.cfg.task != MYO_TASK_NONE) { double rw; bool done; task_observe(m, w, a, env, b.step_count ? b.step_count[env] : 0, &rw, &done);
           int sc = b.step_count ? b.step_count[env]+1 : 0; bool trunc = a.cfg.max_episode_steps > 0 && sc >= a.cfg.max_episode_steps;
           __syncwarp();
           if (w.lane == 0) { if (b.reward) b.reward[env] = (float)rw; if (b.done) b.done[env] = done; if (b.truncated) b.truncated[env] = trunc && !done;
             if (b.step_count) b.step_count[env] = sc; if (b.time) b.time[env] += a.cfg.frame_skip*m.timestep;
             if (b.ep_return) { float R = b.ep_return[env] + (float)rw; b.ep_return[env] = R; if ((done || trunc) && b.last_return) b.last_return[env] = R; } }
           __syncwarp();
-          if ((done || trunc) && a.cfg.auto_reset) { env_reset(m, w, a, env); double d2, a2; write_obs_pose(m, w, a, env, &d2, &a2); }
+          if ((done || trunc) && a.cfg.auto_reset) { env_reset(m, w, a, env); double rw2; bool dn2; task_observe(m, w, a, env, 0, &rw2, &dn2); }
         } else if (w.lane == 0 && b.time) b.time[env] += a.cfg.frame_skip*m.timestep;
       }
       __syncwarp();
@@ -239,10 +321,11 @@ static void fill_devmodel(const myo_model* mm, const myo_task_cfg* cfg, DevModel
   d.nbd = P[PD_NBD]; d.nlevel = P[PD_NLEVEL]; d.nsp = P[PD_NSP]; d.nwe = P[PD_NWE]; d.nta = P[PD_NTA]; d.nnz = P[PD_NNZ]; d.nlim = P[PD_NLIM]; d.neq = P[PD_NEQ];
   d.npair = P[PD_NPAIR]; d.npair_an = P[PD_NPAIR_ANALYTIC]; d.maxpath = P[PD_MAXPATH]; d.ndepth = P[PD_NDEPTH]; d.eq_tree = P[PD_EQ_TREE];
   const double* opt = MYO_DSEC(I, D, MYO_SEC_opt); d.timestep = opt[0]; d.gx = opt[1]; d.gy = opt[2]; d.gz = opt[3]; d.tolerance = opt[4]; d.meaninertia = opt[6];
+  d.ovr_geom = (cfg && cfg->task == MYO_TASK_HOLD) ? cfg->task_i[1] : -1;
   int mc = cfg && cfg->maxcon > 0 ? cfg->maxcon : 32; if (mc > 2*d.npair) mc = 2*d.npair; d.maxcon = mc; d.maxefc = d.neq + 2*d.nlim + 4*mc;
   int o = 0;
   #define TAKE(field, n) d.field = o; o += al2(n)
-  TAKE(o_qpos, d.nq); TAKE(o_qvel, d.nv); TAKE(o_act, d.na); TAKE(o_ctrl, d.nu); TAKE(o_qws, d.nv); TAKE(o_dax, 3*d.nv); TAKE(o_dan, 3*d.nv); TAKE(o_qM, d.nM); TAKE(o_fsm, d.nv);
+  TAKE(o_qpos, d.nq); TAKE(o_qvel, d.nv); TAKE(o_act, d.na); TAKE(o_ctrl, d.nu); TAKE(o_qws, d.nv); TAKE(o_dax, 3*d.nv); TAKE(o_dan, 3*d.nv); TAKE(o_qM, d.nM); TAKE(o_fsm, d.nv); TAKE(o_eprm, 8);
   d.o_scr = o;
   #undef TAKE
   // ---- scratch, time-multiplexed.  Lifetimes:
@@ -284,7 +367,10 @@ extern "C" int myo_batch_create(const myo_model* m, int device, int n_env, const
   fill_devmodel(m, cfg, b->dm);
   if (b->cfg.frame_skip <= 0) b->cfg.frame_skip = 1;
   if (cfg->task == MYO_TASK_POSE && b->dm.nq != b->dm.nv) { delete b; return fail("pose task needs nq == nv"); }
-  b->obs_dim = cfg->task == MYO_TASK_POSE ? 2*b->dm.nq + b->dm.nv + b->dm.na : 0;
+  b->obs_dim = 0;
+  if (cfg->task == MYO_TASK_POSE) b->obs_dim = 2*b->dm.nq + b->dm.nv + b->dm.na;
+  else if (cfg->task == MYO_TASK_WALK) b->obs_dim = (b->dm.nq - 2) + b->dm.nv + 16 + 4*b->dm.nu;
+  else if (cfg->task == MYO_TASK_HOLD) b->obs_dim = (b->dm.nq - 7) + (b->dm.nv - 6) + 6 + b->dm.na;
   { const int32_t* I = m->I.data(); const double* D = m->D.data();
     size_t nI = (size_t)b->dm.nI16w*4, nD = (size_t)b->dm.nD*8;
     CUDA_OK(cudaMalloc(&b->dI, nI ? nI : 16)); CUDA_OK(cudaMalloc(&b->dD, nD ? nD : 16));
@@ -309,6 +395,7 @@ extern "C" int myo_batch_bind(myo_batch* b, const myo_buffers* bufs) {
   if (!b || !bufs) return fail("myo_batch_bind: null");
   if (!bufs->qpos || !bufs->qvel || !bufs->qacc_warmstart || (b->dm.na && !bufs->act)) return fail("myo_batch_bind: qpos/qvel/act/qacc_warmstart are required");
   if (b->cfg.muscle_condition == MYO_COND_FATIGUE && !bufs->fatigue) return fail("myo_batch_bind: fatigue buffer required for MYO_COND_FATIGUE");
+  if (b->cfg.task == MYO_TASK_HOLD && !bufs->env_prm) return fail("myo_batch_bind: env_prm buffer required for MYO_TASK_HOLD");
   b->bufs = *bufs; b->bound = true; return 0;
 }
 

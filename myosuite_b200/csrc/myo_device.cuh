@@ -40,10 +40,10 @@ struct DevModel {
   int32_t hoff[MYO_NSEC];                  // offset of each hot section (in shorts / doubles), -1 if not staged
   int32_t nq, nv, nu, na, nM, njnt;
   int32_t nbd, nlevel, nsp, nwe, nta, nnz, nlim, neq, npair, npair_an, maxpath, ndepth, eq_tree;
-  int32_t maxcon, maxefc;
+  int32_t maxcon, maxefc, ovr_geom;          // ovr_geom: collision geom whose size comes from the per-env overrides (-1: none)
   double timestep, gx, gy, gz, meaninertia, tolerance;
   // per-warp shared-memory layout, in doubles.  Persistent part:
-  int32_t o_qpos, o_qvel, o_act, o_ctrl, o_qws, o_dax, o_dan, o_qM, o_fsm, o_scr, n_per_warp;
+  int32_t o_qpos, o_qvel, o_act, o_ctrl, o_qws, o_dax, o_dan, o_qM, o_fsm, o_eprm, o_scr, n_per_warp;
   // scratch (time-multiplexed by stage; offsets relative to o_scr).  See fill_devmodel() for the overlap rules.
   int32_t s_xpos, s_xmat;                                  // K: body poses, alive kinematics .. constraints
   int32_t s_U, s_WP, s_PL, s_mom, s_tlen, s_tvel, s_tfrc;  // stage 1: tendons + actuation
@@ -54,7 +54,7 @@ struct DevModel {
 };
 
 struct Warp {   // per-warp view (registers)
-  double *qpos, *qvel, *act, *ctrl, *qws, *dax, *dan, *qM, *fsm, *scr;
+  double *qpos, *qvel, *act, *ctrl, *qws, *dax, *dan, *qM, *fsm, *eprm, *scr;
   const double* cd; const idx_t* ci;   // staged constants
   int lane;
   int ncon, nefc, nlimrow, niter, overflow;
@@ -132,9 +132,9 @@ __device__ void phase_kinematics(const DevModel& m, Warp& w) {
       else { mat_vec(pos, xmat + 9*p, bd); pos[0]+=xpos[3*p]; pos[1]+=xpos[3*p+1]; pos[2]+=xpos[3*p+2]; mat_mul(R, xmat + 9*p, bd + 3); }
       for (int j = jadr[k]; j < jadr[k] + jnum[k]; j++) {
         int t = jtype[j], qa = jq[j], da = jd[j];
-        if (t == 0) {   // free joint: pose straight from qpos (quaternion normalised in place, as mj_kinematics does)
-          double* qp = w.qpos + qa; quat_norm(qp + 3);
-          pos[0]=qp[0]; pos[1]=qp[1]; pos[2]=qp[2]; quat2mat(R, qp + 3);
+        if (t == 0) {   // free joint: pose straight from qpos (normalised copy of the quaternion; qpos itself is left untouched)
+          const double* qp = w.qpos + qa; double qn[4] = {qp[3], qp[4], qp[5], qp[6]}; quat_norm(qn);
+          pos[0]=qp[0]; pos[1]=qp[1]; pos[2]=qp[2]; quat2mat(R, qn);
           for (int c = 0; c < 3; c++) {
             w.dax[3*(da+c)] = c==0; w.dax[3*(da+c)+1] = c==1; w.dax[3*(da+c)+2] = c==2;
             w.dan[3*(da+c)] = 0; w.dan[3*(da+c)+1] = 0; w.dan[3*(da+c)+2] = 0;
@@ -411,6 +411,7 @@ __device__ __forceinline__ void geom_pose(const DevModel& m, const Warp& w, int 
   else { const double* X = SCR(s_xmat) + 9*b; const double* xp = SCR(s_xpos) + 3*b; mat_vec(pos, X, gd); pos[0]+=xp[0]; pos[1]+=xp[1]; pos[2]+=xp[2];
     double z[3] = {gd[5], gd[8], gd[11]}; mat_vec(axis, X, z); } }
 
+__device__ __forceinline__ const double* geom_size(const DevModel& m, const Warp& w, int g) { return g == m.ovr_geom ? w.eprm + 3 : CD(PG_d) + g*PG_STRIDE + 12; }
 // full world rotation of a collision geom (ellipsoids need it)
 __device__ __forceinline__ void geom_mat(const DevModel& m, const Warp& w, int g, double* mat) {
   int b = CI(PG_body)[g]; const double* gd = CD(PG_d) + g*PG_STRIDE;
@@ -479,7 +480,7 @@ __device__ __forceinline__ void plane_sph(ConOut& o, double margin, const double
 __device__ void collide_pair(const DevModel& m, const Warp& w, int p, ConOut& o) {
   const idx_t* pr = CI(PPAIR) + PPAIR_ISTRIDE*p; const double* pd = CD(PPAIR_d) + pr[6]*PPAIR_STRIDE; const double* G = CD(PG_d);
   int g1 = pr[0], g2 = pr[1], ct = pr[5]; double margin = pd[0]; o.n = 0; o.has_y = false;
-  const double* s1 = G + g1*PG_STRIDE + 12; const double* s2 = G + g2*PG_STRIDE + 12;
+  const double* s1 = geom_size(m, w, g1); const double* s2 = geom_size(m, w, g2); (void)G;
   double x1[3], a1[3], x2[3], a2[3]; geom_pose(m, w, g1, x1, a1); geom_pose(m, w, g2, x2, a2);
   if (ct == CT_CAP_CAP) {
     double r1 = s1[0], h1 = s1[1], r2 = s2[0], h2 = s2[1];
@@ -548,7 +549,7 @@ __device__ void collide_pair(const DevModel& m, const Warp& w, int p, ConOut& o)
 // cheap conservative test for the iterative (ellipsoid) colliders: can this pair be within its margin at all?
 __device__ __forceinline__ bool expensive_candidate(const DevModel& m, const Warp& w, int p) {
   const idx_t* pr = CI(PPAIR) + PPAIR_ISTRIDE*p; const double* pd = CD(PPAIR_d) + pr[6]*PPAIR_STRIDE; const double* G = CD(PG_d);
-  int g1 = pr[0], g2 = pr[1]; const double* s1 = G + g1*PG_STRIDE + 12; const double* s2 = G + g2*PG_STRIDE + 12; double margin = pd[0];
+  int g1 = pr[0], g2 = pr[1]; const double* s1 = geom_size(m, w, g1); const double* s2 = geom_size(m, w, g2); double margin = pd[0]; (void)G;
   double x1[3], a1[3], x2[3], a2[3]; geom_pose(m, w, g1, x1, a1); geom_pose(m, w, g2, x2, a2);
   double dv[3] = {x2[0]-x1[0], x2[1]-x1[1], x2[2]-x1[2]}, rb2 = fmax(s2[0], fmax(s2[1], s2[2]));
   // any unit direction d gives a lower bound  d.(c2-c1) - h1(d) - h2(d)  on the signed distance: use the centre-to-centre

@@ -68,9 +68,11 @@ class MyoVecEnv:
             self.max_episode_steps, kw, entry = env_spec(env_id)
         kw.update(overrides)
         self.kwargs = kw
-        self.task_on_device = entry is None or entry.endswith("pose_v0:PoseEnvV0")
-        if not self.task_on_device:
-            raise NotImplementedError("device task for %s (%s) is not built yet; pose tasks are (use MyoVecEnv.from_model for physics only)" % (env_id, entry))
+        self.task = ("none" if entry is None else "pose" if entry.endswith("pose_v0:PoseEnvV0") else "walk" if entry.endswith("walk_v0:WalkEnvV0")
+                     else "hold" if "obj_hold_v0:ObjHold" in entry else None)
+        if self.task is None:
+            raise NotImplementedError("device task for %s (%s) is not built yet (pose, walk, hold are; MyoVecEnv.from_model gives physics only)" % (env_id, entry))
+        self.hold_random = entry is not None and entry.endswith("ObjHoldRandomEnvV0")
         self.mj_model = m = model if model is not None else assets.load(_MODEL_OF_XML[kw["model_path"]])
         self.muscle_condition = kw.get("muscle_condition", "")
         if self.muscle_condition == "sarcopenia":       # base_v0.py:62-67: gainprm[:,2] *= 0.5 (biasprm untouched)
@@ -81,10 +83,11 @@ class MyoVecEnv:
         self.dt = m.opt_timestep * self.frame_skip
         self.n_frames = int(self.dt / m.opt_timestep)      # robot.py:901
         prog, self.prog_info = program.build_program(m)
+        self.prog = prog
         self.I, self.D = blob.pack(m, prog)
         self.dev_model = abi.DeviceModel(self.I, self.D)
         cfg = abi.MyoTaskCfg()
-        cfg.task = abi.TASK_POSE if entry is not None else abi.TASK_NONE
+        cfg.task = {"none": abi.TASK_NONE, "pose": abi.TASK_POSE, "walk": abi.TASK_WALK, "hold": abi.TASK_HOLD}[self.task]
         cfg.frame_skip = self.n_frames
         cfg.max_episode_steps = int(self.max_episode_steps or 0)
         cfg.normalize_act = int(bool(kw.get("normalize_act", True)))
@@ -92,14 +95,32 @@ class MyoVecEnv:
         cfg.auto_reset = int(bool(auto_reset))
         cfg.reset_random = int(kw.get("reset_type", "init") == "random")
         cfg.pose_thd = float(kw.get("pose_thd", 0.35))
-        w = kw.get("weighted_reward_keys", {"pose": 1.0, "bonus": 4.0, "act_reg": 1.0, "penalty": 50})
-        cfg.weights[0], cfg.weights[1], cfg.weights[2], cfg.weights[3] = w["pose"], w["bonus"], w["act_reg"], w["penalty"]
+        init_qpos, init_qvel = np.asarray(m.qpos0, dtype=np.float64).copy(), np.zeros(m.nv)
+        if self.task in ("pose", "none"):
+            w = kw.get("weighted_reward_keys", {"pose": 1.0, "bonus": 4.0, "act_reg": 1.0, "penalty": 50})     # pose_v0.py:18-23
+            for i, k in enumerate(("pose", "bonus", "act_reg", "penalty")):
+                cfg.weights[i] = w[k]
+        elif self.task == "walk":
+            w = kw.get("weighted_reward_keys", {"vel_reward": 5.0, "done": -100, "cyclic_hip": -10, "ref_rot": 10.0, "joint_angle_rew": 5.0})   # walk_v0.py:205-211
+            for i, k in enumerate(("vel_reward", "done", "cyclic_hip", "ref_rot", "joint_angle_rew")):
+                cfg.weights[i] = w[k]
+            self._setup_walk(m, kw, cfg, prog_info=None)
+            key = {"init": 2, "random": 2}.get(kw.get("reset_type", "init"), 0)                     # walk_v0.py:344-352 ("random" adds noise: TODO)
+            init_qpos, init_qvel = m.key_qpos[key].copy(), m.key_qvel[key].copy()
+        elif self.task == "hold":
+            w = kw.get("weighted_reward_keys", {"goal_dist": 100.0, "bonus": 4.0, "penalty": 10})     # obj_hold_v0.py:17-21
+            for i, k in enumerate(("goal_dist", "bonus", "penalty")):
+                cfg.weights[i] = w[k]
+            init_qpos[:-7] = 0.0; init_qpos[0] = -1.5                                                  # obj_hold_v0.py:61-62
+            cfg.reset_random = int(self.hold_random)
         cfg.solver_tolerance = float(kw.get("solver_tolerance", 0.0))
         cfg.maxcon = int(kw.get("maxcon", 0))
         cfg.barrier_mode = int(kw.get("barrier_mode", 0))
         cfg.reaf_dst = cfg.reaf_src = -1
         if self.muscle_condition == "reafferentation":   # base_v0.py:78-79,104-108
             cfg.reaf_dst, cfg.reaf_src = m.name2id("actuator", "EPL"), m.name2id("actuator", "EIP")
+        if self.task == "hold":
+            self._setup_hold(m, cfg)
         self.cfg = cfg
         self.device_index = int(device)
         self.device = torch.device("cuda", self.device_index)
@@ -124,7 +145,12 @@ class MyoVecEnv:
             v = np.asarray(kw["target_jnt_value"], dtype=np.float64)
             tr[:, 0] = tr[:, 1] = v
         t["target_range"] = torch.as_tensor(tr, device=dv).contiguous()
-        t["init_qpos"] = torch.as_tensor(np.asarray(m.qpos0, dtype=np.float64), device=dv).contiguous()
+        t["init_qpos"] = torch.as_tensor(init_qpos, device=dv).contiguous()
+        t["init_qvel"] = torch.as_tensor(init_qvel, device=dv).contiguous()
+        self.init_qpos, self.init_qvel = init_qpos, init_qvel
+        if self.task == "hold":
+            t["env_prm"] = z(n, 8)
+            t["env_prm"][:, :6] = torch.as_tensor(np.array([cfg.task_d[6 + i] for i in range(6)]), device=dv)
         if cfg.muscle_condition == abi.COND_FATIGUE:
             t["fatigue"] = z(n, 3, m.nu)
             t["fatigue"][:, 1, :] = 1.0
@@ -136,6 +162,41 @@ class MyoVecEnv:
         self.t = t
         self.batch.bind(**t)
         self._h_action = None
+
+    # ---------------------------------------------------------------- task parameter blocks (indices into the kernel's dynamic-body list)
+    def _dyn(self, body_name):
+        return self.prog_info["dyn_body_ids"].index(self.mj_model.name2id("body", body_name))
+
+    def _setup_walk(self, m, kw, cfg, prog_info=None):
+        """WalkEnvV0 constants (walk_v0.py:235-266,358-494, registry myobase/__init__.py:443-458)."""
+        from . import mjmath as mm
+        root, torso = m.name2id("body", "root"), m.name2id("body", "torso")
+        q, b = np.array([1.0, 0, 0, 0]), torso
+        while b != root:                                   # torso xquat = root quat (x) constant chain offset (no joints in between)
+            if m.body_jntnum[b] != 0:
+                raise NotImplementedError("torso must be rigidly attached to the free root body")
+            q = mm.quat_mul(m.body_quat[b], q); b = int(m.body_parentid[b])
+        ti = [self._dyn("root"), self._dyn("talus_l"), self._dyn("talus_r"), self._dyn("pelvis")]
+        ti += [int(m.jnt_qposadr[m.name2id("joint", j)]) for j in ("hip_flexion_l", "hip_flexion_r", "hip_adduction_l", "hip_adduction_r", "hip_rotation_l", "hip_rotation_r")]
+        for i, v in enumerate(ti):
+            cfg.task_i[i] = v
+        target_rot = kw.get("target_rot") if kw.get("target_rot") is not None else m.key_qpos[0][3:7]      # init_qpos = key_qpos[0] (walk_v0.py:258)
+        td = list(q) + [kw.get("min_height", 0.8), kw.get("max_rot", 0.8), kw.get("hip_period", 100), kw.get("target_x_vel", 0.0), kw.get("target_y_vel", 1.2)] + \
+            list(target_rot) + [float(np.sum(m.body_mass))]
+        for i, v in enumerate(td):
+            cfg.task_d[i] = float(v)
+
+    def _setup_hold(self, m, cfg):
+        """ObjHold constants (obj_hold_v0.py:46-62,126-145)."""
+        from . import mjcf
+        obj_body, sid, gid = m.name2id("body", "object"), m.name2id("site", "object"), m.name2id("geom", "object")
+        pg = {v: k for k, v in self.prog_info["geom_model_ids"].items()}[gid]
+        cfg.task_i[0], cfg.task_i[1] = self._dyn("object"), pg
+        kin = mjcf.kinematics(m, m.qpos0)
+        obj_init = kin["xpos"][obj_body] + kin["xmat"][obj_body] @ m.site_pos[sid]                    # object_init_pos (obj_hold_v0.py:52)
+        goal = m.site_pos[m.name2id("site", "goal")]
+        for i in range(3):
+            cfg.task_d[i] = m.site_pos[sid][i]; cfg.task_d[3 + i] = obj_init[i]; cfg.task_d[6 + i] = goal[i]; cfg.task_d[9 + i] = m.geom_size[gid][i]
 
     # ---------------------------------------------------------------- gym-style API (batched)
     @property

@@ -67,3 +67,55 @@ def env_step(oracle, action, frame_skip, normalize_act=True, fatigue=None):
     oracle.set(ctrl=ctrl)
     oracle.step(frame_skip)
     return ctrl
+
+
+# ----------------------------------------------------------------------------- WalkEnvV0 (walk_v0.py)
+def quat2mat00(q):
+    """[0,0] entry of myosuite.utils.quat_math.quat2mat (used by WalkEnvV0._get_rot_condition, walk_v0.py:463-473)."""
+    w, x, y, z = q
+    n = w * w + x * x + y * y + z * z
+    return 1.0 - 2.0 / n * (y * y + z * z)
+
+
+def walk_obs_reward(m, o, steps, dt, ids, cfg):
+    """obs vector (f32[403]) and reward terms of WalkEnvV0 from the oracle's forward quantities of the observed state.
+    Follows walk_v0.py:268-319 (obs / reward), :358-494 (helpers).  `ids`: dict of model ids; `cfg`: registry kwargs.
+    `steps` is WalkEnvV0.steps at the time _forward runs, i.e. BEFORE the increment in step() (walk_v0.py:339-342)."""
+    qpos, qvel, act = o.f("qpos"), o.f("qvel"), o.f("act")
+    xpos, xquat, xipos, cvel = o.f("xpos").reshape(-1, 3), o.f("xquat").reshape(-1, 4), o.f("xipos").reshape(-1, 3), o.f("cvel").reshape(-1, 6)
+    mass = m.body_mass[:, None]
+    com_vel = (np.sum(mass * (-cvel), 0) / np.sum(mass))[3:5]                  # _get_com_velocity :449-455
+    com = np.sum(mass * xipos, 0) / np.sum(mass)                              # _get_com :475-481
+    phase = (steps / cfg["hip_period"]) % 1
+    fl, fr, pel = xpos[ids["talus_l"]], xpos[ids["talus_r"]], xpos[ids["pelvis"]]
+    obs = np.concatenate([qpos[2:], qvel * dt, com_vel, xquat[ids["torso"]], [fl[2], fr[2]], [com[2]], fl - pel, fr - pel, [phase],
+                          o.f("actuator_length"), np.clip(o.f("actuator_velocity"), -100, 100), np.clip(o.f("actuator_force") / 1000, -100, 100), act]).astype(np.float32)
+    vel_reward = np.exp(-np.square(cfg["target_y_vel"] - com_vel[1])) + np.exp(-np.square(cfg["target_x_vel"] - com_vel[0]))
+    des = np.array([0.8 * np.cos(phase * 2 * np.pi + np.pi), 0.8 * np.cos(phase * 2 * np.pi)], dtype=np.float32)
+    ang = np.array([qpos[ids["q_hip_flexion_l"]], qpos[ids["q_hip_flexion_r"]]])
+    cyclic = np.linalg.norm(des - ang)
+    ref_rot = np.exp(-np.linalg.norm(5.0 * (qpos[3:7] - cfg["target_rot"])))
+    jrew = np.exp(-5 * np.mean(np.abs([qpos[ids[k]] for k in ("q_hip_adduction_l", "q_hip_adduction_r", "q_hip_rotation_l", "q_hip_rotation_r")])))
+    done = bool(com[2] < cfg["min_height"] or abs(quat2mat00(qpos[3:7])) > cfg["max_rot"])
+    dense = 5.0 * vel_reward - 100 * done - 10 * cyclic + 10.0 * ref_rot + 5.0 * jrew      # DEFAULT_RWD_KEYS_AND_WEIGHTS :205-211
+    return obs, dict(vel_reward=vel_reward, cyclic_hip=cyclic, ref_rot=ref_rot, joint_angle_rew=jrew, done=done, dense=dense)
+
+
+def walk_ids(m):
+    ids = {k: m.name2id("body", k) for k in ("talus_l", "talus_r", "pelvis", "torso")}
+    for j in ("hip_flexion_l", "hip_flexion_r", "hip_adduction_l", "hip_adduction_r", "hip_rotation_l", "hip_rotation_r"):
+        ids["q_" + j] = int(m.jnt_qposadr[m.name2id("joint", j)])
+    return ids
+
+
+# ----------------------------------------------------------------------------- ObjHold (obj_hold_v0.py)
+def hold_obs_reward(m, o, dt, goal_pos):
+    """obj_hold_v0.py:79-121: obs = [qpos[:-7], qvel[:-6]*dt, obj_pos, goal - obj_pos, act] (f32[91]); reward terms."""
+    qpos, qvel, act = o.f("qpos"), o.f("qvel"), o.f("act")
+    obj = o.f("site_xpos").reshape(-1, 3)[m.name2id("site", "object")]
+    err = np.asarray(goal_pos) - obj
+    obs = np.concatenate([qpos[:-7], qvel[:-6] * dt, obj, err, act]).astype(np.float32)
+    d = np.abs(np.linalg.norm(err))
+    drop = bool(d > 0.300)
+    dense = 100.0 * (-d) + 4.0 * (1.0 * (d < 0.020) + 1.0 * (d < 0.010)) + 10 * (-1.0 * drop)
+    return obs, dict(goal_dist=-d, done=drop, dense=dense)

@@ -156,8 +156,7 @@ static void kinematics(ora* o) {
     int p=parent[b]; double pos[3], quat[4], v[3];
     if (jnum[b]==1 && jtype[jadr[b]]==JNT_FREE) {
       int a=jq[jadr[b]]; double* qp=o->qpos+a;
-      quat_norm(qp+3);   /* mj_kinematics normalises the quaternion in qpos */
-      memcpy(pos, qp, 24); memcpy(quat, qp+3, 32);
+      memcpy(pos, qp, 24); memcpy(quat, qp+3, 32); quat_norm(quat);   /* normalised copy: mj_kinematics (MuJoCo >= 2.3) leaves qpos untouched */
       memcpy(o->xanchor+3*jadr[b], pos, 24); o->xaxis[3*jadr[b]]=0; o->xaxis[3*jadr[b]+1]=0; o->xaxis[3*jadr[b]+2]=1;
     } else {
       mat_vec(v, o->xmat+9*p, bpos+3*b); for (int k=0;k<3;k++) pos[k]=o->xpos[3*p+k]+v[k];

@@ -234,3 +234,81 @@ def test_legs_physics_parity():
         np.testing.assert_allclose(gq[e], o.f("qpos"), rtol=0, atol=1e-8)
         assert relerr(gv[e], o.f("qvel")) < 1e-5
         assert abs(np.linalg.norm(gq[e, 3:7]) - 1) < 1e-12                                   # quaternion stays normalised
+
+
+TG = np.load(os.path.join(os.path.dirname(__file__), "golden", "tasks.npz"))
+
+
+def test_walk_task_golden_from_reference():
+    """myoLegWalk-v0 obs (403) / reward / done produced by the kernel on states whose expected values come from the reference's own
+    WalkEnvV0 methods (tests/golden/make_golden_tasks.py)."""
+    import torch
+    from myosuite_b200 import vec_env
+    n = len(TG["walk_qpos"])
+    env = vec_env.MyoVecEnv("myoLegWalk-v0", n, auto_reset=False)
+    assert env.obs_dim == 403 and env.act_dim == 80 and env.dt == pytest.approx(0.01) and env.max_episode_steps == 1000
+    env.set_state(qpos=TG["walk_qpos"], qvel=TG["walk_qvel"], act=TG["walk_act"])
+    env.t["step_count"][:] = torch.as_tensor(TG["walk_steps"].astype(np.int32), device=env.device)
+    env.refresh_obs(); torch.cuda.synchronize()
+    np.testing.assert_allclose(env.t["obs"].cpu().numpy(), TG["walk_obs"], rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(env.t["reward"].cpu().numpy(), TG["walk_dense"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_array_equal(env.t["done"].cpu().numpy().astype(bool), TG["walk_done"].astype(bool))
+
+
+def test_walk_env_step_and_reset_vs_oracle():
+    """Full myoFatiLegWalk-v0 control steps (fatigue + 10 substeps with equality/contact constraints + Walk obs) vs the oracles."""
+    import torch
+    from myosuite_b200 import vec_env
+    from oracle import env_oracle
+    from oracle.oracle_py import Oracle
+    n = 4
+    env = vec_env.MyoVecEnv("myoFatiLegWalk-v0", n, auto_reset=False, maxcon=48)
+    m = env.mj_model
+    obs0, _ = env.reset(seed=3); torch.cuda.synchronize()
+    np.testing.assert_allclose(env.t["qpos"].cpu().numpy(), np.tile(m.key_qpos[2], (n, 1)), atol=1e-12)      # reset_type "init": keyframe 2 (walk_v0.py:348-349)
+    np.testing.assert_allclose(env.t["qvel"].cpu().numpy(), np.tile(m.key_qvel[2], (n, 1)), atol=1e-12)
+    ids = env_oracle.walk_ids(m)
+    cfg = dict(hip_period=100, min_height=0.8, max_rot=0.8, target_x_vel=0.0, target_y_vel=1.2, target_rot=m.key_qpos[0][3:7])
+    oracles, fats = [], []
+    for e in range(n):
+        o = Oracle(env.I, env.D); o.reset(); o.set(qpos=m.key_qpos[2], qvel=m.key_qvel[2]); oracles.append(o); fats.append(env_oracle.Fatigue(m.nu, dt=env.dt))
+    rng = np.random.default_rng(8)
+    for step in range(3):
+        a = rng.uniform(-1, 1, (n, m.nu)).astype(np.float32)
+        obs, rew, done, trunc, _ = env.step(torch.as_tensor(a, device=env.device)); torch.cuda.synchronize()
+        obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        for e in range(n):
+            o = oracles[e]
+            env_oracle.env_step(o, a[e].astype(np.float64), env.n_frames, fatigue=fats[e])
+            state = (o.f("qpos").copy(), o.f("qvel").copy(), o.f("act").copy(), o.f("ctrl").copy())
+            o.set(ctrl=np.zeros(m.nu)); o.forward()                       # the reference's observed data: forward with ctrl = 0
+            exp_obs, r = env_oracle.walk_obs_reward(m, o, step, env.dt, ids, cfg)
+            o.set(qpos=state[0], qvel=state[1], act=state[2], ctrl=state[3])
+            np.testing.assert_allclose(obs[e], exp_obs, rtol=1e-4, atol=2e-5)
+            assert rew[e] == pytest.approx(r["dense"], rel=1e-4, abs=1e-4) and bool(done[e]) == bool(r["done"])
+
+
+def test_hold_task_golden_and_reset():
+    import torch
+    from myosuite_b200 import vec_env
+    n = len(TG["hold_qpos"])
+    env = vec_env.MyoVecEnv("myoHandObjHoldRandom-v0", n, auto_reset=False)
+    assert env.obs_dim == 91 and env.max_episode_steps == 75
+    env.set_state(qpos=TG["hold_qpos"], qvel=TG["hold_qvel"], act=TG["hold_act"])
+    env.t["env_prm"][:, :3] = torch.as_tensor(TG["hold_goal"], device=env.device)
+    env.refresh_obs(); torch.cuda.synchronize()
+    np.testing.assert_allclose(env.t["obs"].cpu().numpy(), TG["hold_obs"], rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(env.t["reward"].cpu().numpy(), TG["hold_dense"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_array_equal(env.t["done"].cpu().numpy().astype(bool), TG["hold_done"].astype(bool))
+    # ObjHoldRandomEnvV0.reset: goal within +-3 cm of the object's initial position, object radii in [2, 3] cm, hand open with qpos[0] = -1.5
+    env.reset(seed=5); torch.cuda.synchronize()
+    prm = env.t["env_prm"].cpu().numpy(); q = env.t["qpos"].cpu().numpy()
+    obj0 = np.array([-.235, -.51, 1.450])
+    assert np.all(np.abs(prm[:, :3] - obj0) <= 0.03 + 1e-12) and np.all(prm[:, 3:6] >= 0.02) and np.all(prm[:, 3:6] <= 0.03)
+    assert np.std(prm[:, 3]) > 0 and np.allclose(q[:, 0], -1.5) and np.allclose(q[:, 1:23], 0) and np.allclose(q[:, 23:26], obj0)
+    # the object rests in the palm for a few control steps: finite, contacts active, not dropped immediately
+    a = torch.zeros(n, env.act_dim, device=env.device)
+    for _ in range(5):
+        obs, rew, done, trunc, _ = env.step(a)
+    torch.cuda.synchronize()
+    assert torch.isfinite(obs).all() and not bool(done.any())

@@ -180,3 +180,32 @@ def test_oracle_rollout_stable(models):
             o.step()
         assert np.all(np.isfinite(o.f("qpos"))) and np.abs(o.f("qvel")).max() < 100
         assert np.all(o.f("act") >= -1e-9) and np.all(o.f("act") <= 1 + 1e-9)
+
+
+# ----------------------------------------------------------------------------- golden: Walk / ObjHold task logic (reference classes run on oracle states)
+T = np.load(os.path.join(os.path.dirname(__file__), "golden", "tasks.npz"))
+
+
+def test_walk_obs_reward_golden(models):
+    m = models["myolegs"]
+    o = Oracle(*blob.pack(m))
+    ids = env_oracle.walk_ids(m)
+    cfg = dict(hip_period=100, min_height=0.8, max_rot=0.8, target_x_vel=0.0, target_y_vel=1.2, target_rot=m.key_qpos[0][3:7])
+    for i in range(len(T["walk_qpos"])):
+        o.reset(); o.set(qpos=T["walk_qpos"][i], qvel=T["walk_qvel"][i], act=T["walk_act"][i], ctrl=np.zeros(m.nu)); o.forward()
+        obs, r = env_oracle.walk_obs_reward(m, o, int(T["walk_steps"][i]), 0.01, ids, cfg)
+        np.testing.assert_allclose(obs, T["walk_obs"][i], rtol=1e-6, atol=1e-6)
+        for k in ("vel_reward", "cyclic_hip", "ref_rot", "joint_angle_rew", "dense"):
+            np.testing.assert_allclose(r[k], T["walk_" + k][i], rtol=1e-9, atol=1e-9)
+        assert bool(r["done"]) == bool(T["walk_done"][i])
+
+
+def test_hold_obs_reward_golden(models):
+    m = models["myohand_hold"]
+    o = Oracle(*blob.pack(m))
+    for i in range(len(T["hold_qpos"])):
+        o.reset(); o.set(qpos=T["hold_qpos"][i], qvel=T["hold_qvel"][i], act=T["hold_act"][i]); o.forward()
+        obs, r = env_oracle.hold_obs_reward(m, o, 0.02, T["hold_goal"][i])
+        np.testing.assert_allclose(obs, T["hold_obs"][i], rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(r["dense"], T["hold_dense"][i], rtol=1e-9, atol=1e-9)
+        assert bool(r["done"]) == bool(T["hold_done"][i])
