@@ -25,7 +25,9 @@ sys.path.insert(0, ROOT)
 
 DEFAULT_ENV = "myoHandPoseRandom-v0"       # BASELINE.json target config (configs[2]; 23 dof / 39 muscles), 4096 envs/GPU
 # algorithmic bytes per env-step (A_io): action f32 + state f64 in/out + obs f32 + reward/done
-A_IO = {"myoElbowPose1D6MRandom-v0": 24 + 2 * (8 * 8) + 36 + 5, "myoHandPoseRandom-v0": 156 + 2 * (85 * 8) + 432 + 5}
+A_IO = {"myoElbowPose1D6MRandom-v0": 24 + 2 * (8 * 8) + 36 + 5, "myoHandPoseRandom-v0": 156 + 2 * (85 * 8) + 432 + 5,
+        "myoHandObjHoldRandom-v0": 156 + 2 * (98 * 8) + 364 + 5 + 36, "myoFatiLegWalk-v0": 320 + 2 * (149 * 8) + 2 * (240 * 8) + 1612 + 5,
+        "myoLegWalk-v0": 320 + 2 * (149 * 8) + 1612 + 5}
 
 
 class ClockSampler:
@@ -74,27 +76,34 @@ def _cpu_worker(args):
     rng = np.random.default_rng(seed)
     q = m.qpos0.copy()
     t0 = time.perf_counter()
+    pose = "Pose" in env_id
     for s in range(n_steps):
         if s % steps == 0:
             o.reset()
-            for j in range(m.njnt):
-                if m.jnt_type[j] != 0:
-                    q[m.jnt_qposadr[j]] = rng.uniform(*m.jnt_range[j])
-            o.set(qpos=q)
+            if pose:
+                for j in range(m.njnt):
+                    if m.jnt_type[j] != 0:
+                        q[m.jnt_qposadr[j]] = rng.uniform(*m.jnt_range[j])
+                o.set(qpos=q)
+            elif "Walk" in env_id:
+                o.set(qpos=m.key_qpos[2], qvel=m.key_qvel[2])
         env_oracle.env_step(o, rng.uniform(-1, 1, m.nu), 10)
-        env_oracle.pose_obs(o.f("qpos"), o.f("qvel"), o.f("act"), q, 0.02)
+        if pose:
+            env_oracle.pose_obs(o.f("qpos"), o.f("qvel"), o.f("act"), q, 0.02)
+        else:
+            o.forward()          # the reference's extra mj_forward for the observed data (robot.py:607)
     return time.perf_counter() - t0
 
 
 def cpu_baseline(env_id, n_steps, threads=1):
-    """env-steps/s of `threads` independent single-env loops of the oracle port, one process per host core."""
+    """env-steps/s of `threads` independent single-env loops of the oracle port, one process per host core.  The stepping loops
+    run concurrently; the rate is total steps / the slowest worker's loop time (process start-up and model load excluded)."""
     if threads == 1:
         return n_steps / _cpu_worker((env_id, n_steps, 0))
     import multiprocessing as mp
-    t0 = time.perf_counter()
     with mp.get_context("fork").Pool(threads) as pool:
-        pool.map(_cpu_worker, [(env_id, n_steps, i) for i in range(threads)])
-    return threads * n_steps / (time.perf_counter() - t0)
+        times = pool.map(_cpu_worker, [(env_id, n_steps, i) for i in range(threads)])
+    return threads * n_steps / max(times)
 
 
 def main():
@@ -119,7 +128,8 @@ def main():
         from oracle import oracle_py
         oracle_py.build()
         thr = max(1, cores)
-        per_thread = max(20, min(400, args.steps))        # bounded sample: ~10-30 s of CPU work
+        rate1 = cpu_baseline(args.env, 10, threads=1)      # calibrate, then size the bounded sample to ~8 s of stepping per core
+        per_thread = int(max(20, min(20000, 8.0 * rate1)))
         t0 = time.perf_counter()
         v = cpu_baseline(args.env, per_thread, threads=thr)
         ms = (time.perf_counter() - t0) * 1e3
@@ -218,7 +228,7 @@ def main():
         if not args.no_cpu_baseline:
             from oracle import oracle_py
             oracle_py.build()
-            nst = 300 if "Elbow" in args.env else 60
+            nst = 300 if "Elbow" in args.env else 60 if "Pose" in args.env else 30
             t0 = time.perf_counter()
             v = cpu_baseline(args.env, nst, threads=1)
             line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",

@@ -245,8 +245,9 @@ extern "C" __global__ void __launch_bounds__(384) myo_env_kernel(const __grid_co
       __syncwarp();
     }
     // ---- physics substeps: forward dynamics + semi-implicit Euler (the only copy of the phase code in the kernel)
+    const int bmask = a.cfg.barrier_mode == 0 ? 0xFF : (a.cfg.barrier_mode == 1 ? 0x01 : (a.cfg.barrier_mode == 2 ? 0 : a.cfg.barrier_mode));
     long long cyc[16] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}; int maxcon_seen = 0, maxefc_seen = 0;
-    #define PH(k, stmt) { if (a.cfg.barrier_mode == 0 || (a.cfg.barrier_mode == 1 && k == 0)) __syncthreads(); long long t0_ = prof ? clock64() : 0; if (live) { stmt; } if (prof) cyc[k] += clock64() - t0_; }
+    #define PH(k, stmt) { if (bmask & (1 << k)) __syncthreads(); long long t0_ = prof ? clock64() : 0; if (live) { stmt; } if (prof) cyc[k] += clock64() - t0_; }
     #pragma unroll 1
     for (int s = 0; s < nsub; s++) {
       const bool tap = s == nsub-1;
