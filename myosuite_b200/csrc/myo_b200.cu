@@ -174,6 +174,7 @@ __device__ __noinline__ void task_observe(const DevModel& m, Warp& w, const Step
 extern "C" __global__ void __launch_bounds__(384) myo_env_kernel(const __grid_constant__ DevModel m, const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) unsigned long long mbar;
+  __shared__ int s_ncand[16];
   const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   // ---- stage the model constants into shared memory: bulk async copies (TMA), completion on an mbarrier
   double* s_d = smem; idx_t* s_i = (idx_t*)(smem + m.nD); double* warp0 = smem + m.nD + (m.nI16w + 1)/2;
@@ -197,7 +198,7 @@ extern "C" __global__ void __launch_bounds__(384) myo_env_kernel(const __grid_co
   double* base = warp0 + (size_t)wid*m.n_per_warp;
   w.qpos = base+m.o_qpos; w.qvel = base+m.o_qvel; w.act = base+m.o_act; w.ctrl = base+m.o_ctrl; w.qws = base+m.o_qws; w.dax = base+m.o_dax; w.dan = base+m.o_dan;
   w.qM = base+m.o_qM; w.fsm = base+m.o_fsm; w.eprm = base+m.o_eprm; w.scr = base+m.o_scr;
-  w.ncon = w.nefc = w.nlimrow = w.niter = w.overflow = 0;
+  w.ncon = w.nefc = w.nlimrow = w.niter = w.overflow = w.ncand = 0;
   const myo_buffers& b = a.b;
   // All warps of a CTA walk the phases in lockstep (CTA barriers between phases) so that they share instruction fetches:
   // the step is a long, mostly straight-line program and the instruction cache, not the data path, is the scarce resource.
@@ -256,6 +257,10 @@ extern "C" __global__ void __launch_bounds__(384) myo_env_kernel(const __grid_co
       PH(2, phase_actuation(m, w, integrate, tap && b.tap_actuator_force ? b.tap_actuator_force + (size_t)env*m.nu : nullptr, tap && b.tap_ten_length ? b.tap_ten_length + (size_t)env*m.nu : nullptr));
       PH(3, phase_body_inertia(m, w); phase_crb(m, w); phase_bias(m, w));
       PH(4, phase_collision(m, w));
+      if (m.npair > m.npair_an) {   // CTA-cooperative pass over the expensive candidates of all envs of this CTA
+        if (w.lane == 0) s_ncand[wid] = live ? w.ncand : 0;
+        __syncthreads(); collision_coop(m, w, warp0, s_ncand, nw); __syncthreads();
+        if (live) collision_merge(m, w); }
       PH(5, phase_constraints(m, w); if (tap) write_taps_contacts(m, w, a, env));
       PH(6, phase_solve(m, w, a.tol, prof ? cyc : nullptr));
       PH(7, if (tap) write_taps_solve(m, w, a, env); if (integrate) phase_integrate(m, w));
@@ -340,8 +345,8 @@ static void fill_devmodel(const myo_model* mm, const myo_task_cfg* cfg, DevModel
   int t = 0; d.s_U = t; t += al2(3*(d.nsp+2*d.nwe)); d.s_WP = t; t += al2(6*d.nwe); d.s_PL = t; t += al2(d.nsp+d.nwe); d.s_mom = t; t += al2(d.nnz);
   d.s_tlen = t; t += al2(d.nta); d.s_tvel = t; t += al2(d.nta); d.s_tfrc = t; t += al2(d.nta); int sizeT = t;
   t = 0; d.s_cin = t; t += al2(10*d.nbd); d.s_crb = t; t += al2(10*d.nbd); d.s_bf = t; t += al2(6*d.nbd); int sizeC = t;
-  d.kcand = 64; int candsz = al2((d.kcand+1)/2);
-  t = 0; d.s_conJ = t; d.s_cres = t; d.s_clist = t; d.s_cidx = t; t += imax(al2(3*d.maxpath*mc), candsz); d.s_efD = t; t += al2(d.maxefc); d.s_efA = t; t += al2(d.maxefc); d.s_eqJ = t; t += al2(d.neq);
+  d.kcand = d.npair - d.npair_an; int candsz = al2((d.kcand+1)/2) + al2(7*d.kcand);
+  t = 0; d.s_conJ = t; d.s_clist = t; d.s_cres = t + al2((d.kcand+1)/2); d.s_cidx = t; t += imax(al2(3*d.maxpath*mc), candsz); d.s_efD = t; t += al2(d.maxefc); d.s_efA = t; t += al2(d.maxefc); d.s_eqJ = t; t += al2(d.neq);
   d.s_icon = t; t += al2((3*mc + 2*d.nlim + 4 + 1)/2); int sizeS3 = t;
   d.s_con = sizeS3; int sizeCon = al2(CON_STRIDE*mc);
   t = sizeS3; d.s_efR = t; t += al2(d.maxefc); d.s_efV = t; t += al2(d.maxefc); d.s_va = t; t += al2(d.nv); d.s_vg = t; t += al2(d.nv); d.s_vp = t; t += al2(d.nv);

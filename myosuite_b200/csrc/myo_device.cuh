@@ -57,7 +57,7 @@ struct Warp {   // per-warp view (registers)
   double *qpos, *qvel, *act, *ctrl, *qws, *dax, *dan, *qM, *fsm, *eprm, *scr;
   const double* cd; const idx_t* ci;   // staged constants
   int lane;
-  int ncon, nefc, nlimrow, niter, overflow;
+  int ncon, nefc, nlimrow, niter, overflow, ncand;
 };
 #define CI(name) (w.ci + m.hoff[MYO_SEC_##name])
 #define CD(name) (w.cd + m.hoff[MYO_SEC_##name])
@@ -589,21 +589,37 @@ __device__ void phase_collision(const DevModel& m, Warp& w) {
     int idx = ncon + __popc(m0 & lt) + __popc(m1 & lt);
     for (int c = 0; c < o.n; c++) store_contact(m, w, con, icon, idx + c, p, o, c);
     ncon += __popc(m0) + __popc(m1); }
-  // iterative ellipsoid colliders: rare and expensive -> conservative cull, compact, then one surviving candidate per lane
-  int* clist = (int*)SCR(s_clist);
+  // iterative ellipsoid colliders: rare and expensive -> conservative cull + compaction here; the survivors of ALL envs of the CTA are
+  // then evaluated cooperatively (collision_coop), one candidate per thread, so that no warp waits for another env's worst case
+  int* clist = (int*)SCR(s_clist); int ncand = 0;
   #pragma unroll 1
-  for (int cbase = m.npair_an; cbase < m.npair; ) { int ncand = 0;
-    #pragma unroll 1
-    for (; cbase < m.npair && ncand + 32 <= m.kcand; cbase += 32) { int p = cbase + w.lane; bool cand = p < m.npair && expensive_candidate(m, w, p);
-      unsigned mk = __ballot_sync(FULL, cand); if (cand) clist[ncand + __popc(mk & ((1u << w.lane) - 1))] = p; ncand += __popc(mk); }
-    __syncwarp();
-    #pragma unroll 1
-    for (int kb = 0; kb < ncand; kb += 32) { int k = kb + w.lane; ConOut o; o.n = 0; o.has_y = false; int p = k < ncand ? clist[k] : 0;
-      if (k < ncand) collide_pair(m, w, p, o);
-      unsigned m0 = __ballot_sync(FULL, o.n >= 1); int idx = ncon + __popc(m0 & ((1u << w.lane) - 1));
-      if (o.n) store_contact(m, w, con, icon, idx, p, o, 0);
-      ncon += __popc(m0); }
-    __syncwarp(); }
+  for (int cbase = m.npair_an; cbase < m.npair; cbase += 32) { int p = cbase + w.lane; bool cand = p < m.npair && expensive_candidate(m, w, p);
+    unsigned mk = __ballot_sync(FULL, cand); if (cand) clist[ncand + __popc(mk & ((1u << w.lane) - 1))] = p; ncand += __popc(mk); }
+  w.ncand = ncand;
+  if (ncon > m.maxcon) { w.overflow = 1; ncon = m.maxcon; }
+  w.ncon = ncon;
+  __syncwarp();
+}
+
+// cooperative evaluation: flat item f -> (owner warp, candidate k); the owner's poses / overrides are read from ITS shared-memory region
+__device__ void collision_coop(const DevModel& m, const Warp& self, double* warp0, const int* ncand_of, int nw) {
+  int total = 0; for (int q = 0; q < nw; q++) total += ncand_of[q];
+  #pragma unroll 1
+  for (int f = threadIdx.x; f < total; f += blockDim.x) { int owner = 0, k = f; while (k >= ncand_of[owner]) { k -= ncand_of[owner]; owner++; }
+    Warp w = self; double* base = warp0 + (size_t)owner*m.n_per_warp; w.scr = base + m.o_scr; w.eprm = base + m.o_eprm; w.qpos = base + m.o_qpos;
+    const int* clist = (const int*)SCR(s_clist); double* r = SCR(s_cres) + 7*k;
+    ConOut o; o.n = 0; o.has_y = false; collide_pair(m, w, clist[k], o);
+    r[0] = o.n ? o.dist[0] : 1e30; for (int c = 0; c < 3; c++) { r[1+c] = o.pos[0][c]; r[4+c] = o.nrm[0][c]; } }
+}
+// append the cooperative results (candidate order = pair order) to this env's contact list
+__device__ void collision_merge(const DevModel& m, Warp& w) {
+  double* con = SCR(s_con); int* icon = (int*)SCR(s_icon); const int* clist = (const int*)SCR(s_clist); const double* cres = SCR(s_cres); int ncon = w.ncon;
+  #pragma unroll 1
+  for (int kb = 0; kb < w.ncand; kb += 32) { int k = kb + w.lane; ConOut o; o.n = 0; o.has_y = false; int p = 0;
+    if (k < w.ncand) { const double* r = cres + 7*k; p = clist[k]; if (r[0] < 1e29) { o.n = 1; o.dist[0] = r[0]; for (int c = 0; c < 3; c++) { o.pos[0][c] = r[1+c]; o.nrm[0][c] = r[4+c]; } } }
+    unsigned m0 = __ballot_sync(FULL, o.n >= 1); int idx = ncon + __popc(m0 & ((1u << w.lane) - 1));
+    if (o.n) store_contact(m, w, con, icon, idx, p, o, 0);
+    ncon += __popc(m0); }
   if (ncon > m.maxcon) { w.overflow = 1; ncon = m.maxcon; }
   w.ncon = ncon;
   __syncwarp();

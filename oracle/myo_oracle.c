@@ -476,6 +476,8 @@ static int ellipsoid_ellipsoid(ora* o, int pair, int g1, int g2, double margin) 
   double dl[3] = {c2[0]-c1[0], c2[1]-c1[1], c2[2]-c1[2]};
   double rb1 = fmax(s1[0],fmax(s1[1],s1[2])), rb2 = fmax(s2[0],fmax(s2[1],s2[2]));
   if (norm3(dl)-rb1-rb2 > margin) return 0;
+  { /* any direction gives a lower bound on the signed distance: try the centre line before the expensive search */
+    double n = norm3(dl); if (n > MINVAL && ee_fl(acosl(dl[2]/n), atan2l(dl[1], dl[0]), dl, R1, s1, R2, s2) > margin) return 0; }
   /* signed distance = max over unit d of  d.(c2-c1) - h1(d) - h2(-d): coarse grid, then pattern search on the two angles */
   long double best = -1e30L, bt = 0, bp = 0; double d[3];
   for (int i = 1; i < 60; i++) for (int j = 0; j < 120; j++) { long double th = M_PI*i/60, ph = 2*M_PI*j/120, f = ee_fl(th, ph, dl, R1, s1, R2, s2); if (f > best) { best = f; bt = th; bp = ph; } }
@@ -496,6 +498,10 @@ static int capsule_ellipsoid(ora* o, int pair, int g1, int g2, double margin) { 
   const double* gs = DSEC(o,geom_size); const double *cc=o->geom_xpos+3*g1, *mc=o->geom_xmat+9*g1, *ce=o->geom_xpos+3*g2, *Re=o->geom_xmat+9*g2, *se=gs+3*g2;
   double r = gs[3*g1], h = gs[3*g1+1], ax[3] = {mc[2], mc[5], mc[8]}, dl[3] = {ce[0]-cc[0], ce[1]-cc[1], ce[2]-cc[2]};
   if (norm3(dl)-(r+h)-fmax(se[0],fmax(se[1],se[2])) > margin) return 0;
+  { /* lower bound from the direction (closest segment point -> ellipsoid centre) */
+    double t0 = clip(dot3(dl, ax), -h, h), q[3] = {dl[0]-ax[0]*t0, dl[1]-ax[1]*t0, dl[2]-ax[2]*t0}, nq = norm3(q);
+    if (nq > MINVAL) { double d0[3] = {q[0]/nq, q[1]/nq, q[2]/nq}, b[3]; matT_vec(b, Re, d0);
+      if (nq - sqrt(se[0]*se[0]*b[0]*b[0]+se[1]*se[1]*b[1]*b[1]+se[2]*se[2]*b[2]*b[2]) - r > margin) return 0; } }
   /* min over the segment parameter of the (convex) point-ellipsoid distance: bisection on its derivative n.a */
   double lo = -h, hi = h, n[3], x[3], p[3];
   for (int k = 0; k < 3; k++) p[k] = cc[k]+ax[k]*lo; point_ellipsoid(p, ce, Re, se, n, x); double glo = dot3(n, ax);
