@@ -135,6 +135,7 @@ __device__ void phase_kinematics(const DevModel& m, Warp& w) {
         if (t == 0) {   // free joint: pose straight from qpos (normalised copy of the quaternion; qpos itself is left untouched)
           const double* qp = w.qpos + qa; double qn[4] = {qp[3], qp[4], qp[5], qp[6]}; quat_norm(qn);
           pos[0]=qp[0]; pos[1]=qp[1]; pos[2]=qp[2]; quat2mat(R, qn);
+          #pragma unroll
           for (int c = 0; c < 3; c++) {
             w.dax[3*(da+c)] = c==0; w.dax[3*(da+c)+1] = c==1; w.dax[3*(da+c)+2] = c==2;
             w.dan[3*(da+c)] = 0; w.dan[3*(da+c)+1] = 0; w.dan[3*(da+c)+2] = 0;
@@ -155,7 +156,9 @@ __device__ void phase_kinematics(const DevModel& m, Warp& w) {
           w.dax[3*da]=ax[0]; w.dax[3*da+1]=ax[1]; w.dax[3*da+2]=ax[2]; w.dan[3*da]=an[0]; w.dan[3*da+1]=an[1]; w.dan[3*da+2]=an[2];
         }
       }
+      #pragma unroll
       for (int c = 0; c < 3; c++) xpos[3*k+c] = pos[c];
+      #pragma unroll
       for (int c = 0; c < 9; c++) xmat[9*k+c] = R[c];
     }
     __syncwarp();
@@ -415,14 +418,16 @@ __device__ __forceinline__ const double* geom_size(const DevModel& m, const Warp
 // full world rotation of a collision geom (ellipsoids need it)
 __device__ __forceinline__ void geom_mat(const DevModel& m, const Warp& w, int g, double* mat) {
   int b = CI(PG_body)[g]; const double* gd = CD(PG_d) + g*PG_STRIDE;
-  if (b < 0) { for (int c = 0; c < 9; c++) mat[c] = gd[3+c]; } else mat_mul(mat, SCR(s_xmat) + 9*b, gd + 3); }
+  if (b < 0) {
+    #pragma unroll
+    for (int c = 0; c < 9; c++) mat[c] = gd[3+c]; } else mat_mul(mat, SCR(s_xmat) + 9*b, gd + 3); }
 
 // ---- ellipsoid colliders.  MuJoCo routes ellipsoid-capsule / ellipsoid-ellipsoid through its general convex collider: one
 // contact, signed distance = max over unit d of  d.(c2-c1) - h1(d) - h2(-d)  (h = support function), witnesses = support points.
 // Here: Newton on the unit sphere for that maximisation (smooth for ellipsoids and points).
 // body 1: ellipsoid (R1, s1) or a point (s1 == nullptr); body 2: ellipsoid.  dl = c2 - c1.  d: in = start, out = maximiser.
 // p1, p2: support offsets (witness on body 1 = c1 + p1, on body 2 = c2 - p2).
-__device__ __noinline__ double ell_sd(const double* dl, const double* R1, const double* s1, const double* R2, const double* s2, double* d, double* p1, double* p2) {
+__device__ __forceinline__ double ell_sd(const double* dl, const double* R1, const double* s1, const double* R2, const double* s2, double* d, double* p1, double* p2) {
   double f = 0;
   #pragma unroll 1
   for (int it = 0; it < 40; it++) {
@@ -469,15 +474,24 @@ struct ConOut { int n; double dist[2]; double pos[2][3]; double nrm[2][3]; doubl
 __device__ __forceinline__ void sph_sph(ConOut& o, double margin, const double* p1, double r1, const double* p2, double r2) {
   double dv[3] = {p2[0]-p1[0], p2[1]-p1[1], p2[2]-p1[2]}, cd = sqrt(dot3(dv,dv)), dist = cd-r1-r2;
   if (dist > margin || o.n >= 2) return;
-  int c = o.n++; o.dist[c] = dist;
-  if (cd < MYO_MINVAL) { o.nrm[c][0]=1; o.nrm[c][1]=0; o.nrm[c][2]=0; } else { double q = 1.0/cd; o.nrm[c][0]=dv[0]*q; o.nrm[c][1]=dv[1]*q; o.nrm[c][2]=dv[2]*q; }
-  for (int k = 0; k < 3; k++) o.pos[c][k] = p1[k] + o.nrm[c][k]*(r1+0.5*dist); }
+  double nx, ny, nz; if (cd < MYO_MINVAL) { nx = 1; ny = 0; nz = 0; } else { double q = 1.0/cd; nx = dv[0]*q; ny = dv[1]*q; nz = dv[2]*q; }
+  double off = r1+0.5*dist;
+  if (o.n == 0) { o.dist[0] = dist; o.nrm[0][0] = nx; o.nrm[0][1] = ny; o.nrm[0][2] = nz; o.pos[0][0] = p1[0]+nx*off; o.pos[0][1] = p1[1]+ny*off; o.pos[0][2] = p1[2]+nz*off; }
+  else { o.dist[1] = dist; o.nrm[1][0] = nx; o.nrm[1][1] = ny; o.nrm[1][2] = nz; o.pos[1][0] = p1[0]+nx*off; o.pos[1][1] = p1[1]+ny*off; o.pos[1][2] = p1[2]+nz*off; }
+  o.n++; }
 __device__ __forceinline__ void plane_sph(ConOut& o, double margin, const double* pp, const double* pn, const double* sp, double r) {
   double dv[3] = {sp[0]-pp[0], sp[1]-pp[1], sp[2]-pp[2]}, dist = dot3(dv,pn)-r;
   if (dist > margin || o.n >= 2) return;
-  int c = o.n++; o.dist[c] = dist; for (int k = 0; k < 3; k++) { o.nrm[c][k] = pn[k]; o.pos[c][k] = sp[k]-pn[k]*(r+0.5*dist); } }
+  double off = r+0.5*dist;
+  if (o.n == 0) { o.dist[0] = dist;
+    #pragma unroll
+    for (int k = 0; k < 3; k++) { o.nrm[0][k] = pn[k]; o.pos[0][k] = sp[k]-pn[k]*off; } }
+  else { o.dist[1] = dist;
+    #pragma unroll
+    for (int k = 0; k < 3; k++) { o.nrm[1][k] = pn[k]; o.pos[1][k] = sp[k]-pn[k]*off; } }
+  o.n++; }
 
-__device__ void collide_pair(const DevModel& m, const Warp& w, int p, ConOut& o) {
+__device__ __forceinline__ void collide_analytic(const DevModel& m, const Warp& w, int p, ConOut& o) {
   const idx_t* pr = CI(PPAIR) + PPAIR_ISTRIDE*p; const double* pd = CD(PPAIR_d) + pr[6]*PPAIR_STRIDE; const double* G = CD(PG_d);
   int g1 = pr[0], g2 = pr[1], ct = pr[5]; double margin = pd[0]; o.n = 0; o.has_y = false;
   const double* s1 = geom_size(m, w, g1); const double* s2 = geom_size(m, w, g2); (void)G;
@@ -514,7 +528,15 @@ __device__ void collide_pair(const DevModel& m, const Warp& w, int p, ConOut& o)
     u[0] = s2[0]*s2[0]*nl[0]; u[1] = s2[1]*s2[1]*nl[1]; u[2] = s2[2]*s2[2]*nl[2]; double nn = sqrt(dot3(nl, u)); mat_vec(pw, R2, u);
     double pos[3] = {x2[0]-pw[0]/nn, x2[1]-pw[1]/nn, x2[2]-pw[2]/nn}, dv[3] = {pos[0]-x1[0], pos[1]-x1[1], pos[2]-x1[2]}, dist = dot3(dv, a1);
     if (dist <= margin) { o.n = 1; o.dist[0] = dist; for (int k = 0; k < 3; k++) { o.nrm[0][k] = a1[k]; o.pos[0][k] = pos[k]-a1[k]*0.5*dist; } }
-  } else if (ct == CT_CAP_ELL) {     // g1 capsule (segment + radius), g2 ellipsoid: min over the segment of the point-ellipsoid distance
+  }
+}
+
+__device__ __forceinline__ void collide_ellipsoid(const DevModel& m, const Warp& w, int p, ConOut& o) {
+  const idx_t* pr = CI(PPAIR) + PPAIR_ISTRIDE*p; const double* pd = CD(PPAIR_d) + pr[6]*PPAIR_STRIDE; const double* G = CD(PG_d);
+  int g1 = pr[0], g2 = pr[1], ct = pr[5]; double margin = pd[0]; o.n = 0; o.has_y = false;
+  const double* s1 = geom_size(m, w, g1); const double* s2 = geom_size(m, w, g2); (void)G;
+  double x1[3], a1[3], x2[3], a2[3]; geom_pose(m, w, g1, x1, a1); geom_pose(m, w, g2, x2, a2);
+  if (ct == CT_CAP_ELL) {     // g1 capsule (segment + radius), g2 ellipsoid: min over the segment of the point-ellipsoid distance
     double r = s1[0], h = s1[1], dv[3] = {x2[0]-x1[0], x2[1]-x1[1], x2[2]-x1[2]}, rb = fmax(s2[0], fmax(s2[1], s2[2]));
     double d[3], p1[3], p2[3], t = clipd(dot3(dv, a1), -h, h), dl[3];
     { double q[3] = {dv[0]-a1[0]*t, dv[1]-a1[1]*t, dv[2]-a1[2]*t}; if (sqrt(dot3(q,q)) - r - rb > margin) return; }
@@ -584,10 +606,11 @@ __device__ void phase_collision(const DevModel& m, Warp& w) {
   // analytic primitives: one pair per lane
   #pragma unroll 1
   for (int base = 0; base < m.npair_an; base += 32) { int p = base + w.lane; ConOut o; o.n = 0; o.has_y = false;
-    if (p < m.npair_an) collide_pair(m, w, p, o);
+    if (p < m.npair_an) collide_analytic(m, w, p, o);
     unsigned m0 = __ballot_sync(FULL, o.n >= 1), m1 = __ballot_sync(FULL, o.n >= 2), lt = (1u << w.lane) - 1;
     int idx = ncon + __popc(m0 & lt) + __popc(m1 & lt);
-    for (int c = 0; c < o.n; c++) store_contact(m, w, con, icon, idx + c, p, o, c);
+    if (o.n >= 1) store_contact(m, w, con, icon, idx, p, o, 0);
+    if (o.n >= 2) store_contact(m, w, con, icon, idx + 1, p, o, 1);
     ncon += __popc(m0) + __popc(m1); }
   // iterative ellipsoid colliders: rare and expensive -> conservative cull + compaction here; the survivors of ALL envs of the CTA are
   // then evaluated cooperatively (collision_coop), one candidate per thread, so that no warp waits for another env's worst case
@@ -608,7 +631,7 @@ __device__ void collision_coop(const DevModel& m, const Warp& self, double* warp
   for (int f = threadIdx.x; f < total; f += blockDim.x) { int owner = 0, k = f; while (k >= ncand_of[owner]) { k -= ncand_of[owner]; owner++; }
     Warp w = self; double* base = warp0 + (size_t)owner*m.n_per_warp; w.scr = base + m.o_scr; w.eprm = base + m.o_eprm; w.qpos = base + m.o_qpos;
     const int* clist = (const int*)SCR(s_clist); double* r = SCR(s_cres) + 7*k;
-    ConOut o; o.n = 0; o.has_y = false; collide_pair(m, w, clist[k], o);
+    ConOut o; o.n = 0; o.has_y = false; collide_ellipsoid(m, w, clist[k], o);
     r[0] = o.n ? o.dist[0] : 1e30; for (int c = 0; c < 3; c++) { r[1+c] = o.pos[0][c]; r[4+c] = o.nrm[0][c]; } }
 }
 // append the cooperative results (candidate order = pair order) to this env's contact list
