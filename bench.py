@@ -129,7 +129,7 @@ def main():
         oracle_py.build()
         thr = max(1, cores)
         rate1 = cpu_baseline(args.env, 10, threads=1)      # calibrate, then size the bounded sample to ~8 s of stepping per core
-        per_thread = int(max(20, min(20000, 8.0 * rate1)))
+        per_thread = int(max(20, min(20000, 2.5 * rate1)))   # ~2.5 s of stepping per core at the unloaded rate (longer once all cores are busy)
         t0 = time.perf_counter()
         v = cpu_baseline(args.env, per_thread, threads=thr)
         ms = (time.perf_counter() - t0) * 1e3
