@@ -60,7 +60,7 @@ typedef struct {
   int32_t maxcon;            /* 0 = library default */
   int32_t reaf_dst, reaf_src;/* reafferentation (base_v0.py:104-108): ctrl[dst] = ctrl[src]; ctrl[src] = 0 ; dst == src = off */
   int32_t barrier_mode;      /* CTA phase barriers: 0 = before every phase (default), 1 = once per substep, 2 = none, >2 = bit mask of the 8 phases that start with a barrier (tuning knob) */
-  int32_t reserved_i;
+  int32_t reserved_i;        /* lockstep groups per CTA (tuning knob; 0/1 = the whole CTA is one group) */
   double pose_thd;           /* pose_v0.py:43 */
   double weights[8];         /* reward weights in the task's own key order (pose_v0.py:18-23, walk_v0.py:205-211, obj_hold_v0.py:17-21) */
   double solver_tolerance;   /* scaled-gradient stop of the Newton solver; 0 = library default (1e-10) */

@@ -170,6 +170,10 @@ __device__ __noinline__ void task_observe(const DevModel& m, Warp& w, const Step
   __syncwarp();
 }
 
+// barrier among the warps of one lockstep group (named barrier); one group = the whole CTA -> __syncthreads()
+__device__ __forceinline__ void group_sync(int ngroups, int gid, int gthreads) {
+  if (ngroups <= 1) __syncthreads(); else asm volatile("bar.sync %0, %1;" :: "r"(1 + gid), "r"(gthreads) : "memory"); }
+
 // ------------------------------------------------------------------ the kernel
 extern "C" __global__ void __launch_bounds__(384) myo_env_kernel(const __grid_constant__ DevModel m, const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(16) double smem[];
@@ -247,9 +251,11 @@ extern "C" __global__ void __launch_bounds__(384) myo_env_kernel(const __grid_co
       __syncwarp();
     }
     // ---- physics substeps: forward dynamics + semi-implicit Euler (the only copy of the phase code in the kernel)
+    const int ngroups = a.cfg.reserved_i > 1 ? (a.cfg.reserved_i < nw ? a.cfg.reserved_i : nw) : 1;
+    const int gsz = (nw + ngroups - 1)/ngroups, gid = wid / gsz, gw0 = gid*gsz, gnw = (gw0 + gsz <= nw ? gsz : nw - gw0), gthreads = gnw*32;
     const int bmask = a.cfg.barrier_mode == 0 ? 0xFF : (a.cfg.barrier_mode == 1 ? 0x01 : (a.cfg.barrier_mode == 2 ? 0 : a.cfg.barrier_mode));
     long long cyc[16] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}; int maxcon_seen = 0, maxefc_seen = 0;
-    #define PH(k, stmt) { if (bmask & (1 << k)) __syncthreads(); long long t0_ = prof ? clock64() : 0; if (live) { stmt; } if (prof) cyc[k] += clock64() - t0_; }
+    #define PH(k, stmt) { if (bmask & (1 << k)) group_sync(ngroups, gid, gthreads); long long t0_ = prof ? clock64() : 0; if (live) { stmt; } if (prof) cyc[k] += clock64() - t0_; }
     #pragma unroll 1
     for (int s = 0; s < nsub; s++) {
       const bool tap = s == nsub-1;
@@ -260,7 +266,7 @@ extern "C" __global__ void __launch_bounds__(384) myo_env_kernel(const __grid_co
       PH(4, phase_collision(m, w));
       if (m.npair > m.npair_an) {   // CTA-cooperative pass over the expensive candidates of all envs of this CTA
         if (w.lane == 0) s_ncand[wid] = live ? w.ncand : 0;
-        __syncthreads(); collision_coop(m, w, warp0, s_ncand, nw); __syncthreads();
+        group_sync(ngroups, gid, gthreads); collision_coop(m, w, warp0, s_ncand, gw0, gnw); group_sync(ngroups, gid, gthreads);
         if (live) collision_merge(m, w); }
       PH(5, phase_constraints(m, w); if (tap) write_taps_contacts(m, w, a, env));
       PH(6, phase_solve(m, w, a.tol, prof ? cyc : nullptr));

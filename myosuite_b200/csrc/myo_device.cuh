@@ -636,10 +636,10 @@ __device__ void phase_collision(const DevModel& m, Warp& w) {
 }
 
 // cooperative evaluation: flat item f -> (owner warp, candidate k); the owner's poses / overrides are read from ITS shared-memory region
-__device__ void collision_coop(const DevModel& m, const Warp& self, double* warp0, const int* ncand_of, int nw) {
-  int total = 0; for (int q = 0; q < nw; q++) total += ncand_of[q];
+__device__ void collision_coop(const DevModel& m, const Warp& self, double* warp0, const int* ncand_of, int w0, int nw) {
+  int total = 0; for (int q = 0; q < nw; q++) total += ncand_of[w0+q];
   #pragma unroll 1
-  for (int f = threadIdx.x; f < total; f += blockDim.x) { int owner = 0, k = f; while (k >= ncand_of[owner]) { k -= ncand_of[owner]; owner++; }
+  for (int f = threadIdx.x - 32*w0; f < total; f += 32*nw) { int owner = w0, k = f; while (k >= ncand_of[owner]) { k -= ncand_of[owner]; owner++; }
     Warp w = self; double* base = warp0 + (size_t)owner*m.n_per_warp; w.scr = base + m.o_scr; w.eprm = base + m.o_eprm; w.qpos = base + m.o_qpos;
     const int* clist = (const int*)SCR(s_clist); double* r = SCR(s_cres) + 7*k;
     ConOut o; o.n = 0; o.has_y = false; collide_ellipsoid(m, w, clist[k], o);

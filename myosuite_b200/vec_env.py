@@ -116,6 +116,7 @@ class MyoVecEnv:
         cfg.solver_tolerance = float(kw.get("solver_tolerance", 0.0))
         cfg.maxcon = int(kw.get("maxcon", 0))
         cfg.barrier_mode = int(kw.get("barrier_mode", 0))
+        cfg.reserved_i = int(kw.get("lockstep_groups", 0))
         cfg.reaf_dst = cfg.reaf_src = -1
         if self.muscle_condition == "reafferentation":   # base_v0.py:78-79,104-108
             cfg.reaf_dst, cfg.reaf_src = m.name2id("actuator", "EPL"), m.name2id("actuator", "EIP")
