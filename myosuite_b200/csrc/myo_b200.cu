@@ -317,7 +317,7 @@ extern "C" int myo_model_from_blob(const int32_t* I, int64_t nI, const double* D
   if (I[0] != MYO_BLOB_MAGIC || I[1] != MYO_BLOB_VERSION || I[2] != MYO_NDIM || I[3] != MYO_NSEC) return fail("myo_model_from_blob: blob magic/version/layout mismatch");
   for (int s = 0; s < MYO_NSEC; s++) { long long off = MYO_SEC_OFF(I, s), len = MYO_SEC_LEN(I, s); int kind = I[MYO_BLOB_HDR+MYO_NDIM+3*s];
     if (off < 0 || len < 0 || off + len > (kind ? nD : nI)) return fail("myo_model_from_blob: section out of range"); }
-  if (MYO_SEC_LEN(I, MYO_SEC_P_dims) < 25 || MYO_SEC_LEN(I, MYO_SEC_HOT_off) != MYO_NSEC) return fail("myo_model_from_blob: blob carries no kernel program (pack with program=build_program(m))");
+  if (MYO_SEC_LEN(I, MYO_SEC_P_dims) < 26 || MYO_SEC_LEN(I, MYO_SEC_HOT_off) != MYO_NSEC) return fail("myo_model_from_blob: blob carries no kernel program (pack with program=build_program(m))");
   myo_model* m = new myo_model(); m->I.assign(I, I+nI); m->D.assign(D, D+nD); *out = m; return 0;
 }
 extern "C" void myo_model_destroy(myo_model* m) { delete m; }
@@ -335,7 +335,7 @@ static void fill_devmodel(const myo_model* mm, const myo_task_cfg* cfg, DevModel
   d.npair = P[PD_NPAIR]; d.npair_an = P[PD_NPAIR_ANALYTIC]; d.maxpath = P[PD_MAXPATH]; d.ndepth = P[PD_NDEPTH]; d.eq_tree = P[PD_EQ_TREE];
   const double* opt = MYO_DSEC(I, D, MYO_SEC_opt); d.timestep = opt[0]; d.gx = opt[1]; d.gy = opt[2]; d.gz = opt[3]; d.tolerance = opt[4]; d.meaninertia = opt[6];
   d.ovr_geom = (cfg && cfg->task == MYO_TASK_HOLD) ? cfg->task_i[1] : -1;
-  int mc = cfg && cfg->maxcon > 0 ? cfg->maxcon : 32; if (mc > 2*d.npair) mc = 2*d.npair; d.maxcon = mc; d.maxefc = d.neq + 2*d.nlim + 4*mc;
+  int mc = cfg && cfg->maxcon > 0 ? cfg->maxcon : 32; if (mc > 2*d.npair) mc = 2*d.npair; d.maxcon = mc; d.nlimrow = P[PD_NLIMROW] > 0 ? P[PD_NLIMROW] : 2*d.nlim; d.maxefc = d.neq + d.nlimrow + 4*mc;
   int o = 0;
   #define TAKE(field, n) d.field = o; o += al2(n)
   TAKE(o_qpos, d.nq); TAKE(o_qvel, d.nv); TAKE(o_act, d.na); TAKE(o_ctrl, d.nu); TAKE(o_qws, d.nv); TAKE(o_dax, 3*d.nv); TAKE(o_dan, 3*d.nv); TAKE(o_qM, d.nM); TAKE(o_fsm, d.nv); TAKE(o_eprm, 8); d.nwz = P[PD_NWE_SPH_IN] + P[PD_NWE_CYL_IN]; TAKE(o_wz, d.nwz);
@@ -352,9 +352,11 @@ static void fill_devmodel(const myo_model* mm, const myo_task_cfg* cfg, DevModel
   int t = 0; d.s_U = t; t += al2(3*(d.nsp+2*d.nwe)); d.s_WP = t; t += al2(6*d.nwe); d.s_PL = t; t += al2(d.nsp+d.nwe); d.s_mom = t; t += al2(d.nnz);
   d.s_tlen = t; t += al2(d.nta); d.s_tvel = t; t += al2(d.nta); d.s_tfrc = t; t += al2(d.nta); int sizeT = t;
   t = 0; d.s_cin = t; t += al2(10*d.nbd); d.s_crb = t; t += al2(10*d.nbd); d.s_bf = t; t += al2(6*d.nbd); int sizeC = t;
-  d.kcand = d.npair - d.npair_an; int candsz = al2((d.kcand+1)/2) + al2(7*d.kcand);
-  t = 0; d.s_conJ = t; d.s_clist = t; d.s_cres = t + al2((d.kcand+1)/2); d.s_cidx = t; t += imax(al2(3*d.maxpath*mc), candsz); d.s_efD = t; t += al2(d.maxefc); d.s_efA = t; t += al2(d.maxefc); d.s_eqJ = t; t += al2(d.neq);
-  d.s_icon = t; t += al2((3*mc + 2*d.nlim + 4 + 1)/2); int sizeS3 = t;
+  // expensive-candidate buffers share the contact-Jacobian region; they hold every iterative pair when that fits, else as many as the region takes
+  d.kcand = d.npair - d.npair_an; { int room = al2(3*d.maxpath*mc) - al2((d.kcand+1)/2); if (d.kcand > 16 && 7*d.kcand > room) d.kcand = imax(16, room/7); }
+  int candsz = al2((d.npair - d.npair_an + 1)/2) + al2(7*d.kcand);
+  t = 0; d.s_conJ = t; d.s_clist = t; d.s_cres = t + al2((d.npair - d.npair_an + 1)/2); d.s_cidx = t; t += imax(al2(3*d.maxpath*mc), candsz); d.s_efD = t; t += al2(d.maxefc); d.s_efA = t; t += al2(d.maxefc); d.s_eqJ = t; t += al2(d.neq);
+  d.s_icon = t; t += al2((3*mc + d.nlimrow + 4 + 1)/2); int sizeS3 = t;
   d.s_con = sizeS3; int sizeCon = al2(CON_STRIDE*mc);
   t = sizeS3; d.s_efR = t; t += al2(d.maxefc); d.s_efV = t; t += al2(d.maxefc); d.s_va = t; t += al2(d.nv); d.s_vg = t; t += al2(d.nv); d.s_vp = t; t += al2(d.nv);
   d.s_vMa = t; t += al2(d.nv); d.s_vMp = t; t += al2(d.nv);

@@ -19,7 +19,7 @@ typedef short idx_t;
 
 // P_dims slots (must match myosuite_b200/program.py)
 enum { PD_NBD, PD_NLEVEL, PD_NPT, PD_NSP, PD_NWE, PD_NTA, PD_NNZ, PD_NTERM, PD_NLIM, PD_NEQ, PD_NPAIR, PD_NGC, PD_MAXPATH,
-       PD_MAXCHAIN, PD_NSUB, PD_NROW, PD_NCOL, PD_NPIECE, PD_NWE_SPH_OUT, PD_NWE_SPH_IN, PD_NWE_CYL_OUT, PD_NWE_CYL_IN, PD_NDEPTH, PD_EQ_TREE, PD_NPAIR_ANALYTIC };
+       PD_MAXCHAIN, PD_NSUB, PD_NROW, PD_NCOL, PD_NPIECE, PD_NWE_SPH_OUT, PD_NWE_SPH_IN, PD_NWE_CYL_OUT, PD_NWE_CYL_IN, PD_NDEPTH, PD_EQ_TREE, PD_NPAIR_ANALYTIC, PD_NLIMROW };
 #define PB_STRIDE 22      // pos[3] R[9] ipos[3] mass Iloc[6]
 #define PWE_STRIDE 16
 #define PA_STRIDE 28
@@ -31,7 +31,7 @@ enum { PD_NBD, PD_NLEVEL, PD_NPT, PD_NSP, PD_NWE, PD_NTA, PD_NNZ, PD_NTERM, PD_N
 #define PEQ_STRIDE 16
 #define PEQ_ISTRIDE 6
 enum { CT_NONE, CT_CAP_CAP, CT_SPH_SPH, CT_SPH_CAP, CT_PLANE_SPH, CT_PLANE_CAP, CT_PLANE_ELL, CT_CAP_ELL, CT_ELL_ELL };
-#define CON_STRIDE 14   // dist, pos[3], frame[9], pad
+#define CON_STRIDE 10   // dist, pos[3], normal[3], tangent1[3]  (tangent2 = normal x tangent1 is rebuilt by the constraint phase)
 
 // ------------------------------------------------------------------ device-resident model view (kernel parameter)
 struct DevModel {
@@ -40,7 +40,7 @@ struct DevModel {
   int32_t hoff[MYO_NSEC];                  // offset of each hot section (in shorts / doubles), -1 if not staged
   int32_t nq, nv, nu, na, nM, njnt;
   int32_t nbd, nlevel, nsp, nwe, nta, nnz, nlim, neq, npair, npair_an, maxpath, ndepth, eq_tree;
-  int32_t maxcon, maxefc, ovr_geom;          // ovr_geom: collision geom whose size comes from the per-env overrides (-1: none)
+  int32_t maxcon, maxefc, nlimrow, ovr_geom;          // ovr_geom: collision geom whose size comes from the per-env overrides (-1: none)
   double timestep, gx, gy, gz, meaninertia, tolerance;
   // per-warp shared-memory layout, in doubles.  Persistent part:
   int32_t o_qpos, o_qvel, o_act, o_ctrl, o_qws, o_dax, o_dan, o_qM, o_fsm, o_eprm, o_wz, nwz, o_scr, n_per_warp;
@@ -607,7 +607,7 @@ __device__ __forceinline__ void store_contact(const DevModel& m, Warp& w, double
   if (o.has_y) { y[0]=o.yh[0]; y[1]=o.yh[1]; y[2]=o.yh[2]; }
   if (sqrt(dot3(y,y)) < 0.5) { y[0]=0; y[1]=0; y[2]=0; if (f[1] < 0.5 && f[1] > -0.5) y[1] = 1; else y[2] = 1; }
   double dd = dot3(f, y); y[0]-=dd*f[0]; y[1]-=dd*f[1]; y[2]-=dd*f[2]; double n = 1.0/sqrt(dot3(y,y)); y[0]*=n; y[1]*=n; y[2]*=n;
-  f[3]=y[0]; f[4]=y[1]; f[5]=y[2]; cross3(f+6, f, y);
+  f[3]=y[0]; f[4]=y[1]; f[5]=y[2];
   icon[ci] = p; }
 
 // Contacts are listed analytic colliders first (pair order), then the iterative ellipsoid colliders (pair order).
@@ -628,7 +628,8 @@ __device__ void phase_collision(const DevModel& m, Warp& w) {
   int* clist = (int*)SCR(s_clist); int ncand = 0;
   #pragma unroll 1
   for (int cbase = m.npair_an; cbase < m.npair; cbase += 32) { int p = cbase + w.lane; bool cand = p < m.npair && expensive_candidate(m, w, p);
-    unsigned mk = __ballot_sync(FULL, cand); if (cand) clist[ncand + __popc(mk & ((1u << w.lane) - 1))] = p; ncand += __popc(mk); }
+    unsigned mk = __ballot_sync(FULL, cand); int slot = ncand + __popc(mk & ((1u << w.lane) - 1)); if (cand && slot < m.kcand) clist[slot] = p; ncand += __popc(mk); }
+  if (ncand > m.kcand) { ncand = m.kcand; w.overflow = 1; }   // (kcand = capacity of the candidate buffers)
   w.ncand = ncand;
   if (ncon > m.maxcon) { w.overflow = 1; ncon = m.maxcon; }
   w.ncon = ncon;

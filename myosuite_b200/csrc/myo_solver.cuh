@@ -99,7 +99,7 @@ __device__ void phase_constraints(const DevModel& m, Warp& w) {
     int total = __shfl_sync(FULL, incl, 31);
     if (c < w.ncon) { s.crow[c] = rowbase + incl - nr; s.cnrow[c] = nr; }
     if (c < w.ncon && nr) { const idx_t* q = pr + PPAIR_ISTRIDE*s.cpair[c]; const double* P = pd + q[6]*PPAIR_STRIDE; const double* cd = s.con + c*CON_STRIDE;
-      const double* pos = cd + 1; const double* f = cd + 4; double* J = s.conJ + (size_t)c*3*m.maxpath; double vn = 0, v1 = 0, v2 = 0;
+      const double* pos = cd + 1; double f[9]; for (int k = 0; k < 6; k++) f[k] = cd[4+k]; cross3(f+6, f, f+3); double* J = s.conJ + (size_t)c*3*m.maxpath; double vn = 0, v1 = 0, v2 = 0;
       for (int e = 0; e < q[4]; e++) { int code = path[q[3]+e], d = code >> 1; double sg = (code & 1) ? 1.0 : -1.0, cv[3]; dof_point_vel(m, w, d, pos, cv);
         double jn = sg*dot3(f, cv), j1 = sg*dot3(f+3, cv), j2 = sg*dot3(f+6, cv); J[3*e] = jn; J[3*e+1] = j1; J[3*e+2] = j2;
         double qd = w.qvel[d]; vn += jn*qd; v1 += j1*qd; v2 += j2*qd; }

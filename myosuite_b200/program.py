@@ -21,7 +21,7 @@ from . import mjmath as mm
 # P_dims slots
 (PD_NBD, PD_NLEVEL, PD_NPT, PD_NSP, PD_NWE, PD_NTA, PD_NNZ, PD_NTERM, PD_NLIM, PD_NEQ, PD_NPAIR, PD_NGC, PD_MAXPATH,
  PD_MAXCHAIN, PD_NSUB, PD_NROW, PD_NCOL, PD_NPIECE, PD_NWE_SPH_OUT, PD_NWE_SPH_IN, PD_NWE_CYL_OUT, PD_NWE_CYL_IN,
- PD_NDEPTH, PD_EQ_TREE, PD_NPAIR_ANALYTIC) = range(25)
+ PD_NDEPTH, PD_EQ_TREE, PD_NPAIR_ANALYTIC, PD_NLIMROW) = range(26)
 NPDIM = 26
 
 PB_STRIDE, PWE_STRIDE, PA_STRIDE, PG_STRIDE, PPAIR_STRIDE, PLIM_STRIDE, PEQ_STRIDE = 22, 16, 28, 16, 12, 12, 16
@@ -405,6 +405,8 @@ def build_program(m):
     dims[PD_NPIECE] = len(PT_piece)
     dims[PD_NWE_SPH_OUT], dims[PD_NWE_SPH_IN], dims[PD_NWE_CYL_OUT], dims[PD_NWE_CYL_IN] = counts
     dims[PD_NDEPTH], dims[PD_EQ_TREE], dims[PD_NPAIR_ANALYTIC] = ndepth, eq_tree, n_analytic
+    # limit rows that can be active at once: both sides of a joint only when its range is narrower than twice the margin
+    dims[PD_NLIMROW] = sum(2 if (r[1] - r[0]) < 2 * r[2] else 1 for r in PLIM_d)
 
     def ia(x, shape=None):
         a = np.asarray(x, dtype=np.int32)
