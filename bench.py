@@ -117,6 +117,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--barrier-mode", type=int, default=0)
     ap.add_argument("--lockstep-groups", type=int, default=0)
+    ap.add_argument("--solver-tolerance", type=float, default=0.0, help="Newton stop (scaled gradient); 0 = library default")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -153,7 +154,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n = args.envs_per_gpu
-    env = vec_env.MyoVecEnv(args.env, n, device=local_rank, seed=0, env_offset=rank * n, barrier_mode=args.barrier_mode, lockstep_groups=args.lockstep_groups)
+    env = vec_env.MyoVecEnv(args.env, n, device=local_rank, seed=0, env_offset=rank * n, barrier_mode=args.barrier_mode, lockstep_groups=args.lockstep_groups, solver_tolerance=args.solver_tolerance)
     env.reset(seed=0)
     nu = env.act_dim
     gen = torch.Generator(device=env.device).manual_seed(1234 + rank)

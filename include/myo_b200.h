@@ -66,7 +66,7 @@ typedef struct {
   double solver_tolerance;   /* scaled-gradient stop of the Newton solver; 0 = library default (1e-10) */
   int32_t task_i[16];        /* task-specific indices, filled by the host mirror (vec_env.py): WALK body/joint ids, HOLD object ids */
   double task_d[24];         /* task-specific constants: WALK targets / thresholds / torso quaternion offset, HOLD object site */
-  double reserved[2];
+  double reserved[2];        /* [0] != 0 with the phase-cycle tap bound: record the barrier wait before each phase instead of its work (profiling) */
 } myo_task_cfg;
 
 /* caller-owned device buffers; nullable ones are marked.  f64 state, f32 I/O like the reference
@@ -102,7 +102,7 @@ typedef struct {
   double* tap_contact_dist;  /* [n, maxcon] */
   double* tap_moment;        /* [n, nnz] structural non-zeros of the tendon moment */
   double* tap_qM;            /* [n, nM] */
-  long long* tap_phase_cycles; /* [n, 16] SM-clock cycles spent per phase over the whole call (profiling aid; slots 12,13: max ncon / max nefc over substeps) */
+  long long* tap_phase_cycles; /* [n, 20] SM-clock cycles per phase over the call (profiling aid; 8-11 solver parts, 12,13: max ncon / nefc, 14,15: Newton iterations / dense ones, 16: cooperative collision, 17: load..substeps) */
   void* reserved[1];
 } myo_buffers;
 

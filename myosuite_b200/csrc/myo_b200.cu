@@ -210,7 +210,7 @@ extern "C" __global__ void __launch_bounds__(384) myo_env_kernel(const __grid_co
   const bool integrate = a.mode == 0 || (a.mode == 1 && a.n_substeps > 0);
   const bool prof = b.tap_phase_cycles != nullptr;
   for (int ebase = blockIdx.x*nw; ebase < a.n_env; ebase += gridDim.x*nw) {
-    const int env = ebase + wid; const bool live = env < a.n_env;
+    const int env = ebase + wid; const bool live = env < a.n_env; const long long tstep_ = prof ? clock64() : 0;
     if (live) {
       // ---- load state (coalesced: one env's row per warp)
       for (int i = w.lane; i < m.nq; i += 32) w.qpos[i] = b.qpos[(size_t)env*m.nq+i];
@@ -254,8 +254,9 @@ extern "C" __global__ void __launch_bounds__(384) myo_env_kernel(const __grid_co
     const int ngroups = a.cfg.reserved_i > 1 ? (a.cfg.reserved_i < nw ? a.cfg.reserved_i : nw) : 1;
     const int gsz = (nw + ngroups - 1)/ngroups, gid = wid / gsz, gw0 = gid*gsz, gnw = (gw0 + gsz <= nw ? gsz : nw - gw0), gthreads = gnw*32;
     const int bmask = a.cfg.barrier_mode == 0 ? 0xFF : (a.cfg.barrier_mode == 1 ? 0x01 : (a.cfg.barrier_mode == 2 ? 0 : a.cfg.barrier_mode));
-    long long cyc[16] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}; int maxcon_seen = 0, maxefc_seen = 0;
-    #define PH(k, stmt) { if (bmask & (1 << k)) group_sync(ngroups, gid, gthreads); long long t0_ = prof ? clock64() : 0; if (live) { stmt; } if (prof) cyc[k] += clock64() - t0_; }
+    const bool waitprof = a.cfg.reserved[0] != 0.0;   // profiling: record the barrier wait BEFORE each phase instead of the phase's own cycles
+    long long cyc[20] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}; int maxcon_seen = 0, maxefc_seen = 0;
+    #define PH(k, stmt) { long long tb_ = prof ? clock64() : 0; if (bmask & (1 << k)) group_sync(ngroups, gid, gthreads); long long t0_ = prof ? clock64() : 0; if (live) { stmt; } if (prof) cyc[k] += waitprof ? t0_ - tb_ : clock64() - t0_; }
     #pragma unroll 1
     for (int s = 0; s < nsub; s++) {
       const bool tap = s == nsub-1;
@@ -265,9 +266,11 @@ extern "C" __global__ void __launch_bounds__(384) myo_env_kernel(const __grid_co
       PH(3, phase_body_inertia(m, w); phase_crb(m, w); phase_bias(m, w));
       PH(4, phase_collision(m, w));
       if (m.npair > m.npair_an) {   // CTA-cooperative pass over the expensive candidates of all envs of this CTA
+        long long tc_ = prof ? clock64() : 0;
         if (w.lane == 0) s_ncand[wid] = live ? w.ncand : 0;
         group_sync(ngroups, gid, gthreads); collision_coop(m, w, warp0, s_ncand, gw0, gnw); group_sync(ngroups, gid, gthreads);
-        if (live) collision_merge(m, w); }
+        if (live) collision_merge(m, w);
+        if (prof) cyc[16] += clock64() - tc_; }
       PH(5, phase_constraints(m, w); if (tap) write_taps_contacts(m, w, a, env));
       PH(6, phase_solve(m, w, a.tol, prof ? cyc : nullptr));
       PH(7, if (tap) write_taps_solve(m, w, a, env); if (integrate) phase_integrate(m, w));
@@ -275,7 +278,7 @@ extern "C" __global__ void __launch_bounds__(384) myo_env_kernel(const __grid_co
       if (w.nefc > maxefc_seen) maxefc_seen = w.nefc;
     }
     #undef PH
-    if (prof && live && w.lane == 0) { long long* pc = b.tap_phase_cycles + 16*(size_t)env; for (int k = 0; k < 16; k++) pc[k] = cyc[k]; pc[12] = maxcon_seen; pc[13] = maxefc_seen; }
+    if (prof && live && w.lane == 0) { long long* pc = b.tap_phase_cycles + 20*(size_t)env; for (int k = 0; k < 20; k++) pc[k] = cyc[k]; pc[12] = maxcon_seen; pc[13] = maxefc_seen; pc[17] = clock64() - tstep_; }
     if (live) {
       if (a.mode == 1) { if (integrate && w.lane == 0 && b.time) b.time[env] += nsub*m.timestep; }
       else if (a.mode == 0) {

@@ -438,7 +438,8 @@ __device__ __forceinline__ void geom_mat(const DevModel& m, const Warp& w, int g
 // Here: Newton on the unit sphere for that maximisation (smooth for ellipsoids and points).
 // body 1: ellipsoid (R1, s1) or a point (s1 == nullptr); body 2: ellipsoid.  dl = c2 - c1.  d: in = start, out = maximiser.
 // p1, p2: support offsets (witness on body 1 = c1 + p1, on body 2 = c2 - p2).
-__device__ __forceinline__ double ell_sd(const double* dl, const double* R1, const double* s1, const double* R2, const double* s2, double* d, double* p1, double* p2) {
+// bound: every iterate's f is a lower bound of the signed distance -> return as soon as f > bound (the pair cannot be in contact).
+__device__ __forceinline__ double ell_sd(const double* dl, const double* R1, const double* s1, const double* R2, const double* s2, double* d, double* p1, double* p2, double bound) {
   double f = 0;
   #pragma unroll 1
   for (int it = 0; it < 40; it++) {
@@ -448,6 +449,7 @@ __device__ __forceinline__ double ell_sd(const double* dl, const double* R1, con
     matT_vec(a, R2, d); u[0] = s2[0]*s2[0]*a[0]; u[1] = s2[1]*s2[1]*a[1]; u[2] = s2[2]*s2[2]*a[2]; n2 = sqrt(dot3(a, u)); mat_vec(p2, R2, u); { double q = 1.0/n2; p2[0]*=q; p2[1]*=q; p2[2]*=q; }
     double g[3] = {dl[0]-p1[0]-p2[0], dl[1]-p1[1]-p2[1], dl[2]-p1[2]-p2[2]};
     f = dot3(d, dl) - n1 - n2;
+    if (f > bound) return f;
     // tangent basis
     double e[3] = {0,0,0}; { int k = fabs(d[0]) < fabs(d[1]) ? (fabs(d[0]) < fabs(d[2]) ? 0 : 2) : (fabs(d[1]) < fabs(d[2]) ? 1 : 2); e[k] = 1; }
     double t1[3], t2[3]; cross3(t1, d, e); { double q = 1.0/sqrt(dot3(t1,t1)); t1[0]*=q; t1[1]*=q; t1[2]*=q; } cross3(t2, d, t1);
@@ -548,24 +550,42 @@ __device__ __forceinline__ void collide_ellipsoid(const DevModel& m, const Warp&
   const double* s1 = geom_size(m, w, g1); const double* s2 = geom_size(m, w, g2); (void)G;
   double x1[3], a1[3], x2[3], a2[3]; geom_pose(m, w, g1, x1, a1); geom_pose(m, w, g2, x2, a2);
   if (ct == CT_CAP_ELL) {     // g1 capsule (segment + radius), g2 ellipsoid: min over the segment of the point-ellipsoid distance
-    double r = s1[0], h = s1[1], dv[3] = {x2[0]-x1[0], x2[1]-x1[1], x2[2]-x1[2]}, rb = fmax(s2[0], fmax(s2[1], s2[2]));
-    double d[3], p1[3], p2[3], t = clipd(dot3(dv, a1), -h, h), dl[3];
-    { double q[3] = {dv[0]-a1[0]*t, dv[1]-a1[1]*t, dv[2]-a1[2]*t}; if (sqrt(dot3(q,q)) - r - rb > margin) return; }
+    double r = s1[0], h = s1[1], dv[3] = {x2[0]-x1[0], x2[1]-x1[1], x2[2]-x1[2]};
     double R2[9]; geom_mat(m, w, g2, R2);
-    { double q[3] = {dv[0]-a1[0]*t, dv[1]-a1[1]*t, dv[2]-a1[2]*t}, n = sqrt(dot3(q,q)); if (n < MYO_MINVAL) { d[0]=a1[1]; d[1]=a1[2]; d[2]=a1[0]; } else { d[0]=q[0]/n; d[1]=q[1]/n; d[2]=q[2]/n; } }
-    double lo = -h, hi = h, tl = 0, gl = 0, sd = 0; bool have = false;
+    // (1) distance to the capsule's whole AXIS LINE = distance, in the plane normal to the axis, from the projected centre to the
+    //     ellipsoid's shadow (an ellipse): a 1-D Newton on the unit circle  max_u  c.u - sqrt(u'Au).  Every iterate's value is a
+    //     lower bound of the segment distance, so a pair that is provably out of its margin leaves at once.
+    double e1[3], e2[3]; { double e[3] = {0,0,0}; int k = fabs(a1[0]) < fabs(a1[1]) ? (fabs(a1[0]) < fabs(a1[2]) ? 0 : 2) : (fabs(a1[1]) < fabs(a1[2]) ? 1 : 2); e[k] = 1;
+      cross3(e1, a1, e); double q = 1.0/sqrt(dot3(e1,e1)); e1[0]*=q; e1[1]*=q; e1[2]*=q; cross3(e2, a1, e1); }
+    double b1[3], b2[3]; matT_vec(b1, R2, e1); matT_vec(b2, R2, e2);
+    double v0 = s2[0]*s2[0], v1 = s2[1]*s2[1], v2 = s2[2]*s2[2];
+    double A11 = v0*b1[0]*b1[0]+v1*b1[1]*b1[1]+v2*b1[2]*b1[2], A12 = v0*b1[0]*b2[0]+v1*b1[1]*b2[1]+v2*b1[2]*b2[2], A22 = v0*b2[0]*b2[0]+v1*b2[1]*b2[1]+v2*b2[2]*b2[2];
+    double c1 = dot3(e1, dv), c2 = dot3(e2, dv), cn = sqrt(c1*c1+c2*c2), u1 = 1, u2 = 0, F = 0, scale = cn + sqrt(fmax(A11, A22));
+    if (cn > MYO_MINVAL) { u1 = c1/cn; u2 = c2/cn; }
     #pragma unroll 1
     for (int it = 0; it < 40; it++) {
-      dl[0] = dv[0]-a1[0]*t; dl[1] = dv[1]-a1[1]*t; dl[2] = dv[2]-a1[2]*t;
-      sd = ell_sd(dl, nullptr, nullptr, R2, s2, d, p1, p2);
-      double g = -dot3(d, a1);                      // d(phi)/dt, monotone increasing in t
-      if (fabs(g) < 1e-11 || (t >= h && g <= 0) || (t <= -h && g >= 0)) break;
-      double tn;
-      if (g > 0) hi = t; else lo = t;
-      if (have && g != gl) tn = t - g*(t-tl)/(g-gl); else tn = g > 0 ? (it == 0 ? -h : 0.5*(lo+hi)) : (it == 0 ? h : 0.5*(lo+hi));
-      if (!(tn > lo && tn < hi)) tn = (it < 2) ? (g > 0 ? lo : hi) : 0.5*(lo+hi);
-      if (hi - lo < 1e-13*(h + 1e-3) || fabs(tn - t) < 1e-14*(h + 1e-3)) { t = tn; break; }
-      tl = t; gl = g; have = true; t = tn; }
+      double Au1 = A11*u1+A12*u2, Au2 = A12*u1+A22*u2, n2 = u1*Au1+u2*Au2, n = sqrt(n2), in = 1.0/n;
+      F = c1*u1+c2*u2 - n;
+      if (F - r > margin) return;
+      double p1_ = -u2, p2_ = u1;                                  // u_perp
+      double uAp = p1_*Au1+p2_*Au2, pAp = A11*p1_*p1_+2*A12*p1_*p2_+A22*p2_*p2_;
+      double g = c1*p1_+c2*p2_ - uAp*in, H = -(c1*u1+c2*u2) - ((pAp-n2)*in - uAp*uAp*in*in*in);
+      if (fabs(g) < 1e-12*scale) break;
+      double dx = H < 0 ? -g/H : g/(fabs(H)+1e-12); if (fabs(dx) > 0.5) dx = dx > 0 ? 0.5 : -0.5;
+      bool last = fabs(dx) < 1e-12;
+      #pragma unroll 1
+      for (int bt = 0; bt < 12; bt++) { double w1 = u1+dx*p1_, w2 = u2+dx*p2_, q = 1.0/sqrt(w1*w1+w2*w2); w1 *= q; w2 *= q;
+        double fn = c1*w1+c2*w2 - sqrt(A11*w1*w1+2*A12*w1*w2+A22*w2*w2);
+        if (fn >= F - 1e-14*scale || bt == 11) { u1 = w1; u2 = w2; break; }
+        dx *= 0.5; }
+      if (last) break; }
+    double d[3] = {u1*e1[0]+u2*e2[0], u1*e1[1]+u2*e2[1], u1*e1[2]+u2*e2[2]}, p1[3], p2[3], t, sd;
+    { double a[3], u[3]; matT_vec(a, R2, d); u[0] = v0*a[0]; u[1] = v1*a[1]; u[2] = v2*a[2]; double nn = sqrt(dot3(a, u)); mat_vec(p2, R2, u); double q = 1.0/nn; p2[0]*=q; p2[1]*=q; p2[2]*=q; }
+    t = (dv[0]-p2[0])*a1[0] + (dv[1]-p2[1])*a1[1] + (dv[2]-p2[2])*a1[2];        // axis coordinate of the ellipsoid-side witness
+    if (t >= -h && t <= h) sd = F;
+    else {   // (2) the line's closest point is beyond a cap: the distance over the segment (convex in t) is attained at that end point
+      t = t > h ? h : -h; double dl[3] = {dv[0]-a1[0]*t, dv[1]-a1[1]*t, dv[2]-a1[2]*t};
+      sd = ell_sd(dl, nullptr, nullptr, R2, s2, d, p1, p2, margin + r); }
     double dist = sd - r;
     if (dist <= margin) { o.n = 1; o.dist[0] = dist; for (int k = 0; k < 3; k++) { o.nrm[0][k] = d[k];
         double wa = x1[k]+a1[k]*t + d[k]*r, wb = x2[k]-p2[k]; o.pos[0][k] = 0.5*(wa+wb); } }
@@ -574,7 +594,7 @@ __device__ __forceinline__ void collide_ellipsoid(const DevModel& m, const Warp&
     if (cd - fmax(s1[0], fmax(s1[1], s1[2])) - fmax(s2[0], fmax(s2[1], s2[2])) > margin) return;
     double R1[9], R2[9], d[3], p1[3], p2[3]; geom_mat(m, w, g1, R1); geom_mat(m, w, g2, R2);
     if (cd < MYO_MINVAL) { d[0]=1; d[1]=0; d[2]=0; } else { d[0]=dl[0]/cd; d[1]=dl[1]/cd; d[2]=dl[2]/cd; }
-    double dist = ell_sd(dl, R1, s1, R2, s2, d, p1, p2);
+    double dist = ell_sd(dl, R1, s1, R2, s2, d, p1, p2, margin);
     if (dist <= margin) { o.n = 1; o.dist[0] = dist; for (int k = 0; k < 3; k++) { o.nrm[0][k] = d[k]; o.pos[0][k] = 0.5*((x1[k]+p1[k]) + (x2[k]-p2[k])); } }
   }
 }

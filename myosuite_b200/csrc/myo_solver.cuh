@@ -137,23 +137,25 @@ __device__ void chol_solve(const double* H, int n, double* x, int lane) {
 // exchanged with warp shuffles (no shared-memory latency, no barriers).  H: dense n x n in shared memory (read only); x: rhs in / solution out.
 template <int NMAX>
 __device__ __forceinline__ void chol_reg(const double* H, int n, double* x, int lane) {
-  double r[NMAX], c[NMAX];      // r: row `lane` of L (lower part);  c: column `lane` of L, captured from the shuffles (= row of L')
+  // The matrix is padded with an identity block up to NMAX so that every shuffle below sits in straight-line, branch-free code
+  // (a shuffle under an `if (k < n)` makes the compiler wrap each one in a WARPSYNC/ENDCOLLECTIVE sequence: 6x the instructions).
+  double r[NMAX], c[NMAX];      // r: row `lane` of L (lower part; the upper part holds unread garbage);  c: column `lane` of L, captured from the shuffles
   #pragma unroll
-  for (int j = 0; j < NMAX; j++) { r[j] = (lane < n && j <= lane) ? H[TRI(lane, j)] : 0.0; c[j] = 0.0; }
+  for (int j = 0; j < NMAX; j++) { r[j] = (lane < n && j <= lane) ? H[TRI(lane, j)] : ((j == lane && lane >= n) ? 1.0 : 0.0); c[j] = 0.0; }
   double b = lane < n ? x[lane] : 0.0, dinv = 1.0;
   #pragma unroll
-  for (int k = 0; k < NMAX; k++) { if (k < n) {
+  for (int k = 0; k < NMAX; k++) {
     double inv = rsqrt(fmax(__shfl_sync(FULL, r[k], k), MYO_MINVAL));      // 1/sqrt(pivot)
     if (lane == k) dinv = inv;
     r[k] *= inv;                                   // lanes > k: L[i][k]; lane k: sqrt(pivot) (unused below); lanes < k: 0
     #pragma unroll
-    for (int j = k+1; j < NMAX; j++) { double ljk = __shfl_sync(FULL, r[k], j); if (lane == k) c[j] = ljk; if (lane >= j) r[j] -= r[k]*ljk; } } }
+    for (int j = k+1; j < NMAX; j++) { double ljk = __shfl_sync(FULL, r[k], j); if (lane == k) c[j] = ljk; r[j] = fma(-r[k], ljk, r[j]); } }
   // forward substitution  L y = b
   #pragma unroll
-  for (int k = 0; k < NMAX; k++) { if (k < n) { double yk = __shfl_sync(FULL, b*dinv, k); if (lane == k) b = yk; else if (lane > k) b -= r[k]*yk; } }
-  // backward substitution L' x = y: x_k is final once all j > k are eliminated; lane i < k holds L[k][i] in c[k]
+  for (int k = 0; k < NMAX; k++) { double yk = __shfl_sync(FULL, b*dinv, k); b = lane == k ? yk : (lane > k ? fma(-r[k], yk, b) : b); }
+  // backward substitution L' x = y: x_k is final once all j > k are eliminated; lane i < k holds L[k][i] in c[k]  (c[k] = 0 on lanes >= k)
   #pragma unroll
-  for (int k = NMAX-1; k >= 0; k--) { if (k < n) { double xk = __shfl_sync(FULL, b*dinv, k); if (lane == k) b = xk; else if (lane < k) b -= c[k]*xk; } }
+  for (int k = NMAX-1; k >= 0; k--) { double xk = __shfl_sync(FULL, b*dinv, k); b = lane == k ? xk : fma(-c[k], xk, b); }
   if (lane < n) x[lane] = b;
   __syncwarp();
 }

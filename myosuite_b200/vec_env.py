@@ -117,6 +117,7 @@ class MyoVecEnv:
         cfg.maxcon = int(kw.get("maxcon", 0))
         cfg.barrier_mode = int(kw.get("barrier_mode", 0))
         cfg.reserved_i = int(kw.get("lockstep_groups", 0))
+        cfg.reserved[0] = float(bool(kw.get("profile_waits", False)))
         cfg.reaf_dst = cfg.reaf_src = -1
         if self.muscle_condition == "reafferentation":   # base_v0.py:78-79,104-108
             cfg.reaf_dst, cfg.reaf_src = m.name2id("actuator", "EPL"), m.name2id("actuator", "EIP")
@@ -159,7 +160,7 @@ class MyoVecEnv:
             t.update(tap_qacc=z(n, m.nv), tap_actuator_force=z(n, m.nu), tap_ten_length=z(n, m.nu), tap_qfrc_smooth=z(n, m.nv),
                      tap_ncon=z(n, 4, dtype=torch.int32), tap_contact_pair=z(n, max(self.dims.maxcon, 1), dtype=torch.int32),
                      tap_contact_dist=z(n, max(self.dims.maxcon, 1)), tap_moment=z(n, max(self.dims.reserved[0], 1)), tap_qM=z(n, m.nM),
-                     tap_phase_cycles=z(n, 16, dtype=torch.int64))
+                     tap_phase_cycles=z(n, 20, dtype=torch.int64))
         self.t = t
         self.batch.bind(**t)
         self._h_action = None
