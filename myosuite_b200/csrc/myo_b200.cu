@@ -273,7 +273,7 @@ extern "C" __global__ void __launch_bounds__(384) myo_env_kernel(const __grid_co
         if (prof) cyc[16] += clock64() - tc_; }
       PH(5, phase_constraints(m, w); if (tap) write_taps_contacts(m, w, a, env));
       PH(6, phase_solve(m, w, a.tol, prof ? cyc : nullptr));
-      PH(7, if (tap) write_taps_solve(m, w, a, env); if (integrate) phase_integrate(m, w));
+      PH(7, if (tap) write_taps_solve(m, w, a, env); if (integrate) phase_integrate(m, w, prof ? cyc : nullptr));
       if (w.ncon > maxcon_seen) maxcon_seen = w.ncon;
       if (w.nefc > maxefc_seen) maxefc_seen = w.nefc;
     }
@@ -359,6 +359,7 @@ static void fill_devmodel(const myo_model* mm, const myo_task_cfg* cfg, DevModel
   d.kcand = d.npair - d.npair_an; { int room = al2(3*d.maxpath*mc) - al2((d.kcand+1)/2); if (d.kcand > 16 && 7*d.kcand > room) d.kcand = imax(16, room/7); }
   int candsz = al2((d.npair - d.npair_an + 1)/2) + al2(7*d.kcand);
   t = 0; d.s_conJ = t; d.s_clist = t; d.s_cres = t + al2((d.npair - d.npair_an + 1)/2); d.s_cidx = t; t += imax(al2(3*d.maxpath*mc), candsz); d.s_efD = t; t += al2(d.maxefc); d.s_efA = t; t += al2(d.maxefc); d.s_eqJ = t; t += al2(d.neq);
+  d.ngc = P[PD_NGC]; d.s_gpose = d.s_efD; if (t - d.s_efD < al2(6*d.ngc)) t = d.s_efD + al2(6*d.ngc);     // geom poses (collision only) alias the row arrays (written after it)
   d.s_icon = t; t += al2((3*mc + d.nlimrow + 4 + 1)/2); int sizeS3 = t;
   d.s_con = sizeS3; int sizeCon = al2(CON_STRIDE*mc);
   t = sizeS3; d.s_efR = t; t += al2(d.maxefc); d.s_efV = t; t += al2(d.maxefc); d.s_va = t; t += al2(d.nv); d.s_vg = t; t += al2(d.nv); d.s_vp = t; t += al2(d.nv);

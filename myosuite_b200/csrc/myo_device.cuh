@@ -40,7 +40,7 @@ struct DevModel {
   int32_t hoff[MYO_NSEC];                  // offset of each hot section (in shorts / doubles), -1 if not staged
   int32_t nq, nv, nu, na, nM, njnt;
   int32_t nbd, nlevel, nsp, nwe, nta, nnz, nlim, neq, npair, npair_an, maxpath, ndepth, eq_tree;
-  int32_t maxcon, maxefc, nlimrow, ovr_geom;          // ovr_geom: collision geom whose size comes from the per-env overrides (-1: none)
+  int32_t maxcon, maxefc, nlimrow, ovr_geom, ngc, s_gpose;          // ovr_geom: collision geom whose size comes from the per-env overrides (-1: none)
   double timestep, gx, gy, gz, meaninertia, tolerance;
   // per-warp shared-memory layout, in doubles.  Persistent part:
   int32_t o_qpos, o_qvel, o_act, o_ctrl, o_qws, o_dax, o_dan, o_qM, o_fsm, o_eprm, o_wz, nwz, o_scr, n_per_warp;
@@ -419,11 +419,16 @@ __device__ void phase_bias(const DevModel& m, Warp& w) {
 }
 
 // ------------------------------------------------------------------ phase 6: collision (analytic primitives)
+// world position and z axis of every collision geom, once per substep (each geom takes part in ~20 pairs)
+__device__ __forceinline__ void geom_pose_all(const DevModel& m, const Warp& w) {
+  double* GP = SCR(s_gpose);
+  for (int g = w.lane; g < m.ngc; g += 32) { int b = CI(PG_body)[g]; const double* gd = CD(PG_d) + g*PG_STRIDE; double* o = GP + 6*g;
+    if (b < 0) { o[0]=gd[0]; o[1]=gd[1]; o[2]=gd[2]; o[3]=gd[5]; o[4]=gd[8]; o[5]=gd[11]; }
+    else { const double* X = SCR(s_xmat) + 9*b; const double* xp = SCR(s_xpos) + 3*b; mat_vec(o, X, gd); o[0]+=xp[0]; o[1]+=xp[1]; o[2]+=xp[2];
+      double z[3] = {gd[5], gd[8], gd[11]}; mat_vec(o+3, X, z); } }
+  __syncwarp(); }
 __device__ __forceinline__ void geom_pose(const DevModel& m, const Warp& w, int g, double* pos, double* axis /* z column */) {
-  int b = CI(PG_body)[g]; const double* gd = CD(PG_d) + g*PG_STRIDE;
-  if (b < 0) { pos[0]=gd[0]; pos[1]=gd[1]; pos[2]=gd[2]; axis[0]=gd[5]; axis[1]=gd[8]; axis[2]=gd[11]; }
-  else { const double* X = SCR(s_xmat) + 9*b; const double* xp = SCR(s_xpos) + 3*b; mat_vec(pos, X, gd); pos[0]+=xp[0]; pos[1]+=xp[1]; pos[2]+=xp[2];
-    double z[3] = {gd[5], gd[8], gd[11]}; mat_vec(axis, X, z); } }
+  const double* o = SCR(s_gpose) + 6*g; pos[0]=o[0]; pos[1]=o[1]; pos[2]=o[2]; axis[0]=o[3]; axis[1]=o[4]; axis[2]=o[5]; }
 
 __device__ __forceinline__ const double* geom_size(const DevModel& m, const Warp& w, int g) { return g == m.ovr_geom ? w.eprm + 3 : CD(PG_d) + g*PG_STRIDE + 12; }
 // full world rotation of a collision geom (ellipsoids need it)
@@ -634,6 +639,7 @@ __device__ __forceinline__ void store_contact(const DevModel& m, Warp& w, double
 __device__ void phase_collision(const DevModel& m, Warp& w) {
   double* con = SCR(s_con); int* icon = (int*)SCR(s_icon);
   int ncon = 0; w.overflow = 0;
+  geom_pose_all(m, w);
   // analytic primitives: one pair per lane
   #pragma unroll 1
   for (int base = 0; base < m.npair_an; base += 32) { int p = base + w.lane; ConOut o; o.n = 0; o.has_y = false;

@@ -207,7 +207,7 @@ __device__ void phase_solve(const DevModel& m, Warp& w, double tol, long long* c
   Solv s = solv_views(m, w); int n = m.nv, nefc = w.nefc; w.niter = 0;
   if (nefc == 0) {   // unconstrained: qacc = M^-1 qfrc_smooth
     ldl_factor(m, w, w.qM, s.LD, s.Dinv);
-    for (int i = w.lane; i < n; i += 32) s.a[i] = w.fsm[i]; __syncwarp();
+    for (int i = w.lane; i < n; i += 32) { s.a[i] = w.fsm[i]; s.Ma[i] = w.fsm[i]; } __syncwarp();
     ldl_solve(m, w, s.LD, s.Dinv, s.a); return; }
   for (int i = w.lane; i < n; i += 32) s.a[i] = w.qws[i]; __syncwarp();
   mul_M(m, w, s.Ma, s.a); rows_apply(m, w, s, s.a, s.jar); __syncwarp();
@@ -277,19 +277,26 @@ __device__ void phase_solve(const DevModel& m, Warp& w, double tol, long long* c
       alpha = an; }
     if (alpha == 0) break;   // no descent possible: converged to round-off
     for (int i = w.lane; i < n; i += 32) { s.a[i] += alpha*s.p[i]; s.Ma[i] += alpha*s.Mp[i]; }
-    for (int r = w.lane; r < nefc; r += 32) s.jar[r] += alpha*s.jv[r];
-    __syncwarp(); w.niter = iter+1; LAP(11) }
+    // rows that switch between active and inactive along the step; with none the cost was exactly quadratic along p, the Newton
+    // step (alpha = 1) lands on its minimum and the gradient vanishes to round-off: converged without another gradient pass
+    bool flip = false;
+    for (int r = w.lane; r < nefc; r += 32) { double x0 = s.jar[r], x1 = x0 + alpha*s.jv[r]; s.jar[r] = x1; if (r >= m.neq && (x0 < 0) != (x1 < 0)) flip = true; }
+    __syncwarp(); w.niter = iter+1; LAP(11)
+    if (!__any_sync(FULL, flip)) break; }
   #undef LAP
 }
 
 // ------------------------------------------------------------------ semi-implicit Euler with implicit joint damping
-__device__ void phase_integrate(const DevModel& m, Warp& w) {
-  Solv s = solv_views(m, w); int n = m.nv; double h = m.timestep;
+__device__ void phase_integrate(const DevModel& m, Warp& w, long long* cyc) {
+  Solv s = solv_views(m, w); int n = m.nv; double h = m.timestep; long long tc = cyc ? clock64() : 0;
   // (M + h B) qacc' = M qacc  (= qfrc_smooth + qfrc_constraint at the solver optimum)
-  mul_M(m, w, s.g, s.a); __syncwarp();
+  for (int i = w.lane; i < n; i += 32) s.g[i] = s.Ma[i];     // M qacc, maintained by the solver
+  __syncwarp();
   { const idx_t* mi = CI(PM_i); const idx_t* mj = CI(PM_j); const double* dofp = CD(PDOF_d);
     for (int e = w.lane; e < m.nM; e += 32) { double v = w.qM[e]; if (mi[e] == mj[e]) v += h*dofp[2*mi[e]+1]; s.Hs[e] = v; } __syncwarp(); }
+  if (cyc) { long long t_ = clock64(); cyc[18] += t_ - tc; tc = t_; }
   ldl_factor(m, w, s.Hs, s.LD, s.Dinv); ldl_solve(m, w, s.LD, s.Dinv, s.g);
+  if (cyc) { long long t_ = clock64(); cyc[19] += t_ - tc; tc = t_; }
   for (int i = w.lane; i < n; i += 32) { w.qvel[i] += h*s.g[i]; w.qws[i] = s.a[i]; }
   __syncwarp();
   const idx_t* jtype = CI(jnt_type); const idx_t* jq = CI(jnt_qposadr); const idx_t* jd = CI(jnt_dofadr);
