@@ -399,12 +399,14 @@ extern "C" int myo_batch_create(const myo_model* m, int device, int n_env, const
   b->const_bytes = b->dm.nD*8 + ((b->dm.nI16w + 1)/2)*8;
   int per = b->dm.n_per_warp*8, maxs = (int)prop.sharedMemPerBlockOptin - b->const_bytes - 64;
   int wpc = maxs/per; if (wpc > 12) wpc = 12; if (wpc < 1) { delete b; return fail("model working set exceeds shared memory of one CTA"); }
+  const int wpc0 = wpc;
   if (n_env < wpc) wpc = n_env;
   { // wave quantisation: with one CTA per SM the batch takes ceil(n_env / (SMs * wpc)) rounds; among the warp counts that reach the
     // minimal number of rounds take the SMALLEST (same rounds, less issue contention and less lockstep imbalance per round)
     int sms = prop.multiProcessorCount, best = wpc, rounds = (n_env + sms*wpc - 1)/(sms*wpc);
     for (int q = wpc - 1; q >= 1; q--) if ((n_env + sms*q - 1)/(sms*q) == rounds) best = q;
     if (b->dm.n_per_warp*8*best + b->const_bytes > 100*1024) wpc = best; }   // (small models run several CTAs per SM instead)
+  if (const char* e = getenv("MYO_B200_WARPS_PER_CTA")) { int q = atoi(e); if (q >= 1 && q <= wpc0) wpc = q; }     // tuning override (never above what fits)
   b->warps_per_cta = wpc; b->smem_bytes = b->const_bytes + wpc*per;
   CUDA_OK(cudaFuncSetAttribute(myo_env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes));
   int ctas_per_sm = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, myo_env_kernel, wpc*32, b->smem_bytes); if (ctas_per_sm < 1) ctas_per_sm = 1;

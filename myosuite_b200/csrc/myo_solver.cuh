@@ -164,6 +164,12 @@ __device__ __noinline__ void chol_reg16(const double* H, int n, double* x, int l
 __device__ __noinline__ void chol_reg24(const double* H, int n, double* x, int lane) { chol_reg<24>(H, n, x, lane); }
 __device__ __noinline__ void chol_reg32(const double* H, int n, double* x, int lane) { chol_reg<32>(H, n, x, lane); }
 
+// x <- H^-1 x for a dense SPD H (packed lower triangle in shared memory); returns whether H survived (the n > 32 fallback factors in place)
+__device__ __forceinline__ bool chol_dense(double* H, int n, double* x, int lane) {
+  if (n <= 8) chol_reg8(H, n, x, lane); else if (n <= 16) chol_reg16(H, n, x, lane); else if (n <= 24) chol_reg24(H, n, x, lane);
+  else if (n <= 32) chol_reg32(H, n, x, lane); else { chol_factor(H, n, lane); chol_solve(H, n, x, lane); return false; }
+  return true; }
+
 __device__ __forceinline__ void load_M_dense(const DevModel& m, const Warp& w, double* H, double diag_scale /* h */) {
   int n = m.nv; for (int i = w.lane; i < n*(n+1)/2; i += 32) H[i] = 0; __syncwarp();
   const idx_t* mi = CI(PM_i); const idx_t* mj = CI(PM_j); const double* dofp = CD(PDOF_d);
@@ -259,8 +265,7 @@ __device__ void phase_solve(const DevModel& m, Warp& w, double tol, long long* c
           int di = path[q[3]+ei] >> 1, dj = path[q[3]+ej] >> 1; if (di >= dj) s.H[TRI(di,dj)] += wa0*b[0]+wa1*b[1]+wa2*b[2]; } }
       __syncwarp(); }
     LAP(9)
-    if (n <= 8) chol_reg8(s.H, n, s.p, w.lane); else if (n <= 16) chol_reg16(s.H, n, s.p, w.lane); else if (n <= 24) chol_reg24(s.H, n, s.p, w.lane);
-    else if (n <= 32) chol_reg32(s.H, n, s.p, w.lane); else { chol_factor(s.H, n, w.lane); chol_solve(s.H, n, s.p, w.lane); }
+    chol_dense(s.H, n, s.p, w.lane);
     LAP(10)
     }
     // exact line search along p
@@ -292,10 +297,16 @@ __device__ void phase_integrate(const DevModel& m, Warp& w, long long* cyc) {
   // (M + h B) qacc' = M qacc  (= qfrc_smooth + qfrc_constraint at the solver optimum)
   for (int i = w.lane; i < n; i += 32) s.g[i] = s.Ma[i];     // M qacc, maintained by the solver
   __syncwarp();
+  if (n <= 32) {     // small systems: the register Cholesky beats the level-scheduled sparse factorisation (long index-chasing chains)
+    load_M_dense(m, w, s.H, h);
+    if (cyc) { long long t_ = clock64(); cyc[18] += t_ - tc; tc = t_; }
+    chol_dense(s.H, n, s.g, w.lane);
+  } else {
   { const idx_t* mi = CI(PM_i); const idx_t* mj = CI(PM_j); const double* dofp = CD(PDOF_d);
     for (int e = w.lane; e < m.nM; e += 32) { double v = w.qM[e]; if (mi[e] == mj[e]) v += h*dofp[2*mi[e]+1]; s.Hs[e] = v; } __syncwarp(); }
   if (cyc) { long long t_ = clock64(); cyc[18] += t_ - tc; tc = t_; }
   ldl_factor(m, w, s.Hs, s.LD, s.Dinv); ldl_solve(m, w, s.LD, s.Dinv, s.g);
+  }
   if (cyc) { long long t_ = clock64(); cyc[19] += t_ - tc; tc = t_; }
   for (int i = w.lane; i < n; i += 32) { w.qvel[i] += h*s.g[i]; w.qws[i] = s.a[i]; }
   __syncwarp();
