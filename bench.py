@@ -27,7 +27,8 @@ DEFAULT_ENV = "myoHandPoseRandom-v0"       # BASELINE.json target config (config
 # algorithmic bytes per env-step (A_io): action f32 + state f64 in/out + obs f32 + reward/done
 A_IO = {"myoElbowPose1D6MRandom-v0": 24 + 2 * (8 * 8) + 36 + 5, "myoHandPoseRandom-v0": 156 + 2 * (85 * 8) + 432 + 5,
         "myoHandObjHoldRandom-v0": 156 + 2 * (98 * 8) + 364 + 5 + 36, "myoFatiLegWalk-v0": 320 + 2 * (149 * 8) + 2 * (240 * 8) + 1612 + 5,
-        "myoLegWalk-v0": 320 + 2 * (149 * 8) + 1612 + 5}
+        "myoLegWalk-v0": 320 + 2 * (149 * 8) + 1612 + 5,
+        "myoHandReachRandom-v0": 156 + 2 * (85 * 8) + 460 + 5 + 120}        # (+ 15 target coordinates f64)
 
 
 class ClockSampler:

@@ -34,7 +34,7 @@ extern "C" {
 typedef struct myo_model myo_model;
 typedef struct myo_batch myo_batch;
 
-enum { MYO_TASK_NONE = 0, MYO_TASK_POSE = 1, MYO_TASK_WALK = 2, MYO_TASK_HOLD = 3 };
+enum { MYO_TASK_NONE = 0, MYO_TASK_POSE = 1, MYO_TASK_WALK = 2, MYO_TASK_HOLD = 3, MYO_TASK_REACH = 4 };
 enum { MYO_COND_NONE = 0, MYO_COND_FATIGUE = 2 };   /* sarcopenia / reafferentation are host-side model edits */
 
 /* model dimensions (mirrors the mjModel sizes the reference reads: env.unwrapped.mj_model.{nq,nv,nu,na}) */
@@ -62,10 +62,10 @@ typedef struct {
   int32_t barrier_mode;      /* CTA phase barriers: 0 = before every phase (default), 1 = once per substep, 2 = none, >2 = bit mask of the 8 phases that start with a barrier (tuning knob) */
   int32_t reserved_i;        /* lockstep groups per CTA (tuning knob; 0/1 = the whole CTA is one group) */
   double pose_thd;           /* pose_v0.py:43 */
-  double weights[8];         /* reward weights in the task's own key order (pose_v0.py:18-23, walk_v0.py:205-211, obj_hold_v0.py:17-21) */
+  double weights[8];         /* reward weights in the task's own key order (pose_v0.py:18-23, walk_v0.py:205-211, obj_hold_v0.py:17-21; reach_v0.py:18-22 as reach, bonus, act_reg, penalty) */
   double solver_tolerance;   /* scaled-gradient stop of the Newton solver; 0 = library default (1e-10) */
-  int32_t task_i[16];        /* task-specific indices, filled by the host mirror (vec_env.py): WALK body/joint ids, HOLD object ids */
-  double task_d[24];         /* task-specific constants: WALK targets / thresholds / torso quaternion offset, HOLD object site */
+  int32_t task_i[16];        /* task-specific indices, filled by the host mirror (vec_env.py): WALK body/joint ids, HOLD object ids, REACH [ntip, tip body x ntip] */
+  double task_d[24];         /* task-specific constants: WALK targets / thresholds / torso quaternion offset, HOLD object site, REACH tip-site offsets [3 x ntip] then far_th */
   double reserved[2];        /* [0] != 0 with the phase-cycle tap bound: record the barrier wait before each phase instead of its work (profiling) */
 } myo_task_cfg;
 

@@ -14,7 +14,7 @@ _LIB = None
 
 c_i32, c_i64, c_u64, c_f64, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_double, ctypes.c_void_p
 
-TASK_NONE, TASK_POSE, TASK_WALK, TASK_HOLD = 0, 1, 2, 3
+TASK_NONE, TASK_POSE, TASK_WALK, TASK_HOLD, TASK_REACH = 0, 1, 2, 3, 4
 COND_NONE, COND_FATIGUE = 0, 2
 
 

@@ -66,6 +66,9 @@ __device__ void env_reset(const DevModel& m, Warp& w, const StepArgs& a, int env
       if (b.target && b.target_range) b.target[(size_t)env*m.nq+qa] = b.target_range[2*qa] + u0*(b.target_range[2*qa+1]-b.target_range[2*qa]);
       if (a.cfg.reset_random) w.qpos[qa] = jrange[2*j] + u1*(jrange[2*j+1]-jrange[2*j]); }
   }
+  if (a.cfg.task == MYO_TASK_REACH && b.target && b.target_range) {
+    // ReachEnvV0.generate_target_pose (reach_v0.py:163-170): every target site ~ U(span) per coordinate
+    for (int k = w.lane; k < 3*a.cfg.task_i[0]; k += 32) { double u = philox_uniform(rng); b.target[(size_t)env*m.nq+k] = b.target_range[2*k] + u*(b.target_range[2*k+1]-b.target_range[2*k]); } }
   if (a.cfg.task == MYO_TASK_HOLD && b.env_prm) {
     // ObjHoldRandomEnvV0.reset (obj_hold_v0.py:126-145): goal = object_init_pos + U(-3cm, 3cm)^3 ; object size ~ U(2cm, 3cm)^3
     // (Fixed variant, reset_random == 0: model values in task_d[6..11])
@@ -161,12 +164,30 @@ __device__ void hold_observe(const DevModel& m, Warp& w, const StepArgs& a, int 
   *done_out = drop;
 }
 
+// ReachEnvV0 obs / reward / done (reach_v0.py:98-160): needs kinematics of the post-step state in scratch.  tnow = mjData.time of that state
+__device__ void reach_observe(const DevModel& m, Warp& w, const StepArgs& a, int env, double tnow, double* rw_out, bool* done_out) {
+  const myo_buffers& b = a.b; const int* ti = a.cfg.task_i; const double* td = a.cfg.task_d; const int ntip = ti[0];
+  float* o = b.obs ? b.obs + (size_t)env*a.obs_dim : nullptr; double d2 = 0, a2 = 0; const int base = m.nq + m.nv;
+  if (w.lane < ntip) { int bd = ti[1+w.lane]; const double* lp = td + 3*w.lane; double tip[3] = {lp[0], lp[1], lp[2]};
+    if (bd >= 0) { const double* xp = SCR(s_xpos) + 3*bd; mat_vec(tip, SCR(s_xmat) + 9*bd, lp); tip[0]+=xp[0]; tip[1]+=xp[1]; tip[2]+=xp[2]; }
+    for (int c = 0; c < 3; c++) { double tgt = b.target ? b.target[(size_t)env*m.nq + 3*w.lane + c] : 0.0, err = tgt - tip[c]; d2 += err*err;
+      if (o) { o[base + 3*w.lane + c] = (float)tip[c]; o[base + 3*ntip + 3*w.lane + c] = (float)err; } } }
+  if (o) { for (int i = w.lane; i < m.nq; i += 32) o[i] = (float)w.qpos[i]; for (int i = w.lane; i < m.nv; i += 32) o[m.nq+i] = (float)(w.qvel[i]*a.dt); }
+  for (int i = w.lane; i < m.na; i += 32) { a2 += w.act[i]*w.act[i]; if (o) o[base + 6*ntip + i] = (float)w.act[i]; }      // base_v0.py:33-37 appends "act"
+  double dist = sqrt(warp_sum(d2)), am = sqrt(warp_sum(a2)); if (m.na) am /= m.na;
+  bool armed = tnow > 2*a.dt;                                   // far_th = inf for the first control steps (reach_v0.py:134-138)
+  double far_th = td[3*ntip]*ntip, near_th = ntip*0.0125; bool far = armed && dist > far_th;
+  *rw_out = a.cfg.weights[0]*(-dist) + a.cfg.weights[1]*((dist < 2*near_th ? 1.0 : 0.0) + (dist < near_th ? 1.0 : 0.0)) + a.cfg.weights[2]*(-am) + a.cfg.weights[3]*(far ? -1.0 : 0.0);
+  *done_out = far;
+}
+
 // obs / reward / done of the state held in shared memory, for any task (runs the extra forward stages the task needs)
-__device__ __noinline__ void task_observe(const DevModel& m, Warp& w, const StepArgs& a, int env, int steps, double* rw, bool* done) {
+__device__ __noinline__ void task_observe(const DevModel& m, Warp& w, const StepArgs& a, int env, int steps, double tnow, double* rw, bool* done) {
   *rw = 0; *done = false;
   if (a.cfg.task == MYO_TASK_POSE) pose_reward_done(m, w, a, env, rw, done);
   else if (a.cfg.task == MYO_TASK_WALK) { phase_kinematics(m, w); phase_tendon(m, w); phase_actuation(m, w, false, nullptr, nullptr); walk_observe(m, w, a, env, steps, rw, done); }
   else if (a.cfg.task == MYO_TASK_HOLD) { phase_kinematics(m, w); hold_observe(m, w, a, env, rw, done); }
+  else if (a.cfg.task == MYO_TASK_REACH) { phase_kinematics(m, w); reach_observe(m, w, a, env, tnow, rw, done); }
   __syncwarp();
 }
 
@@ -221,10 +242,10 @@ extern "C" __global__ void __launch_bounds__(384) myo_env_kernel(const __grid_co
       __syncwarp();
       if (a.mode == 2) {
         if (!a.reset_mask || a.reset_mask[env]) { env_reset(m, w, a, env);
-          { double rw_; bool dn_; task_observe(m, w, a, env, 0, &rw_, &dn_); }
+          { double rw_; bool dn_; task_observe(m, w, a, env, 0, 0.0, &rw_, &dn_); }
           if (w.lane == 0) { if (b.done) b.done[env] = 0; if (b.truncated) b.truncated[env] = 0; if (b.reward) b.reward[env] = 0; } }
       } else if (a.mode == 3) {   // observe: obs/reward/done of the current state, nothing advanced (env.forward(), env_base.py:393-432)
-        { double rw; bool done; task_observe(m, w, a, env, b.step_count ? b.step_count[env] : 0, &rw, &done);
+        { double rw; bool done; task_observe(m, w, a, env, b.step_count ? b.step_count[env] : 0, b.time ? b.time[env] : 0.0, &rw, &done);
           if (w.lane == 0) { if (b.reward) b.reward[env] = (float)rw; if (b.done) b.done[env] = done; } }
       } else if (a.mode == 1) {
         for (int i = w.lane; i < m.nu; i += 32) w.ctrl[i] = a.dbg_ctrl[(size_t)env*m.nu+i];
@@ -283,15 +304,17 @@ extern "C" __global__ void __launch_bounds__(384) myo_env_kernel(const __grid_co
       if (a.mode == 1) { if (integrate && w.lane == 0 && b.time) b.time[env] += nsub*m.timestep; }
       else if (a.mode == 0) {
         // ---- obs / reward / done / TimeLimit / auto-reset
-        if (a.cfg.task != MYO_TASK_NONE) { double rw; bool done; task_observe(m, w, a, env, b.step_count ? b.step_count[env] : 0, &rw, &done);
+        // mjData.time advances by one timestep per substep (the accumulated rounding is visible to ReachEnvV0's `time > 2 dt` test)
+        double tnow = b.time ? b.time[env] : 0.0; for (int s_ = 0; s_ < a.cfg.frame_skip; s_++) tnow += m.timestep;
+        if (a.cfg.task != MYO_TASK_NONE) { double rw; bool done; task_observe(m, w, a, env, b.step_count ? b.step_count[env] : 0, tnow, &rw, &done);
           int sc = b.step_count ? b.step_count[env]+1 : 0; bool trunc = a.cfg.max_episode_steps > 0 && sc >= a.cfg.max_episode_steps;
           __syncwarp();
           if (w.lane == 0) { if (b.reward) b.reward[env] = (float)rw; if (b.done) b.done[env] = done; if (b.truncated) b.truncated[env] = trunc && !done;
-            if (b.step_count) b.step_count[env] = sc; if (b.time) b.time[env] += a.cfg.frame_skip*m.timestep;
+            if (b.step_count) b.step_count[env] = sc; if (b.time) b.time[env] = tnow;
             if (b.ep_return) { float R = b.ep_return[env] + (float)rw; b.ep_return[env] = R; if ((done || trunc) && b.last_return) b.last_return[env] = R; } }
           __syncwarp();
-          if ((done || trunc) && a.cfg.auto_reset) { env_reset(m, w, a, env); double rw2; bool dn2; task_observe(m, w, a, env, 0, &rw2, &dn2); }
-        } else if (w.lane == 0 && b.time) b.time[env] += a.cfg.frame_skip*m.timestep;
+          if ((done || trunc) && a.cfg.auto_reset) { env_reset(m, w, a, env); double rw2; bool dn2; task_observe(m, w, a, env, 0, 0.0, &rw2, &dn2); }
+        } else if (w.lane == 0 && b.time) b.time[env] = tnow;
       }
       __syncwarp();
       // ---- store state
@@ -390,6 +413,8 @@ extern "C" int myo_batch_create(const myo_model* m, int device, int n_env, const
   if (cfg->task == MYO_TASK_POSE) b->obs_dim = 2*b->dm.nq + b->dm.nv + b->dm.na;
   else if (cfg->task == MYO_TASK_WALK) b->obs_dim = (b->dm.nq - 2) + b->dm.nv + 16 + 4*b->dm.nu;
   else if (cfg->task == MYO_TASK_HOLD) b->obs_dim = (b->dm.nq - 7) + (b->dm.nv - 6) + 6 + b->dm.na;
+  else if (cfg->task == MYO_TASK_REACH) { if (cfg->task_i[0] < 1 || cfg->task_i[0] > 7 || 3*cfg->task_i[0] > b->dm.nq) { delete b; return fail("reach task: 1..7 tips and 3*ntip <= nq"); }
+    b->obs_dim = b->dm.nq + b->dm.nv + 6*cfg->task_i[0] + b->dm.na; }
   { const int32_t* I = m->I.data(); const double* D = m->D.data();
     size_t nI = (size_t)b->dm.nI16w*4, nD = (size_t)b->dm.nD*8;
     CUDA_OK(cudaMalloc(&b->dI, nI ? nI : 16)); CUDA_OK(cudaMalloc(&b->dD, nD ? nD : 16));

@@ -69,9 +69,9 @@ class MyoVecEnv:
         kw.update(overrides)
         self.kwargs = kw
         self.task = ("none" if entry is None else "pose" if entry.endswith("pose_v0:PoseEnvV0") else "walk" if entry.endswith("walk_v0:WalkEnvV0")
-                     else "hold" if "obj_hold_v0:ObjHold" in entry else None)
+                     else "hold" if "obj_hold_v0:ObjHold" in entry else "reach" if entry.endswith("reach_v0:ReachEnvV0") else None)
         if self.task is None:
-            raise NotImplementedError("device task for %s (%s) is not built yet (pose, walk, hold are; MyoVecEnv.from_model gives physics only)" % (env_id, entry))
+            raise NotImplementedError("device task for %s (%s) is not built yet (pose, walk, hold, reach are; MyoVecEnv.from_model gives physics only)" % (env_id, entry))
         self.hold_random = entry is not None and entry.endswith("ObjHoldRandomEnvV0")
         self.mj_model = m = model if model is not None else assets.load(_MODEL_OF_XML[kw["model_path"]])
         self.muscle_condition = kw.get("muscle_condition", "")
@@ -87,7 +87,7 @@ class MyoVecEnv:
         self.I, self.D = blob.pack(m, prog)
         self.dev_model = abi.DeviceModel(self.I, self.D)
         cfg = abi.MyoTaskCfg()
-        cfg.task = {"none": abi.TASK_NONE, "pose": abi.TASK_POSE, "walk": abi.TASK_WALK, "hold": abi.TASK_HOLD}[self.task]
+        cfg.task = {"none": abi.TASK_NONE, "pose": abi.TASK_POSE, "walk": abi.TASK_WALK, "hold": abi.TASK_HOLD, "reach": abi.TASK_REACH}[self.task]
         cfg.frame_skip = self.n_frames
         cfg.max_episode_steps = int(self.max_episode_steps or 0)
         cfg.normalize_act = int(bool(kw.get("normalize_act", True)))
@@ -113,6 +113,10 @@ class MyoVecEnv:
                 cfg.weights[i] = w[k]
             init_qpos[:-7] = 0.0; init_qpos[0] = -1.5                                                  # obj_hold_v0.py:61-62
             cfg.reset_random = int(self.hold_random)
+        elif self.task == "reach":
+            w = kw.get("weighted_reward_keys", {"reach": 1.0, "bonus": 4.0, "penalty": 50})                 # reach_v0.py:18-22
+            for i, k in enumerate(("reach", "bonus", "act_reg", "penalty")):
+                cfg.weights[i] = w.get(k, 0.0)
         cfg.solver_tolerance = float(kw.get("solver_tolerance", 0.0))
         cfg.maxcon = int(kw.get("maxcon", 0))
         cfg.barrier_mode = int(kw.get("barrier_mode", 0))
@@ -123,6 +127,8 @@ class MyoVecEnv:
             cfg.reaf_dst, cfg.reaf_src = m.name2id("actuator", "EPL"), m.name2id("actuator", "EIP")
         if self.task == "hold":
             self._setup_hold(m, cfg)
+        if self.task == "reach":
+            self._setup_reach(m, kw, cfg)
         self.cfg = cfg
         self.device_index = int(device)
         self.device = torch.device("cuda", self.device_index)
@@ -146,6 +152,9 @@ class MyoVecEnv:
         elif kw.get("target_jnt_value") is not None:
             v = np.asarray(kw["target_jnt_value"], dtype=np.float64)
             tr[:, 0] = tr[:, 1] = v
+        elif self.task == "reach":       # rows 3k..3k+2: span of target site k (reach_v0.py:163-170); `target` rows hold the sampled site positions
+            for k, span in enumerate(kw["target_reach_range"].values()):
+                tr[3 * k:3 * k + 3, 0], tr[3 * k:3 * k + 3, 1] = span[0], span[1]
         t["target_range"] = torch.as_tensor(tr, device=dv).contiguous()
         t["init_qpos"] = torch.as_tensor(init_qpos, device=dv).contiguous()
         t["init_qvel"] = torch.as_tensor(init_qvel, device=dv).contiguous()
@@ -187,6 +196,24 @@ class MyoVecEnv:
             list(target_rot) + [float(np.sum(m.body_mass))]
         for i, v in enumerate(td):
             cfg.task_d[i] = float(v)
+
+    def _setup_reach(self, m, kw, cfg):
+        """ReachEnvV0 constants (reach_v0.py:52-67): tip sites (body + offset), world-fixed target sites, far_th."""
+        tips = list(kw["target_reach_range"].keys())
+        if 3 * len(tips) > m.nq or len(tips) > 7:
+            raise NotImplementedError("reach task: at most 7 tips and 3*ntip <= nq")
+        cfg.task_i[0] = len(tips)
+        dyn = self.prog_info["dyn_body_ids"]
+        for k, name in enumerate(tips):
+            sid, tid = m.name2id("site", name), m.name2id("site", name + "_target")
+            if int(m.site_bodyid[tid]) != 0:
+                raise NotImplementedError("reach targets must be world-fixed sites")
+            b = int(m.site_bodyid[sid])
+            cfg.task_i[1 + k] = dyn.index(b) if b in dyn else -1
+            for c in range(3):
+                cfg.task_d[3 * k + c] = float(m.site_pos[sid][c])
+        cfg.task_d[3 * len(tips)] = float(kw.get("far_th", 0.35))
+        self.tip_names = tips
 
     def _setup_hold(self, m, cfg):
         """ObjHold constants (obj_hold_v0.py:46-62,126-145)."""

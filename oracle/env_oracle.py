@@ -119,3 +119,21 @@ def hold_obs_reward(m, o, dt, goal_pos):
     drop = bool(d > 0.300)
     dense = 100.0 * (-d) + 4.0 * (1.0 * (d < 0.020) + 1.0 * (d < 0.010)) + 10 * (-1.0 * drop)
     return obs, dict(goal_dist=-d, done=drop, dense=dense)
+
+
+def reach_obs_reward(m, o, dt, tips, targets, time, far_th=0.35, weights=None):
+    """reach_v0.py:98-160: obs = [qpos, qvel*dt, tip_pos, target - tip_pos, act] (f32); reach / bonus / penalty terms.
+    tips: site names; targets: [ntip, 3] world positions of the target sites; time: mjData.time of the observed state."""
+    weights = weights or {"reach": 1.0, "bonus": 4.0, "penalty": 50}
+    qpos, qvel, act = o.f("qpos"), o.f("qvel"), o.f("act")
+    sx = o.f("site_xpos").reshape(-1, 3)
+    tip = np.concatenate([sx[m.name2id("site", t)] for t in tips])
+    err = np.asarray(targets, dtype=np.float64).ravel() - tip
+    obs = np.concatenate([qpos, qvel * dt, tip, err, act]).astype(np.float32)
+    d = np.linalg.norm(err)
+    act_mag = np.linalg.norm(act) / m.na if m.na else 0.0
+    far = far_th * len(tips) if time > 2 * dt else np.inf
+    near = len(tips) * 0.0125
+    terms = dict(reach=-d, bonus=1.0 * (d < 2 * near) + 1.0 * (d < near), act_reg=-act_mag, penalty=-1.0 * (d > far))
+    dense = sum(wt * terms[k] for k, wt in weights.items())
+    return obs, dict(reach=-d, done=bool(d > far), solved=bool(d < near), dense=dense)

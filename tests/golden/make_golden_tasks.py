@@ -1,5 +1,5 @@
-"""Golden vectors for the Walk / ObjHold task logic, produced by RUNNING THE REFERENCE'S OWN CLASSES
-(WalkEnvV0 / ObjHoldFixedEnvV0 get_obs_dict, get_reward_dict and helpers, unmodified, created with __new__ so that no
+"""Golden vectors for the Walk / ObjHold / Reach task logic, produced by RUNNING THE REFERENCE'S OWN CLASSES
+(WalkEnvV0 / ObjHoldFixedEnvV0 / ReachEnvV0 get_obs_dict, get_reward_dict and helpers, unmodified, created with __new__ so that no
 simulator is constructed) on mj_data-like records filled from this repo's CPU oracle.  Output: tests/golden/tasks.npz
 Run here (needs /root/reference and oracle/libmyo_oracle.so):  python tests/golden/make_golden_tasks.py
 """
@@ -16,6 +16,7 @@ import _ref_stubs  # noqa: E402
 
 _ref_stubs.install()
 from myosuite.envs.myo.myobase.obj_hold_v0 import ObjHoldFixedEnvV0  # noqa: E402
+from myosuite.envs.myo.myobase.reach_v0 import ReachEnvV0  # noqa: E402
 from myosuite.envs.myo.myobase.walk_v0 import WalkEnvV0  # noqa: E402
 from myosuite.envs.obs_vec_dict import ObsVecDict  # noqa: E402
 
@@ -97,5 +98,43 @@ for i in range(N):
 for k, v in H.items():
     out["hold_" + k] = np.array(v)
 assert out["hold_obs"].shape == (N, 91) and out["hold_done"].sum() >= 1
+
+# ---- Reach (myoHandReachRandom-v0: hand model, five finger tips; registry kwargs from the reference's own registration)
+import json  # noqa: E402
+reg = json.load(open(os.path.join(ROOT, "myosuite_b200", "assets", "registry.json")))["envs"]["myoHandReachRandom-v0"]["kwargs"]
+m = assets.load("myohand_pose")
+o = Oracle(*blob.pack(m))
+tips = list(reg["target_reach_range"].keys())
+N = 20
+R = dict(qpos=[], qvel=[], act=[], targets=[], time=[], obs=[], dense=[], done=[], solved=[])
+for i in range(N):
+    o.reset()
+    o.set(qpos=rng.uniform(m.jnt_range[:, 0], m.jnt_range[:, 1]) * (0.15 if i < 8 else 1.0), qvel=rng.normal(0, 0.5, m.nv), act=rng.uniform(0, 1, m.na)); o.forward()
+    env = ReachEnvV0.__new__(ReachEnvV0)
+    env.mj_model, env.mj_data, env.frame_skip, env.far_th = fake_model(m), fake_data(o, m.nbody), 10, reg["far_th"]       # dt = 0.02
+    env.tip_sids = [m.name2id("site", t) for t in tips]; env.target_sids = [m.name2id("site", t + "_target") for t in tips]
+    sx = env.mj_data.site_xpos
+    if i < 4:            # targets on / next to the tips: the bonus and solved branches
+        tg = np.array([sx[sid] for sid in env.tip_sids]) + rng.normal(0, 0.004 if i < 2 else 0.012, (len(tips), 3))
+    else:
+        tg = np.array([rng.uniform(reg["target_reach_range"][t][0], reg["target_reach_range"][t][1]) for t in tips])
+    for k, sid in enumerate(env.target_sids):
+        sx[sid] = tg[k]
+    # mjData.time as MuJoCo accumulates it (one addition per substep): steps 1, 2, 3 sit around the `time > 2 dt` switch of far_th
+    nstep = [1, 2, 3, 7][i % 4]; tm = 0.0
+    for _ in range(10 * nstep):
+        tm += m.opt_timestep
+    env.mj_data.time = tm
+    env.rwd_keys_wt = ReachEnvV0.DEFAULT_RWD_KEYS_AND_WEIGHTS
+    od = env.get_obs_dict(env.mj_model, env.mj_data)
+    env.obs_dict = od
+    t, vec = ObsVecDict().obsdict2obsvec(od, ReachEnvV0.DEFAULT_OBS_KEYS + ["act"])                      # base_v0.py:33-37 appends "act"
+    rd = env.get_reward_dict(od)
+    R["qpos"].append(o.f("qpos").copy()); R["qvel"].append(o.f("qvel").copy()); R["act"].append(o.f("act").copy()); R["targets"].append(tg); R["time"].append(tm); R["obs"].append(vec)
+    for k in ("dense", "done", "solved"):
+        R[k].append(float(np.asarray(rd[k]).ravel()[0]))
+for k, v in R.items():
+    out["reach_" + k] = np.array(v)
+assert out["reach_obs"].shape == (N, 115) and out["reach_done"].sum() >= 2 and out["reach_solved"].sum() >= 1 and (out["reach_done"] == 0).sum() >= 4
 np.savez_compressed(os.path.join(HERE, "tasks.npz"), **out)
 print("wrote tasks.npz", {k: v.shape for k, v in out.items()})

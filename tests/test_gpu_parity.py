@@ -314,3 +314,37 @@ def test_hold_task_golden_and_reset():
         obs, rew, done, trunc, _ = env.step(a)
     torch.cuda.synchronize()
     assert torch.isfinite(obs).all() and not bool(done.any())
+
+
+def test_reach_task_golden_reset_and_time_switch():
+    """myoHandReachRandom-v0 on the device: obs / reward / done against the reference's own ReachEnvV0 outputs (tests/golden/tasks.npz),
+    target sampling inside the registered spans, and far_th arming at the 2nd control step (mjData.time accumulates per substep)."""
+    import torch
+    from myosuite_b200 import vec_env
+    n = len(TG["reach_qpos"])
+    env = vec_env.MyoVecEnv("myoHandReachRandom-v0", n, auto_reset=False)
+    assert env.obs_dim == 115 and env.max_episode_steps == 100 and env.tip_names == ["THtip", "IFtip", "MFtip", "RFtip", "LFtip"]
+    env.set_state(qpos=TG["reach_qpos"], qvel=TG["reach_qvel"], act=TG["reach_act"])
+    env.t["target"][:, :15] = torch.as_tensor(TG["reach_targets"].reshape(n, 15), device=env.device)
+    env.t["time"][:] = torch.as_tensor(TG["reach_time"], device=env.device)
+    env.refresh_obs(); torch.cuda.synchronize()
+    np.testing.assert_allclose(env.t["obs"].cpu().numpy(), TG["reach_obs"], rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(env.t["reward"].cpu().numpy(), TG["reach_dense"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_array_equal(env.t["done"].cpu().numpy().astype(bool), TG["reach_done"].astype(bool))
+    # reset: targets ~ U(span) per coordinate, initial pose = init_qpos, obs consistent with them
+    env.reset(seed=3); torch.cuda.synchronize()
+    tg = env.t["target"][:, :15].cpu().numpy(); lo, hi = env.t["target_range"][:15, 0].cpu().numpy(), env.t["target_range"][:15, 1].cpu().numpy()
+    assert np.all(tg >= lo - 1e-15) and np.all(tg <= hi + 1e-15) and np.all(np.std(tg, axis=0)[hi > lo] > 0)
+    obs = env.t["obs"].cpu().numpy()
+    np.testing.assert_allclose(obs[:, 46:61] + obs[:, 61:76], tg, rtol=0, atol=1e-6)          # tip_pos + reach_err = target
+    # zero action: far from the targets, done must stay off at step 1 and switch on at step 2 (time = 0.04000000000000002 > 2 dt)
+    a = torch.full((n, env.act_dim), -1.0, device=env.device)
+    for k in range(1, 4):
+        obs, rew, done, trunc, info = env.step(a); torch.cuda.synchronize()
+        dist = np.linalg.norm(obs[:, 61:76].cpu().numpy().astype(np.float64), axis=1); dn = done.cpu().numpy().astype(bool)
+        clear = np.abs(dist - 5 * 0.034) > 1e-5                                            # (f32 obs: skip envs sitting on the threshold)
+        if k == 1:
+            assert not dn.any()
+        else:
+            assert np.array_equal(dn[clear], (dist > 5 * 0.034)[clear])
+    assert info["time"].cpu().numpy()[0] == pytest.approx(0.06)

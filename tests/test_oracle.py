@@ -209,3 +209,20 @@ def test_hold_obs_reward_golden(models):
         np.testing.assert_allclose(obs, T["hold_obs"][i], rtol=1e-6, atol=1e-6)
         np.testing.assert_allclose(r["dense"], T["hold_dense"][i], rtol=1e-9, atol=1e-9)
         assert bool(r["done"]) == bool(T["hold_done"][i])
+
+
+def test_reach_obs_reward_golden(models):
+    """ReachEnvV0 (reach_v0.py:98-160) restated in env_oracle vs vectors produced by the reference's own class, including the
+    `time > 2 dt` switch of far_th that MuJoCo's per-substep time accumulation flips one control step early."""
+    import json, os
+    m = models["myohand_pose"]
+    o = Oracle(*blob.pack(m))
+    reg = json.load(open(os.path.join(os.path.dirname(blob.__file__), "assets", "registry.json")))["envs"]["myoHandReachRandom-v0"]["kwargs"]
+    tips = list(reg["target_reach_range"].keys())
+    assert tips == ["THtip", "IFtip", "MFtip", "RFtip", "LFtip"]           # reference registration order = obs layout order
+    for i in range(len(T["reach_qpos"])):
+        o.reset(); o.set(qpos=T["reach_qpos"][i], qvel=T["reach_qvel"][i], act=T["reach_act"][i]); o.forward()
+        obs, r = env_oracle.reach_obs_reward(m, o, 0.02, tips, T["reach_targets"][i], float(T["reach_time"][i]), far_th=reg["far_th"])
+        np.testing.assert_allclose(obs, T["reach_obs"][i], rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(r["dense"], T["reach_dense"][i], rtol=1e-9, atol=1e-9)
+        assert bool(r["done"]) == bool(T["reach_done"][i]) and bool(r["solved"]) == bool(T["reach_solved"][i])

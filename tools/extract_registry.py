@@ -33,7 +33,7 @@ g = {"__file__": src, "__name__": "myobase_registry"}
 exec(compile(open(src).read(), src, "exec"), g)
 
 WANT = ["myoElbowPose1D6MRandom-v0", "myoHandPoseRandom-v0", "myoLegWalk-v0", "myoHandObjHoldRandom-v0",
-        "myoElbowPose1D6MFixed-v0", "myoHandPoseFixed-v0", "myoHandObjHoldFixed-v0"]
+        "myoElbowPose1D6MFixed-v0", "myoHandPoseFixed-v0", "myoHandObjHoldFixed-v0", "myoHandReachFixed-v0", "myoHandReachRandom-v0"]
 pkg = os.path.join(ref, "myosuite")
 
 
@@ -60,5 +60,5 @@ for vid, v in variants.items():
     if v["base"] in out["envs"]:
         out["variants"][vid] = clean(v)
 dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "myosuite_b200", "assets", "registry.json")
-json.dump(out, open(dst, "w"), indent=1, sort_keys=True)
+json.dump(out, open(dst, "w"), indent=1, sort_keys=False)
 print("wrote", dst, list(out["envs"]), len(out["variants"]), "variants")
