@@ -288,9 +288,11 @@ extern "C" __global__ void __launch_bounds__(384) myo_env_kernel(const __grid_co
       PH(4, phase_collision(m, w));
       if (m.npair > m.npair_an) {   // CTA-cooperative pass over the expensive candidates of all envs of this CTA
         long long tc_ = prof ? clock64() : 0;
-        if (w.lane == 0) s_ncand[wid] = live ? w.ncand : 0;
-        group_sync(ngroups, gid, gthreads); collision_coop(m, w, warp0, s_ncand, gw0, gnw); group_sync(ngroups, gid, gthreads);
-        if (live) collision_merge(m, w);
+        if (m.coop) {
+          if (w.lane == 0) s_ncand[wid] = live ? w.ncand : 0;
+          group_sync(ngroups, gid, gthreads); collision_coop(m, w, warp0, s_ncand, gw0, gnw); group_sync(ngroups, gid, gthreads);
+          if (live) collision_merge(m, w);
+        } else if (live) collision_direct(m, w);
         if (prof) cyc[16] += clock64() - tc_; }
       PH(5, phase_constraints(m, w); if (tap) write_taps_contacts(m, w, a, env));
       PH(6, phase_solve(m, w, a.tol, prof ? cyc : nullptr));
@@ -361,6 +363,7 @@ static void fill_devmodel(const myo_model* mm, const myo_task_cfg* cfg, DevModel
   d.npair = P[PD_NPAIR]; d.npair_an = P[PD_NPAIR_ANALYTIC]; d.maxpath = P[PD_MAXPATH]; d.ndepth = P[PD_NDEPTH]; d.eq_tree = P[PD_EQ_TREE];
   const double* opt = MYO_DSEC(I, D, MYO_SEC_opt); d.timestep = opt[0]; d.gx = opt[1]; d.gy = opt[2]; d.gz = opt[3]; d.tolerance = opt[4]; d.meaninertia = opt[6];
   d.ovr_geom = (cfg && cfg->task == MYO_TASK_HOLD) ? cfg->task_i[1] : -1;
+  { const char* e = getenv("MYO_B200_COOP"); d.coop = e ? atoi(e) : 0; }     // ellipsoid candidates: 0 = inside the owning warp (default; 558k vs 548k on the hand), 1 = CTA-cooperative pass
   int mc = cfg && cfg->maxcon > 0 ? cfg->maxcon : 32; if (mc > 2*d.npair) mc = 2*d.npair; d.maxcon = mc; d.nlimrow = P[PD_NLIMROW] > 0 ? P[PD_NLIMROW] : 2*d.nlim; d.maxefc = d.neq + d.nlimrow + 4*mc;
   int o = 0;
   #define TAKE(field, n) d.field = o; o += al2(n)

@@ -40,7 +40,7 @@ struct DevModel {
   int32_t hoff[MYO_NSEC];                  // offset of each hot section (in shorts / doubles), -1 if not staged
   int32_t nq, nv, nu, na, nM, njnt;
   int32_t nbd, nlevel, nsp, nwe, nta, nnz, nlim, neq, npair, npair_an, maxpath, ndepth, eq_tree;
-  int32_t maxcon, maxefc, nlimrow, ovr_geom, ngc, s_gpose;          // ovr_geom: collision geom whose size comes from the per-env overrides (-1: none)
+  int32_t maxcon, maxefc, nlimrow, ovr_geom, ngc, s_gpose, coop;          // ovr_geom: collision geom whose size comes from the per-env overrides (-1: none)
   double timestep, gx, gy, gz, meaninertia, tolerance;
   // per-warp shared-memory layout, in doubles.  Persistent part:
   int32_t o_qpos, o_qvel, o_act, o_ctrl, o_qws, o_dax, o_dan, o_qM, o_fsm, o_eprm, o_wz, nwz, o_scr, n_per_warp;
@@ -671,6 +671,19 @@ __device__ void collision_coop(const DevModel& m, const Warp& self, double* warp
     const int* clist = (const int*)SCR(s_clist); double* r = SCR(s_cres) + 7*k;
     ConOut o; o.n = 0; o.has_y = false; collide_ellipsoid(m, w, clist[k], o);
     r[0] = o.n ? o.dist[0] : 1e30; for (int c = 0; c < 3; c++) { r[1+c] = o.pos[0][c]; r[4+c] = o.nrm[0][c]; } }
+}
+// in-warp alternative to the cooperative pass: one candidate per lane of the owning warp (no CTA barriers)
+__device__ void collision_direct(const DevModel& m, Warp& w) {
+  double* con = SCR(s_con); int* icon = (int*)SCR(s_icon); const int* clist = (const int*)SCR(s_clist); int ncon = w.ncon;
+  #pragma unroll 1
+  for (int kb = 0; kb < w.ncand; kb += 32) { int k = kb + w.lane; ConOut o; o.n = 0; o.has_y = false; int p = 0;
+    if (k < w.ncand) { p = clist[k]; collide_ellipsoid(m, w, p, o); }
+    unsigned m0 = __ballot_sync(FULL, o.n >= 1); int idx = ncon + __popc(m0 & ((1u << w.lane) - 1));
+    if (o.n) store_contact(m, w, con, icon, idx, p, o, 0);
+    ncon += __popc(m0); }
+  if (ncon > m.maxcon) { w.overflow = 1; ncon = m.maxcon; }
+  w.ncon = ncon;
+  __syncwarp();
 }
 // append the cooperative results (candidate order = pair order) to this env's contact list
 __device__ void collision_merge(const DevModel& m, Warp& w) {

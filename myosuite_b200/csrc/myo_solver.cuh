@@ -258,11 +258,13 @@ __device__ void phase_solve(const DevModel& m, Warp& w, double tol, long long* c
       else { const double* P = pd + q[6]*PPAIR_STRIDE; double mu1 = P[2], mu2 = P[3], Dv = s.D[rb];
         double a0 = s.jar[rb] < 0 ? Dv : 0, a1 = s.jar[rb+1] < 0 ? Dv : 0, a2 = s.jar[rb+2] < 0 ? Dv : 0, a3 = s.jar[rb+3] < 0 ? Dv : 0;
         W[0] = a0+a1+a2+a3; W[1] = mu1*(a0-a1); W[2] = mu2*(a2-a3); W[3] = mu1*mu1*(a0+a1); W[5] = mu2*mu2*(a2+a3); }
-      if (W[0] != 0) { const double* J = s.conJ + (size_t)c*3*m.maxpath; int np = q[4];
-        for (int t = w.lane; t < np*np; t += 32) { int ei = t / np, ej = t - ei*np; if ((path[q[3]+ei] >> 1) < (path[q[3]+ej] >> 1)) continue;
+      if (W[0] != 0) { const double* J = s.conJ + (size_t)c*3*m.maxpath; int np = q[4], ntri = (np*(np+1)) >> 1;
+        // one lane per entry of the lower triangle of J'WJ (the path lists dofs in ascending order, so entry (ei >= ej) lands on H[di >= dj])
+        for (int t = w.lane; t < ntri; t += 32) { int ei = __float2int_rd((sqrtf(8.0f*t + 1.0f) - 1.0f)*0.5f); if (((ei+1)*(ei+2) >> 1) <= t) ei++; if (((ei*(ei+1)) >> 1) > t) ei--;
+          int ej = t - ((ei*(ei+1)) >> 1);
           const double* a = J + 3*ei; const double* b = J + 3*ej;
           double wa0 = W[0]*a[0]+W[1]*a[1]+W[2]*a[2], wa1 = W[1]*a[0]+W[3]*a[1]+W[4]*a[2], wa2 = W[2]*a[0]+W[4]*a[1]+W[5]*a[2];
-          int di = path[q[3]+ei] >> 1, dj = path[q[3]+ej] >> 1; if (di >= dj) s.H[TRI(di,dj)] += wa0*b[0]+wa1*b[1]+wa2*b[2]; } }
+          int di = path[q[3]+ei] >> 1, dj = path[q[3]+ej] >> 1; s.H[TRI(di,dj)] += wa0*b[0]+wa1*b[1]+wa2*b[2]; } }
       __syncwarp(); }
     LAP(9)
     chol_dense(s.H, n, s.p, w.lane);
