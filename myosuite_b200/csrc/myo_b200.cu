@@ -363,6 +363,7 @@ static void fill_devmodel(const myo_model* mm, const myo_task_cfg* cfg, DevModel
   d.npair = P[PD_NPAIR]; d.npair_an = P[PD_NPAIR_ANALYTIC]; d.maxpath = P[PD_MAXPATH]; d.ndepth = P[PD_NDEPTH]; d.eq_tree = P[PD_EQ_TREE];
   const double* opt = MYO_DSEC(I, D, MYO_SEC_opt); d.timestep = opt[0]; d.gx = opt[1]; d.gy = opt[2]; d.gz = opt[3]; d.tolerance = opt[4]; d.meaninertia = opt[6];
   d.ovr_geom = (cfg && cfg->task == MYO_TASK_HOLD) ? cfg->task_i[1] : -1;
+  { const char* e = getenv("MYO_B200_CHOL"); d.chol_mode = e ? atoi(e) : 1; }   // dense Cholesky (nv <= 32): 1 = unrolled register/shuffle version (default: 21 k cycles per 23x23 solve), 0 = rolled shared-memory version (49 k)
   { const char* e = getenv("MYO_B200_COOP"); d.coop = e ? atoi(e) : 0; }     // ellipsoid candidates: 0 = inside the owning warp (default; 558k vs 548k on the hand), 1 = CTA-cooperative pass
   int mc = cfg && cfg->maxcon > 0 ? cfg->maxcon : 32; if (mc > 2*d.npair) mc = 2*d.npair; d.maxcon = mc; d.nlimrow = P[PD_NLIMROW] > 0 ? P[PD_NLIMROW] : 2*d.nlim; d.maxefc = d.neq + d.nlimrow + 4*mc;
   int o = 0;

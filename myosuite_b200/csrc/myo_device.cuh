@@ -40,7 +40,7 @@ struct DevModel {
   int32_t hoff[MYO_NSEC];                  // offset of each hot section (in shorts / doubles), -1 if not staged
   int32_t nq, nv, nu, na, nM, njnt;
   int32_t nbd, nlevel, nsp, nwe, nta, nnz, nlim, neq, npair, npair_an, maxpath, ndepth, eq_tree;
-  int32_t maxcon, maxefc, nlimrow, ovr_geom, ngc, s_gpose, coop;          // ovr_geom: collision geom whose size comes from the per-env overrides (-1: none)
+  int32_t maxcon, maxefc, nlimrow, ovr_geom, ngc, s_gpose, coop, chol_mode;          // ovr_geom: collision geom whose size comes from the per-env overrides (-1: none)
   double timestep, gx, gy, gz, meaninertia, tolerance;
   // per-warp shared-memory layout, in doubles.  Persistent part:
   int32_t o_qpos, o_qvel, o_act, o_ctrl, o_qws, o_dax, o_dan, o_qM, o_fsm, o_eprm, o_wz, nwz, o_scr, n_per_warp;

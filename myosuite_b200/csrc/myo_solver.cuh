@@ -115,16 +115,40 @@ __device__ void phase_constraints(const DevModel& m, Warp& w) {
 
 // ------------------------------------------------------------------ dense Cholesky (packed lower triangle, in place) + solve in shared memory
 #define TRI(i, j) ((i)*((i)+1)/2 + (j))
-__device__ void chol_factor(double* H, int n, int lane) {
+// t -> (i >= j) with t = i(i+1)/2 + j
+__device__ __forceinline__ void tri_index(int t, int& i, int& j) {
+  i = __float2int_rd((sqrtf(8.0f*t + 1.0f) - 1.0f)*0.5f); if (((i+1)*(i+2) >> 1) <= t) i++; if (((i*(i+1)) >> 1) > t) i--;
+  j = t - ((i*(i+1)) >> 1); }
+
+// In-place right-looking Cholesky with the whole trailing update of a column spread flat over the lanes (a short rolled loop: the
+// code stays in the instruction cache, unlike the unrolled register version).  On exit column k holds L[.][k] below the diagonal;
+// the diagonal keeps the PIVOT (not its root): *dinv_lane = 1/sqrt(pivot of row `lane`) for lane < n, and, if fix_diag, H[k][k] = sqrt(pivot).
+__device__ __noinline__ void chol_factor(double* H, int n, int lane, double* dinv_lane, bool fix_diag) {
+  double inv_prev = 0, dinv = 1.0;
+  #pragma unroll 1
   for (int k = 0; k < n; k++) {
-    double dkk = sqrt(fmax(H[TRI(k,k)], MYO_MINVAL));
+    double inv = rsqrt(fmax(H[TRI(k,k)], MYO_MINVAL)), inv2 = inv*inv;       // every lane reads the pivot: no broadcast step
+    if (lane == k) dinv = inv;
+    if (k > 0) for (int i = k + lane; i < n; i += 32) H[TRI(i,k-1)] *= inv_prev;   // scale the previous column (its readers are done)
+    const int m_ = n-1-k, cnt = (m_*(m_+1)) >> 1; const double* colk = H + k;       // H[TRI(i,k)] = H[i(i+1)/2 + k]
+    #pragma unroll 2
+    for (int t = lane; t < cnt; t += 32) { int a, b; tri_index(t, a, b); int i = k+1+a, j = k+1+b;
+      H[TRI(i,j)] -= colk[(i*(i+1)) >> 1]*colk[(j*(j+1)) >> 1]*inv2; }
     __syncwarp();
-    if (lane == 0) H[TRI(k,k)] = dkk;
-    double inv = 1.0/dkk;
-    for (int i = k+1+lane; i < n; i += 32) H[TRI(i,k)] *= inv;
-    __syncwarp();
-    for (int i = k+1+lane; i < n; i += 32) { double lik = H[TRI(i,k)]; for (int j = k+1; j <= i; j++) H[TRI(i,j)] -= lik*H[TRI(j,k)]; }
-    __syncwarp(); }
+    inv_prev = inv; }
+  if (fix_diag) { for (int k = lane; k < n; k += 32) H[TRI(k,k)] = sqrt(fmax(H[TRI(k,k)], MYO_MINVAL)); __syncwarp(); }
+  *dinv_lane = dinv;
+}
+// n <= 32: substitutions with one row per lane (rhs in a register, exchanged by shuffles; L read from shared memory)
+__device__ __noinline__ void chol_smem32(double* H, int n, double* x, int lane) {
+  double dinv; chol_factor(H, n, lane, &dinv, false);
+  double b = lane < n ? x[lane] : 0.0; const double* row = H + ((lane*(lane+1)) >> 1);
+  #pragma unroll 1
+  for (int k = 0; k < n; k++) { double yk = __shfl_sync(FULL, b*dinv, k); if (lane == k) b = yk; else if (lane > k && lane < n) b = fma(-row[k], yk, b); }
+  #pragma unroll 1
+  for (int k = n-1; k >= 0; k--) { double xk = __shfl_sync(FULL, b*dinv, k); if (lane == k) b = xk; else if (lane < k) b = fma(-H[TRI(k,lane)], xk, b); }
+  if (lane < n) x[lane] = b;
+  __syncwarp();
 }
 // x <- H^-1 x  (H holds the Cholesky factor)
 __device__ void chol_solve(const double* H, int n, double* x, int lane) {
@@ -165,9 +189,11 @@ __device__ __noinline__ void chol_reg24(const double* H, int n, double* x, int l
 __device__ __noinline__ void chol_reg32(const double* H, int n, double* x, int lane) { chol_reg<32>(H, n, x, lane); }
 
 // x <- H^-1 x for a dense SPD H (packed lower triangle in shared memory); returns whether H survived (the n > 32 fallback factors in place)
-__device__ __forceinline__ bool chol_dense(double* H, int n, double* x, int lane) {
+__device__ __forceinline__ bool chol_dense(double* H, int n, double* x, int lane, int mode) {
+  if (n > 32) { double dinv; chol_factor(H, n, lane, &dinv, true); chol_solve(H, n, x, lane); return false; }
+  if (mode == 0) { chol_smem32(H, n, x, lane); return false; }
   if (n <= 8) chol_reg8(H, n, x, lane); else if (n <= 16) chol_reg16(H, n, x, lane); else if (n <= 24) chol_reg24(H, n, x, lane);
-  else if (n <= 32) chol_reg32(H, n, x, lane); else { chol_factor(H, n, lane); chol_solve(H, n, x, lane); return false; }
+  else chol_reg32(H, n, x, lane);
   return true; }
 
 __device__ __forceinline__ void load_M_dense(const DevModel& m, const Warp& w, double* H, double diag_scale /* h */) {
@@ -267,7 +293,7 @@ __device__ void phase_solve(const DevModel& m, Warp& w, double tol, long long* c
           int di = path[q[3]+ei] >> 1, dj = path[q[3]+ej] >> 1; s.H[TRI(di,dj)] += wa0*b[0]+wa1*b[1]+wa2*b[2]; } }
       __syncwarp(); }
     LAP(9)
-    chol_dense(s.H, n, s.p, w.lane);
+    chol_dense(s.H, n, s.p, w.lane, m.chol_mode);
     LAP(10)
     }
     // exact line search along p
@@ -302,7 +328,7 @@ __device__ void phase_integrate(const DevModel& m, Warp& w, long long* cyc) {
   if (n <= 32) {     // small systems: the register Cholesky beats the level-scheduled sparse factorisation (long index-chasing chains)
     load_M_dense(m, w, s.H, h);
     if (cyc) { long long t_ = clock64(); cyc[18] += t_ - tc; tc = t_; }
-    chol_dense(s.H, n, s.g, w.lane);
+    chol_dense(s.H, n, s.g, w.lane, m.chol_mode);
   } else {
   { const idx_t* mi = CI(PM_i); const idx_t* mj = CI(PM_j); const double* dofp = CD(PDOF_d);
     for (int e = w.lane; e < m.nM; e += 32) { double v = w.qM[e]; if (mi[e] == mj[e]) v += h*dofp[2*mi[e]+1]; s.Hs[e] = v; } __syncwarp(); }
