@@ -231,7 +231,8 @@ def main():
         if not args.no_cpu_baseline:
             from oracle import oracle_py
             oracle_py.build()
-            nst = 300 if "Elbow" in args.env else 60 if "Pose" in args.env else 30
+            rate1 = cpu_baseline(args.env, 10, threads=1)          # calibrate, then a bounded sample of ~10 s of single-thread stepping
+            nst = int(max(20, min(200000, 10.0 * rate1)))
             t0 = time.perf_counter()
             v = cpu_baseline(args.env, nst, threads=1)
             line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",

@@ -150,6 +150,18 @@ __device__ __noinline__ void chol_smem32(double* H, int n, double* x, int lane) 
   if (lane < n) x[lane] = b;
   __syncwarp();
 }
+// row-per-lane variant (any n): the n > 32 fallback (legs, nv = 34: 176 k vs 167 k env-steps/s with the flat-update version above)
+__device__ void chol_factor_rows(double* H, int n, int lane) {
+  for (int k = 0; k < n; k++) {
+    double dkk = sqrt(fmax(H[TRI(k,k)], MYO_MINVAL));
+    __syncwarp();
+    if (lane == 0) H[TRI(k,k)] = dkk;
+    double inv = 1.0/dkk;
+    for (int i = k+1+lane; i < n; i += 32) H[TRI(i,k)] *= inv;
+    __syncwarp();
+    for (int i = k+1+lane; i < n; i += 32) { double lik = H[TRI(i,k)]; for (int j = k+1; j <= i; j++) H[TRI(i,j)] -= lik*H[TRI(j,k)]; }
+    __syncwarp(); }
+}
 // x <- H^-1 x  (H holds the Cholesky factor)
 __device__ void chol_solve(const double* H, int n, double* x, int lane) {
   for (int k = 0; k < n; k++) { double xk = x[k]/H[TRI(k,k)]; __syncwarp(); if (lane == 0) x[k] = xk;
@@ -190,7 +202,7 @@ __device__ __noinline__ void chol_reg32(const double* H, int n, double* x, int l
 
 // x <- H^-1 x for a dense SPD H (packed lower triangle in shared memory); returns whether H survived (the n > 32 fallback factors in place)
 __device__ __forceinline__ bool chol_dense(double* H, int n, double* x, int lane, int mode) {
-  if (n > 32) { double dinv; chol_factor(H, n, lane, &dinv, true); chol_solve(H, n, x, lane); return false; }
+  if (n > 32) { chol_factor_rows(H, n, lane); chol_solve(H, n, x, lane); return false; }
   if (mode == 0) { chol_smem32(H, n, x, lane); return false; }
   if (n <= 8) chol_reg8(H, n, x, lane); else if (n <= 16) chol_reg16(H, n, x, lane); else if (n <= 24) chol_reg24(H, n, x, lane);
   else chol_reg32(H, n, x, lane);
@@ -325,7 +337,7 @@ __device__ void phase_integrate(const DevModel& m, Warp& w, long long* cyc) {
   // (M + h B) qacc' = M qacc  (= qfrc_smooth + qfrc_constraint at the solver optimum)
   for (int i = w.lane; i < n; i += 32) s.g[i] = s.Ma[i];     // M qacc, maintained by the solver
   __syncwarp();
-  if (n <= 32) {     // small systems: the register Cholesky beats the level-scheduled sparse factorisation (long index-chasing chains)
+  if (n >= 8 && n <= 32) {     // mid-size systems: the register Cholesky beats the level-scheduled sparse factorisation (long index-chasing chains)
     load_M_dense(m, w, s.H, h);
     if (cyc) { long long t_ = clock64(); cyc[18] += t_ - tc; tc = t_; }
     chol_dense(s.H, n, s.g, w.lane, m.chol_mode);
