@@ -56,7 +56,7 @@ typedef struct {
   int32_t normalize_act;     /* sigmoid remap of muscle actions (base_v0.py:86-94) */
   int32_t muscle_condition;  /* MYO_COND_* */
   int32_t auto_reset;        /* 1: envs that finish are reset inside the step kernel */
-  int32_t reset_random;      /* pose: 1 = qpos ~ U(jnt_range) (reset_type="random"), 0 = init_qpos */
+  int32_t reset_random;      /* reset_type="random": pose qpos ~ U(jnt_range); walk keyframe row 0/1 of init_qpos + N(0,0.02) (walk_v0.py:321-337); hold goal/size sampling. 0 = init_qpos */
   int32_t maxcon;            /* 0 = library default */
   int32_t reaf_dst, reaf_src;/* reafferentation (base_v0.py:104-108): ctrl[dst] = ctrl[src]; ctrl[src] = 0 ; dst == src = off */
   int32_t barrier_mode;      /* CTA phase barriers: 0 = before every phase (default), 1 = once per substep, 2 = none, >2 = bit mask of the 8 phases that start with a barrier (tuning knob) */
@@ -81,8 +81,8 @@ typedef struct {
   double* fatigue;           /* [n, 3, nu] MA,MR,MF (nullable unless MYO_COND_FATIGUE) */
   double* target;            /* [n, nq]  pose target_jnt_value, in/out */
   const double* target_range;/* [nq, 2]  per-qpos target sampling range (pose), model-level, in */
-  const double* init_qpos;   /* [nq]     reset pose when !reset_random, in */
-  const double* init_qvel;   /* [nv]     reset velocity (nullable = zeros), in */
+  const double* init_qpos;   /* [nq]     reset pose, in ([2,nq] for the walk task with reset_random: the two candidate keyframes) */
+  const double* init_qvel;   /* [nv]     reset velocity (nullable = zeros), in ([2,nv] alongside a [2,nq] init_qpos) */
   double* env_prm;           /* [n, 8]   per-env model overrides (HOLD: goal site pos[3], object geom size[3]); nullable */
   int32_t* step_count;       /* [n] */
   int64_t* episode_count;    /* [n]  also the Philox stream counter */

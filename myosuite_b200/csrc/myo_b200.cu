@@ -59,6 +59,15 @@ __device__ void env_reset(const DevModel& m, Warp& w, const StepArgs& a, int env
   Philox rng; philox_init(rng, a.seed, (unsigned long long)(a.env_offset + env), (unsigned long long)ep, (uint32_t)w.lane);
   const idx_t* jtype = CI(jnt_type); const idx_t* jq = CI(jnt_qposadr); const double* jrange = CD(jnt_range); const double* qpos0 = CD(qpos0);
   for (int i = w.lane; i < m.nq; i += 32) w.qpos[i] = b.init_qpos ? b.init_qpos[i] : qpos0[i];
+  int key = 0;                                  // row of init_qpos / init_qvel this episode starts from
+  if (a.cfg.task == MYO_TASK_WALK && a.cfg.reset_random && b.init_qpos) {
+    // WalkEnvV0.get_randomized_initial_state (walk_v0.py:321-337): keyframe 2 or 3 with probability 1/2 (init_qpos rows 0 / 1), then
+    // qpos += N(0, 0.02) on every coordinate except the height qpos[2] (the quaternion "restore" there writes a view back onto
+    // itself, so the root quaternion keeps its noise; the kinematics normalise it)
+    double u = __shfl_sync(FULL, philox_uniform(rng), 0); key = u < 0.5 ? 0 : 1;
+    for (int i = w.lane; i < m.nq; i += 32) { double u1 = philox_uniform(rng), u2 = philox_uniform(rng);
+      double z = sqrt(-2.0*log(fmax(u1, 1e-300)))*cos(6.283185307179586*u2), q = b.init_qpos[(size_t)key*m.nq + i];
+      w.qpos[i] = i == 2 ? q : q + 0.02*z; } }
   __syncwarp();
   if (a.cfg.task == MYO_TASK_POSE) {
     // target_jnt_value ~ U(target_jnt_range) ; reset_type "random": qpos ~ U(jnt_range)
@@ -77,7 +86,7 @@ __device__ void env_reset(const DevModel& m, Warp& w, const StepArgs& a, int env
       if (w.lane < 3) v = a.cfg.reset_random ? a.cfg.task_d[3+w.lane] + (-0.030 + 0.060*u) : a.cfg.task_d[6+w.lane];
       else v = a.cfg.reset_random ? 0.020 + 0.010*u : a.cfg.task_d[6+w.lane];
       w.eprm[w.lane] = v; b.env_prm[(size_t)env*8 + w.lane] = v; } }
-  for (int i = w.lane; i < m.nv; i += 32) { w.qvel[i] = b.init_qvel ? b.init_qvel[i] : 0.0; w.qws[i] = 0; }
+  for (int i = w.lane; i < m.nv; i += 32) { w.qvel[i] = b.init_qvel ? b.init_qvel[(size_t)key*m.nv + i] : 0.0; w.qws[i] = 0; }
   for (int i = w.lane; i < m.na; i += 32) w.act[i] = 0;
   if (b.fatigue && a.cfg.muscle_condition == MYO_COND_FATIGUE) for (int i = w.lane; i < m.nu; i += 32) { double* f = b.fatigue + (size_t)env*3*m.nu; f[i] = 0; f[m.nu+i] = 1; f[2*m.nu+i] = 0; }
   if (w.lane == 0) { if (b.time) b.time[env] = 0; if (b.step_count) b.step_count[env] = 0; if (b.episode_count) b.episode_count[env] = ep+1; if (b.ep_return) b.ep_return[env] = 0; }

@@ -200,9 +200,68 @@ __device__ __noinline__ void chol_reg16(const double* H, int n, double* x, int l
 __device__ __noinline__ void chol_reg24(const double* H, int n, double* x, int lane) { chol_reg<24>(H, n, x, lane); }
 __device__ __noinline__ void chol_reg32(const double* H, int n, double* x, int lane) { chol_reg<32>(H, n, x, lane); }
 
+// Bordered register Cholesky for 32 < n <= 32+E: H = [A B'; B C] with A the leading 32x32 block.  A = L11 L11' is factored in
+// registers exactly like chol_reg<32>; the rows of B ride along as extra right-hand sides of the forward substitution
+// (L21 = B L11^-T), the E x E Schur complement C - L21 L21' is reduced with warp sums and factored redundantly by every lane.
+template <int E>
+__device__ __noinline__ void chol_reg32b(const double* H, int n, double* x, int lane) {
+  const int e = n - 32;
+  double r[32], c[32], bq[E];
+  #pragma unroll
+  for (int j = 0; j < 32; j++) { r[j] = j <= lane ? H[TRI(lane, j)] : 0.0; c[j] = 0.0; }
+  #pragma unroll
+  for (int q = 0; q < E; q++) bq[q] = q < e ? H[TRI(32+q, lane)] : 0.0;
+  double b = x[lane], dinv = 1.0;
+  #pragma unroll
+  for (int k = 0; k < 32; k++) {
+    double inv = rsqrt(fmax(__shfl_sync(FULL, r[k], k), MYO_MINVAL));
+    if (lane == k) dinv = inv;
+    r[k] *= inv;
+    #pragma unroll
+    for (int j = k+1; j < 32; j++) { double ljk = __shfl_sync(FULL, r[k], j); if (lane == k) c[j] = ljk; r[j] = fma(-r[k], ljk, r[j]); } }
+  #pragma unroll
+  for (int k = 0; k < 32; k++) { double yk = __shfl_sync(FULL, b*dinv, k); b = lane == k ? yk : (lane > k ? fma(-r[k], yk, b) : b);
+    #pragma unroll
+    for (int q = 0; q < E; q++) { double yq = __shfl_sync(FULL, bq[q]*dinv, k); bq[q] = lane == k ? yq : (lane > k ? fma(-r[k], yq, bq[q]) : bq[q]); } }
+  // b = y1[lane], bq[q] = L21[q][lane]; Schur complement (identity-padded beyond e) and its right-hand side
+  double S[E][E], y2[E];
+  #pragma unroll
+  for (int q = 0; q < E; q++) {
+    #pragma unroll
+    for (int p = 0; p <= q; p++) { double v = warp_sum(bq[q]*bq[p]); S[q][p] = ((q < e && p < e) ? H[TRI(32+q, 32+p)] : (q == p ? 1.0 : 0.0)) - v; }
+    y2[q] = (q < e ? x[32+q] : 0.0) - warp_sum(bq[q]*b); }
+  #pragma unroll
+  for (int k = 0; k < E; k++) { S[k][k] = sqrt(fmax(S[k][k], MYO_MINVAL)); double ik = 1.0/S[k][k];
+    #pragma unroll
+    for (int i = k+1; i < E; i++) S[i][k] *= ik;
+    #pragma unroll
+    for (int i = k+1; i < E; i++) {
+      #pragma unroll
+      for (int j = k+1; j <= i; j++) S[i][j] -= S[i][k]*S[j][k]; } }
+  #pragma unroll
+  for (int k = 0; k < E; k++) { y2[k] /= S[k][k];
+    #pragma unroll
+    for (int i = k+1; i < E; i++) y2[i] -= S[i][k]*y2[k]; }
+  #pragma unroll
+  for (int k = E-1; k >= 0; k--) { y2[k] /= S[k][k];
+    #pragma unroll
+    for (int i = 0; i < k; i++) y2[i] -= S[k][i]*y2[k]; }
+  // x1 = L11^-T (y1 - L21' x2)
+  #pragma unroll
+  for (int q = 0; q < E; q++) b = fma(-bq[q], y2[q], b);
+  #pragma unroll
+  for (int k = 31; k >= 0; k--) { double xk = __shfl_sync(FULL, b*dinv, k); b = lane == k ? xk : fma(-c[k], xk, b); }
+  __syncwarp();
+  x[lane] = b;
+  #pragma unroll
+  for (int q = 0; q < E; q++) if (lane == q && q < e) x[32+q] = y2[q];
+  __syncwarp();
+}
+
 // x <- H^-1 x for a dense SPD H (packed lower triangle in shared memory); returns whether H survived (the n > 32 fallback factors in place)
 __device__ __forceinline__ bool chol_dense(double* H, int n, double* x, int lane, int mode) {
-  if (n > 32) { chol_factor_rows(H, n, lane); chol_solve(H, n, x, lane); return false; }
+  if (n > 36) { chol_factor_rows(H, n, lane); chol_solve(H, n, x, lane); return false; }
+  if (n > 32) { chol_reg32b<4>(H, n, x, lane); return true; }
   if (mode == 0) { chol_smem32(H, n, x, lane); return false; }
   if (n <= 8) chol_reg8(H, n, x, lane); else if (n <= 16) chol_reg16(H, n, x, lane); else if (n <= 24) chol_reg24(H, n, x, lane);
   else chol_reg32(H, n, x, lane);
@@ -337,7 +396,7 @@ __device__ void phase_integrate(const DevModel& m, Warp& w, long long* cyc) {
   // (M + h B) qacc' = M qacc  (= qfrc_smooth + qfrc_constraint at the solver optimum)
   for (int i = w.lane; i < n; i += 32) s.g[i] = s.Ma[i];     // M qacc, maintained by the solver
   __syncwarp();
-  if (n >= 8 && n <= 32) {     // mid-size systems: the register Cholesky beats the level-scheduled sparse factorisation (long index-chasing chains)
+  if (n >= 8 && n <= 36) {     // mid-size systems: the register Cholesky beats the level-scheduled sparse factorisation (long index-chasing chains)
     load_M_dense(m, w, s.H, h);
     if (cyc) { long long t_ = clock64(); cyc[18] += t_ - tc; tc = t_; }
     chol_dense(s.H, n, s.g, w.lane, m.chol_mode);

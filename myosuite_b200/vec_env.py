@@ -105,8 +105,12 @@ class MyoVecEnv:
             for i, k in enumerate(("vel_reward", "done", "cyclic_hip", "ref_rot", "joint_angle_rew")):
                 cfg.weights[i] = w[k]
             self._setup_walk(m, kw, cfg, prog_info=None)
-            key = {"init": 2, "random": 2}.get(kw.get("reset_type", "init"), 0)                     # walk_v0.py:344-352 ("random" adds noise: TODO)
-            init_qpos, init_qvel = m.key_qpos[key].copy(), m.key_qvel[key].copy()
+            rt = kw.get("reset_type", "init")                                                      # walk_v0.py:344-352
+            if rt == "random":       # keyframe 2 or 3 + N(0, 0.02) noise, drawn in the kernel (walk_v0.py:321-337): two rows
+                init_qpos, init_qvel = np.stack([m.key_qpos[2], m.key_qpos[3]]), np.stack([m.key_qvel[2], m.key_qvel[3]])
+            else:
+                key = 2 if rt == "init" else 0
+                init_qpos, init_qvel = m.key_qpos[key].copy(), m.key_qvel[key].copy()
         elif self.task == "hold":
             w = kw.get("weighted_reward_keys", {"goal_dist": 100.0, "bonus": 4.0, "penalty": 10})     # obj_hold_v0.py:17-21
             for i, k in enumerate(("goal_dist", "bonus", "penalty")):

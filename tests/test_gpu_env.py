@@ -113,3 +113,27 @@ def test_sarcopenia_variant_halves_gain():
     a.set_state(qpos=q, qvel=np.zeros((4, 1)), act=np.zeros((4, 6))); a.forward_debug(ctrl, 0); torch.cuda.synchronize()
     passive = a.t["tap_actuator_force"].cpu().numpy()
     np.testing.assert_allclose(fb - passive, 0.5 * (fa - passive), rtol=1e-12, atol=1e-9)   # gainprm[:,2]*=0.5, biasprm untouched (base_v0.py:62-67)
+
+
+def test_walk_random_reset_distribution():
+    """WalkEnvV0 reset_type="random" (walk_v0.py:321-337): keyframe 2 or 3 with probability 1/2, N(0, 0.02) noise on every qpos
+    coordinate except the height (the reference's quaternion "restore" is a no-op on a view, so the quaternion is noisy too)."""
+    import torch
+    from myosuite_b200 import vec_env
+    n = 2048
+    env = vec_env.MyoVecEnv("myoLegWalk-v0", n, auto_reset=False, reset_type="random")
+    m = env.mj_model
+    env.reset(seed=11); torch.cuda.synchronize()
+    q = env.t["qpos"].cpu().numpy(); v = env.t["qvel"].cpu().numpy()
+    k2, k3 = m.key_qpos[2], m.key_qpos[3]
+    is2 = np.abs(q - k2).sum(1) < np.abs(q - k3).sum(1)
+    assert 0.42 < is2.mean() < 0.58
+    base = np.where(is2[:, None], k2[None], k3[None]); d = q - base
+    assert np.all(d[:, 2] == 0)                                                     # height untouched
+    rest = np.delete(d, 2, axis=1)
+    assert abs(rest.std() - 0.02) < 0.002 and abs(rest.mean()) < 0.002 and np.abs(rest).max() < 0.12
+    assert np.std(d[:, 3:7]) > 0.01                                                 # quaternion noise kept, as in the reference
+    np.testing.assert_allclose(v, np.where(is2[:, None], m.key_qvel[2][None], m.key_qvel[3][None]))
+    a = torch.zeros(n, env.act_dim, device=env.device)
+    obs, rew, done, trunc, _ = env.step(a); torch.cuda.synchronize()
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
