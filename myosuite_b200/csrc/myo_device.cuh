@@ -22,7 +22,7 @@ enum { PD_NBD, PD_NLEVEL, PD_NPT, PD_NSP, PD_NWE, PD_NTA, PD_NNZ, PD_NTERM, PD_N
        PD_MAXCHAIN, PD_NSUB, PD_NROW, PD_NCOL, PD_NPIECE, PD_NWE_SPH_OUT, PD_NWE_SPH_IN, PD_NWE_CYL_OUT, PD_NWE_CYL_IN, PD_NDEPTH, PD_EQ_TREE, PD_NPAIR_ANALYTIC, PD_NLIMROW };
 #define PB_STRIDE 22      // pos[3] R[9] ipos[3] mass Iloc[6]
 #define PWE_STRIDE 16
-#define PA_STRIDE 28
+#define PA_STRIDE 17      // dynprm[3] | gain: range0 range1 lmin lmax vmax fvmax | bias: range0 range1 lmax fpmax | ctrlrange[2] | ctrllimited | pad
 #define PAM_STRIDE 6
 #define PG_STRIDE 16
 #define PPAIR_STRIDE 12
@@ -342,22 +342,23 @@ __device__ void phase_actuation(const DevModel& m, Warp& w, bool integrate, doub
   const idx_t* atend = CI(PA_tendon); const idx_t* acls = CI(PA_cls); const double* PAc = CD(PA_d); const double* PAm = CD(PAM_d);
   double* tlen = SCR(s_tlen); double* tvel = SCR(s_tvel); double* tfrc = SCR(s_tfrc); double* mom = SCR(s_mom);
   for (int i = w.lane; i < m.nu; i += 32) { const double* a = PAc + acls[i]*PA_STRIDE; const double* am = PAm + i*PAM_STRIDE; int t = atend[i];
-    const double *dyn = a, *gp = a+3, *bp = a+12, *cr = a+23; double gear = am[4], lr0 = am[2], lr1 = am[3];
+    const double *dyn = a, *gp = a+3, *bp = a+9, *cr = a+13; double gear = am[4], lr0 = am[2], lr1 = am[3];
     double len = gear*tlen[t], vel = gear*tvel[t], ctrl = w.ctrl[i], act = w.act[i];
-    if (a[25] != 0) ctrl = clipd(ctrl, cr[0], cr[1]);
+    if (a[15] != 0) ctrl = clipd(ctrl, cr[0], cr[1]);
     // activation dynamics
     double cc = clipd(ctrl, 0, 1), ac = clipd(act, 0, 1), ta = dyn[0]*(0.5+1.5*ac), td = dyn[1]/(0.5+1.5*ac), dctrl = cc - act, tau;
     if (dyn[2] < MYO_MINVAL) tau = dctrl > 0 ? ta : td;
     else { double x = clipd(dctrl/dyn[2]+0.5, 0, 1), s = x*x*x*(3*x*(2*x-5)+10); tau = td+(ta-td)*s; }
     double actdot = dctrl/fmax(MYO_MINVAL, tau);
     // gain (active force-length-velocity) and bias (passive force)
-    double F = am[0], L0 = (lr1-lr0)/fmax(MYO_MINVAL, gp[1]-gp[0]), L = gp[0]+(len-lr0)/fmax(MYO_MINVAL, L0), V = vel/fmax(MYO_MINVAL, L0*gp[6]);
-    double FL = muscle_FL(L, gp[4], gp[5]), y = gp[8]-1, FV;
-    if (V <= -1) FV = 0; else if (V <= 0) FV = (V+1)*(V+1); else if (V <= y) FV = gp[8]-(y-V)*(y-V)/fmax(MYO_MINVAL, y); else FV = gp[8];
+    const double g_lmin = gp[2], g_lmax = gp[3], g_vmax = gp[4], g_fvmax = gp[5], b_lmax = bp[2], b_fpmax = bp[3];
+    double F = am[0], L0 = (lr1-lr0)/fmax(MYO_MINVAL, gp[1]-gp[0]), L = gp[0]+(len-lr0)/fmax(MYO_MINVAL, L0), V = vel/fmax(MYO_MINVAL, L0*g_vmax);
+    double FL = muscle_FL(L, g_lmin, g_lmax), y = g_fvmax-1, FV;
+    if (V <= -1) FV = 0; else if (V <= 0) FV = (V+1)*(V+1); else if (V <= y) FV = g_fvmax-(y-V)*(y-V)/fmax(MYO_MINVAL, y); else FV = g_fvmax;
     double gain = -F*FL*FV;
-    double Fb = am[1], L0b = (lr1-lr0)/fmax(MYO_MINVAL, bp[1]-bp[0]), Lb = bp[0]+(len-lr0)/fmax(MYO_MINVAL, L0b), b = 0.5*(1+bp[5]), bias;
-    if (Lb <= 1) bias = 0; else if (Lb <= b) { double x = (Lb-1)/fmax(MYO_MINVAL, b-1); bias = -Fb*bp[7]*0.5*x*x; }
-    else { double x = (Lb-b)/fmax(MYO_MINVAL, b-1); bias = -Fb*bp[7]*(0.5+x); }
+    double Fb = am[1], L0b = (lr1-lr0)/fmax(MYO_MINVAL, bp[1]-bp[0]), Lb = bp[0]+(len-lr0)/fmax(MYO_MINVAL, L0b), b = 0.5*(1+b_lmax), bias;
+    if (Lb <= 1) bias = 0; else if (Lb <= b) { double x = (Lb-1)/fmax(MYO_MINVAL, b-1); bias = -Fb*b_fpmax*0.5*x*x; }
+    else { double x = (Lb-b)/fmax(MYO_MINVAL, b-1); bias = -Fb*b_fpmax*(0.5+x); }
     double force = gain*act + bias;
     tfrc[t] = gear*force;   // one actuator per tendon (checked on the host)
     if (tap_force) tap_force[i] = force;

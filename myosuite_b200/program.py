@@ -24,7 +24,7 @@ from . import mjmath as mm
  PD_NDEPTH, PD_EQ_TREE, PD_NPAIR_ANALYTIC, PD_NLIMROW) = range(26)
 NPDIM = 26
 
-PB_STRIDE, PWE_STRIDE, PA_STRIDE, PG_STRIDE, PPAIR_STRIDE, PLIM_STRIDE, PEQ_STRIDE = 22, 16, 28, 16, 12, 12, 16
+PB_STRIDE, PWE_STRIDE, PA_STRIDE, PG_STRIDE, PPAIR_STRIDE, PLIM_STRIDE, PEQ_STRIDE = 22, 16, 17, 16, 12, 12, 16
 PAM_STRIDE, PPAIR_ISTRIDE = 6, 7
 
 # collision function ids
@@ -302,20 +302,21 @@ def build_program(m):
     PA_tendon = [ta_index[int(t)] for t in m.actuator_trnid[:, 0]] if m.nu else []
     if len(set(PA_tendon)) != m.nu:
         raise mjcf.MJCFError("each actuated tendon must carry exactly one actuator")
-    PA_d = np.zeros((m.nu, PA_STRIDE))
+    # per-muscle record (peak forces, lengthrange, gear) + shared parameter classes holding only what the kernel reads:
+    # [0:3] dynprm (tau_act, tau_deact, tausmooth) | [3:9] gainprm range0, range1, lmin, lmax, vmax, fvmax | [9:13] biasprm range0, range1, lmax, fpmax
+    # | [13:15] ctrlrange | [15] ctrllimited | [16] pad (odd stride: a lane per muscle reads its row without bank conflicts)
+    PAM_d, PA_cls, cls_rows, cls_index = np.zeros((m.nu, PAM_STRIDE)), [], [], {}
     for i in range(m.nu):
         if not (m.actuator_dyntype[i] == mjcf.DYN_MUSCLE and m.actuator_gaintype[i] == mjcf.GAIN_MUSCLE
                 and m.actuator_biastype[i] == mjcf.BIAS_MUSCLE):
             raise mjcf.MJCFError("only muscle actuators are supported on the device path")
-        PA_d[i, 0:3], PA_d[i, 3:12], PA_d[i, 12:21] = m.actuator_dynprm[i, :3], m.actuator_gainprm[i, :9], m.actuator_biasprm[i, :9]
-        PA_d[i, 21:23], PA_d[i, 23:25] = m.actuator_lengthrange[i], m.actuator_ctrlrange[i]
-        PA_d[i, 25], PA_d[i, 26] = float(m.actuator_ctrllimited[i]), m.actuator_gear[i, 0]
-    # per-muscle record (peak forces, lengthrange, gear) + shared parameter classes (everything else)
-    PAM_d, PA_cls, cls_rows, cls_index = np.zeros((m.nu, PAM_STRIDE)), [], [], {}
-    for i in range(m.nu):
-        row = PA_d[i].copy()
-        PAM_d[i] = [row[5], row[14], row[21], row[22], row[26], 0.0]      # gain force, bias force, lengthrange, gear
-        row[5] = row[14] = row[21] = row[22] = row[26] = 0.0
+        g, bp = m.actuator_gainprm[i], m.actuator_biasprm[i]
+        PAM_d[i] = [g[2], bp[2], m.actuator_lengthrange[i, 0], m.actuator_lengthrange[i, 1], m.actuator_gear[i, 0], 0.0]   # gain force, bias force, lengthrange, gear
+        row = np.zeros(PA_STRIDE)
+        row[0:3] = m.actuator_dynprm[i, :3]
+        row[3:9] = [g[0], g[1], g[4], g[5], g[6], g[8]]
+        row[9:13] = [bp[0], bp[1], bp[5], bp[7]]
+        row[13:15], row[15] = m.actuator_ctrlrange[i], float(m.actuator_ctrllimited[i])
         key = row.tobytes()
         if key not in cls_index:
             cls_index[key] = len(cls_rows); cls_rows.append(row)
@@ -397,6 +398,11 @@ def build_program(m):
         PEQ.append([q1, d1, q2, d2, i12 if i12 >= 0 else -1, 0])
         PEQ_d.append([*m.eq_data[e], m.qpos0[q1], m.qpos0[q2] if j2 >= 0 else 0.0, iw, K, B, *si, 0.0])
 
+    # The tree-sparse L'DL lists are dead weight in shared memory when the kernel can never take a sparse path: an equality that
+    # couples dofs across the tree keeps every Newton Hessian dense (and nefc > 0), and the integrator uses the dense register
+    # Cholesky for 8 <= nv <= 36 (myo_solver.cuh: phase_solve / phase_integrate).  Legs: 14 KB of the 74 KB hot blob.
+    if len(PEQ) > 0 and not eq_tree and 8 <= m.nv <= 36:
+        PLV_adr, PLV, PFE_adr, PFE, PFT_adr, PFT, PDS_adr, PDS = [0], [], [0], [], [0], [], [0], []
     dims = np.zeros(NPDIM, np.int32)
     dims[PD_NBD], dims[PD_NLEVEL], dims[PD_NPT], dims[PD_NSP], dims[PD_NWE] = nbd, nlevel, len(PPT_body), nsp, nwe
     dims[PD_NTA], dims[PD_NNZ], dims[PD_NTERM] = len(act_tendons), len(PNZ_dof), len(PTERM) // 3
