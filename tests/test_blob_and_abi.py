@@ -114,3 +114,18 @@ def test_registry_ids():
     assert steps == 100 and kw["muscle_condition"] == "fatigue" and kw["pose_thd"] == 0.7 and len(kw["target_jnt_range"]) == 23
     steps, kw, ep = vec_env.env_spec("myoElbowPose1D6MRandom-v0")
     assert kw["target_jnt_range"]["r_elbow_flex"] == [0, 2.27] and kw["reset_type"] == "random"
+
+
+def test_hot_blob_leaves_out_unreachable_lists():
+    """program.py: a model whose Newton Hessian is always dense (equalities across the tree) and whose integrator uses the dense
+    register Cholesky (8 <= nv <= 36) carries no sparse-LDL schedules; the hand (sparse path reachable) keeps them.  Per-muscle
+    parameter classes are 17 doubles wide (only the fields the kernel reads; odd stride)."""
+    from myosuite_b200 import assets, program
+    legs, _ = program.build_program(assets.load("myolegs"))
+    hand, _ = program.build_program(assets.load("myohand_pose"))
+    assert len(legs["PFT"]) == 0 and len(legs["PLV"]) == 0 and len(legs["PDS"]) == 0 and len(hand["PFT"]) > 0 and len(hand["PLV"]) > 0
+    assert program.PA_STRIDE == 17 and legs["PA_d"].shape[1] == 17 and hand["PA_d"].shape[1] == 17
+    m = assets.load("myohand_pose")
+    cls = np.asarray(hand["PA_cls"]); row = hand["PA_d"][cls[0]]
+    assert np.allclose(row[0:3], m.actuator_dynprm[0, :3]) and row[5] == m.actuator_gainprm[0, 4] and row[8] == m.actuator_gainprm[0, 8]
+    assert row[11] == m.actuator_biasprm[0, 5] and row[12] == m.actuator_biasprm[0, 7] and hand["PAM_d"][0, 0] == m.actuator_gainprm[0, 2]
