@@ -142,6 +142,11 @@ int myo_batch_forward_debug(myo_batch* b, const double* ctrl_dev /* [n, nu] */, 
 /* number of kernel launches issued by this batch so far (bench.py's gpu_launches claim) */
 int64_t myo_batch_launch_count(const myo_batch* b);
 
+/* Unit-test hook for the dense solver the Newton and integrator phases use: solves H x = b for `count` independent SPD systems
+ * (H_host: count x n(n+1)/2 packed lower triangles, row-major; x_host: count x n, rhs in / solution out; HOST pointers), one
+ * warp per system.  mode 1 = register/shuffle Cholesky (bordered for 32 < n <= 36), 0 = shared-memory variant.  n <= 64. */
+int myo_debug_chol_solve(int device, const double* H_host, double* x_host, int n, int count, int mode);
+
 #ifdef __cplusplus
 }
 #endif

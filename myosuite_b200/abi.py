@@ -41,7 +41,7 @@ class MyoBuffers(ctypes.Structure):
 
 EXPORTS = ["myo_last_error", "myo_version", "myo_model_from_blob", "myo_model_dims", "myo_model_destroy", "myo_batch_create",
            "myo_batch_bind", "myo_batch_destroy", "myo_batch_obs_dim", "myo_batch_reset", "myo_batch_step",
-           "myo_batch_forward_debug", "myo_batch_launch_count", "myo_batch_observe"]
+           "myo_batch_forward_debug", "myo_batch_launch_count", "myo_batch_observe", "myo_debug_chol_solve"]
 
 
 class MyoError(RuntimeError):
@@ -75,6 +75,7 @@ def lib():
         L.myo_batch_forward_debug.argtypes = [c_vp, c_vp, ctypes.c_int, c_vp]
         L.myo_batch_launch_count.argtypes = [c_vp]
         L.myo_batch_launch_count.restype = c_i64
+        L.myo_debug_chol_solve.argtypes = [ctypes.c_int, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         _LIB = L
     return _LIB
 
@@ -153,3 +154,11 @@ class Batch:
         if getattr(self, "handle", None):
             lib().myo_batch_destroy(self.handle)
             self.handle = None
+
+
+def debug_chol_solve(H_packed, rhs, mode=1, device=0):
+    """Solve count SPD systems with the kernel's dense solver (unit-test hook).  H_packed: [count, n(n+1)/2] lower triangles; rhs: [count, n]."""
+    H = np.ascontiguousarray(H_packed, dtype=np.float64); x = np.ascontiguousarray(rhs, dtype=np.float64).copy()
+    count, n = x.shape
+    _check(lib().myo_debug_chol_solve(device, H.ctypes.data, x.ctypes.data, n, count, mode))
+    return x

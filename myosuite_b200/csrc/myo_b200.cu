@@ -206,7 +206,7 @@ __device__ __forceinline__ void group_sync(int ngroups, int gid, int gthreads) {
   if (ngroups <= 1) __syncthreads(); else asm volatile("bar.sync %0, %1;" :: "r"(1 + gid), "r"(gthreads) : "memory"); }
 
 // ------------------------------------------------------------------ the kernel
-extern "C" __global__ void __launch_bounds__(384) myo_env_kernel(const __grid_constant__ DevModel m, const __grid_constant__ StepArgs a) {
+extern "C" __global__ void __launch_bounds__(320) myo_env_kernel(const __grid_constant__ DevModel m, const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) unsigned long long mbar;
   __shared__ int s_ncand[16];
@@ -441,7 +441,8 @@ extern "C" int myo_batch_create(const myo_model* m, int device, int n_env, const
   cudaDeviceProp prop; CUDA_OK(cudaGetDeviceProperties(&prop, device));
   b->const_bytes = b->dm.nD*8 + ((b->dm.nI16w + 1)/2)*8;
   int per = b->dm.n_per_warp*8, maxs = (int)prop.sharedMemPerBlockOptin - b->const_bytes - 64;
-  int wpc = maxs/per; if (wpc > 12) wpc = 12; if (wpc < 1) { delete b; return fail("model working set exceeds shared memory of one CTA"); }
+  int wpc = maxs/per; if (wpc > 10) wpc = 10;     // (__launch_bounds__(320): 204 registers per thread)
+  if (wpc < 1) { delete b; return fail("model working set exceeds shared memory of one CTA"); }
   const int wpc0 = wpc;
   if (n_env < wpc) wpc = n_env;
   { // wave quantisation: with one CTA per SM the batch takes ceil(n_env / (SMs * wpc)) rounds; among the warp counts that reach the
@@ -459,6 +460,30 @@ extern "C" int myo_batch_create(const myo_model* m, int device, int n_env, const
 extern "C" void myo_batch_destroy(myo_batch* b) { if (!b) return; cudaSetDevice(b->device); cudaFree(b->dI); cudaFree(b->dD); delete b; }
 extern "C" int myo_batch_obs_dim(const myo_batch* b) { return b ? b->obs_dim : -1; }
 extern "C" int64_t myo_batch_launch_count(const myo_batch* b) { return b ? b->launches : -1; }
+
+// ---- unit-test hook: the dense solver on caller-supplied systems (one warp per system, shared-memory staging like the step kernel)
+__global__ void myo_chol_test_kernel(const double* H, double* x, int n, int count, int mode) {
+  extern __shared__ __align__(16) double sm[];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, sys = blockIdx.x*(blockDim.x >> 5) + wid, nt = n*(n+1)/2;
+  double* h = sm + (size_t)wid*(nt + n + 2); double* v = h + nt;
+  if (sys < count) { for (int i = lane; i < nt; i += 32) h[i] = H[(size_t)sys*nt + i]; for (int i = lane; i < n; i += 32) v[i] = x[(size_t)sys*n + i]; }
+  __syncwarp();
+  if (sys < count) { chol_dense(h, n, v, lane, mode); for (int i = lane; i < n; i += 32) x[(size_t)sys*n + i] = v[i]; }
+}
+extern "C" int myo_debug_chol_solve(int device, const double* H_host, double* x_host, int n, int count, int mode) {
+  if (!H_host || !x_host || n < 1 || n > 64 || count < 1) return fail("myo_debug_chol_solve: bad arguments");
+  int ndev = 0; if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail("myo_debug_chol_solve: no such CUDA device");
+  CUDA_OK(cudaSetDevice(device));
+  const size_t nt = (size_t)n*(n+1)/2; double *dH = nullptr, *dx = nullptr;
+  CUDA_OK(cudaMalloc(&dH, nt*count*8)); CUDA_OK(cudaMalloc(&dx, (size_t)n*count*8));
+  CUDA_OK(cudaMemcpy(dH, H_host, nt*count*8, cudaMemcpyHostToDevice)); CUDA_OK(cudaMemcpy(dx, x_host, (size_t)n*count*8, cudaMemcpyHostToDevice));
+  const int wpb = 4; size_t smem = (size_t)wpb*(nt + n + 2)*8;
+  CUDA_OK(cudaFuncSetAttribute(myo_chol_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  myo_chol_test_kernel<<<(count + wpb - 1)/wpb, wpb*32, smem>>>(dH, dx, n, count, mode);
+  CUDA_OK(cudaGetLastError()); CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpy(x_host, dx, (size_t)n*count*8, cudaMemcpyDeviceToHost));
+  cudaFree(dH); cudaFree(dx); return 0;
+}
 
 extern "C" int myo_batch_bind(myo_batch* b, const myo_buffers* bufs) {
   if (!b || !bufs) return fail("myo_batch_bind: null");
