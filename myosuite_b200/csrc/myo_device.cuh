@@ -511,9 +511,9 @@ __device__ __forceinline__ void plane_sph(ConOut& o, double margin, const double
   o.n++; }
 
 __device__ __forceinline__ void collide_analytic(const DevModel& m, const Warp& w, int p, ConOut& o) {
-  const idx_t* pr = CI(PPAIR) + PPAIR_ISTRIDE*p; const double* pd = CD(PPAIR_d) + pr[6]*PPAIR_STRIDE; const double* G = CD(PG_d);
+  const idx_t* pr = CI(PPAIR) + PPAIR_ISTRIDE*p; const double* pd = CD(PPAIR_d) + pr[6]*PPAIR_STRIDE;
   int g1 = pr[0], g2 = pr[1], ct = pr[5]; double margin = pd[0]; o.n = 0; o.has_y = false;
-  const double* s1 = geom_size(m, w, g1); const double* s2 = geom_size(m, w, g2); (void)G;
+  const double* s1 = geom_size(m, w, g1); const double* s2 = geom_size(m, w, g2);
   double x1[3], a1[3], x2[3], a2[3]; geom_pose(m, w, g1, x1, a1); geom_pose(m, w, g2, x2, a2);
   if (ct == CT_CAP_CAP) {
     double r1 = s1[0], h1 = s1[1], r2 = s2[0], h2 = s2[1];
@@ -551,9 +551,9 @@ __device__ __forceinline__ void collide_analytic(const DevModel& m, const Warp& 
 }
 
 __device__ __forceinline__ void collide_ellipsoid(const DevModel& m, const Warp& w, int p, ConOut& o) {
-  const idx_t* pr = CI(PPAIR) + PPAIR_ISTRIDE*p; const double* pd = CD(PPAIR_d) + pr[6]*PPAIR_STRIDE; const double* G = CD(PG_d);
+  const idx_t* pr = CI(PPAIR) + PPAIR_ISTRIDE*p; const double* pd = CD(PPAIR_d) + pr[6]*PPAIR_STRIDE;
   int g1 = pr[0], g2 = pr[1], ct = pr[5]; double margin = pd[0]; o.n = 0; o.has_y = false;
-  const double* s1 = geom_size(m, w, g1); const double* s2 = geom_size(m, w, g2); (void)G;
+  const double* s1 = geom_size(m, w, g1); const double* s2 = geom_size(m, w, g2);
   double x1[3], a1[3], x2[3], a2[3]; geom_pose(m, w, g1, x1, a1); geom_pose(m, w, g2, x2, a2);
   if (ct == CT_CAP_ELL) {     // g1 capsule (segment + radius), g2 ellipsoid: min over the segment of the point-ellipsoid distance
     double r = s1[0], h = s1[1], dv[3] = {x2[0]-x1[0], x2[1]-x1[1], x2[2]-x1[2]};
@@ -607,8 +607,8 @@ __device__ __forceinline__ void collide_ellipsoid(const DevModel& m, const Warp&
 
 // cheap conservative test for the iterative (ellipsoid) colliders: can this pair be within its margin at all?
 __device__ __forceinline__ bool expensive_candidate(const DevModel& m, const Warp& w, int p) {
-  const idx_t* pr = CI(PPAIR) + PPAIR_ISTRIDE*p; const double* pd = CD(PPAIR_d) + pr[6]*PPAIR_STRIDE; const double* G = CD(PG_d);
-  int g1 = pr[0], g2 = pr[1]; const double* s1 = geom_size(m, w, g1); const double* s2 = geom_size(m, w, g2); double margin = pd[0]; (void)G;
+  const idx_t* pr = CI(PPAIR) + PPAIR_ISTRIDE*p; const double* pd = CD(PPAIR_d) + pr[6]*PPAIR_STRIDE;
+  int g1 = pr[0], g2 = pr[1]; const double* s1 = geom_size(m, w, g1); const double* s2 = geom_size(m, w, g2); double margin = pd[0];
   double x1[3], a1[3], x2[3], a2[3]; geom_pose(m, w, g1, x1, a1); geom_pose(m, w, g2, x2, a2);
   double dv[3] = {x2[0]-x1[0], x2[1]-x1[1], x2[2]-x1[2]}, rb2 = fmax(s2[0], fmax(s2[1], s2[2]));
   // any unit direction d gives a lower bound  d.(c2-c1) - h1(d) - h2(d)  on the signed distance: use the centre-to-centre
