@@ -195,7 +195,7 @@ __device__ void reach_observe(const DevModel& m, Warp& w, const StepArgs& a, int
 __device__ __noinline__ void task_observe(const DevModel& m, Warp& w, const StepArgs& a, int env, int steps, double tnow, double* rw, bool* done) {
   *rw = 0; *done = false;
   if (a.cfg.task == MYO_TASK_POSE) pose_reward_done(m, w, a, env, rw, done);
-  else if (a.cfg.task == MYO_TASK_WALK) { phase_kinematics(m, w); phase_tendon(m, w); phase_actuation(m, w, false, nullptr, nullptr); walk_observe(m, w, a, env, steps, rw, done); }
+  else if (a.cfg.task == MYO_TASK_WALK) { phase_kinematics(m, w); phase_tendon(m, w); phase_tendon_moments(m, w); phase_actuation(m, w, false, nullptr, nullptr); walk_observe(m, w, a, env, steps, rw, done); }
   else if (a.cfg.task == MYO_TASK_HOLD) { phase_kinematics(m, w); hold_observe(m, w, a, env, rw, done); }
   else if (a.cfg.task == MYO_TASK_REACH) { phase_kinematics(m, w); reach_observe(m, w, a, env, tnow, rw, done); }
   __syncwarp();
@@ -296,7 +296,7 @@ extern "C" __global__ void __launch_bounds__(320) myo_env_kernel(const __grid_co
     for (int s = 0; s < nsub; s++) {
       const bool tap = s == nsub-1;
       PH(0, phase_kinematics(m, w));
-      PH(1, phase_tendon(m, w); if (tap && b.tap_moment) { const double* mom = SCR(s_mom); for (int i = w.lane; i < m.nnz; i += 32) b.tap_moment[(size_t)env*m.nnz+i] = mom[i]; });
+      PH(1, phase_tendon(m, w); phase_tendon_moments(m, w); if (tap && b.tap_moment) { const double* mom = SCR(s_mom); for (int i = w.lane; i < m.nnz; i += 32) b.tap_moment[(size_t)env*m.nnz+i] = mom[i]; });
       PH(2, phase_actuation(m, w, integrate, tap && b.tap_actuator_force ? b.tap_actuator_force + (size_t)env*m.nu : nullptr, tap && b.tap_ten_length ? b.tap_ten_length + (size_t)env*m.nu : nullptr));
       PH(3, phase_body_inertia(m, w); phase_crb(m, w); phase_bias(m, w));
       PH(4, phase_collision(m, w));
@@ -309,7 +309,11 @@ extern "C" __global__ void __launch_bounds__(320) myo_env_kernel(const __grid_co
         } else if (live) collision_direct(m, w);
         if (prof) cyc[16] += clock64() - tc_; }
       PH(5, phase_constraints(m, w); if (tap) write_taps_contacts(m, w, a, env));
-      PH(6, phase_solve(m, w, a.tol, prof ? cyc : nullptr));
+      if (ngroups == 1 && m.solve_sync) {   // every warp enters the solver: its inner CTA barriers need the idle warps too
+        long long tb_ = prof ? clock64() : 0; if (bmask & (1 << 6)) __syncthreads(); long long t0_ = prof ? clock64() : 0;
+        phase_solve(m, w, a.tol, (prof && live) ? cyc : nullptr, live, true);
+        if (prof) cyc[6] += waitprof ? t0_ - tb_ : clock64() - t0_;
+      } else PH(6, phase_solve(m, w, a.tol, prof ? cyc : nullptr, true, false));
       PH(7, if (tap) write_taps_solve(m, w, a, env); if (integrate) phase_integrate(m, w, prof ? cyc : nullptr));
       if (w.ncon > maxcon_seen) maxcon_seen = w.ncon;
       if (w.nefc > maxefc_seen) maxefc_seen = w.nefc;
@@ -378,6 +382,7 @@ static void fill_devmodel(const myo_model* mm, const myo_task_cfg* cfg, DevModel
   const double* opt = MYO_DSEC(I, D, MYO_SEC_opt); d.timestep = opt[0]; d.gx = opt[1]; d.gy = opt[2]; d.gz = opt[3]; d.tolerance = opt[4]; d.meaninertia = opt[6];
   d.ovr_geom = (cfg && cfg->task == MYO_TASK_HOLD) ? cfg->task_i[1] : -1;
   { const char* e = getenv("MYO_B200_CHOL"); d.chol_mode = e ? atoi(e) : 1; }   // dense Cholesky (nv <= 32): 1 = unrolled register/shuffle version (default: 21 k cycles per 23x23 solve), 0 = rolled shared-memory version (49 k)
+  { const char* e = getenv("MYO_B200_SOLVE_SYNC"); d.solve_sync = e ? atoi(e) : 1; }   // CTA barriers inside the Newton loop (0 = warps run the solver phase unaligned)
   { const char* e = getenv("MYO_B200_COOP"); d.coop = e ? atoi(e) : 0; }     // ellipsoid candidates: 0 = inside the owning warp (default; 558k vs 548k on the hand), 1 = CTA-cooperative pass
   int mc = cfg && cfg->maxcon > 0 ? cfg->maxcon : 32; if (mc > 2*d.npair) mc = 2*d.npair; d.maxcon = mc; d.nlimrow = P[PD_NLIMROW] > 0 ? P[PD_NLIMROW] : 2*d.nlim; d.maxefc = d.neq + d.nlimrow + 4*mc;
   int o = 0;

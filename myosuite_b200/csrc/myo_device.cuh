@@ -40,7 +40,7 @@ struct DevModel {
   int32_t hoff[MYO_NSEC];                  // offset of each hot section (in shorts / doubles), -1 if not staged
   int32_t nq, nv, nu, na, nM, njnt;
   int32_t nbd, nlevel, nsp, nwe, nta, nnz, nlim, neq, npair, npair_an, maxpath, ndepth, eq_tree;
-  int32_t maxcon, maxefc, nlimrow, ovr_geom, ngc, s_gpose, coop, chol_mode;          // ovr_geom: collision geom whose size comes from the per-env overrides (-1: none)
+  int32_t maxcon, maxefc, nlimrow, ovr_geom, ngc, s_gpose, coop, chol_mode, solve_sync;          // ovr_geom: collision geom whose size comes from the per-env overrides (-1: none)
   double timestep, gx, gy, gz, meaninertia, tolerance;
   // per-warp shared-memory layout, in doubles.  Persistent part:
   int32_t o_qpos, o_qvel, o_act, o_ctrl, o_qws, o_dax, o_dan, o_qM, o_fsm, o_eprm, o_wz, nwz, o_scr, n_per_warp;
@@ -297,8 +297,7 @@ __device__ void wrap_element(const DevModel& m, const Warp& w, int k, double* U,
 }
 
 __device__ void phase_tendon(const DevModel& m, Warp& w) {
-  double* U = SCR(s_U); double* WP = SCR(s_WP); double* PL = SCR(s_PL); double* mom = SCR(s_mom);
-  double* tlen = SCR(s_tlen); double* tvel = SCR(s_tvel); double* tfrc = SCR(s_tfrc);
+  double* U = SCR(s_U); double* WP = SCR(s_WP); double* PL = SCR(s_PL);
   const idx_t* sp = CI(PSP);
   for (int k = w.lane; k < m.nsp; k += 32) { double a[3], b[3]; world_point(m, w, sp[2*k], a); world_point(m, w, sp[2*k+1], b);
     double dv[3] = {b[0]-a[0], b[1]-a[1], b[2]-a[2]}, n = sqrt(dot3(dv,dv));
@@ -307,6 +306,11 @@ __device__ void phase_tendon(const DevModel& m, Warp& w) {
   #pragma unroll 1
   for (int k = w.lane; k < m.nwe; k += 32) wrap_element(m, w, k, U, WP, PL);
   __syncwarp();
+}
+// second half: moments per structural non-zero, tendon lengths and velocities (a CTA barrier in between re-aligns the warps)
+__device__ void phase_tendon_moments(const DevModel& m, Warp& w) {
+  double* U = SCR(s_U); double* WP = SCR(s_WP); double* PL = SCR(s_PL); double* mom = SCR(s_mom);
+  double* tlen = SCR(s_tlen); double* tvel = SCR(s_tvel); double* tfrc = SCR(s_tfrc);
   const idx_t* nzd = CI(PNZ_dof); const idx_t* tadr = CI(PNZ_term_adr); const idx_t* term = CI(PTERM);
   for (int z = w.lane; z < m.nnz; z += 32) { int d = nzd[z]; double acc = 0;
     #pragma unroll 1

@@ -304,30 +304,40 @@ __device__ void ldl_solve(const DevModel& m, const Warp& w, const double* LD, co
 }
 
 // ------------------------------------------------------------------ Newton solver: leaves qacc in s.a
-__device__ void phase_solve(const DevModel& m, Warp& w, double tol, long long* cyc) {
+// Called by EVERY warp of the CTA when cta_sync is set (live = this warp holds an env): the warps still iterating are re-aligned by CTA
+// barriers at the top of each Newton iteration and before the Cholesky, so that they keep sharing instruction fetches inside the
+// phase too (a lone 23x23 register Cholesky costs 29 k cycles out of step with the other warps, 21 k in step); finished and idle
+// warps only take part in the barriers.  The total wait is unchanged: the CTA leaves the phase with its slowest env either way.
+__device__ void phase_solve(const DevModel& m, Warp& w, double tol, long long* cyc, bool live, bool cta_sync) {
   long long tc = cyc ? clock64() : 0;
   #define LAP(k) if (cyc) { long long t_ = clock64(); cyc[k] += t_ - tc; tc = t_; }
-  Solv s = solv_views(m, w); int n = m.nv, nefc = w.nefc; w.niter = 0;
-  if (nefc == 0) {   // unconstrained: qacc = M^-1 qfrc_smooth
+  Solv s = solv_views(m, w); int n = m.nv, nefc = live ? w.nefc : 0; w.niter = 0;
+  bool active = live;
+  if (live && nefc == 0) {   // unconstrained: qacc = M^-1 qfrc_smooth
     ldl_factor(m, w, w.qM, s.LD, s.Dinv);
     for (int i = w.lane; i < n; i += 32) { s.a[i] = w.fsm[i]; s.Ma[i] = w.fsm[i]; } __syncwarp();
-    ldl_solve(m, w, s.LD, s.Dinv, s.a); return; }
-  for (int i = w.lane; i < n; i += 32) s.a[i] = w.qws[i]; __syncwarp();
-  mul_M(m, w, s.Ma, s.a); rows_apply(m, w, s, s.a, s.jar); __syncwarp();
-  for (int r = w.lane; r < nefc; r += 32) s.jar[r] -= s.aref[r]; __syncwarp();
+    ldl_solve(m, w, s.LD, s.Dinv, s.a); active = false; }
+  if (active) {
+    for (int i = w.lane; i < n; i += 32) s.a[i] = w.qws[i]; __syncwarp();
+    mul_M(m, w, s.Ma, s.a); rows_apply(m, w, s, s.a, s.jar); __syncwarp();
+    for (int r = w.lane; r < nefc; r += 32) s.jar[r] -= s.aref[r]; __syncwarp(); }
   const double scale = 1.0/(m.meaninertia*(n > 1 ? n : 1));
   const idx_t* eq = CI(PEQ); const idx_t* pr = CI(PPAIR); const double* pd = CD(PPAIR_d); const idx_t* path = CI(PPATH);
   for (int iter = 0; iter < 50; iter++) {
+    if (cta_sync) { if (!__syncthreads_or(active ? 1 : 0)) break; } else if (!active) break;
+    bool dense = false;
+    if (active) {
     // gradient
     for (int i = w.lane; i < n; i += 32) s.g[i] = s.Ma[i]-w.fsm[i];
     for (int r = w.lane; r < nefc; r += 32) { double x = s.jar[r]; s.jv[r] = (r < m.neq || x < 0) ? s.D[r]*x : 0.0; }   // jv used as scratch weights
     __syncwarp(); rows_applyT_add(m, w, s, s.jv, s.g); __syncwarp();
     double gn = 0; for (int i = w.lane; i < n; i += 32) gn += s.g[i]*s.g[i]; gn = sqrt(warp_sum(gn));
     LAP(8)
-    if (scale*gn < tol) break;
+    if (scale*gn < tol) active = false; }
+    if (active) {
     if (cyc) cyc[14]++;
     // Hessian: tree-sparse L'DL when no contact row is active (limits/equalities keep M's sparsity), dense Cholesky otherwise
-    bool dense = (m.neq > 0 && !m.eq_tree);
+    dense = (m.neq > 0 && !m.eq_tree);
     for (int c = w.lane; c < w.ncon && !dense; c += 32) { int nr = s.cnrow[c], rb = s.crow[c]; for (int r = 0; r < nr; r++) if (s.jar[rb+r] < 0) dense = true; }
     dense = __any_sync(FULL, dense);
     for (int i = w.lane; i < n; i += 32) s.p[i] = -s.g[i];
@@ -364,9 +374,10 @@ __device__ void phase_solve(const DevModel& m, Warp& w, double tol, long long* c
           int di = path[q[3]+ei] >> 1, dj = path[q[3]+ej] >> 1; s.H[TRI(di,dj)] += wa0*b[0]+wa1*b[1]+wa2*b[2]; } }
       __syncwarp(); }
     LAP(9)
-    chol_dense(s.H, n, s.p, w.lane, m.chol_mode);
-    LAP(10)
-    }
+    } }
+    if (cta_sync) __syncthreads();
+    if (active) {
+    if (dense) { chol_dense(s.H, n, s.p, w.lane, m.chol_mode); LAP(10) }
     // exact line search along p
     mul_M(m, w, s.Mp, s.p); rows_apply(m, w, s, s.p, s.jv); __syncwarp();
     double ga = 0, gb = 0; for (int i = w.lane; i < n; i += 32) { ga += s.p[i]*(s.Ma[i]-w.fsm[i]); gb += s.p[i]*s.Mp[i]; } ga = warp_sum(ga); gb = warp_sum(gb);
@@ -379,14 +390,15 @@ __device__ void phase_solve(const DevModel& m, Warp& w, double tol, long long* c
       if (it > 0 && (an <= lo || (hi > 0 && an >= hi))) an = hi > 0 ? 0.5*(lo+hi) : 2*alpha+1;
       if (an == alpha) break;
       alpha = an; }
-    if (alpha == 0) break;   // no descent possible: converged to round-off
+    if (alpha == 0) active = false;   // no descent possible: converged to round-off
+    else {
     for (int i = w.lane; i < n; i += 32) { s.a[i] += alpha*s.p[i]; s.Ma[i] += alpha*s.Mp[i]; }
     // rows that switch between active and inactive along the step; with none the cost was exactly quadratic along p, the Newton
     // step (alpha = 1) lands on its minimum and the gradient vanishes to round-off: converged without another gradient pass
     bool flip = false;
     for (int r = w.lane; r < nefc; r += 32) { double x0 = s.jar[r], x1 = x0 + alpha*s.jv[r]; s.jar[r] = x1; if (r >= m.neq && (x0 < 0) != (x1 < 0)) flip = true; }
     __syncwarp(); w.niter = iter+1; LAP(11)
-    if (!__any_sync(FULL, flip)) break; }
+    if (!__any_sync(FULL, flip)) active = false; } } }
   #undef LAP
 }
 
