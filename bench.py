@@ -66,7 +66,7 @@ class ClockSampler:
 def _cpu_worker(args):
     """One host core: a single env stepped in a loop (reference protocol:
     /root/reference/benchmarks/mjx_benchmark_baseline.py:8-25 -- gym.make, reset, timeit(env.step(random action)))."""
-    env_id, n_steps, seed = args
+    env_id, budget_s, seed = args          # budget_s: wall-clock seconds of stepping (a bounded sample; the oracle's rate varies 10x with the contact load)
     import numpy as np
     from myosuite_b200 import assets, blob, vec_env
     from oracle import env_oracle
@@ -78,7 +78,8 @@ def _cpu_worker(args):
     q = m.qpos0.copy()
     t0 = time.perf_counter()
     pose = "Pose" in env_id
-    for s in range(n_steps):
+    s = 0
+    while time.perf_counter() - t0 < budget_s:
         if s % steps == 0:
             o.reset()
             if pose:
@@ -93,18 +94,20 @@ def _cpu_worker(args):
             env_oracle.pose_obs(o.f("qpos"), o.f("qvel"), o.f("act"), q, 0.02)
         else:
             o.forward()          # the reference's extra mj_forward for the observed data (robot.py:607)
-    return time.perf_counter() - t0
+        s += 1
+    return s, time.perf_counter() - t0
 
 
-def cpu_baseline(env_id, n_steps, threads=1):
-    """env-steps/s of `threads` independent single-env loops of the oracle port, one process per host core.  The stepping loops
-    run concurrently; the rate is total steps / the slowest worker's loop time (process start-up and model load excluded)."""
+def cpu_baseline(env_id, budget_s, threads=1):
+    """(env-steps/s, total steps) of `threads` independent single-env loops of the oracle port, one process per host core, each stepping
+    for budget_s seconds of wall clock; the rate is total steps / the slowest worker's loop time (process start-up and model load excluded)."""
     if threads == 1:
-        return n_steps / _cpu_worker((env_id, n_steps, 0))
+        n, t = _cpu_worker((env_id, budget_s, 0))
+        return n / t, n
     import multiprocessing as mp
     with mp.get_context("fork").Pool(threads) as pool:
-        times = pool.map(_cpu_worker, [(env_id, n_steps, i) for i in range(threads)])
-    return threads * n_steps / max(times)
+        res = pool.map(_cpu_worker, [(env_id, budget_s, i) for i in range(threads)])
+    return sum(r[0] for r in res) / max(r[1] for r in res), sum(r[0] for r in res)
 
 
 def main():
@@ -131,16 +134,16 @@ def main():
         from oracle import oracle_py
         oracle_py.build()
         thr = max(1, cores)
-        rate1 = cpu_baseline(args.env, 10, threads=1)      # calibrate, then size the bounded sample to ~8 s of stepping per core
-        per_thread = int(max(20, min(20000, 2.5 * rate1)))   # ~2.5 s of stepping per core at the unloaded rate (longer once all cores are busy)
+        budget = 8.0                                           # bounded sample: every host core steps its own env for 8 s
         t0 = time.perf_counter()
-        v = cpu_baseline(args.env, per_thread, threads=thr)
+        v, total = cpu_baseline(args.env, budget, threads=thr)
         ms = (time.perf_counter() - t0) * 1e3
-        sample = "%d threads x %d env-steps of %s (1 env each, random actions, reset every episode)" % (thr, per_thread, args.env)
-        print(json.dumps({"impl": "reference", "metric": "env-steps/sec (random actions)", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
+        per_thread = max(total // thr, 1)
+        sample = "%d threads x %.0f s of stepping = %d env-steps of %s (1 env each, random actions, reset every episode)" % (thr, budget, total, args.env)
+        print(json.dumps({"impl": "reference", "metric": "env-steps/sec (random actions, 4096 envs/GPU)", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": W, "ms_per_step": ms / max(per_thread, 1), "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                          "config": {"workload": "%s, single-env CPU loop per host thread" % args.env},
+                          "config": {"workload": "%s, frame_skip 10, random actions U[-1,1], reset every episode; CPU arm: one single-env loop of the oracle port per host thread" % args.env},
                           "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": thr, "kind": "port", "sample": sample},
                           "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
@@ -231,10 +234,8 @@ def main():
         if not args.no_cpu_baseline:
             from oracle import oracle_py
             oracle_py.build()
-            rate1 = cpu_baseline(args.env, 10, threads=1)          # calibrate, then a bounded sample of ~10 s of single-thread stepping
-            nst = int(max(20, min(200000, 10.0 * rate1)))
             t0 = time.perf_counter()
-            v = cpu_baseline(args.env, nst, threads=1)
+            v, nst = cpu_baseline(args.env, 10.0, threads=1)         # bounded sample: 10 s of single-thread stepping
             line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
                                     "sample": "%d env-steps of %s, 1 env, 1 thread (%.1f s)" % (nst, args.env, time.perf_counter() - t0)}
         print(json.dumps(line))
