@@ -134,7 +134,7 @@ def main():
         from oracle import oracle_py
         oracle_py.build()
         thr = max(1, cores)
-        budget = 8.0                                           # bounded sample: every host core steps its own env for 8 s
+        budget = float(os.environ.get("MYO_BENCH_CPU_BUDGET_S", 8.0))      # bounded sample: every host core steps its own env for 8 s
         t0 = time.perf_counter()
         v, total = cpu_baseline(args.env, budget, threads=thr)
         ms = (time.perf_counter() - t0) * 1e3
@@ -235,7 +235,7 @@ def main():
             from oracle import oracle_py
             oracle_py.build()
             t0 = time.perf_counter()
-            v, nst = cpu_baseline(args.env, 10.0, threads=1)         # bounded sample: 10 s of single-thread stepping
+            v, nst = cpu_baseline(args.env, float(os.environ.get("MYO_BENCH_CPU_BUDGET_S", 10.0)), threads=1)         # bounded sample: 10 s of single-thread stepping
             line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
                                     "sample": "%d env-steps of %s, 1 env, 1 thread (%.1f s)" % (nst, args.env, time.perf_counter() - t0)}
         print(json.dumps(line))

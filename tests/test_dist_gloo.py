@@ -43,3 +43,20 @@ def test_env_sharding_and_return_gather_world2():
     for rank, g, tmax in res:
         np.testing.assert_array_equal(g, exp)           # every rank sees all returns in global env order, no overlap / gap
         assert tmax == world
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) prints one JSON line with the contract's keys;
+    under torchrun only rank 0 prints.  Runs on the host cores (oracle port), no GPU needed."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MYO_BENCH_CPU_BUDGET_S="0.5")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "3"], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    env2 = dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out2 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True, text=True, env=env2, timeout=120)
+    assert out2.returncode == 0 and out2.stdout.strip() == ""
