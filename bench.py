@@ -8,9 +8,9 @@ MyoVecEnv.step_host (pinned host action -> H2D, step, D2H of obs/reward/done ins
 Reference arm (--impl reference): the reference's CPU implementation of the path on the host cores.  MuJoCo
 is not installable here (no network, not in /opt/wheelhouse), so this is the CPU oracle port
 (oracle/libmyo_oracle.so) -- labelled kind="port".
-Each env differs (per-env random state and actions); the working set lives in shared memory, HBM traffic per
-step is the compulsory state/action/obs I/O only, so L2 flushing between steps is irrelevant to the timing
-(config.l2 = "state+io larger than one step's reuse; no inter-step reuse exploited").
+Each env differs (per-env random state and actions); the working set lives in shared memory and the HBM traffic per
+step is the compulsory state/action/obs I/O (8 MB for 4096 hand envs, smaller than L2), so L2 is evicted between
+timed steps by a 192 MiB write inside the timed region (config.l2; --no-l2-flush turns it off; it costs < 1 %).
 """
 import argparse
 import json
@@ -119,6 +119,7 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=4096)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-l2-flush", action="store_true", help="do not evict L2 between timed steps (default: a 192 MiB write per step)")
     ap.add_argument("--barrier-mode", type=int, default=0)
     ap.add_argument("--lockstep-groups", type=int, default=0)
     ap.add_argument("--solver-tolerance", type=float, default=0.0, help="Newton stop (scaled gradient); 0 = library default")
@@ -166,6 +167,13 @@ def main():
     ring = [(torch.rand(n, nu, device=env.device, generator=gen) * 2 - 1) for _ in range(16)]
     ring_host = [r.cpu().pin_memory() for r in ring]
 
+    # L2 (126 MB) is evicted between timed steps by writing a 192 MiB buffer: step k+1 reads the state step k wrote from HBM, not from L2
+    flush_buf = None if args.no_l2_flush else torch.empty(192 << 20, dtype=torch.uint8, device=env.device)
+
+    def flush_l2(i):
+        if flush_buf is not None:
+            flush_buf.fill_(i & 1)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -181,6 +189,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(args.steps):
+        flush_l2(i)
         env.step(ring[i % 16])
     ev1.record()
     barrier()
@@ -193,6 +202,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
+        flush_l2(i)
         env.step_host(ring_host[i % 16])
     e1.record()
     barrier()
@@ -225,7 +235,7 @@ def main():
                 "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "impl": "b200",
                 "config": {"workload": "%s, %d envs/GPU, frame_skip 10, random actions U[-1,1], auto-reset" % (args.env, n),
-                           "l2": "no inter-step reuse exploited; per-env working set lives in shared memory", "parallelism": "env-sharded x%d, no data-path collective" % world},
+                           "l2": ("not flushed (--no-l2-flush)" if args.no_l2_flush else "flushed between timed steps: a 192 MiB write per step inside the timed region (inputs, 8 MB of state per step, are smaller than L2)"), "parallelism": "env-sharded x%d, no data-path collective" % world},
                 "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": n * nu * 4, "d2h_bytes_per_step": n * (env.obs_dim * 4 + 4 + 1)},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
