@@ -1,7 +1,7 @@
 // myo_solver.cuh -- constraint assembly, primal Newton solver and semi-implicit Euler (one env per warp).
 // Semantics: MuJoCo's soft-constraint model: rows = joint equalities, joint
 // limits, pyramidal/frictionless contacts; cost 1/2 (a-a0)'M(a-a0) + sum_i s_i(J_i a - aref_i);
-// Newton with exact line search on H = M + J' D_active J (dense Cholesky in shared memory).
+// Newton with exact line search on H = M + J' D_active J (register/shuffle Cholesky of the dense packed H; tree-sparse L'DL when no contact is active).
 #pragma once
 #include "myo_device.cuh"
 
