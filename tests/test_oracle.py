@@ -247,3 +247,33 @@ def test_mujoco_goldens_if_present(models):
             scale = np.abs(G["qacc"][i]).max() + 1e-9
             assert np.abs(o.f("qacc") - G["qacc"][i]).max() <= 1e-5 * scale
             np.testing.assert_allclose(o.f("actuator_force"), G["actuator_force"][i], rtol=1e-5, atol=1e-5 * np.abs(G["actuator_force"][i]).max())
+
+
+@pytest.mark.parametrize("name", ["myoelbow_1dof6muscles", "myohand_pose"])
+def test_oracle_coriolis_from_mass_matrix_derivatives(models, name):
+    """Velocity-dependent bias forces against their textbook definition from the (independently checked) mass matrix:
+    c_i = sum_jk (dM_ij/dq_k - 1/2 dM_jk/dq_i) qd_j qd_k, with dM/dq by central differences.  Hinge/slide models (nq == nv)."""
+    m = models[name]
+    assert m.nq == m.nv
+    o = Oracle(*blob.pack(m))
+    rng = np.random.default_rng(3)
+    q = _rand_state(m, rng, margin=0.25)
+    qd = rng.normal(0, 2.0, m.nv)
+    z = np.zeros(m.na)
+
+    def fwd(qq, vv):
+        o.reset(); o.set(qpos=qq, qvel=vv, act=z, ctrl=np.zeros(m.nu)); o.forward()
+        return o.f("qfrc_bias").copy(), _dense_M(m, o.f("qM").copy())
+
+    b1, _ = fwd(q, qd)
+    b0, _ = fwd(q, np.zeros(m.nv))
+    c = b1 - b0                                            # Coriolis + centrifugal part (gravity removed)
+    eps = 1e-5
+    dM = np.zeros((m.nv, m.nv, m.nv))                      # dM[k] = dM/dq_k
+    for k in range(m.nv):
+        qa = q.copy(); qa[m.jnt_qposadr[m.dof_jntid[k]]] += eps
+        qb = q.copy(); qb[m.jnt_qposadr[m.dof_jntid[k]]] -= eps
+        dM[k] = (fwd(qa, np.zeros(m.nv))[1] - fwd(qb, np.zeros(m.nv))[1]) / (2 * eps)
+    Mdot = np.einsum("kij,k->ij", dM, qd)
+    ref = Mdot @ qd - 0.5 * np.einsum("j,ijk,k->i", qd, dM, qd)
+    np.testing.assert_allclose(c, ref, rtol=2e-5, atol=2e-7 * max(1.0, np.abs(ref).max()))
