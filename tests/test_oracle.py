@@ -277,3 +277,106 @@ def test_oracle_coriolis_from_mass_matrix_derivatives(models, name):
     Mdot = np.einsum("kij,k->ij", dM, qd)
     ref = Mdot @ qd - 0.5 * np.einsum("j,ijk,k->i", qd, dM, qd)
     np.testing.assert_allclose(c, ref, rtol=2e-5, atol=2e-7 * max(1.0, np.abs(ref).max()))
+
+
+# ----------------------------------------------------------------------------- contacts: independent geometry and Jacobian checks
+def _point_ellipsoid_dist(y, a):
+    """Distance from point y (ellipsoid frame) to the ellipsoid with semi-axes a, y outside.  Classical Lagrange-multiplier root:
+    closest point x_i = a_i^2 y_i / (a_i^2 + t) with sum (a_i y_i / (a_i^2 + t))^2 = 1, t > 0 (independent of the oracle's search)."""
+    from scipy.optimize import brentq
+    f = lambda t: np.sum((a * y / (a * a + t)) ** 2) - 1.0
+    assert f(0.0) > 0                                     # outside
+    hi = 1.0
+    while f(hi) > 0:
+        hi *= 4
+    t = brentq(f, 0.0, hi, xtol=1e-18, rtol=1e-15, maxiter=500)
+    x = a * a * y / (a * a + t)
+    return np.linalg.norm(y - x)
+
+
+def _capsule(o, m, g):
+    X = o.f("geom_xmat").reshape(-1, 9)[g].reshape(3, 3); c = o.f("geom_xpos").reshape(-1, 3)[g]
+    return c, X[:, 2], m.geom_size[g, 0], m.geom_size[g, 1]
+
+
+def _pair_distance(o, m, g1, g2):
+    """Signed distance of a capsule-capsule or capsule-ellipsoid pair by an independent route (scipy)."""
+    from scipy.optimize import minimize, minimize_scalar
+    c1, a1, r1, h1 = _capsule(o, m, g1)
+    if m.geom_type[g2] == 3:
+        c2, a2, r2, h2 = _capsule(o, m, g2)
+        f = lambda p: np.linalg.norm((c1 + a1 * p[0]) - (c2 + a2 * p[1]))
+        best = min((minimize(f, [s, t], bounds=[(-h1, h1), (-h2, h2)], method="L-BFGS-B", options=dict(ftol=1e-18, gtol=1e-14)).fun
+                    for s in (-h1, 0, h1) for t in (-h2, 0, h2)))
+        return best - r1 - r2
+    X2 = o.f("geom_xmat").reshape(-1, 9)[g2].reshape(3, 3); c2 = o.f("geom_xpos").reshape(-1, 3)[g2]; a = m.geom_size[g2].copy()
+    f = lambda t: _point_ellipsoid_dist(X2.T @ (c1 + a1 * t - c2), a)
+    res = minimize_scalar(f, bounds=(-h1, h1), method="bounded", options=dict(xatol=1e-13))
+    return min(res.fun, f(-h1), f(h1)) - r1
+
+
+def _hand_states_with_contacts(m, o, rng, want=12):
+    out = []
+    while len(out) < want:
+        q = _rand_state(m, rng, margin=-0.02)
+        o.reset(); o.set(qpos=q, qvel=np.zeros(m.nv), act=np.zeros(m.na), ctrl=np.zeros(m.nu)); o.forward()
+        if o.ncon:
+            out.append(q)
+    return out
+
+
+def test_oracle_contact_distances_independent(models):
+    """Signed distances of the reported capsule-capsule and capsule-ellipsoid contacts against scipy (segment-segment minimisation;
+    point-ellipsoid distance by its Lagrange root, minimised over the segment).  Ellipsoid cases are checked where the capsule axis
+    stays outside the ellipsoid (the regime the colliders are specified for)."""
+    m = models["myohand_pose"]
+    o = Oracle(*blob.pack(m))
+    rng = np.random.default_rng(11)
+    n_cc = n_ce = 0
+    for q in _hand_states_with_contacts(m, o, rng, want=10):
+        o.reset(); o.set(qpos=q, qvel=np.zeros(m.nv), act=np.zeros(m.na), ctrl=np.zeros(m.nu)); o.forward()
+        g1s, g2s, ds = o.i("con_geom1").copy(), o.i("con_geom2").copy(), o.f("con_dist").copy()
+        for g1, g2, d in zip(g1s, g2s, ds):
+            if m.geom_type[g1] != 3 or m.geom_type[g2] not in (3, 4):
+                continue
+            if m.geom_type[g2] == 4:
+                if d < -0.5 * m.geom_size[g1, 0]:
+                    continue                                # deep overlap: outside the specified regime
+                n_ce += 1
+            else:
+                n_cc += 1
+            np.testing.assert_allclose(d, _pair_distance(o, m, int(g1), int(g2)), rtol=0, atol=2e-9)
+    assert n_cc >= 10 and n_ce >= 2
+
+
+def test_oracle_contact_normal_jacobian_fd(models):
+    """Normal row of every contact Jacobian = derivative of that pair's signed distance w.r.t. the joint angles (central differences):
+    checks witness points, normals and the dof paths of the contact rows, capsule and ellipsoid colliders alike."""
+    m = models["myohand_pose"]
+    o = Oracle(*blob.pack(m))
+    rng = np.random.default_rng(12)
+    checked = 0
+    for q in _hand_states_with_contacts(m, o, rng, want=4):
+        o.reset(); o.set(qpos=q, qvel=np.zeros(m.nv), act=np.zeros(m.na), ctrl=np.zeros(m.nu)); o.forward()
+        ncon, nefc = o.ncon, o.nefc
+        g1s, g2s, ds = o.i("con_geom1").copy(), o.i("con_geom2").copy(), o.f("con_dist").copy()
+        J = o.f("efc_J").reshape(nefc, m.nv).copy()
+        assert (nefc - 4 * ncon) >= 0                       # condim-3 pyramids: 4 rows per contact, after the limit rows
+        Jc = J[nefc - 4 * ncon:].reshape(ncon, 4, m.nv)
+        Jn = 0.5 * (Jc[:, 0] + Jc[:, 1])                    # (n + mu t1) and (n - mu t1) average to the normal row
+        margin = 0.001
+        sel = [c for c in range(ncon) if ds[c] < margin - 3e-4 and (m.geom_type[g2s[c]] != 4 or ds[c] > -0.5 * m.geom_size[g1s[c], 0])]
+        fd = np.zeros((len(sel), m.nv)); eps = 1e-6
+        for k in range(m.nv):
+            dd = []
+            for sgn in (+1, -1):
+                qq = q.copy(); qq[m.jnt_qposadr[m.dof_jntid[k]]] += sgn * eps
+                o.reset(); o.set(qpos=qq, qvel=np.zeros(m.nv), act=np.zeros(m.na), ctrl=np.zeros(m.nu)); o.forward()
+                pairs = {(int(a), int(b)): float(x) for a, b, x in zip(o.i("con_geom1"), o.i("con_geom2"), o.f("con_dist"))}
+                dd.append([pairs.get((int(g1s[c]), int(g2s[c])), np.nan) for c in sel])
+            fd[:, k] = (np.array(dd[0]) - np.array(dd[1])) / (2 * eps)
+        ok = ~np.isnan(fd).any(axis=1)
+        assert ok.sum() >= max(1, len(sel) - 1)
+        np.testing.assert_allclose(Jn[np.array(sel)[ok]], fd[ok], rtol=0, atol=5e-7)
+        checked += int(ok.sum())
+    assert checked >= 8
