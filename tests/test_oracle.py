@@ -380,3 +380,22 @@ def test_oracle_contact_normal_jacobian_fd(models):
         np.testing.assert_allclose(Jn[np.array(sel)[ok]], fd[ok], rtol=0, atol=5e-7)
         checked += int(ok.sum())
     assert checked >= 8
+
+
+@pytest.mark.parametrize("name", ["myoelbow_1dof6muscles", "myohand_pose"])
+def test_oracle_euler_step_from_forward_outputs(models, name):
+    """One mj_step equals semi-implicit Euler with implicit joint damping applied to the forward pass's own outputs:
+    qvel' = qvel + h (M + h diag(damping))^-1 M qacc ; qpos' = qpos + h qvel' ; act' = act + h act_dot ; time' = time + h."""
+    m = models[name]
+    o = Oracle(*blob.pack(m))
+    rng = np.random.default_rng(21)
+    q = _rand_state(m, rng, margin=0.2)
+    v, a, u = rng.normal(0, 1.0, m.nv), rng.uniform(0, 1, m.na), rng.uniform(0, 1, m.nu)
+    o.reset(); o.set(qpos=q, qvel=v, act=a, ctrl=u); o.forward()
+    M = _dense_M(m, o.f("qM").copy()); qacc = o.f("qacc").copy(); adot = o.f("act_dot").copy(); h = m.opt_timestep
+    o.reset(); o.set(qpos=q, qvel=v, act=a, ctrl=u); o.step(1)
+    v1 = v + h * np.linalg.solve(M + h * np.diag(m.dof_damping), M @ qacc)
+    np.testing.assert_allclose(o.f("qvel"), v1, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(o.f("qpos"), q + h * v1, rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(o.f("act"), a + h * adot, rtol=1e-12, atol=1e-14)
+    assert o.f("time")[0] == pytest.approx(h)
