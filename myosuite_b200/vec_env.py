@@ -278,6 +278,13 @@ class MyoVecEnv:
                 self.t[name][:, : np.shape(v)[-1]] = torch.as_tensor(np.asarray(v), dtype=torch.float64, device=self.device)
         self.t["qacc_warmstart"].zero_()
 
+    def task_info(self):
+        """`rwd_sparse` / `solved` of the current observations (the reference's info dict, env_base.py:585-616), derived lazily from obs."""
+        from . import task_info
+        m = self.mj_model
+        return task_info.info_from_obs(self.task, self.t["obs"], m.nq, m.nv, m.na, pose_thd=float(self.cfg.pose_thd),
+                                       ntip=len(getattr(self, "tip_names", ())) or None)
+
     def refresh_obs(self):
         """obs / reward / done of the current state (the reference's env.forward(), env_base.py:393-432)."""
         self.batch.observe(stream=self._stream())
