@@ -129,3 +129,22 @@ def test_hot_blob_leaves_out_unreachable_lists():
     cls = np.asarray(hand["PA_cls"]); row = hand["PA_d"][cls[0]]
     assert np.allclose(row[0:3], m.actuator_dynprm[0, :3]) and row[5] == m.actuator_gainprm[0, 4] and row[8] == m.actuator_gainprm[0, 8]
     assert row[11] == m.actuator_biasprm[0, 5] and row[12] == m.actuator_biasprm[0, 7] and hand["PAM_d"][0, 0] == m.actuator_gainprm[0, 2]
+
+
+def test_program_invariants_the_kernel_relies_on():
+    """Structural promises of program.py that device code depends on without checking:
+    * every collision pair lists its dofs in strictly ascending order (the J'WJ assembly maps entry (ei >= ej) to H[di >= dj]);
+    * analytic pairs come first, iterative (ellipsoid) pairs after, and P_dims records the split;
+    * the number of limit rows that can be active at once bounds the row arrays (one per limited joint unless range < 2 margin)."""
+    from myosuite_b200 import assets, program
+    for name in ("myohand_pose", "myohand_hold", "myolegs"):
+        p, _ = program.build_program(assets.load(name))
+        pairs = np.asarray(p["PPAIR"]).reshape(-1, program.PPAIR_ISTRIDE); path = np.asarray(p["PPATH"])
+        for q in pairs:
+            d = path[q[3]:q[3] + q[4]] >> 1
+            assert np.all(np.diff(d) > 0), (name, q)
+        ct = pairs[:, 5]; n_an = int(p["P_dims"][program.PD_NPAIR_ANALYTIC])
+        assert np.all(ct[:n_an] < program.CT_CAP_ELL) and np.all(ct[n_an:] >= program.CT_CAP_ELL)
+        lim = np.asarray(p["PLIM_d"]).reshape(-1, program.PLIM_STRIDE)
+        expect = sum(2 if (r[1] - r[0]) < 2 * r[2] else 1 for r in lim)
+        assert int(p["P_dims"][program.PD_NLIMROW]) == expect and expect >= len(lim)
