@@ -1,10 +1,10 @@
 """Find the first substep where GPU and oracle diverge (developer tool)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from myosuite_b200 import vec_env
 from oracle.oracle_py import Oracle
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
 from test_gpu_parity import _states, relerr
 seed = int(sys.argv[1]) if len(sys.argv) > 1 else 12; NS = int(sys.argv[2]) if len(sys.argv) > 2 else 10; NE = int(sys.argv[3]) if len(sys.argv) > 3 else 16
 env = vec_env.MyoVecEnv("myoHandPoseRandom-v0", 64, taps=True, maxcon=48); m = env.mj_model; n = 64

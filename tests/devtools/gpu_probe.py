@@ -1,6 +1,6 @@
 """GPU parity + timing probe (developer tool; run under gpurun).  Compares the CUDA path with the CPU oracle."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from myosuite_b200 import vec_env, blob
 from oracle.oracle_py import Oracle

@@ -2,7 +2,7 @@
 NPG baselines (myosuite/agents/baslines_NPG/<env>/*/*/logs/log.csv) sampled 96 trajectories of a freshly initialised Gaussian MLP
 policy (output layer scaled 1e-2 => mean action ~ 0, init_log_std = -0.25) on MuJoCo + the reference env code, and logged the mean /
 std / max / min return and the success rate.  This script replays that protocol on this repo's CPU oracle + env logic (test
-infrastructure; no GPU) and prints the same statistics:   python tools/npg_iter0_check.py [env_id] [n_traj]
+infrastructure, hence under tests/; no GPU) and prints the same statistics:   python tests/devtools/npg_iter0_check.py [env_id] [n_traj]
 Reference values (3 seeds each, nearly identical because the env seeds coincide):
   myoElbowPose1D6MRandom-v0: mean 65.5 / 61.3 / 63.0, std 191 / 189 / 191, max 632.9, min -162.3, success 55.2 / 54.2 / 54.2 %
   myoHandPoseRandom-v0:      mean -336.1, std 28.0-28.2, max -265.8, min -408.6, success 0 %
@@ -19,7 +19,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 

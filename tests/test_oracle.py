@@ -432,10 +432,10 @@ def test_statistical_drop_in_vs_reference_npg_logs():
     of the committed NPG baselines (myosuite/agents/baslines_NPG/<env>/*/*/logs/log.csv; 96 trajectories of a freshly initialised
     Gaussian policy: mean ~ 0, log_std -0.25, job_config.yaml) logged for myoHandPoseRandom-v0 mean return -336.1, std 28.1,
     max -265.8, min -408.6, success 0 %, and for myoElbowPose1D6MRandom-v0 mean 61-65, std 189-191, success 54-55 %.
-    The same protocol on this repo's oracle + env logic (tools/npg_iter0_check.py; full-size run: hand -335.8 / 29.8 / -266.5 /
+    The same protocol on this repo's oracle + env logic (tests/devtools/npg_iter0_check.py; full-size run: hand -335.8 / 29.8 / -266.5 /
     -403.7 / 0 %, elbow 62.9 / 187 / 58 %) must land inside sampling error of those."""
     import os, sys
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "devtools"))
     import npg_iter0_check as chk
     h = chk.run("myoHandPoseRandom-v0", 48, seed=1)
     assert abs(h["mean"] + 336.1) < 15 and 18 < h["std"] < 42 and h["success_pct"] == 0 and h["max"] < -200 and h["min"] > -470, h
