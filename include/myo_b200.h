@@ -103,7 +103,7 @@ typedef struct {
   double* tap_moment;        /* [n, nnz] structural non-zeros of the tendon moment */
   double* tap_qM;            /* [n, nM] */
   long long* tap_phase_cycles; /* [n, 20] SM-clock cycles per phase over the call (profiling aid; 8-11 solver parts, 12,13: max ncon / nefc, 14,15: Newton iterations / dense ones, 16: cooperative collision, 17: load..substeps) */
-  void* reserved[1];
+  int32_t* overflow;         /* [n] nullable: sticky flag, set when a substep of this env dropped contacts (more than maxcon, or more ellipsoid candidates than the list holds); cleared by the env's reset */
 } myo_buffers;
 
 const char* myo_last_error(void);
@@ -144,7 +144,8 @@ int64_t myo_batch_launch_count(const myo_batch* b);
 
 /* Unit-test hook for the dense solver the Newton and integrator phases use: solves H x = b for `count` independent SPD systems
  * (H_host: count x n(n+1)/2 packed lower triangles, row-major; x_host: count x n, rhs in / solution out; HOST pointers), one
- * warp per system.  mode 1 = register/shuffle Cholesky (bordered for 32 < n <= 36), 0 = shared-memory variant.  n <= 64. */
+ * warp per system (row-in-registers / column-through-shared-memory L D L' for n <= 32, bordered register Cholesky for 32 < n <= 36, shared-memory
+ * fallback above).  `mode` is ignored (kept for ABI stability).  n <= 64. */
 int myo_debug_chol_solve(int device, const double* H_host, double* x_host, int n, int count, int mode);
 
 #ifdef __cplusplus

@@ -32,11 +32,11 @@ class MyoTaskCfg(ctypes.Structure):
 BUFFER_FIELDS = ["action", "qpos", "qvel", "act", "qacc_warmstart", "time", "fatigue", "target", "target_range", "init_qpos", "init_qvel", "env_prm",
                  "step_count", "episode_count", "obs", "reward", "done", "truncated", "ep_return", "last_return",
                  "tap_qacc", "tap_actuator_force", "tap_ten_length", "tap_qfrc_smooth", "tap_ncon", "tap_contact_pair",
-                 "tap_contact_dist", "tap_moment", "tap_qM", "tap_phase_cycles"]
+                 "tap_contact_dist", "tap_moment", "tap_qM", "tap_phase_cycles", "overflow"]
 
 
 class MyoBuffers(ctypes.Structure):
-    _fields_ = [(n, c_vp) for n in BUFFER_FIELDS] + [("reserved", c_vp * 1)]
+    _fields_ = [(n, c_vp) for n in BUFFER_FIELDS]
 
 
 EXPORTS = ["myo_last_error", "myo_version", "myo_model_from_blob", "myo_model_dims", "myo_model_destroy", "myo_batch_create",

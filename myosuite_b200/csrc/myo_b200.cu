@@ -22,43 +22,44 @@ struct StepArgs {
 };
 
 // ------------------------------------------------------------------ Philox4x32-10 (counter-based RNG, one stream per (seed, env, episode))
-struct Philox { uint32_t c[4], k[2]; uint32_t out[4]; int have; };
-__device__ __forceinline__ void philox_round(uint32_t* c, const uint32_t* k) {
-  uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u*c[0], hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u*c[2];
-  uint32_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0; c[0]=n0; c[1]=n1; c[2]=n2; c[3]=n3; }
+struct Philox { uint32_t c0, c1, c2, c3, k0, k1, o0, o1, o2, o3; int have; };   // scalars only: indexed arrays would live in local memory
 __device__ __forceinline__ void philox_gen(Philox& p) {
-  uint32_t c[4] = {p.c[0], p.c[1], p.c[2], p.c[3]}, k[2] = {p.k[0], p.k[1]};
-  for (int r = 0; r < 10; r++) { philox_round(c, k); k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u; }
-  p.out[0]=c[0]; p.out[1]=c[1]; p.out[2]=c[2]; p.out[3]=c[3]; p.have = 4; if (++p.c[0] == 0) ++p.c[1]; }
+  uint32_t c0 = p.c0, c1 = p.c1, c2 = p.c2, c3 = p.c3, k0 = p.k0, k1 = p.k1;
+  #pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u*c0, hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u*c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0; c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+  p.o0 = c0; p.o1 = c1; p.o2 = c2; p.o3 = c3; p.have = 4; if (++p.c0 == 0) ++p.c1; }
 __device__ __forceinline__ void philox_init(Philox& p, unsigned long long seed, unsigned long long env, unsigned long long episode, uint32_t lane) {
-  p.k[0] = (uint32_t)seed; p.k[1] = (uint32_t)(seed >> 32); p.c[0] = 0; p.c[1] = lane; p.c[2] = (uint32_t)env ^ (uint32_t)(episode << 20); p.c[3] = (uint32_t)(env >> 32) ^ (uint32_t)(episode >> 12) ^ 0x4D594F42u; p.have = 0; }
-__device__ __forceinline__ double philox_uniform(Philox& p) {   // [0,1) with 53 random bits
+  p.k0 = (uint32_t)seed; p.k1 = (uint32_t)(seed >> 32); p.c0 = 0; p.c1 = lane; p.c2 = (uint32_t)env ^ (uint32_t)(episode << 20); p.c3 = (uint32_t)(env >> 32) ^ (uint32_t)(episode >> 12) ^ 0x4D594F42u; p.have = 0; }
+__device__ __noinline__ double philox_uniform(Philox& p) {   // [0,1) with 53 random bits; consumes the outputs in pairs (0,1) then (2,3)
   if (p.have < 2) philox_gen(p);
-  uint32_t a = p.out[4-p.have], b = p.out[5-p.have]; p.have -= 2;
+  uint32_t a = p.have == 4 ? p.o0 : p.o2, b = p.have == 4 ? p.o1 : p.o3; p.have -= 2;
   return ((double)(((unsigned long long)(a >> 5) << 26) | (b >> 6))) * (1.0/9007199254740992.0); }
 
 // ------------------------------------------------------------------ parity taps
-__device__ void write_taps_solve(const DevModel& m, Warp& w, const StepArgs& a, int env) {   // after the Newton solve
-  Solv s = solv_views(m, w); const myo_buffers& b = a.b;
-  if (b.tap_qacc) for (int i = w.lane; i < m.nv; i += 32) b.tap_qacc[(size_t)env*m.nv+i] = s.a[i];
-  if (b.tap_qfrc_smooth) for (int i = w.lane; i < m.nv; i += 32) b.tap_qfrc_smooth[(size_t)env*m.nv+i] = w.fsm[i];
-  if (b.tap_qM) for (int i = w.lane; i < m.nM; i += 32) b.tap_qM[(size_t)env*m.nM+i] = w.qM[i];
-  if (b.tap_ncon && w.lane == 0) { int* t = b.tap_ncon + 4*(size_t)env; t[0] = w.ncon; t[1] = w.nefc; t[2] = w.niter; t[3] = w.overflow; }
+__device__ void write_taps_solve(const DevModel& m, const Warp w, const StepArgs& a, int env) {   // after the Newton solve
+  const myo_buffers& b = a.b;
+  if (b.tap_qacc) for (int i = w.lane; i < m.nv; i += 32) b.tap_qacc[(size_t)env*m.nv+i] = S_a[i];
+  if (b.tap_qfrc_smooth) for (int i = w.lane; i < m.nv; i += 32) b.tap_qfrc_smooth[(size_t)env*m.nv+i] = W_(fsm)[i];
+  if (b.tap_qM) for (int i = w.lane; i < m.nM; i += 32) b.tap_qM[(size_t)env*m.nM+i] = W_(qM)[i];
+  if (b.tap_ncon && w.lane == 0) { int* t = b.tap_ncon + 4*(size_t)env; t[0] = WI_(ncon); t[1] = WI_(nefc); t[2] = WI_(niter); t[3] = WI_(overflow); }
   __syncwarp();
 }
-__device__ void write_taps_contacts(const DevModel& m, Warp& w, const StepArgs& a, int env) {   // after constraint assembly (con is overwritten by the solve)
-  Solv s = solv_views(m, w); const myo_buffers& b = a.b;
-  if (b.tap_contact_pair) for (int c = w.lane; c < m.maxcon; c += 32) b.tap_contact_pair[(size_t)env*m.maxcon+c] = c < w.ncon ? s.cpair[c] : -1;
-  if (b.tap_contact_dist) for (int c = w.lane; c < m.maxcon; c += 32) b.tap_contact_dist[(size_t)env*m.maxcon+c] = c < w.ncon ? s.con[c*CON_STRIDE] : 0.0;
+__device__ void write_taps_contacts(const DevModel& m, const Warp w, const StepArgs& a, int env) {   // after constraint assembly (con is overwritten by the solve)
+  const myo_buffers& b = a.b;
+  if (b.tap_contact_pair) for (int c = w.lane; c < m.maxcon; c += 32) b.tap_contact_pair[(size_t)env*m.maxcon+c] = c < WI_(ncon) ? S_cpair[c] : -1;
+  if (b.tap_contact_dist) for (int c = w.lane; c < m.maxcon; c += 32) b.tap_contact_dist[(size_t)env*m.maxcon+c] = c < WI_(ncon) ? S_con[c*CON_STRIDE] : 0.0;
   __syncwarp();
 }
 
 // ------------------------------------------------------------------ task logic: pose task (pose_v0.py:100-140,154-170,174-257)
-__device__ void env_reset(const DevModel& m, Warp& w, const StepArgs& a, int env) {
+__device__ void env_reset(const DevModel& m, const Warp w, const StepArgs& a, int env) {
   const myo_buffers& b = a.b; long long ep = b.episode_count ? b.episode_count[env] : 0;
   Philox rng; philox_init(rng, a.seed, (unsigned long long)(a.env_offset + env), (unsigned long long)ep, (uint32_t)w.lane);
   const idx_t* jtype = CI(jnt_type); const idx_t* jq = CI(jnt_qposadr); const double* jrange = CD(jnt_range); const double* qpos0 = CD(qpos0);
-  for (int i = w.lane; i < m.nq; i += 32) w.qpos[i] = b.init_qpos ? b.init_qpos[i] : qpos0[i];
+  for (int i = w.lane; i < m.nq; i += 32) W_(qpos)[i] = b.init_qpos ? b.init_qpos[i] : qpos0[i];
   int key = 0;                                  // row of init_qpos / init_qvel this episode starts from
   if (a.cfg.task == MYO_TASK_WALK && a.cfg.reset_random && b.init_qpos) {
     // WalkEnvV0.get_randomized_initial_state (walk_v0.py:321-337): keyframe 2 or 3 with probability 1/2 (init_qpos rows 0 / 1), then
@@ -67,14 +68,14 @@ __device__ void env_reset(const DevModel& m, Warp& w, const StepArgs& a, int env
     double u = __shfl_sync(FULL, philox_uniform(rng), 0); key = u < 0.5 ? 0 : 1;
     for (int i = w.lane; i < m.nq; i += 32) { double u1 = philox_uniform(rng), u2 = philox_uniform(rng);
       double z = sqrt(-2.0*log(fmax(u1, 1e-300)))*cos(6.283185307179586*u2), q = b.init_qpos[(size_t)key*m.nq + i];
-      w.qpos[i] = i == 2 ? q : q + 0.02*z; } }
+      W_(qpos)[i] = i == 2 ? q : q + 0.02*z; } }
   __syncwarp();
   if (a.cfg.task == MYO_TASK_POSE) {
     // target_jnt_value ~ U(target_jnt_range) ; reset_type "random": qpos ~ U(jnt_range)
     for (int j = w.lane; j < m.njnt; j += 32) { if (jtype[j] == 0) continue; int qa = jq[j];
       double u0 = philox_uniform(rng), u1 = philox_uniform(rng);
       if (b.target && b.target_range) b.target[(size_t)env*m.nq+qa] = b.target_range[2*qa] + u0*(b.target_range[2*qa+1]-b.target_range[2*qa]);
-      if (a.cfg.reset_random) w.qpos[qa] = jrange[2*j] + u1*(jrange[2*j+1]-jrange[2*j]); }
+      if (a.cfg.reset_random) W_(qpos)[qa] = jrange[2*j] + u1*(jrange[2*j+1]-jrange[2*j]); }
   }
   if (a.cfg.task == MYO_TASK_REACH && b.target && b.target_range) {
     // ReachEnvV0.generate_target_pose (reach_v0.py:163-170): every target site ~ U(span) per coordinate
@@ -85,40 +86,40 @@ __device__ void env_reset(const DevModel& m, Warp& w, const StepArgs& a, int env
     if (w.lane < 6) { double u = philox_uniform(rng), v;
       if (w.lane < 3) v = a.cfg.reset_random ? a.cfg.task_d[3+w.lane] + (-0.030 + 0.060*u) : a.cfg.task_d[6+w.lane];
       else v = a.cfg.reset_random ? 0.020 + 0.010*u : a.cfg.task_d[6+w.lane];
-      w.eprm[w.lane] = v; b.env_prm[(size_t)env*8 + w.lane] = v; } }
-  for (int i = w.lane; i < m.nv; i += 32) { w.qvel[i] = b.init_qvel ? b.init_qvel[(size_t)key*m.nv + i] : 0.0; w.qws[i] = 0; }
-  for (int i = w.lane; i < m.na; i += 32) w.act[i] = 0;
+      W_(eprm)[w.lane] = v; b.env_prm[(size_t)env*8 + w.lane] = v; } }
+  for (int i = w.lane; i < m.nv; i += 32) { W_(qvel)[i] = b.init_qvel ? b.init_qvel[(size_t)key*m.nv + i] : 0.0; W_(qws)[i] = 0; }
+  for (int i = w.lane; i < m.na; i += 32) W_(act)[i] = 0;
   if (b.fatigue && a.cfg.muscle_condition == MYO_COND_FATIGUE) for (int i = w.lane; i < m.nu; i += 32) { double* f = b.fatigue + (size_t)env*3*m.nu; f[i] = 0; f[m.nu+i] = 1; f[2*m.nu+i] = 0; }
   if (w.lane == 0) { if (b.time) b.time[env] = 0; if (b.step_count) b.step_count[env] = 0; if (b.episode_count) b.episode_count[env] = ep+1; if (b.ep_return) b.ep_return[env] = 0; }
   __syncwarp();
 }
 
-__device__ void write_obs_pose(const DevModel& m, Warp& w, const StepArgs& a, int env, double* dist_out, double* actmag_out) {
+__device__ void write_obs_pose(const DevModel& m, const Warp w, const StepArgs& a, int env, double* dist_out, double* actmag_out) {
   const myo_buffers& b = a.b; float* o = b.obs ? b.obs + (size_t)env*a.obs_dim : nullptr; double d2 = 0, a2 = 0;
-  for (int i = w.lane; i < m.nq; i += 32) { double tgt = b.target ? b.target[(size_t)env*m.nq+i] : 0.0, err = tgt - w.qpos[i]; d2 += err*err;
-    if (o) { o[i] = (float)w.qpos[i]; o[m.nq+m.nv+i] = (float)err; } }
-  if (o) for (int i = w.lane; i < m.nv; i += 32) o[m.nq+i] = (float)(w.qvel[i]*a.dt);
-  for (int i = w.lane; i < m.na; i += 32) { a2 += w.act[i]*w.act[i]; if (o) o[2*m.nq+m.nv+i] = (float)w.act[i]; }
+  for (int i = w.lane; i < m.nq; i += 32) { double tgt = b.target ? b.target[(size_t)env*m.nq+i] : 0.0, err = tgt - W_(qpos)[i]; d2 += err*err;
+    if (o) { o[i] = (float)W_(qpos)[i]; o[m.nq+m.nv+i] = (float)err; } }
+  if (o) for (int i = w.lane; i < m.nv; i += 32) o[m.nq+i] = (float)(W_(qvel)[i]*a.dt);
+  for (int i = w.lane; i < m.na; i += 32) { a2 += W_(act)[i]*W_(act)[i]; if (o) o[2*m.nq+m.nv+i] = (float)W_(act)[i]; }
   *dist_out = sqrt(warp_sum(d2)); double am = sqrt(warp_sum(a2)); *actmag_out = m.na ? am/m.na : am;
 }
 
 // reward / done of the current state (pose_v0.py:113-140); lane 0 writes
-__device__ void pose_reward_done(const DevModel& m, Warp& w, const StepArgs& a, int env, double* rw_out, bool* done_out) {
+__device__ void pose_reward_done(const DevModel& m, const Warp w, const StepArgs& a, int env, double* rw_out, bool* done_out) {
   double dist, am; write_obs_pose(m, w, a, env, &dist, &am);
   const double far_th = 4*3.14159265358979323846/2; double thd = a.cfg.pose_thd;
   *rw_out = a.cfg.weights[0]*(-dist) + a.cfg.weights[1]*((dist < thd ? 1.0 : 0.0)+(dist < 1.5*thd ? 1.0 : 0.0)) + a.cfg.weights[2]*(-am) + a.cfg.weights[3]*(dist > far_th ? -1.0 : 0.0);
   *done_out = dist > far_th; }
 
 // spatial velocity [omega; v_origin] of dynamic body k from its dof chain
-__device__ __forceinline__ void body_velocity(const DevModel& m, const Warp& w, int k, double* v) {
+__device__ __forceinline__ void body_velocity(const DevModel& m, const Warp w, int k, double* v) {
   const idx_t* cadr = CI(PCH_adr); const idx_t* ch = CI(PCH);
   for (int c = 0; c < 6; c++) v[c] = 0;
   #pragma unroll 1
-  for (int e = cadr[k]; e < cadr[k+1]; e++) { int d = ch[e] >> 1; double S[6], qd = w.qvel[d]; dof_motion(m, w, d, S); for (int c = 0; c < 6; c++) v[c] += S[c]*qd; } }
+  for (int e = cadr[k]; e < cadr[k+1]; e++) { int d = ch[e] >> 1; double S[6], qd = W_(qvel)[d]; dof_motion(m, w, d, S); for (int c = 0; c < 6; c++) v[c] += S[c]*qd; } }
 
 // WalkEnvV0 obs / reward / done (walk_v0.py:268-319,358-494) on the post-step state; needs kinematics + tendon + actuation of that
 // state in scratch (the reference's extra mj_forward, robot.py:607).  `steps` = WalkEnvV0.steps BEFORE its increment (walk_v0.py:339-342).
-__device__ void walk_observe(const DevModel& m, Warp& w, const StepArgs& a, int env, int steps, double* rw_out, bool* done_out) {
+__device__ void walk_observe(const DevModel& m, const Warp w, const StepArgs& a, int env, int steps, double* rw_out, bool* done_out) {
   const myo_buffers& b = a.b; const int* ti = a.cfg.task_i; const double* td = a.cfg.task_d;
   const double* PB = CD(PB_d); const double* xpos = SCR(s_xpos); const double* xmat = SCR(s_xmat);
   double acc[9] = {0,0,0,0,0,0,0,0,0};     // sum m*xipos, sum m*v_origin, sum m*omega
@@ -129,14 +130,14 @@ __device__ void walk_observe(const DevModel& m, Warp& w, const StepArgs& a, int 
   double M = td[13], com[3] = {acc[0]/M, acc[1]/M, acc[2]/M}, wxc[3]; cross3(wxc, acc + 6, com);
   // _get_com_velocity: -(sum m*cvel)/M, cvel's linear part being the velocity at the root's subtree COM
   double vx = -(acc[3] + wxc[0])/M, vy = -(acc[4] + wxc[1])/M, height = com[2];
-  const double* quat = w.qpos + 3;
+  const double* quat = W_(qpos) + 3;
   double tq[4]; quat_mul(tq, quat, td); quat_norm(tq);                                        // torso xquat = root quat (x) constant offset
   const double* pl = xpos + 3*ti[1]; const double* pr_ = xpos + 3*ti[2]; const double* pp = xpos + 3*ti[3];
   double phase = fmod((double)steps/td[6], 1.0);
   float* o = b.obs ? b.obs + (size_t)env*a.obs_dim : nullptr;
   if (o) { int nq2 = m.nq - 2, base = nq2 + m.nv;
-    for (int i = w.lane; i < nq2; i += 32) o[i] = (float)w.qpos[2+i];
-    for (int i = w.lane; i < m.nv; i += 32) o[nq2+i] = (float)(w.qvel[i]*a.dt);
+    for (int i = w.lane; i < nq2; i += 32) o[i] = (float)W_(qpos)[2+i];
+    for (int i = w.lane; i < m.nv; i += 32) o[nq2+i] = (float)(W_(qvel)[i]*a.dt);
     if (w.lane == 0) { o[base] = (float)vx; o[base+1] = (float)vy; for (int c = 0; c < 4; c++) o[base+2+c] = (float)tq[c];
       o[base+6] = (float)pl[2]; o[base+7] = (float)pr_[2]; o[base+8] = (float)height;
       for (int c = 0; c < 3; c++) { o[base+9+c] = (float)(pl[c]-pp[c]); o[base+12+c] = (float)(pr_[c]-pp[c]); }
@@ -145,14 +146,14 @@ __device__ void walk_observe(const DevModel& m, Warp& w, const StepArgs& a, int 
     int mb = base + 16;
     for (int i = w.lane; i < m.nu; i += 32) { double gear = PAm[i*PAM_STRIDE+4]; int t = at[i];
       o[mb+i] = (float)(gear*tlen[t]); o[mb+m.nu+i] = (float)clipd(gear*tvel[t], -100, 100); o[mb+2*m.nu+i] = (float)clipd(tfrc[t]/gear/1000.0, -100, 100);
-      o[mb+3*m.nu+i] = (float)w.act[i]; } }
+      o[mb+3*m.nu+i] = (float)W_(act)[i]; } }
   // rewards
   double vel_reward = exp(-(td[8]-vy)*(td[8]-vy)) + exp(-(td[7]-vx)*(td[7]-vx));
   const double PI = 3.14159265358979323846;
   double des0 = (double)(float)(0.8*cos(phase*2*PI + PI)), des1 = (double)(float)(0.8*cos(phase*2*PI));
-  double e0 = des0 - w.qpos[ti[4]], e1 = des1 - w.qpos[ti[5]], cyclic = sqrt(e0*e0 + e1*e1);
+  double e0 = des0 - W_(qpos)[ti[4]], e1 = des1 - W_(qpos)[ti[5]], cyclic = sqrt(e0*e0 + e1*e1);
   double rr = 0; for (int c = 0; c < 4; c++) { double dq = 5.0*(quat[c] - td[9+c]); rr += dq*dq; } double ref_rot = exp(-sqrt(rr));
-  double mag = 0.25*(fabs(w.qpos[ti[6]]) + fabs(w.qpos[ti[7]]) + fabs(w.qpos[ti[8]]) + fabs(w.qpos[ti[9]])), jrew = exp(-5.0*mag);
+  double mag = 0.25*(fabs(W_(qpos)[ti[6]]) + fabs(W_(qpos)[ti[7]]) + fabs(W_(qpos)[ti[8]]) + fabs(W_(qpos)[ti[9]])), jrew = exp(-5.0*mag);
   double qn = quat[0]*quat[0]+quat[1]*quat[1]+quat[2]*quat[2]+quat[3]*quat[3], r00 = (quat[0]*quat[0]+quat[1]*quat[1]-quat[2]*quat[2]-quat[3]*quat[3])/qn;
   bool done = height < td[4] || fabs(r00) > td[5];
   *rw_out = a.cfg.weights[0]*vel_reward + a.cfg.weights[1]*(done ? 1.0 : 0.0) + a.cfg.weights[2]*cyclic + a.cfg.weights[3]*ref_rot + a.cfg.weights[4]*jrew;
@@ -160,30 +161,30 @@ __device__ void walk_observe(const DevModel& m, Warp& w, const StepArgs& a, int 
 }
 
 // ObjHold obs / reward / done (obj_hold_v0.py:79-121): needs kinematics of the post-step state in scratch
-__device__ void hold_observe(const DevModel& m, Warp& w, const StepArgs& a, int env, double* rw_out, bool* done_out) {
+__device__ void hold_observe(const DevModel& m, const Warp w, const StepArgs& a, int env, double* rw_out, bool* done_out) {
   const myo_buffers& b = a.b; const int* ti = a.cfg.task_i; const double* td = a.cfg.task_d;
   int ob = ti[0]; const double* xp = SCR(s_xpos) + 3*ob; double op[3]; mat_vec(op, SCR(s_xmat) + 9*ob, td); op[0]+=xp[0]; op[1]+=xp[1]; op[2]+=xp[2];
-  double err[3] = {w.eprm[0]-op[0], w.eprm[1]-op[1], w.eprm[2]-op[2]}, dist = sqrt(dot3(err, err));
+  double err[3] = {W_(eprm)[0]-op[0], W_(eprm)[1]-op[1], W_(eprm)[2]-op[2]}, dist = sqrt(dot3(err, err));
   float* o = b.obs ? b.obs + (size_t)env*a.obs_dim : nullptr; int nqh = m.nq - 7, nvh = m.nv - 6;
-  if (o) { for (int i = w.lane; i < nqh; i += 32) o[i] = (float)w.qpos[i];
-    for (int i = w.lane; i < nvh; i += 32) o[nqh+i] = (float)(w.qvel[i]*a.dt);
-    if (w.lane < 3) { o[nqh+nvh+w.lane] = (float)op[w.lane]; o[nqh+nvh+3+w.lane] = (float)err[w.lane]; }
-    for (int i = w.lane; i < m.na; i += 32) o[nqh+nvh+6+i] = (float)w.act[i]; }
+  if (o) { for (int i = w.lane; i < nqh; i += 32) o[i] = (float)W_(qpos)[i];
+    for (int i = w.lane; i < nvh; i += 32) o[nqh+i] = (float)(W_(qvel)[i]*a.dt);
+    if (w.lane < 3) { const int l = w.lane; o[nqh+nvh+l] = (float)(l == 0 ? op[0] : (l == 1 ? op[1] : op[2])); o[nqh+nvh+3+l] = (float)(l == 0 ? err[0] : (l == 1 ? err[1] : err[2])); }
+    for (int i = w.lane; i < m.na; i += 32) o[nqh+nvh+6+i] = (float)W_(act)[i]; }
   bool drop = dist > 0.300;
   *rw_out = a.cfg.weights[0]*(-dist) + a.cfg.weights[1]*((dist < 0.020 ? 1.0 : 0.0) + (dist < 0.010 ? 1.0 : 0.0)) + a.cfg.weights[2]*(drop ? -1.0 : 0.0);
   *done_out = drop;
 }
 
 // ReachEnvV0 obs / reward / done (reach_v0.py:98-160): needs kinematics of the post-step state in scratch.  tnow = mjData.time of that state
-__device__ void reach_observe(const DevModel& m, Warp& w, const StepArgs& a, int env, double tnow, double* rw_out, bool* done_out) {
+__device__ void reach_observe(const DevModel& m, const Warp w, const StepArgs& a, int env, double tnow, double* rw_out, bool* done_out) {
   const myo_buffers& b = a.b; const int* ti = a.cfg.task_i; const double* td = a.cfg.task_d; const int ntip = ti[0];
   float* o = b.obs ? b.obs + (size_t)env*a.obs_dim : nullptr; double d2 = 0, a2 = 0; const int base = m.nq + m.nv;
   if (w.lane < ntip) { int bd = ti[1+w.lane]; const double* lp = td + 3*w.lane; double tip[3] = {lp[0], lp[1], lp[2]};
     if (bd >= 0) { const double* xp = SCR(s_xpos) + 3*bd; mat_vec(tip, SCR(s_xmat) + 9*bd, lp); tip[0]+=xp[0]; tip[1]+=xp[1]; tip[2]+=xp[2]; }
     for (int c = 0; c < 3; c++) { double tgt = b.target ? b.target[(size_t)env*m.nq + 3*w.lane + c] : 0.0, err = tgt - tip[c]; d2 += err*err;
       if (o) { o[base + 3*w.lane + c] = (float)tip[c]; o[base + 3*ntip + 3*w.lane + c] = (float)err; } } }
-  if (o) { for (int i = w.lane; i < m.nq; i += 32) o[i] = (float)w.qpos[i]; for (int i = w.lane; i < m.nv; i += 32) o[m.nq+i] = (float)(w.qvel[i]*a.dt); }
-  for (int i = w.lane; i < m.na; i += 32) { a2 += w.act[i]*w.act[i]; if (o) o[base + 6*ntip + i] = (float)w.act[i]; }      // base_v0.py:33-37 appends "act"
+  if (o) { for (int i = w.lane; i < m.nq; i += 32) o[i] = (float)W_(qpos)[i]; for (int i = w.lane; i < m.nv; i += 32) o[m.nq+i] = (float)(W_(qvel)[i]*a.dt); }
+  for (int i = w.lane; i < m.na; i += 32) { a2 += W_(act)[i]*W_(act)[i]; if (o) o[base + 6*ntip + i] = (float)W_(act)[i]; }      // base_v0.py:33-37 appends "act"
   double dist = sqrt(warp_sum(d2)), am = sqrt(warp_sum(a2)); if (m.na) am /= m.na;
   bool armed = tnow > 2*a.dt;                                   // far_th = inf for the first control steps (reach_v0.py:134-138)
   double far_th = td[3*ntip]*ntip, near_th = ntip*0.0125; bool far = armed && dist > far_th;
@@ -192,13 +193,15 @@ __device__ void reach_observe(const DevModel& m, Warp& w, const StepArgs& a, int
 }
 
 // obs / reward / done of the state held in shared memory, for any task (runs the extra forward stages the task needs)
-__device__ __noinline__ void task_observe(const DevModel& m, Warp& w, const StepArgs& a, int env, int steps, double tnow, double* rw, bool* done) {
-  *rw = 0; *done = false;
-  if (a.cfg.task == MYO_TASK_POSE) pose_reward_done(m, w, a, env, rw, done);
-  else if (a.cfg.task == MYO_TASK_WALK) { phase_kinematics(m, w); phase_tendon(m, w); phase_tendon_moments(m, w); phase_actuation(m, w, false, nullptr, nullptr); walk_observe(m, w, a, env, steps, rw, done); }
-  else if (a.cfg.task == MYO_TASK_HOLD) { phase_kinematics(m, w); hold_observe(m, w, a, env, rw, done); }
-  else if (a.cfg.task == MYO_TASK_REACH) { phase_kinematics(m, w); reach_observe(m, w, a, env, tnow, rw, done); }
+struct RwDone { double rw; int done; };   // returned by value (registers), not through pointers to the caller's stack
+__device__ __noinline__ RwDone task_observe(const DevModel& m, const Warp w, const StepArgs& a, int env, int steps, double tnow) {
+  double rw = 0; bool done = false;
+  if (a.cfg.task == MYO_TASK_POSE) pose_reward_done(m, w, a, env, &rw, &done);
+  else if (a.cfg.task == MYO_TASK_WALK) { phase_kinematics(m, w); phase_tendon(m, w); phase_tendon_moments(m, w); phase_actuation(m, w, false, nullptr, nullptr); walk_observe(m, w, a, env, steps, &rw, &done); }
+  else if (a.cfg.task == MYO_TASK_HOLD) { phase_kinematics(m, w); hold_observe(m, w, a, env, &rw, &done); }
+  else if (a.cfg.task == MYO_TASK_REACH) { phase_kinematics(m, w); reach_observe(m, w, a, env, tnow, &rw, &done); }
   __syncwarp();
+  RwDone r; r.rw = rw; r.done = done; return r;
 }
 
 // barrier among the warps of one lockstep group (named barrier); one group = the whole CTA -> __syncthreads()
@@ -206,13 +209,15 @@ __device__ __forceinline__ void group_sync(int ngroups, int gid, int gthreads) {
   if (ngroups <= 1) __syncthreads(); else asm volatile("bar.sync %0, %1;" :: "r"(1 + gid), "r"(gthreads) : "memory"); }
 
 // ------------------------------------------------------------------ the kernel
-extern "C" __global__ void __launch_bounds__(320) myo_env_kernel(const __grid_constant__ DevModel m, const __grid_constant__ StepArgs a) {
-  extern __shared__ __align__(16) double smem[];
+// DBG = false: the product step / reset / observe kernel (modes 0, 2, 3): no parity taps, no cycle counters, fixed barrier scheme.
+// DBG = true: everything -- forward-debug mode (1), parity taps, per-phase cycle counters, the barrier / lockstep-group tuning knobs.
+// MAXT: launch bound (threads per CTA) -> register budget of the instantiation.
+template <bool DBG, int MAXT>
+__device__ __forceinline__ void env_kernel_body(const DevModel& m, const StepArgs& a) {
   __shared__ __align__(8) unsigned long long mbar;
-  __shared__ int s_ncand[16];
   const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   // ---- stage the model constants into shared memory: bulk async copies (TMA), completion on an mbarrier
-  double* s_d = smem; idx_t* s_i = (idx_t*)(smem + m.nD); double* warp0 = smem + m.nD + (m.nI16w + 1)/2;
+  double* s_d = smem; idx_t* s_i = (idx_t*)(smem + m.nD);
   const unsigned mb = (unsigned)__cvta_generic_to_shared(&mbar);
   if (threadIdx.x == 0) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mb)); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
@@ -229,17 +234,15 @@ extern "C" __global__ void __launch_bounds__(320) myo_env_kernel(const __grid_co
   }
   { unsigned done = 0; while (!done) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mb) : "memory"); }
 
-  Warp w; w.lane = threadIdx.x & 31; w.cd = s_d; w.ci = s_i;
-  double* base = warp0 + (size_t)wid*m.n_per_warp;
-  w.qpos = base+m.o_qpos; w.qvel = base+m.o_qvel; w.act = base+m.o_act; w.ctrl = base+m.o_ctrl; w.qws = base+m.o_qws; w.dax = base+m.o_dax; w.dan = base+m.o_dan;
-  w.qM = base+m.o_qM; w.fsm = base+m.o_fsm; w.eprm = base+m.o_eprm; w.wz = base+m.o_wz; w.scr = base+m.o_scr;
-  w.ncon = w.nefc = w.nlimrow = w.niter = w.overflow = w.ncand = 0;
+  const Warp w = { m.nD + (m.nI16w + 1)/2 + wid*m.n_per_warp, (int)(threadIdx.x & 31) };
+  if (w.lane < CNT_N) ((int*)(smem + w.base + m.o_cnt))[w.lane] = 0;
+  __syncwarp();
   const myo_buffers& b = a.b;
   // All warps of a CTA walk the phases in lockstep (CTA barriers between phases) so that they share instruction fetches:
   // the step is a long, mostly straight-line program and the instruction cache, not the data path, is the scarce resource.
-  const int nsub = a.mode == 0 ? a.cfg.frame_skip : (a.mode == 1 ? (a.n_substeps > 0 ? a.n_substeps : 1) : 0);
-  const bool integrate = a.mode == 0 || (a.mode == 1 && a.n_substeps > 0);
-  const bool prof = b.tap_phase_cycles != nullptr;
+  const int nsub = a.mode == 0 ? a.cfg.frame_skip : ((DBG && a.mode == 1) ? (a.n_substeps > 0 ? a.n_substeps : 1) : 0);
+  const bool integrate = a.mode == 0 || (DBG && a.mode == 1 && a.n_substeps > 0);
+  const bool prof = DBG && b.tap_phase_cycles != nullptr;
   // env e belongs to CTA e % gridDim.x: every CTA gets floor or ceil of n_env / gridDim.x envs, so no CTA runs a full extra round
   // while the others idle (4096 envs on 148 SMs: rounds of 10, 10, 8 warps everywhere instead of 10, 10, 10 on three quarters of the SMs)
   const int per_cta = a.balanced ? (a.n_env + (int)gridDim.x - 1)/(int)gridDim.x : ((a.n_env + nw - 1)/nw + (int)gridDim.x - 1)/(int)gridDim.x*nw;
@@ -248,22 +251,22 @@ extern "C" __global__ void __launch_bounds__(320) myo_env_kernel(const __grid_co
     const bool live = (j0 + wid) < per_cta && env < a.n_env; const long long tstep_ = prof ? clock64() : 0;
     if (live) {
       // ---- load state (coalesced: one env's row per warp)
-      for (int i = w.lane; i < m.nq; i += 32) w.qpos[i] = b.qpos[(size_t)env*m.nq+i];
-      for (int i = w.lane; i < m.nv; i += 32) { w.qvel[i] = b.qvel[(size_t)env*m.nv+i]; w.qws[i] = b.qacc_warmstart[(size_t)env*m.nv+i]; }
-      for (int i = w.lane; i < m.na; i += 32) w.act[i] = b.act[(size_t)env*m.na+i];
-      if (w.lane < 8) w.eprm[w.lane] = b.env_prm ? b.env_prm[(size_t)env*8 + w.lane] : 0.0;
-      for (int i = w.lane; i < m.nwz; i += 32) w.wz[i] = -1.0;     // cold start of the inverse-wrap roots at the first substep
+      for (int i = w.lane; i < m.nq; i += 32) W_(qpos)[i] = b.qpos[(size_t)env*m.nq+i];
+      for (int i = w.lane; i < m.nv; i += 32) { W_(qvel)[i] = b.qvel[(size_t)env*m.nv+i]; W_(qws)[i] = b.qacc_warmstart[(size_t)env*m.nv+i]; }
+      for (int i = w.lane; i < m.na; i += 32) W_(act)[i] = b.act[(size_t)env*m.na+i];
+      if (w.lane < 8) W_(eprm)[w.lane] = b.env_prm ? b.env_prm[(size_t)env*8 + w.lane] : 0.0;
+      for (int i = w.lane; i < m.nwz; i += 32) W_(wz)[i] = -1.0;     // cold start of the inverse-wrap roots at the first substep
       __syncwarp();
       if (a.mode == 2) {
         if (!a.reset_mask || a.reset_mask[env]) { env_reset(m, w, a, env);
-          { double rw_; bool dn_; task_observe(m, w, a, env, 0, 0.0, &rw_, &dn_); }
-          if (w.lane == 0) { if (b.done) b.done[env] = 0; if (b.truncated) b.truncated[env] = 0; if (b.reward) b.reward[env] = 0; } }
+          task_observe(m, w, a, env, 0, 0.0);
+          if (w.lane == 0) { if (b.done) b.done[env] = 0; if (b.truncated) b.truncated[env] = 0; if (b.reward) b.reward[env] = 0; if (b.overflow) b.overflow[env] = 0; } }
       } else if (a.mode == 3) {   // observe: obs/reward/done of the current state, nothing advanced (env.forward(), env_base.py:393-432)
-        { double rw; bool done; task_observe(m, w, a, env, b.step_count ? b.step_count[env] : 0, b.time ? b.time[env] : 0.0, &rw, &done);
-          if (w.lane == 0) { if (b.reward) b.reward[env] = (float)rw; if (b.done) b.done[env] = done; } }
-      } else if (a.mode == 1) {
-        for (int i = w.lane; i < m.nu; i += 32) w.ctrl[i] = a.dbg_ctrl[(size_t)env*m.nu+i];
-      } else {
+        { const RwDone rd = task_observe(m, w, a, env, b.step_count ? b.step_count[env] : 0, b.time ? b.time[env] : 0.0);
+          if (w.lane == 0) { if (b.reward) b.reward[env] = (float)rd.rw; if (b.done) b.done[env] = rd.done != 0; } }
+      } else if (DBG && a.mode == 1) {
+        for (int i = w.lane; i < m.nu; i += 32) W_(ctrl)[i] = a.dbg_ctrl[(size_t)env*m.nu+i];
+      } else if (a.mode == 0) {
         // ---- action -> ctrl  (base_v0.py:83-96); fatigue (fatigue.py:38-76)
         for (int i = w.lane; i < m.nu; i += 32) { double c = (double)b.action[(size_t)env*m.nu+i];
           if (a.cfg.reaf_dst != a.cfg.reaf_src && i == a.cfg.reaf_dst) c = (double)b.action[(size_t)env*m.nu+a.cfg.reaf_src];
@@ -281,33 +284,26 @@ extern "C" __global__ void __launch_bounds__(320) myo_env_kernel(const __grid_co
             C = fmin(fmax(C, lo), hi);   // np.clip(C, lo, hi) == minimum(maximum(C, lo), hi)
             double dMA = (C-Fc*MA)*fdt, dMR = (-C+rR*MF)*fdt, dMF = (Fc*MA-rR*MF)*fdt;
             MA += dMA; MR += dMR; MF += dMF; F[i] = MA; F[m.nu+i] = MR; F[2*m.nu+i] = MF; c = MA; }
-          w.ctrl[i] = c; }
+          W_(ctrl)[i] = c; }
       }
       __syncwarp();
     }
     // ---- physics substeps: forward dynamics + semi-implicit Euler (the only copy of the phase code in the kernel)
-    const int ngroups = a.cfg.reserved_i > 1 ? (a.cfg.reserved_i < nw ? a.cfg.reserved_i : nw) : 1;
+    const int ngroups = (DBG && a.cfg.reserved_i > 1) ? (a.cfg.reserved_i < nw ? a.cfg.reserved_i : nw) : 1;
     const int gsz = (nw + ngroups - 1)/ngroups, gid = wid / gsz, gw0 = gid*gsz, gnw = (gw0 + gsz <= nw ? gsz : nw - gw0), gthreads = gnw*32;
-    const int bmask = a.cfg.barrier_mode == 0 ? 0xFF : (a.cfg.barrier_mode == 1 ? 0x01 : (a.cfg.barrier_mode == 2 ? 0 : a.cfg.barrier_mode));
-    const bool waitprof = a.cfg.reserved[0] != 0.0;   // profiling: record the barrier wait BEFORE each phase instead of the phase's own cycles
-    long long cyc[20] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0}; int maxcon_seen = 0, maxefc_seen = 0;
+    const int bmask = !DBG || a.cfg.barrier_mode == 0 ? 0xFF : (a.cfg.barrier_mode == 1 ? 0x01 : (a.cfg.barrier_mode == 2 ? 0 : a.cfg.barrier_mode));
+    const bool waitprof = DBG && a.cfg.reserved[0] != 0.0;   // profiling: record the barrier wait BEFORE each phase instead of the phase's own cycles
+    long long cyc_[DBG ? 20 : 1]; long long* const cyc = DBG ? cyc_ : nullptr; int maxcon_seen = 0, maxefc_seen = 0, overflow_seen = 0;
+    if (DBG) for (int k = 0; k < 20; k++) cyc_[DBG ? k : 0] = 0;
     #define PH(k, stmt) { long long tb_ = prof ? clock64() : 0; if (bmask & (1 << k)) group_sync(ngroups, gid, gthreads); long long t0_ = prof ? clock64() : 0; if (live) { stmt; } if (prof) cyc[k] += waitprof ? t0_ - tb_ : clock64() - t0_; }
     #pragma unroll 1
     for (int s = 0; s < nsub; s++) {
-      const bool tap = s == nsub-1;
+      const bool tap = DBG && s == nsub-1;
       PH(0, phase_kinematics(m, w));
       PH(1, phase_tendon(m, w); phase_tendon_moments(m, w); if (tap && b.tap_moment) { const double* mom = SCR(s_mom); for (int i = w.lane; i < m.nnz; i += 32) b.tap_moment[(size_t)env*m.nnz+i] = mom[i]; });
       PH(2, phase_actuation(m, w, integrate, tap && b.tap_actuator_force ? b.tap_actuator_force + (size_t)env*m.nu : nullptr, tap && b.tap_ten_length ? b.tap_ten_length + (size_t)env*m.nu : nullptr));
       PH(3, phase_body_inertia(m, w); phase_crb(m, w); phase_bias(m, w));
-      PH(4, phase_collision(m, w));
-      if (m.npair > m.npair_an) {   // CTA-cooperative pass over the expensive candidates of all envs of this CTA
-        long long tc_ = prof ? clock64() : 0;
-        if (m.coop) {
-          if (w.lane == 0) s_ncand[wid] = live ? w.ncand : 0;
-          group_sync(ngroups, gid, gthreads); collision_coop(m, w, warp0, s_ncand, gw0, gnw); group_sync(ngroups, gid, gthreads);
-          if (live) collision_merge(m, w);
-        } else if (live) collision_direct(m, w);
-        if (prof) cyc[16] += clock64() - tc_; }
+      PH(4, phase_collision(m, w); overflow_seen |= WI_(overflow));
       PH(5, phase_constraints(m, w); if (tap) write_taps_contacts(m, w, a, env));
       if (ngroups == 1 && m.solve_sync) {   // every warp enters the solver: its inner CTA barriers need the idle warps too
         long long tb_ = prof ? clock64() : 0; if (bmask & (1 << 6)) __syncthreads(); long long t0_ = prof ? clock64() : 0;
@@ -315,36 +311,48 @@ extern "C" __global__ void __launch_bounds__(320) myo_env_kernel(const __grid_co
         if (prof) cyc[6] += waitprof ? t0_ - tb_ : clock64() - t0_;
       } else PH(6, phase_solve(m, w, a.tol, prof ? cyc : nullptr, true, false));
       PH(7, if (tap) write_taps_solve(m, w, a, env); if (integrate) phase_integrate(m, w, prof ? cyc : nullptr));
-      if (w.ncon > maxcon_seen) maxcon_seen = w.ncon;
-      if (w.nefc > maxefc_seen) maxefc_seen = w.nefc;
+      if (DBG && live) { if (WI_(ncon) > maxcon_seen) maxcon_seen = WI_(ncon); if (WI_(nefc) > maxefc_seen) maxefc_seen = WI_(nefc); }
     }
     #undef PH
     if (prof && live && w.lane == 0) { long long* pc = b.tap_phase_cycles + 20*(size_t)env; for (int k = 0; k < 20; k++) pc[k] = cyc[k]; pc[12] = maxcon_seen; pc[13] = maxefc_seen; pc[17] = clock64() - tstep_; }
     if (live) {
-      if (a.mode == 1) { if (integrate && w.lane == 0 && b.time) b.time[env] += nsub*m.timestep; }
+      if (DBG && a.mode == 1) { if (integrate && w.lane == 0 && b.time) b.time[env] += nsub*m.timestep; }
       else if (a.mode == 0) {
         // ---- obs / reward / done / TimeLimit / auto-reset
         // mjData.time advances by one timestep per substep (the accumulated rounding is visible to ReachEnvV0's `time > 2 dt` test)
         double tnow = b.time ? b.time[env] : 0.0; for (int s_ = 0; s_ < a.cfg.frame_skip; s_++) tnow += m.timestep;
-        if (a.cfg.task != MYO_TASK_NONE) { double rw; bool done; task_observe(m, w, a, env, b.step_count ? b.step_count[env] : 0, tnow, &rw, &done);
+        if (overflow_seen && w.lane == 0 && b.overflow) b.overflow[env] |= 1;      // sticky until the next reset of this env
+        if (a.cfg.task != MYO_TASK_NONE) { const RwDone rd = task_observe(m, w, a, env, b.step_count ? b.step_count[env] : 0, tnow); const double rw = rd.rw; const bool done = rd.done != 0;
           int sc = b.step_count ? b.step_count[env]+1 : 0; bool trunc = a.cfg.max_episode_steps > 0 && sc >= a.cfg.max_episode_steps;
           __syncwarp();
-          if (w.lane == 0) { if (b.reward) b.reward[env] = (float)rw; if (b.done) b.done[env] = done; if (b.truncated) b.truncated[env] = trunc && !done;
+          // truncated follows gym's TimeLimit: set whenever the step budget is reached, also when the episode terminated on the same step
+          if (w.lane == 0) { if (b.reward) b.reward[env] = (float)rw; if (b.done) b.done[env] = done; if (b.truncated) b.truncated[env] = trunc;
             if (b.step_count) b.step_count[env] = sc; if (b.time) b.time[env] = tnow;
             if (b.ep_return) { float R = b.ep_return[env] + (float)rw; b.ep_return[env] = R; if ((done || trunc) && b.last_return) b.last_return[env] = R; } }
           __syncwarp();
-          if ((done || trunc) && a.cfg.auto_reset) { env_reset(m, w, a, env); double rw2; bool dn2; task_observe(m, w, a, env, 0, 0.0, &rw2, &dn2); }
+          if ((done || trunc) && a.cfg.auto_reset) { env_reset(m, w, a, env); task_observe(m, w, a, env, 0, 0.0); if (w.lane == 0 && b.overflow) b.overflow[env] = 0; }
         } else if (w.lane == 0 && b.time) b.time[env] = tnow;
       }
       __syncwarp();
       // ---- store state
-      for (int i = w.lane; i < m.nq; i += 32) b.qpos[(size_t)env*m.nq+i] = w.qpos[i];
-      for (int i = w.lane; i < m.nv; i += 32) { b.qvel[(size_t)env*m.nv+i] = w.qvel[i]; b.qacc_warmstart[(size_t)env*m.nv+i] = w.qws[i]; }
-      for (int i = w.lane; i < m.na; i += 32) b.act[(size_t)env*m.na+i] = w.act[i];
+      for (int i = w.lane; i < m.nq; i += 32) b.qpos[(size_t)env*m.nq+i] = W_(qpos)[i];
+      for (int i = w.lane; i < m.nv; i += 32) { b.qvel[(size_t)env*m.nv+i] = W_(qvel)[i]; b.qacc_warmstart[(size_t)env*m.nv+i] = W_(qws)[i]; }
+      for (int i = w.lane; i < m.na; i += 32) b.act[(size_t)env*m.na+i] = W_(act)[i];
       __syncwarp();
     }
   }
 }
+// product kernel: up to 10 env-warps per CTA (204 registers per thread)
+#ifndef MYO_LB
+#define MYO_LB __maxnreg__(200)      /* 10 env-warps x 32 lanes x 200 registers = 64 000 of the SM's 65 536; launch_bounds(320) made ptxas stop at 168 and spill 1.3 KB */
+#endif
+extern "C" __global__ void MYO_LB myo_env_kernel(const __grid_constant__ DevModel m, const __grid_constant__ StepArgs a) { env_kernel_body<false, 320>(m, a); }
+// parity taps / forward-debug / profiling counters / tuning knobs
+#ifndef MYO_EXPERIMENT_NO_DBG     // (compile-time experiments build the product kernel only)
+extern "C" __global__ void __launch_bounds__(320) myo_env_kernel_dbg(const __grid_constant__ DevModel m, const __grid_constant__ StepArgs a) { env_kernel_body<true, 320>(m, a); }
+#else
+#define myo_env_kernel_dbg myo_env_kernel
+#endif
 
 // ================================================================== host side (C-ABI)
 static thread_local std::string g_err;
@@ -353,7 +361,7 @@ static int fail(const std::string& s) { g_err = s; return -1; }
 
 struct myo_model { std::vector<int32_t> I; std::vector<double> D; };
 struct myo_batch { const myo_model* model; int device, n_env; myo_task_cfg cfg; myo_buffers bufs; bool bound; DevModel dm; int32_t* dI; double* dD; int const_bytes;
-  int warps_per_cta, grid, smem_bytes, obs_dim; long long launches; unsigned long long seed; long long env_offset; };
+  int warps_per_cta, grid, smem_bytes, obs_dim; bool force_dbg; long long launches; unsigned long long seed; long long env_offset; };
 
 extern "C" const char* myo_last_error(void) { return g_err.c_str(); }
 extern "C" int myo_version(void) { return 1; }
@@ -381,13 +389,12 @@ static void fill_devmodel(const myo_model* mm, const myo_task_cfg* cfg, DevModel
   d.npair = P[PD_NPAIR]; d.npair_an = P[PD_NPAIR_ANALYTIC]; d.maxpath = P[PD_MAXPATH]; d.ndepth = P[PD_NDEPTH]; d.eq_tree = P[PD_EQ_TREE];
   const double* opt = MYO_DSEC(I, D, MYO_SEC_opt); d.timestep = opt[0]; d.gx = opt[1]; d.gy = opt[2]; d.gz = opt[3]; d.tolerance = opt[4]; d.meaninertia = opt[6];
   d.ovr_geom = (cfg && cfg->task == MYO_TASK_HOLD) ? cfg->task_i[1] : -1;
-  { const char* e = getenv("MYO_B200_CHOL"); d.chol_mode = e ? atoi(e) : 1; }   // dense Cholesky (nv <= 32): 1 = unrolled register/shuffle version (default: 21 k cycles per 23x23 solve), 0 = rolled shared-memory version (49 k)
   { const char* e = getenv("MYO_B200_SOLVE_SYNC"); d.solve_sync = e ? atoi(e) : 1; }   // CTA barriers inside the Newton loop (0 = warps run the solver phase unaligned)
-  { const char* e = getenv("MYO_B200_COOP"); d.coop = e ? atoi(e) : 0; }     // ellipsoid candidates: 0 = inside the owning warp (default; 558k vs 548k on the hand), 1 = CTA-cooperative pass
   int mc = cfg && cfg->maxcon > 0 ? cfg->maxcon : 32; if (mc > 2*d.npair) mc = 2*d.npair; d.maxcon = mc; d.nlimrow = P[PD_NLIMROW] > 0 ? P[PD_NLIMROW] : 2*d.nlim; d.maxefc = d.neq + d.nlimrow + 4*mc;
   int o = 0;
   #define TAKE(field, n) d.field = o; o += al2(n)
-  TAKE(o_qpos, d.nq); TAKE(o_qvel, d.nv); TAKE(o_act, d.na); TAKE(o_ctrl, d.nu); TAKE(o_qws, d.nv); TAKE(o_dax, 3*d.nv); TAKE(o_dan, 3*d.nv); TAKE(o_qM, d.nM); TAKE(o_fsm, d.nv); TAKE(o_eprm, 8); d.nwz = P[PD_NWE_SPH_IN] + P[PD_NWE_CYL_IN]; TAKE(o_wz, d.nwz);
+  TAKE(o_qpos, d.nq); TAKE(o_qvel, d.nv); TAKE(o_act, d.na); TAKE(o_ctrl, d.nu); TAKE(o_qws, d.nv); TAKE(o_dax, 3*d.nv); TAKE(o_dan, 3*d.nv); TAKE(o_qM, d.nM); TAKE(o_fsm, d.nv); TAKE(o_eprm, 8); d.nwz = P[PD_NWE_SPH_IN] + P[PD_NWE_CYL_IN]; TAKE(o_wz, d.nwz); TAKE(o_cnt, CNT_N/2);
+  d.nvp = chol_pad(d.nv);
   d.o_scr = o;
   #undef TAKE
   // ---- scratch, time-multiplexed.  Lifetimes:
@@ -401,18 +408,21 @@ static void fill_devmodel(const myo_model* mm, const myo_task_cfg* cfg, DevModel
   int t = 0; d.s_U = t; t += al2(3*(d.nsp+2*d.nwe)); d.s_WP = t; t += al2(6*d.nwe); d.s_PL = t; t += al2(d.nsp+d.nwe); d.s_mom = t; t += al2(d.nnz);
   d.s_tlen = t; t += al2(d.nta); d.s_tvel = t; t += al2(d.nta); d.s_tfrc = t; t += al2(d.nta); int sizeT = t;
   t = 0; d.s_cin = t; t += al2(10*d.nbd); d.s_crb = t; t += al2(10*d.nbd); d.s_bf = t; t += al2(6*d.nbd); int sizeC = t;
-  // expensive-candidate buffers share the contact-Jacobian region; they hold every iterative pair when that fits, else as many as the region takes
-  d.kcand = d.npair - d.npair_an; { int room = al2(3*d.maxpath*mc) - al2((d.kcand+1)/2); if (d.kcand > 16 && 7*d.kcand > room) d.kcand = imax(16, room/7); }
-  int candsz = al2((d.npair - d.npair_an + 1)/2) + al2(7*d.kcand);
-  t = 0; d.s_conJ = t; d.s_clist = t; d.s_cres = t + al2((d.npair - d.npair_an + 1)/2); d.s_cidx = t; t += imax(al2(3*d.maxpath*mc), candsz); d.s_efD = t; t += al2(d.maxefc); d.s_efA = t; t += al2(d.maxefc); d.s_eqJ = t; t += al2(d.neq);
+  // the list of ellipsoid candidates that survive the cull shares the contact-Jacobian region (ints; it holds every iterative pair)
+  d.kcand = d.npair - d.npair_an; int candsz = al2((d.kcand + 1)/2);
+  t = 0; d.s_conJ = t; d.s_clist = t; t += imax(al2(3*d.maxpath*mc), candsz); d.s_efD = t; t += al2(d.maxefc); d.s_efA = t; t += al2(d.maxefc); d.s_eqJ = t; t += al2(d.neq);
   d.ngc = P[PD_NGC]; d.s_gpose = d.s_efD; if (t - d.s_efD < al2(6*d.ngc)) t = d.s_efD + al2(6*d.ngc);     // geom poses (collision only) alias the row arrays (written after it)
   d.s_icon = t; t += al2((3*mc + d.nlimrow + 4 + 1)/2); int sizeS3 = t;
   d.s_con = sizeS3; int sizeCon = al2(CON_STRIDE*mc);
-  t = sizeS3; d.s_efR = t; t += al2(d.maxefc); d.s_efV = t; t += al2(d.maxefc); d.s_va = t; t += al2(d.nv); d.s_vg = t; t += al2(d.nv); d.s_vp = t; t += al2(d.nv);
-  d.s_vMa = t; t += al2(d.nv); d.s_vMp = t; t += al2(d.nv);
-  d.s_H = t; d.s_Hs = t; d.s_LD = t + al2(d.nM); d.s_Dinv = t + 2*al2(d.nM); t += imax(al2(d.nv*(d.nv+1)/2), 2*al2(d.nM) + al2(d.nv)); int sizeS4 = t;
+  t = sizeS3; d.s_efR = t; t += al2(d.maxefc); d.s_efV = t; t += al2(d.maxefc); d.s_va = t; t += al2(d.nvp); d.s_vg = t; t += al2(d.nvp); d.s_vp = t; t += al2(d.nvp);
+  d.s_vMa = t; t += al2(d.nvp); d.s_vMp = t; t += al2(d.nvp);
+  d.s_H = t; d.s_Hs = t; d.s_LD = t + al2(d.nM); d.s_Dinv = t + 2*al2(d.nM); t += imax(al2(d.nvp*(d.nvp+1)/2), 2*al2(d.nM) + al2(d.nv)); int sizeS4 = t;
   int scratch = imax(imax(sizeT, sizeC) + K, imax(sizeS3 + sizeCon + K, sizeS4));
   d.s_xpos = scratch - K; d.s_xmat = d.s_xpos + al2(3*d.nbd);
+  // scratch offsets are used relative to the warp base
+  { int32_t* f[] = {&d.s_xpos, &d.s_xmat, &d.s_U, &d.s_WP, &d.s_PL, &d.s_mom, &d.s_tlen, &d.s_tvel, &d.s_tfrc, &d.s_cin, &d.s_crb, &d.s_bf, &d.s_conJ, &d.s_efD, &d.s_efA, &d.s_eqJ,
+                    &d.s_icon, &d.s_con, &d.s_clist, &d.s_gpose, &d.s_efR, &d.s_efV, &d.s_va, &d.s_vg, &d.s_vp, &d.s_vMa, &d.s_vMp, &d.s_H, &d.s_Hs, &d.s_LD, &d.s_Dinv};
+    for (int32_t* q : f) *q += d.o_scr; }
   d.n_per_warp = d.o_scr + scratch;
 }
 
@@ -428,7 +438,7 @@ extern "C" int myo_batch_create(const myo_model* m, int device, int n_env, const
   if (e != cudaSuccess || ndev == 0) return fail("myo_batch_create: no CUDA device available (this library has no CPU fallback)");
   if (device < 0 || device >= ndev) return fail("myo_batch_create: bad device index");
   CUDA_OK(cudaSetDevice(device));
-  myo_batch* b = new myo_batch(); memset(&b->bufs, 0, sizeof(b->bufs)); b->model = m; b->device = device; b->n_env = n_env; b->cfg = *cfg; b->bound = false; b->launches = 0; b->seed = 0; b->env_offset = 0;
+  myo_batch* b = new myo_batch(); memset(&b->bufs, 0, sizeof(b->bufs)); b->model = m; b->device = device; b->n_env = n_env; b->cfg = *cfg; b->bound = false; b->force_dbg = getenv("MYO_B200_DEBUG_KERNEL") && atoi(getenv("MYO_B200_DEBUG_KERNEL")); b->launches = 0; b->seed = 0; b->env_offset = 0;
   fill_devmodel(m, cfg, b->dm);
   if (b->cfg.frame_skip <= 0) b->cfg.frame_skip = 1;
   if (cfg->task == MYO_TASK_POSE && b->dm.nq != b->dm.nv) { delete b; return fail("pose task needs nq == nv"); }
@@ -458,6 +468,7 @@ extern "C" int myo_batch_create(const myo_model* m, int device, int n_env, const
   if (const char* e = getenv("MYO_B200_WARPS_PER_CTA")) { int q = atoi(e); if (q >= 1 && q <= wpc0) wpc = q; }     // tuning override (never above what fits)
   b->warps_per_cta = wpc; b->smem_bytes = b->const_bytes + wpc*per;
   CUDA_OK(cudaFuncSetAttribute(myo_env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes));
+  CUDA_OK(cudaFuncSetAttribute(myo_env_kernel_dbg, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes));
   int ctas_per_sm = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, myo_env_kernel, wpc*32, b->smem_bytes); if (ctas_per_sm < 1) ctas_per_sm = 1;
   int need = (n_env + wpc - 1)/wpc, cap = prop.multiProcessorCount*ctas_per_sm; b->grid = need < cap ? need : cap;
   *out = b; return 0;
@@ -467,13 +478,13 @@ extern "C" int myo_batch_obs_dim(const myo_batch* b) { return b ? b->obs_dim : -
 extern "C" int64_t myo_batch_launch_count(const myo_batch* b) { return b ? b->launches : -1; }
 
 // ---- unit-test hook: the dense solver on caller-supplied systems (one warp per system, shared-memory staging like the step kernel)
-__global__ void myo_chol_test_kernel(const double* H, double* x, int n, int count, int mode) {
-  extern __shared__ __align__(16) double sm[];
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, sys = blockIdx.x*(blockDim.x >> 5) + wid, nt = n*(n+1)/2;
-  double* h = sm + (size_t)wid*(nt + n + 2); double* v = h + nt;
-  if (sys < count) { for (int i = lane; i < nt; i += 32) h[i] = H[(size_t)sys*nt + i]; for (int i = lane; i < n; i += 32) v[i] = x[(size_t)sys*n + i]; }
+__global__ void myo_chol_test_kernel(const double* H, double* x, int n, int count) {
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, sys = blockIdx.x*(blockDim.x >> 5) + wid, nt = n*(n+1)/2, np = chol_pad(n), ntp = np*(np+1)/2;
+  double* h = smem + (size_t)wid*(ntp + np + 2); double* v = h + ntp;
+  if (sys < count) { for (int i = lane; i < ntp; i += 32) h[i] = i < nt ? H[(size_t)sys*nt + i] : 0.0; for (int i = lane; i < np; i += 32) v[i] = i < n ? x[(size_t)sys*n + i] : 0.0; }
   __syncwarp();
-  if (sys < count) { chol_dense(h, n, v, lane, mode); for (int i = lane; i < n; i += 32) x[(size_t)sys*n + i] = v[i]; }
+  if (sys < count) { for (int i = n + lane; i < np; i += 32) h[TRI(i,i)] = 1.0; __syncwarp();      // identity padding, as load_M_dense does
+    chol_dense(h, n, v, lane); for (int i = lane; i < n; i += 32) x[(size_t)sys*n + i] = v[i]; }
 }
 extern "C" int myo_debug_chol_solve(int device, const double* H_host, double* x_host, int n, int count, int mode) {
   if (!H_host || !x_host || n < 1 || n > 64 || count < 1) return fail("myo_debug_chol_solve: bad arguments");
@@ -482,9 +493,9 @@ extern "C" int myo_debug_chol_solve(int device, const double* H_host, double* x_
   const size_t nt = (size_t)n*(n+1)/2; double *dH = nullptr, *dx = nullptr;
   CUDA_OK(cudaMalloc(&dH, nt*count*8)); CUDA_OK(cudaMalloc(&dx, (size_t)n*count*8));
   CUDA_OK(cudaMemcpy(dH, H_host, nt*count*8, cudaMemcpyHostToDevice)); CUDA_OK(cudaMemcpy(dx, x_host, (size_t)n*count*8, cudaMemcpyHostToDevice));
-  const int wpb = 4; size_t smem = (size_t)wpb*(nt + n + 2)*8;
+  const int wpb = 4, np = chol_pad(n); size_t smem = (size_t)wpb*((size_t)np*(np+1)/2 + np + 2)*8; (void)nt;
   CUDA_OK(cudaFuncSetAttribute(myo_chol_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  myo_chol_test_kernel<<<(count + wpb - 1)/wpb, wpb*32, smem>>>(dH, dx, n, count, mode);
+  myo_chol_test_kernel<<<(count + wpb - 1)/wpb, wpb*32, smem>>>(dH, dx, n, count); (void)mode;
   CUDA_OK(cudaGetLastError()); CUDA_OK(cudaDeviceSynchronize());
   CUDA_OK(cudaMemcpy(x_host, dx, (size_t)n*count*8, cudaMemcpyDeviceToHost));
   cudaFree(dH); cudaFree(dx); return 0;
@@ -504,7 +515,12 @@ static int launch(myo_batch* b, StepArgs& a, void* stream) {
   a.b = b->bufs; a.cfg = b->cfg; a.n_env = b->n_env; a.obs_dim = b->obs_dim; a.dt = b->dm.timestep*b->cfg.frame_skip;
   a.seed = b->seed; a.env_offset = b->env_offset; a.balanced = b->smem_bytes > 100*1024;
   a.tol = b->cfg.solver_tolerance > 0 ? b->cfg.solver_tolerance : 1e-10;
-  myo_env_kernel<<<b->grid, b->warps_per_cta*32, b->smem_bytes, (cudaStream_t)stream>>>(b->dm, a);
+  // the debug instantiation serves forward-debug calls, bound parity taps / cycle counters and the barrier / lockstep tuning knobs
+  const myo_buffers& q = b->bufs;
+  const bool dbg = a.mode == 1 || b->force_dbg || b->cfg.barrier_mode != 0 || b->cfg.reserved_i > 1 || q.tap_qacc || q.tap_actuator_force || q.tap_ten_length || q.tap_qfrc_smooth ||
+                   q.tap_ncon || q.tap_contact_pair || q.tap_contact_dist || q.tap_moment || q.tap_qM || q.tap_phase_cycles;
+  if (dbg) myo_env_kernel_dbg<<<b->grid, b->warps_per_cta*32, b->smem_bytes, (cudaStream_t)stream>>>(b->dm, a);
+  else myo_env_kernel<<<b->grid, b->warps_per_cta*32, b->smem_bytes, (cudaStream_t)stream>>>(b->dm, a);
   CUDA_OK(cudaGetLastError()); b->launches++; return 0;
 }
 extern "C" int myo_batch_step(myo_batch* b, void* stream) {

@@ -40,28 +40,33 @@ struct DevModel {
   int32_t hoff[MYO_NSEC];                  // offset of each hot section (in shorts / doubles), -1 if not staged
   int32_t nq, nv, nu, na, nM, njnt;
   int32_t nbd, nlevel, nsp, nwe, nta, nnz, nlim, neq, npair, npair_an, maxpath, ndepth, eq_tree;
-  int32_t maxcon, maxefc, nlimrow, ovr_geom, ngc, s_gpose, coop, chol_mode, solve_sync;          // ovr_geom: collision geom whose size comes from the per-env overrides (-1: none)
+  int32_t maxcon, maxefc, nlimrow, ovr_geom, ngc, s_gpose, solve_sync, nvp;          // ovr_geom: collision geom whose size comes from the per-env overrides (-1: none); nvp: nv padded to the dense solver's order
   double timestep, gx, gy, gz, meaninertia, tolerance;
   // per-warp shared-memory layout, in doubles.  Persistent part:
-  int32_t o_qpos, o_qvel, o_act, o_ctrl, o_qws, o_dax, o_dan, o_qM, o_fsm, o_eprm, o_wz, nwz, o_scr, n_per_warp;
-  // scratch (time-multiplexed by stage; offsets relative to o_scr).  See fill_devmodel() for the overlap rules.
+  int32_t o_qpos, o_qvel, o_act, o_ctrl, o_qws, o_dax, o_dan, o_qM, o_fsm, o_eprm, o_wz, nwz, o_cnt, o_scr, n_per_warp;
+  // scratch (time-multiplexed by stage; offsets relative to the warp base, i.e. o_scr included).  See fill_devmodel() for the overlap rules.
   int32_t s_xpos, s_xmat;                                  // K: body poses, alive kinematics .. constraints
   int32_t s_U, s_WP, s_PL, s_mom, s_tlen, s_tvel, s_tfrc;  // stage 1: tendons + actuation
   int32_t s_cin, s_crb, s_bf;                              // stage 2: CRB / bias
   int32_t s_conJ, s_efD, s_efA, s_eqJ, s_icon, s_con;      // stage 3 -> 4: contacts / constraint rows
-  int32_t s_cres, s_clist, s_cidx, kcand;                  // collision only: results / list / per-pair slot of the expensive (ellipsoid) candidates
+  int32_t s_clist, kcand;                                  // collision only: list of the expensive (ellipsoid) candidates that survived the cull
   int32_t s_efR, s_efV, s_va, s_vg, s_vp, s_vMa, s_vMp, s_H, s_Hs, s_LD, s_Dinv;   // stage 4: Newton
 };
 
-struct Warp {   // per-warp view (registers)
-  double *qpos, *qvel, *act, *ctrl, *qws, *dax, *dan, *qM, *fsm, *eprm, *wz, *scr;   // wz: warm starts of the inverse-wrap roots (inside wraps are listed first)
-  const double* cd; const idx_t* ci;   // staged constants
-  int lane;
-  int ncon, nefc, nlimrow, niter, overflow, ncand;
-};
-#define CI(name) (w.ci + m.hoff[MYO_SEC_##name])
-#define CD(name) (w.cd + m.hoff[MYO_SEC_##name])
-#define SCR(field) (w.scr + m.field)
+// The whole dynamic shared-memory window, declared at file scope so that every pointer derived from it is PROVABLY in the
+// shared address space: the working-set and constant accesses compile to LDS/STS with 32-bit address arithmetic instead of
+// generic 64-bit loads (round 1: 4 048 generic LD.E vs 127 LDS in the kernel's SASS).
+// Layout: [hot f64 tables (m.nD)] [hot int16 lists] [per-warp regions of m.n_per_warp doubles]
+extern __shared__ __align__(16) double smem[];
+
+struct Warp { int base, lane; };   // by value: offset (doubles) of this warp's region in smem, lane id.  Everything else lives in shared memory.
+enum { CNT_ncon, CNT_nefc, CNT_nlimrow, CNT_niter, CNT_overflow, CNT_ncand, CNT_N = 8 };   // per-warp int counters (m.o_cnt)
+#define CI(name) ((const idx_t*)(smem + m.nD) + m.hoff[MYO_SEC_##name])
+#define CD(name) ((const double*)smem + m.hoff[MYO_SEC_##name])
+#define W_(f) (smem + w.base + m.o_##f)                       // persistent per-env arrays
+#define WI_(f) (((int*)(smem + w.base + m.o_cnt))[CNT_##f])   // per-env counters
+#define SCR(field) (smem + w.base + m.field)                  // scratch (m.s_* are offsets from the warp base)
+#define SHARED_PTR(p) __builtin_assume(__isShared(p))         // for pointer PARAMETERS of functions that may not be inlined
 
 // ------------------------------------------------------------------ small math
 __device__ __forceinline__ void cross3(double* r, const double* a, const double* b) {
@@ -93,21 +98,21 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v; }
 
 // world position of program point `pt`
-__device__ __forceinline__ void world_point(const DevModel& m, const Warp& w, int pt, double* out) {
+__device__ __forceinline__ void world_point(const DevModel& m, const Warp w, int pt, double* out) {
   int b = CI(PPT_body)[pt]; const double* x = CD(PPT_xyz) + 3*pt;
   if (b < 0) { out[0]=x[0]; out[1]=x[1]; out[2]=x[2]; }
   else { const double* xp = SCR(s_xpos) + 3*b; mat_vec(out, SCR(s_xmat) + 9*b, x); out[0]+=xp[0]; out[1]+=xp[1]; out[2]+=xp[2]; } }
 
 // spatial motion vector of dof d about the world origin: [omega ; velocity of the point at the origin]
-__device__ __forceinline__ void dof_motion(const DevModel& m, const Warp& w, int d, double* S) {
-  const double* ax = w.dax + 3*d;
+__device__ __forceinline__ void dof_motion(const DevModel& m, const Warp w, int d, double* S) {
+  const double* ax = W_(dax) + 3*d;
   if (CI(PD_lin)[d]) { S[0]=S[1]=S[2]=0; S[3]=ax[0]; S[4]=ax[1]; S[5]=ax[2]; }
-  else { S[0]=ax[0]; S[1]=ax[1]; S[2]=ax[2]; cross3(S+3, w.dan + 3*d, ax); } }
+  else { S[0]=ax[0]; S[1]=ax[1]; S[2]=ax[2]; cross3(S+3, W_(dan) + 3*d, ax); } }
 // velocity of world point p due to unit rate of dof d
-__device__ __forceinline__ void dof_point_vel(const DevModel& m, const Warp& w, int d, const double* p, double* c) {
-  const double* ax = w.dax + 3*d;
+__device__ __forceinline__ void dof_point_vel(const DevModel& m, const Warp w, int d, const double* p, double* c) {
+  const double* ax = W_(dax) + 3*d;
   if (CI(PD_lin)[d]) { c[0]=ax[0]; c[1]=ax[1]; c[2]=ax[2]; }
-  else { double r[3] = {p[0]-w.dan[3*d], p[1]-w.dan[3*d+1], p[2]-w.dan[3*d+2]}; cross3(c, ax, r); } }
+  else { double r[3] = {p[0]-W_(dan)[3*d], p[1]-W_(dan)[3*d+1], p[2]-W_(dan)[3*d+2]}; cross3(c, ax, r); } }
 // f = Ic * S for a spatial inertia about the origin: Ic = (Ixx,Iyy,Izz,Ixy,Ixz,Iyz, m*c[3], m)
 __device__ __forceinline__ void inert_mul(double* f, const double* ic, const double* S) {
   const double* wv = S; const double* v = S + 3; const double* mc = ic + 6; double t[3];
@@ -117,7 +122,7 @@ __device__ __forceinline__ void inert_mul(double* f, const double* ic, const dou
 
 // ------------------------------------------------------------------ phase 1: kinematics (rotation matrices, level by level)
 // also writes each dynamic body's spatial inertia about the world origin (cin) into the stage-2 scratch
-__device__ void phase_kinematics(const DevModel& m, Warp& w) {
+__device__ void phase_kinematics(const DevModel& m, const Warp w) {
   const idx_t* level = CI(PB_level_adr); const idx_t* par = CI(PB_parent); const idx_t* jadr = CI(PB_jadr); const idx_t* jnum = CI(PB_jnum);
   const double* PB = CD(PB_d);
   const idx_t* jtype = CI(jnt_type); const idx_t* jq = CI(jnt_qposadr); const idx_t* jd = CI(jnt_dofadr);
@@ -133,18 +138,18 @@ __device__ void phase_kinematics(const DevModel& m, Warp& w) {
       for (int j = jadr[k]; j < jadr[k] + jnum[k]; j++) {
         int t = jtype[j], qa = jq[j], da = jd[j];
         if (t == 0) {   // free joint: pose straight from qpos (normalised copy of the quaternion; qpos itself is left untouched)
-          const double* qp = w.qpos + qa; double qn[4] = {qp[3], qp[4], qp[5], qp[6]}; quat_norm(qn);
+          const double* qp = W_(qpos) + qa; double qn[4] = {qp[3], qp[4], qp[5], qp[6]}; quat_norm(qn);
           pos[0]=qp[0]; pos[1]=qp[1]; pos[2]=qp[2]; quat2mat(R, qn);
           #pragma unroll
           for (int c = 0; c < 3; c++) {
-            w.dax[3*(da+c)] = c==0; w.dax[3*(da+c)+1] = c==1; w.dax[3*(da+c)+2] = c==2;
-            w.dan[3*(da+c)] = 0; w.dan[3*(da+c)+1] = 0; w.dan[3*(da+c)+2] = 0;
-            w.dax[3*(da+3+c)] = R[c]; w.dax[3*(da+3+c)+1] = R[3+c]; w.dax[3*(da+3+c)+2] = R[6+c];
-            w.dan[3*(da+3+c)] = pos[0]; w.dan[3*(da+3+c)+1] = pos[1]; w.dan[3*(da+3+c)+2] = pos[2]; }
+            W_(dax)[3*(da+c)] = c==0; W_(dax)[3*(da+c)+1] = c==1; W_(dax)[3*(da+c)+2] = c==2;
+            W_(dan)[3*(da+c)] = 0; W_(dan)[3*(da+c)+1] = 0; W_(dan)[3*(da+c)+2] = 0;
+            W_(dax)[3*(da+3+c)] = R[c]; W_(dax)[3*(da+3+c)+1] = R[3+c]; W_(dax)[3*(da+3+c)+2] = R[6+c];
+            W_(dan)[3*(da+3+c)] = pos[0]; W_(dan)[3*(da+3+c)+1] = pos[1]; W_(dan)[3*(da+3+c)+2] = pos[2]; }
         } else {
           const double* al = jaxis + 3*j;
           double ax[3], an[3]; mat_vec(ax, R, al); mat_vec(an, R, jpos + 3*j); an[0]+=pos[0]; an[1]+=pos[1]; an[2]+=pos[2];
-          double dq = w.qpos[qa] - qpos0[qa];
+          double dq = W_(qpos)[qa] - qpos0[qa];
           if (t == 2) { pos[0]+=ax[0]*dq; pos[1]+=ax[1]*dq; pos[2]+=ax[2]*dq; }
           else {   // hinge: R <- R * Rodrigues(local axis, dq); pos keeps the anchor fixed
             double s, c; sincos(dq, &s, &c); double oc = 1-c, x = al[0], y = al[1], z = al[2];
@@ -153,7 +158,7 @@ __device__ void phase_kinematics(const DevModel& m, Warp& w) {
             #pragma unroll
             for (int q = 0; q < 9; q++) R[q] = Rn[q];
             double v[3]; mat_vec(v, R, jpos + 3*j); pos[0]=an[0]-v[0]; pos[1]=an[1]-v[1]; pos[2]=an[2]-v[2]; }
-          w.dax[3*da]=ax[0]; w.dax[3*da+1]=ax[1]; w.dax[3*da+2]=ax[2]; w.dan[3*da]=an[0]; w.dan[3*da+1]=an[1]; w.dan[3*da+2]=an[2];
+          W_(dax)[3*da]=ax[0]; W_(dax)[3*da+1]=ax[1]; W_(dax)[3*da+2]=ax[2]; W_(dan)[3*da]=an[0]; W_(dan)[3*da+1]=an[1]; W_(dan)[3*da+2]=an[2];
         }
       }
       #pragma unroll
@@ -166,7 +171,7 @@ __device__ void phase_kinematics(const DevModel& m, Warp& w) {
 }
 
 // spatial inertia of every dynamic body about the world origin (needs final poses; writes stage-2 scratch)
-__device__ void phase_body_inertia(const DevModel& m, Warp& w) {
+__device__ void phase_body_inertia(const DevModel& m, const Warp w) {
   const double* PB = CD(PB_d); const double* xpos = SCR(s_xpos); const double* xmat = SCR(s_xmat); double* cin = SCR(s_cin);
   for (int k = w.lane; k < m.nbd; k += 32) { const double* bd = PB + k*PB_STRIDE; const double* R = xmat + 9*k;
     double c3[3]; mat_vec(c3, R, bd + 12); c3[0]+=xpos[3*k]; c3[1]+=xpos[3*k+1]; c3[2]+=xpos[3*k+2];
@@ -192,7 +197,7 @@ __device__ __forceinline__ bool seg_intersect(const double* p1, const double* p2
   return a >= 0 && a <= 1 && b >= 0 && b <= 1; }
 
 // 2-D tangent wrap of the path d0 -> circle(rad) -> d1 on the outside; returns arc length or -1 (no wrap)
-__device__ __noinline__ double wrap2d_outside(double* pnt, const double* d, const double* sd, bool has_side, double rad) {
+__device__ __forceinline__ double wrap2d_outside(double* pnt, const double* d, const double* sd, bool has_side, double rad) {
   double sq0 = d[0]*d[0]+d[1]*d[1], sq1 = d[2]*d[2]+d[3]*d[3], sqr = rad*rad;
   double dif0 = d[2]-d[0], dif1 = d[3]-d[1], dd = dif0*dif0+dif1*dif1;
   if (sq0 < sqr || sq1 < sqr || rad < MYO_MINVAL || dd < MYO_MINVAL) return -1;
@@ -214,7 +219,7 @@ __device__ __noinline__ double wrap2d_outside(double* pnt, const double* d, cons
   return rad*acos(clipd((pnt[0]*pnt[2]+pnt[1]*pnt[3])/sqr, -1, 1)); }
 
 // inverse wrap: the path must pass through the inside of the circle (touches it in one point); returns 0 or -1
-__device__ __noinline__ double wrap2d_inside(double* pnt, const double* d, double rad, double* zwarm) {
+__device__ __forceinline__ double wrap2d_inside(double* pnt, const double* d, double rad, double* zwarm) {
   double len0 = sqrt(d[0]*d[0]+d[1]*d[1]), len1 = sqrt(d[2]*d[2]+d[3]*d[3]);
   if (len0 <= rad || len1 <= rad || rad < MYO_MINVAL || len0 < MYO_MINVAL || len1 < MYO_MINVAL) return -1;
   double dif0 = d[2]-d[0], dif1 = d[3]-d[1], dd = dif0*dif0+dif1*dif1;
@@ -252,7 +257,7 @@ __device__ __noinline__ double wrap2d_inside(double* pnt, const double* d, doubl
   pnt[0] = rad*(c*vx - s*vy); pnt[1] = rad*(s*vx + c*vy); pnt[2] = pnt[0]; pnt[3] = pnt[1];
   return 0; }
 
-__device__ void wrap_element(const DevModel& m, const Warp& w, int k, double* U, double* WP, double* PL) {
+__device__ void wrap_element(const DevModel& m, const Warp w, int k, double* U, double* WP, double* PL) {
   const idx_t* we = CI(PWE) + 6*k; const double* wd = CD(PWE_d) + k*PWE_STRIDE;
   double x0[3], x1[3]; world_point(m, w, we[0], x0); world_point(m, w, we[1], x1);
   int gb = we[2]; bool cyl = we[3] == 1, has_side = we[4] >= 0, inside = we[5] != 0; double rad = wd[12];
@@ -268,12 +273,12 @@ __device__ void wrap_element(const DevModel& m, const Warp& w, int k, double* U,
       double n0 = sqrt(dot3(p0,p0)); ax0[0]=p0[0]/n0; ax0[1]=p0[1]/n0; ax0[2]=p0[2]/n0;
       double nrm[3]; cross3(nrm, p0, p1); double nn = sqrt(dot3(nrm,nrm));
       if (nn < MYO_MINVAL) { int i = 0; if (fabs(ax0[1]) > fabs(ax0[i])) i = 1; if (fabs(ax0[2]) > fabs(ax0[i])) i = 2;
-        double o[3] = {1,1,1}; o[i] = 0; cross3(nrm, ax0, o); nn = sqrt(dot3(nrm,nrm)); }
+        double o[3] = {i == 0 ? 0.0 : 1.0, i == 1 ? 0.0 : 1.0, i == 2 ? 0.0 : 1.0}; cross3(nrm, ax0, o); nn = sqrt(dot3(nrm,nrm)); }
       nrm[0]/=nn; nrm[1]/=nn; nrm[2]/=nn; cross3(ax1, nrm, ax0); double n1 = sqrt(dot3(ax1,ax1)); ax1[0]/=n1; ax1[1]/=n1; ax1[2]/=n1; }
     double d[4] = {dot3(p0,ax0), dot3(p0,ax1), dot3(p1,ax0), dot3(p1,ax1)}, sd[2] = {0,0};
     if (has_side) { const double* s = wd + 13; sd[0] = dot3(s,ax0); sd[1] = dot3(s,ax1); double n = sqrt(sd[0]*sd[0]+sd[1]*sd[1]);
       if (n < MYO_MINVAL) { sd[0] = rad; sd[1] = 0; } else { sd[0] *= rad/n; sd[1] *= rad/n; } }
-    wlen = inside ? wrap2d_inside(pnt, d, rad, w.wz + k) : wrap2d_outside(pnt, d, sd, has_side, rad);
+    wlen = inside ? wrap2d_inside(pnt, d, rad, W_(wz) + k) : wrap2d_outside(pnt, d, sd, has_side, rad);
   }
   double* u0 = U + 3*(m.nsp + 2*k); double* u1 = u0 + 3; double* w0 = WP + 6*k; double* w1 = w0 + 3;
   if (wlen < 0) {   // straight segment: both "wrap points" sit at x1 (on the line), same direction for both pieces
@@ -296,7 +301,7 @@ __device__ void wrap_element(const DevModel& m, const Warp& w, int k, double* U,
   PL[m.nsp + k] = na + wlen + nb;
 }
 
-__device__ void phase_tendon(const DevModel& m, Warp& w) {
+__device__ void phase_tendon(const DevModel& m, const Warp w) {
   double* U = SCR(s_U); double* WP = SCR(s_WP); double* PL = SCR(s_PL);
   const idx_t* sp = CI(PSP);
   for (int k = w.lane; k < m.nsp; k += 32) { double a[3], b[3]; world_point(m, w, sp[2*k], a); world_point(m, w, sp[2*k+1], b);
@@ -308,7 +313,7 @@ __device__ void phase_tendon(const DevModel& m, Warp& w) {
   __syncwarp();
 }
 // second half: moments per structural non-zero, tendon lengths and velocities (a CTA barrier in between re-aligns the warps)
-__device__ void phase_tendon_moments(const DevModel& m, Warp& w) {
+__device__ void phase_tendon_moments(const DevModel& m, const Warp w) {
   double* U = SCR(s_U); double* WP = SCR(s_WP); double* PL = SCR(s_PL); double* mom = SCR(s_mom);
   double* tlen = SCR(s_tlen); double* tvel = SCR(s_tvel); double* tfrc = SCR(s_tfrc);
   const idx_t* nzd = CI(PNZ_dof); const idx_t* tadr = CI(PNZ_term_adr); const idx_t* term = CI(PTERM);
@@ -327,7 +332,7 @@ __device__ void phase_tendon_moments(const DevModel& m, Warp& w) {
   const idx_t* nadr = CI(PT_nz_adr);
   for (int t = w.lane; t < m.nta; t += 32) { double v = 0;
     #pragma unroll 1
-    for (int z = nadr[t]; z < nadr[t+1]; z++) v += mom[z]*w.qvel[nzd[z]];
+    for (int z = nadr[t]; z < nadr[t+1]; z++) v += mom[z]*W_(qvel)[nzd[z]];
     tvel[t] = v; tfrc[t] = 0; }
   __syncwarp();
 }
@@ -342,12 +347,12 @@ __device__ __forceinline__ double muscle_FL(double L, double lmin, double lmax) 
   return 0; }
 
 // tap_force / tap_len: nullable global rows for the parity taps (values before the activation is advanced)
-__device__ void phase_actuation(const DevModel& m, Warp& w, bool integrate, double* tap_force, double* tap_len) {
+__device__ void phase_actuation(const DevModel& m, const Warp w, bool integrate, double* tap_force, double* tap_len) {
   const idx_t* atend = CI(PA_tendon); const idx_t* acls = CI(PA_cls); const double* PAc = CD(PA_d); const double* PAm = CD(PAM_d);
   double* tlen = SCR(s_tlen); double* tvel = SCR(s_tvel); double* tfrc = SCR(s_tfrc); double* mom = SCR(s_mom);
   for (int i = w.lane; i < m.nu; i += 32) { const double* a = PAc + acls[i]*PA_STRIDE; const double* am = PAm + i*PAM_STRIDE; int t = atend[i];
     const double *dyn = a, *gp = a+3, *bp = a+9, *cr = a+13; double gear = am[4], lr0 = am[2], lr1 = am[3];
-    double len = gear*tlen[t], vel = gear*tvel[t], ctrl = w.ctrl[i], act = w.act[i];
+    double len = gear*tlen[t], vel = gear*tvel[t], ctrl = W_(ctrl)[i], act = W_(act)[i];
     if (a[15] != 0) ctrl = clipd(ctrl, cr[0], cr[1]);
     // activation dynamics
     double cc = clipd(ctrl, 0, 1), ac = clipd(act, 0, 1), ta = dyn[0]*(0.5+1.5*ac), td = dyn[1]/(0.5+1.5*ac), dctrl = cc - act, tau;
@@ -367,19 +372,19 @@ __device__ void phase_actuation(const DevModel& m, Warp& w, bool integrate, doub
     tfrc[t] = gear*force;   // one actuator per tendon (checked on the host)
     if (tap_force) tap_force[i] = force;
     if (tap_len) tap_len[i] = len;
-    if (integrate) w.act[i] = act + m.timestep*actdot;   // mj_Euler's activation update; act is not read again this substep
+    if (integrate) W_(act)[i] = act + m.timestep*actdot;   // mj_Euler's activation update; act is not read again this substep
   }
   __syncwarp();
   const idx_t* cadr = CI(PCOL_adr); const idx_t* col = CI(PCOL); const idx_t* nzt = CI(PNZ_tendon); const double* dofp = CD(PDOF_d);
-  for (int d = w.lane; d < m.nv; d += 32) { double s = -dofp[2*d+1]*w.qvel[d];
+  for (int d = w.lane; d < m.nv; d += 32) { double s = -dofp[2*d+1]*W_(qvel)[d];
     #pragma unroll 1
     for (int e = cadr[d]; e < cadr[d+1]; e++) { int z = col[e]; s += mom[z]*tfrc[nzt[z]]; }
-    w.fsm[d] = s; }
+    W_(fsm)[d] = s; }
   __syncwarp();
 }
 
 // ------------------------------------------------------------------ phase 4: composite inertia -> joint-space mass matrix
-__device__ void phase_crb(const DevModel& m, Warp& w) {
+__device__ void phase_crb(const DevModel& m, const Warp w) {
   double* crb = SCR(s_crb); const double* cin = SCR(s_cin); const idx_t* sadr = CI(PSUB_adr); const idx_t* sub = CI(PSUB);
   for (int k = w.lane; k < m.nbd; k += 32) { double acc[10] = {0,0,0,0,0,0,0,0,0,0};
     #pragma unroll 1
@@ -394,17 +399,17 @@ __device__ void phase_crb(const DevModel& m, Warp& w) {
     dof_motion(m, w, i, Si); inert_mul(f, crb + 10*dbody[i], Si); dof_motion(m, w, j, Sj);
     double v = Sj[0]*f[0]+Sj[1]*f[1]+Sj[2]*f[2]+Sj[3]*f[3]+Sj[4]*f[4]+Sj[5]*f[5];
     if (i == j) v += dofp[2*i];
-    w.qM[e] = v; }
+    W_(qM)[e] = v; }
   __syncwarp();
 }
 
 // ------------------------------------------------------------------ phase 5: Coriolis/centrifugal/gravity bias (subtracts from fsm)
-__device__ void phase_bias(const DevModel& m, Warp& w) {
+__device__ void phase_bias(const DevModel& m, const Warp w) {
   double* bf = SCR(s_bf); const double* cin = SCR(s_cin); const idx_t* cadr = CI(PCH_adr); const idx_t* ch = CI(PCH);
   for (int k = w.lane; k < m.nbd; k += 32) {
     double v[6] = {0,0,0,0,0,0}, vh[6] = {0,0,0,0,0,0}, a[6] = {0,0,0,-m.gx,-m.gy,-m.gz};
     #pragma unroll 1
-    for (int e = cadr[k]; e < cadr[k+1]; e++) { int d = ch[e] >> 1, flag = ch[e] & 1; double S[6], qd = w.qvel[d];
+    for (int e = cadr[k]; e < cadr[k+1]; e++) { int d = ch[e] >> 1, flag = ch[e] & 1; double S[6], qd = W_(qvel)[d];
       dof_motion(m, w, d, S);
       if (!flag) { for (int c = 0; c < 6; c++) vh[c] = v[c]; }
       double c0[3], c1[3], c2[3]; cross3(c0, vh, S); cross3(c1, vh, S+3); cross3(c2, vh+3, S);   // vh x_m S
@@ -419,25 +424,25 @@ __device__ void phase_bias(const DevModel& m, Warp& w) {
   for (int d = w.lane; d < m.nv; d += 32) { double S[6], tot = 0; dof_motion(m, w, d, S); int b = dbody[d];
     #pragma unroll 1
     for (int e = sadr[b]; e < sadr[b+1]; e++) { const double* f = bf + 6*sub[e]; tot += S[0]*f[0]+S[1]*f[1]+S[2]*f[2]+S[3]*f[3]+S[4]*f[4]+S[5]*f[5]; }
-    w.fsm[d] -= tot; }
+    W_(fsm)[d] -= tot; }
   __syncwarp();
 }
 
 // ------------------------------------------------------------------ phase 6: collision (analytic primitives)
 // world position and z axis of every collision geom, once per substep (each geom takes part in ~20 pairs)
-__device__ __forceinline__ void geom_pose_all(const DevModel& m, const Warp& w) {
+__device__ __forceinline__ void geom_pose_all(const DevModel& m, const Warp w) {
   double* GP = SCR(s_gpose);
   for (int g = w.lane; g < m.ngc; g += 32) { int b = CI(PG_body)[g]; const double* gd = CD(PG_d) + g*PG_STRIDE; double* o = GP + 6*g;
     if (b < 0) { o[0]=gd[0]; o[1]=gd[1]; o[2]=gd[2]; o[3]=gd[5]; o[4]=gd[8]; o[5]=gd[11]; }
     else { const double* X = SCR(s_xmat) + 9*b; const double* xp = SCR(s_xpos) + 3*b; mat_vec(o, X, gd); o[0]+=xp[0]; o[1]+=xp[1]; o[2]+=xp[2];
       double z[3] = {gd[5], gd[8], gd[11]}; mat_vec(o+3, X, z); } }
   __syncwarp(); }
-__device__ __forceinline__ void geom_pose(const DevModel& m, const Warp& w, int g, double* pos, double* axis /* z column */) {
+__device__ __forceinline__ void geom_pose(const DevModel& m, const Warp w, int g, double* pos, double* axis /* z column */) {
   const double* o = SCR(s_gpose) + 6*g; pos[0]=o[0]; pos[1]=o[1]; pos[2]=o[2]; axis[0]=o[3]; axis[1]=o[4]; axis[2]=o[5]; }
 
-__device__ __forceinline__ const double* geom_size(const DevModel& m, const Warp& w, int g) { return g == m.ovr_geom ? w.eprm + 3 : CD(PG_d) + g*PG_STRIDE + 12; }
+__device__ __forceinline__ const double* geom_size(const DevModel& m, const Warp w, int g) { return g == m.ovr_geom ? W_(eprm) + 3 : CD(PG_d) + g*PG_STRIDE + 12; }
 // full world rotation of a collision geom (ellipsoids need it)
-__device__ __forceinline__ void geom_mat(const DevModel& m, const Warp& w, int g, double* mat) {
+__device__ __forceinline__ void geom_mat(const DevModel& m, const Warp w, int g, double* mat) {
   int b = CI(PG_body)[g]; const double* gd = CD(PG_d) + g*PG_STRIDE;
   if (b < 0) {
     #pragma unroll
@@ -461,7 +466,7 @@ __device__ __forceinline__ double ell_sd(const double* dl, const double* R1, con
     f = dot3(d, dl) - n1 - n2;
     if (f > bound) return f;
     // tangent basis
-    double e[3] = {0,0,0}; { int k = fabs(d[0]) < fabs(d[1]) ? (fabs(d[0]) < fabs(d[2]) ? 0 : 2) : (fabs(d[1]) < fabs(d[2]) ? 1 : 2); e[k] = 1; }
+    double e[3]; { int k = fabs(d[0]) < fabs(d[1]) ? (fabs(d[0]) < fabs(d[2]) ? 0 : 2) : (fabs(d[1]) < fabs(d[2]) ? 1 : 2); e[0] = k == 0; e[1] = k == 1; e[2] = k == 2; }
     double t1[3], t2[3]; cross3(t1, d, e); { double q = 1.0/sqrt(dot3(t1,t1)); t1[0]*=q; t1[1]*=q; t1[2]*=q; } cross3(t2, d, t1);
     double g1 = dot3(t1, g), g2 = dot3(t2, g), scale = sqrt(dot3(dl,dl)) + n1 + n2;
     if (g1*g1 + g2*g2 < 1e-24*scale*scale) break;      // tangential gradient ~1e-12: direction converged to round-off
@@ -493,28 +498,26 @@ __device__ __forceinline__ double ell_sd(const double* dl, const double* R1, con
   return f;
 }
 
-struct ConOut { int n; double dist[2]; double pos[2][3]; double nrm[2][3]; double yh[3]; bool has_y; };
+// up to two contacts of one geom pair, all scalars (arrays here end up in local memory: round 1's kernel carried a 1.3 KB stack frame)
+struct Con1 { double dist, px, py, pz, nx, ny, nz; };
+struct ConOut { int n; Con1 c0, c1; double yx, yy, yz; bool has_y; };
+__device__ __forceinline__ void con_put(ConOut& o, double dist, double px, double py, double pz, double nx, double ny, double nz) {
+  if (o.n == 0) { o.c0.dist = dist; o.c0.px = px; o.c0.py = py; o.c0.pz = pz; o.c0.nx = nx; o.c0.ny = ny; o.c0.nz = nz; }
+  else { o.c1.dist = dist; o.c1.px = px; o.c1.py = py; o.c1.pz = pz; o.c1.nx = nx; o.c1.ny = ny; o.c1.nz = nz; }
+  o.n++; }
 __device__ __forceinline__ void sph_sph(ConOut& o, double margin, const double* p1, double r1, const double* p2, double r2) {
   double dv[3] = {p2[0]-p1[0], p2[1]-p1[1], p2[2]-p1[2]}, cd = sqrt(dot3(dv,dv)), dist = cd-r1-r2;
   if (dist > margin || o.n >= 2) return;
   double nx, ny, nz; if (cd < MYO_MINVAL) { nx = 1; ny = 0; nz = 0; } else { double q = 1.0/cd; nx = dv[0]*q; ny = dv[1]*q; nz = dv[2]*q; }
   double off = r1+0.5*dist;
-  if (o.n == 0) { o.dist[0] = dist; o.nrm[0][0] = nx; o.nrm[0][1] = ny; o.nrm[0][2] = nz; o.pos[0][0] = p1[0]+nx*off; o.pos[0][1] = p1[1]+ny*off; o.pos[0][2] = p1[2]+nz*off; }
-  else { o.dist[1] = dist; o.nrm[1][0] = nx; o.nrm[1][1] = ny; o.nrm[1][2] = nz; o.pos[1][0] = p1[0]+nx*off; o.pos[1][1] = p1[1]+ny*off; o.pos[1][2] = p1[2]+nz*off; }
-  o.n++; }
+  con_put(o, dist, p1[0]+nx*off, p1[1]+ny*off, p1[2]+nz*off, nx, ny, nz); }
 __device__ __forceinline__ void plane_sph(ConOut& o, double margin, const double* pp, const double* pn, const double* sp, double r) {
   double dv[3] = {sp[0]-pp[0], sp[1]-pp[1], sp[2]-pp[2]}, dist = dot3(dv,pn)-r;
   if (dist > margin || o.n >= 2) return;
   double off = r+0.5*dist;
-  if (o.n == 0) { o.dist[0] = dist;
-    #pragma unroll
-    for (int k = 0; k < 3; k++) { o.nrm[0][k] = pn[k]; o.pos[0][k] = sp[k]-pn[k]*off; } }
-  else { o.dist[1] = dist;
-    #pragma unroll
-    for (int k = 0; k < 3; k++) { o.nrm[1][k] = pn[k]; o.pos[1][k] = sp[k]-pn[k]*off; } }
-  o.n++; }
+  con_put(o, dist, sp[0]-pn[0]*off, sp[1]-pn[1]*off, sp[2]-pn[2]*off, pn[0], pn[1], pn[2]); }
 
-__device__ __forceinline__ void collide_analytic(const DevModel& m, const Warp& w, int p, ConOut& o) {
+__device__ __forceinline__ void collide_analytic(const DevModel& m, const Warp w, int p, ConOut& o) {
   const idx_t* pr = CI(PPAIR) + PPAIR_ISTRIDE*p; const double* pd = CD(PPAIR_d) + pr[6]*PPAIR_STRIDE;
   int g1 = pr[0], g2 = pr[1], ct = pr[5]; double margin = pd[0]; o.n = 0; o.has_y = false;
   const double* s1 = geom_size(m, w, g1); const double* s2 = geom_size(m, w, g2);
@@ -545,16 +548,16 @@ __device__ __forceinline__ void collide_analytic(const DevModel& m, const Warp& 
   } else if (ct == CT_PLANE_CAP) { double e[3];
     for (int k = 0; k < 3; k++) e[k] = x2[k]+a2[k]*s2[1]; plane_sph(o, margin, x1, a1, e, s2[0]);
     for (int k = 0; k < 3; k++) e[k] = x2[k]-a2[k]*s2[1]; plane_sph(o, margin, x1, a1, e, s2[0]);
-    o.has_y = true; o.yh[0]=a2[0]; o.yh[1]=a2[1]; o.yh[2]=a2[2];
+    o.has_y = true; o.yx = a2[0]; o.yy = a2[1]; o.yz = a2[2];
   } else if (ct == CT_PLANE_ELL) {   // deepest point of the ellipsoid along -normal
     double R2[9], nl[3], u[3], pw[3]; geom_mat(m, w, g2, R2); matT_vec(nl, R2, a1);
     u[0] = s2[0]*s2[0]*nl[0]; u[1] = s2[1]*s2[1]*nl[1]; u[2] = s2[2]*s2[2]*nl[2]; double nn = sqrt(dot3(nl, u)); mat_vec(pw, R2, u);
     double pos[3] = {x2[0]-pw[0]/nn, x2[1]-pw[1]/nn, x2[2]-pw[2]/nn}, dv[3] = {pos[0]-x1[0], pos[1]-x1[1], pos[2]-x1[2]}, dist = dot3(dv, a1);
-    if (dist <= margin) { o.n = 1; o.dist[0] = dist; for (int k = 0; k < 3; k++) { o.nrm[0][k] = a1[k]; o.pos[0][k] = pos[k]-a1[k]*0.5*dist; } }
+    if (dist <= margin) con_put(o, dist, pos[0]-a1[0]*0.5*dist, pos[1]-a1[1]*0.5*dist, pos[2]-a1[2]*0.5*dist, a1[0], a1[1], a1[2]);
   }
 }
 
-__device__ __forceinline__ void collide_ellipsoid(const DevModel& m, const Warp& w, int p, ConOut& o) {
+__device__ __forceinline__ void collide_ellipsoid(const DevModel& m, const Warp w, int p, ConOut& o) {
   const idx_t* pr = CI(PPAIR) + PPAIR_ISTRIDE*p; const double* pd = CD(PPAIR_d) + pr[6]*PPAIR_STRIDE;
   int g1 = pr[0], g2 = pr[1], ct = pr[5]; double margin = pd[0]; o.n = 0; o.has_y = false;
   const double* s1 = geom_size(m, w, g1); const double* s2 = geom_size(m, w, g2);
@@ -565,7 +568,7 @@ __device__ __forceinline__ void collide_ellipsoid(const DevModel& m, const Warp&
     // (1) distance to the capsule's whole AXIS LINE = distance, in the plane normal to the axis, from the projected centre to the
     //     ellipsoid's shadow (an ellipse): a 1-D Newton on the unit circle  max_u  c.u - sqrt(u'Au).  Every iterate's value is a
     //     lower bound of the segment distance, so a pair that is provably out of its margin leaves at once.
-    double e1[3], e2[3]; { double e[3] = {0,0,0}; int k = fabs(a1[0]) < fabs(a1[1]) ? (fabs(a1[0]) < fabs(a1[2]) ? 0 : 2) : (fabs(a1[1]) < fabs(a1[2]) ? 1 : 2); e[k] = 1;
+    double e1[3], e2[3]; { double e[3]; int k = fabs(a1[0]) < fabs(a1[1]) ? (fabs(a1[0]) < fabs(a1[2]) ? 0 : 2) : (fabs(a1[1]) < fabs(a1[2]) ? 1 : 2); e[0] = k == 0; e[1] = k == 1; e[2] = k == 2;
       cross3(e1, a1, e); double q = 1.0/sqrt(dot3(e1,e1)); e1[0]*=q; e1[1]*=q; e1[2]*=q; cross3(e2, a1, e1); }
     double b1[3], b2[3]; matT_vec(b1, R2, e1); matT_vec(b2, R2, e2);
     double v0 = s2[0]*s2[0], v1 = s2[1]*s2[1], v2 = s2[2]*s2[2];
@@ -597,20 +600,19 @@ __device__ __forceinline__ void collide_ellipsoid(const DevModel& m, const Warp&
       t = t > h ? h : -h; double dl[3] = {dv[0]-a1[0]*t, dv[1]-a1[1]*t, dv[2]-a1[2]*t};
       sd = ell_sd(dl, nullptr, nullptr, R2, s2, d, p1, p2, margin + r); }
     double dist = sd - r;
-    if (dist <= margin) { o.n = 1; o.dist[0] = dist; for (int k = 0; k < 3; k++) { o.nrm[0][k] = d[k];
-        double wa = x1[k]+a1[k]*t + d[k]*r, wb = x2[k]-p2[k]; o.pos[0][k] = 0.5*(wa+wb); } }
+    if (dist <= margin) con_put(o, dist, 0.5*((x1[0]+a1[0]*t + d[0]*r) + (x2[0]-p2[0])), 0.5*((x1[1]+a1[1]*t + d[1]*r) + (x2[1]-p2[1])), 0.5*((x1[2]+a1[2]*t + d[2]*r) + (x2[2]-p2[2])), d[0], d[1], d[2]);
   } else if (ct == CT_ELL_ELL) {
     double dl[3] = {x2[0]-x1[0], x2[1]-x1[1], x2[2]-x1[2]}, cd = sqrt(dot3(dl,dl));
     if (cd - fmax(s1[0], fmax(s1[1], s1[2])) - fmax(s2[0], fmax(s2[1], s2[2])) > margin) return;
     double R1[9], R2[9], d[3], p1[3], p2[3]; geom_mat(m, w, g1, R1); geom_mat(m, w, g2, R2);
     if (cd < MYO_MINVAL) { d[0]=1; d[1]=0; d[2]=0; } else { d[0]=dl[0]/cd; d[1]=dl[1]/cd; d[2]=dl[2]/cd; }
     double dist = ell_sd(dl, R1, s1, R2, s2, d, p1, p2, margin);
-    if (dist <= margin) { o.n = 1; o.dist[0] = dist; for (int k = 0; k < 3; k++) { o.nrm[0][k] = d[k]; o.pos[0][k] = 0.5*((x1[k]+p1[k]) + (x2[k]-p2[k])); } }
+    if (dist <= margin) con_put(o, dist, 0.5*((x1[0]+p1[0]) + (x2[0]-p2[0])), 0.5*((x1[1]+p1[1]) + (x2[1]-p2[1])), 0.5*((x1[2]+p1[2]) + (x2[2]-p2[2])), d[0], d[1], d[2]);
   }
 }
 
 // cheap conservative test for the iterative (ellipsoid) colliders: can this pair be within its margin at all?
-__device__ __forceinline__ bool expensive_candidate(const DevModel& m, const Warp& w, int p) {
+__device__ __forceinline__ bool expensive_candidate(const DevModel& m, const Warp w, int p) {
   const idx_t* pr = CI(PPAIR) + PPAIR_ISTRIDE*p; const double* pd = CD(PPAIR_d) + pr[6]*PPAIR_STRIDE;
   int g1 = pr[0], g2 = pr[1]; const double* s1 = geom_size(m, w, g1); const double* s2 = geom_size(m, w, g2); double margin = pd[0];
   double x1[3], a1[3], x2[3], a2[3]; geom_pose(m, w, g1, x1, a1); geom_pose(m, w, g2, x2, a2);
@@ -628,22 +630,24 @@ __device__ __forceinline__ bool expensive_candidate(const DevModel& m, const War
   double R1[9], R2[9], b[3], c[3], d[3] = {dv[0]/cd, dv[1]/cd, dv[2]/cd}; geom_mat(m, w, g1, R1); geom_mat(m, w, g2, R2); matT_vec(b, R1, d); matT_vec(c, R2, d);
   return cd - sqrt(s1[0]*s1[0]*b[0]*b[0]+s1[1]*s1[1]*b[1]*b[1]+s1[2]*s1[2]*b[2]*b[2]) - sqrt(s2[0]*s2[0]*c[0]*c[0]+s2[1]*s2[1]*c[1]*c[1]+s2[2]*s2[2]*c[2]*c[2]) <= margin; }
 
-__device__ __forceinline__ void store_contact(const DevModel& m, Warp& w, double* con, int* icon, int ci, int p, const ConOut& o, int c) {
+__device__ __forceinline__ void store_contact(const DevModel& m, double* con, int* icon, int ci, int p, const Con1& c, const ConOut& o) {
   if (ci >= m.maxcon) return;
-  double* cd = con + ci*CON_STRIDE; cd[0] = o.dist[c]; cd[1]=o.pos[c][0]; cd[2]=o.pos[c][1]; cd[3]=o.pos[c][2];
-  double* f = cd + 4; f[0]=o.nrm[c][0]; f[1]=o.nrm[c][1]; f[2]=o.nrm[c][2];
+  double* cd = con + ci*CON_STRIDE; cd[0] = c.dist; cd[1] = c.px; cd[2] = c.py; cd[3] = c.pz;
+  double* f = cd + 4; f[0] = c.nx; f[1] = c.ny; f[2] = c.nz;
   // complete the contact frame (rows: normal, tangent1, tangent2)
-  double y[3] = {0,0,0};
-  if (o.has_y) { y[0]=o.yh[0]; y[1]=o.yh[1]; y[2]=o.yh[2]; }
-  if (sqrt(dot3(y,y)) < 0.5) { y[0]=0; y[1]=0; y[2]=0; if (f[1] < 0.5 && f[1] > -0.5) y[1] = 1; else y[2] = 1; }
-  double dd = dot3(f, y); y[0]-=dd*f[0]; y[1]-=dd*f[1]; y[2]-=dd*f[2]; double n = 1.0/sqrt(dot3(y,y)); y[0]*=n; y[1]*=n; y[2]*=n;
-  f[3]=y[0]; f[4]=y[1]; f[5]=y[2];
+  double y0 = 0, y1 = 0, y2 = 0;
+  if (o.has_y) { y0 = o.yx; y1 = o.yy; y2 = o.yz; }
+  if (sqrt(y0*y0+y1*y1+y2*y2) < 0.5) { y0 = 0; y1 = 0; y2 = 0; if (c.ny < 0.5 && c.ny > -0.5) y1 = 1; else y2 = 1; }
+  double dd = c.nx*y0+c.ny*y1+c.nz*y2; y0 -= dd*c.nx; y1 -= dd*c.ny; y2 -= dd*c.nz; double n = 1.0/sqrt(y0*y0+y1*y1+y2*y2);
+  f[3] = y0*n; f[4] = y1*n; f[5] = y2*n;
   icon[ci] = p; }
 
 // Contacts are listed analytic colliders first (pair order), then the iterative ellipsoid colliders (pair order).
-__device__ void phase_collision(const DevModel& m, Warp& w) {
+// Overflow (more contacts than maxcon, or more surviving ellipsoid candidates than kcand): the extra ones are dropped first-come and
+// CNT_overflow is set; the step kernel ORs it into the caller's sticky per-env `overflow` buffer.
+__device__ void phase_collision(const DevModel& m, const Warp w) {
   double* con = SCR(s_con); int* icon = (int*)SCR(s_icon);
-  int ncon = 0; w.overflow = 0;
+  int ncon = 0, overflow = 0;
   geom_pose_all(m, w);
   // analytic primitives: one pair per lane
   #pragma unroll 1
@@ -651,55 +655,26 @@ __device__ void phase_collision(const DevModel& m, Warp& w) {
     if (p < m.npair_an) collide_analytic(m, w, p, o);
     unsigned m0 = __ballot_sync(FULL, o.n >= 1), m1 = __ballot_sync(FULL, o.n >= 2), lt = (1u << w.lane) - 1;
     int idx = ncon + __popc(m0 & lt) + __popc(m1 & lt);
-    if (o.n >= 1) store_contact(m, w, con, icon, idx, p, o, 0);
-    if (o.n >= 2) store_contact(m, w, con, icon, idx + 1, p, o, 1);
+    if (o.n >= 1) store_contact(m, con, icon, idx, p, o.c0, o);
+    if (o.n >= 2) store_contact(m, con, icon, idx + 1, p, o.c1, o);
     ncon += __popc(m0) + __popc(m1); }
-  // iterative ellipsoid colliders: rare and expensive -> conservative cull + compaction here; the survivors of ALL envs of the CTA are
-  // then evaluated cooperatively (collision_coop), one candidate per thread, so that no warp waits for another env's worst case
-  int* clist = (int*)SCR(s_clist); int ncand = 0;
-  #pragma unroll 1
-  for (int cbase = m.npair_an; cbase < m.npair; cbase += 32) { int p = cbase + w.lane; bool cand = p < m.npair && expensive_candidate(m, w, p);
-    unsigned mk = __ballot_sync(FULL, cand); int slot = ncand + __popc(mk & ((1u << w.lane) - 1)); if (cand && slot < m.kcand) clist[slot] = p; ncand += __popc(mk); }
-  if (ncand > m.kcand) { ncand = m.kcand; w.overflow = 1; }   // (kcand = capacity of the candidate buffers)
-  w.ncand = ncand;
-  if (ncon > m.maxcon) { w.overflow = 1; ncon = m.maxcon; }
-  w.ncon = ncon;
-  __syncwarp();
-}
-
-// cooperative evaluation: flat item f -> (owner warp, candidate k); the owner's poses / overrides are read from ITS shared-memory region
-__device__ void collision_coop(const DevModel& m, const Warp& self, double* warp0, const int* ncand_of, int w0, int nw) {
-  int total = 0; for (int q = 0; q < nw; q++) total += ncand_of[w0+q];
-  #pragma unroll 1
-  for (int f = threadIdx.x - 32*w0; f < total; f += 32*nw) { int owner = w0, k = f; while (k >= ncand_of[owner]) { k -= ncand_of[owner]; owner++; }
-    Warp w = self; double* base = warp0 + (size_t)owner*m.n_per_warp; w.scr = base + m.o_scr; w.eprm = base + m.o_eprm; w.qpos = base + m.o_qpos;
-    const int* clist = (const int*)SCR(s_clist); double* r = SCR(s_cres) + 7*k;
-    ConOut o; o.n = 0; o.has_y = false; collide_ellipsoid(m, w, clist[k], o);
-    r[0] = o.n ? o.dist[0] : 1e30; for (int c = 0; c < 3; c++) { r[1+c] = o.pos[0][c]; r[4+c] = o.nrm[0][c]; } }
-}
-// in-warp alternative to the cooperative pass: one candidate per lane of the owning warp (no CTA barriers)
-__device__ void collision_direct(const DevModel& m, Warp& w) {
-  double* con = SCR(s_con); int* icon = (int*)SCR(s_icon); const int* clist = (const int*)SCR(s_clist); int ncon = w.ncon;
-  #pragma unroll 1
-  for (int kb = 0; kb < w.ncand; kb += 32) { int k = kb + w.lane; ConOut o; o.n = 0; o.has_y = false; int p = 0;
-    if (k < w.ncand) { p = clist[k]; collide_ellipsoid(m, w, p, o); }
-    unsigned m0 = __ballot_sync(FULL, o.n >= 1); int idx = ncon + __popc(m0 & ((1u << w.lane) - 1));
-    if (o.n) store_contact(m, w, con, icon, idx, p, o, 0);
-    ncon += __popc(m0); }
-  if (ncon > m.maxcon) { w.overflow = 1; ncon = m.maxcon; }
-  w.ncon = ncon;
-  __syncwarp();
-}
-// append the cooperative results (candidate order = pair order) to this env's contact list
-__device__ void collision_merge(const DevModel& m, Warp& w) {
-  double* con = SCR(s_con); int* icon = (int*)SCR(s_icon); const int* clist = (const int*)SCR(s_clist); const double* cres = SCR(s_cres); int ncon = w.ncon;
-  #pragma unroll 1
-  for (int kb = 0; kb < w.ncand; kb += 32) { int k = kb + w.lane; ConOut o; o.n = 0; o.has_y = false; int p = 0;
-    if (k < w.ncand) { const double* r = cres + 7*k; p = clist[k]; if (r[0] < 1e29) { o.n = 1; o.dist[0] = r[0]; for (int c = 0; c < 3; c++) { o.pos[0][c] = r[1+c]; o.nrm[0][c] = r[4+c]; } } }
-    unsigned m0 = __ballot_sync(FULL, o.n >= 1); int idx = ncon + __popc(m0 & ((1u << w.lane) - 1));
-    if (o.n) store_contact(m, w, con, icon, idx, p, o, 0);
-    ncon += __popc(m0); }
-  if (ncon > m.maxcon) { w.overflow = 1; ncon = m.maxcon; }
-  w.ncon = ncon;
+  if (ncon > m.maxcon) { overflow = 1; ncon = m.maxcon; }
+  if (m.npair > m.npair_an) {
+    // iterative ellipsoid colliders: rare and expensive -> conservative cull + compaction, then one surviving candidate per lane
+    int* clist = (int*)SCR(s_clist); int ncand = 0;
+    #pragma unroll 1
+    for (int cbase = m.npair_an; cbase < m.npair; cbase += 32) { int p = cbase + w.lane; bool cand = p < m.npair && expensive_candidate(m, w, p);
+      unsigned mk = __ballot_sync(FULL, cand); int slot = ncand + __popc(mk & ((1u << w.lane) - 1)); if (cand && slot < m.kcand) clist[slot] = p; ncand += __popc(mk); }
+    if (ncand > m.kcand) { ncand = m.kcand; overflow = 1; }   // (kcand = capacity of the candidate list)
+    __syncwarp();
+    #pragma unroll 1
+    for (int kb = 0; kb < ncand; kb += 32) { int k = kb + w.lane; ConOut o; o.n = 0; o.has_y = false; int p = 0;
+      if (k < ncand) { p = clist[k]; collide_ellipsoid(m, w, p, o); }
+      unsigned m0 = __ballot_sync(FULL, o.n >= 1); int idx = ncon + __popc(m0 & ((1u << w.lane) - 1));
+      if (o.n) store_contact(m, con, icon, idx, p, o.c0, o);
+      ncon += __popc(m0); }
+    if (ncon > m.maxcon) { overflow = 1; ncon = m.maxcon; }
+  }
+  WI_(ncon) = ncon; WI_(overflow) = overflow;
   __syncwarp();
 }

@@ -5,16 +5,27 @@
 #pragma once
 #include "myo_device.cuh"
 
-struct Solv {   // scratch views (stage 3/4)
-  double *H, *con, *conJ, *D, *aref, *jar, *jv, *a, *g, *p, *Ma, *Mp, *eqJ, *Hs, *LD, *Dinv;
-  int *cpair, *crow, *cnrow, *lrow;   // contact pair idx, first efc row, #rows ; limit row descriptors (dof | side << 16)
-};
-__device__ __forceinline__ Solv solv_views(const DevModel& m, const Warp& w) {
-  Solv s; double* A = w.scr;
-  s.H = A + m.s_H; s.con = A + m.s_con; s.conJ = A + m.s_conJ; s.D = A + m.s_efD; s.aref = A + m.s_efA; s.jar = A + m.s_efR; s.jv = A + m.s_efV;
-  s.a = A + m.s_va; s.g = A + m.s_vg; s.p = A + m.s_vp; s.Ma = A + m.s_vMa; s.Mp = A + m.s_vMp; s.eqJ = A + m.s_eqJ; s.Hs = A + m.s_Hs; s.LD = A + m.s_LD; s.Dinv = A + m.s_Dinv;
-  int* ic = (int*)(A + m.s_icon); s.cpair = ic; s.crow = ic + m.maxcon; s.cnrow = ic + 2*m.maxcon; s.lrow = ic + 3*m.maxcon;
-  return s; }
+// scratch views (stage 3/4): shared-space pointer expressions (m.s_* are offsets from the warp base)
+#define S_H SCR(s_H)
+#define S_con SCR(s_con)
+#define S_conJ SCR(s_conJ)
+#define S_D SCR(s_efD)
+#define S_aref SCR(s_efA)
+#define S_jar SCR(s_efR)
+#define S_jv SCR(s_efV)
+#define S_a SCR(s_va)
+#define S_g SCR(s_vg)
+#define S_p SCR(s_vp)
+#define S_Ma SCR(s_vMa)
+#define S_Mp SCR(s_vMp)
+#define S_eqJ SCR(s_eqJ)
+#define S_Hs SCR(s_Hs)
+#define S_LD SCR(s_LD)
+#define S_Dinv SCR(s_Dinv)
+#define S_cpair ((int*)SCR(s_icon))            // contact -> program pair index
+#define S_crow (S_cpair + m.maxcon)            // contact -> first efc row
+#define S_cnrow (S_cpair + 2*m.maxcon)         // contact -> number of rows
+#define S_lrow (S_cpair + 3*m.maxcon)          // limit row descriptors (dof | side << 16)
 
 __device__ __forceinline__ double impedance(const double* si, double pos, double margin) {
   if (si[0] == si[1] || si[2] <= MYO_MINVAL) return 0.5*(si[0]+si[1]);
@@ -28,35 +39,37 @@ __device__ __forceinline__ double impedance(const double* si, double pos, double
   return si[0]+y*(si[1]-si[0]); }
 
 // y = M x using the per-row non-zero lists
-__device__ __forceinline__ void mul_M(const DevModel& m, const Warp& w, double* y, const double* x) {
+__device__ __forceinline__ void mul_M(const DevModel& m, const Warp w, double* y, const double* x) {
   const idx_t* radr = CI(PROW_adr); const idx_t* rcol = CI(PROW_col); const idx_t* ridx = CI(PROW_idx);
-  for (int i = w.lane; i < m.nv; i += 32) { double s = 0; for (int e = radr[i]; e < radr[i+1]; e++) s += w.qM[ridx[e]]*x[rcol[e]]; y[i] = s; } }
+  for (int i = w.lane; i < m.nv; i += 32) { double s = 0; for (int e = radr[i]; e < radr[i+1]; e++) s += W_(qM)[ridx[e]]*x[rcol[e]]; y[i] = s; } }
 
 // out[r] = (J x)_r for every constraint row
-__device__ void rows_apply(const DevModel& m, const Warp& w, const Solv& s, const double* x, double* out) {
-  const idx_t* eq = CI(PEQ);
-  for (int e = w.lane; e < m.neq; e += 32) { double v = x[eq[PEQ_ISTRIDE*e+1]]; if (eq[PEQ_ISTRIDE*e+3] >= 0) v += s.eqJ[e]*x[eq[PEQ_ISTRIDE*e+3]]; out[e] = v; }
-  for (int r = w.lane; r < w.nlimrow; r += 32) { int dsc = s.lrow[r]; double sg = (dsc >> 16) & 1 ? -1.0 : 1.0; out[m.neq + r] = sg*x[dsc & 0xffff]; }
+__device__ void rows_apply(const DevModel& m, const Warp w, const double* x, double* out) {
+  SHARED_PTR(x); SHARED_PTR(out);
+  const idx_t* eq = CI(PEQ); const int nlimrow = WI_(nlimrow), ncon = WI_(ncon);
+  for (int e = w.lane; e < m.neq; e += 32) { double v = x[eq[PEQ_ISTRIDE*e+1]]; if (eq[PEQ_ISTRIDE*e+3] >= 0) v += S_eqJ[e]*x[eq[PEQ_ISTRIDE*e+3]]; out[e] = v; }
+  for (int r = w.lane; r < nlimrow; r += 32) { int dsc = S_lrow[r]; double sg = (dsc >> 16) & 1 ? -1.0 : 1.0; out[m.neq + r] = sg*x[dsc & 0xffff]; }
   const idx_t* pr = CI(PPAIR); const double* pd = CD(PPAIR_d); const idx_t* path = CI(PPATH);
-  for (int c = w.lane; c < w.ncon; c += 32) { int nr = s.cnrow[c]; if (!nr) continue;
-    const idx_t* q = pr + PPAIR_ISTRIDE*s.cpair[c]; const double* J = s.conJ + (size_t)c*3*m.maxpath; double n = 0, t1 = 0, t2 = 0;
+  for (int c = w.lane; c < ncon; c += 32) { int nr = S_cnrow[c]; if (!nr) continue;
+    const idx_t* q = pr + PPAIR_ISTRIDE*S_cpair[c]; const double* J = S_conJ + c*3*m.maxpath; double n = 0, t1 = 0, t2 = 0;
     for (int e = 0; e < q[4]; e++) { double xv = x[path[q[3]+e] >> 1]; n += J[3*e]*xv; t1 += J[3*e+1]*xv; t2 += J[3*e+2]*xv; }
-    int rb = s.crow[c];
+    int rb = S_crow[c];
     if (nr == 1) out[rb] = n;
     else { const double* P = pd + q[6]*PPAIR_STRIDE; double mu1 = P[2], mu2 = P[3]; out[rb] = n+mu1*t1; out[rb+1] = n-mu1*t1; out[rb+2] = n+mu2*t2; out[rb+3] = n-mu2*t2; } }
 }
 
 // vec[d] += sum_r J[r][d] * wgt[r]  (wgt already includes D and the active mask)
-__device__ void rows_applyT_add(const DevModel& m, const Warp& w, const Solv& s, const double* wgt, double* vec) {
-  const idx_t* eq = CI(PEQ);
-  if (w.lane == 0) for (int e = 0; e < m.neq; e++) { vec[eq[PEQ_ISTRIDE*e+1]] += wgt[e]; if (eq[PEQ_ISTRIDE*e+3] >= 0) vec[eq[PEQ_ISTRIDE*e+3]] += s.eqJ[e]*wgt[e]; }
+__device__ void rows_applyT_add(const DevModel& m, const Warp w, const double* wgt, double* vec) {
+  SHARED_PTR(wgt); SHARED_PTR(vec);
+  const idx_t* eq = CI(PEQ); const int nlimrow = WI_(nlimrow), ncon = WI_(ncon);
+  if (w.lane == 0) for (int e = 0; e < m.neq; e++) { vec[eq[PEQ_ISTRIDE*e+1]] += wgt[e]; if (eq[PEQ_ISTRIDE*e+3] >= 0) vec[eq[PEQ_ISTRIDE*e+3]] += S_eqJ[e]*wgt[e]; }
   __syncwarp();
   for (int pass = 0; pass < 2; pass++) {
-    for (int r = w.lane; r < w.nlimrow; r += 32) { int dsc = s.lrow[r]; int neg = (dsc >> 16) & 1; if (neg == pass) vec[dsc & 0xffff] += (neg ? -1.0 : 1.0)*wgt[m.neq + r]; }
+    for (int r = w.lane; r < nlimrow; r += 32) { int dsc = S_lrow[r]; int neg = (dsc >> 16) & 1; if (neg == pass) vec[dsc & 0xffff] += (neg ? -1.0 : 1.0)*wgt[m.neq + r]; }
     __syncwarp(); }
   const idx_t* pr = CI(PPAIR); const double* pd = CD(PPAIR_d); const idx_t* path = CI(PPATH);
-  for (int c = 0; c < w.ncon; c++) { int nr = s.cnrow[c]; if (!nr) continue;
-    const idx_t* q = pr + PPAIR_ISTRIDE*s.cpair[c]; const double* J = s.conJ + (size_t)c*3*m.maxpath; int rb = s.crow[c]; double wn, w1 = 0, w2 = 0;
+  for (int c = 0; c < ncon; c++) { int nr = S_cnrow[c]; if (!nr) continue;
+    const idx_t* q = pr + PPAIR_ISTRIDE*S_cpair[c]; const double* J = S_conJ + c*3*m.maxpath; int rb = S_crow[c]; double wn, w1 = 0, w2 = 0;
     if (nr == 1) wn = wgt[rb];
     else { const double* P = pd + q[6]*PPAIR_STRIDE; wn = wgt[rb]+wgt[rb+1]+wgt[rb+2]+wgt[rb+3]; w1 = P[2]*(wgt[rb]-wgt[rb+1]); w2 = P[3]*(wgt[rb+2]-wgt[rb+3]); }
     for (int e = w.lane; e < q[4]; e += 32) vec[path[q[3]+e] >> 1] += J[3*e]*wn + J[3*e+1]*w1 + J[3*e+2]*w2;
@@ -64,52 +77,51 @@ __device__ void rows_applyT_add(const DevModel& m, const Warp& w, const Solv& s,
 }
 
 // ------------------------------------------------------------------ constraint assembly
-__device__ void phase_constraints(const DevModel& m, Warp& w) {
-  Solv s = solv_views(m, w);
+__device__ void phase_constraints(const DevModel& m, const Warp w) {
   // joint equalities (always active)
   const idx_t* eq = CI(PEQ); const double* eqd = CD(PEQ_d);
   for (int e = w.lane; e < m.neq; e += 32) { const double* c = eqd + e*PEQ_STRIDE; int q1 = eq[PEQ_ISTRIDE*e], d1 = eq[PEQ_ISTRIDE*e+1], q2 = eq[PEQ_ISTRIDE*e+2], d2 = eq[PEQ_ISTRIDE*e+3];
-    double pos0 = w.qpos[q1]-c[5], cpos, deriv = 0, vel = w.qvel[d1];
-    if (q2 >= 0) { double x = w.qpos[q2]-c[6]; cpos = pos0-(c[0]+x*(c[1]+x*(c[2]+x*(c[3]+x*c[4])))); deriv = c[1]+x*(2*c[2]+x*(3*c[3]+x*4*c[4])); vel -= deriv*w.qvel[d2]; }
+    double pos0 = W_(qpos)[q1]-c[5], cpos, deriv = 0, vel = W_(qvel)[d1];
+    if (q2 >= 0) { double x = W_(qpos)[q2]-c[6]; cpos = pos0-(c[0]+x*(c[1]+x*(c[2]+x*(c[3]+x*c[4])))); deriv = c[1]+x*(2*c[2]+x*(3*c[3]+x*4*c[4])); vel -= deriv*W_(qvel)[d2]; }
     else cpos = pos0-c[0];
-    s.eqJ[e] = -deriv;
+    S_eqJ[e] = -deriv;
     double imp = impedance(c+10, cpos, 0), R = fmax(MYO_MINVAL, (1-imp)*c[7]/imp);
-    s.D[e] = 1.0/R; s.aref[e] = -c[9]*vel - c[8]*imp*cpos; }
+    S_D[e] = 1.0/R; S_aref[e] = -c[9]*vel - c[8]*imp*cpos; }
   // joint limits (one-sided)
   const idx_t* lim = CI(PLIM); const double* limd = CD(PLIM_d); int nrow = 0;
   for (int base = 0; base < m.nlim; base += 32) { int l = base + w.lane; bool lo = false, hi = false; double dlo = 0, dhi = 0; const double* c = limd + (l < m.nlim ? l : 0)*PLIM_STRIDE; int d = 0;
-    if (l < m.nlim) { d = lim[2*l]; double q = w.qpos[lim[2*l+1]]; dlo = q-c[0]; dhi = c[1]-q; lo = dlo < c[2]; hi = dhi < c[2]; }
+    if (l < m.nlim) { d = lim[2*l]; double q = W_(qpos)[lim[2*l+1]]; dlo = q-c[0]; dhi = c[1]-q; lo = dlo < c[2]; hi = dhi < c[2]; }
     unsigned m0 = __ballot_sync(FULL, lo), m1 = __ballot_sync(FULL, hi), lt = (1u << w.lane)-1; int idx = nrow + __popc(m0 & lt) + __popc(m1 & lt);
     for (int side = 0; side < 2; side++) { if (!(side ? hi : lo)) continue;
       double dist = side ? dhi : dlo, sg = side ? -1.0 : 1.0; int r = m.neq + idx; idx++;
-      s.lrow[r - m.neq] = d | (side << 16);
+      S_lrow[r - m.neq] = d | (side << 16);
       double imp = impedance(c+6, dist, c[2]), R = fmax(MYO_MINVAL, (1-imp)*c[3]/imp);
-      s.D[r] = 1.0/R; s.aref[r] = -c[5]*sg*w.qvel[d] - c[4]*imp*(dist-c[2]); }
+      S_D[r] = 1.0/R; S_aref[r] = -c[5]*sg*W_(qvel)[d] - c[4]*imp*(dist-c[2]); }
     nrow += __popc(m0) + __popc(m1); }
-  w.nlimrow = nrow;
+  WI_(nlimrow) = nrow;
   // contacts: Jacobian over the dofs between the two bodies, regulariser, reference acceleration
   const idx_t* pr = CI(PPAIR); const double* pd = CD(PPAIR_d); const idx_t* path = CI(PPATH);
-  int rowbase = m.neq + nrow;
-  for (int base = 0; base < w.ncon; base += 32) { int c = base + w.lane; int nr = 0;
-    if (c < w.ncon) { const idx_t* q = pr + PPAIR_ISTRIDE*s.cpair[c]; const double* P = pd + q[6]*PPAIR_STRIDE; double dist = s.con[c*CON_STRIDE];
+  int rowbase = m.neq + nrow; const int ncon = WI_(ncon);
+  for (int base = 0; base < ncon; base += 32) { int c = base + w.lane; int nr = 0;
+    if (c < ncon) { const idx_t* q = pr + PPAIR_ISTRIDE*S_cpair[c]; const double* P = pd + q[6]*PPAIR_STRIDE; double dist = S_con[c*CON_STRIDE];
       nr = (dist < P[0]-P[1]) ? (q[2] == 1 ? 1 : 4) : 0; }
     int incl = nr;   // inclusive warp scan
     #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, incl, o); if (w.lane >= o) incl += t; }
     int total = __shfl_sync(FULL, incl, 31);
-    if (c < w.ncon) { s.crow[c] = rowbase + incl - nr; s.cnrow[c] = nr; }
-    if (c < w.ncon && nr) { const idx_t* q = pr + PPAIR_ISTRIDE*s.cpair[c]; const double* P = pd + q[6]*PPAIR_STRIDE; const double* cd = s.con + c*CON_STRIDE;
-      const double* pos = cd + 1; double f[9]; for (int k = 0; k < 6; k++) f[k] = cd[4+k]; cross3(f+6, f, f+3); double* J = s.conJ + (size_t)c*3*m.maxpath; double vn = 0, v1 = 0, v2 = 0;
+    if (c < ncon) { S_crow[c] = rowbase + incl - nr; S_cnrow[c] = nr; }
+    if (c < ncon && nr) { const idx_t* q = pr + PPAIR_ISTRIDE*S_cpair[c]; const double* P = pd + q[6]*PPAIR_STRIDE; const double* cd = S_con + c*CON_STRIDE;
+      const double* pos = cd + 1; double f[9]; for (int k = 0; k < 6; k++) f[k] = cd[4+k]; cross3(f+6, f, f+3); double* J = S_conJ + c*3*m.maxpath; double vn = 0, v1 = 0, v2 = 0;
       for (int e = 0; e < q[4]; e++) { int code = path[q[3]+e], d = code >> 1; double sg = (code & 1) ? 1.0 : -1.0, cv[3]; dof_point_vel(m, w, d, pos, cv);
         double jn = sg*dot3(f, cv), j1 = sg*dot3(f+3, cv), j2 = sg*dot3(f+6, cv); J[3*e] = jn; J[3*e+1] = j1; J[3*e+2] = j2;
-        double qd = w.qvel[d]; vn += jn*qd; v1 += j1*qd; v2 += j2*qd; }
-      double dist = cd[0], inc = P[0]-P[1], imp = impedance(P+7, dist, inc), K = P[5], B = P[6], tran = CD(PPAIR_tran)[s.cpair[c]]; int rb = rowbase + incl - nr;
-      if (nr == 1) { double R = fmax(MYO_MINVAL, (1-imp)*tran/imp); s.D[rb] = 1.0/R; s.aref[rb] = -B*vn - K*imp*(dist-inc); }
+        double qd = W_(qvel)[d]; vn += jn*qd; v1 += j1*qd; v2 += j2*qd; }
+      double dist = cd[0], inc = P[0]-P[1], imp = impedance(P+7, dist, inc), K = P[5], B = P[6], tran = CD(PPAIR_tran)[S_cpair[c]]; int rb = rowbase + incl - nr;
+      if (nr == 1) { double R = fmax(MYO_MINVAL, (1-imp)*tran/imp); S_D[rb] = 1.0/R; S_aref[rb] = -B*vn - K*imp*(dist-inc); }
       else { double mu1 = P[2], mu2 = P[3]; double R0 = fmax(MYO_MINVAL, (1-imp)*(tran+mu1*mu1*tran)/imp), Rpy = 2*mu1*mu1*R0, Dv = 1.0/Rpy, kp = K*imp*(dist-inc);
-        s.D[rb] = s.D[rb+1] = s.D[rb+2] = s.D[rb+3] = Dv;
-        s.aref[rb] = -B*(vn+mu1*v1)-kp; s.aref[rb+1] = -B*(vn-mu1*v1)-kp; s.aref[rb+2] = -B*(vn+mu2*v2)-kp; s.aref[rb+3] = -B*(vn-mu2*v2)-kp; } }
+        S_D[rb] = S_D[rb+1] = S_D[rb+2] = S_D[rb+3] = Dv;
+        S_aref[rb] = -B*(vn+mu1*v1)-kp; S_aref[rb+1] = -B*(vn-mu1*v1)-kp; S_aref[rb+2] = -B*(vn+mu2*v2)-kp; S_aref[rb+3] = -B*(vn-mu2*v2)-kp; } }
     rowbase += total; }
-  w.nefc = rowbase;
+  WI_(nefc) = rowbase;
   __syncwarp();
 }
 
@@ -120,38 +132,9 @@ __device__ __forceinline__ void tri_index(int t, int& i, int& j) {
   i = __float2int_rd((sqrtf(8.0f*t + 1.0f) - 1.0f)*0.5f); if (((i+1)*(i+2) >> 1) <= t) i++; if (((i*(i+1)) >> 1) > t) i--;
   j = t - ((i*(i+1)) >> 1); }
 
-// In-place right-looking Cholesky with the whole trailing update of a column spread flat over the lanes (a short rolled loop: the
-// code stays in the instruction cache, unlike the unrolled register version).  On exit column k holds L[.][k] below the diagonal;
-// the diagonal keeps the PIVOT (not its root): *dinv_lane = 1/sqrt(pivot of row `lane`) for lane < n, and, if fix_diag, H[k][k] = sqrt(pivot).
-__device__ __noinline__ void chol_factor(double* H, int n, int lane, double* dinv_lane, bool fix_diag) {
-  double inv_prev = 0, dinv = 1.0;
-  #pragma unroll 1
-  for (int k = 0; k < n; k++) {
-    double inv = rsqrt(fmax(H[TRI(k,k)], MYO_MINVAL)), inv2 = inv*inv;       // every lane reads the pivot: no broadcast step
-    if (lane == k) dinv = inv;
-    if (k > 0) for (int i = k + lane; i < n; i += 32) H[TRI(i,k-1)] *= inv_prev;   // scale the previous column (its readers are done)
-    const int m_ = n-1-k, cnt = (m_*(m_+1)) >> 1; const double* colk = H + k;       // H[TRI(i,k)] = H[i(i+1)/2 + k]
-    #pragma unroll 2
-    for (int t = lane; t < cnt; t += 32) { int a, b; tri_index(t, a, b); int i = k+1+a, j = k+1+b;
-      H[TRI(i,j)] -= colk[(i*(i+1)) >> 1]*colk[(j*(j+1)) >> 1]*inv2; }
-    __syncwarp();
-    inv_prev = inv; }
-  if (fix_diag) { for (int k = lane; k < n; k += 32) H[TRI(k,k)] = sqrt(fmax(H[TRI(k,k)], MYO_MINVAL)); __syncwarp(); }
-  *dinv_lane = dinv;
-}
-// n <= 32: substitutions with one row per lane (rhs in a register, exchanged by shuffles; L read from shared memory)
-__device__ __noinline__ void chol_smem32(double* H, int n, double* x, int lane) {
-  double dinv; chol_factor(H, n, lane, &dinv, false);
-  double b = lane < n ? x[lane] : 0.0; const double* row = H + ((lane*(lane+1)) >> 1);
-  #pragma unroll 1
-  for (int k = 0; k < n; k++) { double yk = __shfl_sync(FULL, b*dinv, k); if (lane == k) b = yk; else if (lane > k && lane < n) b = fma(-row[k], yk, b); }
-  #pragma unroll 1
-  for (int k = n-1; k >= 0; k--) { double xk = __shfl_sync(FULL, b*dinv, k); if (lane == k) b = xk; else if (lane < k) b = fma(-H[TRI(k,lane)], xk, b); }
-  if (lane < n) x[lane] = b;
-  __syncwarp();
-}
-// row-per-lane variant (any n): the n > 32 fallback (legs, nv = 34: 176 k vs 167 k env-steps/s with the flat-update version above)
+// row-per-lane variant (any n): the n > 36 fallback
 __device__ void chol_factor_rows(double* H, int n, int lane) {
+  SHARED_PTR(H);
   for (int k = 0; k < n; k++) {
     double dkk = sqrt(fmax(H[TRI(k,k)], MYO_MINVAL));
     __syncwarp();
@@ -164,47 +147,54 @@ __device__ void chol_factor_rows(double* H, int n, int lane) {
 }
 // x <- H^-1 x  (H holds the Cholesky factor)
 __device__ void chol_solve(const double* H, int n, double* x, int lane) {
+  SHARED_PTR(H); SHARED_PTR(x);
   for (int k = 0; k < n; k++) { double xk = x[k]/H[TRI(k,k)]; __syncwarp(); if (lane == 0) x[k] = xk;
     for (int i = k+1+lane; i < n; i += 32) x[i] -= H[TRI(i,k)]*xk; __syncwarp(); }
   for (int k = n-1; k >= 0; k--) { double xk = x[k]/H[TRI(k,k)]; __syncwarp(); if (lane == 0) x[k] = xk;
     for (int i = lane; i < k; i += 32) x[i] -= H[TRI(k,i)]*xk; __syncwarp(); }
 }
-// Register-resident Cholesky + solve for n <= NMAX <= 32: lane i keeps row i of the lower triangle in registers, columns are
-// exchanged with warp shuffles (no shared-memory latency, no barriers).  H: dense n x n in shared memory (read only); x: rhs in / solution out.
+// Dense SPD solve for n <= NMAX <= 32, "row in registers, column through shared memory" (root-free L D L'):
+// lane i keeps row i of the working lower triangle in registers.  At step k every lane i >= k publishes its (unscaled) entry of
+// column k into the packed matrix in shared memory, IN PLACE; after one __syncwarp all lanes read the pivot and the column with
+// broadcast LDS (one LDS + one DFMA per trailing entry; round 1's shuffle version spent 2 SHFL + select + DFMA there and needed a
+// second register array for the captured columns).  The forward substitution rides along as one more broadcast value per step;
+// the backward one reads column `lane` of the stored factor (conflict-free) and broadcasts x_k with one shuffle pair.
+// H: packed lower triangle PADDED to NMAX rows (identity rows beyond n; see load_M_dense), destroyed.  x: rhs in / solution out, NMAX slots.
 template <int NMAX>
-__device__ __forceinline__ void chol_reg(const double* H, int n, double* x, int lane) {
-  // The matrix is padded with an identity block up to NMAX so that every shuffle below sits in straight-line, branch-free code
-  // (a shuffle under an `if (k < n)` makes the compiler wrap each one in a WARPSYNC/ENDCOLLECTIVE sequence: 6x the instructions).
-  double r[NMAX], c[NMAX];      // r: row `lane` of L (lower part; the upper part holds unread garbage);  c: column `lane` of L, captured from the shuffles
+__device__ __noinline__ void chol_rs(double* H, double* x, int n, int lane) {
+  SHARED_PTR(H); SHARED_PTR(x);
+  const bool own = lane < NMAX; const int rowadr = own ? TRI(lane, 0) : 0;
+  double r[NMAX];
   #pragma unroll
-  for (int j = 0; j < NMAX; j++) { r[j] = (lane < n && j <= lane) ? H[TRI(lane, j)] : ((j == lane && lane >= n) ? 1.0 : 0.0); c[j] = 0.0; }
-  double b = lane < n ? x[lane] : 0.0, dinv = 1.0;
+  for (int j = 0; j < NMAX; j++) r[j] = (own && j <= lane) ? H[rowadr + j] : 0.0;
+  double b = lane < n ? x[lane] : 0.0, invd_own = 1.0;
+  __syncwarp();
   #pragma unroll
   for (int k = 0; k < NMAX; k++) {
-    double inv = rsqrt(fmax(__shfl_sync(FULL, r[k], k), MYO_MINVAL));      // 1/sqrt(pivot)
-    if (lane == k) dinv = inv;
-    r[k] *= inv;                                   // lanes > k: L[i][k]; lane k: sqrt(pivot) (unused below); lanes < k: 0
+    if (own && lane >= k) H[rowadr + k] = r[k];      // column k, unscaled (U[i][k] = L[i][k] d_k); lane k: the pivot d_k
+    if (lane == k) x[k] = b;                         // z_k of the forward substitution is final (x has chol_pad(n) slots)
+    __syncwarp();
+    const double invd = 1.0/fmax(H[TRI(k,k)], MYO_MINVAL), zk = x[k];
+    if (lane == k) invd_own = invd;
+    const double t = r[k]*invd;                      // L[lane][k] on lanes > k
+    b = lane > k ? fma(-t, zk, b) : b;
     #pragma unroll
-    for (int j = k+1; j < NMAX; j++) { double ljk = __shfl_sync(FULL, r[k], j); if (lane == k) c[j] = ljk; r[j] = fma(-r[k], ljk, r[j]); } }
-  // forward substitution  L y = b
+    for (int j = k+1; j < NMAX; j++) r[j] = fma(-t, H[TRI(j,k)], r[j]);
+  }
+  // backward substitution: u_i = z_i - sum_{k>i} U[k][i] x_k ; x_i = u_i / d_i
   #pragma unroll
-  for (int k = 0; k < NMAX; k++) { double yk = __shfl_sync(FULL, b*dinv, k); b = lane == k ? yk : (lane > k ? fma(-r[k], yk, b) : b); }
-  // backward substitution L' x = y: x_k is final once all j > k are eliminated; lane i < k holds L[k][i] in c[k]  (c[k] = 0 on lanes >= k)
-  #pragma unroll
-  for (int k = NMAX-1; k >= 0; k--) { double xk = __shfl_sync(FULL, b*dinv, k); b = lane == k ? xk : fma(-c[k], xk, b); }
-  if (lane < n) x[lane] = b;
+  for (int k = NMAX-1; k >= 0; k--) { const double xk = __shfl_sync(FULL, b*invd_own, k), hk = (own && lane < k) ? H[TRI(k,0) + lane] : 0.0; b = fma(-hk, xk, b); }
+  __syncwarp();
+  if (lane < n) x[lane] = b*invd_own;
   __syncwarp();
 }
-__device__ __noinline__ void chol_reg8(const double* H, int n, double* x, int lane) { chol_reg<8>(H, n, x, lane); }
-__device__ __noinline__ void chol_reg16(const double* H, int n, double* x, int lane) { chol_reg<16>(H, n, x, lane); }
-__device__ __noinline__ void chol_reg24(const double* H, int n, double* x, int lane) { chol_reg<24>(H, n, x, lane); }
-__device__ __noinline__ void chol_reg32(const double* H, int n, double* x, int lane) { chol_reg<32>(H, n, x, lane); }
 
 // Bordered register Cholesky for 32 < n <= 32+E: H = [A B'; B C] with A the leading 32x32 block.  A = L11 L11' is factored in
 // registers exactly like chol_reg<32>; the rows of B ride along as extra right-hand sides of the forward substitution
 // (L21 = B L11^-T), the E x E Schur complement C - L21 L21' is reduced with warp sums and factored redundantly by every lane.
 template <int E>
 __device__ __noinline__ void chol_reg32b(const double* H, int n, double* x, int lane) {
+  SHARED_PTR(H); SHARED_PTR(x);
   const int e = n - 32;
   double r[32], c[32], bq[E];
   #pragma unroll
@@ -258,24 +248,31 @@ __device__ __noinline__ void chol_reg32b(const double* H, int n, double* x, int 
   __syncwarp();
 }
 
-// x <- H^-1 x for a dense SPD H (packed lower triangle in shared memory); returns whether H survived (the n > 32 fallback factors in place)
-__device__ __forceinline__ bool chol_dense(double* H, int n, double* x, int lane, int mode) {
-  if (n > 36) { chol_factor_rows(H, n, lane); chol_solve(H, n, x, lane); return false; }
-  if (n > 32) { chol_reg32b<4>(H, n, x, lane); return true; }
-  if (mode == 0) { chol_smem32(H, n, x, lane); return false; }
-  if (n <= 8) chol_reg8(H, n, x, lane); else if (n <= 16) chol_reg16(H, n, x, lane); else if (n <= 24) chol_reg24(H, n, x, lane);
-  else chol_reg32(H, n, x, lane);
-  return true; }
+// padded order of the dense solver for an n x n system (the row-register variant is instantiated for these orders)
+__host__ __device__ __forceinline__ int chol_pad(int n) { return n > 32 ? n : (n <= 8 ? 8 : (n == 29 || n == 30 ? 30 : (n + 3) & ~3)); }
+// x <- H^-1 x for a dense SPD H (packed lower triangle in shared memory, padded to chol_pad(n) rows with identity); H is destroyed
+__device__ __forceinline__ void chol_dense(double* H, int n, double* x, int lane) {
+  if (n > 36) { chol_factor_rows(H, n, lane); chol_solve(H, n, x, lane); return; }
+  if (n > 32) { chol_reg32b<4>(H, n, x, lane); return; }
+  switch (chol_pad(n)) {
+    case 8: chol_rs<8>(H, x, n, lane); break;   case 12: chol_rs<12>(H, x, n, lane); break; case 16: chol_rs<16>(H, x, n, lane); break;
+    case 20: chol_rs<20>(H, x, n, lane); break; case 24: chol_rs<24>(H, x, n, lane); break; case 28: chol_rs<28>(H, x, n, lane); break;
+    case 30: chol_rs<30>(H, x, n, lane); break; default: chol_rs<32>(H, x, n, lane); break; } }
 
-__device__ __forceinline__ void load_M_dense(const DevModel& m, const Warp& w, double* H, double diag_scale /* h */) {
-  int n = m.nv; for (int i = w.lane; i < n*(n+1)/2; i += 32) H[i] = 0; __syncwarp();
+// H <- M (+ diag_scale * damping on the diagonal), dense packed lower triangle padded with identity rows up to chol_pad(nv)
+__device__ __forceinline__ void load_M_dense(const DevModel& m, const Warp w, double* H, double diag_scale /* h */) {
+  const int n = m.nv, np = chol_pad(n), nt = n*(n+1)/2; for (int i = w.lane; i < np*(np+1)/2; i += 32) H[i] = 0; __syncwarp();
+  if (w.lane >= n && w.lane < np) H[TRI(w.lane, w.lane)] = 1.0;
+  for (int i = 32 + w.lane; i < np; i += 32) if (i >= n) H[TRI(i, i)] = 1.0;
+  (void)nt;
   const idx_t* mi = CI(PM_i); const idx_t* mj = CI(PM_j); const double* dofp = CD(PDOF_d);
-  for (int e = w.lane; e < m.nM; e += 32) { int i = mi[e], j = mj[e]; double v = w.qM[e]; if (i == j) v += diag_scale*dofp[2*i+1]; H[TRI(i,j)] = v; }
+  for (int e = w.lane; e < m.nM; e += 32) { int i = mi[e], j = mj[e]; double v = W_(qM)[e]; if (i == j) v += diag_scale*dofp[2*i+1]; H[TRI(i,j)] = v; }
   __syncwarp(); }
 
 // ------------------------------------------------------------------ tree-sparse L'DL (level-scheduled, left-looking) on the qM layout
 // Hs (nM, input) -> LD (nM: D on the diagonal slots, unit-L off-diagonals), Dinv (nv)
-__device__ void ldl_factor(const DevModel& m, const Warp& w, const double* Hs, double* LD, double* Dinv) {
+__device__ void ldl_factor(const DevModel& m, const Warp w, const double* Hs, double* LD, double* Dinv) {
+  SHARED_PTR(Hs); SHARED_PTR(LD); SHARED_PTR(Dinv);
   const idx_t* fadr = CI(PFE_adr); const idx_t* fe = CI(PFE); const idx_t* tadr = CI(PFT_adr); const idx_t* ft = CI(PFT);
   const idx_t* mi = CI(PM_i); const idx_t* mj = CI(PM_j); const idx_t* madr = CI(dof_Madr);
   for (int lev = m.ndepth-1; lev >= 0; lev--) {
@@ -288,7 +285,8 @@ __device__ void ldl_factor(const DevModel& m, const Warp& w, const double* Hs, d
     __syncwarp(); }
 }
 // x <- (L'DL)^-1 x
-__device__ void ldl_solve(const DevModel& m, const Warp& w, const double* LD, const double* Dinv, double* x) {
+__device__ void ldl_solve(const DevModel& m, const Warp w, const double* LD, const double* Dinv, double* x) {
+  SHARED_PTR(LD); SHARED_PTR(Dinv); SHARED_PTR(x);
   const idx_t* ladr = CI(PLV_adr); const idx_t* lv = CI(PLV); const idx_t* dadr = CI(PDS_adr); const idx_t* ds = CI(PDS);
   const idx_t* madr = CI(dof_Madr); const idx_t* mj = CI(PM_j);
   for (int lev = m.ndepth-1; lev >= 0; lev--) {
@@ -303,24 +301,24 @@ __device__ void ldl_solve(const DevModel& m, const Warp& w, const double* LD, co
     __syncwarp(); }
 }
 
-// ------------------------------------------------------------------ Newton solver: leaves qacc in s.a
+// ------------------------------------------------------------------ Newton solver: leaves qacc in S_a
 // Called by EVERY warp of the CTA when cta_sync is set (live = this warp holds an env): the warps still iterating are re-aligned by CTA
 // barriers at the top of each Newton iteration and before the Cholesky, so that they keep sharing instruction fetches inside the
 // phase too (a lone 23x23 register Cholesky costs 29 k cycles out of step with the other warps, 21 k in step); finished and idle
 // warps only take part in the barriers.  The total wait is unchanged: the CTA leaves the phase with its slowest env either way.
-__device__ void phase_solve(const DevModel& m, Warp& w, double tol, long long* cyc, bool live, bool cta_sync) {
+__device__ void phase_solve(const DevModel& m, const Warp w, double tol, long long* cyc, bool live, bool cta_sync) {
   long long tc = cyc ? clock64() : 0;
   #define LAP(k) if (cyc) { long long t_ = clock64(); cyc[k] += t_ - tc; tc = t_; }
-  Solv s = solv_views(m, w); int n = m.nv, nefc = live ? w.nefc : 0; w.niter = 0;
+  int n = m.nv, nefc = live ? WI_(nefc) : 0; const int ncon = live ? WI_(ncon) : 0, nlimrow = live ? WI_(nlimrow) : 0; int niter = 0;
   bool active = live;
   if (live && nefc == 0) {   // unconstrained: qacc = M^-1 qfrc_smooth
-    ldl_factor(m, w, w.qM, s.LD, s.Dinv);
-    for (int i = w.lane; i < n; i += 32) { s.a[i] = w.fsm[i]; s.Ma[i] = w.fsm[i]; } __syncwarp();
-    ldl_solve(m, w, s.LD, s.Dinv, s.a); active = false; }
+    ldl_factor(m, w, W_(qM), S_LD, S_Dinv);
+    for (int i = w.lane; i < n; i += 32) { S_a[i] = W_(fsm)[i]; S_Ma[i] = W_(fsm)[i]; } __syncwarp();
+    ldl_solve(m, w, S_LD, S_Dinv, S_a); active = false; }
   if (active) {
-    for (int i = w.lane; i < n; i += 32) s.a[i] = w.qws[i]; __syncwarp();
-    mul_M(m, w, s.Ma, s.a); rows_apply(m, w, s, s.a, s.jar); __syncwarp();
-    for (int r = w.lane; r < nefc; r += 32) s.jar[r] -= s.aref[r]; __syncwarp(); }
+    for (int i = w.lane; i < n; i += 32) S_a[i] = W_(qws)[i]; __syncwarp();
+    mul_M(m, w, S_Ma, S_a); rows_apply(m, w, S_a, S_jar); __syncwarp();
+    for (int r = w.lane; r < nefc; r += 32) S_jar[r] -= S_aref[r]; __syncwarp(); }
   const double scale = 1.0/(m.meaninertia*(n > 1 ? n : 1));
   const idx_t* eq = CI(PEQ); const idx_t* pr = CI(PPAIR); const double* pd = CD(PPAIR_d); const idx_t* path = CI(PPATH);
   for (int iter = 0; iter < 50; iter++) {
@@ -328,62 +326,62 @@ __device__ void phase_solve(const DevModel& m, Warp& w, double tol, long long* c
     bool dense = false;
     if (active) {
     // gradient
-    for (int i = w.lane; i < n; i += 32) s.g[i] = s.Ma[i]-w.fsm[i];
-    for (int r = w.lane; r < nefc; r += 32) { double x = s.jar[r]; s.jv[r] = (r < m.neq || x < 0) ? s.D[r]*x : 0.0; }   // jv used as scratch weights
-    __syncwarp(); rows_applyT_add(m, w, s, s.jv, s.g); __syncwarp();
-    double gn = 0; for (int i = w.lane; i < n; i += 32) gn += s.g[i]*s.g[i]; gn = sqrt(warp_sum(gn));
+    for (int i = w.lane; i < n; i += 32) S_g[i] = S_Ma[i]-W_(fsm)[i];
+    for (int r = w.lane; r < nefc; r += 32) { double x = S_jar[r]; S_jv[r] = (r < m.neq || x < 0) ? S_D[r]*x : 0.0; }   // jv used as scratch weights
+    __syncwarp(); rows_applyT_add(m, w, S_jv, S_g); __syncwarp();
+    double gn = 0; for (int i = w.lane; i < n; i += 32) gn += S_g[i]*S_g[i]; gn = sqrt(warp_sum(gn));
     LAP(8)
     if (scale*gn < tol) active = false; }
     if (active) {
     if (cyc) cyc[14]++;
     // Hessian: tree-sparse L'DL when no contact row is active (limits/equalities keep M's sparsity), dense Cholesky otherwise
     dense = (m.neq > 0 && !m.eq_tree);
-    for (int c = w.lane; c < w.ncon && !dense; c += 32) { int nr = s.cnrow[c], rb = s.crow[c]; for (int r = 0; r < nr; r++) if (s.jar[rb+r] < 0) dense = true; }
+    for (int c = w.lane; c < ncon && !dense; c += 32) { int nr = S_cnrow[c], rb = S_crow[c]; for (int r = 0; r < nr; r++) if (S_jar[rb+r] < 0) dense = true; }
     dense = __any_sync(FULL, dense);
-    for (int i = w.lane; i < n; i += 32) s.p[i] = -s.g[i];
+    for (int i = w.lane; i < n; i += 32) S_p[i] = -S_g[i];
     __syncwarp();
     if (cyc && dense) cyc[15]++;
     if (!dense) {
       const idx_t* madr = CI(dof_Madr);
-      for (int e = w.lane; e < m.nM; e += 32) s.Hs[e] = w.qM[e];
+      for (int e = w.lane; e < m.nM; e += 32) S_Hs[e] = W_(qM)[e];
       __syncwarp();
-      if (w.lane == 0) for (int e = 0; e < m.neq; e++) { int d1 = eq[PEQ_ISTRIDE*e+1], d2 = eq[PEQ_ISTRIDE*e+3]; double De = s.D[e], j2 = s.eqJ[e]; s.Hs[madr[d1]] += De;
-        if (d2 >= 0) { s.Hs[eq[PEQ_ISTRIDE*e+4]] += De*j2; s.Hs[madr[d2]] += De*j2*j2; } }
+      if (w.lane == 0) for (int e = 0; e < m.neq; e++) { int d1 = eq[PEQ_ISTRIDE*e+1], d2 = eq[PEQ_ISTRIDE*e+3]; double De = S_D[e], j2 = S_eqJ[e]; S_Hs[madr[d1]] += De;
+        if (d2 >= 0) { S_Hs[eq[PEQ_ISTRIDE*e+4]] += De*j2; S_Hs[madr[d2]] += De*j2*j2; } }
       __syncwarp();
-      for (int pass = 0; pass < 2; pass++) { for (int r = w.lane; r < w.nlimrow; r += 32) { int dsc = s.lrow[r]; if (((dsc >> 16) & 1) == pass && s.jar[m.neq+r] < 0) s.Hs[madr[dsc & 0xffff]] += s.D[m.neq+r]; } __syncwarp(); }
+      for (int pass = 0; pass < 2; pass++) { for (int r = w.lane; r < nlimrow; r += 32) { int dsc = S_lrow[r]; if (((dsc >> 16) & 1) == pass && S_jar[m.neq+r] < 0) S_Hs[madr[dsc & 0xffff]] += S_D[m.neq+r]; } __syncwarp(); }
       LAP(9)
-      ldl_factor(m, w, s.Hs, s.LD, s.Dinv); ldl_solve(m, w, s.LD, s.Dinv, s.p);
+      ldl_factor(m, w, S_Hs, S_LD, S_Dinv); ldl_solve(m, w, S_LD, S_Dinv, S_p);
       LAP(10)
     } else {
-    load_M_dense(m, w, s.H, 0.0);
-    if (w.lane == 0) for (int e = 0; e < m.neq; e++) { int d1 = eq[PEQ_ISTRIDE*e+1], d2 = eq[PEQ_ISTRIDE*e+3]; double De = s.D[e], j2 = s.eqJ[e]; s.H[TRI(d1,d1)] += De;
-      if (d2 >= 0) { s.H[d1 > d2 ? TRI(d1,d2) : TRI(d2,d1)] += De*j2; s.H[TRI(d2,d2)] += De*j2*j2; } }
+    load_M_dense(m, w, S_H, 0.0);
+    if (w.lane == 0) for (int e = 0; e < m.neq; e++) { int d1 = eq[PEQ_ISTRIDE*e+1], d2 = eq[PEQ_ISTRIDE*e+3]; double De = S_D[e], j2 = S_eqJ[e]; S_H[TRI(d1,d1)] += De;
+      if (d2 >= 0) { S_H[d1 > d2 ? TRI(d1,d2) : TRI(d2,d1)] += De*j2; S_H[TRI(d2,d2)] += De*j2*j2; } }
     __syncwarp();
-    for (int pass = 0; pass < 2; pass++) { for (int r = w.lane; r < w.nlimrow; r += 32) { int dsc = s.lrow[r]; if (((dsc >> 16) & 1) == pass && s.jar[m.neq+r] < 0) { int d = dsc & 0xffff; s.H[TRI(d,d)] += s.D[m.neq+r]; } } __syncwarp(); }
-    for (int c = 0; c < w.ncon; c++) { int nr = s.cnrow[c]; if (!nr) continue; int rb = s.crow[c]; const idx_t* q = pr + PPAIR_ISTRIDE*s.cpair[c]; double W[6] = {0,0,0,0,0,0};  // nn n1 n2 11 12 22
-      if (nr == 1) { if (s.jar[rb] < 0) W[0] = s.D[rb]; }
-      else { const double* P = pd + q[6]*PPAIR_STRIDE; double mu1 = P[2], mu2 = P[3], Dv = s.D[rb];
-        double a0 = s.jar[rb] < 0 ? Dv : 0, a1 = s.jar[rb+1] < 0 ? Dv : 0, a2 = s.jar[rb+2] < 0 ? Dv : 0, a3 = s.jar[rb+3] < 0 ? Dv : 0;
+    for (int pass = 0; pass < 2; pass++) { for (int r = w.lane; r < nlimrow; r += 32) { int dsc = S_lrow[r]; if (((dsc >> 16) & 1) == pass && S_jar[m.neq+r] < 0) { int d = dsc & 0xffff; S_H[TRI(d,d)] += S_D[m.neq+r]; } } __syncwarp(); }
+    for (int c = 0; c < ncon; c++) { int nr = S_cnrow[c]; if (!nr) continue; int rb = S_crow[c]; const idx_t* q = pr + PPAIR_ISTRIDE*S_cpair[c]; double W[6] = {0,0,0,0,0,0};  // nn n1 n2 11 12 22
+      if (nr == 1) { if (S_jar[rb] < 0) W[0] = S_D[rb]; }
+      else { const double* P = pd + q[6]*PPAIR_STRIDE; double mu1 = P[2], mu2 = P[3], Dv = S_D[rb];
+        double a0 = S_jar[rb] < 0 ? Dv : 0, a1 = S_jar[rb+1] < 0 ? Dv : 0, a2 = S_jar[rb+2] < 0 ? Dv : 0, a3 = S_jar[rb+3] < 0 ? Dv : 0;
         W[0] = a0+a1+a2+a3; W[1] = mu1*(a0-a1); W[2] = mu2*(a2-a3); W[3] = mu1*mu1*(a0+a1); W[5] = mu2*mu2*(a2+a3); }
-      if (W[0] != 0) { const double* J = s.conJ + (size_t)c*3*m.maxpath; int np = q[4], ntri = (np*(np+1)) >> 1;
+      if (W[0] != 0) { const double* J = S_conJ + c*3*m.maxpath; int np = q[4], ntri = (np*(np+1)) >> 1;
         // one lane per entry of the lower triangle of J'WJ (the path lists dofs in ascending order, so entry (ei >= ej) lands on H[di >= dj])
         for (int t = w.lane; t < ntri; t += 32) { int ei = __float2int_rd((sqrtf(8.0f*t + 1.0f) - 1.0f)*0.5f); if (((ei+1)*(ei+2) >> 1) <= t) ei++; if (((ei*(ei+1)) >> 1) > t) ei--;
           int ej = t - ((ei*(ei+1)) >> 1);
           const double* a = J + 3*ei; const double* b = J + 3*ej;
           double wa0 = W[0]*a[0]+W[1]*a[1]+W[2]*a[2], wa1 = W[1]*a[0]+W[3]*a[1]+W[4]*a[2], wa2 = W[2]*a[0]+W[4]*a[1]+W[5]*a[2];
-          int di = path[q[3]+ei] >> 1, dj = path[q[3]+ej] >> 1; s.H[TRI(di,dj)] += wa0*b[0]+wa1*b[1]+wa2*b[2]; } }
+          int di = path[q[3]+ei] >> 1, dj = path[q[3]+ej] >> 1; S_H[TRI(di,dj)] += wa0*b[0]+wa1*b[1]+wa2*b[2]; } }
       __syncwarp(); }
     LAP(9)
     } }
     if (cta_sync) __syncthreads();
     if (active) {
-    if (dense) { chol_dense(s.H, n, s.p, w.lane, m.chol_mode); LAP(10) }
+    if (dense) { chol_dense(S_H, n, S_p, w.lane); LAP(10) }
     // exact line search along p
-    mul_M(m, w, s.Mp, s.p); rows_apply(m, w, s, s.p, s.jv); __syncwarp();
-    double ga = 0, gb = 0; for (int i = w.lane; i < n; i += 32) { ga += s.p[i]*(s.Ma[i]-w.fsm[i]); gb += s.p[i]*s.Mp[i]; } ga = warp_sum(ga); gb = warp_sum(gb);
+    mul_M(m, w, S_Mp, S_p); rows_apply(m, w, S_p, S_jv); __syncwarp();
+    double ga = 0, gb = 0; for (int i = w.lane; i < n; i += 32) { ga += S_p[i]*(S_Ma[i]-W_(fsm)[i]); gb += S_p[i]*S_Mp[i]; } ga = warp_sum(ga); gb = warp_sum(gb);
     double alpha = 0, lo = 0, hi = -1, d0 = 0;
     for (int it = 0; it < 40; it++) { double dv = 0, hh = 0;
-      for (int r = w.lane; r < nefc; r += 32) { double x = s.jar[r]+alpha*s.jv[r]; if (r < m.neq || x < 0) { dv += s.D[r]*x*s.jv[r]; hh += s.D[r]*s.jv[r]*s.jv[r]; } }
+      for (int r = w.lane; r < nefc; r += 32) { double x = S_jar[r]+alpha*S_jv[r]; if (r < m.neq || x < 0) { dv += S_D[r]*x*S_jv[r]; hh += S_D[r]*S_jv[r]*S_jv[r]; } }
       dv = warp_sum(dv) + ga + gb*alpha; hh = warp_sum(hh) + gb;
       if (it == 0) { d0 = fabs(dv); if (dv >= 0) break; } else { if (dv < 0) lo = alpha; else hi = alpha; if (fabs(dv) <= 1e-10*d0) break; }
       double an = alpha - dv/hh;
@@ -392,42 +390,43 @@ __device__ void phase_solve(const DevModel& m, Warp& w, double tol, long long* c
       alpha = an; }
     if (alpha == 0) active = false;   // no descent possible: converged to round-off
     else {
-    for (int i = w.lane; i < n; i += 32) { s.a[i] += alpha*s.p[i]; s.Ma[i] += alpha*s.Mp[i]; }
+    for (int i = w.lane; i < n; i += 32) { S_a[i] += alpha*S_p[i]; S_Ma[i] += alpha*S_Mp[i]; }
     // rows that switch between active and inactive along the step; with none the cost was exactly quadratic along p, the Newton
     // step (alpha = 1) lands on its minimum and the gradient vanishes to round-off: converged without another gradient pass
     bool flip = false;
-    for (int r = w.lane; r < nefc; r += 32) { double x0 = s.jar[r], x1 = x0 + alpha*s.jv[r]; s.jar[r] = x1; if (r >= m.neq && (x0 < 0) != (x1 < 0)) flip = true; }
-    __syncwarp(); w.niter = iter+1; LAP(11)
+    for (int r = w.lane; r < nefc; r += 32) { double x0 = S_jar[r], x1 = x0 + alpha*S_jv[r]; S_jar[r] = x1; if (r >= m.neq && (x0 < 0) != (x1 < 0)) flip = true; }
+    __syncwarp(); niter = iter+1; LAP(11)
     if (!__any_sync(FULL, flip)) active = false; } } }
+  if (live) WI_(niter) = niter;
   #undef LAP
 }
 
 // ------------------------------------------------------------------ semi-implicit Euler with implicit joint damping
-__device__ void phase_integrate(const DevModel& m, Warp& w, long long* cyc) {
-  Solv s = solv_views(m, w); int n = m.nv; double h = m.timestep; long long tc = cyc ? clock64() : 0;
+__device__ void phase_integrate(const DevModel& m, const Warp w, long long* cyc) {
+  int n = m.nv; double h = m.timestep; long long tc = cyc ? clock64() : 0;
   // (M + h B) qacc' = M qacc  (= qfrc_smooth + qfrc_constraint at the solver optimum)
-  for (int i = w.lane; i < n; i += 32) s.g[i] = s.Ma[i];     // M qacc, maintained by the solver
+  for (int i = w.lane; i < n; i += 32) S_g[i] = S_Ma[i];     // M qacc, maintained by the solver
   __syncwarp();
   if (n >= 8 && n <= 36) {     // mid-size systems: the register Cholesky beats the level-scheduled sparse factorisation (long index-chasing chains)
-    load_M_dense(m, w, s.H, h);
+    load_M_dense(m, w, S_H, h);
     if (cyc) { long long t_ = clock64(); cyc[18] += t_ - tc; tc = t_; }
-    chol_dense(s.H, n, s.g, w.lane, m.chol_mode);
+    chol_dense(S_H, n, S_g, w.lane);
   } else {
   { const idx_t* mi = CI(PM_i); const idx_t* mj = CI(PM_j); const double* dofp = CD(PDOF_d);
-    for (int e = w.lane; e < m.nM; e += 32) { double v = w.qM[e]; if (mi[e] == mj[e]) v += h*dofp[2*mi[e]+1]; s.Hs[e] = v; } __syncwarp(); }
+    for (int e = w.lane; e < m.nM; e += 32) { double v = W_(qM)[e]; if (mi[e] == mj[e]) v += h*dofp[2*mi[e]+1]; S_Hs[e] = v; } __syncwarp(); }
   if (cyc) { long long t_ = clock64(); cyc[18] += t_ - tc; tc = t_; }
-  ldl_factor(m, w, s.Hs, s.LD, s.Dinv); ldl_solve(m, w, s.LD, s.Dinv, s.g);
+  ldl_factor(m, w, S_Hs, S_LD, S_Dinv); ldl_solve(m, w, S_LD, S_Dinv, S_g);
   }
   if (cyc) { long long t_ = clock64(); cyc[19] += t_ - tc; tc = t_; }
-  for (int i = w.lane; i < n; i += 32) { w.qvel[i] += h*s.g[i]; w.qws[i] = s.a[i]; }
+  for (int i = w.lane; i < n; i += 32) { W_(qvel)[i] += h*S_g[i]; W_(qws)[i] = S_a[i]; }
   __syncwarp();
   const idx_t* jtype = CI(jnt_type); const idx_t* jq = CI(jnt_qposadr); const idx_t* jd = CI(jnt_dofadr);
   for (int j = w.lane; j < m.njnt; j += 32) { int qa = jq[j], da = jd[j];
-    if (jtype[j] == 0) { for (int c = 0; c < 3; c++) w.qpos[qa+c] += h*w.qvel[da+c];
-      double wv[3] = {w.qvel[da+3], w.qvel[da+4], w.qvel[da+5]}, nn = sqrt(dot3(wv,wv)), ang = h*nn;
+    if (jtype[j] == 0) { for (int c = 0; c < 3; c++) W_(qpos)[qa+c] += h*W_(qvel)[da+c];
+      double wv[3] = {W_(qvel)[da+3], W_(qvel)[da+4], W_(qvel)[da+5]}, nn = sqrt(dot3(wv,wv)), ang = h*nn;
       if (nn < MYO_MINVAL) { wv[0]=1; wv[1]=0; wv[2]=0; } else { wv[0]/=nn; wv[1]/=nn; wv[2]/=nn; }
-      double sn, cs; sincos(0.5*ang, &sn, &cs); double ql[4] = {cs, wv[0]*sn, wv[1]*sn, wv[2]*sn}, qn[4]; quat_mul(qn, w.qpos+qa+3, ql); quat_norm(qn);
-      for (int c = 0; c < 4; c++) w.qpos[qa+3+c] = qn[c]; }
-    else w.qpos[qa] += h*w.qvel[da]; }
+      double sn, cs; sincos(0.5*ang, &sn, &cs); double ql[4] = {cs, wv[0]*sn, wv[1]*sn, wv[2]*sn}, qn[4]; quat_mul(qn, W_(qpos)+qa+3, ql); quat_norm(qn);
+      for (int c = 0; c < 4; c++) W_(qpos)[qa+3+c] = qn[c]; }
+    else W_(qpos)[qa] += h*W_(qvel)[da]; }
   __syncwarp();
 }

@@ -145,7 +145,7 @@ class MyoVecEnv:
         t = dict(action=z(n, m.nu, dtype=f32), qpos=z(n, m.nq), qvel=z(n, m.nv), act=z(n, max(m.na, 1)), qacc_warmstart=z(n, m.nv),
                  time=z(n), target=z(n, m.nq), step_count=z(n, dtype=torch.int32), episode_count=z(n, dtype=torch.int64),
                  obs=z(n, self.obs_dim, dtype=f32), reward=z(n, dtype=f32), done=z(n, dtype=torch.uint8), truncated=z(n, dtype=torch.uint8),
-                 ep_return=z(n, dtype=f32), last_return=z(n, dtype=f32))
+                 ep_return=z(n, dtype=f32), last_return=z(n, dtype=f32), overflow=z(n, dtype=torch.int32))
         t["qpos"][:] = torch.as_tensor(m.qpos0, device=dv)
         # target ranges per qpos (pose_v0.py:60-70); "fixed" targets collapse the range
         tr = np.zeros((m.nq, 2))
