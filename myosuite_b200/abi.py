@@ -55,7 +55,7 @@ def lib_path():
 def lib():
     global _LIB
     if _LIB is None:
-        path = _build.LIB
+        path = os.environ.get("MYO_B200_LIB") or _build.LIB      # MYO_B200_LIB: a variant build (developer experiments)
         if not os.path.exists(path):
             path = _build.build()
         L = ctypes.CDLL(path)

@@ -24,5 +24,13 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(tag, defines, verbose=False):
+    """Developer aid: libmyo_b200_<tag>.so with extra -D flags (register-budget experiments; selected at run time by MYO_B200_LIB)."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    out = os.path.join(HERE, "libmyo_b200_%s.so" % tag)
+    subprocess.check_call([nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, SRC])
+    return out
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))

@@ -254,7 +254,7 @@ __device__ __forceinline__ void env_kernel_body(const DevModel& m, const StepArg
       for (int i = w.lane; i < m.nq; i += 32) W_(qpos)[i] = b.qpos[(size_t)env*m.nq+i];
       for (int i = w.lane; i < m.nv; i += 32) { W_(qvel)[i] = b.qvel[(size_t)env*m.nv+i]; W_(qws)[i] = b.qacc_warmstart[(size_t)env*m.nv+i]; }
       for (int i = w.lane; i < m.na; i += 32) W_(act)[i] = b.act[(size_t)env*m.na+i];
-      if (w.lane < 8) W_(eprm)[w.lane] = b.env_prm ? b.env_prm[(size_t)env*8 + w.lane] : 0.0;
+      if (w.lane < m.neprm) W_(eprm)[w.lane] = b.env_prm ? b.env_prm[(size_t)env*8 + w.lane] : 0.0;     // per-env model overrides (hold task only)
       for (int i = w.lane; i < m.nwz; i += 32) W_(wz)[i] = -1.0;     // cold start of the inverse-wrap roots at the first substep
       __syncwarp();
       if (a.mode == 2) {
@@ -343,8 +343,17 @@ __device__ __forceinline__ void env_kernel_body(const DevModel& m, const StepArg
   }
 }
 // product kernel: up to 10 env-warps per CTA (204 registers per thread)
-#ifndef MYO_LB
-#define MYO_LB __maxnreg__(200)      /* 10 env-warps x 32 lanes x 200 registers = 64 000 of the SM's 65 536; launch_bounds(320) made ptxas stop at 168 and spill 1.3 KB */
+// Register budget of the product kernel.  ptxas keeps ~36 registers back for the callees of a kernel that makes ABI calls: the entry function
+// gets 168 under launch_bounds(320) (10 env-warps per CTA) and 128 under launch_bounds(448) (14).  __maxnreg__(200) spills a third as much
+// but the kernel then launches with at most 8 warps per CTA (measured round 2: "too many resources requested" at 9).
+#if defined(MYO_LB_MODE) && MYO_LB_MODE == 0
+#define MYO_LB __maxnreg__(200)
+#elif defined(MYO_LB_MODE) && MYO_LB_MODE == 3
+#define MYO_LB __launch_bounds__(448)
+#elif defined(MYO_LB_MODE) && MYO_LB_MODE == 4
+#define MYO_LB __launch_bounds__(384)
+#else
+#define MYO_LB __launch_bounds__(320)
 #endif
 extern "C" __global__ void MYO_LB myo_env_kernel(const __grid_constant__ DevModel m, const __grid_constant__ StepArgs a) { env_kernel_body<false, 320>(m, a); }
 // parity taps / forward-debug / profiling counters / tuning knobs
@@ -393,7 +402,7 @@ static void fill_devmodel(const myo_model* mm, const myo_task_cfg* cfg, DevModel
   int mc = cfg && cfg->maxcon > 0 ? cfg->maxcon : 32; if (mc > 2*d.npair) mc = 2*d.npair; d.maxcon = mc; d.nlimrow = P[PD_NLIMROW] > 0 ? P[PD_NLIMROW] : 2*d.nlim; d.maxefc = d.neq + d.nlimrow + 4*mc;
   int o = 0;
   #define TAKE(field, n) d.field = o; o += al2(n)
-  TAKE(o_qpos, d.nq); TAKE(o_qvel, d.nv); TAKE(o_act, d.na); TAKE(o_ctrl, d.nu); TAKE(o_qws, d.nv); TAKE(o_dax, 3*d.nv); TAKE(o_dan, 3*d.nv); TAKE(o_qM, d.nM); TAKE(o_fsm, d.nv); TAKE(o_eprm, 8); d.nwz = P[PD_NWE_SPH_IN] + P[PD_NWE_CYL_IN]; TAKE(o_wz, d.nwz); TAKE(o_cnt, CNT_N/2);
+  TAKE(o_qpos, d.nq); TAKE(o_qvel, d.nv); TAKE(o_act, d.na); TAKE(o_ctrl, d.nu); TAKE(o_qws, d.nv); TAKE(o_dax, 3*d.nv); TAKE(o_dan, 3*d.nv); TAKE(o_qM, d.nM); TAKE(o_fsm, d.nv); d.neprm = (cfg && cfg->task == MYO_TASK_HOLD) ? 8 : 0; TAKE(o_eprm, d.neprm); d.nwz = P[PD_NWE_SPH_IN] + P[PD_NWE_CYL_IN]; TAKE(o_wz, d.nwz); TAKE(o_cnt, CNT_N/2);
   d.nvp = chol_pad(d.nv);
   d.o_scr = o;
   #undef TAKE
@@ -456,7 +465,10 @@ extern "C" int myo_batch_create(const myo_model* m, int device, int n_env, const
   cudaDeviceProp prop; CUDA_OK(cudaGetDeviceProperties(&prop, device));
   b->const_bytes = b->dm.nD*8 + ((b->dm.nI16w + 1)/2)*8;
   int per = b->dm.n_per_warp*8, maxs = (int)prop.sharedMemPerBlockOptin - b->const_bytes - 64;
-  int wpc = maxs/per; if (wpc > 10) wpc = 10;     // (__launch_bounds__(320): 204 registers per thread)
+  cudaFuncAttributes fa_p, fa_d; CUDA_OK(cudaFuncGetAttributes(&fa_p, myo_env_kernel)); CUDA_OK(cudaFuncGetAttributes(&fa_d, myo_env_kernel_dbg));
+  int maxw = (fa_p.maxThreadsPerBlock < fa_d.maxThreadsPerBlock ? fa_p.maxThreadsPerBlock : fa_d.maxThreadsPerBlock)/32;     // what the kernels' register budgets allow
+  if (const char* e = getenv("MYO_B200_PRODUCT_ONLY")) if (atoi(e)) maxw = fa_p.maxThreadsPerBlock/32;      // (experiments: ignore the debug kernel's bound)
+  int wpc = maxs/per; if (wpc > maxw) wpc = maxw;
   if (wpc < 1) { delete b; return fail("model working set exceeds shared memory of one CTA"); }
   const int wpc0 = wpc;
   if (n_env < wpc) wpc = n_env;

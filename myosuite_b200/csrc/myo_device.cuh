@@ -43,7 +43,7 @@ struct DevModel {
   int32_t maxcon, maxefc, nlimrow, ovr_geom, ngc, s_gpose, solve_sync, nvp;          // ovr_geom: collision geom whose size comes from the per-env overrides (-1: none); nvp: nv padded to the dense solver's order
   double timestep, gx, gy, gz, meaninertia, tolerance;
   // per-warp shared-memory layout, in doubles.  Persistent part:
-  int32_t o_qpos, o_qvel, o_act, o_ctrl, o_qws, o_dax, o_dan, o_qM, o_fsm, o_eprm, o_wz, nwz, o_cnt, o_scr, n_per_warp;
+  int32_t o_qpos, o_qvel, o_act, o_ctrl, o_qws, o_dax, o_dan, o_qM, o_fsm, o_eprm, neprm, o_wz, nwz, o_cnt, o_scr, n_per_warp;
   // scratch (time-multiplexed by stage; offsets relative to the warp base, i.e. o_scr included).  See fill_devmodel() for the overlap rules.
   int32_t s_xpos, s_xmat;                                  // K: body poses, alive kinematics .. constraints
   int32_t s_U, s_WP, s_PL, s_mom, s_tlen, s_tvel, s_tfrc;  // stage 1: tendons + actuation

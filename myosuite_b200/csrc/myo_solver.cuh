@@ -249,7 +249,8 @@ __device__ __noinline__ void chol_reg32b(const double* H, int n, double* x, int 
 }
 
 // padded order of the dense solver for an n x n system (the row-register variant is instantiated for these orders)
-__host__ __device__ __forceinline__ int chol_pad(int n) { return n > 32 ? n : (n <= 8 ? 8 : (n == 29 || n == 30 ? 30 : (n + 3) & ~3)); }
+// (exact orders exist for the hand, 23, and the hand + object, 29: every padded row costs shared memory)
+__host__ __device__ __forceinline__ int chol_pad(int n) { return n > 32 ? n : (n <= 8 ? 8 : (n == 23 || n == 29 ? n : (n + 3) & ~3)); }
 // x <- H^-1 x for a dense SPD H (packed lower triangle in shared memory, padded to chol_pad(n) rows with identity); H is destroyed
 __device__ __forceinline__ void chol_dense(double* H, int n, double* x, int lane) {
   if (n > 36) { chol_factor_rows(H, n, lane); chol_solve(H, n, x, lane); return; }
@@ -257,7 +258,7 @@ __device__ __forceinline__ void chol_dense(double* H, int n, double* x, int lane
   switch (chol_pad(n)) {
     case 8: chol_rs<8>(H, x, n, lane); break;   case 12: chol_rs<12>(H, x, n, lane); break; case 16: chol_rs<16>(H, x, n, lane); break;
     case 20: chol_rs<20>(H, x, n, lane); break; case 24: chol_rs<24>(H, x, n, lane); break; case 28: chol_rs<28>(H, x, n, lane); break;
-    case 30: chol_rs<30>(H, x, n, lane); break; default: chol_rs<32>(H, x, n, lane); break; } }
+    case 23: chol_rs<23>(H, x, n, lane); break; case 29: chol_rs<29>(H, x, n, lane); break; default: chol_rs<32>(H, x, n, lane); break; } }
 
 // H <- M (+ diag_scale * damping on the diagonal), dense packed lower triangle padded with identity rows up to chol_pad(nv)
 __device__ __forceinline__ void load_M_dense(const DevModel& m, const Warp w, double* H, double diag_scale /* h */) {

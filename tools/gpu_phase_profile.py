@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from myosuite_b200 import vec_env
 eid = sys.argv[1] if len(sys.argv) > 1 else "myoHandPoseRandom-v0"
-n, steps = 4096, 60
+n, steps = int(os.environ.get("N", 4096)), int(os.environ.get("STEPS", 60))
 env = vec_env.MyoVecEnv(eid, n, taps=True, maxcon=int(os.environ.get("MAXCON", 0)), profile_waits=bool(int(os.environ.get("WAITS", 0))), solver_tolerance=float(os.environ.get("TOL", 0))); env.reset(seed=0); print("maxcon", env.dims.maxcon, "smem/env", env.dims.smem_bytes_per_env, "const", env.dims.reserved[1])
 names = ["kinematics", "tendon", "actuation", "crb+bias", "collision", "constraints", "solve", "taps+integrate"]
 tot = np.zeros(8); sub = np.zeros(8); extra = np.zeros(4); hist = np.zeros(64, dtype=np.int64); hefc = []; iters = []
