@@ -29,6 +29,31 @@ A_IO = {"myoElbowPose1D6MRandom-v0": 24 + 2 * (8 * 8) + 36 + 5, "myoHandPoseRand
         "myoHandObjHoldRandom-v0": 156 + 2 * (98 * 8) + 364 + 5 + 36, "myoFatiLegWalk-v0": 320 + 2 * (149 * 8) + 2 * (240 * 8) + 1612 + 5,
         "myoLegWalk-v0": 320 + 2 * (149 * 8) + 1612 + 5,
         "myoHandReachRandom-v0": 156 + 2 * (85 * 8) + 460 + 5 + 120}        # (+ 15 target coordinates f64)
+A_OBS = {"myoElbowPose1D6MRandom-v0": 9, "myoHandPoseRandom-v0": 108, "myoHandObjHoldRandom-v0": 91, "myoFatiLegWalk-v0": 403, "myoLegWalk-v0": 403, "myoHandReachRandom-v0": 115}
+
+
+def usable_cores():
+    """Host cores this process may actually use: the scheduler affinity mask capped by the cgroup CPU quota
+    (os.cpu_count() reports the machine, not the lease: round 1's arm forked 128 workers onto ~15 cores)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    quota = None
+    try:                                     # cgroup v2
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        try:                                 # cgroup v1
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    if quota is not None:
+        n = max(1, min(n, int(quota + 0.5)))
+    return n
 
 
 class ClockSampler:
@@ -66,7 +91,7 @@ class ClockSampler:
 def _cpu_worker(args):
     """One host core: a single env stepped in a loop (reference protocol:
     /root/reference/benchmarks/mjx_benchmark_baseline.py:8-25 -- gym.make, reset, timeit(env.step(random action)))."""
-    env_id, budget_s, seed = args          # budget_s: wall-clock seconds of stepping (a bounded sample; the oracle's rate varies 10x with the contact load)
+    env_id, budget_s, seed, u01 = (tuple(args) + (False,))[:4]          # budget_s: wall-clock seconds of stepping (a bounded sample; the oracle's rate varies 10x with the contact load)
     import numpy as np
     from myosuite_b200 import assets, blob, vec_env
     from oracle import env_oracle
@@ -89,7 +114,7 @@ def _cpu_worker(args):
                 o.set(qpos=q)
             elif "Walk" in env_id:
                 o.set(qpos=m.key_qpos[2], qvel=m.key_qvel[2])
-        env_oracle.env_step(o, rng.uniform(-1, 1, m.nu), 10)
+        env_oracle.env_step(o, rng.uniform(0, 1, m.nu) if u01 else rng.uniform(-1, 1, m.nu), 10)
         if pose:
             env_oracle.pose_obs(o.f("qpos"), o.f("qvel"), o.f("act"), q, 0.02)
         else:
@@ -98,16 +123,45 @@ def _cpu_worker(args):
     return s, time.perf_counter() - t0
 
 
-def cpu_baseline(env_id, budget_s, threads=1):
+def cpu_baseline(env_id, budget_s, threads=1, u01=False):
     """(env-steps/s, total steps) of `threads` independent single-env loops of the oracle port, one process per host core, each stepping
     for budget_s seconds of wall clock; the rate is total steps / the slowest worker's loop time (process start-up and model load excluded)."""
     if threads == 1:
-        n, t = _cpu_worker((env_id, budget_s, 0))
+        n, t = _cpu_worker((env_id, budget_s, 0, u01))
         return n / t, n
     import multiprocessing as mp
     with mp.get_context("fork").Pool(threads) as pool:
-        res = pool.map(_cpu_worker, [(env_id, budget_s, i) for i in range(threads)])
+        res = pool.map(_cpu_worker, [(env_id, budget_s, i, u01) for i in range(threads)])
     return sum(r[0] for r in res) / max(r[1] for r in res), sum(r[0] for r in res)
+
+
+MUJOCO_PUBLISHED = {"myoHandPoseRandom-v0": "reference's own CPU MuJoCo single-env figure on the hand model (myoHandReachRandom, derived from its plot): ~1.9 k env-steps/s on 1 core (BASELINE.md section 1)",
+                    "myoElbowPose1D6MRandom-v0": "reference's own CPU MuJoCo single-env figure on this model (derived from its plot): ~10 k env-steps/s on 1 core (BASELINE.md section 1)"}
+
+
+def reference_arm(args, W):
+    """bench.py --impl reference: the CPU implementation of the path on the box's host cores.  MuJoCo is not installable here, so this is
+    the oracle PORT (kind = "port"), built -O3 -march=native on this machine, one single-env loop per usable core."""
+    from oracle import oracle_py
+    os.environ["MYO_ORACLE_LIB"] = oracle_py.build_native()        # inherited by the forked workers
+    thr = usable_cores()
+    budget = float(os.environ.get("MYO_BENCH_CPU_BUDGET_S", 8.0))      # bounded sample: every usable core steps its own env for 8 s
+    u01 = args.actions == "u01"
+    t0 = time.perf_counter()
+    v, total = cpu_baseline(args.env, budget, threads=thr, u01=u01)
+    ms = (time.perf_counter() - t0) * 1e3
+    per_thread = max(total // thr, 1)
+    sample = "%d threads x %.0f s of stepping = %d env-steps of %s (1 env each, random actions %s, reset every episode); machine has %d CPUs, affinity/cgroup leave %d" % (
+        thr, budget, total, args.env, "U(0,1)" if u01 else "U[-1,1]", os.cpu_count() or 0, thr)
+    line = {"impl": "reference", "metric": "env-steps/sec (random actions, 4096 envs/GPU)", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": W, "ms_per_step": ms / max(per_thread, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s, frame_skip 10, random actions %s, reset every episode; CPU arm: one single-env loop of the oracle port (gcc -O3 -march=native) per usable host core"
+                                   % (args.env, "U(0,1)" if u01 else "U[-1,1]"),
+                       "note": "the port is NOT MuJoCo; " + MUJOCO_PUBLISHED.get(args.env, "no published MuJoCo figure for this env")},
+            "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": thr, "per_core": v / thr, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
 
 
 def main():
@@ -118,7 +172,9 @@ def main():
     ap.add_argument("--env", default=DEFAULT_ENV)
     ap.add_argument("--envs-per-gpu", type=int, default=4096)
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--actions", default="u11", choices=["u11", "u01"], help="u11: U[-1,1] = action_space.sample() (default); u01: U(0,1), the reference benchmark's protocol (benchmarks/mjx_benchmark_baseline.py:15)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip config.extra (the other BASELINE configs, the U(0,1) variant, the sustained run)")
     ap.add_argument("--no-l2-flush", action="store_true", help="do not evict L2 between timed steps (default: a 192 MiB write per step)")
     ap.add_argument("--barrier-mode", type=int, default=0)
     ap.add_argument("--lockstep-groups", type=int, default=0)
@@ -127,26 +183,10 @@ def main():
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     W = max(args.warmup, 3)
-    cores = os.cpu_count() or 1
 
     if args.impl == "reference":
-        if rank != 0:
-            return
-        from oracle import oracle_py
-        oracle_py.build()
-        thr = max(1, cores)
-        budget = float(os.environ.get("MYO_BENCH_CPU_BUDGET_S", 8.0))      # bounded sample: every host core steps its own env for 8 s
-        t0 = time.perf_counter()
-        v, total = cpu_baseline(args.env, budget, threads=thr)
-        ms = (time.perf_counter() - t0) * 1e3
-        per_thread = max(total // thr, 1)
-        sample = "%d threads x %.0f s of stepping = %d env-steps of %s (1 env each, random actions, reset every episode)" % (thr, budget, total, args.env)
-        print(json.dumps({"impl": "reference", "metric": "env-steps/sec (random actions, 4096 envs/GPU)", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
-                          "steps": args.steps, "warmup": W, "ms_per_step": ms / max(per_thread, 1), "higher_is_better": True, "scaling": "weak",
-                          "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                          "config": {"workload": "%s, frame_skip 10, random actions U[-1,1], reset every episode; CPU arm: one single-env loop of the oracle port per host thread" % args.env},
-                          "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": thr, "kind": "port", "sample": sample},
-                          "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        if rank == 0:
+            reference_arm(args, W)
         return
 
     import torch
@@ -158,17 +198,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    n = args.envs_per_gpu
-    env = vec_env.MyoVecEnv(args.env, n, device=local_rank, seed=0, env_offset=rank * n, barrier_mode=args.barrier_mode, lockstep_groups=args.lockstep_groups, solver_tolerance=args.solver_tolerance)
-    env.reset(seed=0)
-    nu = env.act_dim
-    gen = torch.Generator(device=env.device).manual_seed(1234 + rank)
-    # a ring of pre-generated random action batches (U[-1,1], the action_space.sample() distribution)
-    ring = [(torch.rand(n, nu, device=env.device, generator=gen) * 2 - 1) for _ in range(16)]
-    ring_host = [r.cpu().pin_memory() for r in ring]
-
+    dev = torch.device("cuda", local_rank)
     # L2 (126 MB) is evicted between timed steps by writing a 192 MiB buffer: step k+1 reads the state step k wrote from HBM, not from L2
-    flush_buf = None if args.no_l2_flush else torch.empty(192 << 20, dtype=torch.uint8, device=env.device)
+    flush_buf = None if args.no_l2_flush else torch.empty(192 << 20, dtype=torch.uint8, device=dev)
 
     def flush_l2(i):
         if flush_buf is not None:
@@ -179,75 +211,122 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(W):
-        env.step(ring[i % 16])
-    barrier()
-    l0 = env.batch.launches
+    def max_over_ranks(*ms):
+        t = torch.tensor(list(ms), device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def make(env_id, n):
+        env = vec_env.MyoVecEnv(env_id, n, device=local_rank, seed=0, env_offset=rank * n, barrier_mode=args.barrier_mode, lockstep_groups=args.lockstep_groups, solver_tolerance=args.solver_tolerance)
+        env.reset(seed=0)
+        return env
+
+    def rings(env, u01):
+        gen = torch.Generator(device=dev).manual_seed(1234 + rank + (7777 if u01 else 0))
+        # a ring of pre-generated random action batches: U[-1,1] = the action_space.sample() distribution; U(0,1) = the reference benchmark's
+        return [(torch.rand(env.num_envs, env.act_dim, device=dev, generator=gen) * (1 if u01 else 2) - (0 if u01 else 1)) for _ in range(16)]
+
+    def timed(env, ring, steps, warm, flush=True, host=False):
+        """ms for `steps` control steps of every env on this rank (CUDA events on the launching stream), max over ranks; launches issued."""
+        step = env.step_host if host else env.step
+        for i in range(warm):
+            step(ring[i % 16])
+        barrier()
+        l0 = env.batch.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            if flush:
+                flush_l2(i)
+            step(ring[i % 16])
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))[0], env.batch.launches - l0
+
+    n = args.envs_per_gpu
+    env = make(args.env, n)
+    nu = env.act_dim
+    ring = rings(env, args.actions == "u01")
+    ring_host = [r.cpu().pin_memory() for r in ring]
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for i in range(args.steps):
-        flush_l2(i)
-        env.step(ring[i % 16])
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    launches = env.batch.launches - l0
-    # end-to-end through the public API with host buffers
-    for i in range(3):
-        env.step_host(ring_host[i % 16])
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        flush_l2(i)
-        env.step_host(ring_host[i % 16])
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
+    ms, launches = timed(env, ring, args.steps, W)
+    ms_e2e, _ = timed(env, ring_host, args.steps, 3, host=True)        # end to end through the public API with host buffers
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms, ms_e2e], device=env.device, dtype=torch.float64)
+    # the one collective of the path: gather finished-episode returns at rollout end (SURVEY.md section 8e), timed on its own
+    allgather_us = None
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        # the one collective of the path: gather finished-episode returns at rollout end
-        gathered = torch.empty(world * n, device=env.device, dtype=torch.float32)
-        dist.all_gather_into_tensor(gathered, env.t["last_return"])
-    ms, ms_e2e = float(t[0]), float(t[1])
+        gathered = torch.empty(world * n, device=dev, dtype=torch.float32)
+        dist.all_gather_into_tensor(gathered, env.t["last_return"])        # warm-up (communicator set-up)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(); dist.all_gather_into_tensor(gathered, env.t["last_return"]); g1.record()
+        barrier()
+        allgather_us = max_over_ranks(g0.elapsed_time(g1))[0] * 1e3
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+
+    def roofline(env_id, n_env, ms_total, n_launch):
+        aio = A_IO.get(env_id, 0)
+        achieved = aio * n_env / (ms_total * 1e-3 / max(n_launch, 1)) / 1e9
+        traffic = None
+        for tf in ("r02_traffic.json", "r01_traffic.json"):
+            f = os.path.join(ROOT, "profiles", tf)
+            if os.path.exists(f):
+                traffic = json.load(open(f)).get(env_id)
+                break
+        return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "note": "fused step is issue/latency bound, not HBM bound (SURVEY 8d): algorithmic bytes %d B/env-step; peak = %s" % (aio, "measured" if peaks else "fallback")}
+
+    extra = {}
+    if not args.no_extra:
+        # (a) sustained: >= 1 s and >= 1 full episode, so that TimeLimit truncation and the in-kernel auto-reset fire inside the timed region
+        per = ms / max(args.steps, 1)
+        ks = max(int(1000.0 / max(per, 1e-3)) + 1, (env.max_episode_steps or 100) + 10)
+        ms_s, _ = timed(env, ring, ks, 0, flush=False)
+        extra["sustained"] = {"steps": ks, "value": world * n * ks / (ms_s * 1e-3), "ms_per_step": ms_s / ks, "l2": "not flushed", "episodes_finished_per_env": float(env.t["episode_count"].double().mean().item()) - 1.0}
+        # (b) the reference benchmark's action protocol, U(0,1)
+        if args.actions == "u11":
+            ms_u, _ = timed(env, rings(env, True), 30, 3)
+            extra["actions_u01"] = {"steps": 30, "value": world * n * 30 / (ms_u * 1e-3), "ms_per_step": ms_u / 30}
+        overflow_frac = float((env.t["overflow"] != 0).double().mean().item())
+        del env
+        # (c) the other BASELINE.json configs (2, 4, 5), measured outside the headline region
+        for eid, ne, st in (("myoElbowPose1D6MRandom-v0", 4096, 100), ("myoFatiLegWalk-v0", 2048, 30), ("myoHandObjHoldRandom-v0", 2048, 40)):
+            if eid == args.env:
+                continue
+            e2 = make(eid, ne)
+            ms2, l2 = timed(e2, rings(e2, False), st, 3)
+            extra[eid] = {"envs_per_gpu": ne, "steps": st, "value": world * ne * st / (ms2 * 1e-3), "ms_per_step": ms2 / st, "roofline": roofline(eid, ne, ms2, l2)}
+            del e2
+    else:
+        overflow_frac = float((env.t["overflow"] != 0).double().mean().item())
     if rank == 0:
         total = world * n * args.steps
         value, e2e = total / (ms * 1e-3), total / (ms_e2e * 1e-3)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        aio = A_IO.get(args.env, 0)
-        per_launch_s = ms * 1e-3 / max(launches, 1)
-        achieved = aio * n / per_launch_s / 1e9
-        traffic = None
-        tf = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tf):
-            traffic = json.load(open(tf)).get(args.env)
         line = {"metric": "env-steps/sec (random actions, 4096 envs/GPU)", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "impl": "b200",
-                "config": {"workload": "%s, %d envs/GPU, frame_skip 10, random actions U[-1,1], auto-reset" % (args.env, n),
-                           "l2": ("not flushed (--no-l2-flush)" if args.no_l2_flush else "flushed between timed steps: a 192 MiB write per step inside the timed region (inputs, 8 MB of state per step, are smaller than L2)"), "parallelism": "env-sharded x%d, no data-path collective" % world},
-                "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": n * nu * 4, "d2h_bytes_per_step": n * (env.obs_dim * 4 + 4 + 1)},
+                "config": {"workload": "%s, %d envs/GPU, frame_skip 10, random actions %s, auto-reset" % (args.env, n, "U(0,1)" if args.actions == "u01" else "U[-1,1]"),
+                           "l2": ("not flushed (--no-l2-flush)" if args.no_l2_flush else "flushed between timed steps: a 192 MiB write per step inside the timed region (inputs, 8 MB of state per step, are smaller than L2)"), "parallelism": "env-sharded x%d, no data-path collective" % world,
+                           "contact_overflow_env_fraction": overflow_frac, "rollout_end_allgather_us": allgather_us, "extra": extra},
+                "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": n * nu * 4, "d2h_bytes_per_step": n * (max(A_OBS.get(args.env, 0), 0) * 4 + 4 + 1)},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                             "note": "fused step is issue/latency bound, not HBM bound (SURVEY 8d): algorithmic bytes %d B/env-step; peak = %s" % (aio, "measured" if peaks else "fallback")},
+                "roofline": roofline(args.env, n, ms, launches),
                 "clocks": clocks}
         if not args.no_cpu_baseline:
             from oracle import oracle_py
-            oracle_py.build()
+            os.environ["MYO_ORACLE_LIB"] = oracle_py.build_native()
             t0 = time.perf_counter()
-            v, nst = cpu_baseline(args.env, float(os.environ.get("MYO_BENCH_CPU_BUDGET_S", 10.0)), threads=1)         # bounded sample: 10 s of single-thread stepping
+            v, nst = cpu_baseline(args.env, float(os.environ.get("MYO_BENCH_CPU_BUDGET_S", 10.0)), threads=1, u01=args.actions == "u01")         # bounded sample: 10 s of single-thread stepping
             line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
-                                    "sample": "%d env-steps of %s, 1 env, 1 thread (%.1f s)" % (nst, args.env, time.perf_counter() - t0)}
+                                    "sample": "%d env-steps of %s, 1 env, 1 thread (%.1f s), oracle port built -O3 -march=native; not MuJoCo: %s" % (nst, args.env, time.perf_counter() - t0, MUJOCO_PUBLISHED.get(args.env, "no published figure"))}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

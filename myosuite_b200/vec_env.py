@@ -237,8 +237,21 @@ class MyoVecEnv:
         return self.max_episode_steps
 
     def reset(self, seed=None, mask=None):
+        """Reset all envs (mask None) or those whose mask entry is non-zero.  Passing `seed` also rewinds the per-env episode counters of
+        the envs being reset (they key the Philox streams), so reset(seed=s) is reproducible like the reference's seeded np_random."""
+        torch = self.torch
+        if mask is not None:
+            mask = torch.as_tensor(mask, device=self.device)
+            if mask.numel() != self.num_envs:
+                raise ValueError("reset mask must have %d entries, got %d" % (self.num_envs, mask.numel()))
+            mask = (mask.reshape(-1) != 0).to(torch.uint8).contiguous()
         if seed is not None:
             self.seed_value = int(seed)
+            if mask is None:
+                self.t["episode_count"].zero_()
+            else:
+                self.t["episode_count"][mask.bool()] = 0
+        self._reset_mask = mask          # keep alive until the launch has consumed it
         self.batch.reset(mask=mask, seed=self.seed_value, env_offset=self.env_offset, stream=self._stream())
         return self.t["obs"], {}
 
@@ -249,10 +262,12 @@ class MyoVecEnv:
         """action: float32 CUDA tensor [num_envs, nu] (values as the reference's action_space: [-1, 1])."""
         a = self.t["action"]
         if action.data_ptr() != a.data_ptr():
+            if tuple(action.shape) != tuple(a.shape):
+                raise ValueError("action must have shape %s, got %s" % (tuple(a.shape), tuple(action.shape)))
             a.copy_(action, non_blocking=True)
         self.batch.step(stream=self._stream())
         t = self.t
-        return t["obs"], t["reward"], t["done"], t["truncated"], {"last_return": t["last_return"], "time": t["time"]}
+        return t["obs"], t["reward"], t["done"], t["truncated"], {"last_return": t["last_return"], "time": t["time"], "overflow": t["overflow"]}
 
     def step_host(self, action_cpu_pinned):
         """End-to-end call with HOST buffers: H2D action copy, step, D2H of reward/done (the e2e bench path)."""
@@ -278,6 +293,29 @@ class MyoVecEnv:
                 self.t[name][:, : np.shape(v)[-1]] = torch.as_tensor(np.asarray(v), dtype=torch.float64, device=self.device)
         self.t["qacc_warmstart"].zero_()
 
+    STATE_KEYS = ("time", "qpos", "qvel", "act", "qacc_warmstart", "target", "step_count", "episode_count", "ep_return", "fatigue", "env_prm")
+
+    def get_env_state(self, index=None):
+        """Full state of the batch (or of env `index`) as numpy arrays: the reference's get_env_state (env_base.py:688-718: time, qpos, qvel, act)
+        plus what this backend keeps per env besides mjData: the solver warm start, the task target (the reference stores it in site_pos /
+        target_jnt_value), TimeLimit and episode counters, fatigue compartments (fatigue.py MA/MR/MF) and per-env model overrides."""
+        self.torch.cuda.current_stream(self.device).synchronize()
+        out = {}
+        for k in self.STATE_KEYS:
+            if k in self.t:
+                v = self.t[k] if index is None else self.t[k][index]
+                out[k] = v.detach().cpu().numpy().copy()
+        return out
+
+    def set_env_state(self, state, index=None):
+        """Inverse of get_env_state (env_base.py:720-759); obs / reward / done are refreshed from the new state like the reference's forward()."""
+        torch = self.torch
+        for k, v in state.items():
+            if k in self.t and k in self.STATE_KEYS and v is not None:
+                dst = self.t[k] if index is None else self.t[k][index]
+                dst.copy_(torch.as_tensor(np.asarray(v), device=self.device).to(dst.dtype).reshape(dst.shape))
+        self.refresh_obs()
+
     def task_info(self):
         """`rwd_sparse` / `solved` of the current observations (the reference's info dict, env_base.py:585-616), derived lazily from obs."""
         from . import task_info
@@ -296,35 +334,177 @@ class MyoVecEnv:
         self.batch.forward_debug(c, n_substeps, stream=self._stream())
 
 
+class _DataView:
+    """`env.mj_data`-like read access to the single env's state (numpy copies of the device rows)."""
+
+    def __init__(self, vec):
+        self._vec = vec
+
+    def _row(self, k):
+        self._vec.torch.cuda.current_stream(self._vec.device).synchronize()
+        return self._vec.t[k][0].detach().cpu().numpy().copy()
+
+    qpos = property(lambda self: self._row("qpos"))
+    qvel = property(lambda self: self._row("qvel"))
+    act = property(lambda self: self._row("act")[: self._vec.mj_model.na])
+    time = property(lambda self: float(self._row("time")))
+
+
 class MyoEnv:
-    """Single-env façade with the reference's gym call shapes (numpy in / numpy out), n_env = 1 on the GPU."""
+    """Single-env facade with the reference's gym call shapes (numpy in / numpy out), n_env = 1 on the GPU.
+
+    Mirrors what agents and the reference's own tests use on `env.unwrapped` (tests/test_envs.py:54-123): action_space, observation_space,
+    obs_dict, rwd_dict, get_obs_dict, get_reward_dict, get_env_infos, get_env_state / set_env_state, seed / get_input_seed, dt, horizon,
+    mj_model, mj_data, pickling (EzPickle semantics: the constructor arguments are pickled, plus the env state).  One device->host
+    transfer per step: obs, reward, done, truncated and time travel in one packed float64 row."""
+
+    metadata = {"render_modes": []}
 
     def __init__(self, env_id, seed=None, device=0, **kwargs):
+        from . import gym_api
+        self._ctor = (env_id, seed, device, dict(kwargs))
         self.vec = MyoVecEnv(env_id, 1, device=device, seed=0 if seed is None else seed, auto_reset=False, **kwargs)
+        v = self.vec
         self.unwrapped = self
-        self.mj_model = self.vec.mj_model
-        self.dt, self.horizon = self.vec.dt, self.vec.max_episode_steps
+        self.env_id, self.mj_model, self.mj_data = env_id, v.mj_model, _DataView(v)
+        self.dt, self.horizon, self.frame_skip = v.dt, v.max_episode_steps, v.frame_skip
         self.input_seed = seed
-        self._elapsed = 0
+        m = v.mj_model
+        self.action_space, self.observation_space = gym_api.make_spaces(m.nu, v.obs_dim, bool(v.kwargs.get("normalize_act", True)), m.actuator_ctrlrange)
+        self._ntip = len(getattr(v, "tip_names", ()))
+        self.obs_keys = [k for k, _ in gym_api.obs_layout(v.task, m.nq, m.nv, m.na, self._ntip)]
+        self.rwd_keys_wt = dict(v.kwargs.get("weighted_reward_keys") or gym_api.DEFAULT_WEIGHTS[v.task])
+        self.rwd_mode = "dense"
+        self.obs_dict, self.rwd_dict, self.proprio_dict, self.visual_dict = {}, {}, {}, {}
+        self._reseed = True
+        self._task_cfg = self._make_task_cfg()
+        self.reset()
 
+    # ---- task constants for the host-side reward dict
+    def _make_task_cfg(self):
+        v, m, kw = self.vec, self.vec.mj_model, self.vec.kwargs
+        cfg = {"pose_thd": float(kw.get("pose_thd", 0.35)), "dt": v.dt, "ntip": self._ntip, "far_th": float(kw.get("far_th", 0.35))}
+        if v.task == "walk":
+            cfg.update(target_x_vel=kw.get("target_x_vel", 0.0), target_y_vel=kw.get("target_y_vel", 1.2), min_height=kw.get("min_height", 0.8), max_rot=kw.get("max_rot", 0.8),
+                       target_rot=np.asarray(kw.get("target_rot") if kw.get("target_rot") is not None else m.key_qpos[0][3:7], dtype=np.float64))
+            for j in ("hip_flexion_l", "hip_flexion_r", "hip_adduction_l", "hip_adduction_r", "hip_rotation_l", "hip_rotation_r"):
+                cfg["q_" + j] = int(m.jnt_qposadr[m.name2id("joint", j)])
+        return cfg
+
+    # ---- seeding (env_base.py:119-123)
     def seed(self, seed=None):
         self.input_seed = seed
         self.vec.seed_value = 0 if seed is None else int(seed)
+        self.action_space.seed(seed)
+        self._reseed = True
         return [seed]
 
     def get_input_seed(self):
         return self.input_seed
 
-    def reset(self, seed=None, **kwargs):
-        obs, info = self.vec.reset(seed=seed)
-        self._elapsed = 0
-        return obs[0].cpu().numpy(), info
+    # ---- one packed device->host transfer
+    def _fetch(self):
+        torch, t = self.vec.torch, self.vec.t
+        row = torch.cat([t["obs"][0].double(), t["reward"].double(), t["done"].double(), t["truncated"].double(), t["time"]]).cpu().numpy()
+        n = self.vec.obs_dim
+        obs = row[:n].astype(np.float32)
+        self._last = dict(obs=obs, reward=float(row[n]), done=bool(row[n + 1]), truncated=bool(row[n + 2]), time=float(row[n + 3]))
+        self.obs_dict = self.get_obs_dict()
+        self.rwd_dict = self.get_reward_dict(self.obs_dict)
+        return self._last
 
-    def step(self, a):
+    def reset(self, seed=None, **kwargs):
+        if seed is not None:
+            self.seed(seed)
+        self.vec.reset(seed=self.vec.seed_value if self._reseed else None)      # a (re)seed rewinds the Philox episode counter: reproducible resets
+        self._reseed = False
+        return self._fetch()["obs"], {}
+
+    def step(self, a, **kwargs):
         torch = self.vec.torch
-        act = torch.as_tensor(np.asarray(a, dtype=np.float32)[None], device=self.vec.device)
-        obs, rew, done, trunc, info = self.vec.step(act)
-        return obs[0].cpu().numpy(), float(rew[0].item()), bool(done[0].item()), bool(trunc[0].item()), {"time": float(info["time"][0].item())}
+        act = torch.as_tensor(np.asarray(a, dtype=np.float32).reshape(1, -1), device=self.vec.device)
+        self.vec.step(act)
+        r = self._fetch()
+        return r["obs"], r["reward"], r["done"], r["truncated"], self.get_env_infos()
+
+    def forward(self, **kwargs):
+        """env.forward() (env_base.py:393-432): recompute obs / reward / done of the current state."""
+        self.vec.refresh_obs()
+        r = self._fetch()
+        return r["obs"], r["reward"], r["done"], self.get_env_infos()
+
+    # ---- dicts (env_base.py:409-432, task get_obs_dict / get_reward_dict)
+    def get_obs_dict(self, *sim_args):
+        """obs_dict of the current observation.  (The reference signature takes (mj_model, mj_data); the state lives on the device here, so
+        any arguments are ignored.)"""
+        from . import gym_api
+        m = self.mj_model
+        return gym_api.obs_dict_from_vec(self.vec.task, self._last["obs"], np.array([self._last["time"]]), m.nq, m.nv, m.na, self._ntip)
+
+    def get_reward_dict(self, obs_dict):
+        from . import gym_api
+        r = gym_api.reward_dict(self.vec.task, obs_dict, self.rwd_keys_wt, self._task_cfg)
+        if obs_dict is self.obs_dict or obs_dict.get("time") is self.obs_dict.get("time"):
+            r["dense"] = np.float64(self._last["reward"])        # the device's f64 reward (the host recomputation only sees the f32 observation)
+        return r
+
+    def get_proprioception(self, obs_dict=None):
+        """env_base.py get_proprioception: (None, None, None) when no proprio_keys are configured (the default of the hot-path envs)."""
+        return None, None, None
+
+    def get_exteroception(self, **kwargs):
+        return {}
+
+    def get_env_infos(self):
+        """env_base.py:585-616."""
+        return {"time": self._last["time"], "rwd_dense": self._last["reward"], "rwd_sparse": float(np.squeeze(self.rwd_dict["sparse"])),
+                "solved": bool(np.squeeze(self.rwd_dict["solved"])), "done": self._last["done"], "obs_dict": self.obs_dict, "visual_dict": {},
+                "proprio_dict": self.proprio_dict, "rwd_dict": self.rwd_dict, "state": self.get_env_state()}
+
+    # ---- state (env_base.py:688-759)
+    def get_env_state(self):
+        return self.vec.get_env_state(index=0)
+
+    def set_env_state(self, state_dict):
+        self.vec.set_env_state(state_dict, index=0)
+        self._fetch()
+
+    # ---- pickling: constructor arguments (EzPickle) + the current state
+    def __getstate__(self):
+        return {"ctor": self._ctor, "input_seed": self.input_seed, "state": self.get_env_state()}
+
+    def __setstate__(self, d):
+        env_id, seed, device, kwargs = d["ctor"]
+        self.__init__(env_id, seed=seed, device=device, **kwargs)
+        self.input_seed = d["input_seed"]
+        self.set_env_state(d["state"])
+
+    def close(self):
+        pass
+
+
+def register_gym():
+    """Register every implemented id with gymnasium (or gym) when one of them is installed: gymnasium.make("myoHandPoseRandom-v0") then
+    returns a MyoEnv (wrapped in the library's TimeLimit / checker wrappers).  Returns the list of registered ids ([] without a gym)."""
+    for mod in ("gymnasium", "gym"):
+        try:
+            g = __import__(mod)
+            break
+        except Exception:
+            g = None
+    if g is None:
+        return []
+    done = []
+    for eid in registered_ids():
+        try:
+            steps, _, entry = env_spec(eid)
+            if not any(entry.endswith(x) for x in ("pose_v0:PoseEnvV0", "walk_v0:WalkEnvV0", "reach_v0:ReachEnvV0")) and "obj_hold_v0:ObjHold" not in entry:
+                continue
+            g.register(id=eid, entry_point="myosuite_b200.vec_env:MyoEnv", max_episode_steps=steps, kwargs={"env_id": eid})
+            done.append(eid)
+        except Exception:
+            pass
+    return done
 
 
 def make(env_id, num_envs=None, **kwargs):

@@ -17,10 +17,23 @@ def build(force=False):
     return so
 
 
+def build_native():
+    """-O3 -march=native build for the timed CPU arm (bench.py --impl reference), compiled ON the machine that runs it:
+    oracle/_native/libmyo_oracle_native.so.  Falls back to the portable build if the compiler refuses."""
+    d = os.path.join(_HERE, "_native"); os.makedirs(d, exist_ok=True)
+    so = os.path.join(d, "libmyo_oracle_native.so")
+    try:
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-std=c11", "-ffp-contract=off", "-shared", "-o", so, os.path.join(_HERE, "myo_oracle.c"), "-lm"],
+                              stderr=subprocess.DEVNULL)
+        return so
+    except Exception:
+        return build()
+
+
 def lib():
     global _LIB
     if _LIB is None:
-        L = ctypes.CDLL(build())
+        L = ctypes.CDLL(os.environ.get("MYO_ORACLE_LIB") or build())
         L.oracle_create.restype = ctypes.c_void_p
         L.oracle_create.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.oracle_field.restype = ctypes.POINTER(ctypes.c_double)
