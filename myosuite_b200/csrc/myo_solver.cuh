@@ -174,12 +174,19 @@ __device__ __noinline__ void chol_rs(double* H, double* x, int n, int lane) {
     if (own && lane >= k) H[rowadr + k] = r[k];      // column k, unscaled (U[i][k] = L[i][k] d_k); lane k: the pivot d_k
     if (lane == k) x[k] = b;                         // z_k of the forward substitution is final (x has chol_pad(n) slots)
     __syncwarp();
-    const double invd = 1.0/fmax(H[TRI(k,k)], MYO_MINVAL), zk = x[k];
+    // all broadcast loads of this step are issued as ONE batch, ahead of the reciprocal's dependent chain (left to itself ptxas
+    // alternates LDS / DFMA through a single register: 29 cycles of shared-memory latency per trailing entry, 14 k cycles per solve)
+    double col[NMAX];
+    #pragma unroll
+    for (int j = k+1; j < NMAX; j++) col[j] = H[TRI(j,k)];
+    const double dk = H[TRI(k,k)], zk = x[k];
+    asm volatile("" ::: "memory");
+    const double invd = 1.0/fmax(dk, MYO_MINVAL);
     if (lane == k) invd_own = invd;
     const double t = r[k]*invd;                      // L[lane][k] on lanes > k
     b = lane > k ? fma(-t, zk, b) : b;
     #pragma unroll
-    for (int j = k+1; j < NMAX; j++) r[j] = fma(-t, H[TRI(j,k)], r[j]);
+    for (int j = k+1; j < NMAX; j++) r[j] = fma(-t, col[j], r[j]);
   }
   // backward substitution: u_i = z_i - sum_{k>i} U[k][i] x_k ; x_i = u_i / d_i
   #pragma unroll
