@@ -26,7 +26,7 @@ enum { PD_NBD, PD_NLEVEL, PD_NPT, PD_NSP, PD_NWE, PD_NTA, PD_NNZ, PD_NTERM, PD_N
 #define PAM_STRIDE 6
 #define PG_STRIDE 16
 #define PPAIR_STRIDE 12
-#define PPAIR_ISTRIDE 7
+#define PPAIR_ISTRIDE 8     // g1 g2 condim path_adr path_n collider class model-pair-index
 #define PLIM_STRIDE 12
 #define PEQ_STRIDE 16
 #define PEQ_ISTRIDE 6
@@ -642,7 +642,32 @@ __device__ __forceinline__ void store_contact(const DevModel& m, double* con, in
   f[3] = y0*n; f[4] = y1*n; f[5] = y2*n;
   icon[ci] = p; }
 
-// Contacts are listed analytic colliders first (pair order), then the iterative ellipsoid colliders (pair order).
+// The two collider passes leave two runs of contacts, each in model pair order: [0, na) from the analytic colliders, [na, ncon) from the
+// iterative ellipsoid colliders.  Merge them into ONE list in model pair order (the order MuJoCo reports contacts in, and therefore the
+// order of the constraint rows): stable rank of every contact among the other run, records moved through registers.  Up to 64 contacts.
+__device__ __noinline__ void contacts_merge_order(const DevModel& m, const Warp w, int na, int ncon) {
+  double* con = SCR(s_con); int* icon = (int*)SCR(s_icon); int* key = (int*)SCR(s_clist);      // (the candidate list is dead by now)
+  const idx_t* pr = CI(PPAIR);
+  for (int c = w.lane; c < ncon; c += 32) key[c] = pr[PPAIR_ISTRIDE*icon[c] + 7];
+  __syncwarp();
+  double rec[2][CON_STRIDE]; int pp[2], dst[2];
+  #pragma unroll
+  for (int s = 0; s < 2; s++) { const int c = w.lane + 32*s; dst[s] = -1; pp[s] = 0;
+    if (c < ncon) { const int k = key[c]; int cnt = 0;
+      if (c < na) { for (int q = na; q < ncon; q++) cnt += key[q] < k; dst[s] = c + cnt; }
+      else { for (int q = 0; q < na; q++) cnt += key[q] < k; dst[s] = (c - na) + cnt; }
+      pp[s] = icon[c];
+      #pragma unroll
+      for (int i = 0; i < CON_STRIDE; i++) rec[s][i] = con[c*CON_STRIDE + i]; } }
+  __syncwarp();
+  #pragma unroll
+  for (int s = 0; s < 2; s++) if (dst[s] >= 0) { icon[dst[s]] = pp[s];
+    #pragma unroll
+    for (int i = 0; i < CON_STRIDE; i++) con[dst[s]*CON_STRIDE + i] = rec[s][i]; }
+  __syncwarp();
+}
+
+// Contacts are found by the analytic colliders first, then by the iterative ellipsoid colliders, and merged into model pair order.
 // Overflow (more contacts than maxcon, or more surviving ellipsoid candidates than kcand): the extra ones are dropped first-come and
 // CNT_overflow is set; the step kernel ORs it into the caller's sticky per-env `overflow` buffer.
 __device__ void phase_collision(const DevModel& m, const Warp w) {
@@ -659,6 +684,7 @@ __device__ void phase_collision(const DevModel& m, const Warp w) {
     if (o.n >= 2) store_contact(m, con, icon, idx + 1, p, o.c1, o);
     ncon += __popc(m0) + __popc(m1); }
   if (ncon > m.maxcon) { overflow = 1; ncon = m.maxcon; }
+  const int na = ncon;
   if (m.npair > m.npair_an) {
     // iterative ellipsoid colliders: rare and expensive -> conservative cull + compaction, then one surviving candidate per lane
     int* clist = (int*)SCR(s_clist); int ncand = 0;
@@ -674,6 +700,8 @@ __device__ void phase_collision(const DevModel& m, const Warp w) {
       if (o.n) store_contact(m, con, icon, idx, p, o.c0, o);
       ncon += __popc(m0); }
     if (ncon > m.maxcon) { overflow = 1; ncon = m.maxcon; }
+    __syncwarp();
+    if (ncon > na && na > 0) contacts_merge_order(m, w, na, ncon);
   }
   WI_(ncon) = ncon; WI_(overflow) = overflow;
   __syncwarp();

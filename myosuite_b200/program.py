@@ -25,7 +25,7 @@ from . import mjmath as mm
 NPDIM = 26
 
 PB_STRIDE, PWE_STRIDE, PA_STRIDE, PG_STRIDE, PPAIR_STRIDE, PLIM_STRIDE, PEQ_STRIDE = 22, 16, 17, 16, 12, 12, 16
-PAM_STRIDE, PPAIR_ISTRIDE = 6, 7
+PAM_STRIDE, PPAIR_ISTRIDE = 6, 8
 
 # collision function ids
 CT_NONE, CT_CAP_CAP, CT_SPH_SPH, CT_SPH_CAP, CT_PLANE_SPH, CT_PLANE_CAP, CT_PLANE_ELL, CT_CAP_ELL, CT_ELL_ELL = range(9)
@@ -44,7 +44,13 @@ def _kbimp(solref, solimp, timestep):
     return K, B, si
 
 
-def build_program(m):
+# Collision pairs whose geom-type combination has no device collider are an ERROR unless listed here by (model name of geom1, geom2).
+# myohand_hold: the free object ellipsoid vs the scene's static pedestal cylinder.  The pair can only act after the object has fallen
+# 1.4 m; ObjHold terminates ("drop") at 0.3 m from the goal (obj_hold_v0.py:100), so it never produces a contact inside an episode.
+ALLOWED_UNSUPPORTED_PAIRS = {("object", "<static cylinder>"), ("<static cylinder>", "object")}        # unnamed static geoms are labelled <static TYPE>
+
+
+def build_program(m, allow_unsupported=ALLOWED_UNSUPPORTED_PAIRS):
     nb = m.nbody
     dyn_ids = [b for b in range(1, nb) if m.body_weldid[b] != 0]
     kin0 = mjcf.kinematics(m, m.qpos0)
@@ -349,6 +355,22 @@ def build_program(m):
     pair_model_index = []
     def _ct(p):
         return ctype_of.get((int(m.geom_type[int(m.pair_geom1[p])]), int(m.geom_type[int(m.pair_geom2[p])])), CT_NONE)
+    dropped_pairs = []
+    for p in range(m.npair):
+        if _ct(p) == CT_NONE:
+            tname = {mjcf.GEOM_PLANE: "plane", mjcf.GEOM_SPHERE: "sphere", mjcf.GEOM_CAPSULE: "capsule", mjcf.GEOM_ELLIPSOID: "ellipsoid"}
+
+            def _label(g):
+                nm = m.id2name("geom", g)
+                if nm and not nm.startswith("geom"):
+                    return nm
+                kind = tname.get(int(m.geom_type[g]), {5: "cylinder", 6: "box", 7: "mesh"}.get(int(m.geom_type[g]), "type%d" % int(m.geom_type[g])))
+                return "<static %s>" % kind if m.body_weldid[int(m.geom_bodyid[g])] == 0 else "<%s on %s>" % (kind, m.id2name("body", int(m.geom_bodyid[g])))
+            names = tuple(_label(int(g)) for g in (m.pair_geom1[p], m.pair_geom2[p]))
+            if names not in allow_unsupported:
+                raise mjcf.MJCFError("collision pair %s (geom types %d, %d) has no device collider; pass it in allow_unsupported to drop it knowingly"
+                                     % (names, int(m.geom_type[int(m.pair_geom1[p])]), int(m.geom_type[int(m.pair_geom2[p])])))
+            dropped_pairs.append(names)
     pair_order = [p for p in range(m.npair) if _ct(p) not in (CT_NONE, CT_CAP_ELL, CT_ELL_ELL)] + \
                  [p for p in range(m.npair) if _ct(p) in (CT_CAP_ELL, CT_ELL_ELL)]
     n_analytic = sum(1 for p in pair_order if _ct(p) not in (CT_CAP_ELL, CT_ELL_ELL))
@@ -370,7 +392,7 @@ def build_program(m):
         ckey = crow.tobytes()
         if ckey not in pcls_index:
             pcls_index[ckey] = len(PPAIR_d); PPAIR_d.append(crow)
-        PPAIR.append([geom_ref(g1), geom_ref(g2), dim, path_adr, len(ds), ct, pcls_index[ckey]])
+        PPAIR.append([geom_ref(g1), geom_ref(g2), dim, path_adr, len(ds), ct, pcls_index[ckey], p])      # [7]: model pair index = rank in MuJoCo contact order
         PPAIR_tran.append(tran)
         pair_model_index.append(p)
     # ---- joint limits
@@ -440,7 +462,7 @@ def build_program(m):
         "PLV_adr": ia(PLV_adr), "PLV": ia(PLV), "PFE_adr": ia(PFE_adr), "PFE": ia(PFE), "PFT_adr": ia(PFT_adr), "PFT": ia(PFT),
         "PDS_adr": ia(PDS_adr), "PDS": ia(PDS), "PEQ_d": np.array(PEQ_d, dtype=np.float64).reshape(-1, PEQ_STRIDE),
     }
-    info = dict(dyn_body_ids=order, act_tendons=act_tendons, pair_model_index=pair_model_index,
+    info = dict(dyn_body_ids=order, act_tendons=act_tendons, pair_model_index=pair_model_index, dropped_pairs=dropped_pairs,
                 geom_model_ids={v: k for k, v in gmap.items()})
     return prog, info
 
