@@ -148,3 +148,17 @@ def test_program_invariants_the_kernel_relies_on():
         lim = np.asarray(p["PLIM_d"]).reshape(-1, program.PLIM_STRIDE)
         expect = sum(2 if (r[1] - r[0]) < 2 * r[2] else 1 for r in lim)
         assert int(p["P_dims"][program.PD_NLIMROW]) == expect and expect >= len(lim)
+
+
+def test_dims_contact_capacity(models):
+    """myo_model_dims reports the contact / row capacities the kernel will run with (a zero here once silently disabled every contact)."""
+    from myosuite_b200 import abi, blob, program
+    m = models["myohand_pose"]; prog, _ = program.build_program(m)
+    dm = abi.DeviceModel(*blob.pack(m, prog))
+    cfg = abi.MyoTaskCfg(); cfg.task = abi.TASK_POSE
+    d = dm.dims(cfg)
+    assert d.maxcon == 32 and d.maxefc == 23 + 4 * 32 and d.smem_bytes_per_env * 10 + d.reserved[1] + 64 <= 232448      # 10 env-warps per SM
+    cfg.maxcon = 48
+    assert dm.dims(cfg).maxcon == 48
+    cfg.maxcon = 1000
+    assert dm.dims(cfg).maxcon == 64
