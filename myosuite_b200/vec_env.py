@@ -444,7 +444,7 @@ class MyoEnv:
     def get_reward_dict(self, obs_dict):
         from . import gym_api
         r = gym_api.reward_dict(self.vec.task, obs_dict, self.rwd_keys_wt, self._task_cfg)
-        if obs_dict is self.obs_dict or obs_dict.get("time") is self.obs_dict.get("time"):
+        if float(np.squeeze(obs_dict["time"])) == self._last["time"]:
             r["dense"] = np.float64(self._last["reward"])        # the device's f64 reward (the host recomputation only sees the f32 observation)
         return r
 

@@ -403,14 +403,15 @@ def test_mid_episode_forward_and_rollout_parity(eid, warm):
     env.forward_debug(ctrl, 0); torch.cuda.synchronize()
     t = {k: v.cpu().numpy().copy() for k, v in env.t.items() if k.startswith("tap_")}
     pmi = env.prog_info["pair_model_index"]
-    ncon_total = checked = 0
+    ncon_total = checked = 0; worst = 0.0
     oracles = [_oracle_for(env, e) for e in range(n)]
     for e in range(n):
         o = oracles[e]; o.reset(); o.set(qpos=qpos[e], qvel=qvel[e], act=act[e, :m.na], ctrl=ctrl[e]); o.forward()
         if not alive[e] or not _in_regime(o, m):
             continue
         checked += 1
-        assert relerr(t["tap_qacc"][e], o.f("qacc")) < RTOL
+        worst = max(worst, relerr(t["tap_qacc"][e], o.f("qacc")))
+        assert relerr(t["tap_qacc"][e], o.f("qacc")) < 1e-6          # (stiff object / finger contacts; north star: 1e-5)
         assert relerr(t["tap_actuator_force"][e], o.f("actuator_force")) < RTOL
         nc = int(t["tap_ncon"][e, 0])
         got = [pmi[p] for p in t["tap_contact_pair"][e][:nc]]
@@ -418,6 +419,7 @@ def test_mid_episode_forward_and_rollout_parity(eid, warm):
         assert got == exp
         np.testing.assert_allclose(t["tap_contact_dist"][e][:nc], [d for p, d in zip(o.i("con_pair"), o.f("con_dist")) if int(p) in set(pmi)], rtol=1e-7, atol=1e-11)
         ncon_total += nc
+    print("%s after %d steps: %d/%d envs checked, %d contacts, worst qacc deviation %.2e" % (eid, warm, checked, n, ncon_total, worst))
     assert checked == int(alive.sum()) and checked >= n // 2          # every live env is inside the parity regime
     assert ncon_total > 0
     if env.task == "hold":      # the object really is in contact with the hand in this batch

@@ -95,7 +95,7 @@ def test_env_contract_like_reference_test_envs(env_id):
     od = env1.get_obs_dict(env1.mj_model, env1.mj_data); assert len(od) > 0 and "act" in od and "time" in od
     rd = env1.get_reward_dict(od); assert {"dense", "sparse", "solved", "done"} <= set(rd)
     np.testing.assert_allclose(np.concatenate([np.ravel(od[k]) for k in env1.obs_keys]), obs1)       # obs vector == concatenated obs_dict (obs_vec_dict.py:76-88)
-    assert abs(float(np.squeeze(rd["dense"])) - rwd1) < 1e-9
+    assert abs(float(np.squeeze(rd["dense"])) - rwd1) < 1e-9          # the device's own reward is reported for the current observation
     st = env1.get_env_state(); assert {"time", "qpos", "qvel", "act"} <= set(st) and len(st["qpos"]) == env1.mj_model.nq
     np.testing.assert_allclose(env1.mj_data.qpos, st["qpos"])
     env1.reset()
