@@ -701,7 +701,9 @@ __device__ void phase_collision(const DevModel& m, const Warp w) {
       ncon += __popc(m0); }
     if (ncon > m.maxcon) { overflow = 1; ncon = m.maxcon; }
     __syncwarp();
+#ifndef MYO_NO_MERGE
     if (ncon > na && na > 0) contacts_merge_order(m, w, na, ncon);
+#endif
   }
   WI_(ncon) = ncon; WI_(overflow) = overflow;
   __syncwarp();

@@ -180,7 +180,9 @@ __device__ __noinline__ void chol_rs(double* H, double* x, int n, int lane) {
     #pragma unroll
     for (int j = k+1; j < NMAX; j++) col[j] = H[TRI(j,k)];
     const double dk = H[TRI(k,k)], zk = x[k];
+#ifndef MYO_CHOL_NOBATCH
     asm volatile("" ::: "memory");
+#endif
     const double invd = 1.0/fmax(dk, MYO_MINVAL);
     if (lane == k) invd_own = invd;
     const double t = r[k]*invd;                      // L[lane][k] on lanes > k
