@@ -48,9 +48,13 @@ __device__ void write_taps_solve(const DevModel& m, const Warp w, const StepArgs
   __syncwarp();
 }
 __device__ void write_taps_contacts(const DevModel& m, const Warp w, const StepArgs& a, int env) {   // after constraint assembly (con is overwritten by the solve)
-  const myo_buffers& b = a.b;
-  if (b.tap_contact_pair) for (int c = w.lane; c < m.maxcon; c += 32) b.tap_contact_pair[(size_t)env*m.maxcon+c] = c < WI_(ncon) ? S_cpair[c] : -1;
-  if (b.tap_contact_dist) for (int c = w.lane; c < m.maxcon; c += 32) b.tap_contact_dist[(size_t)env*m.maxcon+c] = c < WI_(ncon) ? S_con[c*CON_STRIDE] : 0.0;
+  const myo_buffers& b = a.b; const int ncon = WI_(ncon);
+  // reported in model pair order (the rank phase_constraints assigned), -1 / 0 padded
+  if (b.tap_contact_pair) for (int c = w.lane; c < m.maxcon; c += 32) if (c >= ncon) b.tap_contact_pair[(size_t)env*m.maxcon+c] = -1;
+  if (b.tap_contact_dist) for (int c = w.lane; c < m.maxcon; c += 32) if (c >= ncon) b.tap_contact_dist[(size_t)env*m.maxcon+c] = 0.0;
+  for (int c = w.lane; c < ncon; c += 32) { const int r = CRANK(S_crown[c]);
+    if (b.tap_contact_pair) b.tap_contact_pair[(size_t)env*m.maxcon+r] = S_cpair[c];
+    if (b.tap_contact_dist) b.tap_contact_dist[(size_t)env*m.maxcon+r] = S_con[c*CON_STRIDE]; }
   __syncwarp();
 }
 
@@ -421,7 +425,7 @@ static void fill_devmodel(const myo_model* mm, const myo_task_cfg* cfg, DevModel
   d.kcand = d.npair - d.npair_an; int candsz = al2((d.kcand + 1)/2);
   t = 0; d.s_conJ = t; d.s_clist = t; t += imax(al2(3*d.maxpath*mc), candsz); d.s_efD = t; t += al2(d.maxefc); d.s_efA = t; t += al2(d.maxefc); d.s_eqJ = t; t += al2(d.neq);
   d.ngc = P[PD_NGC]; d.s_gpose = d.s_efD; if (t - d.s_efD < al2(6*d.ngc)) t = d.s_efD + al2(6*d.ngc);     // geom poses (collision only) alias the row arrays (written after it)
-  d.s_icon = t; t += al2((3*mc + d.nlimrow + 4 + 1)/2); int sizeS3 = t;
+  d.s_icon = t; t += al2((4*mc + d.nlimrow + 4 + 1)/2); int sizeS3 = t;      // path masks (2 ints per contact), pair, row|nrow, limit rows
   d.s_con = sizeS3; int sizeCon = al2(CON_STRIDE*mc);
   t = sizeS3; d.s_efR = t; t += al2(d.maxefc); d.s_efV = t; t += al2(d.maxefc); d.s_va = t; t += al2(d.nvp); d.s_vg = t; t += al2(d.nvp); d.s_vp = t; t += al2(d.nvp);
   d.s_vMa = t; t += al2(d.nvp); d.s_vMp = t; t += al2(d.nvp);

@@ -60,12 +60,13 @@ struct DevModel {
 extern __shared__ __align__(16) double smem[];
 
 struct Warp { int base, lane; };   // by value: offset (doubles) of this warp's region in smem, lane id.  Everything else lives in shared memory.
-enum { CNT_ncon, CNT_nefc, CNT_nlimrow, CNT_niter, CNT_overflow, CNT_ncand, CNT_N = 8 };   // per-warp int counters (m.o_cnt)
+enum { CNT_ncon, CNT_nefc, CNT_nlimrow, CNT_niter, CNT_overflow, CNT_ncand, CNT_na, CNT_N = 8 };   // per-warp int counters (m.o_cnt)
 #define CI(name) ((const idx_t*)(smem + m.nD) + m.hoff[MYO_SEC_##name])
 #define CD(name) ((const double*)smem + m.hoff[MYO_SEC_##name])
 #define W_(f) (smem + w.base + m.o_##f)                       // persistent per-env arrays
 #define WI_(f) (((int*)(smem + w.base + m.o_cnt))[CNT_##f])   // per-env counters
 #define SCR(field) (smem + w.base + m.field)                  // scratch (m.s_* are offsets from the warp base)
+#define S_cpair (((int*)SCR(s_icon)) + 2*m.maxcon)             // contact -> program pair index (after the 64-bit path masks; see myo_solver.cuh)
 #define SHARED_PTR(p) __builtin_assume(__isShared(p))         // for pointer PARAMETERS of functions that may not be inlined
 
 // ------------------------------------------------------------------ small math
@@ -642,36 +643,12 @@ __device__ __forceinline__ void store_contact(const DevModel& m, double* con, in
   f[3] = y0*n; f[4] = y1*n; f[5] = y2*n;
   icon[ci] = p; }
 
-// The two collider passes leave two runs of contacts, each in model pair order: [0, na) from the analytic colliders, [na, ncon) from the
-// iterative ellipsoid colliders.  Merge them into ONE list in model pair order (the order MuJoCo reports contacts in, and therefore the
-// order of the constraint rows): stable rank of every contact among the other run, records moved through registers.  Up to 64 contacts.
-__device__ __noinline__ void contacts_merge_order(const DevModel& m, const Warp w, int na, int ncon) {
-  double* con = SCR(s_con); int* icon = (int*)SCR(s_icon); int* key = (int*)SCR(s_clist);      // (the candidate list is dead by now)
-  const idx_t* pr = CI(PPAIR);
-  for (int c = w.lane; c < ncon; c += 32) key[c] = pr[PPAIR_ISTRIDE*icon[c] + 7];
-  __syncwarp();
-  double rec[2][CON_STRIDE]; int pp[2], dst[2];
-  #pragma unroll
-  for (int s = 0; s < 2; s++) { const int c = w.lane + 32*s; dst[s] = -1; pp[s] = 0;
-    if (c < ncon) { const int k = key[c]; int cnt = 0;
-      if (c < na) { for (int q = na; q < ncon; q++) cnt += key[q] < k; dst[s] = c + cnt; }
-      else { for (int q = 0; q < na; q++) cnt += key[q] < k; dst[s] = (c - na) + cnt; }
-      pp[s] = icon[c];
-      #pragma unroll
-      for (int i = 0; i < CON_STRIDE; i++) rec[s][i] = con[c*CON_STRIDE + i]; } }
-  __syncwarp();
-  #pragma unroll
-  for (int s = 0; s < 2; s++) if (dst[s] >= 0) { icon[dst[s]] = pp[s];
-    #pragma unroll
-    for (int i = 0; i < CON_STRIDE; i++) con[dst[s]*CON_STRIDE + i] = rec[s][i]; }
-  __syncwarp();
-}
-
-// Contacts are found by the analytic colliders first, then by the iterative ellipsoid colliders, and merged into model pair order.
+// Contacts are found by the analytic colliders first ([0, na)), then by the iterative ellipsoid colliders ([na, ncon)), each run in model pair
+// order; phase_constraints ranks them into ONE model-pair order (contact reporting, numbering of the constraint rows) without moving records.
 // Overflow (more contacts than maxcon, or more surviving ellipsoid candidates than kcand): the extra ones are dropped first-come and
 // CNT_overflow is set; the step kernel ORs it into the caller's sticky per-env `overflow` buffer.
 __device__ void phase_collision(const DevModel& m, const Warp w) {
-  double* con = SCR(s_con); int* icon = (int*)SCR(s_icon);
+  double* con = SCR(s_con); int* icon = S_cpair;
   int ncon = 0, overflow = 0;
   geom_pose_all(m, w);
   // analytic primitives: one pair per lane
@@ -700,11 +677,7 @@ __device__ void phase_collision(const DevModel& m, const Warp w) {
       if (o.n) store_contact(m, con, icon, idx, p, o.c0, o);
       ncon += __popc(m0); }
     if (ncon > m.maxcon) { overflow = 1; ncon = m.maxcon; }
-    __syncwarp();
-#ifndef MYO_NO_MERGE
-    if (ncon > na && na > 0) contacts_merge_order(m, w, na, ncon);
-#endif
   }
-  WI_(ncon) = ncon; WI_(overflow) = overflow;
+  WI_(ncon) = ncon; WI_(na) = na; WI_(overflow) = overflow;
   __syncwarp();
 }

@@ -22,10 +22,13 @@
 #define S_Hs SCR(s_Hs)
 #define S_LD SCR(s_LD)
 #define S_Dinv SCR(s_Dinv)
-#define S_cpair ((int*)SCR(s_icon))            // contact -> program pair index
-#define S_crow (S_cpair + m.maxcon)            // contact -> first efc row
-#define S_cnrow (S_cpair + 2*m.maxcon)         // contact -> number of rows
-#define S_lrow (S_cpair + 3*m.maxcon)          // limit row descriptors (dof | side << 16)
+// integer records of the contact / row lists (S_cpair is defined in myo_device.cuh: the colliders write it)
+#define S_cmask ((unsigned long long*)SCR(s_icon))   // contact -> bit mask of the dofs on its path (the Jacobian's non-zero columns, ascending)
+#define S_crown (S_cpair + m.maxcon)           // contact -> first efc row | number of rows << 12 | rank in model pair order << 16
+#define CROW(rn) ((rn) & 0xfff)
+#define CNR(rn) (((rn) >> 12) & 7)
+#define CRANK(rn) ((rn) >> 16)
+#define S_lrow (S_cpair + 2*m.maxcon)          // limit row descriptors (dof | side << 16)
 
 __device__ __forceinline__ double impedance(const double* si, double pos, double margin) {
   if (si[0] == si[1] || si[2] <= MYO_MINVAL) return 0.5*(si[0]+si[1]);
@@ -50,16 +53,19 @@ __device__ void rows_apply(const DevModel& m, const Warp w, const double* x, dou
   for (int e = w.lane; e < m.neq; e += 32) { double v = x[eq[PEQ_ISTRIDE*e+1]]; if (eq[PEQ_ISTRIDE*e+3] >= 0) v += S_eqJ[e]*x[eq[PEQ_ISTRIDE*e+3]]; out[e] = v; }
   for (int r = w.lane; r < nlimrow; r += 32) { int dsc = S_lrow[r]; double sg = (dsc >> 16) & 1 ? -1.0 : 1.0; out[m.neq + r] = sg*x[dsc & 0xffff]; }
   const idx_t* pr = CI(PPAIR); const double* pd = CD(PPAIR_d); const idx_t* path = CI(PPATH);
-  for (int c = w.lane; c < ncon; c += 32) { int nr = S_cnrow[c]; if (!nr) continue;
+  for (int c = w.lane; c < ncon; c += 32) { const int rn = S_crown[c], nr = CNR(rn); if (!nr) continue;
     const idx_t* q = pr + PPAIR_ISTRIDE*S_cpair[c]; const double* J = S_conJ + c*3*m.maxpath; double n = 0, t1 = 0, t2 = 0;
     for (int e = 0; e < q[4]; e++) { double xv = x[path[q[3]+e] >> 1]; n += J[3*e]*xv; t1 += J[3*e+1]*xv; t2 += J[3*e+2]*xv; }
-    int rb = S_crow[c];
+    int rb = CROW(rn);
     if (nr == 1) out[rb] = n;
     else { const double* P = pd + q[6]*PPAIR_STRIDE; double mu1 = P[2], mu2 = P[3]; out[rb] = n+mu1*t1; out[rb+1] = n-mu1*t1; out[rb+2] = n+mu2*t2; out[rb+3] = n-mu2*t2; } }
 }
 
-// vec[d] += sum_r J[r][d] * wgt[r]  (wgt already includes D and the active mask)
-__device__ void rows_applyT_add(const DevModel& m, const Warp w, const double* wgt, double* vec) {
+// vec[d] += sum_r J[r][d] * wgt[r]  (wgt already includes D and the active mask; wgt is DESTROYED: the rows of a contact are folded into its
+// normal / tangent weights in place).  Contacts are GATHERED: lane d owns vec[d] and walks the contact list, testing its bit in each contact's
+// path mask; the position of d in the contact's Jacobian is the number of lower bits set (paths list dofs in ascending order).  No lane
+// waits for another contact's rows: round 1 looped over the contacts with a warp sync and <= 8 busy lanes per contact.
+__device__ void rows_applyT_add(const DevModel& m, const Warp w, double* wgt, double* vec) {
   SHARED_PTR(wgt); SHARED_PTR(vec);
   const idx_t* eq = CI(PEQ); const int nlimrow = WI_(nlimrow), ncon = WI_(ncon);
   if (w.lane == 0) for (int e = 0; e < m.neq; e++) { vec[eq[PEQ_ISTRIDE*e+1]] += wgt[e]; if (eq[PEQ_ISTRIDE*e+3] >= 0) vec[eq[PEQ_ISTRIDE*e+3]] += S_eqJ[e]*wgt[e]; }
@@ -67,13 +73,17 @@ __device__ void rows_applyT_add(const DevModel& m, const Warp w, const double* w
   for (int pass = 0; pass < 2; pass++) {
     for (int r = w.lane; r < nlimrow; r += 32) { int dsc = S_lrow[r]; int neg = (dsc >> 16) & 1; if (neg == pass) vec[dsc & 0xffff] += (neg ? -1.0 : 1.0)*wgt[m.neq + r]; }
     __syncwarp(); }
-  const idx_t* pr = CI(PPAIR); const double* pd = CD(PPAIR_d); const idx_t* path = CI(PPATH);
-  for (int c = 0; c < ncon; c++) { int nr = S_cnrow[c]; if (!nr) continue;
-    const idx_t* q = pr + PPAIR_ISTRIDE*S_cpair[c]; const double* J = S_conJ + c*3*m.maxpath; int rb = S_crow[c]; double wn, w1 = 0, w2 = 0;
-    if (nr == 1) wn = wgt[rb];
-    else { const double* P = pd + q[6]*PPAIR_STRIDE; wn = wgt[rb]+wgt[rb+1]+wgt[rb+2]+wgt[rb+3]; w1 = P[2]*(wgt[rb]-wgt[rb+1]); w2 = P[3]*(wgt[rb+2]-wgt[rb+3]); }
-    for (int e = w.lane; e < q[4]; e += 32) vec[path[q[3]+e] >> 1] += J[3*e]*wn + J[3*e+1]*w1 + J[3*e+2]*w2;
-    __syncwarp(); }
+  const idx_t* pr = CI(PPAIR); const double* pd = CD(PPAIR_d);
+  for (int c = w.lane; c < ncon; c += 32) { const int rn = S_crown[c], nr = CNR(rn), rb = CROW(rn);      // fold the pyramid edges: (wn, w1, w2) into wgt[rb .. rb+2]
+    if (nr == 4) { const double* P = pd + pr[PPAIR_ISTRIDE*S_cpair[c] + 6]*PPAIR_STRIDE; const double a0 = wgt[rb], a1 = wgt[rb+1], a2 = wgt[rb+2], a3 = wgt[rb+3];
+      wgt[rb] = a0+a1+a2+a3; wgt[rb+1] = P[2]*(a0-a1); wgt[rb+2] = P[3]*(a2-a3); } }
+  __syncwarp();
+  for (int d = w.lane; d < m.nv; d += 32) { double acc = 0; const unsigned long long below = (1ull << d) - 1;
+    for (int c = 0; c < ncon; c++) { const unsigned long long mk = S_cmask[c];
+      if ((mk >> d) & 1) { const int rn = S_crown[c], nr = CNR(rn), rb = CROW(rn); const double* J = S_conJ + c*3*m.maxpath + 3*__popcll(mk & below);
+        if (nr == 4) acc += J[0]*wgt[rb] + J[1]*wgt[rb+1] + J[2]*wgt[rb+2]; else if (nr == 1) acc += J[0]*wgt[rb]; } }
+    vec[d] += acc; }
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------ constraint assembly
@@ -99,28 +109,50 @@ __device__ void phase_constraints(const DevModel& m, const Warp w) {
       S_D[r] = 1.0/R; S_aref[r] = -c[5]*sg*W_(qvel)[d] - c[4]*imp*(dist-c[2]); }
     nrow += __popc(m0) + __popc(m1); }
   WI_(nlimrow) = nrow;
-  // contacts: Jacobian over the dofs between the two bodies, regulariser, reference acceleration
+  // contacts: Jacobian over the dofs between the two bodies, regulariser, reference acceleration.
+  // The contact list holds two runs (analytic colliders [0, na), ellipsoid colliders [na, ncon)), each in model pair order.  Records stay
+  // where the colliders put them; what follows MuJoCo's contact order is the RANK of each contact (reported by the parity taps) and the
+  // numbering of the constraint rows, which are assigned in rank order.
   const idx_t* pr = CI(PPAIR); const double* pd = CD(PPAIR_d); const idx_t* path = CI(PPATH);
-  int rowbase = m.neq + nrow; const int ncon = WI_(ncon);
-  for (int base = 0; base < ncon; base += 32) { int c = base + w.lane; int nr = 0;
-    if (c < ncon) { const idx_t* q = pr + PPAIR_ISTRIDE*S_cpair[c]; const double* P = pd + q[6]*PPAIR_STRIDE; double dist = S_con[c*CON_STRIDE];
-      nr = (dist < P[0]-P[1]) ? (q[2] == 1 ? 1 : 4) : 0; }
-    int incl = nr;   // inclusive warp scan
+  int rowbase = m.neq + nrow; const int ncon = WI_(ncon), na = WI_(na);
+  int* key = (int*)S_conJ;                              // scratch: the Jacobians are written after the last read of the keys
+  for (int c = w.lane; c < ncon; c += 32) key[c] = pr[PPAIR_ISTRIDE*S_cpair[c] + 7];
+  __syncwarp();
+  int nrs[2] = {0, 0}, rank[2] = {0, 0}, rbs[2] = {0, 0};
+  #pragma unroll
+  for (int s = 0; s < 2; s++) { const int c = w.lane + 32*s;
+    if (c < ncon) { const idx_t* q = pr + PPAIR_ISTRIDE*S_cpair[c]; const double* P = pd + q[6]*PPAIR_STRIDE;
+      nrs[s] = (S_con[c*CON_STRIDE] < P[0]-P[1]) ? (q[2] == 1 ? 1 : 4) : 0;
+      const int k = key[c]; int cnt = 0;
+      if (c < na) { for (int q2 = na; q2 < ncon; q2++) cnt += key[q2] < k; rank[s] = c + cnt; }
+      else { for (int q2 = 0; q2 < na; q2++) cnt += key[q2] < k; rank[s] = (c - na) + cnt; }
+      S_crown[rank[s]] = nrs[s]; } }
+  __syncwarp();
+  #pragma unroll
+  for (int s = 0; s < 2; s++) { const int k = w.lane + 32*s; const int v = k < ncon ? S_crown[k] : 0; int incl = v;   // inclusive warp scan in rank order
     #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, incl, o); if (w.lane >= o) incl += t; }
-    int total = __shfl_sync(FULL, incl, 31);
-    if (c < ncon) { S_crow[c] = rowbase + incl - nr; S_cnrow[c] = nr; }
+    if (k < ncon) S_crown[k] = rowbase + incl - v;
+    rowbase += __shfl_sync(FULL, incl, 31); }
+  __syncwarp();
+  #pragma unroll
+  for (int s = 0; s < 2; s++) { const int c = w.lane + 32*s; if (c < ncon) rbs[s] = S_crown[rank[s]]; }
+  __syncwarp();
+  #pragma unroll
+  for (int s = 0; s < 2; s++) { const int c = w.lane + 32*s, nr = nrs[s], rb = rbs[s];
+    if (c < ncon) S_crown[c] = rb | (nr << 12) | (rank[s] << 16);
     if (c < ncon && nr) { const idx_t* q = pr + PPAIR_ISTRIDE*S_cpair[c]; const double* P = pd + q[6]*PPAIR_STRIDE; const double* cd = S_con + c*CON_STRIDE;
       const double* pos = cd + 1; double f[9]; for (int k = 0; k < 6; k++) f[k] = cd[4+k]; cross3(f+6, f, f+3); double* J = S_conJ + c*3*m.maxpath; double vn = 0, v1 = 0, v2 = 0;
-      for (int e = 0; e < q[4]; e++) { int code = path[q[3]+e], d = code >> 1; double sg = (code & 1) ? 1.0 : -1.0, cv[3]; dof_point_vel(m, w, d, pos, cv);
+      unsigned long long mk = 0;
+      for (int e = 0; e < q[4]; e++) { int code = path[q[3]+e], d = code >> 1; double sg = (code & 1) ? 1.0 : -1.0, cv[3]; dof_point_vel(m, w, d, pos, cv); mk |= 1ull << d;
         double jn = sg*dot3(f, cv), j1 = sg*dot3(f+3, cv), j2 = sg*dot3(f+6, cv); J[3*e] = jn; J[3*e+1] = j1; J[3*e+2] = j2;
         double qd = W_(qvel)[d]; vn += jn*qd; v1 += j1*qd; v2 += j2*qd; }
-      double dist = cd[0], inc = P[0]-P[1], imp = impedance(P+7, dist, inc), K = P[5], B = P[6], tran = CD(PPAIR_tran)[S_cpair[c]]; int rb = rowbase + incl - nr;
+      S_cmask[c] = mk;
+      double dist = cd[0], inc = P[0]-P[1], imp = impedance(P+7, dist, inc), K = P[5], B = P[6], tran = CD(PPAIR_tran)[S_cpair[c]];
       if (nr == 1) { double R = fmax(MYO_MINVAL, (1-imp)*tran/imp); S_D[rb] = 1.0/R; S_aref[rb] = -B*vn - K*imp*(dist-inc); }
       else { double mu1 = P[2], mu2 = P[3]; double R0 = fmax(MYO_MINVAL, (1-imp)*(tran+mu1*mu1*tran)/imp), Rpy = 2*mu1*mu1*R0, Dv = 1.0/Rpy, kp = K*imp*(dist-inc);
         S_D[rb] = S_D[rb+1] = S_D[rb+2] = S_D[rb+3] = Dv;
-        S_aref[rb] = -B*(vn+mu1*v1)-kp; S_aref[rb+1] = -B*(vn-mu1*v1)-kp; S_aref[rb+2] = -B*(vn+mu2*v2)-kp; S_aref[rb+3] = -B*(vn-mu2*v2)-kp; } }
-    rowbase += total; }
+        S_aref[rb] = -B*(vn+mu1*v1)-kp; S_aref[rb+1] = -B*(vn-mu1*v1)-kp; S_aref[rb+2] = -B*(vn+mu2*v2)-kp; S_aref[rb+3] = -B*(vn-mu2*v2)-kp; } } }
   WI_(nefc) = rowbase;
   __syncwarp();
 }
@@ -346,7 +378,7 @@ __device__ void phase_solve(const DevModel& m, const Warp w, double tol, long lo
     if (cyc) cyc[14]++;
     // Hessian: tree-sparse L'DL when no contact row is active (limits/equalities keep M's sparsity), dense Cholesky otherwise
     dense = (m.neq > 0 && !m.eq_tree);
-    for (int c = w.lane; c < ncon && !dense; c += 32) { int nr = S_cnrow[c], rb = S_crow[c]; for (int r = 0; r < nr; r++) if (S_jar[rb+r] < 0) dense = true; }
+    for (int c = w.lane; c < ncon && !dense; c += 32) { const int rn = S_crown[c], nr = CNR(rn), rb = CROW(rn); for (int r = 0; r < nr; r++) if (S_jar[rb+r] < 0) dense = true; }
     dense = __any_sync(FULL, dense);
     for (int i = w.lane; i < n; i += 32) S_p[i] = -S_g[i];
     __syncwarp();
@@ -368,18 +400,24 @@ __device__ void phase_solve(const DevModel& m, const Warp w, double tol, long lo
       if (d2 >= 0) { S_H[d1 > d2 ? TRI(d1,d2) : TRI(d2,d1)] += De*j2; S_H[TRI(d2,d2)] += De*j2*j2; } }
     __syncwarp();
     for (int pass = 0; pass < 2; pass++) { for (int r = w.lane; r < nlimrow; r += 32) { int dsc = S_lrow[r]; if (((dsc >> 16) & 1) == pass && S_jar[m.neq+r] < 0) { int d = dsc & 0xffff; S_H[TRI(d,d)] += S_D[m.neq+r]; } } __syncwarp(); }
-    for (int c = 0; c < ncon; c++) { int nr = S_cnrow[c]; if (!nr) continue; int rb = S_crow[c]; const idx_t* q = pr + PPAIR_ISTRIDE*S_cpair[c]; double W[6] = {0,0,0,0,0,0};  // nn n1 n2 11 12 22
-      if (nr == 1) { if (S_jar[rb] < 0) W[0] = S_D[rb]; }
-      else { const double* P = pd + q[6]*PPAIR_STRIDE; double mu1 = P[2], mu2 = P[3], Dv = S_D[rb];
-        double a0 = S_jar[rb] < 0 ? Dv : 0, a1 = S_jar[rb+1] < 0 ? Dv : 0, a2 = S_jar[rb+2] < 0 ? Dv : 0, a3 = S_jar[rb+3] < 0 ? Dv : 0;
-        W[0] = a0+a1+a2+a3; W[1] = mu1*(a0-a1); W[2] = mu2*(a2-a3); W[3] = mu1*mu1*(a0+a1); W[5] = mu2*mu2*(a2+a3); }
-      if (W[0] != 0) { const double* J = S_conJ + c*3*m.maxpath; int np = q[4], ntri = (np*(np+1)) >> 1;
-        // one lane per entry of the lower triangle of J'WJ (the path lists dofs in ascending order, so entry (ei >= ej) lands on H[di >= dj])
-        for (int t = w.lane; t < ntri; t += 32) { int ei = __float2int_rd((sqrtf(8.0f*t + 1.0f) - 1.0f)*0.5f); if (((ei+1)*(ei+2) >> 1) <= t) ei++; if (((ei*(ei+1)) >> 1) > t) ei--;
-          int ej = t - ((ei*(ei+1)) >> 1);
-          const double* a = J + 3*ei; const double* b = J + 3*ej;
-          double wa0 = W[0]*a[0]+W[1]*a[1]+W[2]*a[2], wa1 = W[1]*a[0]+W[3]*a[1]+W[4]*a[2], wa2 = W[2]*a[0]+W[4]*a[1]+W[5]*a[2];
-          int di = path[q[3]+ei] >> 1, dj = path[q[3]+ej] >> 1; S_H[TRI(di,dj)] += wa0*b[0]+wa1*b[1]+wa2*b[2]; } }
+    // contacts: J' W J with W = the active pyramid edges' weights folded into (nn, n1, n2, 11, 22).  Gathered like the gradient: first every
+    // contact's weights (one contact per lane, parked in the jv rows of the contact: jv is free until the line search), then every lane
+    // accumulates the entries of the packed lower triangle it owns over the contacts whose path mask holds both dofs of the entry.
+    for (int c = w.lane; c < ncon; c += 32) { const int rn = S_crown[c], nr = CNR(rn), rb = CROW(rn);
+      if (nr == 1) S_jv[rb] = S_jar[rb] < 0 ? S_D[rb] : 0.0;
+      else if (nr == 4) { const double Dv = S_D[rb]; const double a0 = S_jar[rb] < 0 ? Dv : 0, a1 = S_jar[rb+1] < 0 ? Dv : 0, a2 = S_jar[rb+2] < 0 ? Dv : 0, a3 = S_jar[rb+3] < 0 ? Dv : 0;
+        S_jv[rb] = a0+a1; S_jv[rb+1] = a0-a1; S_jv[rb+2] = a2+a3; S_jv[rb+3] = a2-a3; } }
+    __syncwarp();
+    { const int nt = (n*(n+1)) >> 1;
+      for (int t = w.lane; t < nt; t += 32) { int i, j; tri_index(t, i, j); double acc = 0; const unsigned long long bi = 1ull << i, bj = 1ull << j;
+        for (int c = 0; c < ncon; c++) { const unsigned long long mk = S_cmask[c];
+          if ((mk & bi) && (mk & bj)) { const int rn = S_crown[c], nr = CNR(rn), rb = CROW(rn); if (!nr) continue;
+            const double* a = S_conJ + c*3*m.maxpath + 3*__popcll(mk & (bi - 1)); const double* b = S_conJ + c*3*m.maxpath + 3*__popcll(mk & (bj - 1));
+            if (nr == 1) acc += S_jv[rb]*a[0]*b[0];
+            else { const double* P = pd + pr[PPAIR_ISTRIDE*S_cpair[c] + 6]*PPAIR_STRIDE; const double mu1 = P[2], mu2 = P[3], s01 = S_jv[rb], d01 = S_jv[rb+1], s23 = S_jv[rb+2], d23 = S_jv[rb+3];
+              const double W0 = s01+s23, W1 = mu1*d01, W2 = mu2*d23, W3 = mu1*mu1*s01, W5 = mu2*mu2*s23;
+              acc += (W0*a[0]+W1*a[1]+W2*a[2])*b[0] + (W1*a[0]+W3*a[1])*b[1] + (W2*a[0]+W5*a[2])*b[2]; } } }
+        if (acc != 0) S_H[t] += acc; }
       __syncwarp(); }
     LAP(9)
     } }

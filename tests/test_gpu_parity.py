@@ -409,9 +409,8 @@ def test_mid_episode_forward_and_rollout_parity(eid, warm):
         o = oracles[e]; o.reset(); o.set(qpos=qpos[e], qvel=qvel[e], act=act[e, :m.na], ctrl=ctrl[e]); o.forward()
         if not alive[e]:
             continue
-        if not _in_regime(o, m):          # deep finger-pad overlap: reported, not asserted (see test_regime_and_overflow_rate_on_rollouts)
+        if not _in_regime(o, m):          # deep finger-pad overlap (6 % of env-steps of a random-action rollout, see the regime test): checked like every other env
             deep_n += 1; deep_ok += relerr(t["tap_qacc"][e], o.f("qacc")) < 1e-6
-            continue
         checked += 1
         worst = max(worst, relerr(t["tap_qacc"][e], o.f("qacc")))
         assert relerr(t["tap_qacc"][e], o.f("qacc")) < 1e-6          # (stiff object / finger contacts; north star: 1e-5)
@@ -423,7 +422,7 @@ def test_mid_episode_forward_and_rollout_parity(eid, warm):
         np.testing.assert_allclose(t["tap_contact_dist"][e][:nc], [d for p, d in zip(o.i("con_pair"), o.f("con_dist")) if int(p) in set(pmi)], rtol=1e-7, atol=1e-11)
         ncon_total += nc
     print("%s after %d steps: %d/%d envs checked, %d contacts, worst qacc deviation %.2e; deep-overlap envs: %d, of which %d agree to 1e-6" % (eid, warm, checked, n, ncon_total, worst, deep_n, deep_ok))
-    assert checked + deep_n == int(alive.sum()) and checked >= max(1, int(0.8 * alive.sum()))
+    assert checked == int(alive.sum()) and checked >= n // 4 and deep_ok == deep_n          # EVERY live env is checked: states the simulator reaches are inside the parity claim
     assert ncon_total > 0
     if env.task == "hold":      # the object really is in contact with the hand in this batch
         obj = m.name2id("geom", "object")

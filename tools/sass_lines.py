@@ -2,7 +2,7 @@
    python tools/sass_lines.py KERNEL OPCODE_REGEX [--lines]"""
 import collections, re, subprocess, sys, os, tempfile
 root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
-lib = os.path.join(root, "myosuite_b200", "libmyo_b200.so")
+lib = os.environ.get("SASS_LIB") or os.path.join(root, "myosuite_b200", "libmyo_b200.so")
 kernel, opre = sys.argv[1], re.compile(sys.argv[2]); by_line = "--lines" in sys.argv
 tmp = tempfile.mkdtemp(); subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, capture_output=True)
 cub = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
