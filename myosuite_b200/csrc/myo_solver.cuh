@@ -400,24 +400,18 @@ __device__ void phase_solve(const DevModel& m, const Warp w, double tol, long lo
       if (d2 >= 0) { S_H[d1 > d2 ? TRI(d1,d2) : TRI(d2,d1)] += De*j2; S_H[TRI(d2,d2)] += De*j2*j2; } }
     __syncwarp();
     for (int pass = 0; pass < 2; pass++) { for (int r = w.lane; r < nlimrow; r += 32) { int dsc = S_lrow[r]; if (((dsc >> 16) & 1) == pass && S_jar[m.neq+r] < 0) { int d = dsc & 0xffff; S_H[TRI(d,d)] += S_D[m.neq+r]; } } __syncwarp(); }
-    // contacts: J' W J with W = the active pyramid edges' weights folded into (nn, n1, n2, 11, 22).  Gathered like the gradient: first every
-    // contact's weights (one contact per lane, parked in the jv rows of the contact: jv is free until the line search), then every lane
-    // accumulates the entries of the packed lower triangle it owns over the contacts whose path mask holds both dofs of the entry.
-    for (int c = w.lane; c < ncon; c += 32) { const int rn = S_crown[c], nr = CNR(rn), rb = CROW(rn);
-      if (nr == 1) S_jv[rb] = S_jar[rb] < 0 ? S_D[rb] : 0.0;
-      else if (nr == 4) { const double Dv = S_D[rb]; const double a0 = S_jar[rb] < 0 ? Dv : 0, a1 = S_jar[rb+1] < 0 ? Dv : 0, a2 = S_jar[rb+2] < 0 ? Dv : 0, a3 = S_jar[rb+3] < 0 ? Dv : 0;
-        S_jv[rb] = a0+a1; S_jv[rb+1] = a0-a1; S_jv[rb+2] = a2+a3; S_jv[rb+3] = a2-a3; } }
-    __syncwarp();
-    { const int nt = (n*(n+1)) >> 1;
-      for (int t = w.lane; t < nt; t += 32) { int i, j; tri_index(t, i, j); double acc = 0; const unsigned long long bi = 1ull << i, bj = 1ull << j;
-        for (int c = 0; c < ncon; c++) { const unsigned long long mk = S_cmask[c];
-          if ((mk & bi) && (mk & bj)) { const int rn = S_crown[c], nr = CNR(rn), rb = CROW(rn); if (!nr) continue;
-            const double* a = S_conJ + c*3*m.maxpath + 3*__popcll(mk & (bi - 1)); const double* b = S_conJ + c*3*m.maxpath + 3*__popcll(mk & (bj - 1));
-            if (nr == 1) acc += S_jv[rb]*a[0]*b[0];
-            else { const double* P = pd + pr[PPAIR_ISTRIDE*S_cpair[c] + 6]*PPAIR_STRIDE; const double mu1 = P[2], mu2 = P[3], s01 = S_jv[rb], d01 = S_jv[rb+1], s23 = S_jv[rb+2], d23 = S_jv[rb+3];
-              const double W0 = s01+s23, W1 = mu1*d01, W2 = mu2*d23, W3 = mu1*mu1*s01, W5 = mu2*mu2*s23;
-              acc += (W0*a[0]+W1*a[1]+W2*a[2])*b[0] + (W1*a[0]+W3*a[1])*b[1] + (W2*a[0]+W5*a[2])*b[2]; } } }
-        if (acc != 0) S_H[t] += acc; }
+    // contacts: J' W J, one contact at a time, one lane per entry of the lower triangle of its block (the gather form that pays for the
+    // gradient does not pay here: with one H entry per lane nearly every contact hits SOME lane and the warp runs the hit path 9 x ncon times)
+    for (int c = 0; c < ncon; c++) { const int rn = S_crown[c], nr = CNR(rn), rb = CROW(rn); if (!nr) continue; const idx_t* q = pr + PPAIR_ISTRIDE*S_cpair[c]; double W[6] = {0,0,0,0,0,0};  // nn n1 n2 11 12 22
+      if (nr == 1) { if (S_jar[rb] < 0) W[0] = S_D[rb]; }
+      else { const double* P = pd + q[6]*PPAIR_STRIDE; double mu1 = P[2], mu2 = P[3], Dv = S_D[rb];
+        double a0 = S_jar[rb] < 0 ? Dv : 0, a1 = S_jar[rb+1] < 0 ? Dv : 0, a2 = S_jar[rb+2] < 0 ? Dv : 0, a3 = S_jar[rb+3] < 0 ? Dv : 0;
+        W[0] = a0+a1+a2+a3; W[1] = mu1*(a0-a1); W[2] = mu2*(a2-a3); W[3] = mu1*mu1*(a0+a1); W[5] = mu2*mu2*(a2+a3); }
+      if (W[0] != 0) { const double* J = S_conJ + c*3*m.maxpath; int np = q[4], ntri = (np*(np+1)) >> 1;
+        for (int t = w.lane; t < ntri; t += 32) { int ei, ej; tri_index(t, ei, ej);
+          const double* a = J + 3*ei; const double* b = J + 3*ej;
+          double wa0 = W[0]*a[0]+W[1]*a[1]+W[2]*a[2], wa1 = W[1]*a[0]+W[3]*a[1], wa2 = W[2]*a[0]+W[5]*a[2];
+          int di = path[q[3]+ei] >> 1, dj = path[q[3]+ej] >> 1; S_H[TRI(di,dj)] += wa0*b[0]+wa1*b[1]+wa2*b[2]; } }
       __syncwarp(); }
     LAP(9)
     } }
