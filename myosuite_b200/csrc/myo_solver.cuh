@@ -73,6 +73,16 @@ __device__ void rows_applyT_add(const DevModel& m, const Warp w, double* wgt, do
   for (int pass = 0; pass < 2; pass++) {
     for (int r = w.lane; r < nlimrow; r += 32) { int dsc = S_lrow[r]; int neg = (dsc >> 16) & 1; if (neg == pass) vec[dsc & 0xffff] += (neg ? -1.0 : 1.0)*wgt[m.neq + r]; }
     __syncwarp(); }
+#ifdef MYO_OLD_GRAD
+  { const idx_t* pr = CI(PPAIR); const double* pd = CD(PPAIR_d); const idx_t* path = CI(PPATH);
+  for (int c = 0; c < ncon; c++) { const int rn = S_crown[c], nr = CNR(rn); if (!nr) continue;
+    const idx_t* q = pr + PPAIR_ISTRIDE*S_cpair[c]; const double* J = S_conJ + c*3*m.maxpath; int rb = CROW(rn); double wn, w1 = 0, w2 = 0;
+    if (nr == 1) wn = wgt[rb];
+    else { const double* P = pd + q[6]*PPAIR_STRIDE; wn = wgt[rb]+wgt[rb+1]+wgt[rb+2]+wgt[rb+3]; w1 = P[2]*(wgt[rb]-wgt[rb+1]); w2 = P[3]*(wgt[rb+2]-wgt[rb+3]); }
+    for (int e = w.lane; e < q[4]; e += 32) vec[path[q[3]+e] >> 1] += J[3*e]*wn + J[3*e+1]*w1 + J[3*e+2]*w2;
+    __syncwarp(); } }
+}
+#else
   const idx_t* pr = CI(PPAIR); const double* pd = CD(PPAIR_d);
   for (int c = w.lane; c < ncon; c += 32) { const int rn = S_crown[c], nr = CNR(rn), rb = CROW(rn);      // fold the pyramid edges: (wn, w1, w2) into wgt[rb .. rb+2]
     if (nr == 4) { const double* P = pd + pr[PPAIR_ISTRIDE*S_cpair[c] + 6]*PPAIR_STRIDE; const double a0 = wgt[rb], a1 = wgt[rb+1], a2 = wgt[rb+2], a3 = wgt[rb+3];
@@ -85,6 +95,7 @@ __device__ void rows_applyT_add(const DevModel& m, const Warp w, double* wgt, do
     vec[d] += acc; }
   __syncwarp();
 }
+#endif
 
 // ------------------------------------------------------------------ constraint assembly
 __device__ void phase_constraints(const DevModel& m, const Warp w) {
@@ -123,9 +134,13 @@ __device__ void phase_constraints(const DevModel& m, const Warp w) {
   for (int s = 0; s < 2; s++) { const int c = w.lane + 32*s;
     if (c < ncon) { const idx_t* q = pr + PPAIR_ISTRIDE*S_cpair[c]; const double* P = pd + q[6]*PPAIR_STRIDE;
       nrs[s] = (S_con[c*CON_STRIDE] < P[0]-P[1]) ? (q[2] == 1 ? 1 : 4) : 0;
+#ifdef MYO_NO_RANK
+      rank[s] = c;
+#else
       const int k = key[c]; int cnt = 0;
       if (c < na) { for (int q2 = na; q2 < ncon; q2++) cnt += key[q2] < k; rank[s] = c + cnt; }
       else { for (int q2 = 0; q2 < na; q2++) cnt += key[q2] < k; rank[s] = (c - na) + cnt; }
+#endif
       S_crown[rank[s]] = nrs[s]; } }
   __syncwarp();
   #pragma unroll
