@@ -423,13 +423,15 @@ static void fill_devmodel(const myo_model* mm, const myo_task_cfg* cfg, DevModel
   t = 0; d.s_cin = t; t += al2(10*d.nbd); d.s_crb = t; t += al2(10*d.nbd); d.s_bf = t; t += al2(6*d.nbd); int sizeC = t;
   // the list of ellipsoid candidates that survive the cull shares the contact-Jacobian region (ints; it holds every iterative pair)
   d.kcand = d.npair - d.npair_an; int candsz = al2((d.kcand + 1)/2);
-  t = 0; d.s_conJ = t; d.s_clist = t; t += imax(al2(3*d.maxpath*mc), candsz); d.s_efD = t; t += al2(d.maxefc); d.s_efA = t; t += al2(d.maxefc); d.s_eqJ = t; t += al2(d.neq);
+  t = 0; d.s_conJ = t; d.s_clist = t; t += imax(al2(3*d.maxpath*mc), candsz); d.s_efD = t; t += al2(d.maxefc); const int hsize = imax(al2(d.nvp*(d.nvp+1)/2), 2*al2(d.nM) + al2(d.nv)); const bool arefInH = al2(d.maxefc) <= hsize;
+  d.s_efA = t; if (!arefInH) t += al2(d.maxefc);      /* aref (constraints -> start of the solve) lives in the Hessian region when it fits: H is first written after its last read */
+  d.s_eqJ = t; t += al2(d.neq);
   d.ngc = P[PD_NGC]; d.s_gpose = d.s_efD; if (t - d.s_efD < al2(6*d.ngc)) t = d.s_efD + al2(6*d.ngc);     // geom poses (collision only) alias the row arrays (written after it)
   d.s_icon = t; t += al2((4*mc + d.nlimrow + 4 + 1)/2); int sizeS3 = t;      // path masks (2 ints per contact), pair, row|nrow, limit rows
   d.s_con = sizeS3; int sizeCon = al2(CON_STRIDE*mc);
   t = sizeS3; d.s_efR = t; t += al2(d.maxefc); d.s_efV = t; t += al2(d.maxefc); d.s_va = t; t += al2(d.nvp); d.s_vg = t; t += al2(d.nvp); d.s_vp = t; t += al2(d.nvp);
   d.s_vMa = t; t += al2(d.nvp); d.s_vMp = t; t += al2(d.nvp);
-  d.s_H = t; d.s_Hs = t; d.s_LD = t + al2(d.nM); d.s_Dinv = t + 2*al2(d.nM); t += imax(al2(d.nvp*(d.nvp+1)/2), 2*al2(d.nM) + al2(d.nv)); int sizeS4 = t;
+  d.s_H = t; d.s_Hs = t; d.s_LD = t + al2(d.nM); d.s_Dinv = t + 2*al2(d.nM); if (arefInH) d.s_efA = t; t += hsize; int sizeS4 = t;
   int scratch = imax(imax(sizeT, sizeC) + K, imax(sizeS3 + sizeCon + K, sizeS4));
   d.s_xpos = scratch - K; d.s_xmat = d.s_xpos + al2(3*d.nbd);
   // scratch offsets are used relative to the warp base

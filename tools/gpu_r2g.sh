@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-B="python bench.py --steps 60 --warmup 5 --no-cpu-baseline --no-extra"
-echo "=== default product"; timeout 100 $B 2>&1 | tail -1 | cut -c1-130
-echo "=== default dbg kernel"; MYO_B200_DEBUG_KERNEL=1 timeout 100 $B 2>&1 | tail -1 | cut -c1-130
-for v in oldgrad norank oldgrad_norank; do echo "=== $v"; MYO_B200_LIB=$PWD/myosuite_b200/libmyo_b200_$v.so timeout 100 $B 2>&1 | tail -1 | cut -c1-130;
-  echo "=== $v dbg"; MYO_B200_DEBUG_KERNEL=1 MYO_B200_LIB=$PWD/myosuite_b200/libmyo_b200_$v.so timeout 100 $B 2>&1 | tail -1 | cut -c1-130; done
+echo "=== pytest -m gpu (all)"; timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; tail -4 gpurun_out/pytest_gpu.log | cut -c1-300
+echo "=== bench hand"; timeout 200 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --no-extra | tee gpurun_out/r2g_bench_hand.json | cut -c1-200
+echo "=== 10-warp phase cycles"; STEPS=30 timeout 200 python tools/gpu_phase_profile.py 2>&1 | sed -n 2,4p | cut -c1-700
+echo "=== 10-warp phase waits"; WAITS=1 STEPS=30 timeout 200 python tools/gpu_phase_profile.py 2>&1 | sed -n 2,3p | cut -c1-700
