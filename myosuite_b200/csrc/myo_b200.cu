@@ -412,13 +412,13 @@ static void fill_devmodel(const myo_model* mm, const myo_task_cfg* cfg, DevModel
   #undef TAKE
   // ---- scratch, time-multiplexed.  Lifetimes:
   //   K  (xpos,xmat)                       kinematics .. constraints           -> parked at the END of the scratch
-  //   T  (U,WP,PL,mom,tlen,tvel,tfrc)      tendon .. actuation                 -> from 0
+  //   T  (U,PL,mom,tlen,tvel,tfrc)         tendon .. actuation                 -> from 0
   //   C  (cin,crb,bf)                      body inertia .. bias                -> from 0
   //   S3 (conJ,D,aref,eqJ,icon)            collision/constraints .. solve      -> from 0   (T and C are dead by then)
   //   con                                  collision .. constraints            -> right after S3 (overwritten by the solve vectors)
   //   S4 (jar,jv,a,g,p,Ma,Mp,H|Hs,LD,Dinv) solve .. integrate                  -> right after S3 (may overwrite con and K)
   int K = al2(3*d.nbd) + al2(9*d.nbd);
-  int t = 0; d.s_U = t; t += al2(3*(d.nsp+2*d.nwe)); d.s_WP = t; t += al2(6*d.nwe); d.s_PL = t; t += al2(d.nsp+d.nwe); d.s_mom = t; t += al2(d.nnz);
+  int t = 0; d.s_U = t; t += al2(3*(d.nsp+2*d.nwe)); d.s_PL = t; t += al2(d.nsp+d.nwe); d.s_mom = t; t += al2(d.nnz);
   d.s_tlen = t; t += al2(d.nta); d.s_tvel = t; t += al2(d.nta); d.s_tfrc = t; t += al2(d.nta); int sizeT = t;
   t = 0; d.s_cin = t; t += al2(10*d.nbd); d.s_crb = t; t += al2(10*d.nbd); d.s_bf = t; t += al2(6*d.nbd); int sizeC = t;
   // the list of ellipsoid candidates that survive the cull shares the contact-Jacobian region (ints; it holds every iterative pair)
@@ -435,7 +435,7 @@ static void fill_devmodel(const myo_model* mm, const myo_task_cfg* cfg, DevModel
   int scratch = imax(imax(sizeT, sizeC) + K, imax(sizeS3 + sizeCon + K, sizeS4));
   d.s_xpos = scratch - K; d.s_xmat = d.s_xpos + al2(3*d.nbd);
   // scratch offsets are used relative to the warp base
-  { int32_t* f[] = {&d.s_xpos, &d.s_xmat, &d.s_U, &d.s_WP, &d.s_PL, &d.s_mom, &d.s_tlen, &d.s_tvel, &d.s_tfrc, &d.s_cin, &d.s_crb, &d.s_bf, &d.s_conJ, &d.s_efD, &d.s_efA, &d.s_eqJ,
+  { int32_t* f[] = {&d.s_xpos, &d.s_xmat, &d.s_U, &d.s_PL, &d.s_mom, &d.s_tlen, &d.s_tvel, &d.s_tfrc, &d.s_cin, &d.s_crb, &d.s_bf, &d.s_conJ, &d.s_efD, &d.s_efA, &d.s_eqJ,
                     &d.s_icon, &d.s_con, &d.s_clist, &d.s_gpose, &d.s_efR, &d.s_efV, &d.s_va, &d.s_vg, &d.s_vp, &d.s_vMa, &d.s_vMp, &d.s_H, &d.s_Hs, &d.s_LD, &d.s_Dinv};
     for (int32_t* q : f) *q += d.o_scr; }
   d.n_per_warp = d.o_scr + scratch;

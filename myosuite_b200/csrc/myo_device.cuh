@@ -46,7 +46,7 @@ struct DevModel {
   int32_t o_qpos, o_qvel, o_act, o_ctrl, o_qws, o_dax, o_dan, o_qM, o_fsm, o_eprm, neprm, o_wz, nwz, o_cnt, o_scr, n_per_warp;
   // scratch (time-multiplexed by stage; offsets relative to the warp base, i.e. o_scr included).  See fill_devmodel() for the overlap rules.
   int32_t s_xpos, s_xmat;                                  // K: body poses, alive kinematics .. constraints
-  int32_t s_U, s_WP, s_PL, s_mom, s_tlen, s_tvel, s_tfrc;  // stage 1: tendons + actuation
+  int32_t s_U, s_PL, s_mom, s_tlen, s_tvel, s_tfrc;  // stage 1: tendons + actuation
   int32_t s_cin, s_crb, s_bf;                              // stage 2: CRB / bias
   int32_t s_conJ, s_efD, s_efA, s_eqJ, s_icon, s_con;      // stage 3 -> 4: contacts / constraint rows
   int32_t s_clist, kcand;                                  // collision only: list of the expensive (ellipsoid) candidates that survived the cull
@@ -97,6 +97,15 @@ __device__ __forceinline__ double warp_sum(double v) {
   #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v; }
+
+// Reciprocal and square root without libdevice's IEEE special-case paths: MUFU seed (~20 bits) + two Newton steps, 1-2 ulp.  Measured on the
+// B200 (profiles/r02_ubench_latencies.txt): a dependent f64 division costs 141 cycles, a DFMA 10 -- these run in ~65 / ~90.  Arguments
+// must be normal numbers; m_sqrt(0) = 0.  (acos costs 645 cycles against asin's 337: the wrap arc uses pi/2 - asin.)
+__device__ __forceinline__ double m_rcp(double x) { double y; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x)); double e = fma(-x, y, 1.0); y = fma(y, e, y); e = fma(-x, y, 1.0); return fma(y, e, y); }
+__device__ __forceinline__ double m_sqrt(double x) { double y; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double h = 0.5*x; double t = fma(-h*y, y, 0.5); y = fma(y, t, y); t = fma(-h*y, y, 0.5); y = fma(y, t, y);
+  double s = x*y; s = fma(fma(-s, s, x), 0.5*y, s); return x > 1e-300 ? s : 0.0; }
+#define FDIV(a, b) ((a)*m_rcp(b))
 
 // world position of program point `pt`
 __device__ __forceinline__ void world_point(const DevModel& m, const Warp w, int pt, double* out) {
@@ -193,8 +202,9 @@ __device__ void phase_body_inertia(const DevModel& m, const Warp w) {
 __device__ __forceinline__ bool seg_intersect(const double* p1, const double* p2, const double* p3, const double* p4) {
   double det = (p4[1]-p3[1])*(p2[0]-p1[0]) - (p4[0]-p3[0])*(p2[1]-p1[1]);
   if (fabs(det) < MYO_MINVAL) return false;
-  double a = ((p4[0]-p3[0])*(p1[1]-p3[1]) - (p4[1]-p3[1])*(p1[0]-p3[0]))/det;
-  double b = ((p2[0]-p1[0])*(p1[1]-p3[1]) - (p2[1]-p1[1])*(p1[0]-p3[0]))/det;
+  const double id = m_rcp(det);
+  double a = ((p4[0]-p3[0])*(p1[1]-p3[1]) - (p4[1]-p3[1])*(p1[0]-p3[0]))*id;
+  double b = ((p2[0]-p1[0])*(p1[1]-p3[1]) - (p2[1]-p1[1])*(p1[0]-p3[0]))*id;
   return a >= 0 && a <= 1 && b >= 0 && b <= 1; }
 
 // 2-D tangent wrap of the path d0 -> circle(rad) -> d1 on the outside; returns arc length or -1 (no wrap)
@@ -202,22 +212,22 @@ __device__ __forceinline__ double wrap2d_outside(double* pnt, const double* d, c
   double sq0 = d[0]*d[0]+d[1]*d[1], sq1 = d[2]*d[2]+d[3]*d[3], sqr = rad*rad;
   double dif0 = d[2]-d[0], dif1 = d[3]-d[1], dd = dif0*dif0+dif1*dif1;
   if (sq0 < sqr || sq1 < sqr || rad < MYO_MINVAL || dd < MYO_MINVAL) return -1;
-  double a = clipd(-(dif0*d[0]+dif1*d[1])/dd, 0, 1);
+  double a = clipd(-(dif0*d[0]+dif1*d[1])*m_rcp(dd), 0, 1);
   double t0 = a*dif0+d[0], t1 = a*dif1+d[1];
   if (t0*t0+t1*t1 > sqr && (!has_side || t0*sd[0]+t1*sd[1] >= 0)) return -1;
-  double s0 = sqrt(sq0-sqr), s1 = sqrt(sq1-sqr), sol[2][4], good[2], i0 = 1.0/sq0, i1 = 1.0/sq1;
+  double s0 = m_sqrt(sq0-sqr), s1 = m_sqrt(sq1-sqr), sol[2][4], good[2], i0 = m_rcp(sq0), i1 = m_rcp(sq1);
   #pragma unroll
   for (int i = 0; i < 2; i++) { double sg = i==0 ? 1.0 : -1.0;
     sol[i][0] = (d[0]*sqr + sg*rad*d[1]*s0)*i0; sol[i][1] = (d[1]*sqr - sg*rad*d[0]*s0)*i0;
     sol[i][2] = (d[2]*sqr - sg*rad*d[3]*s1)*i1; sol[i][3] = (d[3]*sqr + sg*rad*d[2]*s1)*i1;
-    if (has_side) { double x = sol[i][0]+sol[i][2], y = sol[i][1]+sol[i][3], n = sqrt(x*x+y*y);
-      if (n < MYO_MINVAL) { x = 1; y = 0; } else { x /= n; y /= n; } good[i] = x*sd[0]+y*sd[1]; }
+    if (has_side) { double x = sol[i][0]+sol[i][2], y = sol[i][1]+sol[i][3], n = m_sqrt(x*x+y*y);
+      if (n < MYO_MINVAL) { x = 1; y = 0; } else { const double q = m_rcp(n); x *= q; y *= q; } good[i] = x*sd[0]+y*sd[1]; }
     else { double x = sol[i][0]-sol[i][2], y = sol[i][1]-sol[i][3]; good[i] = -(x*x+y*y); }
     if (seg_intersect(d, sol[i], d+2, sol[i]+2)) good[i] = -10000; }
   int i = good[0] > good[1] ? 0 : 1;
   pnt[0]=sol[i][0]; pnt[1]=sol[i][1]; pnt[2]=sol[i][2]; pnt[3]=sol[i][3];
   if (seg_intersect(d, pnt, d+2, pnt+2)) return -1;
-  return rad*acos(clipd((pnt[0]*pnt[2]+pnt[1]*pnt[3])/sqr, -1, 1)); }
+  return rad*(1.5707963267948966 - asin(clipd((pnt[0]*pnt[2]+pnt[1]*pnt[3])*m_rcp(sqr), -1, 1))); }
 
 // inverse wrap: the path must pass through the inside of the circle (touches it in one point); returns 0 or -1
 __device__ __forceinline__ double wrap2d_inside(double* pnt, const double* d, double rad, double* zwarm) {
@@ -258,7 +268,7 @@ __device__ __forceinline__ double wrap2d_inside(double* pnt, const double* d, do
   pnt[0] = rad*(c*vx - s*vy); pnt[1] = rad*(s*vx + c*vy); pnt[2] = pnt[0]; pnt[3] = pnt[1];
   return 0; }
 
-__device__ void wrap_element(const DevModel& m, const Warp w, int k, double* U, double* WP, double* PL) {
+__device__ void wrap_element(const DevModel& m, const Warp w, int k, double* U, double* PL) {
   const idx_t* we = CI(PWE) + 6*k; const double* wd = CD(PWE_d) + k*PWE_STRIDE;
   double x0[3], x1[3]; world_point(m, w, we[0], x0); world_point(m, w, we[1], x1);
   int gb = we[2]; bool cyl = we[3] == 1, has_side = we[4] >= 0, inside = we[5] != 0; double rad = wd[12];
@@ -269,59 +279,59 @@ __device__ void wrap_element(const DevModel& m, const Warp w, int k, double* U, 
   t[0]=x0[0]-gpos[0]; t[1]=x0[1]-gpos[1]; t[2]=x0[2]-gpos[2]; matT_vec(p0, gmat, t);
   t[0]=x1[0]-gpos[0]; t[1]=x1[1]-gpos[1]; t[2]=x1[2]-gpos[2]; matT_vec(p1, gmat, t);
   double wlen = -1, pnt[4], ax0[3] = {1,0,0}, ax1[3] = {0,1,0};
-  if (sqrt(dot3(p0,p0)) >= MYO_MINVAL && sqrt(dot3(p1,p1)) >= MYO_MINVAL) {
+  if (dot3(p0,p0) >= MYO_MINVAL*MYO_MINVAL && dot3(p1,p1) >= MYO_MINVAL*MYO_MINVAL) {
     if (!cyl) {   // plane through p0, p1 and the sphere centre
-      double n0 = sqrt(dot3(p0,p0)); ax0[0]=p0[0]/n0; ax0[1]=p0[1]/n0; ax0[2]=p0[2]/n0;
-      double nrm[3]; cross3(nrm, p0, p1); double nn = sqrt(dot3(nrm,nrm));
+      double n0 = m_rcp(m_sqrt(dot3(p0,p0))); ax0[0]=p0[0]*n0; ax0[1]=p0[1]*n0; ax0[2]=p0[2]*n0;
+      double nrm[3]; cross3(nrm, p0, p1); double nn = m_sqrt(dot3(nrm,nrm));
       if (nn < MYO_MINVAL) { int i = 0; if (fabs(ax0[1]) > fabs(ax0[i])) i = 1; if (fabs(ax0[2]) > fabs(ax0[i])) i = 2;
-        double o[3] = {i == 0 ? 0.0 : 1.0, i == 1 ? 0.0 : 1.0, i == 2 ? 0.0 : 1.0}; cross3(nrm, ax0, o); nn = sqrt(dot3(nrm,nrm)); }
-      nrm[0]/=nn; nrm[1]/=nn; nrm[2]/=nn; cross3(ax1, nrm, ax0); double n1 = sqrt(dot3(ax1,ax1)); ax1[0]/=n1; ax1[1]/=n1; ax1[2]/=n1; }
+        double o[3] = {i == 0 ? 0.0 : 1.0, i == 1 ? 0.0 : 1.0, i == 2 ? 0.0 : 1.0}; cross3(nrm, ax0, o); nn = m_sqrt(dot3(nrm,nrm)); }
+      { const double q = m_rcp(nn); nrm[0]*=q; nrm[1]*=q; nrm[2]*=q; } cross3(ax1, nrm, ax0); { const double q = m_rcp(m_sqrt(dot3(ax1,ax1))); ax1[0]*=q; ax1[1]*=q; ax1[2]*=q; } }
     double d[4] = {dot3(p0,ax0), dot3(p0,ax1), dot3(p1,ax0), dot3(p1,ax1)}, sd[2] = {0,0};
-    if (has_side) { const double* s = wd + 13; sd[0] = dot3(s,ax0); sd[1] = dot3(s,ax1); double n = sqrt(sd[0]*sd[0]+sd[1]*sd[1]);
-      if (n < MYO_MINVAL) { sd[0] = rad; sd[1] = 0; } else { sd[0] *= rad/n; sd[1] *= rad/n; } }
+    if (has_side) { const double* s = wd + 13; sd[0] = dot3(s,ax0); sd[1] = dot3(s,ax1); double n = m_sqrt(sd[0]*sd[0]+sd[1]*sd[1]);
+      if (n < MYO_MINVAL) { sd[0] = rad; sd[1] = 0; } else { const double q = rad*m_rcp(n); sd[0] *= q; sd[1] *= q; } }
     wlen = inside ? wrap2d_inside(pnt, d, rad, W_(wz) + k) : wrap2d_outside(pnt, d, sd, has_side, rad);
   }
-  double* u0 = U + 3*(m.nsp + 2*k); double* u1 = u0 + 3; double* w0 = WP + 6*k; double* w1 = w0 + 3;
+  double* u0 = U + 3*(m.nsp + 2*k); double* u1 = u0 + 3; double w0[3], w1[3];      // tangent points: only the two straight pieces' directions and the path length leave this function
   if (wlen < 0) {   // straight segment: both "wrap points" sit at x1 (on the line), same direction for both pieces
-    double dv[3] = {x1[0]-x0[0], x1[1]-x0[1], x1[2]-x0[2]}, n = sqrt(dot3(dv,dv));
-    if (n < MYO_MINVAL) { dv[0]=1; dv[1]=0; dv[2]=0; } else { dv[0]/=n; dv[1]/=n; dv[2]/=n; }
-    for (int c = 0; c < 3; c++) { u0[c]=dv[c]; u1[c]=dv[c]; w0[c]=x1[c]; w1[c]=x1[c]; }
+    double dv[3] = {x1[0]-x0[0], x1[1]-x0[1], x1[2]-x0[2]}, n = m_sqrt(dot3(dv,dv));
+    if (n < MYO_MINVAL) { dv[0]=1; dv[1]=0; dv[2]=0; } else { const double q = m_rcp(n); dv[0]*=q; dv[1]*=q; dv[2]*=q; }
+    for (int c = 0; c < 3; c++) { u0[c]=dv[c]; u1[c]=dv[c]; }
     PL[m.nsp + k] = n; return; }
   double r0[3], r1[3];
   for (int c = 0; c < 3; c++) { r0[c] = ax0[c]*pnt[0]+ax1[c]*pnt[1]; r1[c] = ax0[c]*pnt[2]+ax1[c]*pnt[3]; }
-  if (cyl) { double L0 = sqrt((p0[0]-pnt[0])*(p0[0]-pnt[0])+(p0[1]-pnt[1])*(p0[1]-pnt[1])), L1 = sqrt((p1[0]-pnt[2])*(p1[0]-pnt[2])+(p1[1]-pnt[3])*(p1[1]-pnt[3]));
-    double inv = 1.0/(L0+wlen+L1);
+  if (cyl) { double L0 = m_sqrt((p0[0]-pnt[0])*(p0[0]-pnt[0])+(p0[1]-pnt[1])*(p0[1]-pnt[1])), L1 = m_sqrt((p1[0]-pnt[2])*(p1[0]-pnt[2])+(p1[1]-pnt[3])*(p1[1]-pnt[3]));
+    double inv = m_rcp(L0+wlen+L1);
     r0[2] = p0[2]+(p1[2]-p0[2])*L0*inv; r1[2] = p0[2]+(p1[2]-p0[2])*(L0+wlen)*inv;
-    double h = fabs(r1[2]-r0[2]); wlen = sqrt(wlen*wlen+h*h); }
+    double h = fabs(r1[2]-r0[2]); wlen = m_sqrt(wlen*wlen+h*h); }
   mat_vec(w0, gmat, r0); mat_vec(w1, gmat, r1);
   for (int c = 0; c < 3; c++) { w0[c]+=gpos[c]; w1[c]+=gpos[c]; }
   double a[3] = {w0[0]-x0[0], w0[1]-x0[1], w0[2]-x0[2]}, b[3] = {x1[0]-w1[0], x1[1]-w1[1], x1[2]-w1[2]};
-  double na = sqrt(dot3(a,a)), nb = sqrt(dot3(b,b));
-  if (na < MYO_MINVAL) { u0[0]=1; u0[1]=0; u0[2]=0; } else { double q = 1.0/na; u0[0]=a[0]*q; u0[1]=a[1]*q; u0[2]=a[2]*q; }
-  if (nb < MYO_MINVAL) { u1[0]=1; u1[1]=0; u1[2]=0; } else { double q = 1.0/nb; u1[0]=b[0]*q; u1[1]=b[1]*q; u1[2]=b[2]*q; }
+  double na = m_sqrt(dot3(a,a)), nb = m_sqrt(dot3(b,b));
+  if (na < MYO_MINVAL) { u0[0]=1; u0[1]=0; u0[2]=0; } else { double q = m_rcp(na); u0[0]=a[0]*q; u0[1]=a[1]*q; u0[2]=a[2]*q; }
+  if (nb < MYO_MINVAL) { u1[0]=1; u1[1]=0; u1[2]=0; } else { double q = m_rcp(nb); u1[0]=b[0]*q; u1[1]=b[1]*q; u1[2]=b[2]*q; }
   PL[m.nsp + k] = na + wlen + nb;
 }
 
 __device__ void phase_tendon(const DevModel& m, const Warp w) {
-  double* U = SCR(s_U); double* WP = SCR(s_WP); double* PL = SCR(s_PL);
+  double* U = SCR(s_U); double* PL = SCR(s_PL);
   const idx_t* sp = CI(PSP);
   for (int k = w.lane; k < m.nsp; k += 32) { double a[3], b[3]; world_point(m, w, sp[2*k], a); world_point(m, w, sp[2*k+1], b);
-    double dv[3] = {b[0]-a[0], b[1]-a[1], b[2]-a[2]}, n = sqrt(dot3(dv,dv));
-    if (n < MYO_MINVAL) { U[3*k]=1; U[3*k+1]=0; U[3*k+2]=0; } else { double q = 1.0/n; U[3*k]=dv[0]*q; U[3*k+1]=dv[1]*q; U[3*k+2]=dv[2]*q; }
+    double dv[3] = {b[0]-a[0], b[1]-a[1], b[2]-a[2]}, n = m_sqrt(dot3(dv,dv));
+    if (n < MYO_MINVAL) { U[3*k]=1; U[3*k+1]=0; U[3*k+2]=0; } else { double q = m_rcp(n); U[3*k]=dv[0]*q; U[3*k+1]=dv[1]*q; U[3*k+2]=dv[2]*q; }
     PL[k] = n; }
   #pragma unroll 1
-  for (int k = w.lane; k < m.nwe; k += 32) wrap_element(m, w, k, U, WP, PL);
+  for (int k = w.lane; k < m.nwe; k += 32) wrap_element(m, w, k, U, PL);
   __syncwarp();
 }
 // second half: moments per structural non-zero, tendon lengths and velocities (a CTA barrier in between re-aligns the warps)
 __device__ void phase_tendon_moments(const DevModel& m, const Warp w) {
-  double* U = SCR(s_U); double* WP = SCR(s_WP); double* PL = SCR(s_PL); double* mom = SCR(s_mom);
+  double* U = SCR(s_U); double* PL = SCR(s_PL); double* mom = SCR(s_mom);
   double* tlen = SCR(s_tlen); double* tvel = SCR(s_tvel); double* tfrc = SCR(s_tfrc);
   const idx_t* nzd = CI(PNZ_dof); const idx_t* tadr = CI(PNZ_term_adr); const idx_t* term = CI(PTERM);
   for (int z = w.lane; z < m.nnz; z += 32) { int d = nzd[z]; double acc = 0;
     #pragma unroll 1
     for (int e = tadr[z]; e < tadr[z+1]; e++) { int ui = term[3*e], pc = term[3*e+1]; double sg = term[3*e+2];
-      double pt[3], c[3]; if (pc >= 0) world_point(m, w, pc, pt); else { const double* q = WP + 3*(-pc-1); pt[0]=q[0]; pt[1]=q[1]; pt[2]=q[2]; }
+      double pt[3], c[3]; world_point(m, w, pc, pt);
       dof_point_vel(m, w, d, pt, c); acc += sg*dot3(U + 3*ui, c); }
     mom[z] = acc; }
   const idx_t* padr = CI(PT_piece_adr); const idx_t* piece = CI(PT_piece); const double* tconst = CD(PT_const);
@@ -507,9 +517,9 @@ __device__ __forceinline__ void con_put(ConOut& o, double dist, double px, doubl
   else { o.c1.dist = dist; o.c1.px = px; o.c1.py = py; o.c1.pz = pz; o.c1.nx = nx; o.c1.ny = ny; o.c1.nz = nz; }
   o.n++; }
 __device__ __forceinline__ void sph_sph(ConOut& o, double margin, const double* p1, double r1, const double* p2, double r2) {
-  double dv[3] = {p2[0]-p1[0], p2[1]-p1[1], p2[2]-p1[2]}, cd = sqrt(dot3(dv,dv)), dist = cd-r1-r2;
+  double dv[3] = {p2[0]-p1[0], p2[1]-p1[1], p2[2]-p1[2]}, cd = m_sqrt(dot3(dv,dv)), dist = cd-r1-r2;
   if (dist > margin || o.n >= 2) return;
-  double nx, ny, nz; if (cd < MYO_MINVAL) { nx = 1; ny = 0; nz = 0; } else { double q = 1.0/cd; nx = dv[0]*q; ny = dv[1]*q; nz = dv[2]*q; }
+  double nx, ny, nz; if (cd < MYO_MINVAL) { nx = 1; ny = 0; nz = 0; } else { double q = m_rcp(cd); nx = dv[0]*q; ny = dv[1]*q; nz = dv[2]*q; }
   double off = r1+0.5*dist;
   con_put(o, dist, p1[0]+nx*off, p1[1]+ny*off, p1[2]+nz*off, nx, ny, nz); }
 __device__ __forceinline__ void plane_sph(ConOut& o, double margin, const double* pp, const double* pn, const double* sp, double r) {
@@ -530,9 +540,9 @@ __device__ __forceinline__ void collide_analytic(const DevModel& m, const Warp w
     { double rb = r1+h1+r2+h2+margin; if (dot3(dv,dv) > rb*rb) return; }
     double ma = dot3(a1,a1), mb = -dot3(a1,a2), mc = dot3(a2,a2), u = -dot3(a1,dv), v = dot3(a2,dv), det = ma*mc-mb*mb, v1[3], v2[3];
     if (fabs(det) >= MYO_MINVAL) {
-      double id = 1.0/det, t1 = (mc*u-mb*v)*id, t2 = (ma*v-mb*u)*id;
-      if (t1 > h1) { t1 = h1; t2 = (v-mb*h1)/mc; } else if (t1 < -h1) { t1 = -h1; t2 = (v+mb*h1)/mc; }
-      if (t2 > h2) { t2 = h2; t1 = clipd((u-mb*h2)/ma, -h1, h1); } else if (t2 < -h2) { t2 = -h2; t1 = clipd((u+mb*h2)/ma, -h1, h1); }
+      double id = m_rcp(det), t1 = (mc*u-mb*v)*id, t2 = (ma*v-mb*u)*id; const double imc = m_rcp(mc), ima = m_rcp(ma);
+      if (t1 > h1) { t1 = h1; t2 = (v-mb*h1)*imc; } else if (t1 < -h1) { t1 = -h1; t2 = (v+mb*h1)*imc; }
+      if (t2 > h2) { t2 = h2; t1 = clipd((u-mb*h2)*ima, -h1, h1); } else if (t2 < -h2) { t2 = -h2; t1 = clipd((u+mb*h2)*ima, -h1, h1); }
       for (int k = 0; k < 3; k++) { v1[k] = x1[k]+a1[k]*t1; v2[k] = x2[k]+a2[k]*t2; }
       sph_sph(o, margin, v1, r1, v2, r2);
     } else {   // parallel axes: up to two contacts
@@ -638,8 +648,8 @@ __device__ __forceinline__ void store_contact(const DevModel& m, double* con, in
   // complete the contact frame (rows: normal, tangent1, tangent2)
   double y0 = 0, y1 = 0, y2 = 0;
   if (o.has_y) { y0 = o.yx; y1 = o.yy; y2 = o.yz; }
-  if (sqrt(y0*y0+y1*y1+y2*y2) < 0.5) { y0 = 0; y1 = 0; y2 = 0; if (c.ny < 0.5 && c.ny > -0.5) y1 = 1; else y2 = 1; }
-  double dd = c.nx*y0+c.ny*y1+c.nz*y2; y0 -= dd*c.nx; y1 -= dd*c.ny; y2 -= dd*c.nz; double n = 1.0/sqrt(y0*y0+y1*y1+y2*y2);
+  if (y0*y0+y1*y1+y2*y2 < 0.25) { y0 = 0; y1 = 0; y2 = 0; if (c.ny < 0.5 && c.ny > -0.5) y1 = 1; else y2 = 1; }
+  double dd = c.nx*y0+c.ny*y1+c.nz*y2; y0 -= dd*c.nx; y1 -= dd*c.ny; y2 -= dd*c.nz; double n = m_rcp(m_sqrt(y0*y0+y1*y1+y2*y2));
   f[3] = y0*n; f[4] = y1*n; f[5] = y2*n;
   icon[ci] = p; }
 

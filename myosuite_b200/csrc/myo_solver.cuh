@@ -230,7 +230,7 @@ __device__ __noinline__ void chol_rs(double* H, double* x, int n, int lane) {
 #ifndef MYO_CHOL_NOBATCH
     asm volatile("" ::: "memory");
 #endif
-    const double invd = 1.0/fmax(dk, MYO_MINVAL);
+    const double invd = m_rcp(fmax(dk, MYO_MINVAL));
     if (lane == k) invd_own = invd;
     const double t = r[k]*invd;                      // L[lane][k] on lanes > k
     b = lane > k ? fma(-t, zk, b) : b;

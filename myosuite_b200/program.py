@@ -273,8 +273,10 @@ def build_program(m, allow_unsupported=ALLOWED_UNSUPPORTED_PAIRS):
     nsp, nwe = len(sp_list), len(we_sorted)
     for new, w in enumerate(we_sorted):
         # piece A: pa (b0) -> w0 (bg), unit slot nsp+2*new ; piece B: w1 (bg) -> pb (b1), unit slot nsp+2*new+1
-        add_terms(w["ta"], w["b0"], w["bg"], ("W", 2 * new), w["pa"], -(1 + 2 * new))
-        add_terms(w["ta"], w["bg"], w["b1"], ("W", 2 * new + 1), -(1 + 2 * new + 1), w["pb"])
+        # The moment of a straight piece is  u . (axis x (p - anchor))  for ANY point p on the piece's line (p may slide along u), so the
+        # tangent point riding on the wrap geom's body is replaced by the piece's site: no wrap points are stored at run time.
+        add_terms(w["ta"], w["b0"], w["bg"], ("W", 2 * new), w["pa"], w["pa"])
+        add_terms(w["ta"], w["bg"], w["b1"], ("W", 2 * new + 1), w["pb"], w["pb"])
     counts = [0, 0, 0, 0]
     for w in we_sorted:
         counts[2 * w["typ"] + w["inside"]] += 1
