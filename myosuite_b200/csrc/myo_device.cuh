@@ -231,32 +231,32 @@ __device__ __forceinline__ double wrap2d_outside(double* pnt, const double* d, c
 
 // inverse wrap: the path must pass through the inside of the circle (touches it in one point); returns 0 or -1
 __device__ __forceinline__ double wrap2d_inside(double* pnt, const double* d, double rad, double* zwarm) {
-  double len0 = sqrt(d[0]*d[0]+d[1]*d[1]), len1 = sqrt(d[2]*d[2]+d[3]*d[3]);
+  double len0 = m_sqrt(d[0]*d[0]+d[1]*d[1]), len1 = m_sqrt(d[2]*d[2]+d[3]*d[3]);
   if (len0 <= rad || len1 <= rad || rad < MYO_MINVAL || len0 < MYO_MINVAL || len1 < MYO_MINVAL) return -1;
   double dif0 = d[2]-d[0], dif1 = d[3]-d[1], dd = dif0*dif0+dif1*dif1;
-  if (dd > MYO_MINVAL) { double a = -(dif0*d[0]+dif1*d[1])/dd;
-    if (a > 0 && a < 1) { double x = d[0]+a*dif0, y = d[1]+a*dif1; if (sqrt(x*x+y*y) <= rad) return -1; } }
-  { double x = 0.5*(d[0]+d[2]), y = 0.5*(d[1]+d[3]), n = sqrt(x*x+y*y); if (n < MYO_MINVAL) { x = 1; y = 0; n = 1; }
-    pnt[0]=pnt[2]=rad*x/n; pnt[1]=pnt[3]=rad*y/n; }
-  double A = rad/len0, B = rad/len1, cosG = (len0*len0+len1*len1-dd)/(2*len0*len1);
+  if (dd > MYO_MINVAL) { double a = -(dif0*d[0]+dif1*d[1])*m_rcp(dd);
+    if (a > 0 && a < 1) { double x = d[0]+a*dif0, y = d[1]+a*dif1; if (x*x+y*y <= rad*rad) return -1; } }
+  { double x = 0.5*(d[0]+d[2]), y = 0.5*(d[1]+d[3]), n = m_sqrt(x*x+y*y); if (n < MYO_MINVAL) { x = 1; y = 0; n = 1; }
+    const double q = rad*m_rcp(n); pnt[0]=pnt[2]=x*q; pnt[1]=pnt[3]=y*q; }
+  double A = rad*m_rcp(len0), B = rad*m_rcp(len1), cosG = (len0*len0+len1*len1-dd)*m_rcp(2*len0*len1);
   if (cosG < -1+MYO_MINVAL) return -1; else if (cosG > 1-MYO_MINVAL) return 0;
   double G = acos(cosG), z, f; bool solved = false;
   if (*zwarm > 0 && *zwarm < 1-1e-7) {   // warm start from the previous substep's root: a few safeguarded Newton steps, else fall back to the cold start
     z = *zwarm;
     #pragma unroll 1
     for (int it = 0; it < 4; it++) { f = asin(A*z)+asin(B*z)-2*asin(z)+G; if (fabs(f) < 1e-10) { solved = true; break; }
-      double df = A/fmax(MYO_MINVAL, sqrt(1-z*z*A*A)) + B/fmax(MYO_MINVAL, sqrt(1-z*z*B*B)) - 2/fmax(MYO_MINVAL, sqrt(1-z*z));
+      double df = A*m_rcp(fmax(MYO_MINVAL, m_sqrt(1-z*z*A*A))) + B*m_rcp(fmax(MYO_MINVAL, m_sqrt(1-z*z*B*B))) - 2*m_rcp(fmax(MYO_MINVAL, m_sqrt(1-z*z)));
       if (df > -MYO_MINVAL) break;
-      z -= f/df; if (!(z > 0 && z < 1-1e-7)) break; } }
+      z -= f*m_rcp(df); if (!(z > 0 && z < 1-1e-7)) break; } }
   int it = 0;
   if (!solved) {
   z = 1-1e-7; f = asin(A*z)+asin(B*z)-2*asin(z)+G;
   if (f > 0) { *zwarm = -1; return 0; }
   #pragma unroll 1
   for (; it < 20 && fabs(f) > 1e-6; it++) {
-    double df = A/fmax(MYO_MINVAL, sqrt(1-z*z*A*A)) + B/fmax(MYO_MINVAL, sqrt(1-z*z*B*B)) - 2/fmax(MYO_MINVAL, sqrt(1-z*z));
+    double df = A*m_rcp(fmax(MYO_MINVAL, m_sqrt(1-z*z*A*A))) + B*m_rcp(fmax(MYO_MINVAL, m_sqrt(1-z*z*B*B))) - 2*m_rcp(fmax(MYO_MINVAL, m_sqrt(1-z*z)));
     if (df > -MYO_MINVAL) return 0;
-    double z1 = z - f/df; if (z1 > z) return 0;
+    double z1 = z - f*m_rcp(df); if (z1 > z) return 0;
     z = z1; f = asin(A*z)+asin(B*z)-2*asin(z)+G;
     if (f > 1e-6) return 0; }
   if (it >= 20) return 0;
@@ -264,7 +264,7 @@ __device__ __forceinline__ double wrap2d_inside(double* pnt, const double* d, do
   *zwarm = z;
   double vx, vy, ang;
   if (d[0]*d[3]-d[1]*d[2] > 0) { vx = d[0]; vy = d[1]; ang = asin(z)-asin(A*z); } else { vx = d[2]; vy = d[3]; ang = asin(z)-asin(B*z); }
-  double n = sqrt(vx*vx+vy*vy); vx /= n; vy /= n; double s, c; sincos(ang, &s, &c);
+  { const double q = m_rcp(m_sqrt(vx*vx+vy*vy)); vx *= q; vy *= q; } double s, c; sincos(ang, &s, &c);
   pnt[0] = rad*(c*vx - s*vy); pnt[1] = rad*(s*vx + c*vy); pnt[2] = pnt[0]; pnt[3] = pnt[1];
   return 0; }
 
@@ -351,10 +351,10 @@ __device__ void phase_tendon_moments(const DevModel& m, const Warp w) {
 // ------------------------------------------------------------------ phase 3: muscle actuation -> qfrc_smooth (passive + actuator); act integration
 __device__ __forceinline__ double muscle_FL(double L, double lmin, double lmax) {
   if (lmin <= L && L <= lmax) { double a = 0.5*(lmin+1), b = 0.5*(1+lmax), x;
-    if (L <= a) { x = (L-lmin)/fmax(MYO_MINVAL, a-lmin); return 0.5*x*x; }
-    else if (L <= 1) { x = (1-L)/fmax(MYO_MINVAL, 1-a); return 1-0.5*x*x; }
-    else if (L <= b) { x = (L-1)/fmax(MYO_MINVAL, b-1); return 1-0.5*x*x; }
-    else { x = (lmax-L)/fmax(MYO_MINVAL, lmax-b); return 0.5*x*x; } }
+    if (L <= a) { x = (L-lmin)*m_rcp(fmax(MYO_MINVAL, a-lmin)); return 0.5*x*x; }
+    else if (L <= 1) { x = (1-L)*m_rcp(fmax(MYO_MINVAL, 1-a)); return 1-0.5*x*x; }
+    else if (L <= b) { x = (L-1)*m_rcp(fmax(MYO_MINVAL, b-1)); return 1-0.5*x*x; }
+    else { x = (lmax-L)*m_rcp(fmax(MYO_MINVAL, lmax-b)); return 0.5*x*x; } }
   return 0; }
 
 // tap_force / tap_len: nullable global rows for the parity taps (values before the activation is advanced)
@@ -366,19 +366,19 @@ __device__ void phase_actuation(const DevModel& m, const Warp w, bool integrate,
     double len = gear*tlen[t], vel = gear*tvel[t], ctrl = W_(ctrl)[i], act = W_(act)[i];
     if (a[15] != 0) ctrl = clipd(ctrl, cr[0], cr[1]);
     // activation dynamics
-    double cc = clipd(ctrl, 0, 1), ac = clipd(act, 0, 1), ta = dyn[0]*(0.5+1.5*ac), td = dyn[1]/(0.5+1.5*ac), dctrl = cc - act, tau;
+    double cc = clipd(ctrl, 0, 1), ac = clipd(act, 0, 1), ta = dyn[0]*(0.5+1.5*ac), td = dyn[1]*m_rcp(0.5+1.5*ac), dctrl = cc - act, tau;
     if (dyn[2] < MYO_MINVAL) tau = dctrl > 0 ? ta : td;
     else { double x = clipd(dctrl/dyn[2]+0.5, 0, 1), s = x*x*x*(3*x*(2*x-5)+10); tau = td+(ta-td)*s; }
-    double actdot = dctrl/fmax(MYO_MINVAL, tau);
+    double actdot = dctrl*m_rcp(fmax(MYO_MINVAL, tau));
     // gain (active force-length-velocity) and bias (passive force)
     const double g_lmin = gp[2], g_lmax = gp[3], g_vmax = gp[4], g_fvmax = gp[5], b_lmax = bp[2], b_fpmax = bp[3];
-    double F = am[0], L0 = (lr1-lr0)/fmax(MYO_MINVAL, gp[1]-gp[0]), L = gp[0]+(len-lr0)/fmax(MYO_MINVAL, L0), V = vel/fmax(MYO_MINVAL, L0*g_vmax);
+    double F = am[0], L0 = (lr1-lr0)*m_rcp(fmax(MYO_MINVAL, gp[1]-gp[0])), L = gp[0]+(len-lr0)*m_rcp(fmax(MYO_MINVAL, L0)), V = vel*m_rcp(fmax(MYO_MINVAL, L0*g_vmax));
     double FL = muscle_FL(L, g_lmin, g_lmax), y = g_fvmax-1, FV;
-    if (V <= -1) FV = 0; else if (V <= 0) FV = (V+1)*(V+1); else if (V <= y) FV = g_fvmax-(y-V)*(y-V)/fmax(MYO_MINVAL, y); else FV = g_fvmax;
+    if (V <= -1) FV = 0; else if (V <= 0) FV = (V+1)*(V+1); else if (V <= y) FV = g_fvmax-(y-V)*(y-V)*m_rcp(fmax(MYO_MINVAL, y)); else FV = g_fvmax;
     double gain = -F*FL*FV;
-    double Fb = am[1], L0b = (lr1-lr0)/fmax(MYO_MINVAL, bp[1]-bp[0]), Lb = bp[0]+(len-lr0)/fmax(MYO_MINVAL, L0b), b = 0.5*(1+b_lmax), bias;
-    if (Lb <= 1) bias = 0; else if (Lb <= b) { double x = (Lb-1)/fmax(MYO_MINVAL, b-1); bias = -Fb*b_fpmax*0.5*x*x; }
-    else { double x = (Lb-b)/fmax(MYO_MINVAL, b-1); bias = -Fb*b_fpmax*(0.5+x); }
+    double Fb = am[1], L0b = (lr1-lr0)*m_rcp(fmax(MYO_MINVAL, bp[1]-bp[0])), Lb = bp[0]+(len-lr0)*m_rcp(fmax(MYO_MINVAL, L0b)), b = 0.5*(1+b_lmax), bias;
+    if (Lb <= 1) bias = 0; else if (Lb <= b) { double x = (Lb-1)*m_rcp(fmax(MYO_MINVAL, b-1)); bias = -Fb*b_fpmax*0.5*x*x; }
+    else { double x = (Lb-b)*m_rcp(fmax(MYO_MINVAL, b-1)); bias = -Fb*b_fpmax*(0.5+x); }
     double force = gain*act + bias;
     tfrc[t] = gear*force;   // one actuator per tendon (checked on the host)
     if (tap_force) tap_force[i] = force;
@@ -471,37 +471,37 @@ __device__ __forceinline__ double ell_sd(const double* dl, const double* R1, con
   for (int it = 0; it < 40; it++) {
     double a[3], u[3], n1 = 0, n2;
     p1[0] = p1[1] = p1[2] = 0;
-    if (s1) { matT_vec(a, R1, d); u[0] = s1[0]*s1[0]*a[0]; u[1] = s1[1]*s1[1]*a[1]; u[2] = s1[2]*s1[2]*a[2]; n1 = sqrt(dot3(a, u)); mat_vec(p1, R1, u); double q = 1.0/n1; p1[0]*=q; p1[1]*=q; p1[2]*=q; }
-    matT_vec(a, R2, d); u[0] = s2[0]*s2[0]*a[0]; u[1] = s2[1]*s2[1]*a[1]; u[2] = s2[2]*s2[2]*a[2]; n2 = sqrt(dot3(a, u)); mat_vec(p2, R2, u); { double q = 1.0/n2; p2[0]*=q; p2[1]*=q; p2[2]*=q; }
+    if (s1) { matT_vec(a, R1, d); u[0] = s1[0]*s1[0]*a[0]; u[1] = s1[1]*s1[1]*a[1]; u[2] = s1[2]*s1[2]*a[2]; n1 = m_sqrt(dot3(a, u)); mat_vec(p1, R1, u); double q = m_rcp(n1); p1[0]*=q; p1[1]*=q; p1[2]*=q; }
+    matT_vec(a, R2, d); u[0] = s2[0]*s2[0]*a[0]; u[1] = s2[1]*s2[1]*a[1]; u[2] = s2[2]*s2[2]*a[2]; n2 = m_sqrt(dot3(a, u)); mat_vec(p2, R2, u); { double q = m_rcp(n2); p2[0]*=q; p2[1]*=q; p2[2]*=q; }
     double g[3] = {dl[0]-p1[0]-p2[0], dl[1]-p1[1]-p2[1], dl[2]-p1[2]-p2[2]};
     f = dot3(d, dl) - n1 - n2;
     if (f > bound) return f;
     // tangent basis
     double e[3]; { int k = fabs(d[0]) < fabs(d[1]) ? (fabs(d[0]) < fabs(d[2]) ? 0 : 2) : (fabs(d[1]) < fabs(d[2]) ? 1 : 2); e[0] = k == 0; e[1] = k == 1; e[2] = k == 2; }
-    double t1[3], t2[3]; cross3(t1, d, e); { double q = 1.0/sqrt(dot3(t1,t1)); t1[0]*=q; t1[1]*=q; t1[2]*=q; } cross3(t2, d, t1);
-    double g1 = dot3(t1, g), g2 = dot3(t2, g), scale = sqrt(dot3(dl,dl)) + n1 + n2;
+    double t1[3], t2[3]; cross3(t1, d, e); { double q = m_rcp(m_sqrt(dot3(t1,t1))); t1[0]*=q; t1[1]*=q; t1[2]*=q; } cross3(t2, d, t1);
+    double g1 = dot3(t1, g), g2 = dot3(t2, g), scale = m_sqrt(dot3(dl,dl)) + n1 + n2;
     if (g1*g1 + g2*g2 < 1e-24*scale*scale) break;      // tangential gradient ~1e-12: direction converged to round-off
     // tangent Hessian of the Lagrangian:  -sum_i (t_k.A_i t_l - (t_k.p_i)(t_l.p_i))/n_i - f delta_kl
     double H11 = -f, H12 = 0, H22 = -f;
     { double b1[3], b2[3], v[3]; matT_vec(b1, R2, t1); matT_vec(b2, R2, t2);
       v[0] = s2[0]*s2[0]; v[1] = s2[1]*s2[1]; v[2] = s2[2]*s2[2];
       double a11 = v[0]*b1[0]*b1[0]+v[1]*b1[1]*b1[1]+v[2]*b1[2]*b1[2], a12 = v[0]*b1[0]*b2[0]+v[1]*b1[1]*b2[1]+v[2]*b1[2]*b2[2], a22 = v[0]*b2[0]*b2[0]+v[1]*b2[1]*b2[1]+v[2]*b2[2]*b2[2];
-      double q1 = dot3(t1, p2), q2 = dot3(t2, p2), in = 1.0/n2; H11 -= (a11-q1*q1)*in; H12 -= (a12-q1*q2)*in; H22 -= (a22-q2*q2)*in;
+      double q1 = dot3(t1, p2), q2 = dot3(t2, p2), in = m_rcp(n2); H11 -= (a11-q1*q1)*in; H12 -= (a12-q1*q2)*in; H22 -= (a22-q2*q2)*in;
     }
     if (s1) { double b1[3], b2[3], v[3]; matT_vec(b1, R1, t1); matT_vec(b2, R1, t2);
       v[0] = s1[0]*s1[0]; v[1] = s1[1]*s1[1]; v[2] = s1[2]*s1[2];
       double a11 = v[0]*b1[0]*b1[0]+v[1]*b1[1]*b1[1]+v[2]*b1[2]*b1[2], a12 = v[0]*b1[0]*b2[0]+v[1]*b1[1]*b2[1]+v[2]*b1[2]*b2[2], a22 = v[0]*b2[0]*b2[0]+v[1]*b2[1]*b2[1]+v[2]*b2[2]*b2[2];
-      double q1 = dot3(t1, p1), q2 = dot3(t2, p1), in = 1.0/n1; H11 -= (a11-q1*q1)*in; H12 -= (a12-q1*q2)*in; H22 -= (a22-q2*q2)*in; }
+      double q1 = dot3(t1, p1), q2 = dot3(t2, p1), in = m_rcp(n1); H11 -= (a11-q1*q1)*in; H12 -= (a12-q1*q2)*in; H22 -= (a22-q2*q2)*in; }
     double det = H11*H22 - H12*H12, dx, dy;
-    if (H11 < 0 && det > 0) { double id = 1.0/det; dx = -(H22*g1 - H12*g2)*id; dy = -(-H12*g1 + H11*g2)*id; }
-    else { double L = fabs(H11) + fabs(H22) + fabs(H12) + 1e-12; dx = g1/L; dy = g2/L; }     // safeguarded ascent step
-    double nn = sqrt(dx*dx + dy*dy); if (nn > 0.5) { dx *= 0.5/nn; dy *= 0.5/nn; }
+    if (H11 < 0 && det > 1e-200) { double id = m_rcp(det); dx = -(H22*g1 - H12*g2)*id; dy = -(-H12*g1 + H11*g2)*id; }
+    else { double L = m_rcp(fabs(H11) + fabs(H22) + fabs(H12) + 1e-12); dx = g1*L; dy = g2*L; }     // safeguarded ascent step
+    double nn = m_sqrt(dx*dx + dy*dy); if (nn > 0.5) { const double q = 0.5*m_rcp(nn); dx *= q; dy *= q; }
     bool last = nn < 1e-12;                            // a step this small cannot change the result
     // backtracking: accept the first step that does not decrease f
     #pragma unroll 1
-    for (int bt = 0; bt < 12; bt++) { double dn[3] = {d[0]+dx*t1[0]+dy*t2[0], d[1]+dx*t1[1]+dy*t2[1], d[2]+dx*t1[2]+dy*t2[2]}; double q = 1.0/sqrt(dot3(dn,dn)); dn[0]*=q; dn[1]*=q; dn[2]*=q;
-      double fn = dot3(dn, dl); { double aa[3]; matT_vec(aa, R2, dn); fn -= sqrt(s2[0]*s2[0]*aa[0]*aa[0]+s2[1]*s2[1]*aa[1]*aa[1]+s2[2]*s2[2]*aa[2]*aa[2]); }
-      if (s1) { double aa[3]; matT_vec(aa, R1, dn); fn -= sqrt(s1[0]*s1[0]*aa[0]*aa[0]+s1[1]*s1[1]*aa[1]*aa[1]+s1[2]*s1[2]*aa[2]*aa[2]); }
+    for (int bt = 0; bt < 12; bt++) { double dn[3] = {d[0]+dx*t1[0]+dy*t2[0], d[1]+dx*t1[1]+dy*t2[1], d[2]+dx*t1[2]+dy*t2[2]}; double q = m_rcp(m_sqrt(dot3(dn,dn))); dn[0]*=q; dn[1]*=q; dn[2]*=q;
+      double fn = dot3(dn, dl); { double aa[3]; matT_vec(aa, R2, dn); fn -= m_sqrt(s2[0]*s2[0]*aa[0]*aa[0]+s2[1]*s2[1]*aa[1]*aa[1]+s2[2]*s2[2]*aa[2]*aa[2]); }
+      if (s1) { double aa[3]; matT_vec(aa, R1, dn); fn -= m_sqrt(s1[0]*s1[0]*aa[0]*aa[0]+s1[1]*s1[1]*aa[1]*aa[1]+s1[2]*s1[2]*aa[2]*aa[2]); }
       if (fn >= f - 1e-14*scale || bt == 11) { d[0]=dn[0]; d[1]=dn[1]; d[2]=dn[2]; break; }
       dx *= 0.5; dy *= 0.5; }
     if (last) break;
@@ -562,8 +562,8 @@ __device__ __forceinline__ void collide_analytic(const DevModel& m, const Warp w
     o.has_y = true; o.yx = a2[0]; o.yy = a2[1]; o.yz = a2[2];
   } else if (ct == CT_PLANE_ELL) {   // deepest point of the ellipsoid along -normal
     double R2[9], nl[3], u[3], pw[3]; geom_mat(m, w, g2, R2); matT_vec(nl, R2, a1);
-    u[0] = s2[0]*s2[0]*nl[0]; u[1] = s2[1]*s2[1]*nl[1]; u[2] = s2[2]*s2[2]*nl[2]; double nn = sqrt(dot3(nl, u)); mat_vec(pw, R2, u);
-    double pos[3] = {x2[0]-pw[0]/nn, x2[1]-pw[1]/nn, x2[2]-pw[2]/nn}, dv[3] = {pos[0]-x1[0], pos[1]-x1[1], pos[2]-x1[2]}, dist = dot3(dv, a1);
+    u[0] = s2[0]*s2[0]*nl[0]; u[1] = s2[1]*s2[1]*nl[1]; u[2] = s2[2]*s2[2]*nl[2]; double nn = m_rcp(m_sqrt(dot3(nl, u))); mat_vec(pw, R2, u);
+    double pos[3] = {x2[0]-pw[0]*nn, x2[1]-pw[1]*nn, x2[2]-pw[2]*nn}, dv[3] = {pos[0]-x1[0], pos[1]-x1[1], pos[2]-x1[2]}, dist = dot3(dv, a1);
     if (dist <= margin) con_put(o, dist, pos[0]-a1[0]*0.5*dist, pos[1]-a1[1]*0.5*dist, pos[2]-a1[2]*0.5*dist, a1[0], a1[1], a1[2]);
   }
 }
@@ -580,31 +580,31 @@ __device__ __forceinline__ void collide_ellipsoid(const DevModel& m, const Warp 
     //     ellipsoid's shadow (an ellipse): a 1-D Newton on the unit circle  max_u  c.u - sqrt(u'Au).  Every iterate's value is a
     //     lower bound of the segment distance, so a pair that is provably out of its margin leaves at once.
     double e1[3], e2[3]; { double e[3]; int k = fabs(a1[0]) < fabs(a1[1]) ? (fabs(a1[0]) < fabs(a1[2]) ? 0 : 2) : (fabs(a1[1]) < fabs(a1[2]) ? 1 : 2); e[0] = k == 0; e[1] = k == 1; e[2] = k == 2;
-      cross3(e1, a1, e); double q = 1.0/sqrt(dot3(e1,e1)); e1[0]*=q; e1[1]*=q; e1[2]*=q; cross3(e2, a1, e1); }
+      cross3(e1, a1, e); double q = m_rcp(m_sqrt(dot3(e1,e1))); e1[0]*=q; e1[1]*=q; e1[2]*=q; cross3(e2, a1, e1); }
     double b1[3], b2[3]; matT_vec(b1, R2, e1); matT_vec(b2, R2, e2);
     double v0 = s2[0]*s2[0], v1 = s2[1]*s2[1], v2 = s2[2]*s2[2];
     double A11 = v0*b1[0]*b1[0]+v1*b1[1]*b1[1]+v2*b1[2]*b1[2], A12 = v0*b1[0]*b2[0]+v1*b1[1]*b2[1]+v2*b1[2]*b2[2], A22 = v0*b2[0]*b2[0]+v1*b2[1]*b2[1]+v2*b2[2]*b2[2];
-    double c1 = dot3(e1, dv), c2 = dot3(e2, dv), cn = sqrt(c1*c1+c2*c2), u1 = 1, u2 = 0, F = 0, scale = cn + sqrt(fmax(A11, A22));
-    if (cn > MYO_MINVAL) { u1 = c1/cn; u2 = c2/cn; }
+    double c1 = dot3(e1, dv), c2 = dot3(e2, dv), cn = m_sqrt(c1*c1+c2*c2), u1 = 1, u2 = 0, F = 0, scale = cn + m_sqrt(fmax(A11, A22));
+    if (cn > MYO_MINVAL) { const double q = m_rcp(cn); u1 = c1*q; u2 = c2*q; }
     #pragma unroll 1
     for (int it = 0; it < 40; it++) {
-      double Au1 = A11*u1+A12*u2, Au2 = A12*u1+A22*u2, n2 = u1*Au1+u2*Au2, n = sqrt(n2), in = 1.0/n;
+      double Au1 = A11*u1+A12*u2, Au2 = A12*u1+A22*u2, n2 = u1*Au1+u2*Au2, n = m_sqrt(n2), in = m_rcp(n);
       F = c1*u1+c2*u2 - n;
       if (F - r > margin) return;
       double p1_ = -u2, p2_ = u1;                                  // u_perp
       double uAp = p1_*Au1+p2_*Au2, pAp = A11*p1_*p1_+2*A12*p1_*p2_+A22*p2_*p2_;
       double g = c1*p1_+c2*p2_ - uAp*in, H = -(c1*u1+c2*u2) - ((pAp-n2)*in - uAp*uAp*in*in*in);
       if (fabs(g) < 1e-12*scale) break;
-      double dx = H < 0 ? -g/H : g/(fabs(H)+1e-12); if (fabs(dx) > 0.5) dx = dx > 0 ? 0.5 : -0.5;
+      double dx = H < -1e-200 ? -g*m_rcp(H) : g*m_rcp(fabs(H)+1e-12); if (fabs(dx) > 0.5) dx = dx > 0 ? 0.5 : -0.5;
       bool last = fabs(dx) < 1e-12;
       #pragma unroll 1
-      for (int bt = 0; bt < 12; bt++) { double w1 = u1+dx*p1_, w2 = u2+dx*p2_, q = 1.0/sqrt(w1*w1+w2*w2); w1 *= q; w2 *= q;
-        double fn = c1*w1+c2*w2 - sqrt(A11*w1*w1+2*A12*w1*w2+A22*w2*w2);
+      for (int bt = 0; bt < 12; bt++) { double w1 = u1+dx*p1_, w2 = u2+dx*p2_, q = m_rcp(m_sqrt(w1*w1+w2*w2)); w1 *= q; w2 *= q;
+        double fn = c1*w1+c2*w2 - m_sqrt(A11*w1*w1+2*A12*w1*w2+A22*w2*w2);
         if (fn >= F - 1e-14*scale || bt == 11) { u1 = w1; u2 = w2; break; }
         dx *= 0.5; }
       if (last) break; }
     double d[3] = {u1*e1[0]+u2*e2[0], u1*e1[1]+u2*e2[1], u1*e1[2]+u2*e2[2]}, p1[3], p2[3], t, sd;
-    { double a[3], u[3]; matT_vec(a, R2, d); u[0] = v0*a[0]; u[1] = v1*a[1]; u[2] = v2*a[2]; double nn = sqrt(dot3(a, u)); mat_vec(p2, R2, u); double q = 1.0/nn; p2[0]*=q; p2[1]*=q; p2[2]*=q; }
+    { double a[3], u[3]; matT_vec(a, R2, d); u[0] = v0*a[0]; u[1] = v1*a[1]; u[2] = v2*a[2]; double nn = m_sqrt(dot3(a, u)); mat_vec(p2, R2, u); double q = m_rcp(nn); p2[0]*=q; p2[1]*=q; p2[2]*=q; }
     t = (dv[0]-p2[0])*a1[0] + (dv[1]-p2[1])*a1[1] + (dv[2]-p2[2])*a1[2];        // axis coordinate of the ellipsoid-side witness
     if (t >= -h && t <= h) sd = F;
     else {   // (2) the line's closest point is beyond a cap: the distance over the segment (convex in t) is attained at that end point
@@ -613,10 +613,10 @@ __device__ __forceinline__ void collide_ellipsoid(const DevModel& m, const Warp 
     double dist = sd - r;
     if (dist <= margin) con_put(o, dist, 0.5*((x1[0]+a1[0]*t + d[0]*r) + (x2[0]-p2[0])), 0.5*((x1[1]+a1[1]*t + d[1]*r) + (x2[1]-p2[1])), 0.5*((x1[2]+a1[2]*t + d[2]*r) + (x2[2]-p2[2])), d[0], d[1], d[2]);
   } else if (ct == CT_ELL_ELL) {
-    double dl[3] = {x2[0]-x1[0], x2[1]-x1[1], x2[2]-x1[2]}, cd = sqrt(dot3(dl,dl));
+    double dl[3] = {x2[0]-x1[0], x2[1]-x1[1], x2[2]-x1[2]}, cd = m_sqrt(dot3(dl,dl));
     if (cd - fmax(s1[0], fmax(s1[1], s1[2])) - fmax(s2[0], fmax(s2[1], s2[2])) > margin) return;
     double R1[9], R2[9], d[3], p1[3], p2[3]; geom_mat(m, w, g1, R1); geom_mat(m, w, g2, R2);
-    if (cd < MYO_MINVAL) { d[0]=1; d[1]=0; d[2]=0; } else { d[0]=dl[0]/cd; d[1]=dl[1]/cd; d[2]=dl[2]/cd; }
+    if (cd < MYO_MINVAL) { d[0]=1; d[1]=0; d[2]=0; } else { const double q = m_rcp(cd); d[0]=dl[0]*q; d[1]=dl[1]*q; d[2]=dl[2]*q; }
     double dist = ell_sd(dl, R1, s1, R2, s2, d, p1, p2, margin);
     if (dist <= margin) con_put(o, dist, 0.5*((x1[0]+p1[0]) + (x2[0]-p2[0])), 0.5*((x1[1]+p1[1]) + (x2[1]-p2[1])), 0.5*((x1[2]+p1[2]) + (x2[2]-p2[2])), d[0], d[1], d[2]);
   }
@@ -630,16 +630,16 @@ __device__ __forceinline__ bool expensive_candidate(const DevModel& m, const War
   double dv[3] = {x2[0]-x1[0], x2[1]-x1[1], x2[2]-x1[2]}, rb2 = fmax(s2[0], fmax(s2[1], s2[2]));
   // any unit direction d gives a lower bound  d.(c2-c1) - h1(d) - h2(d)  on the signed distance: use the centre-to-centre
   // (or centre-to-segment) direction -- tight for the flat finger-pad ellipsoids, unlike a bounding sphere
-  if (pr[5] == CT_CAP_ELL) { double t = clipd(dot3(dv, a1), -s1[1], s1[1]), q[3] = {dv[0]-a1[0]*t, dv[1]-a1[1]*t, dv[2]-a1[2]*t}, nq = sqrt(dot3(q,q));
+  if (pr[5] == CT_CAP_ELL) { double t = clipd(dot3(dv, a1), -s1[1], s1[1]), q[3] = {dv[0]-a1[0]*t, dv[1]-a1[1]*t, dv[2]-a1[2]*t}, nq = m_sqrt(dot3(q,q));
     if (nq - s1[0] - rb2 > margin) return false;
     if (nq < MYO_MINVAL) return true;
-    double R2[9], b[3], d[3] = {q[0]/nq, q[1]/nq, q[2]/nq}; geom_mat(m, w, g2, R2); matT_vec(b, R2, d);
-    return nq - sqrt(s2[0]*s2[0]*b[0]*b[0]+s2[1]*s2[1]*b[1]*b[1]+s2[2]*s2[2]*b[2]*b[2]) - s1[0] <= margin; }
-  double cd = sqrt(dot3(dv,dv));
+    double R2[9], b[3], iq = m_rcp(nq), d[3] = {q[0]*iq, q[1]*iq, q[2]*iq}; geom_mat(m, w, g2, R2); matT_vec(b, R2, d);
+    return nq - m_sqrt(s2[0]*s2[0]*b[0]*b[0]+s2[1]*s2[1]*b[1]*b[1]+s2[2]*s2[2]*b[2]*b[2]) - s1[0] <= margin; }
+  double cd = m_sqrt(dot3(dv,dv));
   if (cd - fmax(s1[0], fmax(s1[1], s1[2])) - rb2 > margin) return false;
   if (cd < MYO_MINVAL) return true;
-  double R1[9], R2[9], b[3], c[3], d[3] = {dv[0]/cd, dv[1]/cd, dv[2]/cd}; geom_mat(m, w, g1, R1); geom_mat(m, w, g2, R2); matT_vec(b, R1, d); matT_vec(c, R2, d);
-  return cd - sqrt(s1[0]*s1[0]*b[0]*b[0]+s1[1]*s1[1]*b[1]*b[1]+s1[2]*s1[2]*b[2]*b[2]) - sqrt(s2[0]*s2[0]*c[0]*c[0]+s2[1]*s2[1]*c[1]*c[1]+s2[2]*s2[2]*c[2]*c[2]) <= margin; }
+  double R1[9], R2[9], b[3], c[3], icd = m_rcp(cd), d[3] = {dv[0]*icd, dv[1]*icd, dv[2]*icd}; geom_mat(m, w, g1, R1); geom_mat(m, w, g2, R2); matT_vec(b, R1, d); matT_vec(c, R2, d);
+  return cd - m_sqrt(s1[0]*s1[0]*b[0]*b[0]+s1[1]*s1[1]*b[1]*b[1]+s1[2]*s1[2]*b[2]*b[2]) - m_sqrt(s2[0]*s2[0]*c[0]*c[0]+s2[1]*s2[1]*c[1]*c[1]+s2[2]*s2[2]*c[2]*c[2]) <= margin; }
 
 __device__ __forceinline__ void store_contact(const DevModel& m, double* con, int* icon, int ci, int p, const Con1& c, const ConOut& o) {
   if (ci >= m.maxcon) return;

@@ -32,11 +32,11 @@
 
 __device__ __forceinline__ double impedance(const double* si, double pos, double margin) {
   if (si[0] == si[1] || si[2] <= MYO_MINVAL) return 0.5*(si[0]+si[1]);
-  double x = fabs((pos-margin)/si[2]);
+  double x = fabs((pos-margin)*m_rcp(si[2]));
   if (x >= 1 || x <= 0) return x >= 1 ? si[1] : si[0];
   double y;
   if (si[4] == 1) y = x;
-  else if (si[4] == 2) y = x <= si[3] ? x*x/si[3] : 1-(1-x)*(1-x)/(1-si[3]);   // the default power, without pow()
+  else if (si[4] == 2) y = x <= si[3] ? x*x*m_rcp(si[3]) : 1-(1-x)*(1-x)*m_rcp(1-si[3]);   // the default power, without pow()
   else if (x <= si[3]) y = pow(x, si[4])/pow(si[3], si[4]-1);
   else y = 1-pow(1-x, si[4])/pow(1-si[3], si[4]-1);
   return si[0]+y*(si[1]-si[0]); }
@@ -106,8 +106,8 @@ __device__ void phase_constraints(const DevModel& m, const Warp w) {
     if (q2 >= 0) { double x = W_(qpos)[q2]-c[6]; cpos = pos0-(c[0]+x*(c[1]+x*(c[2]+x*(c[3]+x*c[4])))); deriv = c[1]+x*(2*c[2]+x*(3*c[3]+x*4*c[4])); vel -= deriv*W_(qvel)[d2]; }
     else cpos = pos0-c[0];
     S_eqJ[e] = -deriv;
-    double imp = impedance(c+10, cpos, 0), R = fmax(MYO_MINVAL, (1-imp)*c[7]/imp);
-    S_D[e] = 1.0/R; S_aref[e] = -c[9]*vel - c[8]*imp*cpos; }
+    double imp = impedance(c+10, cpos, 0), R = fmax(MYO_MINVAL, (1-imp)*c[7]*m_rcp(imp));
+    S_D[e] = m_rcp(R); S_aref[e] = -c[9]*vel - c[8]*imp*cpos; }
   // joint limits (one-sided)
   const idx_t* lim = CI(PLIM); const double* limd = CD(PLIM_d); int nrow = 0;
   for (int base = 0; base < m.nlim; base += 32) { int l = base + w.lane; bool lo = false, hi = false; double dlo = 0, dhi = 0; const double* c = limd + (l < m.nlim ? l : 0)*PLIM_STRIDE; int d = 0;
@@ -116,8 +116,8 @@ __device__ void phase_constraints(const DevModel& m, const Warp w) {
     for (int side = 0; side < 2; side++) { if (!(side ? hi : lo)) continue;
       double dist = side ? dhi : dlo, sg = side ? -1.0 : 1.0; int r = m.neq + idx; idx++;
       S_lrow[r - m.neq] = d | (side << 16);
-      double imp = impedance(c+6, dist, c[2]), R = fmax(MYO_MINVAL, (1-imp)*c[3]/imp);
-      S_D[r] = 1.0/R; S_aref[r] = -c[5]*sg*W_(qvel)[d] - c[4]*imp*(dist-c[2]); }
+      double imp = impedance(c+6, dist, c[2]), R = fmax(MYO_MINVAL, (1-imp)*c[3]*m_rcp(imp));
+      S_D[r] = m_rcp(R); S_aref[r] = -c[5]*sg*W_(qvel)[d] - c[4]*imp*(dist-c[2]); }
     nrow += __popc(m0) + __popc(m1); }
   WI_(nlimrow) = nrow;
   // contacts: Jacobian over the dofs between the two bodies, regulariser, reference acceleration.
@@ -164,8 +164,8 @@ __device__ void phase_constraints(const DevModel& m, const Warp w) {
         double qd = W_(qvel)[d]; vn += jn*qd; v1 += j1*qd; v2 += j2*qd; }
       S_cmask[c] = mk;
       double dist = cd[0], inc = P[0]-P[1], imp = impedance(P+7, dist, inc), K = P[5], B = P[6], tran = CD(PPAIR_tran)[S_cpair[c]];
-      if (nr == 1) { double R = fmax(MYO_MINVAL, (1-imp)*tran/imp); S_D[rb] = 1.0/R; S_aref[rb] = -B*vn - K*imp*(dist-inc); }
-      else { double mu1 = P[2], mu2 = P[3]; double R0 = fmax(MYO_MINVAL, (1-imp)*(tran+mu1*mu1*tran)/imp), Rpy = 2*mu1*mu1*R0, Dv = 1.0/Rpy, kp = K*imp*(dist-inc);
+      if (nr == 1) { double R = fmax(MYO_MINVAL, (1-imp)*tran*m_rcp(imp)); S_D[rb] = m_rcp(R); S_aref[rb] = -B*vn - K*imp*(dist-inc); }
+      else { double mu1 = P[2], mu2 = P[3]; double R0 = fmax(MYO_MINVAL, (1-imp)*(tran+mu1*mu1*tran)*m_rcp(imp)), Rpy = 2*mu1*mu1*R0, Dv = m_rcp(Rpy), kp = K*imp*(dist-inc);
         S_D[rb] = S_D[rb+1] = S_D[rb+2] = S_D[rb+3] = Dv;
         S_aref[rb] = -B*(vn+mu1*v1)-kp; S_aref[rb+1] = -B*(vn-mu1*v1)-kp; S_aref[rb+2] = -B*(vn+mu2*v2)-kp; S_aref[rb+3] = -B*(vn-mu2*v2)-kp; } } }
   WI_(nefc) = rowbase;
@@ -441,7 +441,7 @@ __device__ void phase_solve(const DevModel& m, const Warp w, double tol, long lo
       for (int r = w.lane; r < nefc; r += 32) { double x = S_jar[r]+alpha*S_jv[r]; if (r < m.neq || x < 0) { dv += S_D[r]*x*S_jv[r]; hh += S_D[r]*S_jv[r]*S_jv[r]; } }
       dv = warp_sum(dv) + ga + gb*alpha; hh = warp_sum(hh) + gb;
       if (it == 0) { d0 = fabs(dv); if (dv >= 0) break; } else { if (dv < 0) lo = alpha; else hi = alpha; if (fabs(dv) <= 1e-10*d0) break; }
-      double an = alpha - dv/hh;
+      double an = alpha - dv*m_rcp(hh);
       if (it > 0 && (an <= lo || (hi > 0 && an >= hi))) an = hi > 0 ? 0.5*(lo+hi) : 2*alpha+1;
       if (an == alpha) break;
       alpha = an; }
