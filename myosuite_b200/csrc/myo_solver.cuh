@@ -58,7 +58,7 @@ __device__ void rows_apply(const DevModel& m, const Warp w, const double* x, dou
     for (int e = 0; e < q[4]; e++) { double xv = x[path[q[3]+e] >> 1]; n += J[3*e]*xv; t1 += J[3*e+1]*xv; t2 += J[3*e+2]*xv; }
     int rb = CROW(rn);
     if (nr == 1) out[rb] = n;
-    else { const double* P = pd + q[6]*PPAIR_STRIDE; double mu1 = P[2], mu2 = P[3]; out[rb] = n+mu1*t1; out[rb+1] = n-mu1*t1; out[rb+2] = n+mu2*t2; out[rb+3] = n-mu2*t2; } }
+    else { out[rb] = n+t1; out[rb+1] = n-t1; out[rb+2] = n+t2; out[rb+3] = n-t2; } }
 }
 
 // vec[d] += sum_r J[r][d] * wgt[r]  (wgt already includes D and the active mask; wgt is DESTROYED: the rows of a contact are folded into its
@@ -78,15 +78,15 @@ __device__ void rows_applyT_add(const DevModel& m, const Warp w, double* wgt, do
   for (int c = 0; c < ncon; c++) { const int rn = S_crown[c], nr = CNR(rn); if (!nr) continue;
     const idx_t* q = pr + PPAIR_ISTRIDE*S_cpair[c]; const double* J = S_conJ + c*3*m.maxpath; int rb = CROW(rn); double wn, w1 = 0, w2 = 0;
     if (nr == 1) wn = wgt[rb];
-    else { const double* P = pd + q[6]*PPAIR_STRIDE; wn = wgt[rb]+wgt[rb+1]+wgt[rb+2]+wgt[rb+3]; w1 = P[2]*(wgt[rb]-wgt[rb+1]); w2 = P[3]*(wgt[rb+2]-wgt[rb+3]); }
+    else { wn = wgt[rb]+wgt[rb+1]+wgt[rb+2]+wgt[rb+3]; w1 = wgt[rb]-wgt[rb+1]; w2 = wgt[rb+2]-wgt[rb+3]; }
     for (int e = w.lane; e < q[4]; e += 32) vec[path[q[3]+e] >> 1] += J[3*e]*wn + J[3*e+1]*w1 + J[3*e+2]*w2;
     __syncwarp(); } }
 }
 #else
   const idx_t* pr = CI(PPAIR); const double* pd = CD(PPAIR_d);
   for (int c = w.lane; c < ncon; c += 32) { const int rn = S_crown[c], nr = CNR(rn), rb = CROW(rn);      // fold the pyramid edges: (wn, w1, w2) into wgt[rb .. rb+2]
-    if (nr == 4) { const double* P = pd + pr[PPAIR_ISTRIDE*S_cpair[c] + 6]*PPAIR_STRIDE; const double a0 = wgt[rb], a1 = wgt[rb+1], a2 = wgt[rb+2], a3 = wgt[rb+3];
-      wgt[rb] = a0+a1+a2+a3; wgt[rb+1] = P[2]*(a0-a1); wgt[rb+2] = P[3]*(a2-a3); } }
+    if (nr == 4) { const double a0 = wgt[rb], a1 = wgt[rb+1], a2 = wgt[rb+2], a3 = wgt[rb+3];
+      wgt[rb] = a0+a1+a2+a3; wgt[rb+1] = a0-a1; wgt[rb+2] = a2-a3; } }
   __syncwarp();
   for (int d = w.lane; d < m.nv; d += 32) { double acc = 0; const unsigned long long below = (1ull << d) - 1;
     for (int c = 0; c < ncon; c++) { const unsigned long long mk = S_cmask[c];
@@ -158,16 +158,16 @@ __device__ void phase_constraints(const DevModel& m, const Warp w) {
     if (c < ncon) S_crown[c] = rb | (nr << 12) | (rank[s] << 16);
     if (c < ncon && nr) { const idx_t* q = pr + PPAIR_ISTRIDE*S_cpair[c]; const double* P = pd + q[6]*PPAIR_STRIDE; const double* cd = S_con + c*CON_STRIDE;
       const double* pos = cd + 1; double f[9]; for (int k = 0; k < 6; k++) f[k] = cd[4+k]; cross3(f+6, f, f+3); double* J = S_conJ + c*3*m.maxpath; double vn = 0, v1 = 0, v2 = 0;
-      unsigned long long mk = 0;
+      unsigned long long mk = 0; const double mu1 = P[2], mu2 = P[3];
       for (int e = 0; e < q[4]; e++) { int code = path[q[3]+e], d = code >> 1; double sg = (code & 1) ? 1.0 : -1.0, cv[3]; dof_point_vel(m, w, d, pos, cv); mk |= 1ull << d;
-        double jn = sg*dot3(f, cv), j1 = sg*dot3(f+3, cv), j2 = sg*dot3(f+6, cv); J[3*e] = jn; J[3*e+1] = j1; J[3*e+2] = j2;
+        double jn = sg*dot3(f, cv), j1 = sg*mu1*dot3(f+3, cv), j2 = sg*mu2*dot3(f+6, cv); J[3*e] = jn; J[3*e+1] = j1; J[3*e+2] = j2;      // tangents stored times mu: the pyramid edges are n +- mu t
         double qd = W_(qvel)[d]; vn += jn*qd; v1 += j1*qd; v2 += j2*qd; }
       S_cmask[c] = mk;
       double dist = cd[0], inc = P[0]-P[1], imp = impedance(P+7, dist, inc), K = P[5], B = P[6], tran = CD(PPAIR_tran)[S_cpair[c]];
       if (nr == 1) { double R = fmax(MYO_MINVAL, (1-imp)*tran*m_rcp(imp)); S_D[rb] = m_rcp(R); S_aref[rb] = -B*vn - K*imp*(dist-inc); }
-      else { double mu1 = P[2], mu2 = P[3]; double R0 = fmax(MYO_MINVAL, (1-imp)*(tran+mu1*mu1*tran)*m_rcp(imp)), Rpy = 2*mu1*mu1*R0, Dv = m_rcp(Rpy), kp = K*imp*(dist-inc);
+      else { double R0 = fmax(MYO_MINVAL, (1-imp)*(tran+mu1*mu1*tran)*m_rcp(imp)), Rpy = 2*mu1*mu1*R0, Dv = m_rcp(Rpy), kp = K*imp*(dist-inc);
         S_D[rb] = S_D[rb+1] = S_D[rb+2] = S_D[rb+3] = Dv;
-        S_aref[rb] = -B*(vn+mu1*v1)-kp; S_aref[rb+1] = -B*(vn-mu1*v1)-kp; S_aref[rb+2] = -B*(vn+mu2*v2)-kp; S_aref[rb+3] = -B*(vn-mu2*v2)-kp; } } }
+        S_aref[rb] = -B*(vn+v1)-kp; S_aref[rb+1] = -B*(vn-v1)-kp; S_aref[rb+2] = -B*(vn+v2)-kp; S_aref[rb+3] = -B*(vn-v2)-kp; } } }
   WI_(nefc) = rowbase;
   __syncwarp();
 }
@@ -419,11 +419,12 @@ __device__ void phase_solve(const DevModel& m, const Warp w, double tol, long lo
     // gradient does not pay here: with one H entry per lane nearly every contact hits SOME lane and the warp runs the hit path 9 x ncon times)
     for (int c = 0; c < ncon; c++) { const int rn = S_crown[c], nr = CNR(rn), rb = CROW(rn); if (!nr) continue; const idx_t* q = pr + PPAIR_ISTRIDE*S_cpair[c]; double W[6] = {0,0,0,0,0,0};  // nn n1 n2 11 12 22
       if (nr == 1) { if (S_jar[rb] < 0) W[0] = S_D[rb]; }
-      else { const double* P = pd + q[6]*PPAIR_STRIDE; double mu1 = P[2], mu2 = P[3], Dv = S_D[rb];
+      else { const double Dv = S_D[rb];
         double a0 = S_jar[rb] < 0 ? Dv : 0, a1 = S_jar[rb+1] < 0 ? Dv : 0, a2 = S_jar[rb+2] < 0 ? Dv : 0, a3 = S_jar[rb+3] < 0 ? Dv : 0;
-        W[0] = a0+a1+a2+a3; W[1] = mu1*(a0-a1); W[2] = mu2*(a2-a3); W[3] = mu1*mu1*(a0+a1); W[5] = mu2*mu2*(a2+a3); }
+        W[0] = a0+a1+a2+a3; W[1] = a0-a1; W[2] = a2-a3; W[3] = a0+a1; W[5] = a2+a3; }
       if (W[0] != 0) { const double* J = S_conJ + c*3*m.maxpath; int np = q[4], ntri = (np*(np+1)) >> 1;
-        for (int t = w.lane; t < ntri; t += 32) { int ei, ej; tri_index(t, ei, ej);
+        for (int t = w.lane; t < ntri; t += 32) { int ei, ej;
+          if (np <= 8) { ei = (t >= 1) + (t >= 3) + (t >= 6) + (t >= 10) + (t >= 15) + (t >= 21) + (t >= 28); ej = t - ((ei*(ei+1)) >> 1); } else tri_index(t, ei, ej);
           const double* a = J + 3*ei; const double* b = J + 3*ej;
           double wa0 = W[0]*a[0]+W[1]*a[1]+W[2]*a[2], wa1 = W[1]*a[0]+W[3]*a[1], wa2 = W[2]*a[0]+W[5]*a[2];
           int di = path[q[3]+ei] >> 1, dj = path[q[3]+ej] >> 1; S_H[TRI(di,dj)] += wa0*b[0]+wa1*b[1]+wa2*b[2]; } }
