@@ -16,6 +16,7 @@ MODEL_XML = {
     "myohand_hold": ("envs/myo/assets/hand/myohand_hold.xml", {}),
     # Walk moves the hfield terrain out of reach (walk_v0.py:262-266): compile without it
     "myolegs": ("simhive/myo_sim/leg/myolegs.xml", {"drop_geoms": ("terrain",)}),
+    "myotorso": ("simhive/myo_sim/torso/myotorso.xml", {}),
 }
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CACHE = {}

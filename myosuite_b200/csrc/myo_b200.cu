@@ -110,7 +110,7 @@ __device__ void write_obs_pose(const DevModel& m, const Warp w, const StepArgs& 
 // reward / done of the current state (pose_v0.py:113-140); lane 0 writes
 __device__ void pose_reward_done(const DevModel& m, const Warp w, const StepArgs& a, int env, double* rw_out, bool* done_out) {
   double dist, am; write_obs_pose(m, w, a, env, &dist, &am);
-  const double far_th = 4*3.14159265358979323846/2; double thd = a.cfg.pose_thd;
+  const double far_th = a.cfg.task_d[0] > 0 ? a.cfg.task_d[0] : 4*3.14159265358979323846/2; double thd = a.cfg.pose_thd;      // PoseEnvV0: 2 pi (pose_v0.py:117); TorsoEnvV0: pi (torso_v0.py:104), passed in task_d[0]
   *rw_out = a.cfg.weights[0]*(-dist) + a.cfg.weights[1]*((dist < thd ? 1.0 : 0.0)+(dist < 1.5*thd ? 1.0 : 0.0)) + a.cfg.weights[2]*(-am) + a.cfg.weights[3]*(dist > far_th ? -1.0 : 0.0);
   *done_out = dist > far_th; }
 

@@ -99,7 +99,7 @@ def reward_dict(task, obs_dict, weights, cfg):
     na = obs_dict["act"].shape[-1]
     act_mag = np.linalg.norm(obs_dict["act"], axis=-1) / na if na else 0.0
     if task == "pose":                                                     # pose_v0.py:113-140
-        d = np.linalg.norm(obs_dict["pose_err"], axis=-1); far_th = 4 * np.pi / 2; thd = cfg["pose_thd"]
+        d = np.linalg.norm(obs_dict["pose_err"], axis=-1); far_th = cfg.get("pose_far_th", 4 * np.pi / 2); thd = cfg["pose_thd"]      # TorsoEnvV0: far_th = pi (torso_v0.py:104)
         r = collections.OrderedDict((("pose", -1.0 * d), ("bonus", 1.0 * (d < thd) + 1.0 * (d < 1.5 * thd)), ("penalty", -1.0 * (d > far_th)), ("act_reg", -1.0 * act_mag),
                                      ("sparse", -1.0 * d), ("solved", d < thd), ("done", d > far_th)))
     elif task == "reach":                                                  # reach_v0.py:120-160

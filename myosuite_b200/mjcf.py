@@ -939,6 +939,8 @@ def _reach_sphere(m, geom):
                 if not m.jnt_limited[j]:
                     return None
                 reach += np.max(np.abs(m.jnt_range[j] - m.qpos0[m.jnt_qposadr[j]]))
+            # a hinge with an off-origin anchor swings the body origin on a circle of radius |jnt_pos| around the anchor
+            reach += 2.0 * np.linalg.norm(m.jnt_pos[j])
         reach += np.linalg.norm(m.body_pos[b])
         b = m.body_parentid[b]
     # b is static: its world pose at qpos0 is its pose always

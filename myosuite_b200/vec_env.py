@@ -68,10 +68,11 @@ class MyoVecEnv:
             self.max_episode_steps, kw, entry = env_spec(env_id)
         kw.update(overrides)
         self.kwargs = kw
-        self.task = ("none" if entry is None else "pose" if entry.endswith("pose_v0:PoseEnvV0") else "walk" if entry.endswith("walk_v0:WalkEnvV0")
+        self.torso = entry is not None and entry.endswith("torso_v0:TorsoEnvV0")        # TorsoEnvV0 = the pose task with a fixed mean-of-range target, far_th = pi, pose_thd 0.25
+        self.task = ("none" if entry is None else "pose" if (entry.endswith("pose_v0:PoseEnvV0") or self.torso) else "walk" if entry.endswith("walk_v0:WalkEnvV0")
                      else "hold" if "obj_hold_v0:ObjHold" in entry else "reach" if entry.endswith("reach_v0:ReachEnvV0") else None)
         if self.task is None:
-            raise NotImplementedError("device task for %s (%s) is not built yet (pose, walk, hold, reach are; MyoVecEnv.from_model gives physics only)" % (env_id, entry))
+            raise NotImplementedError("device task for %s (%s) is not built yet (pose, torso, walk, hold, reach are; MyoVecEnv.from_model gives physics only)" % (env_id, entry))
         self.hold_random = entry is not None and entry.endswith("ObjHoldRandomEnvV0")
         self.mj_model = m = model if model is not None else assets.load(_MODEL_OF_XML[kw["model_path"]])
         self.muscle_condition = kw.get("muscle_condition", "")
@@ -94,7 +95,9 @@ class MyoVecEnv:
         cfg.muscle_condition = abi.COND_FATIGUE if self.muscle_condition == "fatigue" else abi.COND_NONE
         cfg.auto_reset = int(bool(auto_reset))
         cfg.reset_random = int(kw.get("reset_type", "init") == "random")
-        cfg.pose_thd = float(kw.get("pose_thd", 0.35))
+        cfg.pose_thd = float(kw.get("pose_thd", 0.25 if self.torso else 0.35))         # pose_v0.py:43 / torso_v0.py:52
+        if self.torso:
+            cfg.task_d[0] = float(np.pi)                                                # far_th (torso_v0.py:104)
         init_qpos, init_qvel = np.asarray(m.qpos0, dtype=np.float64).copy(), np.zeros(m.nv)
         if self.task in ("pose", "none"):
             w = kw.get("weighted_reward_keys", {"pose": 1.0, "bonus": 4.0, "act_reg": 1.0, "penalty": 50})     # pose_v0.py:18-23
@@ -152,7 +155,7 @@ class MyoVecEnv:
         if kw.get("target_jnt_range"):
             for jn, (lo, hi) in kw["target_jnt_range"].items():
                 qa = m.jnt_qposadr[m.name2id("joint", jn)]
-                tr[qa] = (lo, hi)
+                tr[qa] = (0.5 * (lo + hi),) * 2 if self.torso else (lo, hi)     # TorsoEnvV0 never resamples: target = mean of the range (torso_v0.py:66-68)
         elif kw.get("target_jnt_value") is not None:
             v = np.asarray(kw["target_jnt_value"], dtype=np.float64)
             tr[:, 0] = tr[:, 1] = v
@@ -383,7 +386,9 @@ class MyoEnv:
     # ---- task constants for the host-side reward dict
     def _make_task_cfg(self):
         v, m, kw = self.vec, self.vec.mj_model, self.vec.kwargs
-        cfg = {"pose_thd": float(kw.get("pose_thd", 0.35)), "dt": v.dt, "ntip": self._ntip, "far_th": float(kw.get("far_th", 0.35))}
+        cfg = {"pose_thd": float(v.cfg.pose_thd), "dt": v.dt, "ntip": self._ntip, "far_th": float(kw.get("far_th", 0.35))}
+        if v.torso:
+            cfg["pose_far_th"] = float(np.pi)
         if v.task == "walk":
             cfg.update(target_x_vel=kw.get("target_x_vel", 0.0), target_y_vel=kw.get("target_y_vel", 1.2), min_height=kw.get("min_height", 0.8), max_rot=kw.get("max_rot", 0.8),
                        target_rot=np.asarray(kw.get("target_rot") if kw.get("target_rot") is not None else m.key_qpos[0][3:7], dtype=np.float64))
@@ -498,7 +503,7 @@ def register_gym():
     for eid in registered_ids():
         try:
             steps, _, entry = env_spec(eid)
-            if not any(entry.endswith(x) for x in ("pose_v0:PoseEnvV0", "walk_v0:WalkEnvV0", "reach_v0:ReachEnvV0")) and "obj_hold_v0:ObjHold" not in entry:
+            if not any(entry.endswith(x) for x in ("pose_v0:PoseEnvV0", "walk_v0:WalkEnvV0", "reach_v0:ReachEnvV0", "torso_v0:TorsoEnvV0")) and "obj_hold_v0:ObjHold" not in entry:
                 continue
             g.register(id=eid, entry_point="myosuite_b200.vec_env:MyoEnv", max_episode_steps=steps, kwargs={"env_id": eid})
             done.append(eid)

@@ -48,11 +48,11 @@ def pose_obs(qpos, qvel, act, target, dt):
     return np.concatenate([qpos, np.asarray(qvel) * dt, np.asarray(target) - qpos, act]).astype(np.float32)
 
 
-def pose_reward(qpos, act, target, pose_thd, weights=(1.0, 4.0, 1.0, 50.0)):
-    """/root/reference/myosuite/envs/myo/myobase/pose_v0.py:113-140 -> dict(dense, solved, done, pose, bonus, penalty, act_reg)."""
+def pose_reward(qpos, act, target, pose_thd, weights=(1.0, 4.0, 1.0, 50.0), far_th=4 * np.pi / 2):
+    """/root/reference/myosuite/envs/myo/myobase/pose_v0.py:113-140 -> dict(dense, solved, done, pose, bonus, penalty, act_reg).
+    TorsoEnvV0 (torso_v0.py:98-125) is the same rule with far_th = pi."""
     pose_dist = np.linalg.norm(np.asarray(target) - qpos)
     act_mag = np.linalg.norm(act) / (len(act) if len(act) else 1)
-    far_th = 4 * np.pi / 2
     r = dict(pose=-pose_dist, bonus=1.0 * (pose_dist < pose_thd) + 1.0 * (pose_dist < 1.5 * pose_thd), penalty=-1.0 * (pose_dist > far_th),
              act_reg=-act_mag, sparse=-pose_dist, solved=pose_dist < pose_thd, done=pose_dist > far_th)
     r["dense"] = weights[0] * r["pose"] + weights[1] * r["bonus"] + weights[2] * r["act_reg"] + weights[3] * r["penalty"]

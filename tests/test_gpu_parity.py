@@ -469,3 +469,54 @@ def test_regime_and_overflow_rate_on_rollouts(eid, n):
     assert rate_over < 1e-3
     # the product-path flag: sticky per env until its next reset
     assert int((env.t["overflow"] != 0).sum().item()) <= n * 0.05
+
+
+# ----------------------------------------------------------------------------- torso model / TorsoEnvV0 (myoTorsoPoseFixed-v0: 18 dof, 210 muscles, 15 joint couplings)
+def test_torso_task_golden_physics_parity_and_env_step():
+    import torch
+    from myosuite_b200 import vec_env
+    from oracle import env_oracle
+    from oracle.oracle_py import Oracle
+    T = np.load(os.path.join(os.path.dirname(__file__), "golden", "torso.npz"))
+    n = len(T["qpos"])
+    env = vec_env.MyoVecEnv("myoTorsoPoseFixed-v0", n, taps=True, auto_reset=False)
+    m = env.mj_model
+    assert (m.nq, m.nv, m.nu, env.obs_dim, env.max_episode_steps, env.n_frames) == (18, 18, 210, 264, 200, 5)
+    env.reset(seed=0)
+    np.testing.assert_allclose(env.t["target"][0].cpu().numpy(), T["target"], atol=0)           # target = mean of the registered ranges, never resampled
+    # (1) task logic on the device vs the reference's own TorsoEnvV0 outputs
+    env.set_state(qpos=T["qpos"], qvel=T["qvel"], act=T["act"])
+    env.refresh_obs(); torch.cuda.synchronize()
+    np.testing.assert_array_equal(env.t["obs"].cpu().numpy(), T["obs"])                       # float32, bit-exact
+    np.testing.assert_allclose(env.t["reward"].cpu().numpy(), T["dense"], rtol=3e-6, atol=3e-6)
+    np.testing.assert_array_equal(env.t["done"].cpu().numpy().astype(bool), T["done"].astype(bool))
+    # (2) physics: one forward pass and 5 chained substeps vs the oracle, on states inside the joint ranges
+    rng = np.random.default_rng(3)
+    qpos, qvel, act, ctrl = _states(m, n, rng, overshoot=0.02, vel=0.5)
+    env.set_state(qpos=qpos, qvel=qvel, act=act)
+    env.forward_debug(ctrl, 0); torch.cuda.synchronize()
+    t = {k: v.cpu().numpy().copy() for k, v in env.t.items() if k.startswith("tap_")}
+    o = Oracle(env.I, env.D)
+    for e in range(0, n, 3):
+        o.reset(); o.set(qpos=qpos[e], qvel=qvel[e], act=act[e], ctrl=ctrl[e]); o.forward()
+        assert relerr(t["tap_qacc"][e], o.f("qacc")) < RTOL
+        assert relerr(t["tap_actuator_force"][e], o.f("actuator_force")) < RTOL
+        assert relerr(t["tap_ten_length"][e], o.f("actuator_length")) < 1e-10
+        assert int(t["tap_ncon"][e, 1]) == o.nefc
+    env.set_state(qpos=qpos, qvel=qvel, act=act)
+    env.forward_debug(ctrl, 5); torch.cuda.synchronize()
+    gq = env.t["qpos"].cpu().numpy()
+    for e in range(0, n, 6):
+        o.reset(); o.set(qpos=qpos[e], qvel=qvel[e], act=act[e], ctrl=ctrl[e]); o.step(5)
+        np.testing.assert_allclose(gq[e], o.f("qpos"), rtol=0, atol=1e-8)
+    # (3) one full env step (sigmoid remap, 5 substeps, obs / reward) vs env_oracle
+    env.set_state(qpos=qpos, qvel=qvel, act=act); env.t["time"].zero_(); env.t["step_count"].zero_()
+    a = rng.uniform(-1, 1, (n, m.nu)).astype(np.float32)
+    obs, rew, done, trunc, _ = env.step(torch.as_tensor(a, device=env.device)); torch.cuda.synchronize()
+    obs, rew = obs.cpu().numpy(), rew.cpu().numpy()
+    for e in range(0, n, 6):
+        o.reset(); o.set(qpos=qpos[e], qvel=qvel[e], act=act[e])
+        env_oracle.env_step(o, a[e].astype(np.float64), env.n_frames)
+        np.testing.assert_allclose(obs[e], env_oracle.pose_obs(o.f("qpos"), o.f("qvel"), o.f("act"), T["target"], env.dt), rtol=2e-6, atol=2e-6)
+        r = env_oracle.pose_reward(o.f("qpos"), o.f("act"), T["target"], 0.25, far_th=np.pi)
+        assert rew[e] == pytest.approx(r["dense"], rel=1e-5, abs=1e-5)

@@ -118,3 +118,13 @@ def test_env_contract_like_reference_test_envs(env_id):
         k = list(env1.obs_keys).index("phase_var"); off = sum(np.size(env1.obs_dict[q]) for q in env1.obs_keys[:k])
         obs3 = obs3.copy(); obs3[off] = obs1[off]
     _assert_close(obs3, obs1, atol=1e-6)
+
+
+def test_torso_dicts_vs_reference_golden():
+    """TorsoEnvV0 (torso_v0.py:84-125): the pose rule with far_th = pi, pose_thd 0.25, target = mean of the registered ranges."""
+    z = np.load(os.path.join(G, "torso.npz"))
+    d = gym_api.obs_dict_from_vec("pose", z["obs"], np.zeros(len(z["obs"])), 18, 18, 210)
+    np.testing.assert_array_equal(d["pose_err"], (z["target"] - z["qpos"]).astype(np.float32))
+    r = gym_api.reward_dict("pose", d, {"pose": 1.0, "bonus": 4.0, "act_reg": 1.0, "penalty": 50, "done": 0}, {"pose_thd": 0.25, "pose_far_th": np.pi})
+    np.testing.assert_allclose(r["dense"], z["dense"], rtol=3e-6, atol=3e-6)
+    assert np.array_equal(np.asarray(r["done"], bool), z["done"].astype(bool)) and np.array_equal(np.asarray(r["solved"], bool), z["solved"].astype(bool))
