@@ -331,6 +331,12 @@ class MyoVecEnv:
         self.batch.observe(stream=self._stream())
         return self.t["obs"], self.t["reward"], self.t["done"]
 
+    def examine_policy(self, policy, horizon=None, mode="exploration", seed=None, generator=None, keep_obs=True):
+        """Batched MujocoEnv.examine_policy_new (env_base.py:853-969): one episode per env, observations / actions stay on the device;
+        returns (Trace with one "Trial<k>" group per env, summary dict).  See myosuite_b200/rollout.py."""
+        from . import rollout
+        return rollout.examine_policy(self, policy, horizon=horizon, mode=mode, seed=seed, generator=generator, keep_obs=keep_obs)
+
     def forward_debug(self, ctrl, n_substeps=0):
         c = self.torch.as_tensor(np.asarray(ctrl), dtype=self.torch.float64, device=self.device).contiguous()
         self._dbg_ctrl = c
@@ -483,6 +489,25 @@ class MyoEnv:
         self.__init__(env_id, seed=seed, device=device, **kwargs)
         self.input_seed = d["input_seed"]
         self.set_env_state(d["state"])
+
+    def examine_policy_new(self, policy, horizon=1000, num_episodes=1, mode="exploration", render=None, **kwargs):
+        """MujocoEnv.examine_policy_new (env_base.py:853-969) for the single env: `policy.get_action(obs)` as in mjrl, a Trace with one
+        "Trial<k>" group per episode (time, observations, actions, rewards, env_infos, done; NaN action in the last row).  No rendering."""
+        from .rollout import Trace
+        trace = Trace(str(self.env_id) + "_rollouts")
+        for ep in range(num_episodes):
+            g = "Trial" + str(ep); trace.create_group(g)
+            self.reset()
+            obs, rwd, done, env_info = self.forward()
+            t = 0
+            while t < horizon and done is False:
+                act = policy.get_action(obs)[0] if mode == "exploration" else policy.get_action(obs)[1]["evaluation"]
+                trace.append_datums(g, dict(time=self._last["time"], observations=obs, actions=np.asarray(act).copy(), rewards=rwd, env_infos=env_info, done=done))
+                obs, rwd, done, trunc, env_info = self.step(act)
+                t += 1
+            trace.append_datums(g, dict(time=self._last["time"], observations=obs, actions=np.nan * np.ones(self.action_space.shape), rewards=rwd, env_infos=env_info, done=done))
+        trace.stack()
+        return trace
 
     def close(self):
         pass
