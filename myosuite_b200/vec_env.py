@@ -68,6 +68,7 @@ class MyoVecEnv:
             self.max_episode_steps, kw, entry = env_spec(env_id)
         kw.update(overrides)
         self.kwargs = kw
+        self._check_kwargs(kw)
         self.torso = entry is not None and entry.endswith("torso_v0:TorsoEnvV0")        # TorsoEnvV0 = the pose task with a fixed mean-of-range target, far_th = pi, pose_thd 0.25
         self.task = ("none" if entry is None else "pose" if (entry.endswith("pose_v0:PoseEnvV0") or self.torso) else "walk" if entry.endswith("walk_v0:WalkEnvV0")
                      else "hold" if "obj_hold_v0:ObjHold" in entry else "reach" if entry.endswith("reach_v0:ReachEnvV0") else None)
@@ -180,6 +181,32 @@ class MyoVecEnv:
         self.t = t
         self.batch.bind(**t)
         self._h_action = None
+
+    # kwargs of the reference's env classes this backend implements; anything else with a non-default value is an error, not a silent no-op
+    _KNOWN = {"model_path", "normalize_act", "frame_skip", "muscle_condition", "reset_type", "target_type", "pose_thd", "weighted_reward_keys", "target_jnt_range",
+              "target_jnt_value", "viz_site_targets", "target_reach_range", "far_th", "min_height", "max_rot", "hip_period", "target_x_vel", "target_y_vel", "target_rot",
+              "obs_keys", "fatigue_reset_vec", "fatigue_reset_random", "weight_bodyname", "weight_range",
+              # backend knobs
+              "solver_tolerance", "maxcon", "barrier_mode", "lockstep_groups", "profile_waits"}
+
+    @staticmethod
+    def _check_kwargs(kw):
+        unknown = sorted(set(kw) - MyoVecEnv._KNOWN)
+        if unknown:
+            raise NotImplementedError("env kwargs not implemented by this backend: %s" % unknown)
+        bad = []
+        if kw.get("fatigue_reset_vec") is not None or kw.get("fatigue_reset_random"):
+            bad.append("fatigue_reset_vec / fatigue_reset_random (resets always start from MA = 0, MR = 1, MF = 0: fatigue.py:82-99 defaults)")
+        if kw.get("reset_type", "init") not in ("init", "random"):
+            bad.append("reset_type=%r (init and random are implemented)" % kw.get("reset_type"))
+        if kw.get("target_type", "generate") == "switch":
+            bad.append("target_type='switch'")
+        if kw.get("weight_bodyname") is not None or kw.get("weight_range") is not None:
+            bad.append("weight_bodyname / weight_range")
+        if kw.get("obs_keys") is not None:
+            bad.append("custom obs_keys (the observation layout is the task's DEFAULT_OBS_KEYS + act)")
+        if bad:
+            raise NotImplementedError("reference kwargs accepted by the reference but not by this backend: " + "; ".join(bad))
 
     # ---------------------------------------------------------------- task parameter blocks (indices into the kernel's dynamic-body list)
     def _dyn(self, body_name):
