@@ -304,17 +304,64 @@ __device__ __noinline__ void chol_reg32b(const double* H, int n, double* x, int 
   __syncwarp();
 }
 
-// padded order of the dense solver for an n x n system (the row-register variant is instantiated for these orders)
-// (exact orders exist for the hand, 23, and the hand + object, 29: every padded row costs shared memory)
+// The same L D L' with a ROLLED elimination loop: after column k is eliminated every lane shifts its row registers left by one (the shift is
+// folded into the destination of the update FMA), so the pivot column is r[0] at EVERY step and the loop body has static register
+// indices.  Why it matters: the unrolled variant above is ~2 500 straight-line instructions (40 KB) that every call streams from L2 at the
+// ~3.8 B/cycle the SM's instruction fetch sustains for uncached code (profiles/r02_ubench_icache.txt): 10.7 k cycles per solve inside
+// the step kernel against 5-7 k when the code is warm (tools/ubench/ubench_chol.cu).  The rolled body (~100 instructions) stays in the
+// instruction cache; it pays with FMAs on columns that are already finished (NMAX - 1 per step instead of n - 1 - k).
+// H: packed lower triangle, n rows (no padding needed: reads past the last row are clamped onto it and only feed dead slots); destroyed.
+template <int NMAX>
+__device__ __noinline__ void chol_rot(double* H, double* x, int n, int lane) {
+  SHARED_PTR(H); SHARED_PTR(x);
+  const bool own = lane < n; const int rowadr = own ? TRI(lane, 0) : 0;
+  double r[NMAX];
+  #pragma unroll
+  for (int j = 0; j < NMAX; j++) r[j] = (own && j <= lane) ? H[rowadr + j] : 0.0;
+  double b = own ? x[lane] : 0.0, invd_own = 1.0;
+  __syncwarp();
+  #pragma unroll 1
+  for (int k = 0; k < n; k++) {
+    if (own && lane >= k) H[rowadr + k] = r[0];      // column k, unscaled (U[i][k] = L[i][k] d_k); lane k: the pivot d_k
+    if (lane == k) x[k] = b;                         // z_k of the forward substitution is final
+    __syncwarp();
+    double col[NMAX-1];
+    { int row = k + 1 < n ? k + 1 : n - 1, adr = TRI(row, k);      // H[row][k], row = k+1 .. (clamped to n-1)
+      #pragma unroll
+      for (int j = 0; j < NMAX-1; j++) { col[j] = H[adr]; const bool more = row + 1 < n; adr += more ? row + 1 : 0; row += more ? 1 : 0; } }
+    const double dk = H[TRI(k,k)], zk = x[k];
+    asm volatile("" ::: "memory");
+    const double invd = m_rcp(fmax(dk, MYO_MINVAL));
+    if (lane == k) invd_own = invd;
+    const double t = r[0]*invd;                      // L[lane][k] on lanes > k
+    b = lane > k ? fma(-t, zk, b) : b;
+    #pragma unroll
+    for (int j = 0; j < NMAX-1; j++) r[j] = fma(-t, col[j], r[j+1]);      // eliminate AND shift: column k+1 becomes r[0]
+    r[NMAX-1] = 0.0;
+  }
+  // backward substitution: u_i = z_i - sum_{k>i} U[k][i] x_k ; x_i = u_i / d_i
+  #pragma unroll 1
+  for (int k = n-1; k >= 0; k--) { const double xk = __shfl_sync(FULL, b*invd_own, k), hk = (own && lane < k) ? H[TRI(k,0) + lane] : 0.0; b = fma(-hk, xk, b); }
+  __syncwarp();
+  if (own) x[lane] = b*invd_own;
+  __syncwarp();
+}
+
+// padded order of the dense solver for an n x n system (kept for the layout of H and of the solver vectors; the rolled solver needs no padding)
 __host__ __device__ __forceinline__ int chol_pad(int n) { return n > 32 ? n : (n <= 8 ? 8 : (n == 23 || n == 29 ? n : (n + 3) & ~3)); }
-// x <- H^-1 x for a dense SPD H (packed lower triangle in shared memory, padded to chol_pad(n) rows with identity); H is destroyed
+// x <- H^-1 x for a dense SPD H (packed lower triangle in shared memory); H is destroyed
 __device__ __forceinline__ void chol_dense(double* H, int n, double* x, int lane) {
   if (n > 36) { chol_factor_rows(H, n, lane); chol_solve(H, n, x, lane); return; }
   if (n > 32) { chol_reg32b<4>(H, n, x, lane); return; }
+#ifdef MYO_CHOL_UNROLLED
   switch (chol_pad(n)) {
     case 8: chol_rs<8>(H, x, n, lane); break;   case 12: chol_rs<12>(H, x, n, lane); break; case 16: chol_rs<16>(H, x, n, lane); break;
     case 20: chol_rs<20>(H, x, n, lane); break; case 24: chol_rs<24>(H, x, n, lane); break; case 28: chol_rs<28>(H, x, n, lane); break;
-    case 23: chol_rs<23>(H, x, n, lane); break; case 29: chol_rs<29>(H, x, n, lane); break; default: chol_rs<32>(H, x, n, lane); break; } }
+    case 23: chol_rs<23>(H, x, n, lane); break; case 29: chol_rs<29>(H, x, n, lane); break; default: chol_rs<32>(H, x, n, lane); break; }
+#else
+  if (n <= 16) chol_rot<16>(H, x, n, lane); else if (n <= 24) chol_rot<24>(H, x, n, lane); else chol_rot<32>(H, x, n, lane);
+#endif
+}
 
 // H <- M (+ diag_scale * damping on the diagonal), dense packed lower triangle padded with identity rows up to chol_pad(nv)
 __device__ __forceinline__ void load_M_dense(const DevModel& m, const Warp w, double* H, double diag_scale /* h */) {
