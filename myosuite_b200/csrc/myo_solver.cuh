@@ -310,6 +310,9 @@ __device__ __noinline__ void chol_reg32b(const double* H, int n, double* x, int 
 // ~3.8 B/cycle the SM's instruction fetch sustains for uncached code (profiles/r02_ubench_icache.txt): 10.7 k cycles per solve inside
 // the step kernel against 5-7 k when the code is warm (tools/ubench/ubench_chol.cu).  The rolled body (~100 instructions) stays in the
 // instruction cache; it pays with FMAs on columns that are already finished (NMAX - 1 per step instead of n - 1 - k).
+// MEASURED (round 2, tools/ubench/ubench_chol.cu and the step kernel): 27.6 k cycles per 23 x 23 solve with 10 warps per SM against 7.0 k
+// for the unrolled variant (30 k vs 10.7 k inside the step kernel) -- the clamped address chain and the dead-column FMAs cost far more than
+// the instruction fetch they save.  Kept as an experiment behind MYO_CHOL_ROLLED; the unrolled variant is the product path.
 // H: packed lower triangle, n rows (no padding needed: reads past the last row are clamped onto it and only feed dead slots); destroyed.
 template <int NMAX>
 __device__ __noinline__ void chol_rot(double* H, double* x, int n, int lane) {
@@ -353,7 +356,7 @@ __host__ __device__ __forceinline__ int chol_pad(int n) { return n > 32 ? n : (n
 __device__ __forceinline__ void chol_dense(double* H, int n, double* x, int lane) {
   if (n > 36) { chol_factor_rows(H, n, lane); chol_solve(H, n, x, lane); return; }
   if (n > 32) { chol_reg32b<4>(H, n, x, lane); return; }
-#ifdef MYO_CHOL_UNROLLED
+#ifndef MYO_CHOL_ROLLED
   switch (chol_pad(n)) {
     case 8: chol_rs<8>(H, x, n, lane); break;   case 12: chol_rs<12>(H, x, n, lane); break; case 16: chol_rs<16>(H, x, n, lane); break;
     case 20: chol_rs<20>(H, x, n, lane); break; case 24: chol_rs<24>(H, x, n, lane); break; case 28: chol_rs<28>(H, x, n, lane); break;
