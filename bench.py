@@ -57,12 +57,42 @@ def usable_cores():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """SM clock and throttle reasons DURING the timed region: NVML polled from a thread every few ms (the timed region of the default run is
+    only ~0.1 s, shorter than nvidia-smi's start-up); falls back to an `nvidia-smi -lms` child when NVML cannot be loaded."""
+    _BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))      # nvmlClocksThrottleReason* / ClocksEventReason*
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.h, self.run, self.thread, self.max_mhz = [], None, index, None, False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.h = None
+
+    def _poll(self):
+        nv = self.nv
+        while self.run:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((mhz, bits))
+            except Exception:
+                pass
+            time.sleep(0.004)
 
     def start(self):
+        if self.h is not None:
+            self.run = True
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
@@ -76,6 +106,13 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.h is not None:
+            self.run = False
+            if self.thread:
+                self.thread.join(timeout=1.0)
+            sm = sorted(r[0] for r in self.rows)
+            reasons = sorted(name for name, bit in self._BITS if any(r[1] & bit for r in self.rows))
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm), "source": "nvml"}
         if self.proc:
             self.proc.terminate()
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
@@ -85,7 +122,7 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def _cpu_worker(args):
@@ -176,6 +213,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip config.extra (the other BASELINE configs, the U(0,1) variant, the sustained run)")
     ap.add_argument("--no-l2-flush", action="store_true", help="do not evict L2 between timed steps (default: a 192 MiB write per step)")
+    ap.add_argument("--maxcon", type=int, default=0, help="contact capacity per env (0 = library default 32); experiments only")
     ap.add_argument("--barrier-mode", type=int, default=0)
     ap.add_argument("--lockstep-groups", type=int, default=0)
     ap.add_argument("--solver-tolerance", type=float, default=0.0, help="Newton stop (scaled gradient); 0 = library default")
@@ -218,7 +256,7 @@ def main():
         return [float(x) for x in t]
 
     def make(env_id, n):
-        env = vec_env.MyoVecEnv(env_id, n, device=local_rank, seed=0, env_offset=rank * n, barrier_mode=args.barrier_mode, lockstep_groups=args.lockstep_groups, solver_tolerance=args.solver_tolerance)
+        env = vec_env.MyoVecEnv(env_id, n, device=local_rank, seed=0, env_offset=rank * n, barrier_mode=args.barrier_mode, lockstep_groups=args.lockstep_groups, solver_tolerance=args.solver_tolerance, maxcon=args.maxcon)
         env.reset(seed=0)
         return env
 

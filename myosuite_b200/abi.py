@@ -52,57 +52,74 @@ def lib_path():
     return _build.LIB
 
 
-def lib():
+def lib(variant=None):
+    """The product library, or (variant="f64rows") the verification build of the same source whose contact rows are stored in f64."""
     global _LIB
+    if variant:
+        if variant not in _VARIANTS:
+            if variant not in _build.VARIANTS:
+                raise MyoError("unknown library variant %r" % (variant,))
+            path = _build.variant_path(variant)
+            if not os.path.exists(path):          # (mtimes do not survive the snapshot to a GPU box: existence only, like the product library)
+                path = _build.build_variant(variant, _build.VARIANTS[variant])
+            _VARIANTS[variant] = _bind(ctypes.CDLL(path))
+        return _VARIANTS[variant]
     if _LIB is None:
         path = os.environ.get("MYO_B200_LIB") or _build.LIB      # MYO_B200_LIB: a variant build (developer experiments)
         if not os.path.exists(path):
             path = _build.build()
-        L = ctypes.CDLL(path)
-        L.myo_last_error.restype = ctypes.c_char_p
-        L.myo_model_from_blob.argtypes = [c_vp, c_i64, c_vp, c_i64, ctypes.POINTER(c_vp)]
-        L.myo_model_dims.argtypes = [c_vp, ctypes.POINTER(MyoTaskCfg), ctypes.POINTER(MyoDims)]
-        L.myo_model_destroy.argtypes = [c_vp]
-        L.myo_model_destroy.restype = None
-        L.myo_batch_create.argtypes = [c_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(MyoTaskCfg), ctypes.POINTER(c_vp)]
-        L.myo_batch_bind.argtypes = [c_vp, ctypes.POINTER(MyoBuffers)]
-        L.myo_batch_destroy.argtypes = [c_vp]
-        L.myo_batch_destroy.restype = None
-        L.myo_batch_obs_dim.argtypes = [c_vp]
-        L.myo_batch_reset.argtypes = [c_vp, c_vp, c_u64, c_i64, c_vp]
-        L.myo_batch_step.argtypes = [c_vp, c_vp]
-        L.myo_batch_observe.argtypes = [c_vp, c_vp]
-        L.myo_batch_forward_debug.argtypes = [c_vp, c_vp, ctypes.c_int, c_vp]
-        L.myo_batch_launch_count.argtypes = [c_vp]
-        L.myo_batch_launch_count.restype = c_i64
-        L.myo_debug_chol_solve.argtypes = [ctypes.c_int, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
-        _LIB = L
+        _LIB = _bind(ctypes.CDLL(path))
     return _LIB
 
 
-def _check(rc):
+_VARIANTS = {}
+
+
+def _bind(L):
+    L.myo_last_error.restype = ctypes.c_char_p
+    L.myo_model_from_blob.argtypes = [c_vp, c_i64, c_vp, c_i64, ctypes.POINTER(c_vp)]
+    L.myo_model_dims.argtypes = [c_vp, ctypes.POINTER(MyoTaskCfg), ctypes.POINTER(MyoDims)]
+    L.myo_model_destroy.argtypes = [c_vp]
+    L.myo_model_destroy.restype = None
+    L.myo_batch_create.argtypes = [c_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(MyoTaskCfg), ctypes.POINTER(c_vp)]
+    L.myo_batch_bind.argtypes = [c_vp, ctypes.POINTER(MyoBuffers)]
+    L.myo_batch_destroy.argtypes = [c_vp]
+    L.myo_batch_destroy.restype = None
+    L.myo_batch_obs_dim.argtypes = [c_vp]
+    L.myo_batch_reset.argtypes = [c_vp, c_vp, c_u64, c_i64, c_vp]
+    L.myo_batch_step.argtypes = [c_vp, c_vp]
+    L.myo_batch_observe.argtypes = [c_vp, c_vp]
+    L.myo_batch_forward_debug.argtypes = [c_vp, c_vp, ctypes.c_int, c_vp]
+    L.myo_batch_launch_count.argtypes = [c_vp]
+    L.myo_batch_launch_count.restype = c_i64
+    L.myo_debug_chol_solve.argtypes = [ctypes.c_int, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    return L
+
+
+def _check(rc, L=None):
     if rc != 0:
-        raise MyoError(lib().myo_last_error().decode())
+        raise MyoError((L or lib()).myo_last_error().decode())
 
 
 class DeviceModel:
     """Host handle of a packed model (myo_model*)."""
 
-    def __init__(self, I, D):
+    def __init__(self, I, D, variant=None):
         self.I = np.ascontiguousarray(I, dtype=np.int32)
         self.D = np.ascontiguousarray(D, dtype=np.float64)
+        self.L = lib(variant)
         h = c_vp()
-        _check(lib().myo_model_from_blob(self.I.ctypes.data, self.I.size, self.D.ctypes.data, self.D.size, ctypes.byref(h)))
+        _check(self.L.myo_model_from_blob(self.I.ctypes.data, self.I.size, self.D.ctypes.data, self.D.size, ctypes.byref(h)), self.L)
         self.handle = h
 
     def dims(self, cfg=None):
         d = MyoDims()
-        _check(lib().myo_model_dims(self.handle, ctypes.byref(cfg) if cfg is not None else None, ctypes.byref(d)))
+        _check(self.L.myo_model_dims(self.handle, ctypes.byref(cfg) if cfg is not None else None, ctypes.byref(d)), self.L)
         return d
 
     def __del__(self):
         if getattr(self, "handle", None):
-            lib().myo_model_destroy(self.handle)
+            self.L.myo_model_destroy(self.handle)
             self.handle = None
 
 
@@ -110,15 +127,15 @@ class Batch:
     """myo_batch*: n_env envs of one model on one CUDA device, driven through bound torch tensors."""
 
     def __init__(self, model, device, n_env, cfg):
-        self.model, self.cfg, self.n_env, self.device = model, cfg, n_env, device
+        self.model, self.cfg, self.n_env, self.device, self.L = model, cfg, n_env, device, model.L
         h = c_vp()
-        _check(lib().myo_batch_create(model.handle, device, n_env, ctypes.byref(cfg), ctypes.byref(h)))
+        _check(self.L.myo_batch_create(model.handle, device, n_env, ctypes.byref(cfg), ctypes.byref(h)), self.L)
         self.handle = h
         self.tensors = {}
 
     @property
     def obs_dim(self):
-        return lib().myo_batch_obs_dim(self.handle)
+        return self.L.myo_batch_obs_dim(self.handle)
 
     def bind(self, **tensors):
         """tensors: name -> torch CUDA tensor (contiguous) for the fields of myo_buffers."""
@@ -132,27 +149,27 @@ class Batch:
             if not t.is_contiguous():
                 raise ValueError("%s must be contiguous" % k)
             setattr(b, k, t.data_ptr())
-        _check(lib().myo_batch_bind(self.handle, ctypes.byref(b)))
+        _check(self.L.myo_batch_bind(self.handle, ctypes.byref(b)), self.L)
 
     def reset(self, mask=None, seed=0, env_offset=0, stream=None):
-        _check(lib().myo_batch_reset(self.handle, mask.data_ptr() if mask is not None else None, seed, env_offset, stream))
+        _check(self.L.myo_batch_reset(self.handle, mask.data_ptr() if mask is not None else None, seed, env_offset, stream), self.L)
 
     def step(self, stream=None):
-        _check(lib().myo_batch_step(self.handle, stream))
+        _check(self.L.myo_batch_step(self.handle, stream), self.L)
 
     def observe(self, stream=None):
-        _check(lib().myo_batch_observe(self.handle, stream))
+        _check(self.L.myo_batch_observe(self.handle, stream), self.L)
 
     def forward_debug(self, ctrl, n_substeps=0, stream=None):
-        _check(lib().myo_batch_forward_debug(self.handle, ctrl.data_ptr(), n_substeps, stream))
+        _check(self.L.myo_batch_forward_debug(self.handle, ctrl.data_ptr(), n_substeps, stream), self.L)
 
     @property
     def launches(self):
-        return lib().myo_batch_launch_count(self.handle)
+        return self.L.myo_batch_launch_count(self.handle)
 
     def __del__(self):
         if getattr(self, "handle", None):
-            lib().myo_batch_destroy(self.handle)
+            self.L.myo_batch_destroy(self.handle)
             self.handle = None
 
 

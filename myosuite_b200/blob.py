@@ -96,10 +96,18 @@ def _raw_arrays(m):
     return a
 
 
+# double tables the kernels read straight from HBM / L2 instead of the shared-memory copy: each is touched once per substep (or once per
+# stored contact) by lane-parallel, independent loads, so the latency is paid once per phase -- and the 20 KB they free per CTA is what
+# lets 14 env-warps of the hand model share one SM with f64-grade constraint rows.  They sit at the END of HOT_D; HOT_off[len(SECTIONS)]
+# is the number of doubles that ARE staged.
+COLD_D = ["PWE_d", "PPT_xyz", "PPAIR_tran", "PLIM_d", "PAM_d", "PA_d"]
+
+
 def _hot_pack(arrays):
     kinds = dict(SECTIONS)
     names = KERNEL_RAW + [n for n, _ in PROGRAM_SECTIONS if not n.startswith("HOT_") and n != "P_dims"]
-    i16, dd, off = [], [], np.full(len(SECTIONS), -1, dtype=np.int64)
+    names = [n for n in names if n not in COLD_D] + [n for n in names if n in COLD_D]
+    i16, dd, off = [], [], np.full(len(SECTIONS) + 1, -1, dtype=np.int64)
     ni = nd = 0
     for n in names:
         a = np.asarray(arrays.get(n, np.zeros(0)))
@@ -110,6 +118,10 @@ def _hot_pack(arrays):
             off[SEC_ID[n]] = ni
             i16.append(v.astype(np.int16)); ni += v.size
         else:
+            if n in COLD_D and off[len(SECTIONS)] < 0:
+                if nd % 2:
+                    dd.append(np.zeros(1)); nd += 1                        # staged part: a 16-byte multiple (bulk-copy granularity)
+                off[len(SECTIONS)] = nd
             v = a.astype(np.float64).ravel()
             off[SEC_ID[n]] = nd
             dd.append(v); nd += v.size

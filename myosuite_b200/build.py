@@ -11,8 +11,18 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC"]
 
 
-def needs_build():
-    return (not os.path.exists(LIB)) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in DEPS)
+# Verification builds of the same source (loaded by abi.lib(variant)); "f64rows": contact Jacobian rows and regularisers stored in f64
+# instead of f32 -- the parity tests run both, so that storage rounding and algorithmic agreement are measured separately.
+VARIANTS = {"f64rows": ["MYO_F64_ROWS"]}
+
+
+def variant_path(tag):
+    return os.path.join(HERE, "libmyo_b200_%s.so" % tag)
+
+
+def needs_build(lib=None):
+    lib = lib or LIB
+    return (not os.path.exists(lib)) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in DEPS)
 
 
 def build(force=False, verbose=False):
@@ -25,10 +35,19 @@ def build(force=False, verbose=False):
 
 
 def build_variant(tag, defines, verbose=False):
-    """Developer aid: libmyo_b200_<tag>.so with extra -D flags (register-budget experiments; selected at run time by MYO_B200_LIB)."""
+    """libmyo_b200_<tag>.so with extra -D flags (VARIANTS above; also register-budget experiments selected at run time by MYO_B200_LIB)."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    out = os.path.join(HERE, "libmyo_b200_%s.so" % tag)
+    out = variant_path(tag)
     subprocess.check_call([nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, SRC])
+    return out
+
+
+def build_all(force=False):
+    out = [build(force=force)]
+    for tag, defs in VARIANTS.items():
+        if force or needs_build(variant_path(tag)):
+            build_variant(tag, defs)
+        out.append(variant_path(tag))
     return out
 
 

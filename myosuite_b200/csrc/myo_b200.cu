@@ -146,9 +146,9 @@ __device__ void walk_observe(const DevModel& m, const Warp w, const StepArgs& a,
       o[base+6] = (float)pl[2]; o[base+7] = (float)pr_[2]; o[base+8] = (float)height;
       for (int c = 0; c < 3; c++) { o[base+9+c] = (float)(pl[c]-pp[c]); o[base+12+c] = (float)(pr_[c]-pp[c]); }
       o[base+15] = (float)phase; }
-    const idx_t* at = CI(PA_tendon); const double* PAm = CD(PAM_d); const double* tlen = SCR(s_tlen); const double* tvel = SCR(s_tvel); const double* tfrc = SCR(s_tfrc);
+    const idx_t* at = CI(PA_tendon); const double* __restrict__ PAm = GD(PAM_d); const double* tlen = SCR(s_tlen); const double* tvel = SCR(s_tvel); const double* tfrc = SCR(s_tfrc);
     int mb = base + 16;
-    for (int i = w.lane; i < m.nu; i += 32) { double gear = PAm[i*PAM_STRIDE+4]; int t = at[i];
+    for (int i = w.lane; i < m.nu; i += 32) { double gear = LDC(PAm + i*PAM_STRIDE + 4); int t = at[i];
       o[mb+i] = (float)(gear*tlen[t]); o[mb+m.nu+i] = (float)clipd(gear*tvel[t], -100, 100); o[mb+2*m.nu+i] = (float)clipd(tfrc[t]/gear/1000.0, -100, 100);
       o[mb+3*m.nu+i] = (float)W_(act)[i]; } }
   // rewards
@@ -201,7 +201,7 @@ struct RwDone { double rw; int done; };   // returned by value (registers), not 
 __device__ __noinline__ RwDone task_observe(const DevModel& m, const Warp w, const StepArgs& a, int env, int steps, double tnow) {
   double rw = 0; bool done = false;
   if (a.cfg.task == MYO_TASK_POSE) pose_reward_done(m, w, a, env, &rw, &done);
-  else if (a.cfg.task == MYO_TASK_WALK) { phase_kinematics(m, w); phase_tendon(m, w); phase_tendon_moments(m, w); phase_actuation(m, w, false, nullptr, nullptr); walk_observe(m, w, a, env, steps, &rw, &done); }
+  else if (a.cfg.task == MYO_TASK_WALK) { phase_kinematics(m, w); phase_tendon_all(m, w); phase_actuation(m, w, false, m.g_ctrl + (size_t)env*m.nu, nullptr, nullptr); walk_observe(m, w, a, env, steps, &rw, &done); }
   else if (a.cfg.task == MYO_TASK_HOLD) { phase_kinematics(m, w); hold_observe(m, w, a, env, &rw, &done); }
   else if (a.cfg.task == MYO_TASK_REACH) { phase_kinematics(m, w); reach_observe(m, w, a, env, tnow, &rw, &done); }
   __syncwarp();
@@ -269,14 +269,14 @@ __device__ __forceinline__ void env_kernel_body(const DevModel& m, const StepArg
         { const RwDone rd = task_observe(m, w, a, env, b.step_count ? b.step_count[env] : 0, b.time ? b.time[env] : 0.0);
           if (w.lane == 0) { if (b.reward) b.reward[env] = (float)rd.rw; if (b.done) b.done[env] = rd.done != 0; } }
       } else if (DBG && a.mode == 1) {
-        for (int i = w.lane; i < m.nu; i += 32) W_(ctrl)[i] = a.dbg_ctrl[(size_t)env*m.nu+i];
+        for (int i = w.lane; i < m.nu; i += 32) m.g_ctrl[(size_t)env*m.nu+i] = a.dbg_ctrl[(size_t)env*m.nu+i];
       } else if (a.mode == 0) {
         // ---- action -> ctrl  (base_v0.py:83-96); fatigue (fatigue.py:38-76)
         for (int i = w.lane; i < m.nu; i += 32) { double c = (double)b.action[(size_t)env*m.nu+i];
           if (a.cfg.reaf_dst != a.cfg.reaf_src && i == a.cfg.reaf_dst) c = (double)b.action[(size_t)env*m.nu+a.cfg.reaf_src];
           if (a.cfg.normalize_act) c = 1.0/(1.0+exp(-5.0*(c-0.5)));
           if (a.cfg.reaf_dst != a.cfg.reaf_src && i == a.cfg.reaf_src) c = 0.0;
-          if (a.cfg.muscle_condition == MYO_COND_FATIGUE && b.fatigue) { double* F = b.fatigue + (size_t)env*3*m.nu; const double* PA = CD(PA_d) + CI(PA_cls)[i]*PA_STRIDE;
+          if (a.cfg.muscle_condition == MYO_COND_FATIGUE && b.fatigue) { double* F = b.fatigue + (size_t)env*3*m.nu; const double* __restrict__ PAg = GD(PA_d) + CI(PA_cls)[i]*PA_STRIDE; const double PA[2] = {LDC(PAg), LDC(PAg + 1)};
             double MA = F[i], MR = F[m.nu+i], MF = F[2*m.nu+i], TL = c, fdt = a.dt, tauact = PA[0], taudeact = PA[1];
             const double r = 10*15, Fc = 0.00912, Rc = 0.1*0.00094;
             double LD = 1.0/tauact*(0.5+1.5*MA), LR = (0.5+1.5*MA)/taudeact, C = 0;
@@ -288,7 +288,7 @@ __device__ __forceinline__ void env_kernel_body(const DevModel& m, const StepArg
             C = fmin(fmax(C, lo), hi);   // np.clip(C, lo, hi) == minimum(maximum(C, lo), hi)
             double dMA = (C-Fc*MA)*fdt, dMR = (-C+rR*MF)*fdt, dMF = (Fc*MA-rR*MF)*fdt;
             MA += dMA; MR += dMR; MF += dMF; F[i] = MA; F[m.nu+i] = MR; F[2*m.nu+i] = MF; c = MA; }
-          W_(ctrl)[i] = c; }
+          m.g_ctrl[(size_t)env*m.nu+i] = c; }       // ctrl row in global memory (same lane re-reads it in every substep's actuation phase)
       }
       __syncwarp();
     }
@@ -304,12 +304,12 @@ __device__ __forceinline__ void env_kernel_body(const DevModel& m, const StepArg
     for (int s = 0; s < nsub; s++) {
       const bool tap = DBG && s == nsub-1;
       PH(0, phase_kinematics(m, w));
-      PH(1, phase_tendon(m, w); phase_tendon_moments(m, w); if (tap && b.tap_moment) { const double* mom = SCR(s_mom); for (int i = w.lane; i < m.nnz; i += 32) b.tap_moment[(size_t)env*m.nnz+i] = mom[i]; });
-      PH(2, phase_actuation(m, w, integrate, tap && b.tap_actuator_force ? b.tap_actuator_force + (size_t)env*m.nu : nullptr, tap && b.tap_ten_length ? b.tap_ten_length + (size_t)env*m.nu : nullptr));
+      PH(1, phase_tendon_all(m, w); if (tap && b.tap_moment) { const double* mom = SCR(s_mom); for (int i = w.lane; i < m.nnz; i += 32) b.tap_moment[(size_t)env*m.nnz+i] = mom[i]; });
+      PH(2, phase_actuation(m, w, integrate, m.g_ctrl + (size_t)env*m.nu, tap && b.tap_actuator_force ? b.tap_actuator_force + (size_t)env*m.nu : nullptr, tap && b.tap_ten_length ? b.tap_ten_length + (size_t)env*m.nu : nullptr));
       PH(3, phase_body_inertia(m, w); phase_crb(m, w); phase_bias(m, w));
       PH(4, phase_collision(m, w); overflow_seen |= WI_(overflow));
       PH(5, phase_constraints(m, w); if (tap) write_taps_contacts(m, w, a, env));
-      if (ngroups == 1 && m.solve_sync) {   // every warp enters the solver: its inner CTA barriers need the idle warps too
+      if (ngroups == 1 && (!DBG || m.solve_sync)) {   // every warp enters the solver: its inner CTA barriers need the idle warps too (the unaligned variant is a debug-kernel experiment)
         long long tb_ = prof ? clock64() : 0; if (bmask & (1 << 6)) __syncthreads(); long long t0_ = prof ? clock64() : 0;
         phase_solve(m, w, a.tol, (prof && live) ? cyc : nullptr, live, true);
         if (prof) cyc[6] += waitprof ? t0_ - tb_ : clock64() - t0_;
@@ -360,6 +360,16 @@ __device__ __forceinline__ void env_kernel_body(const DevModel& m, const StepArg
 #define MYO_LB __launch_bounds__(320)
 #endif
 extern "C" __global__ void MYO_LB myo_env_kernel(const __grid_constant__ DevModel m, const __grid_constant__ StepArgs a) { env_kernel_body<false, 320>(m, a); }
+// the same product body under launch_bounds(448): 128 registers for the entry function, up to 14 env-warps per CTA.  Chosen when the model's
+// shared-memory footprint lets that many warps cut the number of rounds (hand, 4096 envs: 2 rounds of 14 instead of 3 of 10).
+#ifndef MYO_EXPERIMENT_NO_W14
+#ifndef MYO_W14_REGS
+#define MYO_W14_REGS 144
+#endif
+extern "C" __global__ void __launch_bounds__(448) myo_env_kernel_w14(const __grid_constant__ DevModel m, const __grid_constant__ StepArgs a) { env_kernel_body<false, 448>(m, a); }
+#else
+#define myo_env_kernel_w14 myo_env_kernel
+#endif
 // parity taps / forward-debug / profiling counters / tuning knobs
 #ifndef MYO_EXPERIMENT_NO_DBG     // (compile-time experiments build the product kernel only)
 extern "C" __global__ void __launch_bounds__(320) myo_env_kernel_dbg(const __grid_constant__ DevModel m, const __grid_constant__ StepArgs a) { env_kernel_body<true, 320>(m, a); }
@@ -373,8 +383,8 @@ static int fail(const std::string& s) { g_err = s; return -1; }
 #define CUDA_OK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
 
 struct myo_model { std::vector<int32_t> I; std::vector<double> D; };
-struct myo_batch { const myo_model* model; int device, n_env; myo_task_cfg cfg; myo_buffers bufs; bool bound; DevModel dm; int32_t* dI; double* dD; int const_bytes;
-  int warps_per_cta, grid, smem_bytes, obs_dim; bool force_dbg; long long launches; unsigned long long seed; long long env_offset; };
+struct myo_batch { const myo_model* model; int device, n_env; myo_task_cfg cfg; myo_buffers bufs; bool bound; DevModel dm; int32_t* dI; double* dD; double* dCtrl; int const_bytes;
+  int warps_per_cta, grid, smem_bytes, obs_dim; int dbg_warps, dbg_grid, dbg_smem; bool use_w14; bool force_dbg; long long launches; unsigned long long seed; long long env_offset; };
 
 extern "C" const char* myo_last_error(void) { return g_err.c_str(); }
 extern "C" int myo_version(void) { return 1; }
@@ -384,7 +394,7 @@ extern "C" int myo_model_from_blob(const int32_t* I, int64_t nI, const double* D
   if (I[0] != MYO_BLOB_MAGIC || I[1] != MYO_BLOB_VERSION || I[2] != MYO_NDIM || I[3] != MYO_NSEC) return fail("myo_model_from_blob: blob magic/version/layout mismatch");
   for (int s = 0; s < MYO_NSEC; s++) { long long off = MYO_SEC_OFF(I, s), len = MYO_SEC_LEN(I, s); int kind = I[MYO_BLOB_HDR+MYO_NDIM+3*s];
     if (off < 0 || len < 0 || off + len > (kind ? nD : nI)) return fail("myo_model_from_blob: section out of range"); }
-  if (MYO_SEC_LEN(I, MYO_SEC_P_dims) < 26 || MYO_SEC_LEN(I, MYO_SEC_HOT_off) != MYO_NSEC) return fail("myo_model_from_blob: blob carries no kernel program (pack with program=build_program(m))");
+  if (MYO_SEC_LEN(I, MYO_SEC_P_dims) < 30 || MYO_SEC_LEN(I, MYO_SEC_HOT_off) != MYO_NSEC + 1) return fail("myo_model_from_blob: blob carries no kernel program (pack with program=build_program(m))");
   myo_model* m = new myo_model(); m->I.assign(I, I+nI); m->D.assign(D, D+nD); *out = m; return 0;
 }
 extern "C" void myo_model_destroy(myo_model* m) { delete m; }
@@ -395,10 +405,12 @@ static void fill_devmodel(const myo_model* mm, const myo_task_cfg* cfg, DevModel
   const int32_t* I = mm->I.data(); const double* D = mm->D.data(); memset(&d, 0, sizeof(d));
   const int32_t* hoff = MYO_ISEC(I, MYO_SEC_HOT_off);
   for (int s = 0; s < MYO_NSEC; s++) d.hoff[s] = hoff[s];
-  d.nI16w = MYO_SEC_LEN(I, MYO_SEC_HOT_I16); d.nD = MYO_SEC_LEN(I, MYO_SEC_HOT_D);
+  d.nI16w = MYO_SEC_LEN(I, MYO_SEC_HOT_I16); d.nD = hoff[MYO_NSEC] >= 0 ? hoff[MYO_NSEC] : MYO_SEC_LEN(I, MYO_SEC_HOT_D);      // doubles staged to shared memory (the cold tables behind them stay in HBM)
   d.nq = MYO_DIM(I, MYO_DIM_nq); d.nv = MYO_DIM(I, MYO_DIM_nv); d.nu = MYO_DIM(I, MYO_DIM_nu); d.na = MYO_DIM(I, MYO_DIM_na); d.nM = MYO_DIM(I, MYO_DIM_nM); d.njnt = MYO_DIM(I, MYO_DIM_njnt);
   const int32_t* P = MYO_ISEC(I, MYO_SEC_P_dims);
   d.nbd = P[PD_NBD]; d.nlevel = P[PD_NLEVEL]; d.nsp = P[PD_NSP]; d.nwe = P[PD_NWE]; d.nta = P[PD_NTA]; d.nnz = P[PD_NNZ]; d.nlim = P[PD_NLIM]; d.neq = P[PD_NEQ];
+  { const int sp_[3] = {0, P[PD_SPLIT_SP], d.nsp}, we_[3] = {0, P[PD_SPLIT_WE], d.nwe}, ta_[3] = {0, P[PD_SPLIT_TA], d.nta}, nz_[3] = {0, P[PD_SPLIT_NZ], d.nnz};
+    for (int k = 0; k < 3; k++) { d.tg_sp[k] = sp_[k]; d.tg_we[k] = we_[k]; d.tg_ta[k] = ta_[k]; d.tg_nz[k] = nz_[k]; } }
   d.npair = P[PD_NPAIR]; d.npair_an = P[PD_NPAIR_ANALYTIC]; d.maxpath = P[PD_MAXPATH]; d.ndepth = P[PD_NDEPTH]; d.eq_tree = P[PD_EQ_TREE];
   const double* opt = MYO_DSEC(I, D, MYO_SEC_opt); d.timestep = opt[0]; d.gx = opt[1]; d.gy = opt[2]; d.gz = opt[3]; d.tolerance = opt[4]; d.meaninertia = opt[6];
   d.ovr_geom = (cfg && cfg->task == MYO_TASK_HOLD) ? cfg->task_i[1] : -1;
@@ -406,34 +418,50 @@ static void fill_devmodel(const myo_model* mm, const myo_task_cfg* cfg, DevModel
   int mc = cfg && cfg->maxcon > 0 ? cfg->maxcon : 32; if (mc > 64) mc = 64; if (mc > 2*d.npair) mc = 2*d.npair; /* (the contact-order merge handles up to 64) */ d.maxcon = mc; d.nlimrow = P[PD_NLIMROW] > 0 ? P[PD_NLIMROW] : 2*d.nlim; d.maxefc = d.neq + d.nlimrow + 4*mc;
   int o = 0;
   #define TAKE(field, n) d.field = o; o += al2(n)
-  TAKE(o_qpos, d.nq); TAKE(o_qvel, d.nv); TAKE(o_act, d.na); TAKE(o_ctrl, d.nu); TAKE(o_qws, d.nv); TAKE(o_dax, 3*d.nv); TAKE(o_dan, 3*d.nv); TAKE(o_qM, d.nM); TAKE(o_fsm, d.nv); d.neprm = (cfg && cfg->task == MYO_TASK_HOLD) ? 8 : 0; TAKE(o_eprm, d.neprm); d.nwz = P[PD_NWE_SPH_IN] + P[PD_NWE_CYL_IN]; TAKE(o_wz, d.nwz); TAKE(o_cnt, CNT_N/2);
+  // persistent per-env arrays.  ctrl is NOT here: it is written once per control step to a library-owned global row and re-read by the actuation
+  // phase of every substep (an L2 hit); the solver's warm start lives in the tail of the Hessian region when that tail is provably idle (below).
+  TAKE(o_qpos, d.nq); TAKE(o_qvel, d.nv); TAKE(o_act, d.na); TAKE(o_dax, 3*d.nv); TAKE(o_dan, 3*d.nv); TAKE(o_qM, d.nM); TAKE(o_fsm, d.nv);
+  d.neprm = (cfg && cfg->task == MYO_TASK_HOLD) ? 8 : 0; TAKE(o_eprm, d.neprm); d.nwz = P[PD_NWE_SPH_IN] + P[PD_NWE_CYL_IN]; TAKE(o_wz, d.nwz); TAKE(o_cnt, CNT_N/2);
   d.nvp = chol_pad(d.nv);
-  d.o_scr = o;
+  const int o_qws_persistent = o;          // (claimed only if the warm start cannot alias the Hessian tail)
+  // ---- scratch, time-multiplexed by stage (offsets from d.o_scr, fixed up at the end).  Lifetimes:
+  //   head: icon (contact / row integer records), con (contact records)     collision .. constraints ; in the solve the con region holds jar, jv
+  //   K   (xpos, xmat)                                                      kinematics .. collision              -> right after the head
+  //   T   (U, PL, mom, tlen, tvel, tfrc)                                    tendon .. actuation                  -> around K
+  //   C   (cin, crb, bf)                                                    body inertia .. bias                 -> around K
+  //   G   (gpose, clist)                                                    collision                            -> after K
+  //   S   (conJ 48-bit, D, eqJ, a, g|p, Ma, Mp, H | Hs LD Dinv, aref->H)   constraints .. integrate             -> after the head (K is dead)
+  const int icon = al2(mc + (mc + 1)/2 + (2*(mc + d.nlimrow + 4) + d.maxefc + 7)/8);       // cmask u64[mc] | crown i32[mc] | cpair i16[mc] | lrow i16[nlimrow+4] | drow u8[maxefc]
+  const int rows = al2(d.maxefc), conReg = imax(al2(CON_STRIDE*mc), 2*rows), K = al2(3*d.nbd) + al2(9*d.nbd);
+  d.s_icon = 0; d.s_con = icon; d.s_efR = icon; d.s_efV = icon + rows; const int head = icon + conReg;
+  d.s_xpos = head; d.s_xmat = head + al2(3*d.nbd); const int afterK = head + K;
+  int c0, c1, ext;      // two cursors: inside [0, head) and after K
+  #define PLACE(field, n) { const int n_ = al2(n); if (c0 + n_ <= head) { d.field = c0; c0 += n_; } else { d.field = c1; c1 += n_; } }
+  c0 = 0; c1 = afterK;
+  PLACE(s_mom, d.nnz); PLACE(s_tlen, d.nta); PLACE(s_tvel, d.nta); PLACE(s_tfrc, d.nta); { const int nsA = d.tg_sp[1], nsB = d.nsp - nsA, nwA = d.tg_we[1], nwB = d.nwe - nwA;      // one tendon group at a time lives in U / PL
+    PLACE(s_PL, imax(nsA + nwA, nsB + nwB)); PLACE(s_U, 3*imax(nsA + 2*nwA, nsB + 2*nwB)); }
+  ext = c1;
+  c0 = 0; c1 = afterK;
+  PLACE(s_cin, 10*d.nbd); PLACE(s_crb, 10*d.nbd); PLACE(s_bf, 6*d.nbd);
+  ext = imax(ext, c1);
+  d.kcand = d.npair - d.npair_an; d.ngc = P[PD_NGC];
+  d.s_gpose = afterK; d.s_clist = afterK + al2(6*d.ngc); ext = imax(ext, d.s_clist + al2((d.kcand + 1)/2));
+  const int extNonSolve = ext;
+  int t = head;
+  d.s_conJ = t; t += al2(imax((3*d.maxpath*mc*JAC_BYTES + 7)/8, (mc + 1)/2)); d.s_efD = t; t += al2(d.neq + d.nlimrow + mc); d.s_eqJ = t; t += al2(d.neq);      /* (the Jacobian region doubles as the int rank keys of the contact ordering) */
+  d.s_va = t; t += al2(d.nvp); d.s_vg = t; d.s_vp = t; t += al2(d.nvp); d.s_vMa = t; t += al2(d.nvp); d.s_vMp = t; t += al2(d.nvp);
+  const int hsize = imax(al2(d.nvp*(d.nvp+1)/2), 2*al2(d.nM) + al2(d.nv)); const bool arefInH = rows <= hsize;
+  d.s_efA = t; if (!arefInH) t += rows;      /* aref (constraints -> start of the solve) lives in the Hessian region when it fits: H is first written after its last read */
+  d.s_H = t; d.s_Hs = t; d.s_LD = t + al2(d.nM); d.s_Dinv = t + 2*al2(d.nM); if (arefInH) d.s_efA = t; t += hsize;
+  // warm start in the last nv slots of the Hessian region: read once at the start of the solve (before any write to H), rewritten at the end
+  // of the integrator (after the last read of H).  Requires that no other stage reaches that far and that aref (head of H) does not overlap it.
+  int qws = t - al2(d.nv);
+  const bool qwsInH = qws >= extNonSolve && (!arefInH || d.s_H + rows <= qws) && d.s_H + al2(d.nvp*(d.nvp+1)/2) <= t;
+  ext = imax(ext, t);
+  int scratch = ext;
+  if (qwsInH) { d.o_scr = o; d.o_qws = o + qws; } else { d.o_qws = o_qws_persistent; o += al2(d.nv); d.o_scr = o; }
+  #undef PLACE
   #undef TAKE
-  // ---- scratch, time-multiplexed.  Lifetimes:
-  //   K  (xpos,xmat)                       kinematics .. constraints           -> parked at the END of the scratch
-  //   T  (U,PL,mom,tlen,tvel,tfrc)         tendon .. actuation                 -> from 0
-  //   C  (cin,crb,bf)                      body inertia .. bias                -> from 0
-  //   S3 (conJ,D,aref,eqJ,icon)            collision/constraints .. solve      -> from 0   (T and C are dead by then)
-  //   con                                  collision .. constraints            -> right after S3 (overwritten by the solve vectors)
-  //   S4 (jar,jv,a,g,p,Ma,Mp,H|Hs,LD,Dinv) solve .. integrate                  -> right after S3 (may overwrite con and K)
-  int K = al2(3*d.nbd) + al2(9*d.nbd);
-  int t = 0; d.s_U = t; t += al2(3*(d.nsp+2*d.nwe)); d.s_PL = t; t += al2(d.nsp+d.nwe); d.s_mom = t; t += al2(d.nnz);
-  d.s_tlen = t; t += al2(d.nta); d.s_tvel = t; t += al2(d.nta); d.s_tfrc = t; t += al2(d.nta); int sizeT = t;
-  t = 0; d.s_cin = t; t += al2(10*d.nbd); d.s_crb = t; t += al2(10*d.nbd); d.s_bf = t; t += al2(6*d.nbd); int sizeC = t;
-  // the list of ellipsoid candidates that survive the cull shares the contact-Jacobian region (ints; it holds every iterative pair)
-  d.kcand = d.npair - d.npair_an; int candsz = al2((d.kcand + 1)/2);
-  t = 0; d.s_conJ = t; d.s_clist = t; t += imax(al2(3*d.maxpath*mc), candsz); d.s_efD = t; t += al2(d.maxefc); const int hsize = imax(al2(d.nvp*(d.nvp+1)/2), 2*al2(d.nM) + al2(d.nv)); const bool arefInH = al2(d.maxefc) <= hsize;
-  d.s_efA = t; if (!arefInH) t += al2(d.maxefc);      /* aref (constraints -> start of the solve) lives in the Hessian region when it fits: H is first written after its last read */
-  d.s_eqJ = t; t += al2(d.neq);
-  d.ngc = P[PD_NGC]; d.s_gpose = d.s_efD; if (t - d.s_efD < al2(6*d.ngc)) t = d.s_efD + al2(6*d.ngc);     // geom poses (collision only) alias the row arrays (written after it)
-  d.s_icon = t; t += al2((4*mc + d.nlimrow + 4 + 1)/2); int sizeS3 = t;      // path masks (2 ints per contact), pair, row|nrow, limit rows
-  d.s_con = sizeS3; int sizeCon = al2(CON_STRIDE*mc);
-  t = sizeS3; d.s_efR = t; t += al2(d.maxefc); d.s_efV = t; t += al2(d.maxefc); d.s_va = t; t += al2(d.nvp); d.s_vg = t; t += al2(d.nvp); d.s_vp = t; t += al2(d.nvp);
-  d.s_vMa = t; t += al2(d.nvp); d.s_vMp = t; t += al2(d.nvp);
-  d.s_H = t; d.s_Hs = t; d.s_LD = t + al2(d.nM); d.s_Dinv = t + 2*al2(d.nM); if (arefInH) d.s_efA = t; t += hsize; int sizeS4 = t;
-  int scratch = imax(imax(sizeT, sizeC) + K, imax(sizeS3 + sizeCon + K, sizeS4));
-  d.s_xpos = scratch - K; d.s_xmat = d.s_xpos + al2(3*d.nbd);
   // scratch offsets are used relative to the warp base
   { int32_t* f[] = {&d.s_xpos, &d.s_xmat, &d.s_U, &d.s_PL, &d.s_mom, &d.s_tlen, &d.s_tvel, &d.s_tfrc, &d.s_cin, &d.s_crb, &d.s_bf, &d.s_conJ, &d.s_efD, &d.s_efA, &d.s_eqJ,
                     &d.s_icon, &d.s_con, &d.s_clist, &d.s_gpose, &d.s_efR, &d.s_efV, &d.s_va, &d.s_vg, &d.s_vp, &d.s_vMa, &d.s_vMp, &d.s_H, &d.s_Hs, &d.s_LD, &d.s_Dinv};
@@ -464,34 +492,46 @@ extern "C" int myo_batch_create(const myo_model* m, int device, int n_env, const
   else if (cfg->task == MYO_TASK_REACH) { if (cfg->task_i[0] < 1 || cfg->task_i[0] > 7 || 3*cfg->task_i[0] > b->dm.nq) { delete b; return fail("reach task: 1..7 tips and 3*ntip <= nq"); }
     b->obs_dim = b->dm.nq + b->dm.nv + 6*cfg->task_i[0] + b->dm.na; }
   { const int32_t* I = m->I.data(); const double* D = m->D.data();
-    size_t nI = (size_t)b->dm.nI16w*4, nD = (size_t)b->dm.nD*8;
+    size_t nI = (size_t)b->dm.nI16w*4, nD = (size_t)MYO_SEC_LEN(I, MYO_SEC_HOT_D)*8;      /* ALL hot doubles go to HBM; the first dm.nD of them are staged per CTA */
     CUDA_OK(cudaMalloc(&b->dI, nI ? nI : 16)); CUDA_OK(cudaMalloc(&b->dD, nD ? nD : 16));
     CUDA_OK(cudaMemcpy(b->dI, MYO_ISEC(I, MYO_SEC_HOT_I16), nI, cudaMemcpyHostToDevice)); CUDA_OK(cudaMemcpy(b->dD, MYO_DSEC(I, D, MYO_SEC_HOT_D), nD, cudaMemcpyHostToDevice)); }
-  b->dm.gI16 = b->dI; b->dm.gD = b->dD;
+  CUDA_OK(cudaMalloc(&b->dCtrl, (size_t)n_env*imax(b->dm.nu, 1)*8)); CUDA_OK(cudaMemset(b->dCtrl, 0, (size_t)n_env*imax(b->dm.nu, 1)*8));
+  b->dm.gI16 = b->dI; b->dm.gD = b->dD; b->dm.g_ctrl = b->dCtrl;
   cudaDeviceProp prop; CUDA_OK(cudaGetDeviceProperties(&prop, device));
   b->const_bytes = b->dm.nD*8 + ((b->dm.nI16w + 1)/2)*8;
   int per = b->dm.n_per_warp*8, maxs = (int)prop.sharedMemPerBlockOptin - b->const_bytes - 64;
-  cudaFuncAttributes fa_p, fa_d; CUDA_OK(cudaFuncGetAttributes(&fa_p, myo_env_kernel)); CUDA_OK(cudaFuncGetAttributes(&fa_d, myo_env_kernel_dbg));
-  int maxw = (fa_p.maxThreadsPerBlock < fa_d.maxThreadsPerBlock ? fa_p.maxThreadsPerBlock : fa_d.maxThreadsPerBlock)/32;     // what the kernels' register budgets allow
-  if (const char* e = getenv("MYO_B200_PRODUCT_ONLY")) if (atoi(e)) maxw = fa_p.maxThreadsPerBlock/32;      // (experiments: ignore the debug kernel's bound)
-  int wpc = maxs/per; if (wpc > maxw) wpc = maxw;
-  if (wpc < 1) { delete b; return fail("model working set exceeds shared memory of one CTA"); }
-  const int wpc0 = wpc;
-  if (n_env < wpc) wpc = n_env;
-  { // wave quantisation: with one CTA per SM the batch takes ceil(n_env / (SMs * wpc)) rounds; among the warp counts that reach the
+  // Launch configurations.  Product: the launch_bounds(320) kernel (168 registers, <= 10 warps) unless more warps fit in shared memory AND cut the
+  // number of rounds, then the launch_bounds(448) kernel (128 registers, <= 14 warps).  Debug kernel: its own configuration (<= 10 warps).
+  cudaFuncAttributes fa_p, fa_w, fa_d; CUDA_OK(cudaFuncGetAttributes(&fa_p, myo_env_kernel)); CUDA_OK(cudaFuncGetAttributes(&fa_w, myo_env_kernel_w14)); CUDA_OK(cudaFuncGetAttributes(&fa_d, myo_env_kernel_dbg));
+  const int sms = prop.multiProcessorCount, fit = maxs/per;
+  if (fit < 1) { delete b; return fail("model working set exceeds shared memory of one CTA"); }
+  if (b->dm.neq + b->dm.nlimrow + b->dm.maxcon > 255) { delete b; return fail("equality + limit rows + contact capacity exceed the 255 regulariser slots of the row map"); }
+  const bool big = (size_t)per*(fit < 4 ? fit : 4) + b->const_bytes > 50*1024;      // a 4-warp CTA already takes > 50 KB: one CTA per SM, sized by the round count below (small models run several CTAs per SM instead)
+  auto pick = [&](int maxw) { int wpc = fit < maxw ? fit : maxw; if (n_env < wpc) wpc = n_env;
+    // wave quantisation: with one CTA per SM the batch takes ceil(n_env / (SMs * wpc)) rounds; among the warp counts that reach the
     // minimal number of rounds take the SMALLEST (same rounds, less issue contention and less lockstep imbalance per round)
-    int sms = prop.multiProcessorCount, best = wpc, rounds = (n_env + sms*wpc - 1)/(sms*wpc);
-    for (int q = wpc - 1; q >= 1; q--) if ((n_env + sms*q - 1)/(sms*q) == rounds) best = q;
-    if (b->dm.n_per_warp*8*best + b->const_bytes > 100*1024) wpc = best; }   // (small models run several CTAs per SM instead)
-  if (const char* e = getenv("MYO_B200_WARPS_PER_CTA")) { int q = atoi(e); if (q >= 1 && q <= wpc0) wpc = q; }     // tuning override (never above what fits)
-  b->warps_per_cta = wpc; b->smem_bytes = b->const_bytes + wpc*per;
+    if (big) { int best = wpc, rounds = (n_env + sms*wpc - 1)/(sms*wpc); for (int q = wpc - 1; q >= 1; q--) if ((n_env + sms*q - 1)/(sms*q) == rounds) best = q;
+      if ((size_t)b->dm.n_per_warp*8*best + b->const_bytes > 100*1024) wpc = best; }
+    return wpc; };
+  auto rounds_of = [&](int wpc) { return (n_env + sms*wpc - 1)/(sms*wpc); };
+  int wp = pick(fa_p.maxThreadsPerBlock/32), ww = pick(fa_w.maxThreadsPerBlock/32), wd = pick(fa_d.maxThreadsPerBlock/32);
+  b->use_w14 = big && ww > wp && rounds_of(ww) < rounds_of(wp);
+  if (const char* e = getenv("MYO_B200_W14")) b->use_w14 = atoi(e) != 0 && fa_w.maxThreadsPerBlock > fa_p.maxThreadsPerBlock;      // tuning override
+  int wpc = b->use_w14 ? ww : wp;
+  if (const char* e = getenv("MYO_B200_WARPS_PER_CTA")) { int q = atoi(e), cap = (b->use_w14 ? fa_w.maxThreadsPerBlock : fa_p.maxThreadsPerBlock)/32; if (cap > fit) cap = fit;
+    if (q >= 1 && q <= cap) wpc = q; if (q >= 1 && q <= (fa_d.maxThreadsPerBlock/32 < fit ? fa_d.maxThreadsPerBlock/32 : fit)) wd = q; }     // tuning override (never above what fits)
+  b->warps_per_cta = wpc; b->smem_bytes = b->const_bytes + wpc*per; b->dbg_warps = wd; b->dbg_smem = b->const_bytes + wd*per;
   CUDA_OK(cudaFuncSetAttribute(myo_env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes));
-  CUDA_OK(cudaFuncSetAttribute(myo_env_kernel_dbg, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes));
-  int ctas_per_sm = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, myo_env_kernel, wpc*32, b->smem_bytes); if (ctas_per_sm < 1) ctas_per_sm = 1;
-  int need = (n_env + wpc - 1)/wpc, cap = prop.multiProcessorCount*ctas_per_sm; b->grid = need < cap ? need : cap;
+  CUDA_OK(cudaFuncSetAttribute(myo_env_kernel_w14, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem_bytes));
+  CUDA_OK(cudaFuncSetAttribute(myo_env_kernel_dbg, cudaFuncAttributeMaxDynamicSharedMemorySize, b->dbg_smem));
+  { int c = 1; if (b->use_w14) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, myo_env_kernel_w14, wpc*32, b->smem_bytes); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, myo_env_kernel, wpc*32, b->smem_bytes);
+    if (c < 1) c = 1; int need = (n_env + wpc - 1)/wpc, cap = sms*c; b->grid = need < cap ? need : cap; }
+  { int c = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, myo_env_kernel_dbg, wd*32, b->dbg_smem); if (c < 1) c = 1; int need = (n_env + wd - 1)/wd, cap = sms*c; b->dbg_grid = need < cap ? need : cap; }
+  if (getenv("MYO_B200_VERBOSE")) fprintf(stderr, "[myo_b200] n_env %d: %s kernel, %d warps/CTA, grid %d, smem %d B (const %d + %d/env, %d fit); debug kernel %d warps, grid %d; max threads / regs: product %d / %d, w14 %d / %d, debug %d / %d\n",
+    n_env, b->use_w14 ? "launch_bounds(448)" : "launch_bounds(320)", b->warps_per_cta, b->grid, b->smem_bytes, b->const_bytes, per, fit, b->dbg_warps, b->dbg_grid, fa_p.maxThreadsPerBlock, fa_p.numRegs, fa_w.maxThreadsPerBlock, fa_w.numRegs, fa_d.maxThreadsPerBlock, fa_d.numRegs);
   *out = b; return 0;
 }
-extern "C" void myo_batch_destroy(myo_batch* b) { if (!b) return; cudaSetDevice(b->device); cudaFree(b->dI); cudaFree(b->dD); delete b; }
+extern "C" void myo_batch_destroy(myo_batch* b) { if (!b) return; cudaSetDevice(b->device); cudaFree(b->dI); cudaFree(b->dD); cudaFree(b->dCtrl); delete b; }
 extern "C" int myo_batch_obs_dim(const myo_batch* b) { return b ? b->obs_dim : -1; }
 extern "C" int64_t myo_batch_launch_count(const myo_batch* b) { return b ? b->launches : -1; }
 
@@ -531,14 +571,16 @@ static int launch(myo_batch* b, StepArgs& a, void* stream) {
   if (!b->bound) return fail("batch has no bound buffers (call myo_batch_bind)");
   CUDA_OK(cudaSetDevice(b->device));
   a.b = b->bufs; a.cfg = b->cfg; a.n_env = b->n_env; a.obs_dim = b->obs_dim; a.dt = b->dm.timestep*b->cfg.frame_skip;
-  a.seed = b->seed; a.env_offset = b->env_offset; a.balanced = b->smem_bytes > 100*1024;
+  a.seed = b->seed; a.env_offset = b->env_offset;
   a.tol = b->cfg.solver_tolerance > 0 ? b->cfg.solver_tolerance : 1e-10;
   // the debug instantiation serves forward-debug calls, bound parity taps / cycle counters and the barrier / lockstep tuning knobs
   const myo_buffers& q = b->bufs;
   const bool dbg = a.mode == 1 || b->force_dbg || b->cfg.barrier_mode != 0 || b->cfg.reserved_i > 1 || q.tap_qacc || q.tap_actuator_force || q.tap_ten_length || q.tap_qfrc_smooth ||
                    q.tap_ncon || q.tap_contact_pair || q.tap_contact_dist || q.tap_moment || q.tap_qM || q.tap_phase_cycles;
-  if (dbg) myo_env_kernel_dbg<<<b->grid, b->warps_per_cta*32, b->smem_bytes, (cudaStream_t)stream>>>(b->dm, a);
-  else myo_env_kernel<<<b->grid, b->warps_per_cta*32, b->smem_bytes, (cudaStream_t)stream>>>(b->dm, a);
+  if (dbg) { a.balanced = b->dbg_smem > 100*1024; myo_env_kernel_dbg<<<b->dbg_grid, b->dbg_warps*32, b->dbg_smem, (cudaStream_t)stream>>>(b->dm, a); }
+  else { a.balanced = b->smem_bytes > 100*1024;
+    if (b->use_w14) myo_env_kernel_w14<<<b->grid, b->warps_per_cta*32, b->smem_bytes, (cudaStream_t)stream>>>(b->dm, a);
+    else myo_env_kernel<<<b->grid, b->warps_per_cta*32, b->smem_bytes, (cudaStream_t)stream>>>(b->dm, a); }
   CUDA_OK(cudaGetLastError()); b->launches++; return 0;
 }
 extern "C" int myo_batch_step(myo_batch* b, void* stream) {

@@ -19,7 +19,8 @@ typedef short idx_t;
 
 // P_dims slots (must match myosuite_b200/program.py)
 enum { PD_NBD, PD_NLEVEL, PD_NPT, PD_NSP, PD_NWE, PD_NTA, PD_NNZ, PD_NTERM, PD_NLIM, PD_NEQ, PD_NPAIR, PD_NGC, PD_MAXPATH,
-       PD_MAXCHAIN, PD_NSUB, PD_NROW, PD_NCOL, PD_NPIECE, PD_NWE_SPH_OUT, PD_NWE_SPH_IN, PD_NWE_CYL_OUT, PD_NWE_CYL_IN, PD_NDEPTH, PD_EQ_TREE, PD_NPAIR_ANALYTIC, PD_NLIMROW };
+       PD_MAXCHAIN, PD_NSUB, PD_NROW, PD_NCOL, PD_NPIECE, PD_NWE_SPH_OUT, PD_NWE_SPH_IN, PD_NWE_CYL_OUT, PD_NWE_CYL_IN, PD_NDEPTH, PD_EQ_TREE, PD_NPAIR_ANALYTIC, PD_NLIMROW,
+       PD_SPLIT_SP, PD_SPLIT_WE, PD_SPLIT_TA, PD_SPLIT_NZ };
 #define PB_STRIDE 22      // pos[3] R[9] ipos[3] mass Iloc[6]
 #define PWE_STRIDE 16
 #define PA_STRIDE 17      // dynprm[3] | gain: range0 range1 lmin lmax vmax fvmax | bias: range0 range1 lmax fpmax | ctrlrange[2] | ctrllimited | pad
@@ -36,14 +37,16 @@ enum { CT_NONE, CT_CAP_CAP, CT_SPH_SPH, CT_SPH_CAP, CT_PLANE_SPH, CT_PLANE_CAP, 
 // ------------------------------------------------------------------ device-resident model view (kernel parameter)
 struct DevModel {
   const int32_t* gI16; const double* gD;   // hot constant arrays in HBM (source of the per-CTA staging copy)
-  int32_t nI16w, nD;                       // sizes: int32 words of packed int16, doubles
+  double* g_ctrl;                          // [n_env, nu] library-owned: this control step's ctrl rows (written by the prologue, read by every substep)
+  int32_t nI16w, nD;                       // sizes of the STAGED arrays: int32 words of packed int16, doubles (gD holds further "cold" tables behind the staged ones: GD())
   int32_t hoff[MYO_NSEC];                  // offset of each hot section (in shorts / doubles), -1 if not staged
   int32_t nq, nv, nu, na, nM, njnt;
   int32_t nbd, nlevel, nsp, nwe, nta, nnz, nlim, neq, npair, npair_an, maxpath, ndepth, eq_tree;
+  int32_t tg_sp[3], tg_we[3], tg_ta[3], tg_nz[3];          // tendon groups A / B (two passes through the tendon scratch): ranges of segments, wrap elements, tendons, moment non-zeros
   int32_t maxcon, maxefc, nlimrow, ovr_geom, ngc, s_gpose, solve_sync, nvp;          // ovr_geom: collision geom whose size comes from the per-env overrides (-1: none); nvp: nv padded to the dense solver's order
   double timestep, gx, gy, gz, meaninertia, tolerance;
   // per-warp shared-memory layout, in doubles.  Persistent part:
-  int32_t o_qpos, o_qvel, o_act, o_ctrl, o_qws, o_dax, o_dan, o_qM, o_fsm, o_eprm, neprm, o_wz, nwz, o_cnt, o_scr, n_per_warp;
+  int32_t o_qpos, o_qvel, o_act, o_qws, o_dax, o_dan, o_qM, o_fsm, o_eprm, neprm, o_wz, nwz, o_cnt, o_scr, n_per_warp;
   // scratch (time-multiplexed by stage; offsets relative to the warp base, i.e. o_scr included).  See fill_devmodel() for the overlap rules.
   int32_t s_xpos, s_xmat;                                  // K: body poses, alive kinematics .. constraints
   int32_t s_U, s_PL, s_mom, s_tlen, s_tvel, s_tfrc;  // stage 1: tendons + actuation
@@ -63,10 +66,16 @@ struct Warp { int base, lane; };   // by value: offset (doubles) of this warp's 
 enum { CNT_ncon, CNT_nefc, CNT_nlimrow, CNT_niter, CNT_overflow, CNT_ncand, CNT_na, CNT_N = 8 };   // per-warp int counters (m.o_cnt)
 #define CI(name) ((const idx_t*)(smem + m.nD) + m.hoff[MYO_SEC_##name])
 #define CD(name) ((const double*)smem + m.hoff[MYO_SEC_##name])
+#ifdef MYO_COLD_L2ONLY
+#define LDC(p) __ldcg(p)                                      // (measured round 2: bypassing L1 costs 5 % at 14 warps -- the L1 hit rate of these loads is 97 %)
+#else
+#define LDC(p) __ldg(p)
+#endif
+#define GD(name) (m.gD + m.hoff[MYO_SEC_##name])              // cold f64 tables (blob.py COLD_D): read from HBM / L2 through the read-only path (__ldg)
 #define W_(f) (smem + w.base + m.o_##f)                       // persistent per-env arrays
 #define WI_(f) (((int*)(smem + w.base + m.o_cnt))[CNT_##f])   // per-env counters
 #define SCR(field) (smem + w.base + m.field)                  // scratch (m.s_* are offsets from the warp base)
-#define S_cpair (((int*)SCR(s_icon)) + 2*m.maxcon)             // contact -> program pair index (after the 64-bit path masks; see myo_solver.cuh)
+#define S_cpair ((idx_t*)(SCR(s_icon) + m.maxcon + (m.maxcon + 1)/2))   // contact -> program pair index, int16 (after the 64-bit path masks and the row words; see myo_solver.cuh)
 #define SHARED_PTR(p) __builtin_assume(__isShared(p))         // for pointer PARAMETERS of functions that may not be inlined
 
 // ------------------------------------------------------------------ small math
@@ -109,7 +118,7 @@ __device__ __forceinline__ double m_sqrt(double x) { double y; asm("rsqrt.approx
 
 // world position of program point `pt`
 __device__ __forceinline__ void world_point(const DevModel& m, const Warp w, int pt, double* out) {
-  int b = CI(PPT_body)[pt]; const double* x = CD(PPT_xyz) + 3*pt;
+  int b = CI(PPT_body)[pt]; const double* __restrict__ xg = GD(PPT_xyz) + 3*pt; const double x[3] = {LDC(xg), LDC(xg+1), LDC(xg+2)};
   if (b < 0) { out[0]=x[0]; out[1]=x[1]; out[2]=x[2]; }
   else { const double* xp = SCR(s_xpos) + 3*b; mat_vec(out, SCR(s_xmat) + 9*b, x); out[0]+=xp[0]; out[1]+=xp[1]; out[2]+=xp[2]; } }
 
@@ -268,10 +277,12 @@ __device__ __forceinline__ double wrap2d_inside(double* pnt, const double* d, do
   pnt[0] = rad*(c*vx - s*vy); pnt[1] = rad*(s*vx + c*vy); pnt[2] = pnt[0]; pnt[3] = pnt[1];
   return 0; }
 
-__device__ void wrap_element(const DevModel& m, const Warp w, int k, double* U, double* PL) {
-  const idx_t* we = CI(PWE) + 6*k; const double* wd = CD(PWE_d) + k*PWE_STRIDE;
+__device__ void wrap_element(const DevModel& m, const Warp w, int k, int g, double* U, double* PL) {
+  const idx_t* we = CI(PWE) + 6*k; const double* __restrict__ wdg = GD(PWE_d) + k*PWE_STRIDE;      // (cold table: 16 independent read-only loads per element)
+  double wd[12]; for (int c = 0; c < 12; c++) wd[c] = LDC(wdg + c);
   double x0[3], x1[3]; world_point(m, w, we[0], x0); world_point(m, w, we[1], x1);
-  int gb = we[2]; bool cyl = we[3] == 1, has_side = we[4] >= 0, inside = we[5] != 0; double rad = wd[12];
+  int gb = we[2]; bool cyl = we[3] == 1, has_side = we[4] >= 0, inside = we[5] != 0; const double rad = LDC(wdg + 12);
+  const int nspg = m.tg_sp[g+1] - m.tg_sp[g], kl = k - m.tg_we[g];      // slots inside this group's scratch
   double gpos[3], gmat[9];
   if (gb < 0) { for (int c = 0; c < 3; c++) gpos[c] = wd[c]; for (int c = 0; c < 9; c++) gmat[c] = wd[3+c]; }
   else { const double* X = SCR(s_xmat) + 9*gb; const double* xp = SCR(s_xpos) + 3*gb; mat_vec(gpos, X, wd); gpos[0]+=xp[0]; gpos[1]+=xp[1]; gpos[2]+=xp[2]; mat_mul(gmat, X, wd + 3); }
@@ -287,16 +298,16 @@ __device__ void wrap_element(const DevModel& m, const Warp w, int k, double* U, 
         double o[3] = {i == 0 ? 0.0 : 1.0, i == 1 ? 0.0 : 1.0, i == 2 ? 0.0 : 1.0}; cross3(nrm, ax0, o); nn = m_sqrt(dot3(nrm,nrm)); }
       { const double q = m_rcp(nn); nrm[0]*=q; nrm[1]*=q; nrm[2]*=q; } cross3(ax1, nrm, ax0); { const double q = m_rcp(m_sqrt(dot3(ax1,ax1))); ax1[0]*=q; ax1[1]*=q; ax1[2]*=q; } }
     double d[4] = {dot3(p0,ax0), dot3(p0,ax1), dot3(p1,ax0), dot3(p1,ax1)}, sd[2] = {0,0};
-    if (has_side) { const double* s = wd + 13; sd[0] = dot3(s,ax0); sd[1] = dot3(s,ax1); double n = m_sqrt(sd[0]*sd[0]+sd[1]*sd[1]);
+    if (has_side) { const double s[3] = {LDC(wdg + 13), LDC(wdg + 14), LDC(wdg + 15)}; sd[0] = dot3(s,ax0); sd[1] = dot3(s,ax1); double n = m_sqrt(sd[0]*sd[0]+sd[1]*sd[1]);
       if (n < MYO_MINVAL) { sd[0] = rad; sd[1] = 0; } else { const double q = rad*m_rcp(n); sd[0] *= q; sd[1] *= q; } }
-    wlen = inside ? wrap2d_inside(pnt, d, rad, W_(wz) + k) : wrap2d_outside(pnt, d, sd, has_side, rad);
+    wlen = inside ? wrap2d_inside(pnt, d, rad, W_(wz) + (we[5] - 1)) : wrap2d_outside(pnt, d, sd, has_side, rad);
   }
-  double* u0 = U + 3*(m.nsp + 2*k); double* u1 = u0 + 3; double w0[3], w1[3];      // tangent points: only the two straight pieces' directions and the path length leave this function
+  double* u0 = U + 3*(nspg + 2*kl); double* u1 = u0 + 3; double w0[3], w1[3];      // tangent points: only the two straight pieces' directions and the path length leave this function
   if (wlen < 0) {   // straight segment: both "wrap points" sit at x1 (on the line), same direction for both pieces
     double dv[3] = {x1[0]-x0[0], x1[1]-x0[1], x1[2]-x0[2]}, n = m_sqrt(dot3(dv,dv));
     if (n < MYO_MINVAL) { dv[0]=1; dv[1]=0; dv[2]=0; } else { const double q = m_rcp(n); dv[0]*=q; dv[1]*=q; dv[2]*=q; }
     for (int c = 0; c < 3; c++) { u0[c]=dv[c]; u1[c]=dv[c]; }
-    PL[m.nsp + k] = n; return; }
+    PL[nspg + kl] = n; return; }
   double r0[3], r1[3];
   for (int c = 0; c < 3; c++) { r0[c] = ax0[c]*pnt[0]+ax1[c]*pnt[1]; r1[c] = ax0[c]*pnt[2]+ax1[c]*pnt[3]; }
   if (cyl) { double L0 = m_sqrt((p0[0]-pnt[0])*(p0[0]-pnt[0])+(p0[1]-pnt[1])*(p0[1]-pnt[1])), L1 = m_sqrt((p1[0]-pnt[2])*(p1[0]-pnt[2])+(p1[1]-pnt[3])*(p1[1]-pnt[3]));
@@ -309,43 +320,53 @@ __device__ void wrap_element(const DevModel& m, const Warp w, int k, double* U, 
   double na = m_sqrt(dot3(a,a)), nb = m_sqrt(dot3(b,b));
   if (na < MYO_MINVAL) { u0[0]=1; u0[1]=0; u0[2]=0; } else { double q = m_rcp(na); u0[0]=a[0]*q; u0[1]=a[1]*q; u0[2]=a[2]*q; }
   if (nb < MYO_MINVAL) { u1[0]=1; u1[1]=0; u1[2]=0; } else { double q = m_rcp(nb); u1[0]=b[0]*q; u1[1]=b[1]*q; u1[2]=b[2]*q; }
-  PL[m.nsp + k] = na + wlen + nb;
+  PL[nspg + kl] = na + wlen + nb;
 }
 
-__device__ void phase_tendon(const DevModel& m, const Warp w) {
+// One tendon group (pass): straight segments and wrap elements of the group into the group-local unit-vector / piece-length scratch
+__device__ void phase_tendon(const DevModel& m, const Warp w, int g) {
   double* U = SCR(s_U); double* PL = SCR(s_PL);
-  const idx_t* sp = CI(PSP);
-  for (int k = w.lane; k < m.nsp; k += 32) { double a[3], b[3]; world_point(m, w, sp[2*k], a); world_point(m, w, sp[2*k+1], b);
+  const idx_t* sp = CI(PSP); const int s0 = m.tg_sp[g], s1 = m.tg_sp[g+1];
+  for (int k = s0 + w.lane; k < s1; k += 32) { double a[3], b[3]; world_point(m, w, sp[2*k], a); world_point(m, w, sp[2*k+1], b); const int kl = k - s0;
     double dv[3] = {b[0]-a[0], b[1]-a[1], b[2]-a[2]}, n = m_sqrt(dot3(dv,dv));
-    if (n < MYO_MINVAL) { U[3*k]=1; U[3*k+1]=0; U[3*k+2]=0; } else { double q = m_rcp(n); U[3*k]=dv[0]*q; U[3*k+1]=dv[1]*q; U[3*k+2]=dv[2]*q; }
-    PL[k] = n; }
+    if (n < MYO_MINVAL) { U[3*kl]=1; U[3*kl+1]=0; U[3*kl+2]=0; } else { double q = m_rcp(n); U[3*kl]=dv[0]*q; U[3*kl+1]=dv[1]*q; U[3*kl+2]=dv[2]*q; }
+    PL[kl] = n; }
   #pragma unroll 1
-  for (int k = w.lane; k < m.nwe; k += 32) wrap_element(m, w, k, U, PL);
+  for (int k = m.tg_we[g] + w.lane; k < m.tg_we[g+1]; k += 32) wrap_element(m, w, k, g, U, PL);
   __syncwarp();
 }
-// second half: moments per structural non-zero, tendon lengths and velocities (a CTA barrier in between re-aligns the warps)
-__device__ void phase_tendon_moments(const DevModel& m, const Warp w) {
-  double* U = SCR(s_U); double* PL = SCR(s_PL); double* mom = SCR(s_mom);
-  double* tlen = SCR(s_tlen); double* tvel = SCR(s_tvel); double* tfrc = SCR(s_tfrc);
+// second half of a pass: moments per structural non-zero and tendon lengths of the group
+__device__ void phase_tendon_moments(const DevModel& m, const Warp w, int g) {
+  double* U = SCR(s_U); double* PL = SCR(s_PL); double* mom = SCR(s_mom); double* tlen = SCR(s_tlen);
   const idx_t* nzd = CI(PNZ_dof); const idx_t* tadr = CI(PNZ_term_adr); const idx_t* term = CI(PTERM);
-  for (int z = w.lane; z < m.nnz; z += 32) { int d = nzd[z]; double acc = 0;
+  for (int z = m.tg_nz[g] + w.lane; z < m.tg_nz[g+1]; z += 32) { int d = nzd[z]; double acc = 0;
     #pragma unroll 1
     for (int e = tadr[z]; e < tadr[z+1]; e++) { int ui = term[3*e], pc = term[3*e+1]; double sg = term[3*e+2];
       double pt[3], c[3]; world_point(m, w, pc, pt);
       dof_point_vel(m, w, d, pt, c); acc += sg*dot3(U + 3*ui, c); }
     mom[z] = acc; }
   const idx_t* padr = CI(PT_piece_adr); const idx_t* piece = CI(PT_piece); const double* tconst = CD(PT_const);
-  for (int t = w.lane; t < m.nta; t += 32) { double l = tconst[t];
+  for (int t = m.tg_ta[g] + w.lane; t < m.tg_ta[g+1]; t += 32) { double l = tconst[t];
     #pragma unroll 1
     for (int e = padr[t]; e < padr[t+1]; e++) l += PL[piece[e]];
     tlen[t] = l; }
   __syncwarp();
-  const idx_t* nadr = CI(PT_nz_adr);
+}
+// after both passes: tendon velocities (moment . qvel); tendon forces start at zero
+__device__ void phase_tendon_velocity(const DevModel& m, const Warp w) {
+  const double* mom = SCR(s_mom); double* tvel = SCR(s_tvel); double* tfrc = SCR(s_tfrc);
+  const idx_t* nadr = CI(PT_nz_adr); const idx_t* nzd = CI(PNZ_dof);
   for (int t = w.lane; t < m.nta; t += 32) { double v = 0;
     #pragma unroll 1
     for (int z = nadr[t]; z < nadr[t+1]; z++) v += mom[z]*W_(qvel)[nzd[z]];
     tvel[t] = v; tfrc[t] = 0; }
   __syncwarp();
+}
+// both passes (groups A, B) + velocities: the whole tendon stage
+__device__ __forceinline__ void phase_tendon_all(const DevModel& m, const Warp w) {
+  #pragma unroll 1
+  for (int g = 0; g < 2; g++) if (m.tg_ta[g+1] > m.tg_ta[g]) { phase_tendon(m, w, g); phase_tendon_moments(m, w, g); }
+  phase_tendon_velocity(m, w);
 }
 
 // ------------------------------------------------------------------ phase 3: muscle actuation -> qfrc_smooth (passive + actuator); act integration
@@ -358,12 +379,12 @@ __device__ __forceinline__ double muscle_FL(double L, double lmin, double lmax) 
   return 0; }
 
 // tap_force / tap_len: nullable global rows for the parity taps (values before the activation is advanced)
-__device__ void phase_actuation(const DevModel& m, const Warp w, bool integrate, double* tap_force, double* tap_len) {
-  const idx_t* atend = CI(PA_tendon); const idx_t* acls = CI(PA_cls); const double* PAc = CD(PA_d); const double* PAm = CD(PAM_d);
+__device__ void phase_actuation(const DevModel& m, const Warp w, bool integrate, const double* ctrl_row, double* tap_force, double* tap_len) {
+  const idx_t* atend = CI(PA_tendon); const idx_t* acls = CI(PA_cls); const double* __restrict__ PAc = GD(PA_d); const double* __restrict__ PAm = GD(PAM_d);      // (cold tables: 17 + 5 independent read-only loads per actuator)
   double* tlen = SCR(s_tlen); double* tvel = SCR(s_tvel); double* tfrc = SCR(s_tfrc); double* mom = SCR(s_mom);
-  for (int i = w.lane; i < m.nu; i += 32) { const double* a = PAc + acls[i]*PA_STRIDE; const double* am = PAm + i*PAM_STRIDE; int t = atend[i];
+  for (int i = w.lane; i < m.nu; i += 32) { double a[PA_STRIDE]; { const double* __restrict__ ag = PAc + acls[i]*PA_STRIDE; for (int c = 0; c < 16; c++) a[c] = LDC(ag + c); } double am[5]; for (int c = 0; c < 5; c++) am[c] = LDC(PAm + i*PAM_STRIDE + c); int t = atend[i];
     const double *dyn = a, *gp = a+3, *bp = a+9, *cr = a+13; double gear = am[4], lr0 = am[2], lr1 = am[3];
-    double len = gear*tlen[t], vel = gear*tvel[t], ctrl = W_(ctrl)[i], act = W_(act)[i];
+    double len = gear*tlen[t], vel = gear*tvel[t], ctrl = ctrl_row[i], act = W_(act)[i];
     if (a[15] != 0) ctrl = clipd(ctrl, cr[0], cr[1]);
     // activation dynamics
     double cc = clipd(ctrl, 0, 1), ac = clipd(act, 0, 1), ta = dyn[0]*(0.5+1.5*ac), td = dyn[1]*m_rcp(0.5+1.5*ac), dctrl = cc - act, tau;
@@ -641,7 +662,7 @@ __device__ __forceinline__ bool expensive_candidate(const DevModel& m, const War
   double R1[9], R2[9], b[3], c[3], icd = m_rcp(cd), d[3] = {dv[0]*icd, dv[1]*icd, dv[2]*icd}; geom_mat(m, w, g1, R1); geom_mat(m, w, g2, R2); matT_vec(b, R1, d); matT_vec(c, R2, d);
   return cd - m_sqrt(s1[0]*s1[0]*b[0]*b[0]+s1[1]*s1[1]*b[1]*b[1]+s1[2]*s1[2]*b[2]*b[2]) - m_sqrt(s2[0]*s2[0]*c[0]*c[0]+s2[1]*s2[1]*c[1]*c[1]+s2[2]*s2[2]*c[2]*c[2]) <= margin; }
 
-__device__ __forceinline__ void store_contact(const DevModel& m, double* con, int* icon, int ci, int p, const Con1& c, const ConOut& o) {
+__device__ __forceinline__ void store_contact(const DevModel& m, double* con, idx_t* icon, int ci, int p, const Con1& c, const ConOut& o) {
   if (ci >= m.maxcon) return;
   double* cd = con + ci*CON_STRIDE; cd[0] = c.dist; cd[1] = c.px; cd[2] = c.py; cd[3] = c.pz;
   double* f = cd + 4; f[0] = c.nx; f[1] = c.ny; f[2] = c.nz;
@@ -651,14 +672,14 @@ __device__ __forceinline__ void store_contact(const DevModel& m, double* con, in
   if (y0*y0+y1*y1+y2*y2 < 0.25) { y0 = 0; y1 = 0; y2 = 0; if (c.ny < 0.5 && c.ny > -0.5) y1 = 1; else y2 = 1; }
   double dd = c.nx*y0+c.ny*y1+c.nz*y2; y0 -= dd*c.nx; y1 -= dd*c.ny; y2 -= dd*c.nz; double n = m_rcp(m_sqrt(y0*y0+y1*y1+y2*y2));
   f[3] = y0*n; f[4] = y1*n; f[5] = y2*n;
-  icon[ci] = p; }
+  icon[ci] = (idx_t)p; }
 
 // Contacts are found by the analytic colliders first ([0, na)), then by the iterative ellipsoid colliders ([na, ncon)), each run in model pair
 // order; phase_constraints ranks them into ONE model-pair order (contact reporting, numbering of the constraint rows) without moving records.
 // Overflow (more contacts than maxcon, or more surviving ellipsoid candidates than kcand): the extra ones are dropped first-come and
 // CNT_overflow is set; the step kernel ORs it into the caller's sticky per-env `overflow` buffer.
 __device__ void phase_collision(const DevModel& m, const Warp w) {
-  double* con = SCR(s_con); int* icon = S_cpair;
+  double* con = SCR(s_con); idx_t* icon = S_cpair;
   int ncon = 0, overflow = 0;
   geom_pose_all(m, w);
   // analytic primitives: one pair per lane

@@ -8,8 +8,36 @@
 // scratch views (stage 3/4): shared-space pointer expressions (m.s_* are offsets from the warp base)
 #define S_H SCR(s_H)
 #define S_con SCR(s_con)
-#define S_conJ SCR(s_conJ)
+// Contact Jacobian rows are STORED as the upper 48 bits of the f64 value (sign, exponent, 36 mantissa bits: a u32 high word and a u16 middle
+// word, rounded to nearest), i.e. 1.5e-11 relative per entry; the arithmetic stays f64 and no conversion instruction is needed to rebuild
+// the double.  Measured round 2: f32 storage (6e-8 per entry) moved qacc by up to 9e-5 relative on stiff multi-contact hand states -- beyond
+// the north-star's 1e-5 -- while f64 storage does not leave room for 14 env-warps per SM.  -DMYO_F64_ROWS stores plain doubles (the
+// verification build, abi.lib("f64rows")).  The regularisers D are f64 in both builds: one per equality / limit row and ONE per contact (the
+// rows of a contact share it), found through the byte map S_drow.
+struct JacRef {
+#ifdef MYO_F64_ROWS
+  double* p;
+  __device__ __forceinline__ double operator[](int i) const { return p[i]; }
+  __device__ __forceinline__ double put(int i, double v) const { p[i] = v; return v; }
+  __device__ __forceinline__ JacRef operator+(int k) const { return JacRef{p + k}; }
+#else
+  unsigned* h; unsigned short* l;
+  __device__ __forceinline__ double operator[](int i) const { return __hiloint2double((int)h[i], (int)((unsigned)l[i] << 16)); }
+  __device__ __forceinline__ double put(int i, double v) const {            // stores and returns the rounded value
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v) + 0x8000ull; const unsigned hi = (unsigned)(b >> 32), mid = (unsigned)(b >> 16) & 0xffffu;
+    h[i] = hi; l[i] = (unsigned short)mid; return __hiloint2double((int)hi, (int)(mid << 16)); }
+  __device__ __forceinline__ JacRef operator+(int k) const { return JacRef{h + k, l + k}; }
+#endif
+};
+#ifdef MYO_F64_ROWS
+#define JAC_BYTES 8
+#define S_jac(c) (JacRef{SCR(s_conJ) + (c)*3*m.maxpath})
+#else
+#define JAC_BYTES 6
+#define S_jac(c) (JacRef{(unsigned*)SCR(s_conJ) + (c)*3*m.maxpath, (unsigned short*)((unsigned*)SCR(s_conJ) + 3*m.maxpath*m.maxcon) + (c)*3*m.maxpath})
+#endif
 #define S_D SCR(s_efD)
+#define S_DCON(c) (m.neq + m.nlimrow + (c))      // index of contact c's regulariser in S_D
 #define S_aref SCR(s_efA)
 #define S_jar SCR(s_efR)
 #define S_jv SCR(s_efV)
@@ -24,11 +52,12 @@
 #define S_Dinv SCR(s_Dinv)
 // integer records of the contact / row lists (S_cpair is defined in myo_device.cuh: the colliders write it)
 #define S_cmask ((unsigned long long*)SCR(s_icon))   // contact -> bit mask of the dofs on its path (the Jacobian's non-zero columns, ascending)
-#define S_crown (S_cpair + m.maxcon)           // contact -> first efc row | number of rows << 12 | rank in model pair order << 16
+#define S_crown ((int*)(SCR(s_icon) + m.maxcon))     // contact -> first efc row | number of rows << 12 | rank in model pair order << 16
 #define CROW(rn) ((rn) & 0xfff)
 #define CNR(rn) (((rn) >> 12) & 7)
 #define CRANK(rn) ((rn) >> 16)
-#define S_lrow (S_cpair + 2*m.maxcon)          // limit row descriptors (dof | side << 16)
+#define S_lrow (S_cpair + m.maxcon)            // limit row descriptors, int16: dof | side << 8
+#define S_drow ((unsigned char*)(S_lrow + m.nlimrow + 4))      // constraint row -> index of its regulariser in S_D
 
 __device__ __forceinline__ double impedance(const double* si, double pos, double margin) {
   if (si[0] == si[1] || si[2] <= MYO_MINVAL) return 0.5*(si[0]+si[1]);
@@ -51,10 +80,10 @@ __device__ void rows_apply(const DevModel& m, const Warp w, const double* x, dou
   SHARED_PTR(x); SHARED_PTR(out);
   const idx_t* eq = CI(PEQ); const int nlimrow = WI_(nlimrow), ncon = WI_(ncon);
   for (int e = w.lane; e < m.neq; e += 32) { double v = x[eq[PEQ_ISTRIDE*e+1]]; if (eq[PEQ_ISTRIDE*e+3] >= 0) v += S_eqJ[e]*x[eq[PEQ_ISTRIDE*e+3]]; out[e] = v; }
-  for (int r = w.lane; r < nlimrow; r += 32) { int dsc = S_lrow[r]; double sg = (dsc >> 16) & 1 ? -1.0 : 1.0; out[m.neq + r] = sg*x[dsc & 0xffff]; }
+  for (int r = w.lane; r < nlimrow; r += 32) { int dsc = S_lrow[r]; double sg = (dsc >> 8) & 1 ? -1.0 : 1.0; out[m.neq + r] = sg*x[dsc & 0xff]; }
   const idx_t* pr = CI(PPAIR); const double* pd = CD(PPAIR_d); const idx_t* path = CI(PPATH);
   for (int c = w.lane; c < ncon; c += 32) { const int rn = S_crown[c], nr = CNR(rn); if (!nr) continue;
-    const idx_t* q = pr + PPAIR_ISTRIDE*S_cpair[c]; const double* J = S_conJ + c*3*m.maxpath; double n = 0, t1 = 0, t2 = 0;
+    const idx_t* q = pr + PPAIR_ISTRIDE*S_cpair[c]; const JacRef J = S_jac(c); double n = 0, t1 = 0, t2 = 0;
     for (int e = 0; e < q[4]; e++) { double xv = x[path[q[3]+e] >> 1]; n += J[3*e]*xv; t1 += J[3*e+1]*xv; t2 += J[3*e+2]*xv; }
     int rb = CROW(rn);
     if (nr == 1) out[rb] = n;
@@ -71,12 +100,12 @@ __device__ void rows_applyT_add(const DevModel& m, const Warp w, double* wgt, do
   if (w.lane == 0) for (int e = 0; e < m.neq; e++) { vec[eq[PEQ_ISTRIDE*e+1]] += wgt[e]; if (eq[PEQ_ISTRIDE*e+3] >= 0) vec[eq[PEQ_ISTRIDE*e+3]] += S_eqJ[e]*wgt[e]; }
   __syncwarp();
   for (int pass = 0; pass < 2; pass++) {
-    for (int r = w.lane; r < nlimrow; r += 32) { int dsc = S_lrow[r]; int neg = (dsc >> 16) & 1; if (neg == pass) vec[dsc & 0xffff] += (neg ? -1.0 : 1.0)*wgt[m.neq + r]; }
+    for (int r = w.lane; r < nlimrow; r += 32) { int dsc = S_lrow[r]; int neg = (dsc >> 8) & 1; if (neg == pass) vec[dsc & 0xff] += (neg ? -1.0 : 1.0)*wgt[m.neq + r]; }
     __syncwarp(); }
 #ifdef MYO_OLD_GRAD
   { const idx_t* pr = CI(PPAIR); const double* pd = CD(PPAIR_d); const idx_t* path = CI(PPATH);
   for (int c = 0; c < ncon; c++) { const int rn = S_crown[c], nr = CNR(rn); if (!nr) continue;
-    const idx_t* q = pr + PPAIR_ISTRIDE*S_cpair[c]; const double* J = S_conJ + c*3*m.maxpath; int rb = CROW(rn); double wn, w1 = 0, w2 = 0;
+    const idx_t* q = pr + PPAIR_ISTRIDE*S_cpair[c]; const JacRef J = S_jac(c); int rb = CROW(rn); double wn, w1 = 0, w2 = 0;
     if (nr == 1) wn = wgt[rb];
     else { wn = wgt[rb]+wgt[rb+1]+wgt[rb+2]+wgt[rb+3]; w1 = wgt[rb]-wgt[rb+1]; w2 = wgt[rb+2]-wgt[rb+3]; }
     for (int e = w.lane; e < q[4]; e += 32) vec[path[q[3]+e] >> 1] += J[3*e]*wn + J[3*e+1]*w1 + J[3*e+2]*w2;
@@ -90,7 +119,7 @@ __device__ void rows_applyT_add(const DevModel& m, const Warp w, double* wgt, do
   __syncwarp();
   for (int d = w.lane; d < m.nv; d += 32) { double acc = 0; const unsigned long long below = (1ull << d) - 1;
     for (int c = 0; c < ncon; c++) { const unsigned long long mk = S_cmask[c];
-      if ((mk >> d) & 1) { const int rn = S_crown[c], nr = CNR(rn), rb = CROW(rn); const double* J = S_conJ + c*3*m.maxpath + 3*__popcll(mk & below);
+      if ((mk >> d) & 1) { const int rn = S_crown[c], nr = CNR(rn), rb = CROW(rn); const JacRef J = S_jac(c) + 3*__popcll(mk & below);
         if (nr == 4) acc += J[0]*wgt[rb] + J[1]*wgt[rb+1] + J[2]*wgt[rb+2]; else if (nr == 1) acc += J[0]*wgt[rb]; } }
     vec[d] += acc; }
   __syncwarp();
@@ -107,17 +136,17 @@ __device__ void phase_constraints(const DevModel& m, const Warp w) {
     else cpos = pos0-c[0];
     S_eqJ[e] = -deriv;
     double imp = impedance(c+10, cpos, 0), R = fmax(MYO_MINVAL, (1-imp)*c[7]*m_rcp(imp));
-    S_D[e] = m_rcp(R); S_aref[e] = -c[9]*vel - c[8]*imp*cpos; }
+    S_D[e] = m_rcp(R); S_drow[e] = (unsigned char)e; S_aref[e] = -c[9]*vel - c[8]*imp*cpos; }
   // joint limits (one-sided)
-  const idx_t* lim = CI(PLIM); const double* limd = CD(PLIM_d); int nrow = 0;
-  for (int base = 0; base < m.nlim; base += 32) { int l = base + w.lane; bool lo = false, hi = false; double dlo = 0, dhi = 0; const double* c = limd + (l < m.nlim ? l : 0)*PLIM_STRIDE; int d = 0;
+  const idx_t* lim = CI(PLIM); const double* __restrict__ limd = GD(PLIM_d); int nrow = 0;      // (cold table: one 12-double record per limited joint, read once per substep)
+  for (int base = 0; base < m.nlim; base += 32) { int l = base + w.lane; bool lo = false, hi = false; double dlo = 0, dhi = 0; double c[PLIM_STRIDE]; for (int k = 0; k < PLIM_STRIDE; k++) c[k] = LDC(limd + (l < m.nlim ? l : 0)*PLIM_STRIDE + k); int d = 0;
     if (l < m.nlim) { d = lim[2*l]; double q = W_(qpos)[lim[2*l+1]]; dlo = q-c[0]; dhi = c[1]-q; lo = dlo < c[2]; hi = dhi < c[2]; }
     unsigned m0 = __ballot_sync(FULL, lo), m1 = __ballot_sync(FULL, hi), lt = (1u << w.lane)-1; int idx = nrow + __popc(m0 & lt) + __popc(m1 & lt);
     for (int side = 0; side < 2; side++) { if (!(side ? hi : lo)) continue;
       double dist = side ? dhi : dlo, sg = side ? -1.0 : 1.0; int r = m.neq + idx; idx++;
-      S_lrow[r - m.neq] = d | (side << 16);
+      S_lrow[r - m.neq] = (idx_t)(d | (side << 8));
       double imp = impedance(c+6, dist, c[2]), R = fmax(MYO_MINVAL, (1-imp)*c[3]*m_rcp(imp));
-      S_D[r] = m_rcp(R); S_aref[r] = -c[5]*sg*W_(qvel)[d] - c[4]*imp*(dist-c[2]); }
+      S_D[r] = m_rcp(R); S_drow[r] = (unsigned char)r; S_aref[r] = -c[5]*sg*W_(qvel)[d] - c[4]*imp*(dist-c[2]); }
     nrow += __popc(m0) + __popc(m1); }
   WI_(nlimrow) = nrow;
   // contacts: Jacobian over the dofs between the two bodies, regulariser, reference acceleration.
@@ -126,7 +155,7 @@ __device__ void phase_constraints(const DevModel& m, const Warp w) {
   // numbering of the constraint rows, which are assigned in rank order.
   const idx_t* pr = CI(PPAIR); const double* pd = CD(PPAIR_d); const idx_t* path = CI(PPATH);
   int rowbase = m.neq + nrow; const int ncon = WI_(ncon), na = WI_(na);
-  int* key = (int*)S_conJ;                              // scratch: the Jacobians are written after the last read of the keys
+  int* key = (int*)SCR(s_conJ);                              // scratch: the Jacobians are written after the last read of the keys
   for (int c = w.lane; c < ncon; c += 32) key[c] = pr[PPAIR_ISTRIDE*S_cpair[c] + 7];
   __syncwarp();
   int nrs[2] = {0, 0}, rank[2] = {0, 0}, rbs[2] = {0, 0};
@@ -157,16 +186,17 @@ __device__ void phase_constraints(const DevModel& m, const Warp w) {
   for (int s = 0; s < 2; s++) { const int c = w.lane + 32*s, nr = nrs[s], rb = rbs[s];
     if (c < ncon) S_crown[c] = rb | (nr << 12) | (rank[s] << 16);
     if (c < ncon && nr) { const idx_t* q = pr + PPAIR_ISTRIDE*S_cpair[c]; const double* P = pd + q[6]*PPAIR_STRIDE; const double* cd = S_con + c*CON_STRIDE;
-      const double* pos = cd + 1; double f[9]; for (int k = 0; k < 6; k++) f[k] = cd[4+k]; cross3(f+6, f, f+3); double* J = S_conJ + c*3*m.maxpath; double vn = 0, v1 = 0, v2 = 0;
+      const double* pos = cd + 1; double f[9]; for (int k = 0; k < 6; k++) f[k] = cd[4+k]; cross3(f+6, f, f+3); const JacRef J = S_jac(c); double vn = 0, v1 = 0, v2 = 0;
       unsigned long long mk = 0; const double mu1 = P[2], mu2 = P[3];
       for (int e = 0; e < q[4]; e++) { int code = path[q[3]+e], d = code >> 1; double sg = (code & 1) ? 1.0 : -1.0, cv[3]; dof_point_vel(m, w, d, pos, cv); mk |= 1ull << d;
-        double jn = sg*dot3(f, cv), j1 = sg*mu1*dot3(f+3, cv), j2 = sg*mu2*dot3(f+6, cv); J[3*e] = jn; J[3*e+1] = j1; J[3*e+2] = j2;      // tangents stored times mu: the pyramid edges are n +- mu t
-        double qd = W_(qvel)[d]; vn += jn*qd; v1 += j1*qd; v2 += j2*qd; }
+        const double jn = J.put(3*e, sg*dot3(f, cv)), j1 = J.put(3*e+1, sg*mu1*dot3(f+3, cv)), j2 = J.put(3*e+2, sg*mu2*dot3(f+6, cv));      // tangents stored times mu: the pyramid edges are n +- mu t
+        double qd = W_(qvel)[d]; vn += jn*qd; v1 += j1*qd; v2 += j2*qd; }      // (aref from the stored Jacobian: consistent with J v in the solver)
       S_cmask[c] = mk;
-      double dist = cd[0], inc = P[0]-P[1], imp = impedance(P+7, dist, inc), K = P[5], B = P[6], tran = CD(PPAIR_tran)[S_cpair[c]];
-      if (nr == 1) { double R = fmax(MYO_MINVAL, (1-imp)*tran*m_rcp(imp)); S_D[rb] = m_rcp(R); S_aref[rb] = -B*vn - K*imp*(dist-inc); }
+      double dist = cd[0], inc = P[0]-P[1], imp = impedance(P+7, dist, inc), K = P[5], B = P[6], tran = LDC(GD(PPAIR_tran) + S_cpair[c]);
+      const unsigned char dc = (unsigned char)S_DCON(c);
+      if (nr == 1) { double R = fmax(MYO_MINVAL, (1-imp)*tran*m_rcp(imp)); S_D[dc] = m_rcp(R); S_drow[rb] = dc; S_aref[rb] = -B*vn - K*imp*(dist-inc); }
       else { double R0 = fmax(MYO_MINVAL, (1-imp)*(tran+mu1*mu1*tran)*m_rcp(imp)), Rpy = 2*mu1*mu1*R0, Dv = m_rcp(Rpy), kp = K*imp*(dist-inc);
-        S_D[rb] = S_D[rb+1] = S_D[rb+2] = S_D[rb+3] = Dv;
+        S_D[dc] = Dv; S_drow[rb] = S_drow[rb+1] = S_drow[rb+2] = S_drow[rb+3] = dc;
         S_aref[rb] = -B*(vn+v1)-kp; S_aref[rb+1] = -B*(vn-v1)-kp; S_aref[rb+2] = -B*(vn+v2)-kp; S_aref[rb+3] = -B*(vn-v2)-kp; } } }
   WI_(nefc) = rowbase;
   __syncwarp();
@@ -413,7 +443,9 @@ __device__ void ldl_solve(const DevModel& m, const Warp w, const double* LD, con
 // barriers at the top of each Newton iteration and before the Cholesky, so that they keep sharing instruction fetches inside the
 // phase too (a lone 23x23 register Cholesky costs 29 k cycles out of step with the other warps, 21 k in step); finished and idle
 // warps only take part in the barriers.  The total wait is unchanged: the CTA leaves the phase with its slowest env either way.
-__device__ void phase_solve(const DevModel& m, const Warp w, double tol, long long* cyc, bool live, bool cta_sync) {
+// __forceinline__: as a real call the function receives the DevModel by address and every m.field becomes a generic load that is repeated
+// after each shared-memory store (measured round 2: 310 LD.E in the solver of the launch_bounds(448) kernel, which had not inlined it).
+__device__ __forceinline__ void phase_solve(const DevModel& m, const Warp w, double tol, long long* cyc, bool live, bool cta_sync) {
   long long tc = cyc ? clock64() : 0;
   #define LAP(k) if (cyc) { long long t_ = clock64(); cyc[k] += t_ - tc; tc = t_; }
   int n = m.nv, nefc = live ? WI_(nefc) : 0; const int ncon = live ? WI_(ncon) : 0, nlimrow = live ? WI_(nlimrow) : 0; int niter = 0;
@@ -434,7 +466,7 @@ __device__ void phase_solve(const DevModel& m, const Warp w, double tol, long lo
     if (active) {
     // gradient
     for (int i = w.lane; i < n; i += 32) S_g[i] = S_Ma[i]-W_(fsm)[i];
-    for (int r = w.lane; r < nefc; r += 32) { double x = S_jar[r]; S_jv[r] = (r < m.neq || x < 0) ? S_D[r]*x : 0.0; }   // jv used as scratch weights
+    for (int r = w.lane; r < nefc; r += 32) { double x = S_jar[r]; S_jv[r] = (r < m.neq || x < 0) ? S_D[S_drow[r]]*x : 0.0; }   // jv used as scratch weights
     __syncwarp(); rows_applyT_add(m, w, S_jv, S_g); __syncwarp();
     double gn = 0; for (int i = w.lane; i < n; i += 32) gn += S_g[i]*S_g[i]; gn = sqrt(warp_sum(gn));
     LAP(8)
@@ -445,7 +477,7 @@ __device__ void phase_solve(const DevModel& m, const Warp w, double tol, long lo
     dense = (m.neq > 0 && !m.eq_tree);
     for (int c = w.lane; c < ncon && !dense; c += 32) { const int rn = S_crown[c], nr = CNR(rn), rb = CROW(rn); for (int r = 0; r < nr; r++) if (S_jar[rb+r] < 0) dense = true; }
     dense = __any_sync(FULL, dense);
-    for (int i = w.lane; i < n; i += 32) S_p[i] = -S_g[i];
+    for (int i = w.lane; i < n; i += 32) S_p[i] = -S_g[i];      // (p shares g's storage: the gradient is not read again this iteration)
     __syncwarp();
     if (cyc && dense) cyc[15]++;
     if (!dense) {
@@ -455,7 +487,7 @@ __device__ void phase_solve(const DevModel& m, const Warp w, double tol, long lo
       if (w.lane == 0) for (int e = 0; e < m.neq; e++) { int d1 = eq[PEQ_ISTRIDE*e+1], d2 = eq[PEQ_ISTRIDE*e+3]; double De = S_D[e], j2 = S_eqJ[e]; S_Hs[madr[d1]] += De;
         if (d2 >= 0) { S_Hs[eq[PEQ_ISTRIDE*e+4]] += De*j2; S_Hs[madr[d2]] += De*j2*j2; } }
       __syncwarp();
-      for (int pass = 0; pass < 2; pass++) { for (int r = w.lane; r < nlimrow; r += 32) { int dsc = S_lrow[r]; if (((dsc >> 16) & 1) == pass && S_jar[m.neq+r] < 0) S_Hs[madr[dsc & 0xffff]] += S_D[m.neq+r]; } __syncwarp(); }
+      for (int pass = 0; pass < 2; pass++) { for (int r = w.lane; r < nlimrow; r += 32) { int dsc = S_lrow[r]; if (((dsc >> 8) & 1) == pass && S_jar[m.neq+r] < 0) S_Hs[madr[dsc & 0xff]] += S_D[m.neq+r]; } __syncwarp(); }
       LAP(9)
       ldl_factor(m, w, S_Hs, S_LD, S_Dinv); ldl_solve(m, w, S_LD, S_Dinv, S_p);
       LAP(10)
@@ -464,18 +496,18 @@ __device__ void phase_solve(const DevModel& m, const Warp w, double tol, long lo
     if (w.lane == 0) for (int e = 0; e < m.neq; e++) { int d1 = eq[PEQ_ISTRIDE*e+1], d2 = eq[PEQ_ISTRIDE*e+3]; double De = S_D[e], j2 = S_eqJ[e]; S_H[TRI(d1,d1)] += De;
       if (d2 >= 0) { S_H[d1 > d2 ? TRI(d1,d2) : TRI(d2,d1)] += De*j2; S_H[TRI(d2,d2)] += De*j2*j2; } }
     __syncwarp();
-    for (int pass = 0; pass < 2; pass++) { for (int r = w.lane; r < nlimrow; r += 32) { int dsc = S_lrow[r]; if (((dsc >> 16) & 1) == pass && S_jar[m.neq+r] < 0) { int d = dsc & 0xffff; S_H[TRI(d,d)] += S_D[m.neq+r]; } } __syncwarp(); }
+    for (int pass = 0; pass < 2; pass++) { for (int r = w.lane; r < nlimrow; r += 32) { int dsc = S_lrow[r]; if (((dsc >> 8) & 1) == pass && S_jar[m.neq+r] < 0) { int d = dsc & 0xff; S_H[TRI(d,d)] += S_D[m.neq+r]; } } __syncwarp(); }
     // contacts: J' W J, one contact at a time, one lane per entry of the lower triangle of its block (the gather form that pays for the
     // gradient does not pay here: with one H entry per lane nearly every contact hits SOME lane and the warp runs the hit path 9 x ncon times)
     for (int c = 0; c < ncon; c++) { const int rn = S_crown[c], nr = CNR(rn), rb = CROW(rn); if (!nr) continue; const idx_t* q = pr + PPAIR_ISTRIDE*S_cpair[c]; double W[6] = {0,0,0,0,0,0};  // nn n1 n2 11 12 22
-      if (nr == 1) { if (S_jar[rb] < 0) W[0] = S_D[rb]; }
-      else { const double Dv = S_D[rb];
+      if (nr == 1) { if (S_jar[rb] < 0) W[0] = S_D[S_DCON(c)]; }
+      else { const double Dv = S_D[S_DCON(c)];
         double a0 = S_jar[rb] < 0 ? Dv : 0, a1 = S_jar[rb+1] < 0 ? Dv : 0, a2 = S_jar[rb+2] < 0 ? Dv : 0, a3 = S_jar[rb+3] < 0 ? Dv : 0;
         W[0] = a0+a1+a2+a3; W[1] = a0-a1; W[2] = a2-a3; W[3] = a0+a1; W[5] = a2+a3; }
-      if (W[0] != 0) { const double* J = S_conJ + c*3*m.maxpath; int np = q[4], ntri = (np*(np+1)) >> 1;
+      if (W[0] != 0) { const JacRef J = S_jac(c); int np = q[4], ntri = (np*(np+1)) >> 1;
         for (int t = w.lane; t < ntri; t += 32) { int ei, ej;
           if (np <= 8) { ei = (t >= 1) + (t >= 3) + (t >= 6) + (t >= 10) + (t >= 15) + (t >= 21) + (t >= 28); ej = t - ((ei*(ei+1)) >> 1); } else tri_index(t, ei, ej);
-          const double* a = J + 3*ei; const double* b = J + 3*ej;
+          const JacRef ja = J + 3*ei, jb = J + 3*ej; const double a[3] = {ja[0], ja[1], ja[2]}, b[3] = {jb[0], jb[1], jb[2]};
           double wa0 = W[0]*a[0]+W[1]*a[1]+W[2]*a[2], wa1 = W[1]*a[0]+W[3]*a[1], wa2 = W[2]*a[0]+W[5]*a[2];
           int di = path[q[3]+ei] >> 1, dj = path[q[3]+ej] >> 1; S_H[TRI(di,dj)] += wa0*b[0]+wa1*b[1]+wa2*b[2]; } }
       __syncwarp(); }
@@ -489,7 +521,7 @@ __device__ void phase_solve(const DevModel& m, const Warp w, double tol, long lo
     double ga = 0, gb = 0; for (int i = w.lane; i < n; i += 32) { ga += S_p[i]*(S_Ma[i]-W_(fsm)[i]); gb += S_p[i]*S_Mp[i]; } ga = warp_sum(ga); gb = warp_sum(gb);
     double alpha = 0, lo = 0, hi = -1, d0 = 0;
     for (int it = 0; it < 40; it++) { double dv = 0, hh = 0;
-      for (int r = w.lane; r < nefc; r += 32) { double x = S_jar[r]+alpha*S_jv[r]; if (r < m.neq || x < 0) { dv += S_D[r]*x*S_jv[r]; hh += S_D[r]*S_jv[r]*S_jv[r]; } }
+      for (int r = w.lane; r < nefc; r += 32) { double x = S_jar[r]+alpha*S_jv[r]; if (r < m.neq || x < 0) { const double Dr = S_D[S_drow[r]], jv = S_jv[r]; dv += Dr*x*jv; hh += Dr*jv*jv; } }
       dv = warp_sum(dv) + ga + gb*alpha; hh = warp_sum(hh) + gb;
       if (it == 0) { d0 = fabs(dv); if (dv >= 0) break; } else { if (dv < 0) lo = alpha; else hi = alpha; if (fabs(dv) <= 1e-10*d0) break; }
       double an = alpha - dv*m_rcp(hh);

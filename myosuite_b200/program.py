@@ -21,8 +21,8 @@ from . import mjmath as mm
 # P_dims slots
 (PD_NBD, PD_NLEVEL, PD_NPT, PD_NSP, PD_NWE, PD_NTA, PD_NNZ, PD_NTERM, PD_NLIM, PD_NEQ, PD_NPAIR, PD_NGC, PD_MAXPATH,
  PD_MAXCHAIN, PD_NSUB, PD_NROW, PD_NCOL, PD_NPIECE, PD_NWE_SPH_OUT, PD_NWE_SPH_IN, PD_NWE_CYL_OUT, PD_NWE_CYL_IN,
- PD_NDEPTH, PD_EQ_TREE, PD_NPAIR_ANALYTIC, PD_NLIMROW) = range(26)
-NPDIM = 26
+ PD_NDEPTH, PD_EQ_TREE, PD_NPAIR_ANALYTIC, PD_NLIMROW, PD_SPLIT_SP, PD_SPLIT_WE, PD_SPLIT_TA, PD_SPLIT_NZ) = range(30)
+NPDIM = 30
 
 PB_STRIDE, PWE_STRIDE, PA_STRIDE, PG_STRIDE, PPAIR_STRIDE, PLIM_STRIDE, PEQ_STRIDE = 22, 16, 17, 16, 12, 12, 16
 PAM_STRIDE, PPAIR_ISTRIDE = 6, 8
@@ -209,8 +209,35 @@ def build_program(m, allow_unsupported=ALLOWED_UNSUPPORTED_PAIRS):
     act_tendons = sorted(set(int(t) for t in m.actuator_trnid[:, 0])) if m.nu else []
     if m.nu and not np.all(m.actuator_trntype == mjcf.TRN_TENDON):
         raise mjcf.MJCFError("only tendon transmissions are supported")
+    # Two passes over the tendons (group A = the first `split` program tendons, B = the rest): the unit vectors and piece lengths of a pass are
+    # dead once its moments and lengths are formed, so the kernel's scratch holds one group at a time.  The program's tendon ORDER is internal
+    # (actuators reach their tendon through PA_tendon), so the groups are chosen as a subset: first keep the number of 32-lane rounds over the
+    # straight segments and the wrap elements minimal (a group of 33 wrap elements costs a whole extra round of the wrap code for one lane),
+    # then balance the two groups' scratch need.
+    def _count(t):
+        adr, num = int(m.tendon_adr[t]), int(m.tendon_num[t]); ns = nw = 0; j = 0
+        while j < num - 1:
+            if m.wrap_type[adr + j + 1] == mjcf.WRAP_SITE:
+                ns += 0 if _same_rigid(m, int(m.site_bodyid[int(m.wrap_objid[adr + j])]), int(m.site_bodyid[int(m.wrap_objid[adr + j + 1])])) else 1; j += 1
+            else:
+                nw += 1; j += 2
+        return ns, nw
+    _cnt = {t: _count(t) for t in act_tendons}
+    _need = lambda ns, nw: 3 * (ns + 2 * nw) + ns + nw
+    _reach = {(0, 0): 0}                                       # (ns, nw) of a subset -> bit mask of one subset reaching it
+    for k_, t in enumerate(act_tendons):
+        for (ns_, nw_), msk in list(_reach.items()):
+            key = (ns_ + _cnt[t][0], nw_ + _cnt[t][1])
+            if key not in _reach:
+                _reach[key] = msk | (1 << k_)
+    _NS, _NW = sum(c[0] for c in _cnt.values()), sum(c[1] for c in _cnt.values())
+    _r32 = lambda x: (x + 31) // 32
+    _best = min(_reach, key=lambda q: (_r32(q[0]) + _r32(_NS - q[0]) + _r32(q[1]) + _r32(_NW - q[1]), max(_need(*q), _need(_NS - q[0], _NW - q[1])), q))
+    _msk = _reach[_best]
+    act_tendons = [t for k_, t in enumerate(act_tendons) if (_msk >> k_) & 1] + [t for k_, t in enumerate(act_tendons) if not (_msk >> k_) & 1]
+    split = bin(_msk).count("1")
     ta_index = {t: k for k, t in enumerate(act_tendons)}
-    sp_list, we_list = [], []      # runtime pieces
+    sp_list, we_list, sp_ta = [], [], []      # runtime pieces (sp_ta: tendon of each straight segment)
     T_const, T_pieces = [], []     # per active tendon
     # term bookkeeping: terms[(ta, dof)] = list of (ukind, uidx, ptcode, sign)
     terms = {}
@@ -241,7 +268,7 @@ def build_program(m, allow_unsupported=ALLOWED_UNSUPPORTED_PAIRS):
                 else:
                     pa, pb = site_ref(s0), site_ref(s1)
                     k = len(sp_list)
-                    sp_list.append((pa, pb))
+                    sp_list.append((pa, pb)); sp_ta.append(ta)
                     pieces.append(("S", k))
                     add_terms(ta, b0, b1, ("S", k), pa, pb)
                 j += 1
@@ -271,11 +298,29 @@ def build_program(m, allow_unsupported=ALLOWED_UNSUPPORTED_PAIRS):
                 pieces.append(("W", k))
                 j += 2
         T_const.append(const); T_pieces.append(pieces)
-    # sort wrap elements by (type, inside) so that a warp round is branch-uniform
-    we_order = sorted(range(len(we_list)), key=lambda k: (-we_list[k]["inside"], we_list[k]["typ"], k))
+    nta_all = len(act_tendons)
+    grp = lambda ta_: 0 if ta_ < split else 1
+    # within a group: wrap elements by (inside, type) so that a warp round is branch-uniform
+    we_order = sorted(range(len(we_list)), key=lambda k: (grp(we_list[k]["ta"]), -we_list[k]["inside"], we_list[k]["typ"], k))
     we_new = {old: new for new, old in enumerate(we_order)}
     we_sorted = [we_list[k] for k in we_order]
     nsp, nwe = len(sp_list), len(we_sorted)
+    sp0 = [0, sum(1 for t_ in sp_ta if t_ < split), nsp]                      # straight segments are generated in tendon order: already grouped
+    we0 = [0, sum(1 for w_ in we_sorted if w_["ta"] < split), nwe]
+    nspg = [sp0[1] - sp0[0], sp0[2] - sp0[1]]
+
+    def u_local(ta_, kind, idx):
+        """index of a unit-vector slot / piece inside its group's scratch: segments first, then two slots (one length) per wrap element"""
+        g_ = grp(ta_)
+        return idx - sp0[g_] if kind == "S" else nspg[g_] + (idx - 2 * we0[g_])
+
+    def pl_local(ta_, kind, idx):
+        g_ = grp(ta_)
+        return idx - sp0[g_] if kind == "S" else nspg[g_] + (idx - we0[g_])
+    wz_slot, nwz_ = {}, 0
+    for new_, w_ in enumerate(we_sorted):
+        if w_["inside"]:
+            wz_slot[new_] = nwz_; nwz_ += 1
     for new, w in enumerate(we_sorted):
         # piece A: pa (b0) -> w0 (bg), unit slot nsp+2*new ; piece B: w1 (bg) -> pb (b1), unit slot nsp+2*new+1
         # The moment of a straight piece is  u . (axis x (p - anchor))  for ANY point p on the piece's line (p may slide along u), so the
@@ -286,9 +331,9 @@ def build_program(m, allow_unsupported=ALLOWED_UNSUPPORTED_PAIRS):
     for w in we_sorted:
         counts[2 * w["typ"] + w["inside"]] += 1
     PT_piece_adr, PT_piece = [0], []
-    for pieces in T_pieces:
+    for ta_, pieces in enumerate(T_pieces):
         for kind, k in pieces:
-            PT_piece.append(k if kind == "S" else nsp + we_new[k])
+            PT_piece.append(pl_local(ta_, kind, k if kind == "S" else we_new[k]))
         PT_piece_adr.append(len(PT_piece))
     # non-zeros sorted by (tendon, dof)
     keys = sorted(terms.keys())
@@ -297,7 +342,7 @@ def build_program(m, allow_unsupported=ALLOWED_UNSUPPORTED_PAIRS):
     for (ta, d) in keys:
         PNZ_dof.append(d); PNZ_tendon.append(ta); PT_nz_adr[ta + 1] += 1
         for (ukind, uk), ptcode, sign in terms[(ta, d)]:
-            PTERM += [uk if ukind == "S" else nsp + uk, ptcode, sign]
+            PTERM += [u_local(ta, ukind, uk), ptcode, sign]
         PNZ_term_adr.append(len(PTERM) // 3)
     PT_nz_adr = np.cumsum(PT_nz_adr).tolist()
     cols = [[] for _ in range(nv)]
@@ -306,7 +351,8 @@ def build_program(m, allow_unsupported=ALLOWED_UNSUPPORTED_PAIRS):
     PCOL_adr, PCOL = [0], []
     for d in range(nv):
         PCOL += cols[d]; PCOL_adr.append(len(PCOL))
-    PWE = np.array([[w["pa"], w["pb"], w["gb"], w["typ"], w["side"], w["inside"]] for w in we_sorted], dtype=np.int32).reshape(-1, 6)
+    # [5]: 0 = outside wrap, else 1 + slot of this element's warm-started inverse-wrap root
+    PWE = np.array([[w["pa"], w["pb"], w["gb"], w["typ"], w["side"], (1 + wz_slot[k_]) if w["inside"] else 0] for k_, w in enumerate(we_sorted)], dtype=np.int32).reshape(-1, 6)
     PWE_d = np.zeros((nwe, PWE_STRIDE))
     for k, w in enumerate(we_sorted):
         PWE_d[k, 0:3], PWE_d[k, 3:12], PWE_d[k, 12] = w["gpos"], np.asarray(w["gmat"]).ravel(), w["r"]
@@ -442,6 +488,8 @@ def build_program(m, allow_unsupported=ALLOWED_UNSUPPORTED_PAIRS):
     dims[PD_NDEPTH], dims[PD_EQ_TREE], dims[PD_NPAIR_ANALYTIC] = ndepth, eq_tree, n_analytic
     # limit rows that can be active at once: both sides of a joint only when its range is narrower than twice the margin
     dims[PD_NLIMROW] = sum(2 if (r[1] - r[0]) < 2 * r[2] else 1 for r in PLIM_d)
+    dims[PD_SPLIT_SP], dims[PD_SPLIT_WE], dims[PD_SPLIT_TA] = sp0[1], we0[1], split
+    dims[PD_SPLIT_NZ] = sum(1 for t_ in PNZ_tendon if t_ < split)
 
     def ia(x, shape=None):
         a = np.asarray(x, dtype=np.int32)

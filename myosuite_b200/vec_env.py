@@ -87,7 +87,12 @@ class MyoVecEnv:
         prog, self.prog_info = program.build_program(m)
         self.prog = prog
         self.I, self.D = blob.pack(m, prog)
-        self.dev_model = abi.DeviceModel(self.I, self.D)
+        # row_storage: "p48" (product: contact Jacobian rows held as the upper 48 bits of the f64 value -- 36 mantissa bits -- in shared memory,
+        # 14 env-warps per SM on the hand) or "f64" (verification build of the same source, abi.lib("f64rows"): plain doubles, fewer warps)
+        self.row_storage = kw.get("row_storage", "p48")
+        if self.row_storage not in ("p48", "f64"):
+            raise ValueError("row_storage must be 'p48' or 'f64'")
+        self.dev_model = abi.DeviceModel(self.I, self.D, variant="f64rows" if self.row_storage == "f64" else None)
         cfg = abi.MyoTaskCfg()
         cfg.task = {"none": abi.TASK_NONE, "pose": abi.TASK_POSE, "walk": abi.TASK_WALK, "hold": abi.TASK_HOLD, "reach": abi.TASK_REACH}[self.task]
         cfg.frame_skip = self.n_frames
@@ -187,7 +192,7 @@ class MyoVecEnv:
               "target_jnt_value", "viz_site_targets", "target_reach_range", "far_th", "min_height", "max_rot", "hip_period", "target_x_vel", "target_y_vel", "target_rot",
               "obs_keys", "fatigue_reset_vec", "fatigue_reset_random", "weight_bodyname", "weight_range",
               # backend knobs
-              "solver_tolerance", "maxcon", "barrier_mode", "lockstep_groups", "profile_waits"}
+              "solver_tolerance", "maxcon", "barrier_mode", "lockstep_groups", "profile_waits", "row_storage"}
 
     @staticmethod
     def _check_kwargs(kw):

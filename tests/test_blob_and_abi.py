@@ -72,6 +72,11 @@ def test_library_builds_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), n
     assert abi.lib().myo_version() >= 1
+    V = abi.lib("f64rows")                      # verification build of the same source (f64 row storage): same ABI
+    for n in names:
+        assert hasattr(V, n), n
+    with pytest.raises(abi.MyoError):
+        abi.lib("nope")
 
 
 def test_no_cpu_fallback_without_gpu(models):
