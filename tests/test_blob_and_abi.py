@@ -162,8 +162,13 @@ def test_dims_contact_capacity(models):
     dm = abi.DeviceModel(*blob.pack(m, prog))
     cfg = abi.MyoTaskCfg(); cfg.task = abi.TASK_POSE
     d = dm.dims(cfg)
-    assert d.maxcon == 32 and d.maxefc == 23 + 4 * 32 and d.smem_bytes_per_env * 10 + d.reserved[1] + 64 <= 232448      # 10 env-warps per SM
+    assert d.maxcon == 32 and d.maxefc == 23 + 4 * 32 and d.smem_bytes_per_env * 14 + d.reserved[1] + 64 <= 232448      # 14 env-warps per SM: 4096 envs in two rounds
     cfg.maxcon = 48
     assert dm.dims(cfg).maxcon == 48
     cfg.maxcon = 1000
     assert dm.dims(cfg).maxcon == 64
+    # the legs model must keep 7 env-warps per SM (2048 envs in two rounds) and the verification build the same ABI numbers
+    ml = models["myolegs"]; pl, _ = program.build_program(ml); dl = abi.DeviceModel(*blob.pack(ml, pl)).dims()
+    assert dl.smem_bytes_per_env * 7 + dl.reserved[1] + 64 <= 232448
+    dv = abi.DeviceModel(*blob.pack(m, prog), variant="f64rows").dims(cfg)
+    assert dv.maxcon == 64 and dv.smem_bytes_per_env > dm.dims(cfg).smem_bytes_per_env          # plain f64 rows take more room
