@@ -309,7 +309,12 @@ __device__ __forceinline__ void env_kernel_body(const DevModel& m, const StepArg
       PH(3, phase_body_inertia(m, w); phase_crb(m, w); phase_bias(m, w));
       PH(4, phase_collision(m, w); overflow_seen |= WI_(overflow));
       PH(5, phase_constraints(m, w); if (tap) write_taps_contacts(m, w, a, env));
-      if (ngroups == 1 && (!DBG || m.solve_sync)) {   // every warp enters the solver: its inner CTA barriers need the idle warps too (the unaligned variant is a debug-kernel experiment)
+#ifdef MYO_SOLVE_NOSYNC
+      const bool solver_aligned = DBG && ngroups == 1 && m.solve_sync;
+#else
+      const bool solver_aligned = ngroups == 1 && (!DBG || m.solve_sync);
+#endif
+      if (solver_aligned) {   // every warp enters the solver: its inner CTA barriers need the idle warps too (the unaligned variant is a debug-kernel experiment)
         long long tb_ = prof ? clock64() : 0; if (bmask & (1 << 6)) __syncthreads(); long long t0_ = prof ? clock64() : 0;
         phase_solve(m, w, a.tol, (prof && live) ? cyc : nullptr, live, true);
         if (prof) cyc[6] += waitprof ? t0_ - tb_ : clock64() - t0_;

@@ -275,6 +275,88 @@ __device__ __noinline__ void chol_rs(double* H, double* x, int n, int lane) {
   __syncwarp();
 }
 
+// Bordered root-free L D L' for 32 < n <= 32+E (the legs model: n = 34): H = [A B'; B C] with A the leading 32 x 32 block.  A is eliminated
+// exactly like chol_rs<32> (row per lane in registers, columns published in shared memory, batched broadcast loads); the e = n - 32 border
+// rows ride along DISTRIBUTED over the lanes (lane j keeps B[q][j]): at step k lane k publishes its now final entries, every lane j > k
+// applies the same rank-1 update to its border entries with its own U[j][k].  The e x e Schur complement C - L21 D L21' and the border
+// right-hand side are warp sums; the small system is solved redundantly by every lane.  Replaces the shuffle-based chol_reg32b below
+// (two 32-double register arrays, 800 spill instructions): measured round 2 on the legs model, 48.7 k cycles per solve before.
+template <int E>
+__device__ __noinline__ void chol_rs32b(double* H, double* x, int n, int lane) {
+  SHARED_PTR(H); SHARED_PTR(x);
+  const int rowadr = TRI(lane, 0);      // n == 32 + E exactly: every border loop is static (a run-time border size cost 8 branches per step: 18.8 k -> see tools/ubench/ubench_chol34.cu)
+  double r[32], bq[E];
+  #pragma unroll
+  for (int j = 0; j < 32; j++) r[j] = j <= lane ? H[rowadr + j] : 0.0;
+  #pragma unroll
+  for (int q = 0; q < E; q++) bq[q] = H[TRI(32+q, lane)];
+  double b = x[lane], invd_own = 1.0;
+  __syncwarp();
+  #pragma unroll
+  for (int k = 0; k < 32; k++) {
+    if (lane >= k) H[rowadr + k] = r[k];
+    if (lane == k) { x[k] = b;
+      #pragma unroll
+      for (int q = 0; q < E; q++) H[TRI(32+q, k)] = bq[q]; }
+    __syncwarp();
+    // the trailing columns are loaded in at most two batches of CH: with 64 row registers, a full batch of 31 and the border values
+    // the function overflowed its register budget (196 LDL / 169 STL in SASS, 31 k cycles per solve with 7 warps)
+    constexpr int CH = 18;
+    double col[32], bk[E];
+    #pragma unroll
+    for (int j = k+1; j < 32 && j < k+1+CH; j++) col[j] = H[TRI(j,k)];
+    #pragma unroll
+    for (int q = 0; q < E; q++) bk[q] = H[TRI(32+q, k)];
+    const double dk = H[TRI(k,k)], zk = x[k];
+    asm volatile("" ::: "memory");
+    const double invd = m_rcp(fmax(dk, MYO_MINVAL));
+    if (lane == k) invd_own = invd;
+    const double t = r[k]*invd;
+    b = lane > k ? fma(-t, zk, b) : b;
+    #pragma unroll
+    for (int j = k+1; j < 32 && j < k+1+CH; j++) r[j] = fma(-t, col[j], r[j]);
+    #pragma unroll
+    for (int q = 0; q < E; q++) bq[q] = lane > k ? fma(-bk[q]*invd, r[k], bq[q]) : bq[q];
+    if (k+1+CH < 32) {
+      #pragma unroll
+      for (int j = k+1+CH; j < 32; j++) col[j] = H[TRI(j,k)];
+      asm volatile("" ::: "memory");
+      #pragma unroll
+      for (int j = k+1+CH; j < 32; j++) r[j] = fma(-t, col[j], r[j]); }
+  }
+  // lane j now holds z1[j] (b), 1/d_j and U[32+q][j] = L21[q][j] d_j (bq).  Schur complement and border right-hand side:
+  double S[E][E], y2[E];
+  #pragma unroll
+  for (int q = 0; q < E; q++) {
+    #pragma unroll
+    for (int p = 0; p <= q; p++) { const double v = warp_sum(bq[q]*bq[p]*invd_own); S[q][p] = H[TRI(32+q, 32+p)] - v; }
+    y2[q] = x[32+q] - warp_sum(bq[q]*invd_own*b); }
+  // S = Ls Ds Ls' (root-free, every lane redundantly), x2 = S^-1 y2
+  double sinv[E];
+  #pragma unroll
+  for (int k = 0; k < E; k++) { sinv[k] = m_rcp(fmax(S[k][k], MYO_MINVAL));
+    #pragma unroll
+    for (int i = k+1; i < E; i++) {
+      #pragma unroll
+      for (int j = k+1; j <= i; j++) S[i][j] -= S[i][k]*sinv[k]*S[j][k]; }      // (column k still unscaled here)
+    #pragma unroll
+    for (int i = k+1; i < E; i++) { S[i][k] *= sinv[k]; y2[i] -= S[i][k]*y2[k]; } }
+  #pragma unroll
+  for (int k = E-1; k >= 0; k--) { y2[k] *= sinv[k];
+    #pragma unroll
+    for (int i = k+1; i < E; i++) y2[k] -= S[i][k]*y2[i]; }
+  // x1 = L^-T D^-1 (z1 - D L21' x2)
+  #pragma unroll
+  for (int q = 0; q < E; q++) b = fma(-bq[q], y2[q], b);
+  #pragma unroll
+  for (int k = 31; k >= 0; k--) { const double xk = __shfl_sync(FULL, b*invd_own, k), hk = lane < k ? H[TRI(k,0) + lane] : 0.0; b = fma(-hk, xk, b); }
+  __syncwarp();
+  x[lane] = b*invd_own;
+  #pragma unroll
+  for (int q = 0; q < E; q++) if (lane == q) x[32+q] = y2[q];
+  __syncwarp();
+}
+
 // Bordered register Cholesky for 32 < n <= 32+E: H = [A B'; B C] with A the leading 32x32 block.  A = L11 L11' is factored in
 // registers exactly like chol_reg<32>; the rows of B ride along as extra right-hand sides of the forward substitution
 // (L21 = B L11^-T), the E x E Schur complement C - L21 L21' is reduced with warp sums and factored redundantly by every lane.
@@ -385,7 +467,11 @@ __host__ __device__ __forceinline__ int chol_pad(int n) { return n > 32 ? n : (n
 // x <- H^-1 x for a dense SPD H (packed lower triangle in shared memory); H is destroyed
 __device__ __forceinline__ void chol_dense(double* H, int n, double* x, int lane) {
   if (n > 36) { chol_factor_rows(H, n, lane); chol_solve(H, n, x, lane); return; }
+#ifdef MYO_CHOL_SHFL32B
   if (n > 32) { chol_reg32b<4>(H, n, x, lane); return; }
+#else
+  if (n > 32) { switch (n) { case 33: chol_rs32b<1>(H, x, n, lane); break; case 34: chol_rs32b<2>(H, x, n, lane); break; case 35: chol_rs32b<3>(H, x, n, lane); break; default: chol_rs32b<4>(H, x, n, lane); break; } return; }
+#endif
 #ifndef MYO_CHOL_ROLLED
   switch (chol_pad(n)) {
     case 8: chol_rs<8>(H, x, n, lane); break;   case 12: chol_rs<12>(H, x, n, lane); break; case 16: chol_rs<16>(H, x, n, lane); break;
