@@ -17,6 +17,10 @@ struct StepArgs {
   int balanced;                 // env -> CTA map: 1 = e % grid (equal env counts per CTA, big models), 0 = contiguous groups of warps (small models: neighbouring rows share cache lines)
   const double* dbg_ctrl;       // mode 1
   const uint8_t* reset_mask;    // mode 2 (nullable)
+  int* load;                    // mode 0, product kernels (nullable): per-env load key written at the end of the step (mean contacts + Newton iterations per substep)
+  const int* perm;              // mode 0, product kernels (nullable): slot -> env, built from last step's load keys by myo_regroup_kernel (-1 = idle slot)
+  int perm_rounds;              // rounds of warps each CTA walks when perm is set
+  int load_wn, load_wi;         // load key = (load_wn * contacts + load_wi * Newton iterations) averaged over the substeps
   unsigned long long seed; long long env_offset;
   double tol, dt;
 };
@@ -249,10 +253,13 @@ __device__ __forceinline__ void env_kernel_body(const DevModel& m, const StepArg
   const bool prof = DBG && b.tap_phase_cycles != nullptr;
   // env e belongs to CTA e % gridDim.x: every CTA gets floor or ceil of n_env / gridDim.x envs, so no CTA runs a full extra round
   // while the others idle (4096 envs on 148 SMs: rounds of 10, 10, 8 warps everywhere instead of 10, 10, 10 on three quarters of the SMs)
-  const int per_cta = a.balanced ? (a.n_env + (int)gridDim.x - 1)/(int)gridDim.x : ((a.n_env + nw - 1)/nw + (int)gridDim.x - 1)/(int)gridDim.x*nw;
+  // With a.perm (big models, env steps of the product kernels) the slot -> env map is the load-sorted one: the envs of a round carry
+  // similar contact loads, so the lockstep barriers wait for a slowest env that is close to the average one.
+  const bool regrouped = !DBG && a.perm != nullptr;
+  const int per_cta = regrouped ? a.perm_rounds*nw : (a.balanced ? (a.n_env + (int)gridDim.x - 1)/(int)gridDim.x : ((a.n_env + nw - 1)/nw + (int)gridDim.x - 1)/(int)gridDim.x*nw);
   for (int j0 = 0; j0 < per_cta; j0 += nw) {
-    const int env = a.balanced ? (int)blockIdx.x + (int)gridDim.x*(j0 + wid) : ((int)blockIdx.x + (int)gridDim.x*(j0/nw))*nw + wid;
-    const bool live = (j0 + wid) < per_cta && env < a.n_env; const long long tstep_ = prof ? clock64() : 0;
+    const int env = regrouped ? a.perm[(int)blockIdx.x + (int)gridDim.x*(j0 + wid)] : (a.balanced ? (int)blockIdx.x + (int)gridDim.x*(j0 + wid) : ((int)blockIdx.x + (int)gridDim.x*(j0/nw))*nw + wid);
+    const bool live = (j0 + wid) < per_cta && env >= 0 && env < a.n_env; const long long tstep_ = prof ? clock64() : 0; int load_acc = 0;
     if (live) {
       // ---- load state (coalesced: one env's row per warp)
       for (int i = w.lane; i < m.nq; i += 32) W_(qpos)[i] = b.qpos[(size_t)env*m.nq+i];
@@ -321,6 +328,7 @@ __device__ __forceinline__ void env_kernel_body(const DevModel& m, const StepArg
       } else PH(6, phase_solve(m, w, a.tol, prof ? cyc : nullptr, true, false));
       PH(7, if (tap) write_taps_solve(m, w, a, env); if (integrate) phase_integrate(m, w, prof ? cyc : nullptr));
       if (DBG && live) { if (WI_(ncon) > maxcon_seen) maxcon_seen = WI_(ncon); if (WI_(nefc) > maxefc_seen) maxefc_seen = WI_(nefc); }
+      if (!DBG && live) load_acc += a.load_wn*WI_(ncon) + a.load_wi*WI_(niter);
     }
     #undef PH
     if (prof && live && w.lane == 0) { long long* pc = b.tap_phase_cycles + 20*(size_t)env; for (int k = 0; k < 20; k++) pc[k] = cyc[k]; pc[12] = maxcon_seen; pc[13] = maxefc_seen; pc[17] = clock64() - tstep_; }
@@ -331,6 +339,7 @@ __device__ __forceinline__ void env_kernel_body(const DevModel& m, const StepArg
         // mjData.time advances by one timestep per substep (the accumulated rounding is visible to ReachEnvV0's `time > 2 dt` test)
         double tnow = b.time ? b.time[env] : 0.0; for (int s_ = 0; s_ < a.cfg.frame_skip; s_++) tnow += m.timestep;
         if (overflow_seen && w.lane == 0 && b.overflow) b.overflow[env] |= 1;      // sticky until the next reset of this env
+        if (!DBG && a.load && w.lane == 0) a.load[env] = load_acc/(nsub > 0 ? nsub : 1);
         if (a.cfg.task != MYO_TASK_NONE) { const RwDone rd = task_observe(m, w, a, env, b.step_count ? b.step_count[env] : 0, tnow); const double rw = rd.rw; const bool done = rd.done != 0;
           int sc = b.step_count ? b.step_count[env]+1 : 0; bool trunc = a.cfg.max_episode_steps > 0 && sc >= a.cfg.max_episode_steps;
           __syncwarp();
@@ -388,8 +397,25 @@ static int fail(const std::string& s) { g_err = s; return -1; }
 #define CUDA_OK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
 
 struct myo_model { std::vector<int32_t> I; std::vector<double> D; };
+// Counting sort of the envs by last step's load key (descending), then groups of `nw` consecutive envs -> one round of one CTA, the rounds
+// filled boustrophedon (round 0: CTA 0 .. grid-1 takes the heaviest groups in order, round 1 runs back) so that every CTA's rounds add up to
+// about the same work.  One CTA; the order inside a bucket is whatever the atomics give (results do not depend on the grouping).
+__global__ void __launch_bounds__(1024) myo_regroup_kernel(const int* __restrict__ load, int* __restrict__ perm, int n, int grid, int nw, int nslots) {
+  __shared__ int cnt[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) cnt[i] = 0;
+  for (int i = threadIdx.x; i < nslots; i += blockDim.x) perm[i] = -1;
+  __syncthreads();
+  for (int e = threadIdx.x; e < n; e += blockDim.x) { int k = load[e]; k = k < 0 ? 0 : (k > 255 ? 255 : k); atomicAdd(&cnt[255 - k], 1); }
+  __syncthreads();
+  if (threadIdx.x == 0) { int run = 0; for (int i = 0; i < 256; i++) { int c = cnt[i]; cnt[i] = run; run += c; } }
+  __syncthreads();
+  for (int e = threadIdx.x; e < n; e += blockDim.x) { int k = load[e]; k = k < 0 ? 0 : (k > 255 ? 255 : k);
+    const int p = atomicAdd(&cnt[255 - k], 1), g = p / nw, u = p % nw, r = g / grid; int c = g % grid; if (r & 1) c = grid - 1 - c;
+    perm[c + grid*(r*nw + u)] = e; }
+}
+
 struct myo_batch { const myo_model* model; int device, n_env; myo_task_cfg cfg; myo_buffers bufs; bool bound; DevModel dm; int32_t* dI; double* dD; double* dCtrl; int const_bytes;
-  int warps_per_cta, grid, smem_bytes, obs_dim; int dbg_warps, dbg_grid, dbg_smem; bool use_w14; bool force_dbg; long long launches; unsigned long long seed; long long env_offset; };
+  int warps_per_cta, grid, smem_bytes, obs_dim; int dbg_warps, dbg_grid, dbg_smem; bool use_w14; bool force_dbg; bool regroup; int* dLoad; int* dPerm; int perm_rounds, perm_slots, load_wn, load_wi; long long launches; unsigned long long seed; long long env_offset; };
 
 extern "C" const char* myo_last_error(void) { return g_err.c_str(); }
 extern "C" int myo_version(void) { return 1; }
@@ -532,11 +558,17 @@ extern "C" int myo_batch_create(const myo_model* m, int device, int n_env, const
   { int c = 1; if (b->use_w14) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, myo_env_kernel_w14, wpc*32, b->smem_bytes); else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, myo_env_kernel, wpc*32, b->smem_bytes);
     if (c < 1) c = 1; int need = (n_env + wpc - 1)/wpc, cap = sms*c; b->grid = need < cap ? need : cap; }
   { int c = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, myo_env_kernel_dbg, wd*32, b->dbg_smem); if (c < 1) c = 1; int need = (n_env + wd - 1)/wd, cap = sms*c; b->dbg_grid = need < cap ? need : cap; }
+  // load-sorted env -> round map (one-CTA-per-SM models only; MYO_B200_REGROUP=0 switches it off)
+  b->regroup = big; if (const char* e = getenv("MYO_B200_REGROUP")) b->regroup = big && atoi(e) != 0;
+  b->dLoad = nullptr; b->dPerm = nullptr; b->perm_rounds = 0; b->perm_slots = 0; b->load_wn = 2; b->load_wi = 3;
+  if (const char* e = getenv("MYO_B200_LOADKEY")) sscanf(e, "%d,%d", &b->load_wn, &b->load_wi);      // tuning: weights of contacts and Newton iterations in the load key
+  if (b->regroup) { const int per_cta = (n_env + b->grid - 1)/b->grid; b->perm_rounds = (per_cta + wpc - 1)/wpc; b->perm_slots = b->grid*wpc*b->perm_rounds;
+    CUDA_OK(cudaMalloc(&b->dLoad, (size_t)n_env*4)); CUDA_OK(cudaMemset(b->dLoad, 0, (size_t)n_env*4)); CUDA_OK(cudaMalloc(&b->dPerm, (size_t)b->perm_slots*4)); }
   if (getenv("MYO_B200_VERBOSE")) fprintf(stderr, "[myo_b200] n_env %d: %s kernel, %d warps/CTA, grid %d, smem %d B (const %d + %d/env, %d fit); debug kernel %d warps, grid %d; max threads / regs: product %d / %d, w14 %d / %d, debug %d / %d\n",
     n_env, b->use_w14 ? "launch_bounds(448)" : "launch_bounds(320)", b->warps_per_cta, b->grid, b->smem_bytes, b->const_bytes, per, fit, b->dbg_warps, b->dbg_grid, fa_p.maxThreadsPerBlock, fa_p.numRegs, fa_w.maxThreadsPerBlock, fa_w.numRegs, fa_d.maxThreadsPerBlock, fa_d.numRegs);
   *out = b; return 0;
 }
-extern "C" void myo_batch_destroy(myo_batch* b) { if (!b) return; cudaSetDevice(b->device); cudaFree(b->dI); cudaFree(b->dD); cudaFree(b->dCtrl); delete b; }
+extern "C" void myo_batch_destroy(myo_batch* b) { if (!b) return; cudaSetDevice(b->device); cudaFree(b->dI); cudaFree(b->dD); cudaFree(b->dCtrl); if (b->dLoad) cudaFree(b->dLoad); if (b->dPerm) cudaFree(b->dPerm); delete b; }
 extern "C" int myo_batch_obs_dim(const myo_batch* b) { return b ? b->obs_dim : -1; }
 extern "C" int64_t myo_batch_launch_count(const myo_batch* b) { return b ? b->launches : -1; }
 
@@ -584,6 +616,9 @@ static int launch(myo_batch* b, StepArgs& a, void* stream) {
                    q.tap_ncon || q.tap_contact_pair || q.tap_contact_dist || q.tap_moment || q.tap_qM || q.tap_phase_cycles;
   if (dbg) { a.balanced = b->dbg_smem > 100*1024; myo_env_kernel_dbg<<<b->dbg_grid, b->dbg_warps*32, b->dbg_smem, (cudaStream_t)stream>>>(b->dm, a); }
   else { a.balanced = b->smem_bytes > 100*1024;
+    if (a.mode == 0 && b->regroup) {      // env steps: regroup by last step's load first (same stream), then step through the permutation
+      myo_regroup_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(b->dLoad, b->dPerm, b->n_env, b->grid, b->warps_per_cta, b->perm_slots);
+      a.load = b->dLoad; a.perm = b->dPerm; a.perm_rounds = b->perm_rounds; a.load_wn = b->load_wn; a.load_wi = b->load_wi; b->launches++; }
     if (b->use_w14) myo_env_kernel_w14<<<b->grid, b->warps_per_cta*32, b->smem_bytes, (cudaStream_t)stream>>>(b->dm, a);
     else myo_env_kernel<<<b->grid, b->warps_per_cta*32, b->smem_bytes, (cudaStream_t)stream>>>(b->dm, a); }
   CUDA_OK(cudaGetLastError()); b->launches++; return 0;
