@@ -67,6 +67,20 @@ def test_determinism_and_batch_size_independence():
     assert not torch.equal(a[0][0], d[0][0])
 
 
+def test_load_sorted_rounds_do_not_change_results(monkeypatch):
+    """The env -> (CTA, round) map of the product kernel is re-sorted by contact load before every step (myo_regroup_kernel); each env's
+    trajectory must be bit-identical to the fixed e % grid map, for a batch that fills two rounds and for one with idle slots."""
+    import torch
+    eid = "myoHandPoseRandom-v0"
+    for n in (4096, 300):
+        monkeypatch.setenv("MYO_B200_REGROUP", "1"); env_a, a = _run(eid, n, 8, seed=11)
+        monkeypatch.setenv("MYO_B200_REGROUP", "0"); env_b, b = _run(eid, n, 8, seed=11)
+        for (oa, ra, da, ta), (ob, rb, db, tb) in zip(a, b):
+            assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db)
+        assert torch.equal(env_a.t["qpos"], env_b.t["qpos"]) and torch.equal(env_a.t["qvel"], env_b.t["qvel"])
+        assert env_a.batch.launches == env_b.batch.launches + 8               # one regroup launch per env step
+
+
 def test_env_offset_shards_reproduce_global_batch():
     """Multi-GPU sharding rule: rank r simulates envs [r*n, (r+1)*n) with env_offset = r*n and gets exactly the
     rows a single big batch would have produced (no data-path collective needed)."""
