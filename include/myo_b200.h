@@ -61,6 +61,7 @@ typedef struct {
   int32_t reaf_dst, reaf_src;/* reafferentation (base_v0.py:104-108): ctrl[dst] = ctrl[src]; ctrl[src] = 0 ; dst == src = off */
   int32_t barrier_mode;      /* CTA phase barriers: 0 = before every phase (default), 1 = once per substep, 2 = none, >2 = bit mask of the 8 phases that start with a barrier (tuning knob) */
   int32_t reserved_i;        /* lockstep groups per CTA (tuning knob; 0/1 = the whole CTA is one group) */
+  int32_t fatigue_reset;     /* fatigue state at reset (fatigue.py:82-99): 0 = MA 0, MR 1, MF 0 ; 1 = fatigue_reset_random (u1, u2 ~ U(0,1): MA = u1 u2, MR = u1 (1 - u2), MF = 1 - u1) ; 2 = fatigue_reset_vec (MF = vec, MR = 1 - vec, MA = 0) */
   double pose_thd;           /* pose_v0.py:43 */
   double weights[8];         /* reward weights in the task's own key order (pose_v0.py:18-23, walk_v0.py:205-211, obj_hold_v0.py:17-21; reach_v0.py:18-22 as reach, bonus, act_reg, penalty) */
   double solver_tolerance;   /* scaled-gradient stop of the Newton solver; 0 = library default (1e-10) */
@@ -103,6 +104,7 @@ typedef struct {
   double* tap_moment;        /* [n, nnz] structural non-zeros of the tendon moment */
   double* tap_qM;            /* [n, nM] */
   long long* tap_phase_cycles; /* [n, 20] SM-clock cycles per phase over the call (profiling aid; 8-11 solver parts, 12,13: max ncon / nefc, 14,15: Newton iterations / dense ones, 16: cooperative collision, 17: load..substeps) */
+  const double* fatigue_reset_vec; /* [nu] nullable unless cfg.fatigue_reset == 2: the reference's fatigue_reset_vec (base_v0.py:29,48; fatigue.py:90-94) */
   int32_t* overflow;         /* [n] nullable: sticky flag, set when a substep of this env dropped contacts (more than maxcon, or more ellipsoid candidates than the list holds); cleared by the env's reset */
 } myo_buffers;
 

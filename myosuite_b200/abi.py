@@ -25,14 +25,14 @@ class MyoDims(ctypes.Structure):
 
 class MyoTaskCfg(ctypes.Structure):
     _fields_ = [(n, c_i32) for n in ("task", "frame_skip", "max_episode_steps", "normalize_act", "muscle_condition",
-                                      "auto_reset", "reset_random", "maxcon", "reaf_dst", "reaf_src", "barrier_mode", "reserved_i")] + \
+                                      "auto_reset", "reset_random", "maxcon", "reaf_dst", "reaf_src", "barrier_mode", "reserved_i", "fatigue_reset")] + \
                [("pose_thd", c_f64), ("weights", c_f64 * 8), ("solver_tolerance", c_f64), ("task_i", c_i32 * 16), ("task_d", c_f64 * 24), ("reserved", c_f64 * 2)]
 
 
 BUFFER_FIELDS = ["action", "qpos", "qvel", "act", "qacc_warmstart", "time", "fatigue", "target", "target_range", "init_qpos", "init_qvel", "env_prm",
                  "step_count", "episode_count", "obs", "reward", "done", "truncated", "ep_return", "last_return",
                  "tap_qacc", "tap_actuator_force", "tap_ten_length", "tap_qfrc_smooth", "tap_ncon", "tap_contact_pair",
-                 "tap_contact_dist", "tap_moment", "tap_qM", "tap_phase_cycles", "overflow"]
+                 "tap_contact_dist", "tap_moment", "tap_qM", "tap_phase_cycles", "fatigue_reset_vec", "overflow"]
 
 
 class MyoBuffers(ctypes.Structure):

@@ -97,7 +97,10 @@ __device__ void env_reset(const DevModel& m, const Warp w, const StepArgs& a, in
       W_(eprm)[w.lane] = v; b.env_prm[(size_t)env*8 + w.lane] = v; } }
   for (int i = w.lane; i < m.nv; i += 32) { W_(qvel)[i] = b.init_qvel ? b.init_qvel[(size_t)key*m.nv + i] : 0.0; W_(qws)[i] = 0; }
   for (int i = w.lane; i < m.na; i += 32) W_(act)[i] = 0;
-  if (b.fatigue && a.cfg.muscle_condition == MYO_COND_FATIGUE) for (int i = w.lane; i < m.nu; i += 32) { double* f = b.fatigue + (size_t)env*3*m.nu; f[i] = 0; f[m.nu+i] = 1; f[2*m.nu+i] = 0; }
+  if (b.fatigue && a.cfg.muscle_condition == MYO_COND_FATIGUE) for (int i = w.lane; i < m.nu; i += 32) { double* f = b.fatigue + (size_t)env*3*m.nu;      // CumulativeFatigue.reset (fatigue.py:82-99)
+    if (a.cfg.fatigue_reset == 1) { const double nf = philox_uniform(rng), ap = philox_uniform(rng); f[i] = nf*ap; f[m.nu+i] = nf*(1-ap); f[2*m.nu+i] = 1-nf; }
+    else if (a.cfg.fatigue_reset == 2 && b.fatigue_reset_vec) { const double v = b.fatigue_reset_vec[i]; f[i] = 0; f[m.nu+i] = 1-v; f[2*m.nu+i] = v; }
+    else { f[i] = 0; f[m.nu+i] = 1; f[2*m.nu+i] = 0; } }
   if (w.lane == 0) { if (b.time) b.time[env] = 0; if (b.step_count) b.step_count[env] = 0; if (b.episode_count) b.episode_count[env] = ep+1; if (b.ep_return) b.ep_return[env] = 0; }
   __syncwarp();
 }
@@ -600,6 +603,7 @@ extern "C" int myo_batch_bind(myo_batch* b, const myo_buffers* bufs) {
   if (!b || !bufs) return fail("myo_batch_bind: null");
   if (!bufs->qpos || !bufs->qvel || !bufs->qacc_warmstart || (b->dm.na && !bufs->act)) return fail("myo_batch_bind: qpos/qvel/act/qacc_warmstart are required");
   if (b->cfg.muscle_condition == MYO_COND_FATIGUE && !bufs->fatigue) return fail("myo_batch_bind: fatigue buffer required for MYO_COND_FATIGUE");
+  if (b->cfg.muscle_condition == MYO_COND_FATIGUE && b->cfg.fatigue_reset == 2 && !bufs->fatigue_reset_vec) return fail("myo_batch_bind: fatigue_reset_vec buffer required for fatigue_reset = 2");
   if (b->cfg.task == MYO_TASK_HOLD && !bufs->env_prm) return fail("myo_batch_bind: env_prm buffer required for MYO_TASK_HOLD");
   b->bufs = *bufs; b->bound = true; return 0;
 }

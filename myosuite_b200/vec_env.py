@@ -99,6 +99,11 @@ class MyoVecEnv:
         cfg.max_episode_steps = int(self.max_episode_steps or 0)
         cfg.normalize_act = int(bool(kw.get("normalize_act", True)))
         cfg.muscle_condition = abi.COND_FATIGUE if self.muscle_condition == "fatigue" else abi.COND_NONE
+        # fatigue state at reset (base_v0.py:120-128 -> fatigue.py:82-99)
+        self.fatigue_reset_vec = None if kw.get("fatigue_reset_vec") is None else np.asarray(kw["fatigue_reset_vec"], dtype=np.float64).ravel()
+        if self.fatigue_reset_vec is not None and len(self.fatigue_reset_vec) != m.na:
+            raise AssertionError("Invalid length of initial/reset fatigue vector (expected %d, but obtained %d)" % (m.na, len(self.fatigue_reset_vec)))      # fatigue.py:91
+        cfg.fatigue_reset = 1 if kw.get("fatigue_reset_random") else (2 if self.fatigue_reset_vec is not None else 0)
         cfg.auto_reset = int(bool(auto_reset))
         cfg.reset_random = int(kw.get("reset_type", "init") == "random")
         cfg.pose_thd = float(kw.get("pose_thd", 0.25 if self.torso else 0.35))         # pose_v0.py:43 / torso_v0.py:52
@@ -178,6 +183,8 @@ class MyoVecEnv:
         if cfg.muscle_condition == abi.COND_FATIGUE:
             t["fatigue"] = z(n, 3, m.nu)
             t["fatigue"][:, 1, :] = 1.0
+            if self.fatigue_reset_vec is not None:
+                t["fatigue_reset_vec"] = torch.as_tensor(self.fatigue_reset_vec, device=dv).contiguous()
         if taps:
             t.update(tap_qacc=z(n, m.nv), tap_actuator_force=z(n, m.nu), tap_ten_length=z(n, m.nu), tap_qfrc_smooth=z(n, m.nv),
                      tap_ncon=z(n, 4, dtype=torch.int32), tap_contact_pair=z(n, max(self.dims.maxcon, 1), dtype=torch.int32),
@@ -200,8 +207,8 @@ class MyoVecEnv:
         if unknown:
             raise NotImplementedError("env kwargs not implemented by this backend: %s" % unknown)
         bad = []
-        if kw.get("fatigue_reset_vec") is not None or kw.get("fatigue_reset_random"):
-            bad.append("fatigue_reset_vec / fatigue_reset_random (resets always start from MA = 0, MR = 1, MF = 0: fatigue.py:82-99 defaults)")
+        if kw.get("fatigue_reset_vec") is not None and kw.get("fatigue_reset_random"):
+            raise AssertionError("Cannot use 'fatigue_reset_vec' if fatigue_reset_random=False.")          # (the reference's own assertion and wording, fatigue.py:84)
         if kw.get("reset_type", "init") not in ("init", "random"):
             bad.append("reset_type=%r (init and random are implemented)" % kw.get("reset_type"))
         if kw.get("target_type", "generate") == "switch":

@@ -151,3 +151,28 @@ def test_walk_random_reset_distribution():
     a = torch.zeros(n, env.act_dim, device=env.device)
     obs, rew, done, trunc, _ = env.step(a); torch.cuda.synchronize()
     assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+
+
+def test_fatigue_reset_modes():
+    """CumulativeFatigue.reset (fatigue.py:82-99) on the device: default, fatigue_reset_vec, fatigue_reset_random -- also for auto-resets."""
+    import torch
+    from myosuite_b200 import vec_env
+    eid, n = "myoFatiElbowPose1D6MRandom-v0", 256
+    env = vec_env.MyoVecEnv(eid, n, seed=1); env.reset(seed=1)
+    F = env.t["fatigue"].cpu().numpy(); assert np.all(F[:, 0] == 0) and np.all(F[:, 1] == 1) and np.all(F[:, 2] == 0)
+    vec = np.linspace(0.1, 0.6, env.mj_model.na)
+    env = vec_env.MyoVecEnv(eid, n, seed=1, fatigue_reset_vec=vec); env.reset(seed=1)
+    F = env.t["fatigue"].cpu().numpy()
+    np.testing.assert_array_equal(F[:, 2], np.tile(vec, (n, 1))); np.testing.assert_array_equal(F[:, 1], np.tile(1 - vec, (n, 1))); assert np.all(F[:, 0] == 0)
+    for _ in range(env.max_episode_steps + 2):                     # run through a TimeLimit auto-reset: the vector is applied again
+        env.step(torch.rand(n, env.act_dim, device=env.device) * 2 - 1)
+    sc = env.t["step_count"].cpu().numpy(); F = env.t["fatigue"].cpu().numpy()
+    assert sc.max() <= 2 and np.all(F[:, 2] > 0.05)                # two steps after the reset MF is still close to the vector (recovery is slow)
+    env = vec_env.MyoVecEnv(eid, n, seed=2, fatigue_reset_random=True); env.reset(seed=2)
+    F = env.t["fatigue"].cpu().numpy()
+    np.testing.assert_allclose(F.sum(1), 1.0, atol=1e-12); assert F.min() >= 0 and F.max() <= 1
+    assert 0.4 < F[:, 2].mean() < 0.6 and 0.2 < F[:, 0].mean() < 0.3 and F[:, 0].std() > 0.1          # MF = 1 - u1 ; MA = u1 u2
+    with pytest.raises(AssertionError):
+        vec_env.MyoVecEnv(eid, 4, fatigue_reset_vec=vec, fatigue_reset_random=True)
+    with pytest.raises(AssertionError):
+        vec_env.MyoVecEnv(eid, 4, fatigue_reset_vec=vec[:3])
