@@ -155,10 +155,29 @@ class MyoVecEnv:
         n, dv = self.num_envs, self.device
         f64, f32 = torch.float64, torch.float32
         z = lambda *s, dtype=f64: torch.zeros(*s, dtype=dtype, device=dv)
-        self.obs_dim, self.act_dim = max(self.batch.obs_dim, 1), m.nu
+        self.full_obs_dim = self.obs_dim = max(self.batch.obs_dim, 1); self.act_dim = m.nu
+        # custom obs_keys (env_base.py:110,190,458 obsdict2obsvec over `obs_keys`; base_v0.py:33-37 appends "act"): the kernel always writes the
+        # task's full default layout into t["obs_full"]; t["obs"] is the gather of the requested keys' columns, refreshed after every launch
+        self._obs_cols = None
+        if kw.get("obs_keys") is not None and self.task != "none":
+            from . import gym_api
+            keys = list(kw["obs_keys"])
+            if m.na > 0 and "act" not in keys:
+                keys.append("act")
+            lay, off, o = gym_api.obs_layout(self.task, m.nq, m.nv, m.na, len(getattr(self, "tip_names", ()))), {}, 0
+            for k_, w_ in lay:
+                off[k_] = (o, w_); o += w_
+            missing = [k_ for k_ in keys if k_ not in off]
+            if missing:
+                raise KeyError("obs_keys not available from this task's obs_dict: %s (available: %s)" % (missing, [k_ for k_, _ in lay]))
+            self.obs_keys = keys
+            if keys != [k_ for k_, _ in lay]:
+                cols = np.concatenate([np.arange(off[k_][0], off[k_][0] + off[k_][1]) for k_ in keys])
+                self._obs_cols, self._obs_cols_np = torch.as_tensor(cols, dtype=torch.int64, device=self.device), cols
+                self.obs_dim = int(len(cols))
         t = dict(action=z(n, m.nu, dtype=f32), qpos=z(n, m.nq), qvel=z(n, m.nv), act=z(n, max(m.na, 1)), qacc_warmstart=z(n, m.nv),
                  time=z(n), target=z(n, m.nq), step_count=z(n, dtype=torch.int32), episode_count=z(n, dtype=torch.int64),
-                 obs=z(n, self.obs_dim, dtype=f32), reward=z(n, dtype=f32), done=z(n, dtype=torch.uint8), truncated=z(n, dtype=torch.uint8),
+                 obs=z(n, self.full_obs_dim, dtype=f32), reward=z(n, dtype=f32), done=z(n, dtype=torch.uint8), truncated=z(n, dtype=torch.uint8),
                  ep_return=z(n, dtype=f32), last_return=z(n, dtype=f32), overflow=z(n, dtype=torch.int32))
         t["qpos"][:] = torch.as_tensor(m.qpos0, device=dv)
         # target ranges per qpos (pose_v0.py:60-70); "fixed" targets collapse the range
@@ -192,7 +211,14 @@ class MyoVecEnv:
                      tap_phase_cycles=z(n, 20, dtype=torch.int64))
         self.t = t
         self.batch.bind(**t)
+        t["obs_full"] = t["obs"]                                  # what the kernel writes (bound above); t["obs"] is what callers see
+        if self._obs_cols is not None:
+            t["obs"] = z(n, self.obs_dim, dtype=f32)
         self._h_action = None
+
+    def _sync_obs(self):
+        if self._obs_cols is not None:
+            self.torch.index_select(self.t["obs_full"], 1, self._obs_cols, out=self.t["obs"])
 
     # kwargs of the reference's env classes this backend implements; anything else with a non-default value is an error, not a silent no-op
     _KNOWN = {"model_path", "normalize_act", "frame_skip", "muscle_condition", "reset_type", "target_type", "pose_thd", "weighted_reward_keys", "target_jnt_range",
@@ -215,8 +241,6 @@ class MyoVecEnv:
             bad.append("target_type='switch'")
         if kw.get("weight_bodyname") is not None or kw.get("weight_range") is not None:
             bad.append("weight_bodyname / weight_range")
-        if kw.get("obs_keys") is not None:
-            bad.append("custom obs_keys (the observation layout is the task's DEFAULT_OBS_KEYS + act)")
         if bad:
             raise NotImplementedError("reference kwargs accepted by the reference but not by this backend: " + "; ".join(bad))
 
@@ -295,6 +319,7 @@ class MyoVecEnv:
                 self.t["episode_count"][mask.bool()] = 0
         self._reset_mask = mask          # keep alive until the launch has consumed it
         self.batch.reset(mask=mask, seed=self.seed_value, env_offset=self.env_offset, stream=self._stream())
+        self._sync_obs()
         return self.t["obs"], {}
 
     def _stream(self):
@@ -308,6 +333,7 @@ class MyoVecEnv:
                 raise ValueError("action must have shape %s, got %s" % (tuple(a.shape), tuple(action.shape)))
             a.copy_(action, non_blocking=True)
         self.batch.step(stream=self._stream())
+        self._sync_obs()
         t = self.t
         return t["obs"], t["reward"], t["done"], t["truncated"], {"last_return": t["last_return"], "time": t["time"], "overflow": t["overflow"]}
 
@@ -316,6 +342,7 @@ class MyoVecEnv:
         torch = self.torch
         self.t["action"].copy_(action_cpu_pinned, non_blocking=True)
         self.batch.step(stream=self._stream())
+        self._sync_obs()
         if self._h_action is None:
             self._h_reward = torch.empty(self.num_envs, dtype=torch.float32, pin_memory=True)
             self._h_done = torch.empty(self.num_envs, dtype=torch.uint8, pin_memory=True)
@@ -362,12 +389,13 @@ class MyoVecEnv:
         """`rwd_sparse` / `solved` of the current observations (the reference's info dict, env_base.py:585-616), derived lazily from obs."""
         from . import task_info
         m = self.mj_model
-        return task_info.info_from_obs(self.task, self.t["obs"], m.nq, m.nv, m.na, pose_thd=float(self.cfg.pose_thd),
+        return task_info.info_from_obs(self.task, self.t["obs_full"], m.nq, m.nv, m.na, pose_thd=float(self.cfg.pose_thd),
                                        ntip=len(getattr(self, "tip_names", ())) or None)
 
     def refresh_obs(self):
         """obs / reward / done of the current state (the reference's env.forward(), env_base.py:393-432)."""
         self.batch.observe(stream=self._stream())
+        self._sync_obs()
         return self.t["obs"], self.t["reward"], self.t["done"]
 
     def examine_policy(self, policy, horizon=None, mode="exploration", seed=None, generator=None, keep_obs=True):
@@ -420,7 +448,7 @@ class MyoEnv:
         m = v.mj_model
         self.action_space, self.observation_space = gym_api.make_spaces(m.nu, v.obs_dim, bool(v.kwargs.get("normalize_act", True)), m.actuator_ctrlrange)
         self._ntip = len(getattr(v, "tip_names", ()))
-        self.obs_keys = [k for k, _ in gym_api.obs_layout(v.task, m.nq, m.nv, m.na, self._ntip)]
+        self.obs_keys = list(getattr(v, "obs_keys", None) or [k for k, _ in gym_api.obs_layout(v.task, m.nq, m.nv, m.na, self._ntip)])
         self.rwd_keys_wt = dict(v.kwargs.get("weighted_reward_keys") or gym_api.DEFAULT_WEIGHTS[v.task])
         self.rwd_mode = "dense"
         self.obs_dict, self.rwd_dict, self.proprio_dict, self.visual_dict = {}, {}, {}, {}
@@ -455,10 +483,11 @@ class MyoEnv:
     # ---- one packed device->host transfer
     def _fetch(self):
         torch, t = self.vec.torch, self.vec.t
-        row = torch.cat([t["obs"][0].double(), t["reward"].double(), t["done"].double(), t["truncated"].double(), t["time"]]).cpu().numpy()
-        n = self.vec.obs_dim
-        obs = row[:n].astype(np.float32)
-        self._last = dict(obs=obs, reward=float(row[n]), done=bool(row[n + 1]), truncated=bool(row[n + 2]), time=float(row[n + 3]))
+        row = torch.cat([t["obs_full"][0].double(), t["reward"].double(), t["done"].double(), t["truncated"].double(), t["time"]]).cpu().numpy()
+        n = self.vec.full_obs_dim
+        full = row[:n].astype(np.float32)
+        obs = full if self.vec._obs_cols is None else full[self.vec._obs_cols_np]          # obs vector = concatenation of obs_keys (obs_vec_dict.py:76-88)
+        self._last = dict(obs=obs, obs_full=full, reward=float(row[n]), done=bool(row[n + 1]), truncated=bool(row[n + 2]), time=float(row[n + 3]))
         self.obs_dict = self.get_obs_dict()
         self.rwd_dict = self.get_reward_dict(self.obs_dict)
         return self._last
@@ -489,7 +518,7 @@ class MyoEnv:
         any arguments are ignored.)"""
         from . import gym_api
         m = self.mj_model
-        return gym_api.obs_dict_from_vec(self.vec.task, self._last["obs"], np.array([self._last["time"]]), m.nq, m.nv, m.na, self._ntip)
+        return gym_api.obs_dict_from_vec(self.vec.task, self._last["obs_full"], np.array([self._last["time"]]), m.nq, m.nv, m.na, self._ntip)
 
     def get_reward_dict(self, obs_dict):
         from . import gym_api

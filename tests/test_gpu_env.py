@@ -176,3 +176,30 @@ def test_fatigue_reset_modes():
         vec_env.MyoVecEnv(eid, 4, fatigue_reset_vec=vec, fatigue_reset_random=True)
     with pytest.raises(AssertionError):
         vec_env.MyoVecEnv(eid, 4, fatigue_reset_vec=vec[:3])
+
+
+def test_custom_obs_keys():
+    """obs_keys kwarg (env_base.py:110,190,458; base_v0.py:33-37 appends "act"): the observation is the concatenation of the requested keys."""
+    import torch
+    import myosuite_b200 as myo
+    from myosuite_b200 import vec_env
+    eid, n = "myoHandPoseRandom-v0", 32
+    ref = vec_env.MyoVecEnv(eid, n, seed=4); ref.reset(seed=4)
+    env = vec_env.MyoVecEnv(eid, n, seed=4, obs_keys=["pose_err", "qpos"]); obs0, _ = env.reset(seed=4)
+    m = env.mj_model
+    assert env.obs_keys == ["pose_err", "qpos", "act"] and env.obs_dim == 2 * m.nq + m.na and tuple(obs0.shape) == (n, env.obs_dim)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    for _ in range(3):
+        a = (torch.rand(n, env.act_dim, generator=g) * 2 - 1).to(env.device)
+        o_ref, r_ref, *_ = ref.step(a); o, r, *_ = env.step(a)
+        full = o_ref.cpu().numpy(); nq, nv = m.nq, m.nv
+        want = np.concatenate([full[:, nq + nv:2 * nq + nv], full[:, :nq], full[:, 2 * nq + nv:]], axis=1)
+        assert np.array_equal(o.cpu().numpy(), want) and torch.equal(r, r_ref)
+    assert env.task_info()["solved"].shape[0] == n                      # the info path still reads the full layout
+    with pytest.raises(KeyError):
+        vec_env.MyoVecEnv(eid, 4, obs_keys=["qpos", "nope"])
+    e1 = myo.make("myoElbowPose1D6MRandom-v0", seed=1, obs_keys=["qvel", "pose_err"]).unwrapped
+    obs, _ = e1.reset()
+    assert e1.obs_keys == ["qvel", "pose_err", "act"] and e1.observation_space.shape == obs.shape == (1 + 1 + 6,)
+    obs, *_ = e1.step(np.zeros(6, dtype=np.float32))
+    np.testing.assert_array_equal(obs, np.concatenate([np.ravel(e1.obs_dict[k]) for k in e1.obs_keys]))
