@@ -549,7 +549,7 @@ extern "C" int myo_batch_create(const myo_model* m, int device, int n_env, const
     return wpc; };
   auto rounds_of = [&](int wpc) { return (n_env + sms*wpc - 1)/(sms*wpc); };
   int wp = pick(fa_p.maxThreadsPerBlock/32), ww = pick(fa_w.maxThreadsPerBlock/32), wd = pick(fa_d.maxThreadsPerBlock/32);
-  b->use_w14 = big && ww > wp && rounds_of(ww) < rounds_of(wp);
+  b->use_w14 = ww > wp && rounds_of(ww) < rounds_of(wp);      // (small models too: the elbow runs 4096 envs in 2 rounds of 14 warps instead of 3 of 10 -- registers, not shared memory, keep it at one CTA per SM)
   if (const char* e = getenv("MYO_B200_W14")) b->use_w14 = atoi(e) != 0 && fa_w.maxThreadsPerBlock > fa_p.maxThreadsPerBlock;      // tuning override
   int wpc = b->use_w14 ? ww : wp;
   if (const char* e = getenv("MYO_B200_WARPS_PER_CTA")) { int q = atoi(e), cap = (b->use_w14 ? fa_w.maxThreadsPerBlock : fa_p.maxThreadsPerBlock)/32; if (cap > fit) cap = fit;
