@@ -11,6 +11,12 @@ What matches and what does not (Feb 2022 logs vs the present reference tree):
   * hand pose / reach: the hand XML has changed since the logs were written (FDS/FDP wraps at the MCP joints commented out, the whole muscle
     block replaced: simhive/myo_sim/hand/assets/myohand_assets.xml:129-240,540-582), so only the bulk of the trained policies' gain over an
     untrained policy is recovered (pose-random: 90 %, reach-fixed: success 94 % vs 100 %) -> asserted as lower bounds;
+  * myoHandObjHoldRandom-v0 (hand + free object: the contact-rich model; all three logged seeds): return -199.5 / -198.5 / -196.4 (std 28.7 /
+    26.1 / 27.0, success 1.0 / 0.5 / 0.5 %) against the logged -192.7 / -193.3 / -188.8 (std 26.3 / 24.3 / 23.7, success 1.0 / 0.0 / 1.0 %);
+    an untrained policy scores -245 -> 88 % of the trained gain on a drifted hand model, same spread, same success rate -> asserted on the device;
+    the Fixed variant's policies (trained to one object pose) keep 60-75 % (two seeds) or nothing (one seed) of their return: documented only;
+  * myoHandReachRandom-v0 does not transfer (return 9 +- 150 vs 583 logged): with random targets the episodes end at the far_th test a few
+    steps in unless the policy closes the distance at once, which the 2022 muscles did and today's do not.  Documented, not asserted;
   * myoHandPoseFixed-v0 (registration marked "revisit" in the reference) does not transfer at all: the policy drives mcp5 into its limit where
     the 2022 model flexed pm5 -- the little-finger flexors are exactly the tendons whose MCP wraps were removed.  Documented, not asserted.
 """
@@ -23,7 +29,7 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "devtools")); sys.path.insert(0, os.path.join(HERE, "golden"))
 
-UNTRAINED = {"myoHandPoseRandom-v0": -336.1, "myoHandReachFixed-v0": -20.6}      # iteration 0 of the same logs (stoc_pol_mean)
+UNTRAINED = {"myoHandPoseRandom-v0": -336.1, "myoHandReachFixed-v0": -20.6, "myoHandObjHoldRandom-v0": -244.7}      # iteration 0 of the same logs (stoc_pol_mean)
 
 
 @pytest.mark.parametrize("env_id", ["myoElbowPose1D6MFixed-v0", "myoElbowPose1D6MRandom-v0"])
@@ -55,7 +61,8 @@ def test_trained_policy_replay_on_device_and_trace():
     import npg_policies
     from myosuite_b200 import rollout, vec_env
     pols = npg_policies.load_npz()
-    for env_id, n, k in (("myoElbowPose1D6MFixed-v0", 1024, 0), ("myoElbowPose1D6MRandom-v0", 1024, 0), ("myoHandPoseRandom-v0", 1024, 0), ("myoHandReachFixed-v0", 512, 1)):
+    for env_id, n, k in (("myoElbowPose1D6MFixed-v0", 1024, 0), ("myoElbowPose1D6MRandom-v0", 1024, 0), ("myoHandPoseRandom-v0", 1024, 0), ("myoHandReachFixed-v0", 512, 1),
+                          ("myoHandObjHoldRandom-v0", 1024, 0), ("myoHandObjHoldRandom-v0", 1024, 1), ("myoHandObjHoldRandom-v0", 1024, 2)):
         env = vec_env.MyoVecEnv(env_id, n, auto_reset=False, seed=11)
         pol = rollout.MLPPolicy(pols[env_id][k], device=env.device)
         g = torch.Generator(device=env.device).manual_seed(3)
@@ -66,6 +73,9 @@ def test_trained_policy_replay_on_device_and_trace():
             assert min(lg["stoc_pol_mean"], lg["best_stoc_pol_mean"]) - 4 <= mean <= max(lg["stoc_pol_mean"], lg["best_stoc_pol_mean"]) + 4 and s["success_pct"] > 99.0
         elif "PoseRandom" in env_id:
             assert mean - UNTRAINED[env_id] > 0.8 * (lg["stoc_pol_mean"] - UNTRAINED[env_id])
+        elif "ObjHold" in env_id:      # contact-rich anchor: most of the trained gain, the logged spread and the logged (near-zero) success rate
+            assert mean - UNTRAINED[env_id] > 0.8 * (lg["stoc_pol_mean"] - UNTRAINED[env_id]) and mean < lg["stoc_pol_mean"] + 5
+            assert abs(float(s["returns"].std()) - lg["stoc_pol_std"]) < 0.25 * lg["stoc_pol_std"] and s["success_pct"] <= 3.0
         else:
             assert s["success_pct"] >= 80.0
         # Trace layout of the reference's logger: one Trial group per env, T+1 rows, NaN action in the last row
