@@ -81,7 +81,7 @@ __device__ void rows_apply(const DevModel& m, const Warp w, const double* x, dou
   const idx_t* eq = CI(PEQ); const int nlimrow = WI_(nlimrow), ncon = WI_(ncon);
   for (int e = w.lane; e < m.neq; e += 32) { double v = x[eq[PEQ_ISTRIDE*e+1]]; if (eq[PEQ_ISTRIDE*e+3] >= 0) v += S_eqJ[e]*x[eq[PEQ_ISTRIDE*e+3]]; out[e] = v; }
   for (int r = w.lane; r < nlimrow; r += 32) { int dsc = S_lrow[r]; double sg = (dsc >> 8) & 1 ? -1.0 : 1.0; out[m.neq + r] = sg*x[dsc & 0xff]; }
-  const idx_t* pr = CI(PPAIR); const double* pd = CD(PPAIR_d); const idx_t* path = CI(PPATH);
+  const idx_t* pr = CI(PPAIR); const idx_t* path = CI(PPATH);
   for (int c = w.lane; c < ncon; c += 32) { const int rn = S_crown[c], nr = CNR(rn); if (!nr) continue;
     const idx_t* q = pr + PPAIR_ISTRIDE*S_cpair[c]; const JacRef J = S_jac(c); double n = 0, t1 = 0, t2 = 0;
     for (int e = 0; e < q[4]; e++) { double xv = x[path[q[3]+e] >> 1]; n += J[3*e]*xv; t1 += J[3*e+1]*xv; t2 += J[3*e+2]*xv; }
@@ -112,7 +112,7 @@ __device__ void rows_applyT_add(const DevModel& m, const Warp w, double* wgt, do
     __syncwarp(); } }
 }
 #else
-  const idx_t* pr = CI(PPAIR); const double* pd = CD(PPAIR_d);
+
   for (int c = w.lane; c < ncon; c += 32) { const int rn = S_crown[c], nr = CNR(rn), rb = CROW(rn);      // fold the pyramid edges: (wn, w1, w2) into wgt[rb .. rb+2]
     if (nr == 4) { const double a0 = wgt[rb], a1 = wgt[rb+1], a2 = wgt[rb+2], a3 = wgt[rb+3];
       wgt[rb] = a0+a1+a2+a3; wgt[rb+1] = a0-a1; wgt[rb+2] = a2-a3; } }
@@ -545,7 +545,7 @@ __device__ __forceinline__ void phase_solve(const DevModel& m, const Warp w, dou
     mul_M(m, w, S_Ma, S_a); rows_apply(m, w, S_a, S_jar); __syncwarp();
     for (int r = w.lane; r < nefc; r += 32) S_jar[r] -= S_aref[r]; __syncwarp(); }
   const double scale = 1.0/(m.meaninertia*(n > 1 ? n : 1));
-  const idx_t* eq = CI(PEQ); const idx_t* pr = CI(PPAIR); const double* pd = CD(PPAIR_d); const idx_t* path = CI(PPATH);
+  const idx_t* eq = CI(PEQ); const idx_t* pr = CI(PPAIR); const idx_t* path = CI(PPATH);
   for (int iter = 0; iter < 50; iter++) {
     if (cta_sync) { if (!__syncthreads_or(active ? 1 : 0)) break; } else if (!active) break;
     bool dense = false;
