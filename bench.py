@@ -57,7 +57,7 @@ def usable_cores():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons DURING the timed region: NVML polled from a thread every few ms (the timed region of the default run is
+    """SM clock and throttle reasons DURING the timed region: NVML polled from a thread every 10 ms (the timed region of the default run is
     only ~0.1 s, shorter than nvidia-smi's start-up); falls back to an `nvidia-smi -lms` child when NVML cannot be loaded."""
     _BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))      # nvmlClocksThrottleReason* / ClocksEventReason*
 
@@ -85,7 +85,7 @@ class ClockSampler:
                 self.rows.append((mhz, bits))
             except Exception:
                 pass
-            time.sleep(0.004)
+            time.sleep(0.010)
 
     def start(self):
         if self.h is not None:
