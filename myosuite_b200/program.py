@@ -215,24 +215,50 @@ def build_program(m, allow_unsupported=ALLOWED_UNSUPPORTED_PAIRS):
     # straight segments and the wrap elements minimal (a group of 33 wrap elements costs a whole extra round of the wrap code for one lane),
     # then balance the two groups' scratch need.
     def _count(t):
-        adr, num = int(m.tendon_adr[t]), int(m.tendon_num[t]); ns = nw = 0; j = 0
+        """(straight segments, wrap elements, bit mask of the wrap classes {sphere, cylinder} x {outside, inside}) of tendon t"""
+        adr, num = int(m.tendon_adr[t]), int(m.tendon_num[t]); ns = nw = cls = 0; j = 0; ccount = [0, 0, 0, 0]
         while j < num - 1:
             if m.wrap_type[adr + j + 1] == mjcf.WRAP_SITE:
                 ns += 0 if _same_rigid(m, int(m.site_bodyid[int(m.wrap_objid[adr + j])]), int(m.site_bodyid[int(m.wrap_objid[adr + j + 1])])) else 1; j += 1
             else:
+                g_, ss_ = int(m.wrap_objid[adr + j + 1]), int(m.wrap_prm[adr + j + 1]); inside_ = 0
+                if ss_ >= 0:
+                    bg_ = int(m.geom_bodyid[g_])
+                    inside_ = int(np.linalg.norm(_site_world(m, kin0, ss_) - (kin0["xpos"][bg_] + kin0["xmat"][bg_] @ m.geom_pos[g_])) < m.geom_size[g_][0])
+                c_ = 2 * (0 if m.wrap_type[adr + j + 1] == mjcf.WRAP_SPHERE else 1) + inside_
+                cls |= 1 << c_; ccount[c_] += 1
                 nw += 1; j += 2
-        return ns, nw
+        return ns, nw, cls, tuple(ccount)
     _cnt = {t: _count(t) for t in act_tendons}
     _need = lambda ns, nw: 3 * (ns + 2 * nw) + ns + nw
-    _reach = {(0, 0): 0}                                       # (ns, nw) of a subset -> bit mask of one subset reaching it
+    # reachable (ns_A, nw_A, classes_A, classes_B) -> bit mask of one subset A reaching it.  A lane round of wrap elements executes every
+    # class present in it one after the other (the four wrap variants diverge), so after the round count the number of classes per group
+    # is minimised: hand model 4 + 4 -> 4 + 1 (one group is all cylinder-outside wraps).
+    _reach = {(0, 0, 0, 0): 0}
     for k_, t in enumerate(act_tendons):
-        for (ns_, nw_), msk in list(_reach.items()):
-            key = (ns_ + _cnt[t][0], nw_ + _cnt[t][1])
-            if key not in _reach:
-                _reach[key] = msk | (1 << k_)
+        nxt = {}
+        for (ns_, nw_, ca, cb), msk in _reach.items():
+            nxt.setdefault((ns_ + _cnt[t][0], nw_ + _cnt[t][1], ca | _cnt[t][2], cb), msk | (1 << k_))       # t joins A
+            nxt.setdefault((ns_, nw_, ca, cb | _cnt[t][2]), msk)                                             # t stays in B
+        _reach = nxt
     _NS, _NW = sum(c[0] for c in _cnt.values()), sum(c[1] for c in _cnt.values())
     _r32 = lambda x: (x + 31) // 32
-    _best = min(_reach, key=lambda q: (_r32(q[0]) + _r32(_NS - q[0]) + _r32(q[1]) + _r32(_NW - q[1]), max(_need(*q), _need(_NS - q[0], _NW - q[1])), q))
+
+    def _class_runs(msk):
+        """number of (lane round, wrap class) combinations the two groups execute: elements are sorted by (inside first, type) inside a group
+        (the order of we_order below) and dealt to rounds of 32 lanes"""
+        tot = 0
+        for grp_ in (1, 0):
+            cc = [0, 0, 0, 0]
+            for k_, t in enumerate(act_tendons):
+                if ((msk >> k_) & 1) == grp_:
+                    for c_ in range(4):
+                        cc[c_] += _cnt[t][3][c_]
+            seq = [c_ for c_ in (1, 3, 0, 2) for _ in range(cc[c_])]           # inside sphere, inside cylinder, outside sphere, outside cylinder
+            tot += sum(len(set(seq[i:i + 32])) for i in range(0, len(seq), 32))
+        return tot
+    _best = min(_reach, key=lambda q: (_r32(q[0]) + _r32(_NS - q[0]) + _r32(q[1]) + _r32(_NW - q[1]), _class_runs(_reach[q]),
+                                       max(_need(q[0], q[1]), _need(_NS - q[0], _NW - q[1])), q))
     _msk = _reach[_best]
     act_tendons = [t for k_, t in enumerate(act_tendons) if (_msk >> k_) & 1] + [t for k_, t in enumerate(act_tendons) if not (_msk >> k_) & 1]
     split = bin(_msk).count("1")
