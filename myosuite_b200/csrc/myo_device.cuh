@@ -147,6 +147,11 @@ __device__ void phase_kinematics(const DevModel& m, const Warp w) {
   const idx_t* jtype = CI(jnt_type); const idx_t* jq = CI(jnt_qposadr); const idx_t* jd = CI(jnt_dofadr);
   const double* jpos = CD(jnt_pos); const double* jaxis = CD(jnt_axis); const double* qpos0 = CD(qpos0);
   double* xpos = SCR(s_xpos); double* xmat = SCR(s_xmat);
+  // sin / cos of every hinge angle in ONE lane-parallel pass (the level loop below would otherwise run the sincos code once per tree level with
+  // a handful of lanes active).  Parked in the head of the Hessian region, which is idle until the constraint phase (the tail holds the warm start).
+  double* sc = SCR(s_H);
+  for (int j = w.lane; j < m.njnt; j += 32) { const int t = jtype[j]; if (t != 0 && t != 2) { double s_, c_; sincos(W_(qpos)[jq[j]] - qpos0[jq[j]], &s_, &c_); sc[2*j] = s_; sc[2*j+1] = c_; } }
+  __syncwarp();
   for (int L = 0; L < m.nlevel; L++) {
     for (int k = level[L] + w.lane; k < level[L+1]; k += 32) {
       const double* bd = PB + k*PB_STRIDE; int p = par[k]; double pos[3], R[9];
@@ -171,7 +176,7 @@ __device__ void phase_kinematics(const DevModel& m, const Warp w) {
           double dq = W_(qpos)[qa] - qpos0[qa];
           if (t == 2) { pos[0]+=ax[0]*dq; pos[1]+=ax[1]*dq; pos[2]+=ax[2]*dq; }
           else {   // hinge: R <- R * Rodrigues(local axis, dq); pos keeps the anchor fixed
-            double s, c; sincos(dq, &s, &c); double oc = 1-c, x = al[0], y = al[1], z = al[2];
+            const double s = sc[2*j], c = sc[2*j+1]; double oc = 1-c, x = al[0], y = al[1], z = al[2];
             double Q[9] = {c+oc*x*x, oc*x*y-s*z, oc*x*z+s*y,  oc*x*y+s*z, c+oc*y*y, oc*y*z-s*x,  oc*x*z-s*y, oc*y*z+s*x, c+oc*z*z}, Rn[9];
             mat_mul(Rn, R, Q);
             #pragma unroll
