@@ -10,6 +10,11 @@
 #include "myo_solver.cuh"
 
 // ------------------------------------------------------------------ kernel arguments
+#ifndef MYO_BMASK
+#define MYO_BMASK 0x40      /* phases of the product kernels that start with a CTA barrier (bit k = phase k).  Measured round 2 at 14 warps per CTA with
+                               load-sorted rounds (hand, env-steps/s): 0xFF 1.129 M, 0x55 1.138 M, 0x51 1.140 M, 0x41 1.143 M, 0x40 (only the solver entry, whose
+                               inner barriers need aligned warps anyway) 1.147 M, 0x01 1.117 M, 0x00 1.129 M.  (At 10 warps without the sort, 0xFF had won.) */
+#endif
 struct StepArgs {
   myo_buffers b; myo_task_cfg cfg;
   int n_env, obs_dim, mode;     // mode 0: env step ; 1: debug forward (ctrl verbatim, optional substeps) ; 2: reset only
@@ -305,7 +310,7 @@ __device__ __forceinline__ void env_kernel_body(const DevModel& m, const StepArg
     // ---- physics substeps: forward dynamics + semi-implicit Euler (the only copy of the phase code in the kernel)
     const int ngroups = (DBG && a.cfg.reserved_i > 1) ? (a.cfg.reserved_i < nw ? a.cfg.reserved_i : nw) : 1;
     const int gsz = (nw + ngroups - 1)/ngroups, gid = wid / gsz, gw0 = gid*gsz, gnw = (gw0 + gsz <= nw ? gsz : nw - gw0), gthreads = gnw*32;
-    const int bmask = !DBG || a.cfg.barrier_mode == 0 ? 0xFF : (a.cfg.barrier_mode == 1 ? 0x01 : (a.cfg.barrier_mode == 2 ? 0 : a.cfg.barrier_mode));
+    const int bmask = !DBG ? MYO_BMASK : a.cfg.barrier_mode == 0 ? 0xFF : (a.cfg.barrier_mode == 1 ? 0x01 : (a.cfg.barrier_mode == 2 ? 0 : a.cfg.barrier_mode));
     const bool waitprof = DBG && a.cfg.reserved[0] != 0.0;   // profiling: record the barrier wait BEFORE each phase instead of the phase's own cycles
     long long cyc_[DBG ? 20 : 1]; long long* const cyc = DBG ? cyc_ : nullptr; int maxcon_seen = 0, maxefc_seen = 0, overflow_seen = 0;
     if (DBG) for (int k = 0; k < 20; k++) cyc_[DBG ? k : 0] = 0;
