@@ -583,8 +583,37 @@ __device__ __forceinline__ void phase_solve(const DevModel& m, const Warp w, dou
       if (d2 >= 0) { S_H[d1 > d2 ? TRI(d1,d2) : TRI(d2,d1)] += De*j2; S_H[TRI(d2,d2)] += De*j2*j2; } }
     __syncwarp();
     for (int pass = 0; pass < 2; pass++) { for (int r = w.lane; r < nlimrow; r += 32) { int dsc = S_lrow[r]; if (((dsc >> 8) & 1) == pass && S_jar[m.neq+r] < 0) { int d = dsc & 0xff; S_H[TRI(d,d)] += S_D[m.neq+r]; } } __syncwarp(); }
-    // contacts: J' W J, one contact at a time, one lane per entry of the lower triangle of its block (the gather form that pays for the
-    // gradient does not pay here: with one H entry per lane nearly every contact hits SOME lane and the warp runs the hit path 9 x ncon times)
+    // contacts: J' W J.  (The gather form that pays for the gradient does not pay here: with one H entry per lane nearly every contact
+    // hits SOME lane and the warp runs the hit path 9 x ncon times.)  Two contacts at a time, one per half-warp, 16 lanes over the lower
+    // triangle of the contact's block: a finger-finger block has 36 entries -- two passes of 32 lanes with 4 busy in the second, now
+    // three passes of 16 for TWO contacts.  The two halves may touch the same H entry, so their read-modify-writes take turns
+    // (half 0 first: a fixed order).  MEASURED (round 2, hand, 14 warps): 1.144 M env-steps/s against 1.147 M for the one-contact loop below --
+    // the two ordered updates and the wider predication eat the saved pass.  Kept as an experiment behind -DMYO_H_PAIRED.
+#ifdef MYO_H_PAIRED
+    for (int c0 = 0; c0 < ncon; c0 += 2) { const int half = w.lane >> 4, hl = w.lane & 15, c = c0 + half;
+      bool ok = c < ncon; int nr = 0, rb = 0; double W[6] = {0,0,0,0,0,0};  // nn n1 n2 11 12 22
+      if (ok) { const int rn = S_crown[c]; nr = CNR(rn); rb = CROW(rn); ok = nr != 0; }
+      const idx_t* q = pr + (ok ? PPAIR_ISTRIDE*S_cpair[c] : 0);
+      if (ok) {
+        if (nr == 1) { if (S_jar[rb] < 0) W[0] = S_D[S_DCON(c)]; }
+        else { const double Dv = S_D[S_DCON(c)];
+          double a0 = S_jar[rb] < 0 ? Dv : 0, a1 = S_jar[rb+1] < 0 ? Dv : 0, a2 = S_jar[rb+2] < 0 ? Dv : 0, a3 = S_jar[rb+3] < 0 ? Dv : 0;
+          W[0] = a0+a1+a2+a3; W[1] = a0-a1; W[2] = a2-a3; W[3] = a0+a1; W[5] = a2+a3; }
+        ok = W[0] != 0; }
+      const int np = ok ? q[4] : 0, ntri = (np*(np+1)) >> 1; const int other = __shfl_xor_sync(FULL, ntri, 16), nmax = ntri > other ? ntri : other;
+      const JacRef J = S_jac(ok ? c : 0);
+      for (int t = hl; t - hl < nmax; t += 16) {       // (warp-uniform trip count: the warp syncs below sit inside the loop)
+        const bool v = t < ntri; double val = 0; int idx = 0;
+        if (v) { int ei, ej;
+          if (np <= 8) { ei = (t >= 1) + (t >= 3) + (t >= 6) + (t >= 10) + (t >= 15) + (t >= 21) + (t >= 28); ej = t - ((ei*(ei+1)) >> 1); } else tri_index(t, ei, ej);
+          const JacRef ja = J + 3*ei, jb = J + 3*ej; const double a[3] = {ja[0], ja[1], ja[2]}, b[3] = {jb[0], jb[1], jb[2]};
+          double wa0 = W[0]*a[0]+W[1]*a[1]+W[2]*a[2], wa1 = W[1]*a[0]+W[3]*a[1], wa2 = W[2]*a[0]+W[5]*a[2];
+          int di = path[q[3]+ei] >> 1, dj = path[q[3]+ej] >> 1; idx = TRI(di,dj); val = wa0*b[0]+wa1*b[1]+wa2*b[2]; }
+        if (v && half == 0) S_H[idx] += val;
+        __syncwarp();
+        if (v && half == 1) S_H[idx] += val;
+        __syncwarp(); } }
+#else
     for (int c = 0; c < ncon; c++) { const int rn = S_crown[c], nr = CNR(rn), rb = CROW(rn); if (!nr) continue; const idx_t* q = pr + PPAIR_ISTRIDE*S_cpair[c]; double W[6] = {0,0,0,0,0,0};  // nn n1 n2 11 12 22
       if (nr == 1) { if (S_jar[rb] < 0) W[0] = S_D[S_DCON(c)]; }
       else { const double Dv = S_D[S_DCON(c)];
@@ -597,6 +626,7 @@ __device__ __forceinline__ void phase_solve(const DevModel& m, const Warp w, dou
           double wa0 = W[0]*a[0]+W[1]*a[1]+W[2]*a[2], wa1 = W[1]*a[0]+W[3]*a[1], wa2 = W[2]*a[0]+W[5]*a[2];
           int di = path[q[3]+ei] >> 1, dj = path[q[3]+ej] >> 1; S_H[TRI(di,dj)] += wa0*b[0]+wa1*b[1]+wa2*b[2]; } }
       __syncwarp(); }
+#endif
     LAP(9)
     } }
     if (cta_sync) __syncthreads();
