@@ -172,3 +172,23 @@ def test_dims_contact_capacity(models):
     assert dl.smem_bytes_per_env * 7 + dl.reserved[1] + 64 <= 232448
     dv = abi.DeviceModel(*blob.pack(m, prog), variant="f64rows").dims(cfg)
     assert dv.maxcon == 64 and dv.smem_bytes_per_env > dm.dims(cfg).smem_bytes_per_env          # plain f64 rows take more room
+
+
+def test_tendon_grouping_keeps_lane_rounds_full_and_class_pure(models):
+    """program.build_program picks the tendon groups as a subset: minimal number of 32-lane rounds over segments and wrap elements first,
+    then minimal number of (round, wrap class) combinations, then balanced scratch."""
+    import collections
+    for name, want_runs in (("myohand_pose", 5), ("myolegs", 3), ("myotorso", 2), ("myoelbow_1dof6muscles", 2)):
+        prog, _ = program.build_program(models[name]); P = [int(x) for x in prog["P_dims"]]
+        nsp, nwe = P[3], P[4]; sp_split, we_split = P[26], P[27]
+        PWE = np.asarray(prog["PWE"]).reshape(-1, 6)
+        rounds = sum((x + 31) // 32 for x in (sp_split, nsp - sp_split, we_split, nwe - we_split))
+        assert rounds == (nsp + 31) // 32 + (nwe + 31) // 32, (name, rounds)                      # splitting never costs a lane round
+        runs = 0
+        for a, b in ((0, we_split), (we_split, nwe)):
+            cls = [(int(r[3]), int(r[5] != 0)) for r in PWE[a:b]]
+            runs += sum(len(set(cls[i:i + 32])) for i in range(0, len(cls), 32))
+        assert runs == want_runs, (name, runs)
+        # inside-wrap warm-start slots are a permutation of 0 .. n_inside-1
+        slots = sorted(int(r[5]) - 1 for r in PWE if r[5] != 0)
+        assert slots == list(range(len(slots)))
