@@ -137,3 +137,56 @@ DEFAULT_WEIGHTS = {
     "hold": {"goal_dist": 100.0, "bonus": 4.0, "penalty": 10},                                                         # obj_hold_v0.py:17-21
     "walk": {"vel_reward": 5.0, "done": -100, "cyclic_hip": -10, "ref_rot": 10.0, "joint_angle_rew": 5.0},          # walk_v0.py:205-211
 }
+
+
+# --------------------------------------------------------------------------------------------- methods on paths (env_base.py:763-826)
+def obsvec2obsdict(obsvec, key_widths):
+    """ObsVecDict.obsvec2obsdict (obs_vec_dict.py:90-97): obsvec [num_traj, horizon, obs_dim] -> {key: [num_traj, horizon, width]} for the keys
+    (and widths) that form the observation vector, in order."""
+    obsvec = np.asarray(obsvec)
+    assert obsvec.ndim == 3, "obsvec should be of shape (num_traj, horizon, obs_dim)"
+    d, o = {}, 0
+    for k, w in key_widths:
+        d[k] = obsvec[:, :, o:o + w]; o += w
+    assert o == obsvec.shape[-1], "observation width %d does not match the obs_keys (%d)" % (obsvec.shape[-1], o)
+    return d
+
+
+def compute_path_rewards(task, paths, key_widths, weights, cfg, rwd_mode="dense"):
+    """MujocoEnv.compute_path_rewards (env_base.py:763-780): vectorised rewards / done flags of paths["observations"] [num_traj, horizon, obs_dim],
+    time-aligned the way the reference does it (entry t takes the value computed from observation t+1; the last entry is redundant)."""
+    od = obsvec2obsdict(paths["observations"], key_widths)
+    if task == "reach" and "time" not in od:
+        raise KeyError("the reach reward needs obs_dict['time'] (reach_v0.py:127-131), which an observation vector does not carry")
+    rd = reward_dict(task, od, weights, cfg)
+    rewards, done = np.array(rd[rwd_mode], dtype=np.float64), np.array(rd["done"])
+    done[..., :-1] = done[..., 1:]; rewards[..., :-1] = rewards[..., 1:]
+    paths["done"] = done if done.shape[0] > 1 else done.ravel()
+    paths["rewards"] = rewards if rewards.shape[0] > 1 else rewards.ravel()
+    return paths
+
+
+def truncate_paths(paths):
+    """MujocoEnv.truncate_paths (env_base.py:782-796): cut every path at its first done flag and mark it terminated."""
+    hor = paths[0]["rewards"].shape[0]
+    for path in paths:
+        if path["done"][-1] == False:          # noqa: E712  (the reference's own comparisons: done may be an object / float array)
+            path["terminated"] = False
+            terminated_idx = hor               # noqa: F841
+        elif path["done"][0] == False:         # noqa: E712
+            terminated_idx = sum(~np.asarray(path["done"], dtype=bool)) + 1
+            for key in list(path.keys()):
+                path[key] = path[key][: terminated_idx + 1, ...]
+            path["terminated"] = True
+    return paths
+
+
+def evaluate_success(paths, horizon, logger=None, successful_steps=5):
+    """MujocoEnv.evaluate_success (env_base.py:798-826): percentage of paths solved for more than `successful_steps` steps; optional mjrl-style logger."""
+    num_success = sum(1 for p in paths if np.sum(np.asarray(p["env_infos"]["solved"]) * 1.0) > successful_steps)
+    success_percentage = num_success * 100.0 / len(paths)
+    if logger:
+        logger.log_kv("rwd_sparse", np.mean([np.mean(p["env_infos"]["rwd_sparse"]) for p in paths]))
+        logger.log_kv("rwd_dense", np.mean([np.sum(p["env_infos"]["rwd_dense"]) / horizon for p in paths]))
+        logger.log_kv("success_percentage", success_percentage)
+    return success_percentage

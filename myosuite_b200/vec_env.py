@@ -527,6 +527,40 @@ class MyoEnv:
             r["dense"] = np.float64(self._last["reward"])        # the device's f64 reward (the host recomputation only sees the f32 observation)
         return r
 
+    # ---- methods on paths and small accessors (env_base.py:434-459, 664-686, 763-826)
+    @property
+    def time(self):
+        return self._last["time"]
+
+    @property
+    def id(self):
+        return self.env_id
+
+    def get_obs(self, **kwargs):
+        return self.forward()[0]
+
+    def _key_widths(self):
+        from . import gym_api
+        m = self.mj_model
+        w = dict(gym_api.obs_layout(self.vec.task, m.nq, m.nv, m.na, self._ntip))
+        return [(k, w[k]) for k in self.obs_keys]
+
+    def obsvec2obsdict(self, obsvec):
+        from . import gym_api
+        return gym_api.obsvec2obsdict(obsvec, self._key_widths())
+
+    def compute_path_rewards(self, paths):
+        from . import gym_api
+        return gym_api.compute_path_rewards(self.vec.task, paths, self._key_widths(), self.rwd_keys_wt, self._task_cfg, self.rwd_mode)
+
+    def truncate_paths(self, paths):
+        from . import gym_api
+        return gym_api.truncate_paths(paths)
+
+    def evaluate_success(self, paths, logger=None, successful_steps=5):
+        from . import gym_api
+        return gym_api.evaluate_success(paths, self.horizon, logger, successful_steps)
+
     def get_proprioception(self, obs_dict=None):
         """env_base.py get_proprioception: (None, None, None) when no proprio_keys are configured (the default of the hot-path envs)."""
         return None, None, None

@@ -128,3 +128,30 @@ def test_torso_dicts_vs_reference_golden():
     r = gym_api.reward_dict("pose", d, {"pose": 1.0, "bonus": 4.0, "act_reg": 1.0, "penalty": 50, "done": 0}, {"pose_thd": 0.25, "pose_far_th": np.pi})
     np.testing.assert_allclose(r["dense"], z["dense"], rtol=3e-6, atol=3e-6)
     assert np.array_equal(np.asarray(r["done"], bool), z["done"].astype(bool)) and np.array_equal(np.asarray(r["solved"], bool), z["solved"].astype(bool))
+
+
+def test_path_methods_like_env_base():
+    """compute_path_rewards / truncate_paths / evaluate_success / obsvec2obsdict (env_base.py:763-826, obs_vec_dict.py:90-97) on the elbow pose layout."""
+    z = np.load(os.path.join(G, "pylogic.npz"))
+    obs = z["pose_elbow_obs"]; N = (len(obs) // 4) * 4
+    lay = gym_api.obs_layout("pose", 1, 1, 6)
+    vec = obs[:N].reshape(4, N // 4, -1)
+    od = gym_api.obsvec2obsdict(vec, lay)
+    assert list(od) == ["qpos", "qvel", "pose_err", "act"] and od["act"].shape == (4, N // 4, 6)
+    with pytest.raises(AssertionError):
+        gym_api.obsvec2obsdict(vec[0], lay)
+    paths = gym_api.compute_path_rewards("pose", {"observations": vec.copy()}, lay, gym_api.DEFAULT_WEIGHTS["pose"], {"pose_thd": 0.175})
+    dense = z["pose_elbow_rwd_dense"][:N].reshape(4, N // 4); done = z["pose_elbow_rwd_done"][:N].reshape(4, N // 4).astype(bool)
+    np.testing.assert_allclose(paths["rewards"][:, :-1], dense[:, 1:], rtol=2e-6, atol=2e-6)          # time-aligned: entry t is the reward of observation t+1
+    np.testing.assert_allclose(paths["rewards"][:, -1], dense[:, -1], rtol=2e-6, atol=2e-6)           # (last entry redundant, as in the reference)
+    assert np.array_equal(paths["done"][:, :-1], done[:, 1:])
+    # truncate_paths: first done at step 3 -> entries 0..4 kept (the reference's sum(~done) + 1 rule) and terminated = True
+    p1 = {"rewards": np.arange(8.0), "done": np.array([0, 0, 0, 1, 1, 1, 1, 1], bool), "observations": np.zeros((8, 2))}
+    p2 = {"rewards": np.arange(8.0), "done": np.zeros(8, bool), "observations": np.zeros((8, 2))}
+    out = gym_api.truncate_paths([p1, p2])
+    assert out[0]["terminated"] is True and len(out[0]["rewards"]) == 5 and out[0]["observations"].shape == (5, 2) and out[1]["terminated"] is False and len(out[1]["rewards"]) == 8
+    logged = {}
+    lg = type("L", (), {"log_kv": lambda self, k, v: logged.__setitem__(k, v)})()
+    mk = lambda n_solved: {"env_infos": {"solved": np.array([True] * n_solved + [False] * (10 - n_solved)), "rwd_sparse": np.ones(10), "rwd_dense": np.full(10, 2.0)}}
+    assert gym_api.evaluate_success([mk(6), mk(5), mk(0), mk(10)], horizon=10, logger=lg) == 50.0          # "solved for MORE than 5 steps"
+    assert logged == {"rwd_sparse": 1.0, "rwd_dense": 2.0, "success_percentage": 50.0}
