@@ -114,6 +114,13 @@ def test_env_contract_like_reference_test_envs(env_id):
     env2.step(u); env2.set_env_state(infos1["state"])
     _assert_close(env2.get_env_state()["qpos"], infos1["state"]["qpos"], atol=0)
     obs3, *_ = env2.forward()
+    # path-level helpers (env_base.py:434-459, 664-686, 763-826)
+    assert env2.id == env_id and env2.time == pytest.approx(float(infos1["time"])) and np.array_equal(env2.get_obs(), obs3)
+    od3 = env2.obsvec2obsdict(np.stack([obs3, obs3])[None]); assert list(od3) == list(env2.obs_keys) and od3["act"].shape == (1, 2, env2.mj_model.na)
+    if "Reach" not in env_id:
+        pr = env2.compute_path_rewards({"observations": np.stack([obs3, obs3, obs3])[None]})
+        assert pr["rewards"].shape == (3,) and pr["done"].shape == (3,)
+    assert env2.evaluate_success([{"env_infos": {"solved": np.ones(7, bool), "rwd_sparse": np.zeros(7), "rwd_dense": np.zeros(7)}}]) == 100.0
     if "Walk" in env_id:       # phase_var = steps / hip_period: the reference builds a step's observation BEFORE it increments `steps` (walk_v0.py:339-342), forward() sees the count after
         k = list(env1.obs_keys).index("phase_var"); off = sum(np.size(env1.obs_dict[q]) for q in env1.obs_keys[:k])
         obs3 = obs3.copy(); obs3[off] = obs1[off]
