@@ -357,11 +357,11 @@ def main():
                 "config": {"workload": "%s, %d envs/GPU, frame_skip 10, random actions %s, auto-reset" % (args.env, n, "U(0,1)" if args.actions == "u01" else "U[-1,1]"),
                            "l2": ("not flushed (--no-l2-flush)" if args.no_l2_flush else "flushed between timed steps: a 192 MiB write per step inside the timed region (inputs, 8 MB of state per step, are smaller than L2)"), "parallelism": "env-sharded x%d, no data-path collective" % world,
                            "contact_overflow_env_fraction": overflow_frac, "rollout_end_allgather_us": allgather_us, "extra": extra},
-                "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": n * nu * 4, "d2h_bytes_per_step": n * (max(A_OBS.get(args.env, 0), 0) * 4 + 4 + 1)},
+                "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": world * n * nu * 4, "d2h_bytes_per_step": world * n * (max(A_OBS.get(args.env, 0), 0) * 4 + 4 + 1)},      # whole job, like `value`
                 "gpu_launches": int(launches),
                 "roofline": roofline(args.env, n, ms, args.steps),
                 "clocks": clocks}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # the CPU leg is an N = 1 figure (rank 0 only); at N > 1 the other ranks would just wait for it
             from oracle import oracle_py
             os.environ["MYO_ORACLE_LIB"] = oracle_py.build_native()
             t0 = time.perf_counter()
